@@ -1,0 +1,149 @@
+/* sarlacc_b200 -- C ABI of the B200-native adaptor-alignment hot path.
+ *
+ * This is the drop-in boundary for the four `.Call` entry points of the reference R package
+ * (registered in /root/reference/src/init.cpp:10-13, prototypes src/sarlacc.h:14-17):
+ *
+ *     reference `.Call` symbol (file:line)                     replaced by
+ *     -------------------------------------------------------  ----------------------------------
+ *     adaptor_align            src/adaptor_align.cpp:11-77      sarlacc_adaptor_align
+ *     adaptor_align_score_only src/adaptor_align.cpp:79-110     sarlacc_adaptor_align_score_only
+ *     barcode_align            src/barcode_align.cpp:10-44      sarlacc_barcode_align
+ *     general_align            src/general_align.cpp:10-62      sarlacc_general_align
+ *
+ * plus one fused entry that folds the per-barcode R loop of R/barcodeAlign.R:20-35 into one launch
+ * (sarlacc_barcode_align_multi) and a "resident" variant of the same calls that keeps packed read
+ * windows in HBM between calls (what adaptorAlign -> getAdaptorThresholds -> tuneAlignment re-use).
+ *
+ * Plain pointers and sizes only: no R, Rcpp, torch or CUDA types appear in any signature.  The R-side
+ * glue a maintainer would add (SEXP unpacking -> these calls) is shown in INTEGRATION.md and kept as
+ * source in sarlacc_b200/csrc/r_glue.cpp.
+ *
+ * Conventions
+ *   - every function returns 0 on success and non-zero on failure; the message (the reference's own
+ *     std::runtime_error text where one exists) is then available from sarlacc_last_error() on the
+ *     calling thread -- the glue passes it to Rf_error(), which is what BEGIN_RCPP/END_RCPP did.
+ *   - inputs are caller-owned and never modified; outputs are caller-allocated.
+ *   - there is NO CPU implementation behind these calls: without a usable CUDA device they fail with
+ *     an error, they never fall back.
+ */
+#ifndef SARLACC_B200_H
+#define SARLACC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SARLACC_SEQ_ASCII      0 /* character vector / already decoded: bytes are 'A','C','G','T',...   */
+#define SARLACC_SEQ_BIOSTRINGS 1 /* DNAStringSet payload: Biostrings DNA byte codes (A=1,C=2,G=4,T=8,...)
+                                    i.e. what src/DNA_input.cpp:64-75 runs DNAdecode() over               */
+
+/* A set of n (sequence, quality) string pairs.  Two layouts are accepted:
+ *   views : seq[i]/qual[i] point at the i-th string (what get_elt_from_XStringSet_holder returns for
+ *           every element, src/adaptor_align.cpp:46-50); seq_len[i]/qual_len[i] are the lengths.
+ *   CSR   : seq == NULL; string i is seq_pool[seq_off[i] .. seq_off[i+1]) (same for qual).
+ * Sequence and quality lengths are passed separately so that the reference's "sequence and quality
+ * strings should have the same length" check (src/adaptor_align.cpp:51-53) is made here, not upstream. */
+typedef struct {
+    int64_t n;
+    int seq_encoding;               /* SARLACC_SEQ_ASCII or SARLACC_SEQ_BIOSTRINGS */
+    const uint8_t* const* seq;      /* views layout (or NULL)  */
+    const int32_t* seq_len;
+    const uint8_t* const* qual;
+    const int32_t* qual_len;
+    const uint8_t* seq_pool;        /* CSR layout (used when seq == NULL) */
+    const int64_t* seq_off;
+    const uint8_t* qual_pool;
+    const int64_t* qual_off;
+} sarlacc_reads;
+
+/* The named numeric vector every hot-path .Call receives from .create_encoding_vector
+ * (R/qualityMask.R:19-27): names[i] is the i-th name as a C string, err[i] its error probability.
+ * Validation follows quality_encoding's constructor (src/quality_encoding.cpp:5-32) message for message. */
+typedef struct {
+    int n;
+    const char* const* names;       /* NULL = unnamed vector */
+    const double* err;
+} sarlacc_encoding;
+
+/* ---- process-wide state ------------------------------------------------------------------------ */
+const char* sarlacc_last_error(void);           /* thread-local, valid until the next call on this thread */
+int  sarlacc_device_count(void);                /* CUDA devices visible; <0 on error */
+int  sarlacc_set_devices(const int* devices, int ndevices); /* devices the host-buffer calls shard reads over
+                                                   (contiguous read-index ranges, R/adaptorAlign.R:126-134).
+                                                   Default: device 0 only. */
+int  sarlacc_set_host_threads(int nthreads);    /* packer threads per device (default: hardware concurrency / devices) */
+const char* sarlacc_version(void);
+/* Launch accounting for bench.py's "gpu_launches": kernels launched by this library since the last reset. */
+int64_t sarlacc_kernel_launches(int reset);
+
+/* ---- the four reference entry points (host buffers in, host buffers out) ------------------------- */
+
+/* adaptor_align(readseq, readqual, encoding, gapopen, gapext, adaptor, sec_starts, sec_ends)
+ * src/adaptor_align.cpp:11-77.  Local-in-read / global-in-adaptor alignment with traceback.
+ *   sec_starts are 0-based, sec_ends 1-based, as R passes them (R/adaptorAlign.R:158).
+ *   score[n]; start[n], end[n] are 1-based read coordinates or 0,0 when the guard at :58 fails;
+ *   sec_start / sec_width are [nsec][n] (section-major, one R IntegerVector per section, :64-68). */
+int sarlacc_adaptor_align(const sarlacc_reads* reads, const sarlacc_encoding* encoding,
+        double gapopen, double gapext, const char* adaptor,
+        int nsec, const int32_t* sec_starts, const int32_t* sec_ends,
+        double* score, int32_t* start, int32_t* end, int32_t* sec_start, int32_t* sec_width);
+
+/* adaptor_align_score_only(readseq, readqual, encoding, gapopen, gapext, adaptor)  src/adaptor_align.cpp:79-110 */
+int sarlacc_adaptor_align_score_only(const sarlacc_reads* reads, const sarlacc_encoding* encoding,
+        double gapopen, double gapext, const char* adaptor, double* score);
+
+/* barcode_align(barcodeseq, barcodequal, encoding, gapopen, gapext, reference)  src/barcode_align.cpp:10-44
+ * Fully global alignment, score only. */
+int sarlacc_barcode_align(const sarlacc_reads* reads, const sarlacc_encoding* encoding,
+        double gapopen, double gapext, const char* reference, double* score);
+
+/* general_align(inputseq, inputqual, encoding, gapopen, gapext, reference, edit_only)  src/general_align.cpp:10-62
+ * Global alignment + gapped strings + edit distance.  When edit_only == 0, ref_aln/query_aln receive
+ * NUL-terminated strings at i*aln_stride (aln_stride >= max len + strlen(reference) + 1). */
+int sarlacc_general_align(const sarlacc_reads* reads, const sarlacc_encoding* encoding,
+        double gapopen, double gapext, const char* reference, int edit_only,
+        double* score, int32_t* edit, char* ref_aln, char* query_aln, int64_t aln_stride);
+
+/* ---- fused extension: every barcode in one pass ---------------------------------------------------
+ * Replaces the body of the `for (b in seq_along(barcodes))` loop of R/barcodeAlign.R:20-35 (nbarcodes
+ * calls of barcode_align + the running best / next-best update with its strict `>` rule):
+ *   best_id[n]  1-based index of the best barcode (0 where R would hold NA, i.e. nbarcodes == 0 or all NaN)
+ *   best[n]     its score (-Inf if none);  next_best[n] the runner-up (-Inf if none).
+ * R's `gap` column is best - next_best (R/barcodeAlign.R:37).  all_scores may be NULL; otherwise it
+ * receives the [nbarcodes][n] matrix of scores exactly as nbarcodes barcode_align calls would. */
+int sarlacc_barcode_align_multi(const sarlacc_reads* reads, const sarlacc_encoding* encoding,
+        double gapopen, double gapext, const char* const* barcodes, int nbarcodes,
+        int32_t* best_id, double* best, double* next_best, double* all_scores);
+
+/* ---- resident read windows -----------------------------------------------------------------------
+ * Packs the reads once (2 bytes per base: quality index + one-hot base), uploads them and keeps them
+ * in HBM.  The *_resident calls then run on that copy; results stay on the device until fetched.
+ * `stream` is a cudaStream_t passed as void* (NULL = the library's own stream for that object); the
+ * call only enqueues work, so the caller may bracket it with its own events. */
+typedef struct sarlacc_resident sarlacc_resident;
+
+sarlacc_resident* sarlacc_resident_create(const sarlacc_reads* reads, const sarlacc_encoding* encoding, int device);
+void    sarlacc_resident_free(sarlacc_resident* r);
+int64_t sarlacc_resident_n(const sarlacc_resident* r);
+int64_t sarlacc_resident_cells(const sarlacc_resident* r, int rlen);   /* sum(len_i) * rlen: DP cells of one pass */
+int64_t sarlacc_resident_bytes(const sarlacc_resident* r);             /* packed bytes resident in HBM */
+
+/* mode: 0 = score only, local (adaptor_align_score_only); 1 = local + traceback (adaptor_align);
+ *       2 = score only, global (barcode_align). */
+int sarlacc_resident_align(sarlacc_resident* r, int mode, double gapopen, double gapext, const char* reference,
+        int nsec, const int32_t* sec_starts, const int32_t* sec_ends, void* stream);
+/* Copies the results of the last sarlacc_resident_align to the host (any pointer may be NULL). */
+int sarlacc_resident_fetch(sarlacc_resident* r, double* score, int32_t* start, int32_t* end,
+        int32_t* sec_start, int32_t* sec_width, void* stream);
+/* Device pointer of the last run's score vector (double[n]) -- for callers that keep working on the device. */
+const double* sarlacc_resident_scores_device(const sarlacc_resident* r);
+/* Name of the forward kernel variant the last sarlacc_resident_align used (for reports), e.g. "wf<C=9,G=8,trace>". */
+const char* sarlacc_resident_last_kernel(const sarlacc_resident* r);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,1322 @@
+/* Host side of the C ABI declared in include/sarlacc_b200.h.
+ *
+ * What lives here (all of it replaces reference host code, cited per function):
+ *   - argument validation with the reference's error texts (src/quality_encoding.cpp:5-32,
+ *     src/adaptor_align.cpp:23-31,51-53, src/reference_align.cpp:211,215-217);
+ *   - cost tables (src/reference_align.cpp:21-52) -- computed on the host with libm log, exactly the
+ *     reference's expression, and shipped to the device, so no device transcendental is involved;
+ *   - the packer: reads (views or CSR, ASCII or Biostrings byte codes; src/DNA_input.cpp:64-75) ->
+ *     2 bytes per base in pinned buffers -> cudaMemcpyAsync;
+ *   - chunked, double-buffered execution, sharded over the configured devices by contiguous read
+ *     index ranges (the axis .parallelize uses, R/adaptorAlign.R:126-134); no collective is needed;
+ *   - the resident (HBM-resident windows) variant.
+ * There is deliberately no CPU implementation of the alignment here.
+ */
+#include "sarlacc_b200.h"
+#include "kernels.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace sarlacc;
+
+namespace {
+
+thread_local std::string g_error;
+std::atomic<long long> g_launches{0};
+std::mutex g_cfg_mutex;
+std::vector<int> g_devices;       /* empty = {0} */
+int g_host_threads = 0;           /* 0 = auto */
+
+int fail(const std::string& msg) {
+    g_error = msg;
+    return 1;
+}
+
+struct CudaError { std::string msg; };
+
+#define CUDA_CHECK(expr)                                                                       \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            throw CudaError{std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #expr}; \
+        }                                                                                      \
+    } while (0)
+
+/* ---- encoding + cost tables ----------------------------------------------------------------- */
+
+struct Encoding {
+    int n = 0;
+    char offset = 0;
+    std::vector<double> cost;   /* [5][n]: match1, mismatch1, mismatch2, match3, match4 */
+};
+
+/* quality_encoding::quality_encoding, src/quality_encoding.cpp:5-32 (messages verbatim). */
+const char* check_encoding(const sarlacc_encoding* enc, char* offset) {
+    if (!enc || enc->names == nullptr || enc->n <= 0) {
+        return "encoding vector must be non-empty and named";
+    }
+    char last = 0;
+    for (int i = 0; i < enc->n; ++i) {
+        const char* nm = enc->names[i];
+        if (!nm || std::strlen(nm) != 1) {
+            return "names of encoding vector must be one character in length";
+        }
+        const char curval = nm[0];
+        if (i > 0) {
+            if (curval != last + 1) {   /* int arithmetic on (signed) char, as in the reference */
+                return "names of encoding vector should increase consecutively";
+            } else if (enc->err[i] > enc->err[i - 1]) {
+                return "error probabilities should decrease";
+            }
+        } else {
+            *offset = curval;
+        }
+        last = curval;
+    }
+    return nullptr;
+}
+
+/* reference_align::create_qualities, src/reference_align.cpp:21-52.  Only the five tables the scoring
+ * can reach are kept (src/reference_align.cpp:184-212): match m=1, mismatch m=1, mismatch m=2, match m=3,
+ * match m=4.  Expression and evaluation order are the reference's; built with -ffp-contract=off. */
+const char* build_encoding(const sarlacc_encoding* enc, Encoding& out) {
+    const char* msg = check_encoding(enc, &out.offset);
+    if (msg) return msg;
+    out.n = enc->n;
+    out.cost.assign((size_t)5 * enc->n, 0.0);
+    constexpr double n = 4;
+    auto match = [&](int i, double epsilon) {
+        const double gamma_xy = 1.0 / (i + 1.0);
+        const double gamma_xy_1m = 1 - gamma_xy;
+        return std::log(gamma_xy * (1 - epsilon) * n + gamma_xy_1m * epsilon * (n / (n - 1))) / M_LN2;
+    };
+    auto mismatch = [&](int i, double epsilon) {
+        const double gamma_xy = 1.0 / (i + 1.0);
+        const double gamma_xy_1m = 1 - gamma_xy;
+        return std::log(gamma_xy_1m * (1 - epsilon) * n + gamma_xy * epsilon * (n / (n - 1))) / M_LN2;
+    };
+    for (int j = 0; j < enc->n; ++j) {
+        const double e = enc->err[j];
+        out.cost[0 * (size_t)enc->n + j] = match(0, e);
+        out.cost[1 * (size_t)enc->n + j] = mismatch(0, e);
+        out.cost[2 * (size_t)enc->n + j] = mismatch(1, e);
+        out.cost[3 * (size_t)enc->n + j] = match(2, e);
+        out.cost[4 * (size_t)enc->n + j] = match(3, e);
+    }
+    return nullptr;
+}
+
+/* ---- reference (adaptor / barcode) analysis --------------------------------------------------- */
+
+/* compute_cost's switch, src/reference_align.cpp:184-212.  Returns false for an unrecognized base. */
+bool classify_ref(char ref, uint8_t* mask, uint8_t* kind) {
+    *mask = 0;
+    switch (ref) {
+        case 'A': *mask = 1; *kind = COL_ACGT; return true;
+        case 'C': *mask = 2; *kind = COL_ACGT; return true;
+        case 'G': *mask = 4; *kind = COL_ACGT; return true;
+        case 'T': *mask = 8; *kind = COL_ACGT; return true;
+        case 'M': case 'R': case 'W': case 'S': case 'Y': case 'K': *kind = COL_TWO; return true;
+        case 'V': case 'H': case 'D': case 'B': *kind = COL_THREE; return true;
+        case 'N': *kind = COL_N; return true;
+    }
+    *kind = COL_ACGT;
+    return false;
+}
+
+struct Plan {
+    int L = 0, nref = 1;
+    bool local = true;
+    double gop = 0, ge = 0;
+    const Encoding* enc = nullptr;
+    std::vector<double> row0;
+    std::vector<uint8_t> refmask, refkind;
+    int first_bad_col = -1;       /* first unrecognized reference column over all refs, per ref */
+    std::vector<int> bad_col;     /* per reference: first unrecognized column or -1 */
+    bool fast = false;
+    bool has_alt = false;
+    int alt_row = 4;
+    int G = 1, C = 1;
+    std::vector<int32_t> sec_starts, sec_ends;
+};
+
+void choose_geometry(Plan& P) {
+    const char* force = std::getenv("SARLACC_FORCE_GC");
+    if (force) {
+        int g = 0, c = 0;
+        if (std::sscanf(force, "%d,%d", &g, &c) == 2 && g >= 1 && g <= 32 && (g & (g - 1)) == 0 && c >= 1 && c <= kMaxC &&
+            g * c >= P.L) {
+            P.G = g;
+            P.C = c;
+            return;
+        }
+    }
+    double best = 1e300;
+    for (int g = 1; g <= kMaxGroup; g *= 2) {
+        const int c = (P.L + g - 1) / g;
+        if (c > kMaxC) continue;
+        const double util = (double)P.L / ((double)g * c);
+        double est = (26.0 + 14.0 / c) / util;     /* issue slots per DP cell, see DESIGN.md */
+        if (c > 9) est *= 1.10;                      /* 3 instead of 4 resident blocks per SM */
+        if (est < best) {
+            best = est;
+            P.G = g;
+            P.C = c;
+        }
+    }
+}
+
+void build_plan(Plan& P, const Encoding& enc, const char* const* refs, int nref, int L, bool local, double go, double ge) {
+    P.enc = &enc;
+    P.L = L;
+    P.nref = nref;
+    P.local = local;
+    P.gop = go + ge;     /* src/reference_align.cpp:8 */
+    P.ge = ge;
+    P.row0.assign((size_t)L + 1, 0.0);
+    for (int c = 1; c <= L; ++c) {   /* src/reference_align.cpp:116-118 */
+        P.row0[c] = P.row0[c - 1] - (c == 1 ? P.gop : P.ge);
+    }
+    P.refmask.assign((size_t)nref * L, 0);
+    P.refkind.assign((size_t)nref * L, COL_ACGT);
+    P.bad_col.assign(nref, -1);
+    bool kinds[4] = {false, false, false, false};
+    for (int b = 0; b < nref; ++b) {
+        for (int c = 0; c < L; ++c) {
+            uint8_t m, k;
+            if (!classify_ref(refs[b][c], &m, &k)) {
+                if (P.bad_col[b] < 0) P.bad_col[b] = c;
+            }
+            P.refmask[(size_t)b * L + c] = m;
+            P.refkind[(size_t)b * L + c] = k;
+            kinds[k] = true;
+        }
+    }
+    const int nalt = (int)kinds[COL_TWO] + (int)kinds[COL_THREE] + (int)kinds[COL_N];
+    P.has_alt = nalt > 0;
+    P.alt_row = kinds[COL_TWO] ? 2 : (kinds[COL_THREE] ? 3 : 4);
+    const bool finite = std::isfinite(go) && std::isfinite(ge);
+    /* The wavefront kernel folds "left/up neighbour already chose a gap" into a max(), which needs
+     * gap_open >= gap_ext, i.e. go >= 0 (see kernels.cu).  Anything else takes the literal kernel. */
+    P.fast = L >= 1 && L <= kMaxFastL && nalt <= 1 && finite && go >= 0.0 && enc.n <= 256 &&
+             std::getenv("SARLACC_FORCE_GENERIC") == nullptr;
+    if (P.fast) choose_geometry(P);
+}
+
+/* ---- read access + packing --------------------------------------------------------------------- */
+
+struct ReadView {
+    const sarlacc_reads* R;
+    inline int64_t seq_len(int64_t i) const { return R->seq ? R->seq_len[i] : R->seq_off[i + 1] - R->seq_off[i]; }
+    inline int64_t qual_len(int64_t i) const { return R->seq ? R->qual_len[i] : R->qual_off[i + 1] - R->qual_off[i]; }
+    inline const uint8_t* seq(int64_t i) const { return R->seq ? R->seq[i] : R->seq_pool + R->seq_off[i]; }
+    inline const uint8_t* qual(int64_t i) const { return R->seq ? R->qual[i] : R->qual_pool + R->qual_off[i]; }
+};
+
+struct PackTables {
+    uint8_t base[256];
+    /* quality byte -> index, or 0xFFFF when below the offset (signed char comparison, :215) */
+    uint16_t qidx[256];
+};
+
+void build_pack_tables(PackTables& T, int seq_encoding, const Encoding& enc) {
+    std::memset(T.base, 0, sizeof(T.base));
+    if (seq_encoding == SARLACC_SEQ_BIOSTRINGS) {
+        T.base[1] = 1; T.base[2] = 2; T.base[4] = 4; T.base[8] = 8;   /* DNAdecode: A C G T */
+    } else {
+        T.base[(unsigned char)'A'] = 1; T.base[(unsigned char)'C'] = 2;
+        T.base[(unsigned char)'G'] = 4; T.base[(unsigned char)'T'] = 8;
+    }
+    for (int b = 0; b < 256; ++b) {
+        const char q = (char)(unsigned char)b;
+        if (q < enc.offset) {
+            T.qidx[b] = 0xFFFF;
+        } else {
+            size_t loc = (size_t)(q - enc.offset);
+            if (loc >= (size_t)enc.n) loc = (size_t)enc.n - 1;   /* :219-221 */
+            T.qidx[b] = (uint16_t)loc;
+        }
+    }
+}
+
+enum ErrKind { ERR_NONE = 0, ERR_LEN, ERR_QUAL, ERR_REF };
+
+struct FirstError {
+    int64_t at = std::numeric_limits<int64_t>::max();
+    ErrKind kind = ERR_NONE;
+    void offer(int64_t i, ErrKind k) {
+        if (i < at) { at = i; kind = k; }
+    }
+    void merge(const FirstError& o) {
+        if (o.kind != ERR_NONE) offer(o.at, o.kind);
+    }
+};
+
+const char* err_text(ErrKind k) {
+    switch (k) {
+        case ERR_LEN: return "sequence and quality strings should have the same length";
+        case ERR_QUAL: return "quality cannot be lower than smallest encoded value";
+        case ERR_REF: return "unrecognized base in reference sequence";
+        default: return "";
+    }
+}
+
+int host_threads_for(int ndev) {
+    int t = g_host_threads;
+    if (t <= 0) {
+        t = (int)std::thread::hardware_concurrency();
+        if (t <= 0) t = 4;
+        t = std::max(1, t / std::max(1, ndev));
+        t = std::min(t, 32);
+    }
+    return t;
+}
+
+template <class F>
+void parallel_for(int64_t lo, int64_t hi, int nthreads, F body) {
+    const int64_t n = hi - lo;
+    if (n <= 0) return;
+    if (nthreads > n / 2048 + 1) nthreads = (int)(n / 2048 + 1);
+    if (nthreads <= 1) {
+        body(lo, hi, 0);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t) {
+        const int64_t a = lo + n * t / nthreads, b = lo + n * (t + 1) / nthreads;
+        pool.emplace_back([=] { body(a, b, t); });
+    }
+    for (auto& th : pool) th.join();
+}
+
+/* Pass 1 over [lo,hi): lengths, length-mismatch errors, max length. */
+void scan_lengths(const ReadView& V, int64_t lo, int64_t hi, int32_t* lens, int nthreads, FirstError& err, int& maxlen) {
+    std::vector<FirstError> errs(nthreads + 1);
+    std::vector<int> mx(nthreads + 1, 0);
+    parallel_for(lo, hi, nthreads, [&](int64_t a, int64_t b, int t) {
+        for (int64_t i = a; i < b; ++i) {
+            const int64_t sl = V.seq_len(i);
+            if (sl != V.qual_len(i)) {
+                errs[t].offer(i, ERR_LEN);
+                lens[i - lo] = 0;
+                continue;
+            }
+            lens[i - lo] = (int32_t)sl;
+            if (sl > mx[t]) mx[t] = (int)sl;
+        }
+    });
+    maxlen = 0;
+    for (int t = 0; t <= nthreads; ++t) {
+        err.merge(errs[t]);
+        maxlen = std::max(maxlen, mx[t]);
+    }
+}
+
+/* Pass 2: rows[(i-lo)*stride + r] = qidx | base << 8.  Quality errors only matter when a cost would have been
+ * computed for that read, i.e. L > 0 (src/reference_align.cpp:184-225 is only reached from align_column). */
+void pack_rows(const ReadView& V, int64_t lo, int64_t hi, const PackTables& T, const int32_t* lens, int stride,
+        uint16_t* rows, int nthreads, bool check_qual, FirstError& err)
+{
+    std::vector<FirstError> errs(nthreads + 1);
+    parallel_for(lo, hi, nthreads, [&](int64_t a, int64_t b, int t) {
+        for (int64_t i = a; i < b; ++i) {
+            const int len = lens[i - lo];
+            uint16_t* out = rows + (size_t)(i - lo) * stride;
+            const uint8_t* s = V.seq(i);
+            const uint8_t* q = V.qual(i);
+            unsigned bad = 0;
+            for (int r = 0; r < len; ++r) {
+                const unsigned qi = T.qidx[q[r]];
+                bad |= qi;
+                out[r] = (uint16_t)((qi & 0xFFu) | ((unsigned)T.base[s[r]] << 8));
+            }
+            if (check_qual && (bad & 0xFF00u)) errs[t].offer(i, ERR_QUAL);
+        }
+    });
+    for (int t = 0; t <= nthreads; ++t) err.merge(errs[t]);
+}
+
+/* ---- device-side resources ------------------------------------------------------------------- */
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) CUDA_CHECK(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        CUDA_CHECK(cudaMalloc(&p, want));
+        cap = want;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) CUDA_CHECK(cudaFreeHost(p));
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        CUDA_CHECK(cudaMallocHost(&p, want));
+        cap = want;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+/* Device copy of a Plan's small tables. */
+struct DevPlan {
+    DevBuf buf;
+    const double* row0 = nullptr;
+    const double* cost = nullptr;
+    const uint8_t* refmask = nullptr;
+    const uint8_t* refkind = nullptr;
+    const int32_t* sec_starts = nullptr;
+    const int32_t* sec_ends = nullptr;
+
+    void upload(const Plan& P, cudaStream_t st) {
+        auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+        const size_t o_row0 = 0;
+        const size_t o_cost = o_row0 + al(sizeof(double) * P.row0.size());
+        const size_t o_mask = o_cost + al(sizeof(double) * P.enc->cost.size());
+        const size_t o_kind = o_mask + al(P.refmask.size() + 1);
+        const size_t o_ss = o_kind + al(P.refkind.size() + 1);
+        const size_t o_se = o_ss + al(sizeof(int32_t) * (P.sec_starts.size() + 1));
+        const size_t total = o_se + al(sizeof(int32_t) * (P.sec_ends.size() + 1));
+        std::vector<uint8_t> h(total, 0);
+        std::memcpy(h.data() + o_row0, P.row0.data(), sizeof(double) * P.row0.size());
+        std::memcpy(h.data() + o_cost, P.enc->cost.data(), sizeof(double) * P.enc->cost.size());
+        if (!P.refmask.empty()) std::memcpy(h.data() + o_mask, P.refmask.data(), P.refmask.size());
+        if (!P.refkind.empty()) std::memcpy(h.data() + o_kind, P.refkind.data(), P.refkind.size());
+        if (!P.sec_starts.empty()) {
+            std::memcpy(h.data() + o_ss, P.sec_starts.data(), sizeof(int32_t) * P.sec_starts.size());
+            std::memcpy(h.data() + o_se, P.sec_ends.data(), sizeof(int32_t) * P.sec_ends.size());
+        }
+        buf.reserve(total);
+        CUDA_CHECK(cudaMemcpyAsync(buf.p, h.data(), total, cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));   /* h is a stack-owned staging vector */
+        const uint8_t* base = buf.as<uint8_t>();
+        row0 = reinterpret_cast<const double*>(base + o_row0);
+        cost = reinterpret_cast<const double*>(base + o_cost);
+        refmask = base + o_mask;
+        refkind = base + o_kind;
+        sec_starts = reinterpret_cast<const int32_t*>(base + o_ss);
+        sec_ends = reinterpret_cast<const int32_t*>(base + o_se);
+    }
+};
+
+struct Outputs {   /* device pointers; any may be null */
+    double* score = nullptr;       /* [nref][n] */
+    int32_t* best_id = nullptr;
+    double* best = nullptr;
+    double* next_best = nullptr;
+    int32_t* start = nullptr;
+    int32_t* end = nullptr;
+    int32_t* sec_start = nullptr;  /* [nsec][n] */
+    int32_t* sec_width = nullptr;
+    uint8_t* ops = nullptr;
+    int32_t* nops = nullptr;
+    long long ops_stride = 0;
+};
+
+/* Scratch for one in-flight run on one stream. */
+struct Scratch {
+    DevBuf flags, map, gS, gE, gC;
+    void release() { flags.release(); map.release(); gS.release(); gE.release(); gC.release(); }
+};
+
+size_t scratch_budget_bytes() {
+    const char* e = std::getenv("SARLACC_SCRATCH_MB");
+    size_t mb = 4096;
+    if (e) {
+        const long v = std::atol(e);
+        if (v >= 16) mb = (size_t)v;
+    }
+    return mb << 20;
+}
+
+/* How many alignments of at most `maxlen` rows one sub-launch may cover under the scratch budget. */
+long long sub_chunk(const Plan& P, int maxlen, bool trace, long long n) {
+    size_t per = 0;
+    if (trace) {
+        if (P.fast) {
+            per += (size_t)(maxlen + P.G) * P.G * (P.C <= 8 ? 4 : 8);
+        } else {
+            per += (size_t)std::max(1, maxlen) * P.L;
+        }
+        per += sizeof(int32_t) * ((size_t)P.L + 1);
+    }
+    if (per == 0) return n;
+    long long cn = (long long)(scratch_budget_bytes() / per);
+    if (cn < 1) cn = 1;
+    return std::min(cn, n);
+}
+
+const char* g_last_kernel = "";
+
+/* Enqueue forward (+ traceback) for device-resident packed reads [0,n).  Sub-chunks by scratch budget. */
+const char* run_device(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t st,
+        const uint16_t* d_rows, const int32_t* d_lens, long long n, int stride, int maxlen,
+        bool trace, const Outputs& out, int sms)
+{
+    const char* name = "";
+    if (n == 0) return name;
+    const long long cn = sub_chunk(P, maxlen, trace, n);
+    for (long long off = 0; off < n; off += cn) {
+        const long long m = std::min(cn, n - off);
+        AlignArgs A;
+        std::memset(&A, 0, sizeof(A));
+        A.rows = d_rows + off * (long long)stride;
+        A.lens = d_lens + off;
+        A.n = m;
+        A.stride = stride;
+        A.L = P.L;
+        A.nref = P.nref;
+        A.refmask = D.refmask;
+        A.refkind = D.refkind;
+        A.local = P.local ? 1 : 0;
+        A.gop = P.gop;
+        A.ge = P.ge;
+        A.row0 = D.row0;
+        A.cost = D.cost;
+        A.enc_n = P.enc->n;
+        A.alt_row = P.alt_row;
+        A.G = P.G;
+        A.C = P.C;
+        /* [nref][n] outputs of a sub-chunk cannot be expressed with one base pointer unless n == m or nref == 1 */
+        A.score = out.score ? out.score + off : nullptr;
+        A.best_id = out.best_id ? out.best_id + off : nullptr;
+        A.best = out.best ? out.best + off : nullptr;
+        A.next_best = out.next_best ? out.next_best + off : nullptr;
+
+        TraceArgs T;
+        std::memset(&T, 0, sizeof(T));
+        if (trace) {
+            if (P.fast) {
+                const int wb = P.C <= 8 ? 4 : 8;
+                A.fstride = (long long)(maxlen + P.G) * P.G;
+                S.flags.reserve((size_t)A.fstride * wb * m);
+                T.layout = 0;
+                T.wordbytes = wb;
+            } else {
+                A.fstride = (long long)std::max(1, maxlen) * P.L;
+                S.flags.reserve((size_t)A.fstride * m);
+                T.layout = 1;
+                T.wordbytes = 1;
+            }
+            A.flags = S.flags.p;
+            S.map.reserve(sizeof(int32_t) * ((size_t)P.L + 1) * m);
+        }
+        if (P.fast) {
+            name = launch_wavefront(A, trace, P.has_alt, 0, st);
+        } else {
+            long long threads = std::min<long long>(m, (long long)sms * 1024);
+            threads = (threads + 127) / 128 * 128;
+            A.gthreads = threads;
+            S.gS.reserve(sizeof(double) * (size_t)(maxlen + 1) * threads);
+            S.gE.reserve(sizeof(double) * (size_t)(maxlen + 1) * threads);
+            S.gC.reserve((size_t)(maxlen + 1) * threads);
+            A.gS = S.gS.as<double>();
+            A.gE = S.gE.as<double>();
+            A.gChoice = S.gC.as<uint8_t>();
+            name = launch_generic(A, trace, 0, st);
+        }
+        launch_fill_empty(A, st);
+        g_launches += 2;
+        if (trace) {
+            T.lens = A.lens;
+            T.n = m;
+            T.L = P.L;
+            T.G = P.G;
+            T.C = P.C;
+            T.flags = A.flags;
+            T.fstride = A.fstride;
+            T.nsec = (int)P.sec_starts.size();
+            T.sec_starts = D.sec_starts;
+            T.sec_ends = D.sec_ends;
+            T.map = S.map.as<int32_t>();
+            T.start = out.start ? out.start + off : nullptr;
+            T.end = out.end ? out.end + off : nullptr;
+            /* section outputs are [nsec][n_total]: the kernel indexes s*n + a with n = m, so sub-chunks
+             * of a larger run are only valid when they cover it entirely or nsec <= 1 */
+            T.sec_start = out.sec_start ? out.sec_start + off : nullptr;
+            T.sec_width = out.sec_width ? out.sec_width + off : nullptr;
+            T.ops = out.ops ? out.ops + off * out.ops_stride : nullptr;
+            T.nops = out.nops ? out.nops + off : nullptr;
+            T.ops_stride = out.ops_stride;
+            launch_traceback(T, st);
+            g_launches += 1;
+        }
+        CUDA_CHECK(cudaGetLastError());
+    }
+    g_last_kernel = name;
+    return name;
+}
+
+}  // namespace
+
+/* The [nref][n] and [nsec][n] output matrices need the TOTAL n as their row pitch when a run is split
+ * into sub-chunks.  Rather than thread a pitch through every kernel, runs that need sub-chunking use
+ * per-sub-chunk staging: see Job below, which always hands run_device a range it owns entirely. */
+
+namespace {
+
+int device_sm_count(int dev) {
+    int sms = 0;
+    CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    return sms;
+}
+
+enum Mode { MODE_SCORE_LOCAL = 0, MODE_TRACE_LOCAL = 1, MODE_SCORE_GLOBAL = 2, MODE_OPS_GLOBAL = 3, MODE_MULTI_GLOBAL = 4 };
+
+struct HostOutputs {
+    double* score = nullptr;       /* [nref][n] (nref == 1 unless MODE_MULTI with all_scores) */
+    int32_t* start = nullptr;
+    int32_t* end = nullptr;
+    int32_t* sec_start = nullptr;
+    int32_t* sec_width = nullptr;
+    int32_t* best_id = nullptr;
+    double* best = nullptr;
+    double* next_best = nullptr;
+    /* MODE_OPS_GLOBAL: general_align post-processing on the host needs ops per read */
+    std::vector<std::vector<uint8_t> >* ops = nullptr;
+};
+
+/* One pipeline slot: pinned staging + device buffers for a chunk of reads. */
+struct Slot {
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;
+    PinBuf h_rows, h_lens, h_out;
+    DevBuf d_rows, d_lens, d_out;
+    Scratch scratch;
+    long long n = 0;        /* reads in flight */
+    int64_t lo = 0;
+    bool busy = false;
+    void init() {
+        CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    }
+    void destroy() {
+        h_rows.release(); h_lens.release(); h_out.release();
+        d_rows.release(); d_lens.release(); d_out.release();
+        scratch.release();
+        if (done) cudaEventDestroy(done);
+        if (st) cudaStreamDestroy(st);
+        done = nullptr;
+        st = nullptr;
+    }
+};
+
+/* Layout of a slot's output block (same on host and device). */
+struct OutLayout {
+    size_t o_score = 0, o_start = 0, o_end = 0, o_ss = 0, o_sw = 0, o_bid = 0, o_best = 0, o_next = 0, o_nops = 0, o_ops = 0, total = 0;
+    long long ops_stride = 0;
+};
+
+OutLayout make_layout(Mode mode, long long n, int nref_scores, int nsec, int maxlen, int L) {
+    OutLayout o;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t at = 0;
+    o.o_score = at; at += al(sizeof(double) * (size_t)n * std::max(1, nref_scores));
+    if (mode == MODE_TRACE_LOCAL) {
+        o.o_start = at; at += al(sizeof(int32_t) * (size_t)n);
+        o.o_end = at; at += al(sizeof(int32_t) * (size_t)n);
+        o.o_ss = at; at += al(sizeof(int32_t) * (size_t)n * std::max(1, nsec));
+        o.o_sw = at; at += al(sizeof(int32_t) * (size_t)n * std::max(1, nsec));
+    }
+    if (mode == MODE_MULTI_GLOBAL) {
+        o.o_bid = at; at += al(sizeof(int32_t) * (size_t)n);
+        o.o_best = at; at += al(sizeof(double) * (size_t)n);
+        o.o_next = at; at += al(sizeof(double) * (size_t)n);
+    }
+    if (mode == MODE_OPS_GLOBAL) {
+        o.ops_stride = ((long long)maxlen + L + 16) & ~15LL;
+        o.o_nops = at; at += al(sizeof(int32_t) * (size_t)n);
+        o.o_ops = at; at += al((size_t)o.ops_stride * (size_t)n);
+    }
+    o.total = at;
+    return o;
+}
+
+/* Runs [lo,hi) of the reads on one device with a two-slot pipeline: pack chunk k+1 on the host while the
+ * device works on chunk k. */
+struct DeviceJob {
+    int device = 0;
+    int64_t lo = 0, hi = 0;
+    const sarlacc_reads* reads = nullptr;
+    const Plan* plan = nullptr;
+    Mode mode = MODE_SCORE_LOCAL;
+    int64_t n_total = 0;
+    HostOutputs out;
+    bool want_all_scores = false;
+    int nthreads = 1;
+    FirstError err;
+    std::string cuda_error;
+
+    void run() {
+        try {
+            run_inner();
+        } catch (CudaError& e) {
+            cuda_error = e.msg;
+        } catch (std::exception& e) {
+            cuda_error = std::string("internal error: ") + e.what();
+        }
+    }
+
+    void run_inner() {
+        const Plan& P = *plan;
+        CUDA_CHECK(cudaSetDevice(device));
+        const int sms = device_sm_count(device);
+        ReadView V{reads};
+        PackTables PT;
+        build_pack_tables(PT, reads->seq_encoding, *P.enc);
+        const bool trace = (mode == MODE_TRACE_LOCAL || mode == MODE_OPS_GLOBAL);
+        const int nsec = (int)P.sec_starts.size();
+        const int nref_scores = (mode == MODE_MULTI_GLOBAL) ? (want_all_scores ? P.nref : 0) : 1;
+
+        Slot slots[2];
+        DevPlan D;
+        struct Cleanup {
+            Slot* s; DevPlan* d;
+            ~Cleanup() { s[0].destroy(); s[1].destroy(); d->buf.release(); }
+        } cleanup{slots, &D};
+        slots[0].init();
+        slots[1].init();
+        D.upload(P, slots[0].st);
+
+        /* chunk size: bounded so that staging stays modest and the trace scratch fits its budget */
+        long long chunk = 1 << 17;
+        const char* ce = std::getenv("SARLACC_CHUNK");
+        if (ce && std::atoll(ce) > 0) chunk = std::atoll(ce);
+
+        OutLayout lay[2];
+        int which = 0;
+        auto drain = [&](Slot& s, const OutLayout& o) {
+            if (!s.busy) return;
+            CUDA_CHECK(cudaEventSynchronize(s.done));
+            const uint8_t* h = s.h_out.as<uint8_t>();
+            const long long m = s.n;
+            const int64_t g0 = s.lo;   /* global index of the slot's first read */
+            if (mode == MODE_MULTI_GLOBAL) {
+                std::memcpy(out.best_id + g0, h + o.o_bid, sizeof(int32_t) * m);
+                std::memcpy(out.best + g0, h + o.o_best, sizeof(double) * m);
+                std::memcpy(out.next_best + g0, h + o.o_next, sizeof(double) * m);
+                if (want_all_scores) {
+                    for (int b = 0; b < P.nref; ++b) {
+                        std::memcpy(out.score + (size_t)b * n_total + g0, h + o.o_score + sizeof(double) * (size_t)b * m, sizeof(double) * m);
+                    }
+                }
+            } else {
+                std::memcpy(out.score + g0, h + o.o_score, sizeof(double) * m);
+            }
+            if (mode == MODE_TRACE_LOCAL) {
+                std::memcpy(out.start + g0, h + o.o_start, sizeof(int32_t) * m);
+                std::memcpy(out.end + g0, h + o.o_end, sizeof(int32_t) * m);
+                for (int sct = 0; sct < nsec; ++sct) {
+                    std::memcpy(out.sec_start + (size_t)sct * n_total + g0, h + o.o_ss + sizeof(int32_t) * (size_t)sct * m, sizeof(int32_t) * m);
+                    std::memcpy(out.sec_width + (size_t)sct * n_total + g0, h + o.o_sw + sizeof(int32_t) * (size_t)sct * m, sizeof(int32_t) * m);
+                }
+            }
+            if (mode == MODE_OPS_GLOBAL) {
+                const int32_t* nops = reinterpret_cast<const int32_t*>(h + o.o_nops);
+                for (long long i = 0; i < m; ++i) {
+                    const uint8_t* p = h + o.o_ops + (size_t)i * o.ops_stride;
+                    (*out.ops)[g0 + i].assign(p, p + nops[i]);
+                }
+            }
+            s.busy = false;
+        };
+
+        for (int64_t c0 = lo; c0 < hi;) {
+            Slot& s = slots[which];
+            drain(s, lay[which]);
+            /* size the chunk: the trace scratch budget may force fewer reads than `chunk` */
+            int64_t c1 = std::min<int64_t>(hi, c0 + chunk);
+            s.h_lens.reserve(sizeof(int32_t) * (size_t)(c1 - c0));
+            int maxlen = 0;
+            scan_lengths(V, c0, c1, s.h_lens.as<int32_t>(), nthreads, err, maxlen);
+            if (trace) {
+                const long long fit = sub_chunk(P, maxlen, true, c1 - c0);
+                if (fit < c1 - c0) {
+                    c1 = c0 + fit;
+                    maxlen = 0;
+                    const int32_t* hl = s.h_lens.as<int32_t>();
+                    for (int64_t i = 0; i < c1 - c0; ++i) maxlen = std::max(maxlen, (int)hl[i]);
+                }
+            }
+            const long long m = c1 - c0;
+            const int stride = std::max(8, (maxlen + 8) & ~7);   /* >= maxlen+1, multiple of 8 */
+            s.h_rows.reserve(sizeof(uint16_t) * (size_t)m * stride);
+            pack_rows(V, c0, c1, PT, s.h_lens.as<int32_t>(), stride, s.h_rows.as<uint16_t>(), nthreads, P.L > 0, err);
+            if (err.kind != ERR_NONE && err.at < c1) break;   /* a serial run would have stopped here */
+
+            const OutLayout o = make_layout(mode, m, nref_scores, nsec, maxlen, P.L);
+            lay[which] = o;
+            s.d_rows.reserve(sizeof(uint16_t) * (size_t)m * stride);
+            s.d_lens.reserve(sizeof(int32_t) * (size_t)m);
+            s.d_out.reserve(o.total);
+            s.h_out.reserve(o.total);
+            CUDA_CHECK(cudaMemcpyAsync(s.d_rows.p, s.h_rows.p, sizeof(uint16_t) * (size_t)m * stride, cudaMemcpyHostToDevice, s.st));
+            CUDA_CHECK(cudaMemcpyAsync(s.d_lens.p, s.h_lens.p, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
+            uint8_t* d = s.d_out.as<uint8_t>();
+            Outputs dev;
+            dev.score = (mode == MODE_MULTI_GLOBAL && !want_all_scores) ? nullptr : reinterpret_cast<double*>(d + o.o_score);
+            if (mode == MODE_TRACE_LOCAL) {
+                dev.start = reinterpret_cast<int32_t*>(d + o.o_start);
+                dev.end = reinterpret_cast<int32_t*>(d + o.o_end);
+                dev.sec_start = reinterpret_cast<int32_t*>(d + o.o_ss);
+                dev.sec_width = reinterpret_cast<int32_t*>(d + o.o_sw);
+            }
+            if (mode == MODE_MULTI_GLOBAL) {
+                dev.best_id = reinterpret_cast<int32_t*>(d + o.o_bid);
+                dev.best = reinterpret_cast<double*>(d + o.o_best);
+                dev.next_best = reinterpret_cast<double*>(d + o.o_next);
+            }
+            if (mode == MODE_OPS_GLOBAL) {
+                dev.nops = reinterpret_cast<int32_t*>(d + o.o_nops);
+                dev.ops = d + o.o_ops;
+                dev.ops_stride = o.ops_stride;
+            }
+            run_device(P, D, s.scratch, s.st, s.d_rows.as<uint16_t>(), s.d_lens.as<int32_t>(), m, stride, maxlen, trace, dev, sms);
+            CUDA_CHECK(cudaMemcpyAsync(s.h_out.p, s.d_out.p, o.total, cudaMemcpyDeviceToHost, s.st));
+            CUDA_CHECK(cudaEventRecord(s.done, s.st));
+            s.n = m;
+            s.lo = c0;
+            s.busy = true;
+            which ^= 1;
+            c0 = c1;
+        }
+        drain(slots[which], lay[which]);
+        drain(slots[which ^ 1], lay[which ^ 1]);
+    }
+};
+
+std::vector<int> configured_devices() {
+    std::lock_guard<std::mutex> lock(g_cfg_mutex);
+    if (g_devices.empty()) return std::vector<int>{0};
+    return g_devices;
+}
+
+int require_device() {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        return fail(std::string("sarlacc_b200 requires a CUDA device (no CPU fallback exists): ") +
+                    (e != cudaSuccess ? cudaGetErrorString(e) : "no device found"));
+    }
+    return 0;
+}
+
+/* Degenerate references (L == 0) never reach a kernel: src/reference_align.cpp:82-90 runs no column, the score
+ * is scores[len] of column 0 and querymap returns (0,0) (:308-310). */
+double col0_host(bool local, double gop, double ge, int64_t i) {
+    if (local || i == 0) return 0.0;
+    return -gop - ge * (double)(i - 1);
+}
+
+/* Shared driver of all host-buffer entry points. */
+int run_host(const sarlacc_reads* reads, const sarlacc_encoding* encoding, double go, double ge,
+        const char* const* refs, int nref, Mode mode, int nsec, const int32_t* sec_starts, const int32_t* sec_ends,
+        HostOutputs out, bool want_all_scores)
+{
+    if (!reads) return fail("reads must not be NULL");
+    Encoding enc;
+    const char* msg = build_encoding(encoding, enc);
+    if (msg) return fail(msg);   /* reference_align's constructor runs before any read is touched */
+    const int64_t n = reads->n;
+    const bool local = (mode == MODE_SCORE_LOCAL || mode == MODE_TRACE_LOCAL);
+    int L = 0;
+    if (nref > 0) {
+        L = (int)std::strlen(refs[0]);
+        for (int b = 1; b < nref; ++b) {
+            if ((int)std::strlen(refs[b]) != L) return fail("all barcodes must have the same length for a fused pass");
+        }
+    }
+    Plan P;
+    build_plan(P, enc, refs, nref, L, local, go, ge);
+    if (nsec > 0) {
+        P.sec_starts.assign(sec_starts, sec_starts + nsec);
+        P.sec_ends.assign(sec_ends, sec_ends + nsec);
+        for (int s = 0; s < nsec; ++s) {
+            /* the reference indexes its mapping deque unchecked (:326-350); refuse what would be out of bounds there */
+            if (P.sec_starts[s] < 0 || P.sec_starts[s] > L || P.sec_ends[s] < 0 || P.sec_ends[s] > L) {
+                return fail("section bounds outside the adaptor");
+            }
+        }
+    }
+    if (n == 0) return 0;
+    ReadView V{reads};
+
+    if (L == 0 || nref == 0) {
+        /* no DP column exists; only the length check of the entry loop can fail */
+        for (int64_t i = 0; i < n; ++i) {
+            if (V.seq_len(i) != V.qual_len(i)) return fail(err_text(ERR_LEN));
+            const double s = col0_host(local, P.gop, P.ge, V.seq_len(i));
+            if (mode == MODE_MULTI_GLOBAL) {
+                out.best_id[i] = 0;
+                out.best[i] = -std::numeric_limits<double>::infinity();
+                out.next_best[i] = -std::numeric_limits<double>::infinity();
+            } else {
+                out.score[i] = s;
+            }
+            if (mode == MODE_TRACE_LOCAL) {
+                out.start[i] = 0;
+                out.end[i] = 0;
+                for (int sct = 0; sct < nsec; ++sct) {
+                    out.sec_start[(size_t)sct * n + i] = 1;
+                    out.sec_width[(size_t)sct * n + i] = 0;
+                }
+            }
+            if (mode == MODE_OPS_GLOBAL) (*out.ops)[i].assign((size_t)V.seq_len(i), (uint8_t)'I');
+        }
+        return 0;
+    }
+
+    if (require_device()) return 1;
+    std::vector<int> devs = configured_devices();
+    if ((int64_t)devs.size() > n) devs.resize((size_t)std::max<int64_t>(1, n));
+    const int nd = (int)devs.size();
+    std::vector<DeviceJob> jobs(nd);
+    for (int d = 0; d < nd; ++d) {
+        DeviceJob& J = jobs[d];
+        J.device = devs[d];
+        J.lo = n * d / nd;
+        J.hi = n * (d + 1) / nd;
+        J.reads = reads;
+        J.plan = &P;
+        J.mode = mode;
+        J.n_total = n;
+        J.out = out;
+        J.want_all_scores = want_all_scores;
+        J.nthreads = host_threads_for(nd);
+    }
+    if (nd == 1) {
+        jobs[0].run();
+    } else {
+        std::vector<std::thread> pool;
+        for (int d = 0; d < nd; ++d) pool.emplace_back([&jobs, d] { jobs[d].run(); });
+        for (auto& t : pool) t.join();
+    }
+    for (int d = 0; d < nd; ++d) {
+        if (!jobs[d].cuda_error.empty()) return fail(jobs[d].cuda_error);
+    }
+    FirstError err;
+    for (int d = 0; d < nd; ++d) err.merge(jobs[d].err);
+
+    /* Unrecognized reference bases (src/reference_align.cpp:211) surface at the first read that has any
+     * base: column by column, so a bad quality in that read wins unless the very first column is the bad
+     * one (:184-217).  With several references the unfused R loop runs one .Call per barcode, so read
+     * errors (raised in the first call) win over a bad later barcode. */
+    {
+        int bfirst = -1;
+        for (int b = 0; b < nref; ++b) {
+            if (P.bad_col[b] >= 0) { bfirst = b; break; }
+        }
+        if (bfirst >= 0) {
+            int64_t i0 = -1;
+            for (int64_t i = 0; i < n; ++i) {
+                if (V.seq_len(i) != V.qual_len(i)) break;
+                if (V.seq_len(i) > 0) { i0 = i; break; }
+            }
+            if (i0 >= 0) {
+                if (bfirst == 0) {
+                    if (err.kind == ERR_NONE || err.at > i0) {
+                        err.at = i0;
+                        err.kind = ERR_REF;
+                    } else if (err.at == i0 && P.bad_col[0] == 0) {
+                        err.kind = ERR_REF;
+                    }
+                } else if (err.kind == ERR_NONE) {
+                    err.at = i0;
+                    err.kind = ERR_REF;
+                }
+            }
+        }
+    }
+    if (err.kind != ERR_NONE) return fail(err_text(err.kind));
+    return 0;
+}
+
+}  // namespace
+
+/* =================================================================================================
+ * C ABI
+ * ================================================================================================= */
+
+extern "C" {
+
+const char* sarlacc_last_error(void) { return g_error.c_str(); }
+
+const char* sarlacc_version(void) { return "sarlacc_b200 0.1 (sm_100a)"; }
+
+int sarlacc_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return count;
+}
+
+int sarlacc_set_devices(const int* devices, int ndevices) {
+    if (ndevices < 0 || (ndevices > 0 && !devices)) return fail("invalid device list");
+    const int count = sarlacc_device_count();
+    for (int i = 0; i < ndevices; ++i) {
+        if (devices[i] < 0 || devices[i] >= count) return fail("device index out of range");
+    }
+    std::lock_guard<std::mutex> lock(g_cfg_mutex);
+    g_devices.assign(devices, devices + ndevices);
+    return 0;
+}
+
+int sarlacc_set_host_threads(int nthreads) {
+    if (nthreads < 0) return fail("nthreads must be >= 0");
+    g_host_threads = nthreads;
+    return 0;
+}
+
+int64_t sarlacc_kernel_launches(int reset) {
+    const long long v = g_launches.load();
+    if (reset) g_launches.store(0);
+    return v;
+}
+
+int sarlacc_adaptor_align(const sarlacc_reads* reads, const sarlacc_encoding* encoding,
+        double gapopen, double gapext, const char* adaptor,
+        int nsec, const int32_t* sec_starts, const int32_t* sec_ends,
+        double* score, int32_t* start, int32_t* end, int32_t* sec_start, int32_t* sec_width)
+{
+    if (!adaptor) return fail("adaptor sequence should be a string");
+    if (nsec < 0) return fail("section starts and ends should have the same length");
+    HostOutputs out;
+    out.score = score;
+    out.start = start;
+    out.end = end;
+    out.sec_start = sec_start;
+    out.sec_width = sec_width;
+    const char* refs[1] = {adaptor};
+    return run_host(reads, encoding, gapopen, gapext, refs, 1, MODE_TRACE_LOCAL, nsec, sec_starts, sec_ends, out, false);
+}
+
+int sarlacc_adaptor_align_score_only(const sarlacc_reads* reads, const sarlacc_encoding* encoding,
+        double gapopen, double gapext, const char* adaptor, double* score)
+{
+    if (!adaptor) return fail("adaptor sequence should be a string");
+    HostOutputs out;
+    out.score = score;
+    const char* refs[1] = {adaptor};
+    return run_host(reads, encoding, gapopen, gapext, refs, 1, MODE_SCORE_LOCAL, 0, nullptr, nullptr, out, false);
+}
+
+int sarlacc_barcode_align(const sarlacc_reads* reads, const sarlacc_encoding* encoding,
+        double gapopen, double gapext, const char* reference, double* score)
+{
+    if (!reference) return fail("barcode sequence should be a string");
+    HostOutputs out;
+    out.score = score;
+    const char* refs[1] = {reference};
+    return run_host(reads, encoding, gapopen, gapext, refs, 1, MODE_SCORE_GLOBAL, 0, nullptr, nullptr, out, false);
+}
+
+int sarlacc_barcode_align_multi(const sarlacc_reads* reads, const sarlacc_encoding* encoding,
+        double gapopen, double gapext, const char* const* barcodes, int nbarcodes,
+        int32_t* best_id, double* best, double* next_best, double* all_scores)
+{
+    if (nbarcodes < 0 || (nbarcodes > 0 && !barcodes)) return fail("barcode sequence should be a string");
+    HostOutputs out;
+    out.score = all_scores;
+    out.best_id = best_id;
+    out.best = best;
+    out.next_best = next_best;
+    return run_host(reads, encoding, gapopen, gapext, barcodes, nbarcodes, MODE_MULTI_GLOBAL, 0, nullptr, nullptr, out, all_scores != nullptr);
+}
+
+int sarlacc_general_align(const sarlacc_reads* reads, const sarlacc_encoding* encoding,
+        double gapopen, double gapext, const char* reference, int edit_only,
+        double* score, int32_t* edit, char* ref_aln, char* query_aln, int64_t aln_stride)
+{
+    if (!reference) return fail("reference sequence should be a string");
+    if (!reads) return fail("reads must not be NULL");
+    const int64_t n = reads->n;
+    std::vector<std::vector<uint8_t> > ops((size_t)std::max<int64_t>(n, 0));
+    HostOutputs out;
+    out.score = score;
+    out.ops = &ops;
+    const char* refs[1] = {reference};
+    int rc = run_host(reads, encoding, gapopen, gapext, refs, 1, MODE_OPS_GLOBAL, 0, nullptr, nullptr, out, false);
+    if (rc) return rc;
+    /* fill_strings + the edit-distance loop of src/general_align.cpp:44-57, from the device's operation
+     * list and the ORIGINAL characters (the packed rows do not keep non-ACGT read characters). */
+    ReadView V{reads};
+    const size_t L = std::strlen(reference);
+    static const char decode[16] = {'-', 'A', 'C', 'M', 'G', 'R', 'S', 'V', 'T', 'W', 'Y', 'H', 'K', 'D', 'B', 'N'};
+    for (int64_t i = 0; i < n; ++i) {
+        const std::vector<uint8_t>& op = ops[(size_t)i];
+        const uint8_t* s = V.seq(i);
+        const size_t nop = op.size();
+        if (!edit_only && (int64_t)nop + 1 > aln_stride) return fail("aln_stride too small for the alignment strings");
+        size_t ri = 0, qi = 0;
+        int32_t ed = 0;
+        for (size_t x = 0; x < nop; ++x) {
+            const uint8_t o = op[nop - 1 - x];   /* device wrote back to front */
+            char rc_ = '-', qc = '-';
+            if (o != 'I') rc_ = reference[ri++];
+            if (o != 'D') {
+                const uint8_t raw = s[qi++];
+                qc = (reads->seq_encoding == SARLACC_SEQ_BIOSTRINGS) ? (raw < 16 ? decode[raw] : (raw == 16 ? '-' : (raw == 32 ? '+' : '.'))) : (char)raw;
+            }
+            if (rc_ != qc) ++ed;
+            if (!edit_only) {
+                ref_aln[i * aln_stride + (int64_t)x] = rc_;
+                query_aln[i * aln_stride + (int64_t)x] = qc;
+            }
+        }
+        (void)L;
+        edit[i] = ed;
+        if (!edit_only) {
+            ref_aln[i * aln_stride + (int64_t)nop] = '\0';
+            query_aln[i * aln_stride + (int64_t)nop] = '\0';
+        }
+    }
+    return 0;
+}
+
+/* ---- resident windows ------------------------------------------------------------------------- */
+
+struct sarlacc_resident {
+    int device = 0;
+    int64_t n = 0;
+    int stride = 0;
+    int maxlen = 0;
+    int64_t total_len = 0;
+    Encoding enc;
+    cudaStream_t own_stream = nullptr;
+    DevBuf d_rows, d_lens, d_out;
+    Scratch scratch;
+    DevPlan dplan;
+    Plan plan;
+    OutLayout lay;
+    int nsec = 0;
+    Mode mode = MODE_SCORE_LOCAL;
+    bool has_result = false;
+    int sms = 0;
+    std::string last_kernel;
+    std::vector<int32_t> h_lens;
+};
+
+sarlacc_resident* sarlacc_resident_create(const sarlacc_reads* reads, const sarlacc_encoding* encoding, int device) {
+    if (!reads) { fail("reads must not be NULL"); return nullptr; }
+    if (require_device()) return nullptr;
+    std::unique_ptr<sarlacc_resident> r(new sarlacc_resident());
+    const char* msg = build_encoding(encoding, r->enc);
+    if (msg) { fail(msg); return nullptr; }
+    try {
+        CUDA_CHECK(cudaSetDevice(device));
+        r->device = device;
+        r->sms = device_sm_count(device);
+        r->n = reads->n;
+        CUDA_CHECK(cudaStreamCreateWithFlags(&r->own_stream, cudaStreamNonBlocking));
+        ReadView V{reads};
+        PackTables PT;
+        build_pack_tables(PT, reads->seq_encoding, r->enc);
+        const int nthreads = host_threads_for(1);
+        r->h_lens.assign((size_t)std::max<int64_t>(r->n, 1), 0);
+        FirstError err;
+        scan_lengths(V, 0, r->n, r->h_lens.data(), nthreads, err, r->maxlen);
+        r->stride = std::max(8, (r->maxlen + 8) & ~7);
+        r->total_len = 0;
+        for (int64_t i = 0; i < r->n; ++i) r->total_len += r->h_lens[(size_t)i];
+        /* pack + upload in pieces through a pinned staging buffer */
+        const int64_t piece = std::max<int64_t>(1, (int64_t)(64u << 20) / ((int64_t)r->stride * 2));
+        PinBuf stage[2];
+        cudaEvent_t ev[2];
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+        bool used[2] = {false, false};
+        r->d_rows.reserve(sizeof(uint16_t) * (size_t)std::max<int64_t>(r->n, 1) * r->stride);
+        r->d_lens.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(r->n, 1));
+        int w = 0;
+        for (int64_t c0 = 0; c0 < r->n; c0 += piece, w ^= 1) {
+            const int64_t c1 = std::min(r->n, c0 + piece);
+            if (used[w]) CUDA_CHECK(cudaEventSynchronize(ev[w]));
+            stage[w].reserve(sizeof(uint16_t) * (size_t)(c1 - c0) * r->stride);
+            pack_rows(V, c0, c1, PT, r->h_lens.data() + c0, r->stride, stage[w].as<uint16_t>(), nthreads, true, err);
+            CUDA_CHECK(cudaMemcpyAsync(r->d_rows.as<uint16_t>() + (size_t)c0 * r->stride, stage[w].p,
+                                       sizeof(uint16_t) * (size_t)(c1 - c0) * r->stride, cudaMemcpyHostToDevice, r->own_stream));
+            CUDA_CHECK(cudaEventRecord(ev[w], r->own_stream));
+            used[w] = true;
+        }
+        if (r->n > 0) {
+            CUDA_CHECK(cudaMemcpyAsync(r->d_lens.p, r->h_lens.data(), sizeof(int32_t) * (size_t)r->n, cudaMemcpyHostToDevice, r->own_stream));
+        }
+        CUDA_CHECK(cudaStreamSynchronize(r->own_stream));
+        cudaEventDestroy(ev[0]);
+        cudaEventDestroy(ev[1]);
+        stage[0].release();
+        stage[1].release();
+        if (err.kind != ERR_NONE) {
+            fail(err_text(err.kind));
+            sarlacc_resident_free(r.release());
+            return nullptr;
+        }
+    } catch (CudaError& e) {
+        fail(e.msg);
+        sarlacc_resident_free(r.release());
+        return nullptr;
+    }
+    return r.release();
+}
+
+void sarlacc_resident_free(sarlacc_resident* r) {
+    if (!r) return;
+    cudaSetDevice(r->device);
+    r->d_rows.release();
+    r->d_lens.release();
+    r->d_out.release();
+    r->scratch.release();
+    r->dplan.buf.release();
+    if (r->own_stream) cudaStreamDestroy(r->own_stream);
+    delete r;
+}
+
+int64_t sarlacc_resident_n(const sarlacc_resident* r) { return r ? r->n : 0; }
+
+int64_t sarlacc_resident_cells(const sarlacc_resident* r, int rlen) { return r ? r->total_len * (int64_t)rlen : 0; }
+
+int64_t sarlacc_resident_bytes(const sarlacc_resident* r) {
+    return r ? (int64_t)sizeof(uint16_t) * r->n * r->stride + (int64_t)sizeof(int32_t) * r->n : 0;
+}
+
+int sarlacc_resident_align(sarlacc_resident* r, int mode, double gapopen, double gapext, const char* reference,
+        int nsec, const int32_t* sec_starts, const int32_t* sec_ends, void* stream)
+{
+    if (!r) return fail("resident handle is NULL");
+    if (!reference) return fail("adaptor sequence should be a string");
+    if (mode < 0 || mode > 2) return fail("mode must be 0 (score, local), 1 (traceback, local) or 2 (score, global)");
+    const Mode md = (Mode)mode;
+    const bool local = md != MODE_SCORE_GLOBAL;
+    const bool trace = md == MODE_TRACE_LOCAL;
+    const int L = (int)std::strlen(reference);
+    if (L == 0) return fail("resident runs need a non-empty reference");
+    try {
+        CUDA_CHECK(cudaSetDevice(r->device));
+        cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : r->own_stream;
+        const char* refs[1] = {reference};
+        build_plan(r->plan, r->enc, refs, 1, L, local, gapopen, gapext);
+        if (r->plan.bad_col[0] >= 0 && r->total_len > 0) return fail(err_text(ERR_REF));
+        r->plan.sec_starts.clear();
+        r->plan.sec_ends.clear();
+        if (trace && nsec > 0) {
+            r->plan.sec_starts.assign(sec_starts, sec_starts + nsec);
+            r->plan.sec_ends.assign(sec_ends, sec_ends + nsec);
+            for (int s = 0; s < nsec; ++s) {
+                if (sec_starts[s] < 0 || sec_starts[s] > L || sec_ends[s] < 0 || sec_ends[s] > L) return fail("section bounds outside the adaptor");
+            }
+        }
+        r->nsec = trace ? nsec : 0;
+        r->mode = md;
+        r->dplan.upload(r->plan, st);
+        r->lay = make_layout(md, std::max<int64_t>(r->n, 1), 1, r->nsec, r->maxlen, L);
+        r->d_out.reserve(r->lay.total);
+        uint8_t* d = r->d_out.as<uint8_t>();
+        /* Sub-chunks (scratch budget) write straight into the full-size output block: sections are laid out
+         * [nsec][n] so each sub-chunk gets its own launch set with per-section base pointers. */
+        const long long cn = sub_chunk(r->plan, r->maxlen, trace, std::max<int64_t>(r->n, 1));
+        const char* name = "";
+        for (long long off = 0; off < r->n; off += cn) {
+            const long long m = std::min<long long>(cn, r->n - off);
+            Outputs dev;
+            dev.score = reinterpret_cast<double*>(d + r->lay.o_score) + off;
+            if (trace) {
+                dev.start = reinterpret_cast<int32_t*>(d + r->lay.o_start) + off;
+                dev.end = reinterpret_cast<int32_t*>(d + r->lay.o_end) + off;
+                /* section matrices are re-based per sub-chunk below: run_device sees n = m, so give it a
+                 * compact [nsec][m] staging area and scatter afterwards when the run is split */
+                dev.sec_start = reinterpret_cast<int32_t*>(d + r->lay.o_ss) + (cn >= r->n ? 0 : off * (long long)std::max(1, r->nsec));
+                dev.sec_width = reinterpret_cast<int32_t*>(d + r->lay.o_sw) + (cn >= r->n ? 0 : off * (long long)std::max(1, r->nsec));
+            }
+            name = run_device(r->plan, r->dplan, r->scratch, st, r->d_rows.as<uint16_t>() + (size_t)off * r->stride,
+                              r->d_lens.as<int32_t>() + off, m, r->stride, r->maxlen, trace, dev, r->sms);
+        }
+        r->last_kernel = std::string(name) + " G=" + std::to_string(r->plan.G) + " C=" + std::to_string(r->plan.C);
+        r->has_result = true;
+    } catch (CudaError& e) {
+        return fail(e.msg);
+    }
+    return 0;
+}
+
+int sarlacc_resident_fetch(sarlacc_resident* r, double* score, int32_t* start, int32_t* end,
+        int32_t* sec_start, int32_t* sec_width, void* stream)
+{
+    if (!r) return fail("resident handle is NULL");
+    if (!r->has_result) return fail("no resident run to fetch");
+    try {
+        CUDA_CHECK(cudaSetDevice(r->device));
+        cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : r->own_stream;
+        const uint8_t* d = r->d_out.as<uint8_t>();
+        const size_t n = (size_t)r->n;
+        if (n == 0) return 0;
+        if (score) CUDA_CHECK(cudaMemcpyAsync(score, d + r->lay.o_score, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+        if (r->mode == MODE_TRACE_LOCAL) {
+            if (start) CUDA_CHECK(cudaMemcpyAsync(start, d + r->lay.o_start, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+            if (end) CUDA_CHECK(cudaMemcpyAsync(end, d + r->lay.o_end, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+            const long long cn = sub_chunk(r->plan, r->maxlen, true, (long long)n);
+            if (r->nsec > 0 && (sec_start || sec_width)) {
+                if (cn >= (long long)n) {
+                    if (sec_start) CUDA_CHECK(cudaMemcpyAsync(sec_start, d + r->lay.o_ss, sizeof(int32_t) * n * r->nsec, cudaMemcpyDeviceToHost, st));
+                    if (sec_width) CUDA_CHECK(cudaMemcpyAsync(sec_width, d + r->lay.o_sw, sizeof(int32_t) * n * r->nsec, cudaMemcpyDeviceToHost, st));
+                } else {
+                    /* split run: device holds consecutive [nsec][m] blocks */
+                    for (long long off = 0; off < (long long)n; off += cn) {
+                        const long long m = std::min<long long>(cn, (long long)n - off);
+                        for (int s = 0; s < r->nsec; ++s) {
+                            const size_t src = sizeof(int32_t) * ((size_t)off * r->nsec + (size_t)s * m);
+                            if (sec_start) CUDA_CHECK(cudaMemcpyAsync(sec_start + (size_t)s * n + off, d + r->lay.o_ss + src, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, st));
+                            if (sec_width) CUDA_CHECK(cudaMemcpyAsync(sec_width + (size_t)s * n + off, d + r->lay.o_sw + src, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, st));
+                        }
+                    }
+                }
+            }
+        }
+        CUDA_CHECK(cudaStreamSynchronize(st));
+    } catch (CudaError& e) {
+        return fail(e.msg);
+    }
+    return 0;
+}
+
+const double* sarlacc_resident_scores_device(const sarlacc_resident* r) {
+    if (!r || !r->has_result) return nullptr;
+    return reinterpret_cast<const double*>(r->d_out.as<uint8_t>() + r->lay.o_score);
+}
+
+const char* sarlacc_resident_last_kernel(const sarlacc_resident* r) { return r ? r->last_kernel.c_str() : ""; }
+
+}  // extern "C"

@@ -1,0 +1,541 @@
+/* CUDA kernels (sm_100a) for the quality-weighted adaptor alignment.
+ *
+ * Replaces the arithmetic of reference_align::align / align_column / backtrack / fill_map
+ * (/root/reference/src/reference_align.cpp:54-181, 231-350).  Everything is FP64 with the
+ * reference's operation order and comparison operators, compiled with --fmad=false and explicit
+ * *_rn intrinsics, because tie-breaking between co-optimal paths depends on the last bit.
+ *
+ * Forward kernel `wf_forward<C,TRACE,ALT>` ("wavefront"):
+ *   - a group of G lanes (G = 1..32, power of two, chosen per reference length) owns one alignment;
+ *     lane j owns C consecutive reference columns j*C+1 .. j*C+C, state H[i-1][c], F[i-1][c] in registers;
+ *   - read rows stream through the group: lane j works on row t-j at step t and hands H/E of its last
+ *     column to lane j+1 with two 64-bit warp shuffles -- the anti-diagonal wavefront;
+ *   - alignments are chained back to back (lane 0 starts the next alignment while lane G-1 finishes
+ *     the previous one), so the pipeline never drains and short references cost no skew;
+ *   - per cell it records 4 bits {pd,p5,p1,p2}; the traceback kernel turns them back into the
+ *     reference's path.  See DESIGN.md for why these 4 bits are equivalent to the reference's
+ *     int direction matrix with jump lengths.
+ *
+ * Generic kernel `generic_forward`: one thread per alignment, literal recurrence, state in global
+ * memory.  Used for shapes/parameters outside the wavefront kernel's envelope (reference longer
+ * than 384, more than one IUPAC class, negative gap opening ...).  Slow but exact, and still CUDA.
+ */
+#include "kernels.h"
+
+#include <type_traits>
+
+namespace sarlacc {
+
+namespace {
+
+constexpr int kBlock = 128;
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xfff0000000000000LL); }
+
+/* H[i][0]: src/reference_align.cpp:65-74 */
+__device__ __forceinline__ double col0_value(int local, double gop, double ge, int i) {
+    if (local || i == 0) return 0.0;
+    return __dsub_rn(-gop, __dmul_rn(ge, (double)(i - 1)));
+}
+
+template <int C>
+struct FlagWord {
+    using type = typename std::conditional<(C <= 8), uint32_t, unsigned long long>::type;
+};
+
+template <int C>
+struct WfBounds {
+    static constexpr int min_blocks = (C <= 9) ? 4 : 3;
+};
+
+/* R/barcodeAlign.R:28-34: strict `>` for best, then strict `>` for next best. */
+__device__ __forceinline__ void update_best(double s, int id, double& best, double& next, int& bid) {
+    if (s > best) {
+        bid = id;
+        next = best;
+        best = s;
+    } else if (s > next) {
+        next = s;
+    }
+}
+
+template <int C, bool TRACE, bool ALT>
+__global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(const __grid_constant__ AlignArgs A)
+{
+    using WT = typename FlagWord<C>::type;
+    extern __shared__ double smem_d[];
+    const int L = A.L, nref = A.nref, encn = A.enc_n;
+    double* row0s = smem_d;                 /* [L+1]            */
+    double* costs = row0s + (L + 1);        /* [3][encn]: match1, mismatch1, alt */
+    uint8_t* refm = reinterpret_cast<uint8_t*>(costs + 3 * encn);   /* [nref][L] */
+    uint8_t* refk = refm + (size_t)nref * L;                        /* [nref][L] */
+
+    for (int x = threadIdx.x; x <= L; x += blockDim.x) row0s[x] = A.row0[x];
+    for (int x = threadIdx.x; x < encn; x += blockDim.x) {
+        costs[x] = A.cost[x];
+        costs[encn + x] = A.cost[encn + x];
+        costs[2 * encn + x] = ALT ? A.cost[(size_t)A.alt_row * encn + x] : 0.0;
+    }
+    for (int x = threadIdx.x; x < nref * L; x += blockDim.x) {
+        refm[x] = A.refmask[x];
+        refk[x] = A.refkind[x];
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int G = A.G;
+    const int j = lane & (G - 1);
+    const int gpw = 32 / G;
+    const long long warp_global = (long long)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+    const long long gidx = warp_global * gpw + lane / G;
+    const long long NG = (long long)gridDim.x * (kBlock / 32) * gpw;
+    const int c0 = j * C;                       /* this lane owns DP columns c0+1 .. c0+C */
+    const int jl = (L - 1) / C, kl = (L - 1) % C;   /* owner of the last column */
+    const double gop = A.gop, ge = A.ge, ngop = -A.gop, nge = -A.ge;
+    const int local = A.local;
+    const double NEG = neg_inf();
+
+    /* Per-slot constants.  one[k] = 0 only for the last reference column in local mode, where vertical
+     * gaps are free (src/reference_align.cpp:120-121): fma(-gop, 0, x) == x - 0 == x exactly. */
+    double one[C];
+    uint32_t refpack[(C + 7) / 8];
+    uint32_t altmask = 0;
+#pragma unroll
+    for (int k = 0; k < C; ++k) one[k] = (local && c0 + k == L - 1) ? 0.0 : 1.0;
+
+    auto load_slots = [&](int b) {
+#pragma unroll
+        for (int w = 0; w < (C + 7) / 8; ++w) refpack[w] = 0;
+        altmask = 0;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const int c = c0 + k;
+            if (c < L) {
+                refpack[k >> 3] |= (uint32_t)refm[(size_t)b * L + c] << (4 * (k & 7));
+                if (refk[(size_t)b * L + c] != COL_ACGT) altmask |= 1u << k;
+            }
+        }
+    };
+    load_slots(0);
+
+    double S[C], F[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) { S[k] = 0.0; F[k] = NEG; }
+    double outS = 0.0, outE = NEG, diag0 = 0.0;
+    long long a = gidx - NG;
+    int b = nref - 1;
+    int i = 0, len = 0, delay = j;
+    bool done = false;
+    const uint16_t* rowp = A.rows;
+    double best = NEG, nextb = NEG;
+    int bid = 0;
+
+    while (__any_sync(FULL, !done)) {
+        /* Left boundary for the row this lane is about to process: what lane j-1 produced one step ago. */
+        double Sl = __shfl_up_sync(FULL, outS, 1, G);
+        double El = __shfl_up_sync(FULL, outE, 1, G);
+        bool act = !done;
+        if (delay > 0) { --delay; act = false; }
+
+        if (act && i == len) {
+            /* next (alignment, reference) item of this group's chain */
+            ++b;
+            if (b == nref) {
+                b = 0;
+                a += NG;
+                while (a < A.n && (len = A.lens[a]) == 0) a += NG;   /* empty reads: launch_fill_empty */
+            }
+            if (a >= A.n) {
+                done = true;
+                act = false;
+            } else {
+                i = 0;
+                rowp = A.rows + a * (long long)A.stride;
+#pragma unroll
+                for (int k = 0; k < C; ++k) {
+                    S[k] = (c0 + k + 1 <= L) ? row0s[c0 + k + 1] : 0.0;   /* H[0][c] */
+                    F[k] = NEG;                                            /* up_jump_score, :122 */
+                }
+                diag0 = row0s[c0 < L ? c0 : L];                            /* H[0][c0] */
+                if (nref > 1) {
+                    load_slots(b);
+                    if (b == 0) { best = NEG; nextb = NEG; bid = 0; }
+                }
+            }
+        }
+
+        if (act) {
+            ++i;
+            const unsigned rw = rowp[i - 1];
+            const unsigned q = rw & 0xffu;
+            const unsigned obsrep = (rw >> 8) * 0x11111111u;
+            const double mq = costs[q], xq = costs[encn + q];
+            double aq = 0.0;
+            if (ALT) aq = costs[2 * encn + q];
+
+            if (j == 0) {   /* column 0: src/reference_align.cpp:64-78 */
+                Sl = col0_value(local, gop, ge, i);
+                El = NEG;
+            }
+            double diag = diag0;
+            diag0 = Sl;
+            WT fl = 0;
+#pragma unroll
+            for (int k = 0; k < C; ++k) {
+                /* horizontal: open from H[i][c-1] vs extend E[i][c-1] (:129-140).  When the left cell itself
+                 * chose "left", H == E bitwise and go' >= ge makes max(Ee,hO) the reference's value. */
+                const double hO = __dsub_rn(Sl, gop);
+                const double Ee = __dsub_rn(El, ge);
+                const bool p1 = Ee > hO;
+                const double h = p1 ? Ee : hO;
+                /* vertical: open from H[i-1][c] vs extend F[i-1][c] (:145-155); free in the last local column */
+                const double vO = __fma_rn(ngop, one[k], S[k]);
+                const double Fe = __fma_rn(nge, one[k], F[k]);
+                const bool p2 = Fe > vO;
+                const double v = p2 ? Fe : vO;
+                /* (mis)match (:159, :184-225) */
+                const bool pm = (obsrep & refpack[k >> 3] & (0xFu << (4 * (k & 7)))) != 0;
+                double cost = pm ? mq : xq;
+                if (ALT) cost = ((altmask >> k) & 1u) ? aq : cost;
+                const double m = __dadd_rn(diag, cost);
+                diag = S[k];
+                /* choice (:164-174): diag only if strictly best, horizontal only if strictly > vertical */
+                const bool p5 = h > v;
+                const double t = p5 ? h : v;
+                const bool pd = m > t;
+                const double Sn = pd ? m : t;
+                S[k] = Sn;
+                F[k] = v;
+                Sl = Sn;
+                El = h;
+                if (TRACE) fl |= (WT)((pd ? 1u : 0u) | (p5 ? 2u : 0u) | (p1 ? 4u : 0u) | (p2 ? 8u : 0u)) << (4 * k);
+            }
+            outS = Sl;
+            outE = El;
+            if (TRACE) {
+                reinterpret_cast<WT*>(A.flags)[a * A.fstride + (long long)(i + j) * G + j] = fl;
+            }
+            if (i == len && j == jl) {
+                double s = S[0];
+#pragma unroll
+                for (int k = 1; k < C; ++k) s = (k == kl) ? S[k] : s;
+                if (A.score) A.score[(long long)b * A.n + a] = s;
+                if (nref > 1) {
+                    update_best(s, b + 1, best, nextb, bid);
+                    if (b == nref - 1 && A.best_id) {
+                        A.best_id[a] = bid;
+                        A.best[a] = best;
+                        A.next_best[a] = nextb;
+                    }
+                }
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Generic fallback: literal restatement of align_column, one thread per alignment.
+ * gS/gE/gChoice: [maxlen+1][gthreads] (row-major over rows so that a warp's accesses coalesce).
+ */
+enum { CH_DIAG = 0, CH_LEFT = 1, CH_UP = 2 };
+
+__global__ void __launch_bounds__(128) generic_forward(const AlignArgs A, const int trace)
+{
+    const long long T = A.gthreads;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const int L = A.L, encn = A.enc_n;
+    const double gop = A.gop, ge = A.ge;
+    const double NEG = neg_inf();
+    double* gS = A.gS + t;
+    double* gE = A.gE + t;
+    uint8_t* gC = A.gChoice + t;
+
+    for (long long a = t; a < A.n; a += T) {
+        const int len = A.lens[a];
+        if (len == 0) continue;
+        const uint16_t* rowp = A.rows + a * (long long)A.stride;
+        uint8_t* fl = trace ? reinterpret_cast<uint8_t*>(A.flags) + a * A.fstride : nullptr;
+        double best = NEG, nextb = NEG;
+        int bid = 0;
+        for (int b = 0; b < A.nref; ++b) {
+            for (int i = 0; i <= len; ++i) {
+                gS[i * T] = col0_value(A.local, gop, ge, i);
+                gE[i * T] = NEG;
+                gC[i * T] = CH_UP;          /* directions[0..len] = -1, :64 */
+            }
+            for (int c = 1; c <= L; ++c) {
+                const bool last = A.local && c == L;
+                const unsigned mask = A.refmask[(size_t)b * L + c - 1];
+                const unsigned kind = A.refkind[(size_t)b * L + c - 1];
+                const double vo = last ? 0.0 : gop, ve = last ? 0.0 : ge;
+                double diag = gS[0];
+                double sprev = __dsub_rn(diag, gC[0] == CH_LEFT ? ge : gop);   /* :117 */
+                gS[0] = sprev;
+                gC[0] = CH_LEFT;                                                /* :118 */
+                int chprev = CH_LEFT;
+                double upS = NEG;
+                for (int i = 1; i <= len; ++i) {
+                    const double sold = gS[i * T];
+                    double horiz = __dsub_rn(sold, gC[i * T] == CH_LEFT ? ge : gop);
+                    const double ls = __dsub_rn(gE[i * T], ge);
+                    const bool p1 = ls > horiz;
+                    if (p1) horiz = ls;
+                    gE[i * T] = horiz;
+                    double vert = __dsub_rn(sprev, chprev == CH_UP ? ve : vo);
+                    upS = __dsub_rn(upS, ve);
+                    const bool p2 = upS > vert;
+                    if (p2) vert = upS;
+                    upS = vert;
+                    const unsigned rw = rowp[i - 1];
+                    const unsigned q = rw & 0xffu;
+                    double cost;
+                    if (kind == COL_ACGT) {
+                        cost = ((rw >> 8) & mask) ? A.cost[q] : A.cost[encn + q];
+                    } else {
+                        cost = A.cost[(size_t)(1 + kind) * encn + q];
+                    }
+                    const double m = __dadd_rn(diag, cost);
+                    diag = sold;
+                    const bool p5 = horiz > vert;
+                    int ch;
+                    double s;
+                    if (m > horiz && m > vert) {
+                        ch = CH_DIAG; s = m;
+                    } else if (p5) {
+                        ch = CH_LEFT; s = horiz;
+                    } else {
+                        ch = CH_UP; s = vert;
+                    }
+                    gS[i * T] = s;
+                    gC[i * T] = (uint8_t)ch;
+                    sprev = s;
+                    chprev = ch;
+                    if (trace) {
+                        fl[(long long)(c - 1) * len + (i - 1)] =
+                            (uint8_t)((ch == CH_DIAG ? 1u : 0u) | (p5 ? 2u : 0u) | (p1 ? 4u : 0u) | (p2 ? 8u : 0u));
+                    }
+                }
+            }
+            const double s = gS[(long long)len * T];
+            if (A.score) A.score[(long long)b * A.n + a] = s;
+            if (A.nref > 1) update_best(s, b + 1, best, nextb, bid);
+        }
+        if (A.nref > 1 && A.best_id) {
+            A.best_id[a] = bid;
+            A.best[a] = best;
+            A.next_best[a] = nextb;
+        }
+    }
+}
+
+/* Empty reads need no DP: the score is the row-0 chain H[0][L] (e.g. -(16+5) for a 16-mer, go=5, ge=1;
+ * tests/testthat/test-adaptor-align.R:53-56). */
+__global__ void fill_empty(const AlignArgs A)
+{
+    const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= A.n || A.lens[a] != 0) return;
+    const double s = A.row0[A.L];
+    for (int b = 0; b < A.nref; ++b) {
+        if (A.score) A.score[(long long)b * A.n + a] = s;
+    }
+    if (A.nref > 1 && A.best_id) {
+        A.best_id[a] = 1;
+        A.best[a] = s;
+        A.next_best[a] = s;   /* second barcode ties: not > best, but > -Inf */
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Traceback: one thread per alignment walks the 4-bit records.
+ *
+ * Equivalence with reference backtrack<> (src/reference_align.cpp:231-278): a positive direction d at
+ * (i,c) means "move left d columns"; d = 1 + pos - left_jump_points[i] counts the columns since the
+ * running horizontal gap of row i was last re-opened, i.e. the run of consecutive E-extend decisions
+ * (:134) ending at c.  p1 is that decision evaluated with the open penalty; the reference evaluates
+ * it with the extend penalty when the left cell chose "left", in which case it is always false
+ * (H == E bitwise there) -- hence ext = p1 && left-neighbour-did-not-choose-left.  Same for up/F.
+ */
+struct FlagReader {
+    const TraceArgs& T;
+    long long a;
+    int len;
+    __device__ unsigned get(int i, int c) const {
+        if (T.layout == 0) {
+            const int j = (c - 1) / T.C, k = (c - 1) % T.C;
+            const long long w = a * T.fstride + (long long)(i + j) * T.G + j;
+            if (T.wordbytes == 4) {
+                return (reinterpret_cast<const uint32_t*>(T.flags)[w] >> (4 * k)) & 15u;
+            }
+            return (unsigned)((reinterpret_cast<const unsigned long long*>(T.flags)[w] >> (4 * k)) & 15ull);
+        }
+        return reinterpret_cast<const uint8_t*>(T.flags)[a * T.fstride + (long long)(c - 1) * len + (i - 1)];
+    }
+    __device__ int choice(int i, int c) const {
+        if (c == 0) return CH_UP;      /* column 0: -1 (:64) */
+        if (i == 0) return CH_LEFT;    /* row 0: +1 (:118) */
+        const unsigned f = get(i, c);
+        return (f & 1u) ? CH_DIAG : ((f & 2u) ? CH_LEFT : CH_UP);
+    }
+};
+
+__global__ void __launch_bounds__(128) traceback(const TraceArgs T)
+{
+    const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= T.n) return;
+    const int L = T.L;
+    const int len = T.lens[a];
+    const long long n = T.n;
+    FlagReader R{T, a, len};
+    int32_t* map = T.map + a;        /* map[c*n]: (row << 1) | is_match, fill_map's mapping (:280-305) */
+    uint8_t* ops = T.ops ? T.ops + a * T.ops_stride : nullptr;
+    int nops = 0;
+
+    int i = len, c = L;
+    while (c > 0) {
+        const int ch = R.choice(i, c);
+        if (ch == CH_DIAG) {
+            map[(long long)c * n] = (i << 1) | 1;
+            if (ops) ops[nops] = 'M';
+            ++nops;
+            --i;
+            --c;
+        } else if (ch == CH_LEFT) {
+            for (;;) {
+                map[(long long)c * n] = ((i + 1) << 1);
+                if (ops) ops[nops] = 'D';
+                ++nops;
+                bool ext = false;
+                if (i > 0) ext = (R.get(i, c) & 4u) && R.choice(i, c - 1) != CH_LEFT;
+                --c;
+                if (!ext || c == 0) break;
+            }
+        } else {
+            for (;;) {
+                if (ops) ops[nops] = 'I';
+                ++nops;
+                const bool ext = (R.get(i, c) & 8u) && R.choice(i - 1, c) != CH_UP;
+                --i;
+                if (!ext || i == 0) break;
+            }
+        }
+    }
+    while (i > 0) {   /* leading read bases, consumed at column 0 (:273-276) */
+        if (ops) ops[nops] = 'I';
+        ++nops;
+        --i;
+    }
+    if (T.nops) T.nops[a] = nops;
+
+    if (!T.start) return;
+    /* querymap::operator() (:307-351) and the guards of src/adaptor_align.cpp:57-68 */
+    const int nrows = len + 1;
+    {
+        const int m1 = map[n], mL = map[(long long)L * n];
+        const int first = (m1 >> 1) - 1;
+        const int second = (mL >> 1) + (mL & 1) - 1;
+        if (first < second) {
+            T.start[a] = first + 1;
+            T.end[a] = second;
+        } else {
+            T.start[a] = 0;
+            T.end[a] = 0;
+        }
+    }
+    for (int s = 0; s < T.nsec; ++s) {
+        const int rs = T.sec_starts[s];
+        int re = T.sec_ends[s];
+        int curstart, curend;
+        if (rs == 0) {
+            curstart = 1;
+        } else {
+            const int m = map[(long long)rs * n];
+            curstart = (m >> 1) + (m & 1);
+        }
+        ++re;
+        if (re == L + 1) {
+            curend = nrows;
+        } else {
+            curend = map[(long long)re * n] >> 1;
+        }
+        T.sec_start[(long long)s * n + a] = curstart;            /* (curstart-1) + 1 */
+        T.sec_width[(long long)s * n + a] = curend - curstart;
+    }
+}
+
+template <int C, bool TRACE, bool ALT>
+const char* launch_wf(const AlignArgs& a, int grid, cudaStream_t st, size_t smem) {
+    auto kern = wf_forward<C, TRACE, ALT>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (grid <= 0) {
+        int dev = 0, sms = 0, per = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, kBlock, smem);
+        if (per < 1) per = 1;
+        grid = sms * per;
+    }
+    /* never more groups than alignments */
+    const long long groups_per_block = (long long)(kBlock / 32) * (32 / a.G);
+    const long long need = (a.n + groups_per_block - 1) / groups_per_block;
+    if (need < grid) grid = (int)(need > 0 ? need : 1);
+    kern<<<grid, kBlock, smem, st>>>(a);
+    return TRACE ? (ALT ? "wf_forward<trace,alt>" : "wf_forward<trace>") : (ALT ? "wf_forward<alt>" : "wf_forward<>");
+}
+
+template <int C>
+const char* dispatch_flags(const AlignArgs& a, bool trace, bool alt, int grid, cudaStream_t st, size_t smem) {
+    if (trace) {
+        return alt ? launch_wf<C, true, true>(a, grid, st, smem) : launch_wf<C, true, false>(a, grid, st, smem);
+    }
+    return alt ? launch_wf<C, false, true>(a, grid, st, smem) : launch_wf<C, false, false>(a, grid, st, smem);
+}
+
+}  // namespace
+
+size_t wavefront_smem_bytes(const AlignArgs& a) {
+    return sizeof(double) * ((size_t)a.L + 1 + 3 * (size_t)a.enc_n) + 2 * (size_t)a.nref * a.L;
+}
+
+int wavefront_block_threads() { return kBlock; }
+
+const char* launch_wavefront(const AlignArgs& a, bool trace, bool has_alt, int grid, cudaStream_t st) {
+    const size_t smem = wavefront_smem_bytes(a);
+    switch (a.C) {
+        case 1: return dispatch_flags<1>(a, trace, has_alt, grid, st, smem);
+        case 2: return dispatch_flags<2>(a, trace, has_alt, grid, st, smem);
+        case 3: return dispatch_flags<3>(a, trace, has_alt, grid, st, smem);
+        case 4: return dispatch_flags<4>(a, trace, has_alt, grid, st, smem);
+        case 5: return dispatch_flags<5>(a, trace, has_alt, grid, st, smem);
+        case 6: return dispatch_flags<6>(a, trace, has_alt, grid, st, smem);
+        case 7: return dispatch_flags<7>(a, trace, has_alt, grid, st, smem);
+        case 8: return dispatch_flags<8>(a, trace, has_alt, grid, st, smem);
+        case 9: return dispatch_flags<9>(a, trace, has_alt, grid, st, smem);
+        case 10: return dispatch_flags<10>(a, trace, has_alt, grid, st, smem);
+        case 11: return dispatch_flags<11>(a, trace, has_alt, grid, st, smem);
+        case 12: return dispatch_flags<12>(a, trace, has_alt, grid, st, smem);
+    }
+    return nullptr;
+}
+
+const char* launch_generic(const AlignArgs& a, bool trace, int grid, cudaStream_t st) {
+    const int block = 128;
+    if (grid <= 0) grid = (int)((a.gthreads + block - 1) / block);
+    generic_forward<<<grid, block, 0, st>>>(a, trace ? 1 : 0);
+    return trace ? "generic_forward<trace>" : "generic_forward<>";
+}
+
+void launch_traceback(const TraceArgs& t, cudaStream_t st) {
+    const int block = 128;
+    const int grid = (int)((t.n + block - 1) / block);
+    if (grid > 0) traceback<<<grid, block, 0, st>>>(t);
+}
+
+void launch_fill_empty(const AlignArgs& a, cudaStream_t st) {
+    const int block = 256;
+    const int grid = (int)((a.n + block - 1) / block);
+    if (grid > 0) fill_empty<<<grid, block, 0, st>>>(a);
+}
+
+}  // namespace sarlacc

@@ -1,0 +1,99 @@
+/* Internal interface between the host driver (api.cpp) and the CUDA kernels (kernels.cu).
+ *
+ * Data layout in HBM (see DESIGN.md "Data layout"):
+ *   rows   uint16[n][stride]   one entry per read base: low byte = quality index min(qual-offset, |enc|-1)
+ *                              (reference clamp: src/reference_align.cpp:218-221), high byte = one-hot base
+ *                              A=1 C=2 G=4 T=8, 0 for anything else (never equal to an ACGT reference base,
+ *                              which is all src/reference_align.cpp:186-187 ever tests).
+ *   lens   int32[n]            min(tolerance, read length) etc.; 0 allowed (handled without a DP).
+ *   flags  4 bits per DP cell  {pd, p5, p1, p2} = {diag strictly best, horiz > vert, E-extend raw, F-extend raw}
+ *                              -- the compact equivalent of the reference's int direction matrix
+ *                              (src/reference_align.cpp:164-174 + the jump lengths of :134-155), see traceback.
+ */
+#ifndef SARLACC_B200_KERNELS_H
+#define SARLACC_B200_KERNELS_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sarlacc {
+
+constexpr int kMaxC = 12;        /* adaptor columns per lane in the wavefront kernel */
+constexpr int kMaxGroup = 32;    /* lanes per alignment */
+constexpr int kMaxFastL = kMaxC * kMaxGroup;
+
+/* Column classes of a reference position (src/reference_align.cpp:184-212). */
+enum ColKind : uint8_t {
+    COL_ACGT = 0,   /* table m=1, match iff obs == ref                       */
+    COL_TWO = 1,    /* M R W S Y K -> mismatch table m=2 (quirk kept, :188-199) */
+    COL_THREE = 2,  /* V H D B     -> match table m=3                        */
+    COL_N = 3       /* N           -> match table m=4                        */
+};
+
+struct AlignArgs {
+    /* reads */
+    const uint16_t* rows;
+    const int32_t* lens;
+    long long n;
+    int stride;
+    /* reference(s): nref strings of length L (nref > 1 only for the fused multi-barcode pass) */
+    int L;
+    int nref;
+    const uint8_t* refmask;   /* [nref][L] one-hot nibble for ACGT columns, 0 otherwise */
+    const uint8_t* refkind;   /* [nref][L] ColKind */
+    /* scoring */
+    int local;                /* 1: local in read / global in reference, last column has free vertical gaps */
+    double gop, ge;           /* gap_open = go + ge, gap_ext = ge (src/reference_align.cpp:8) */
+    const double* row0;       /* [L+1] H[0][c] (row 0 chain of src/reference_align.cpp:116-117) */
+    const double* cost;       /* [5][enc_n]: match1, mismatch1, mismatch2, match3, match4 */
+    int enc_n;
+    int alt_row;              /* which row of `cost` the single non-ACGT class of the reference uses (2..4), wavefront only */
+    /* wavefront geometry */
+    int G, C;
+    /* outputs */
+    double* score;            /* [nref][n] (may be null when nref > 1 and only the reduction is wanted) */
+    int32_t* best_id;         /* [n] multi-reference running best (R/barcodeAlign.R:28-34), nref > 1 only */
+    double* best;
+    double* next_best;
+    /* traceback records */
+    void* flags;
+    long long fstride;        /* per alignment, in flag words (wavefront) or bytes (generic) */
+    /* generic kernel scratch: [maxlen+1][nthreads] doubles each */
+    double* gS;
+    double* gE;
+    uint8_t* gChoice;
+    long long gthreads;
+};
+
+struct TraceArgs {
+    const int32_t* lens;
+    long long n;
+    int L;
+    int layout;               /* 0: wavefront words, 1: generic bytes */
+    int G, C, wordbytes;
+    const void* flags;
+    long long fstride;
+    int nsec;
+    const int32_t* sec_starts;  /* device, 0-based */
+    const int32_t* sec_ends;    /* device, 1-based */
+    int32_t* map;               /* scratch [L+1][n] */
+    int32_t* start;
+    int32_t* end;
+    int32_t* sec_start;         /* [nsec][n] */
+    int32_t* sec_width;
+    uint8_t* ops;               /* optional [n][ops_stride] alignment operations, written back to front */
+    int32_t* nops;
+    long long ops_stride;
+};
+
+/* Launchers (return the kernel's name for reporting; throw nothing, errors via cudaGetLastError). */
+const char* launch_wavefront(const AlignArgs& a, bool trace, bool has_alt, int grid, cudaStream_t st);
+const char* launch_generic(const AlignArgs& a, bool trace, int grid, cudaStream_t st);
+void launch_traceback(const TraceArgs& t, cudaStream_t st);
+void launch_fill_empty(const AlignArgs& a, cudaStream_t st);
+size_t wavefront_smem_bytes(const AlignArgs& a);
+int wavefront_block_threads();
+
+}
+
+#endif

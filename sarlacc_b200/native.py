@@ -1,0 +1,224 @@
+"""Python face of the four `.Call` entry points (and the fused/resident extensions), one function per
+reference symbol, same argument order and meaning:
+
+    cxx_adaptor_align            src/adaptor_align.cpp:11-77     -> adaptor_align
+    cxx_adaptor_align_score_only src/adaptor_align.cpp:79-110    -> adaptor_align_score_only
+    cxx_barcode_align            src/barcode_align.cpp:10-44     -> barcode_align
+    cxx_general_align            src/general_align.cpp:10-62     -> general_align
+
+The scalar/shape checks the reference performs on its SEXP arguments before the read loop
+(src/utils.cpp:5-31, src/adaptor_align.cpp:23-31) are made here with the same messages, because in the
+R integration they live in the glue (sarlacc_b200/csrc/r_glue.cpp), not behind the C ABI.
+"""
+import ctypes as C
+import numbers
+
+import numpy as np
+
+from . import _lib
+from ._lib import SarlaccError, SEQ_ASCII, SEQ_BIOSTRINGS  # noqa: F401
+from .reads import ReadSet
+
+
+def phred_encoding(n=94, offset=33):
+    """What .create_encoding_vector (R/qualityMask.R:19-27) returns for PhredQuality input: names
+    '!'..'~' and error probabilities 10^(-q/10)."""
+    names = [chr(offset + i) for i in range(n)]
+    err = np.array([10.0 ** (-q / 10.0) for q in range(n)], dtype=np.float64)
+    return names, err
+
+
+def _numeric_scalar(x, what):
+    # check_numeric_scalar, src/utils.cpp:18-20
+    if isinstance(x, numbers.Real):
+        return float(x)
+    a = np.asarray(x)
+    if a.size != 1:
+        raise SarlaccError("%s should be a numeric scalar" % what)
+    return float(a.reshape(-1)[0])
+
+
+def _string(x, what):
+    # check_string, src/utils.cpp:26-31
+    if isinstance(x, (str, bytes)):
+        return x if isinstance(x, str) else x.decode("latin-1")
+    x = list(x)
+    if len(x) != 1:
+        raise SarlaccError("%s should be a string" % what)
+    return _string(x[0], what)
+
+
+def _reads_arg(reads, views, seq_encoding):
+    if not isinstance(reads, ReadSet):
+        seqs, quals = reads
+        sp, so = (seqs if isinstance(seqs, tuple) else _pool(seqs))
+        qp, qo = (quals if isinstance(quals, tuple) else _pool(quals))
+        if len(so) != len(qo):
+            raise SarlaccError("sequence and quality vectors should have the same length")
+        return _lib.ReadsArg(sp, so, qp, qo, seq_encoding, views)
+    if not reads.has_quality:
+        raise SarlaccError("sequence and quality vectors should have the same length")
+    return _lib.ReadsArg(reads.seq_pool, reads.seq_off, reads.qual_pool, reads.qual_off, seq_encoding, views)
+
+
+def _pool(strings):
+    rs = ReadSet.from_strings(strings)
+    return rs.seq_pool, rs.seq_off
+
+
+def _encoding_arg(encoding):
+    names, err = encoding
+    return _lib.EncodingArg(names, err)
+
+
+def adaptor_align(reads, encoding, gapopen, gapext, adaptor, sec_starts=(), sec_ends=(), views=False, seq_encoding=SEQ_ASCII):
+    """Returns [score, start, end, [sec_start...], [sec_width...]] like the R list of src/adaptor_align.cpp:71-74.
+    sec_starts are 0-based and sec_ends 1-based (R/adaptorAlign.R:158)."""
+    adaptor = _string(adaptor, "adaptor sequence")
+    go = _numeric_scalar(gapopen, "gap opening penalty")
+    ge = _numeric_scalar(gapext, "gap extension penalty")
+    ra = _reads_arg(reads, views, seq_encoding)
+    ss = np.ascontiguousarray(sec_starts, dtype=np.int32).reshape(-1)
+    se = np.ascontiguousarray(sec_ends, dtype=np.int32).reshape(-1)
+    if len(ss) != len(se):
+        raise SarlaccError("section starts and ends should have the same length")
+    ea = _encoding_arg(encoding)
+    n, nsec = ra.n, len(ss)
+    score = np.zeros(n, np.float64)
+    start = np.zeros(n, np.int32)
+    end = np.zeros(n, np.int32)
+    sst = np.zeros((max(nsec, 1), max(n, 1)), np.int32)
+    swd = np.zeros((max(nsec, 1), max(n, 1)), np.int32)
+    _lib.check(_lib.lib.sarlacc_adaptor_align(
+        ra.ref(), ea.ref(), C.c_double(go), C.c_double(ge), adaptor.encode("latin-1"),
+        C.c_int(nsec), _lib._ptr(ss), _lib._ptr(se),
+        _lib._ptr(score), _lib._ptr(start), _lib._ptr(end), _lib._ptr(sst), _lib._ptr(swd)))
+    return [score, start, end, [sst[i, :n].copy() for i in range(nsec)], [swd[i, :n].copy() for i in range(nsec)]]
+
+
+def _score_call(fn, reads, encoding, gapopen, gapext, reference, what, views, seq_encoding):
+    reference = _string(reference, what)
+    go = _numeric_scalar(gapopen, "gap opening penalty")
+    ge = _numeric_scalar(gapext, "gap extension penalty")
+    ra = _reads_arg(reads, views, seq_encoding)
+    ea = _encoding_arg(encoding)
+    score = np.zeros(ra.n, np.float64)
+    _lib.check(fn(ra.ref(), ea.ref(), C.c_double(go), C.c_double(ge), reference.encode("latin-1"), _lib._ptr(score)))
+    return score
+
+
+def adaptor_align_score_only(reads, encoding, gapopen, gapext, adaptor, views=False, seq_encoding=SEQ_ASCII):
+    return _score_call(_lib.lib.sarlacc_adaptor_align_score_only, reads, encoding, gapopen, gapext, adaptor,
+                       "adaptor sequence", views, seq_encoding)
+
+
+def barcode_align(reads, encoding, gapopen, gapext, reference, views=False, seq_encoding=SEQ_ASCII):
+    return _score_call(_lib.lib.sarlacc_barcode_align, reads, encoding, gapopen, gapext, reference,
+                       "barcode sequence", views, seq_encoding)
+
+
+def general_align(reads, encoding, gapopen, gapext, reference, edit_only=False, views=False, seq_encoding=SEQ_ASCII):
+    """Returns [score, edit distance, reference strings, query strings] (src/general_align.cpp:60)."""
+    reference = _string(reference, "reference sequence")
+    go = _numeric_scalar(gapopen, "gap opening penalty")
+    ge = _numeric_scalar(gapext, "gap extension penalty")
+    ra = _reads_arg(reads, views, seq_encoding)
+    ea = _encoding_arg(encoding)
+    n = ra.n
+    score = np.zeros(n, np.float64)
+    edit = np.zeros(n, np.int32)
+    maxlen = int(np.max(np.diff(ra.seq_off))) if n else 0
+    stride = maxlen + len(reference) + 2
+    ref_aln = np.zeros((max(n, 1), stride), np.uint8)
+    q_aln = np.zeros((max(n, 1), stride), np.uint8)
+    _lib.check(_lib.lib.sarlacc_general_align(
+        ra.ref(), ea.ref(), C.c_double(go), C.c_double(ge), reference.encode("latin-1"), C.c_int(1 if edit_only else 0),
+        _lib._ptr(score), _lib._ptr(edit), _lib._ptr(ref_aln), _lib._ptr(q_aln), C.c_int64(stride)))
+    if edit_only:
+        return [score, edit, [], []]
+    rs = [bytes(ref_aln[i]).split(b"\0", 1)[0].decode("latin-1") for i in range(n)]
+    qs = [bytes(q_aln[i]).split(b"\0", 1)[0].decode("latin-1") for i in range(n)]
+    return [score, edit, rs, qs]
+
+
+def barcode_align_multi(reads, encoding, gapopen, gapext, barcodes, all_scores=False, views=False, seq_encoding=SEQ_ASCII):
+    """All barcodes in one pass (R/barcodeAlign.R:20-35 fused).  Returns best_id (1-based, 0 = NA), best, next_best
+    and, if requested, the [nbarcodes][n] score matrix."""
+    go = _numeric_scalar(gapopen, "gap opening penalty")
+    ge = _numeric_scalar(gapext, "gap extension penalty")
+    ra = _reads_arg(reads, views, seq_encoding)
+    ea = _encoding_arg(encoding)
+    bs = [_string(b, "barcode sequence").encode("latin-1") for b in barcodes]
+    arr = (C.c_char_p * max(len(bs), 1))(*bs)
+    n = ra.n
+    bid = np.zeros(n, np.int32)
+    best = np.zeros(n, np.float64)
+    nxt = np.zeros(n, np.float64)
+    mat = np.zeros((max(len(bs), 1), max(n, 1)), np.float64) if all_scores else None
+    _lib.check(_lib.lib.sarlacc_barcode_align_multi(
+        ra.ref(), ea.ref(), C.c_double(go), C.c_double(ge), arr, C.c_int(len(bs)),
+        _lib._ptr(bid), _lib._ptr(best), _lib._ptr(nxt), _lib._ptr(mat)))
+    if all_scores:
+        return bid, best, nxt, mat[:len(bs), :n]
+    return bid, best, nxt
+
+
+class Resident:
+    """Read windows packed once and kept in HBM (sarlacc_resident_*)."""
+
+    MODE_SCORE_LOCAL, MODE_TRACE_LOCAL, MODE_SCORE_GLOBAL = 0, 1, 2
+
+    def __init__(self, reads, encoding, device=0, views=False, seq_encoding=SEQ_ASCII):
+        ra = _reads_arg(reads, views, seq_encoding)
+        ea = _encoding_arg(encoding)
+        self.handle = _lib.lib.sarlacc_resident_create(ra.ref(), ea.ref(), C.c_int(device))
+        if not self.handle:
+            raise SarlaccError(_lib.last_error())
+        self.n = int(_lib.lib.sarlacc_resident_n(self.handle))
+        self.nsec = 0
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _lib.lib.sarlacc_resident_free(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    def cells(self, rlen):
+        return int(_lib.lib.sarlacc_resident_cells(self.handle, C.c_int(rlen)))
+
+    def nbytes(self):
+        return int(_lib.lib.sarlacc_resident_bytes(self.handle))
+
+    def align(self, mode, gapopen, gapext, reference, sec_starts=(), sec_ends=(), stream=None):
+        ss = np.ascontiguousarray(sec_starts, dtype=np.int32).reshape(-1)
+        se = np.ascontiguousarray(sec_ends, dtype=np.int32).reshape(-1)
+        if len(ss) != len(se):
+            raise SarlaccError("section starts and ends should have the same length")
+        self.nsec = len(ss) if mode == self.MODE_TRACE_LOCAL else 0
+        self.mode = mode
+        _lib.check(_lib.lib.sarlacc_resident_align(
+            self.handle, C.c_int(mode), C.c_double(float(gapopen)), C.c_double(float(gapext)),
+            reference.encode("latin-1"), C.c_int(len(ss)), _lib._ptr(ss), _lib._ptr(se),
+            C.c_void_p(stream) if stream else None))
+
+    def fetch(self, stream=None):
+        n, nsec = self.n, self.nsec
+        score = np.zeros(n, np.float64)
+        trace = self.mode == self.MODE_TRACE_LOCAL
+        start = np.zeros(n, np.int32) if trace else None
+        end = np.zeros(n, np.int32) if trace else None
+        sst = np.zeros((max(nsec, 1), max(n, 1)), np.int32) if trace else None
+        swd = np.zeros((max(nsec, 1), max(n, 1)), np.int32) if trace else None
+        _lib.check(_lib.lib.sarlacc_resident_fetch(
+            self.handle, _lib._ptr(score), _lib._ptr(start), _lib._ptr(end), _lib._ptr(sst), _lib._ptr(swd),
+            C.c_void_p(stream) if stream else None))
+        if not trace:
+            return score
+        return [score, start, end, [sst[i, :n].copy() for i in range(nsec)], [swd[i, :n].copy() for i in range(nsec)]]
+
+    def scores_device_ptr(self):
+        return _lib.lib.sarlacc_resident_scores_device(self.handle)
+
+    def last_kernel(self):
+        return _lib.lib.sarlacc_resident_last_kernel(self.handle).decode()

@@ -1,0 +1,202 @@
+"""ReadSet: the host-side stand-in for Biostrings' QualityScaledDNAStringSet on this path.
+
+A CSR container (byte pools + offsets) with exactly the operations the reference's R drivers apply to
+reads around the hot path: width, subseq, reverseComplement, subsetting, names
+(R/adaptorAlign.R:86-95,104-110,160-174).  Everything is vectorised numpy; nothing here aligns.
+"""
+import gzip
+
+import numpy as np
+
+# Biostrings::reverseComplement on DNA with IUPAC codes
+_COMP = np.arange(256, dtype=np.uint8)
+for _a, _b in ["AT", "CG", "MK", "RY", "VB", "HD", "WW", "SS", "NN"]:
+    _COMP[ord(_a)] = ord(_b)
+    _COMP[ord(_b)] = ord(_a)
+    _COMP[ord(_a.lower())] = ord(_b.lower())
+    _COMP[ord(_b.lower())] = ord(_a.lower())
+
+
+def _csr(strings):
+    bs = [s.encode("latin-1") if isinstance(s, str) else bytes(s) for s in strings]
+    off = np.zeros(len(bs) + 1, dtype=np.int64)
+    if bs:
+        np.cumsum([len(b) for b in bs], out=off[1:])
+    pool = np.frombuffer(b"".join(bs), dtype=np.uint8).copy()
+    return pool, off
+
+
+class ReadSet:
+    """n sequences with per-base qualities (ASCII-encoded, e.g. Phred+33) and optional names."""
+
+    def __init__(self, seq_pool, seq_off, qual_pool=None, qual_off=None, names=None):
+        self.seq_pool = np.ascontiguousarray(seq_pool, dtype=np.uint8)
+        self.seq_off = np.ascontiguousarray(seq_off, dtype=np.int64)
+        self.qual_pool = None if qual_pool is None else np.ascontiguousarray(qual_pool, dtype=np.uint8)
+        self.qual_off = self.seq_off if qual_off is None else np.ascontiguousarray(qual_off, dtype=np.int64)
+        self.names = None if names is None else list(names)
+
+    # -- construction --------------------------------------------------------------------------
+    @classmethod
+    def from_strings(cls, seqs, quals=None, names=None):
+        sp, so = _csr(seqs)
+        if quals is None:
+            return cls(sp, so, None, None, names)
+        qp, qo = _csr(quals)
+        if len(qo) != len(so):
+            raise ValueError("sequence and quality vectors should have the same length")
+        return cls(sp, so, qp, qo, names)
+
+    @classmethod
+    def empty(cls):
+        return cls(np.zeros(0, np.uint8), np.zeros(1, np.int64), np.zeros(0, np.uint8), np.zeros(1, np.int64), [])
+
+    # -- basic accessors -----------------------------------------------------------------------
+    def __len__(self):
+        return len(self.seq_off) - 1
+
+    @property
+    def has_quality(self):
+        return self.qual_pool is not None
+
+    def width(self):
+        return np.diff(self.seq_off).astype(np.int64)
+
+    def seq_strings(self):
+        b = self.seq_pool.tobytes()
+        o = self.seq_off
+        return [b[o[i]:o[i + 1]].decode("latin-1") for i in range(len(self))]
+
+    def qual_strings(self):
+        b = self.qual_pool.tobytes()
+        o = self.qual_off
+        return [b[o[i]:o[i + 1]].decode("latin-1") for i in range(len(self))]
+
+    # -- R-level operations --------------------------------------------------------------------
+    def __getitem__(self, idx):
+        """reads[idx] with an index array or boolean mask."""
+        idx = np.asarray(idx)
+        if idx.dtype == bool:
+            idx = np.nonzero(idx)[0]
+        w = self.width()[idx]
+        starts = np.ones(len(idx), dtype=np.int64)
+        out = self._gather(idx, starts, w)
+        if self.names is not None:
+            out.names = [self.names[i] for i in idx]
+        return out
+
+    def _gather(self, rows, starts, widths):
+        """New ReadSet whose element k is subseq(self[rows[k]], start=starts[k], width=widths[k]) (1-based)."""
+        rows = np.asarray(rows, dtype=np.int64)
+        starts = np.asarray(starts, dtype=np.int64)
+        widths = np.asarray(widths, dtype=np.int64)
+        off = np.zeros(len(rows) + 1, dtype=np.int64)
+        np.cumsum(widths, out=off[1:])
+        total = int(off[-1])
+        src0 = self.seq_off[rows] + starts - 1
+        idx = np.repeat(src0 - off[:-1], widths) + np.arange(total, dtype=np.int64)
+        sp = self.seq_pool[idx]
+        qp = None
+        if self.has_quality:
+            if self.qual_off is self.seq_off:
+                qp = self.qual_pool[idx]
+            else:
+                qsrc0 = self.qual_off[rows] + starts - 1
+                qidx = np.repeat(qsrc0 - off[:-1], widths) + np.arange(total, dtype=np.int64)
+                qp = self.qual_pool[qidx]
+        return ReadSet(sp, off, qp, off if qp is not None else None, None)
+
+    def subseq(self, start=None, end=None, width=None):
+        """XVector::subseq with vector arguments (two of start/end/width)."""
+        w = self.width()
+        n = len(self)
+        if start is not None and width is not None:
+            start = np.broadcast_to(np.asarray(start, dtype=np.int64), (n,))
+            width = np.broadcast_to(np.asarray(width, dtype=np.int64), (n,))
+        elif end is not None and width is not None:
+            end = np.broadcast_to(np.asarray(end, dtype=np.int64), (n,))
+            width = np.broadcast_to(np.asarray(width, dtype=np.int64), (n,))
+            start = end - width + 1
+        elif start is not None and end is not None:
+            start = np.broadcast_to(np.asarray(start, dtype=np.int64), (n,))
+            end = np.broadcast_to(np.asarray(end, dtype=np.int64), (n,))
+            width = end - start + 1
+        else:
+            raise ValueError("two of start, end, width are required")
+        if np.any(start < 1) or np.any(width < 0) or np.any(start + width - 1 > w):
+            raise ValueError("subseq: requested range is out of bounds")
+        out = self._gather(np.arange(n, dtype=np.int64), start, width)
+        out.names = self.names
+        return out
+
+    def reverse_complement(self):
+        """Biostrings::reverseComplement on a QualityScaledDNAStringSet: bases complemented and reversed,
+        qualities reversed with them."""
+        n = len(self)
+        w = self.width()
+        total = int(self.seq_off[-1] - self.seq_off[0])
+        # position p of element k maps to off[k] + off[k+1] - 1 - p
+        base = np.repeat(self.seq_off[:-1] + self.seq_off[1:] - 1, w)
+        idx = base - (np.arange(total, dtype=np.int64) + self.seq_off[0])
+        sp = _COMP[self.seq_pool[idx]]
+        off = self.seq_off - self.seq_off[0]
+        qp = None
+        qo = None
+        if self.has_quality:
+            if self.qual_off is self.seq_off or np.array_equal(self.qual_off, self.seq_off):
+                qp = self.qual_pool[idx]
+            else:
+                qw = np.diff(self.qual_off)
+                qbase = np.repeat(self.qual_off[:-1] + self.qual_off[1:] - 1, qw)
+                qidx = qbase - (np.arange(int(qw.sum()), dtype=np.int64) + self.qual_off[0])
+                qp = self.qual_pool[qidx]
+            qo = off
+        return ReadSet(sp, off, qp, qo, self.names)
+
+    @staticmethod
+    def concat(sets):
+        sets = list(sets)
+        if not sets:
+            return ReadSet.empty()
+        sp = np.concatenate([s.seq_pool[s.seq_off[0]:s.seq_off[-1]] for s in sets])
+        so = np.zeros(sum(len(s) for s in sets) + 1, dtype=np.int64)
+        np.cumsum(np.concatenate([s.width() for s in sets]), out=so[1:])
+        qp = None
+        if all(s.has_quality for s in sets):
+            qp = np.concatenate([s.qual_pool[s.qual_off[0]:s.qual_off[-1]] for s in sets])
+        names = None
+        if all(s.names is not None for s in sets):
+            names = [x for s in sets for x in s.names]
+        return ReadSet(sp, so, qp, so if qp is not None else None, names)
+
+
+def read_fastq(path, number=None, skip=0):
+    """Minimal 4-line FASTQ reader standing in for ShortRead::FastqStreamer + .FASTQ2QSDS
+    (R/adaptorAlign.R:26,36,104-110).  Yields ReadSets of at most `number` reads."""
+    opener = gzip.open if str(path).endswith(".gz") else open
+    with opener(path, "rb") as fh:
+        names, seqs, quals = [], [], []
+        while True:
+            h = fh.readline()
+            if not h:
+                break
+            s = fh.readline().rstrip(b"\r\n")
+            fh.readline()
+            q = fh.readline().rstrip(b"\r\n")
+            names.append(h.rstrip(b"\r\n")[1:].decode("latin-1"))
+            seqs.append(s)
+            quals.append(q)
+            if number is not None and len(seqs) >= number:
+                yield ReadSet.from_strings(seqs, quals, names)
+                names, seqs, quals = [], [], []
+        if seqs:
+            yield ReadSet.from_strings(seqs, quals, names)
+
+
+def write_fastq(path, reads, append=False):
+    s = reads.seq_strings()
+    q = reads.qual_strings()
+    names = reads.names if reads.names is not None else ["READ_%d" % (i + 1) for i in range(len(reads))]
+    with open(path, "ab" if append else "wb") as fh:
+        for i in range(len(reads)):
+            fh.write(("@%s\n%s\n+\n%s\n" % (names[i], s[i], q[i])).encode("latin-1"))
