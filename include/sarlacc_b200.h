@@ -141,6 +141,11 @@ int sarlacc_resident_fetch(sarlacc_resident* r, double* score, int32_t* start, i
 const double* sarlacc_resident_scores_device(const sarlacc_resident* r);
 /* Name of the forward kernel variant the last sarlacc_resident_align used (for reports), e.g. "wf<C=9,G=8,trace>". */
 const char* sarlacc_resident_last_kernel(const sarlacc_resident* r);
+/* Roofline accounting: when enabled, every forward-kernel launch of sarlacc_resident_align is bracketed by CUDA
+ * events on the launching stream; sarlacc_resident_forward_ms() then returns the summed device time of the
+ * last run's forward launches (synchronises on them). */
+void   sarlacc_resident_set_timing(sarlacc_resident* r, int on);
+double sarlacc_resident_forward_ms(sarlacc_resident* r);
 
 #ifdef __cplusplus
 }

@@ -47,6 +47,7 @@ EXPORTS = [
     "sarlacc_resident_create", "sarlacc_resident_free", "sarlacc_resident_n", "sarlacc_resident_cells",
     "sarlacc_resident_bytes", "sarlacc_resident_align", "sarlacc_resident_fetch",
     "sarlacc_resident_scores_device", "sarlacc_resident_last_kernel",
+    "sarlacc_resident_set_timing", "sarlacc_resident_forward_ms",
 ]
 
 
@@ -73,6 +74,10 @@ def _load():
     lib.sarlacc_resident_scores_device.argtypes = [C.c_void_p]
     lib.sarlacc_resident_last_kernel.restype = C.c_char_p
     lib.sarlacc_resident_last_kernel.argtypes = [C.c_void_p]
+    lib.sarlacc_resident_set_timing.argtypes = [C.c_void_p, C.c_int]
+    lib.sarlacc_resident_set_timing.restype = None
+    lib.sarlacc_resident_forward_ms.argtypes = [C.c_void_p]
+    lib.sarlacc_resident_forward_ms.restype = C.c_double
     lib.sarlacc_resident_align.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_char_p,
                                            C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.sarlacc_resident_fetch.argtypes = [C.c_void_p] + [C.c_void_p] * 6

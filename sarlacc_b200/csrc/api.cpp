@@ -479,10 +479,45 @@ long long sub_chunk(const Plan& P, int maxlen, bool trace, long long n) {
 
 const char* g_last_kernel = "";
 
+/* Optional CUDA-event bracket around the forward kernel launches of one run (roofline accounting). */
+struct FwdTimer {
+    std::vector<cudaEvent_t> ev;   /* pairs */
+    size_t used = 0;
+    void begin(cudaStream_t st) {
+        if (used + 2 > ev.size()) {
+            cudaEvent_t a, b;
+            CUDA_CHECK(cudaEventCreate(&a));
+            CUDA_CHECK(cudaEventCreate(&b));
+            ev.push_back(a);
+            ev.push_back(b);
+        }
+        CUDA_CHECK(cudaEventRecord(ev[used], st));
+    }
+    void end(cudaStream_t st) {
+        CUDA_CHECK(cudaEventRecord(ev[used + 1], st));
+        used += 2;
+    }
+    double total_ms() {
+        double t = 0;
+        for (size_t i = 0; i + 1 < used; i += 2) {
+            CUDA_CHECK(cudaEventSynchronize(ev[i + 1]));
+            float ms = 0;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+            t += ms;
+        }
+        return t;
+    }
+    void release() {
+        for (auto e : ev) cudaEventDestroy(e);
+        ev.clear();
+        used = 0;
+    }
+};
+
 /* Enqueue forward (+ traceback) for device-resident packed reads [0,n).  Sub-chunks by scratch budget. */
 const char* run_device(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t st,
         const uint16_t* d_rows, const int32_t* d_lens, long long n, int stride, int maxlen,
-        bool trace, const Outputs& out, int sms)
+        bool trace, const Outputs& out, int sms, FwdTimer* timer = nullptr)
 {
     const char* name = "";
     if (n == 0) return name;
@@ -532,6 +567,7 @@ const char* run_device(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t
             A.flags = S.flags.p;
             S.map.reserve(sizeof(int32_t) * ((size_t)P.L + 1) * m);
         }
+        if (timer) timer->begin(st);
         if (P.fast) {
             name = launch_wavefront(A, trace, P.has_alt, 0, st);
         } else {
@@ -546,6 +582,7 @@ const char* run_device(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t
             A.gChoice = S.gC.as<uint8_t>();
             name = launch_generic(A, trace, 0, st);
         }
+        if (timer) timer->end(st);
         launch_fill_empty(A, st);
         g_launches += 2;
         if (trace) {
@@ -1119,8 +1156,15 @@ struct sarlacc_resident {
     cudaStream_t own_stream = nullptr;
     DevBuf d_rows, d_lens, d_out;
     Scratch scratch;
-    DevPlan dplan;
-    Plan plan;
+    /* plans (host tables + their device copy) are cached per (reference, penalties, mode, sections) so that the
+     * steady state of adaptorAlign -> getAdaptorThresholds style re-use enqueues kernels only */
+    struct CachedPlan {
+        std::string key;
+        Plan plan;
+        DevPlan d;
+    };
+    std::vector<std::unique_ptr<CachedPlan> > plans;
+    CachedPlan* cur = nullptr;
     OutLayout lay;
     int nsec = 0;
     Mode mode = MODE_SCORE_LOCAL;
@@ -1128,6 +1172,8 @@ struct sarlacc_resident {
     int sms = 0;
     std::string last_kernel;
     std::vector<int32_t> h_lens;
+    FwdTimer timer;
+    bool timing = false;
 };
 
 sarlacc_resident* sarlacc_resident_create(const sarlacc_reads* reads, const sarlacc_encoding* encoding, int device) {
@@ -1200,7 +1246,9 @@ void sarlacc_resident_free(sarlacc_resident* r) {
     r->d_lens.release();
     r->d_out.release();
     r->scratch.release();
-    r->dplan.buf.release();
+    for (auto& p : r->plans) p->d.buf.release();
+    r->plans.clear();
+    r->timer.release();
     if (r->own_stream) cudaStreamDestroy(r->own_stream);
     delete r;
 }
@@ -1227,28 +1275,54 @@ int sarlacc_resident_align(sarlacc_resident* r, int mode, double gapopen, double
     try {
         CUDA_CHECK(cudaSetDevice(r->device));
         cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : r->own_stream;
-        const char* refs[1] = {reference};
-        build_plan(r->plan, r->enc, refs, 1, L, local, gapopen, gapext);
-        if (r->plan.bad_col[0] >= 0 && r->total_len > 0) return fail(err_text(ERR_REF));
-        r->plan.sec_starts.clear();
-        r->plan.sec_ends.clear();
-        if (trace && nsec > 0) {
-            r->plan.sec_starts.assign(sec_starts, sec_starts + nsec);
-            r->plan.sec_ends.assign(sec_ends, sec_ends + nsec);
-            for (int s = 0; s < nsec; ++s) {
-                if (sec_starts[s] < 0 || sec_starts[s] > L || sec_ends[s] < 0 || sec_ends[s] > L) return fail("section bounds outside the adaptor");
-            }
+        std::string key(reference);
+        key += '|';
+        key.append(reinterpret_cast<const char*>(&gapopen), sizeof(double));
+        key.append(reinterpret_cast<const char*>(&gapext), sizeof(double));
+        key += local ? 'L' : 'G';
+        if (trace) {
+            if (nsec < 0 || (nsec > 0 && (!sec_starts || !sec_ends))) return fail("section starts and ends should have the same length");
+            key.append(reinterpret_cast<const char*>(sec_starts), sizeof(int32_t) * nsec);
+            key += '|';
+            key.append(reinterpret_cast<const char*>(sec_ends), sizeof(int32_t) * nsec);
         }
+        sarlacc_resident::CachedPlan* cp = nullptr;
+        for (auto& p : r->plans) {
+            if (p->key == key) { cp = p.get(); break; }
+        }
+        if (!cp) {
+            if (r->plans.size() >= 64) {   /* bounded: drop everything once the device is idle */
+                CUDA_CHECK(cudaStreamSynchronize(st));
+                for (auto& p : r->plans) p->d.buf.release();
+                r->plans.clear();
+            }
+            std::unique_ptr<sarlacc_resident::CachedPlan> np(new sarlacc_resident::CachedPlan());
+            np->key = key;
+            const char* refs[1] = {reference};
+            build_plan(np->plan, r->enc, refs, 1, L, local, gapopen, gapext);
+            if (trace && nsec > 0) {
+                np->plan.sec_starts.assign(sec_starts, sec_starts + nsec);
+                np->plan.sec_ends.assign(sec_ends, sec_ends + nsec);
+                for (int s = 0; s < nsec; ++s) {
+                    if (sec_starts[s] < 0 || sec_starts[s] > L || sec_ends[s] < 0 || sec_ends[s] > L) return fail("section bounds outside the adaptor");
+                }
+            }
+            np->d.upload(np->plan, st);
+            cp = np.get();
+            r->plans.push_back(std::move(np));
+        }
+        if (cp->plan.bad_col[0] >= 0 && r->total_len > 0) return fail(err_text(ERR_REF));
+        r->cur = cp;
         r->nsec = trace ? nsec : 0;
         r->mode = md;
-        r->dplan.upload(r->plan, st);
         r->lay = make_layout(md, std::max<int64_t>(r->n, 1), 1, r->nsec, r->maxlen, L);
         r->d_out.reserve(r->lay.total);
         uint8_t* d = r->d_out.as<uint8_t>();
         /* Sub-chunks (scratch budget) write straight into the full-size output block: sections are laid out
          * [nsec][n] so each sub-chunk gets its own launch set with per-section base pointers. */
-        const long long cn = sub_chunk(r->plan, r->maxlen, trace, std::max<int64_t>(r->n, 1));
+        const long long cn = sub_chunk(cp->plan, r->maxlen, trace, std::max<int64_t>(r->n, 1));
         const char* name = "";
+        r->timer.used = 0;
         for (long long off = 0; off < r->n; off += cn) {
             const long long m = std::min<long long>(cn, r->n - off);
             Outputs dev;
@@ -1261,10 +1335,11 @@ int sarlacc_resident_align(sarlacc_resident* r, int mode, double gapopen, double
                 dev.sec_start = reinterpret_cast<int32_t*>(d + r->lay.o_ss) + (cn >= r->n ? 0 : off * (long long)std::max(1, r->nsec));
                 dev.sec_width = reinterpret_cast<int32_t*>(d + r->lay.o_sw) + (cn >= r->n ? 0 : off * (long long)std::max(1, r->nsec));
             }
-            name = run_device(r->plan, r->dplan, r->scratch, st, r->d_rows.as<uint16_t>() + (size_t)off * r->stride,
-                              r->d_lens.as<int32_t>() + off, m, r->stride, r->maxlen, trace, dev, r->sms);
+            name = run_device(cp->plan, cp->d, r->scratch, st, r->d_rows.as<uint16_t>() + (size_t)off * r->stride,
+                              r->d_lens.as<int32_t>() + off, m, r->stride, r->maxlen, trace, dev, r->sms,
+                              r->timing ? &r->timer : nullptr);
         }
-        r->last_kernel = std::string(name) + " G=" + std::to_string(r->plan.G) + " C=" + std::to_string(r->plan.C);
+        r->last_kernel = std::string(name) + " G=" + std::to_string(cp->plan.G) + " C=" + std::to_string(cp->plan.C);
         r->has_result = true;
     } catch (CudaError& e) {
         return fail(e.msg);
@@ -1287,7 +1362,7 @@ int sarlacc_resident_fetch(sarlacc_resident* r, double* score, int32_t* start, i
         if (r->mode == MODE_TRACE_LOCAL) {
             if (start) CUDA_CHECK(cudaMemcpyAsync(start, d + r->lay.o_start, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
             if (end) CUDA_CHECK(cudaMemcpyAsync(end, d + r->lay.o_end, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-            const long long cn = sub_chunk(r->plan, r->maxlen, true, (long long)n);
+            const long long cn = sub_chunk(r->cur->plan, r->maxlen, true, (long long)n);
             if (r->nsec > 0 && (sec_start || sec_width)) {
                 if (cn >= (long long)n) {
                     if (sec_start) CUDA_CHECK(cudaMemcpyAsync(sec_start, d + r->lay.o_ss, sizeof(int32_t) * n * r->nsec, cudaMemcpyDeviceToHost, st));
@@ -1318,5 +1393,20 @@ const double* sarlacc_resident_scores_device(const sarlacc_resident* r) {
 }
 
 const char* sarlacc_resident_last_kernel(const sarlacc_resident* r) { return r ? r->last_kernel.c_str() : ""; }
+
+void sarlacc_resident_set_timing(sarlacc_resident* r, int on) {
+    if (r) r->timing = on != 0;
+}
+
+double sarlacc_resident_forward_ms(sarlacc_resident* r) {
+    if (!r) return -1.0;
+    try {
+        CUDA_CHECK(cudaSetDevice(r->device));
+        return r->timer.total_ms();
+    } catch (CudaError& e) {
+        fail(e.msg);
+        return -1.0;
+    }
+}
 
 }  // extern "C"

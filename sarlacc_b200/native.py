@@ -217,6 +217,12 @@ class Resident:
             return score
         return [score, start, end, [sst[i, :n].copy() for i in range(nsec)], [swd[i, :n].copy() for i in range(nsec)]]
 
+    def set_timing(self, on=True):
+        _lib.lib.sarlacc_resident_set_timing(self.handle, C.c_int(1 if on else 0))
+
+    def forward_ms(self):
+        return float(_lib.lib.sarlacc_resident_forward_ms(self.handle))
+
     def scores_device_ptr(self):
         return _lib.lib.sarlacc_resident_scores_device(self.handle)
 
