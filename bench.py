@@ -205,7 +205,11 @@ def main():
     dev = local_rank
     rf = native.Resident(front, enc, device=dev)
     rb = native.Resident(back, enc, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated (non-null) stream: the library launches on it, and the timing events are recorded on it
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream, "need a non-null stream handle"
     T = native.Resident.MODE_TRACE_LOCAL
 
     def step(timing=False):
