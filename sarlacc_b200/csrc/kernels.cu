@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
     const double gop = A.gop, ge = A.ge, ngop = -A.gop, nge = -A.ge;
     const int local = A.local;
     const double NEG = neg_inf();
+    const bool first_lane = (j == 0);
 
     /* Per-slot constants.  one[k] = 0 only for the last reference column in local mode, where vertical
      * gaps are free (src/reference_align.cpp:120-121): fma(-gop, 0, x) == x - 0 == x exactly. */
@@ -128,16 +129,88 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
     int i = 0, len = 0, delay = j;
     bool done = false;
     const uint16_t* rowp = A.rows;
+    WT* flagp = reinterpret_cast<WT*>(A.flags);
     double best = NEG, nextb = NEG;
     int bid = 0;
 
+    /* One DP row of this lane's C columns.  `live` gates the only side effect (the trace store). */
+    auto row_step = [&](double Sl, double El, bool live) {
+        const unsigned rw = rowp[i - 1];
+        const unsigned q = rw & 0xffu;
+        const unsigned obsrep = (rw >> 8) * 0x11111111u;
+        const double mq = costs[q], xq = costs[encn + q];
+        double aq = 0.0;
+        if (ALT) aq = costs[2 * encn + q];
+        if (first_lane) {   /* column 0: src/reference_align.cpp:64-78 */
+            Sl = col0_value(local, gop, ge, i);
+            El = NEG;
+        }
+        uint32_t flo = 0, fhi = 0;
+        /* Phase 1 (independent of this row's left-to-right chain): for every owned column the vertical
+         * candidate v = max(F[i-1][c]-ve, H[i-1][c]-vo) (:145-155; free in the last local column) and the
+         * (mis)match candidate m = H[i-1][c-1] + cost (:159, :184-225).  F is updated in place, m kept. */
+        double m[C];
+        {
+            double diag = diag0;
+#pragma unroll
+            for (int k = 0; k < C; ++k) {
+                const double vO = __fma_rn(ngop, one[k], S[k]);
+                const double Fe = __fma_rn(nge, one[k], F[k]);
+                const bool p2 = Fe > vO;
+                F[k] = p2 ? Fe : vO;
+                const bool pm = (obsrep & refpack[k >> 3] & (0xFu << (4 * (k & 7)))) != 0;
+                double cost = pm ? mq : xq;
+                if (ALT) cost = (altmask & (1u << k)) ? aq : cost;
+                m[k] = __dadd_rn(diag, cost);
+                diag = S[k];
+                if (TRACE) {
+                    uint32_t& f = (k < 8) ? flo : fhi;
+                    if (p2) f |= 8u << (4 * (k & 7));
+                }
+            }
+        }
+        diag0 = Sl;
+        /* Phase 2 (the serial chain along the row): horizontal candidate h = max(E[i][c-1]-ge, H[i][c-1]-go')
+         * (:129-140; when the left cell itself chose "left", H == E bitwise and go' >= ge makes the max the
+         * reference's value), then the choice (:164-174): diag only if strictly best, horizontal only if
+         * strictly greater than vertical. */
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const double hO = __dsub_rn(Sl, gop);
+            const double Ee = __dsub_rn(El, ge);
+            const bool p1 = Ee > hO;
+            const double h = p1 ? Ee : hO;
+            const double v = F[k];
+            const bool p5 = h > v;
+            const double t = p5 ? h : v;
+            const bool pd = m[k] > t;
+            const double Sn = pd ? m[k] : t;
+            S[k] = Sn;
+            Sl = Sn;
+            El = h;
+            if (TRACE) {
+                uint32_t& f = (k < 8) ? flo : fhi;
+                const int sh = 4 * (k & 7);
+                if (pd) f |= 1u << sh;
+                if (p5) f |= 2u << sh;
+                if (p1) f |= 4u << sh;
+            }
+        }
+        outS = Sl;
+        outE = El;
+        if (TRACE) {
+            if (live) {
+                WT w;
+                if (sizeof(WT) == 4) w = (WT)flo; else w = (WT)(((unsigned long long)fhi << 32) | flo);
+                flagp[(long long)(i + j) * G + j] = w;
+            }
+        }
+    };
+
     while (__any_sync(FULL, !done)) {
-        /* Left boundary for the row this lane is about to process: what lane j-1 produced one step ago. */
-        double Sl = __shfl_up_sync(FULL, outS, 1, G);
-        double El = __shfl_up_sync(FULL, outE, 1, G);
+        /* ---- bookkeeping (no DP work): pipeline start-up and switches to the next chained alignment ---- */
         bool act = !done;
         if (delay > 0) { --delay; act = false; }
-
         if (act && i == len) {
             /* next (alignment, reference) item of this group's chain */
             ++b;
@@ -152,6 +225,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
             } else {
                 i = 0;
                 rowp = A.rows + a * (long long)A.stride;
+                if (TRACE) flagp = reinterpret_cast<WT*>(A.flags) + a * A.fstride;
 #pragma unroll
                 for (int k = 0; k < C; ++k) {
                     S[k] = (c0 + k + 1 <= L) ? row0s[c0 + k + 1] : 0.0;   /* H[0][c] */
@@ -165,69 +239,39 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
             }
         }
 
-        if (act) {
-            ++i;
-            const unsigned rw = rowp[i - 1];
-            const unsigned q = rw & 0xffu;
-            const unsigned obsrep = (rw >> 8) * 0x11111111u;
-            const double mq = costs[q], xq = costs[encn + q];
-            double aq = 0.0;
-            if (ALT) aq = costs[2 * encn + q];
+        /* ---- DP rows: as many as every lane of the warp can take before its next event.  An active lane's
+         * next event is the end of its alignment; a lane still in start-up needs bookkeeping again after one
+         * step; finished lanes do not constrain (they idle on a valid row with the trace store gated off). */
+        int room;
+        if (act) room = len - i;
+        else room = done ? 0x7fffffff : 1;
+        const int steps = __reduce_min_sync(FULL, room);
+        if (steps == 0x7fffffff) break;
+        const int inc = act ? 1 : 0;
+        const uint16_t* keep_rowp = rowp;
+        const int keep_i = i;
+        if (!act) { rowp = A.rows; i = 1; }
+#pragma unroll 1
+        for (int s = 0; s < steps; ++s) {
+            /* Left boundary of this row: what lane j-1 produced one step ago. */
+            const double Sl = __shfl_up_sync(FULL, outS, 1, G);
+            const double El = __shfl_up_sync(FULL, outE, 1, G);
+            i += inc;
+            row_step(Sl, El, act);
+        }
+        if (!act) { rowp = keep_rowp; i = keep_i; }
 
-            if (j == 0) {   /* column 0: src/reference_align.cpp:64-78 */
-                Sl = col0_value(local, gop, ge, i);
-                El = NEG;
-            }
-            double diag = diag0;
-            diag0 = Sl;
-            WT fl = 0;
+        if (act && i == len && j == jl) {
+            double s = S[0];
 #pragma unroll
-            for (int k = 0; k < C; ++k) {
-                /* horizontal: open from H[i][c-1] vs extend E[i][c-1] (:129-140).  When the left cell itself
-                 * chose "left", H == E bitwise and go' >= ge makes max(Ee,hO) the reference's value. */
-                const double hO = __dsub_rn(Sl, gop);
-                const double Ee = __dsub_rn(El, ge);
-                const bool p1 = Ee > hO;
-                const double h = p1 ? Ee : hO;
-                /* vertical: open from H[i-1][c] vs extend F[i-1][c] (:145-155); free in the last local column */
-                const double vO = __fma_rn(ngop, one[k], S[k]);
-                const double Fe = __fma_rn(nge, one[k], F[k]);
-                const bool p2 = Fe > vO;
-                const double v = p2 ? Fe : vO;
-                /* (mis)match (:159, :184-225) */
-                const bool pm = (obsrep & refpack[k >> 3] & (0xFu << (4 * (k & 7)))) != 0;
-                double cost = pm ? mq : xq;
-                if (ALT) cost = ((altmask >> k) & 1u) ? aq : cost;
-                const double m = __dadd_rn(diag, cost);
-                diag = S[k];
-                /* choice (:164-174): diag only if strictly best, horizontal only if strictly > vertical */
-                const bool p5 = h > v;
-                const double t = p5 ? h : v;
-                const bool pd = m > t;
-                const double Sn = pd ? m : t;
-                S[k] = Sn;
-                F[k] = v;
-                Sl = Sn;
-                El = h;
-                if (TRACE) fl |= (WT)((pd ? 1u : 0u) | (p5 ? 2u : 0u) | (p1 ? 4u : 0u) | (p2 ? 8u : 0u)) << (4 * k);
-            }
-            outS = Sl;
-            outE = El;
-            if (TRACE) {
-                reinterpret_cast<WT*>(A.flags)[a * A.fstride + (long long)(i + j) * G + j] = fl;
-            }
-            if (i == len && j == jl) {
-                double s = S[0];
-#pragma unroll
-                for (int k = 1; k < C; ++k) s = (k == kl) ? S[k] : s;
-                if (A.score) A.score[(long long)b * A.n + a] = s;
-                if (nref > 1) {
-                    update_best(s, b + 1, best, nextb, bid);
-                    if (b == nref - 1 && A.best_id) {
-                        A.best_id[a] = bid;
-                        A.best[a] = best;
-                        A.next_best[a] = nextb;
-                    }
+            for (int k = 1; k < C; ++k) s = (k == kl) ? S[k] : s;
+            if (A.score) A.score[(long long)b * A.n + a] = s;
+            if (nref > 1) {
+                update_best(s, b + 1, best, nextb, bid);
+                if (b == nref - 1 && A.best_id) {
+                    A.best_id[a] = bid;
+                    A.best[a] = best;
+                    A.next_best[a] = nextb;
                 }
             }
         }
