@@ -147,6 +147,7 @@ struct Plan {
     bool fast = false;
     bool has_alt = false;
     int alt_row = 4;
+    int kinds = 1;
     int G = 1, C = 1;
     std::vector<int32_t> sec_starts, sec_ends;
 };
@@ -156,7 +157,7 @@ void choose_geometry(Plan& P) {
     if (force) {
         int g = 0, c = 0;
         if (std::sscanf(force, "%d,%d", &g, &c) == 2 && g >= 1 && g <= 32 && (g & (g - 1)) == 0 && c >= 1 && c <= kMaxC &&
-            g * c >= P.L) {
+            g * c >= P.L && g * c - P.L < g) {   /* at most one dummy slot per lane */
             P.G = g;
             P.C = c;
             return;
@@ -206,10 +207,11 @@ void build_plan(Plan& P, const Encoding& enc, const char* const* refs, int nref,
     const int nalt = (int)kinds[COL_TWO] + (int)kinds[COL_THREE] + (int)kinds[COL_N];
     P.has_alt = nalt > 0;
     P.alt_row = kinds[COL_TWO] ? 2 : (kinds[COL_THREE] ? 3 : 4);
+    P.kinds = (kinds[COL_ACGT] ? 1 : 0) | (kinds[COL_TWO] ? 2 : 0) | (kinds[COL_THREE] ? 4 : 0) | (kinds[COL_N] ? 8 : 0);
     const bool finite = std::isfinite(go) && std::isfinite(ge);
     /* The wavefront kernel folds "left/up neighbour already chose a gap" into a max(), which needs
      * gap_open >= gap_ext, i.e. go >= 0 (see kernels.cu).  Anything else takes the literal kernel. */
-    P.fast = L >= 1 && L <= kMaxFastL && nalt <= 1 && finite && go >= 0.0 && enc.n <= 256 &&
+    P.fast = L >= 1 && L <= kMaxFastL && finite && go >= 0.0 && enc.n <= 256 &&
              std::getenv("SARLACC_FORCE_GENERIC") == nullptr;
     if (P.fast) choose_geometry(P);
 }
@@ -540,7 +542,7 @@ const char* run_device(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t
         A.row0 = D.row0;
         A.cost = D.cost;
         A.enc_n = P.enc->n;
-        A.alt_row = P.alt_row;
+        A.kinds = P.kinds;
         A.G = P.G;
         A.C = P.C;
         /* [nref][n] outputs of a sub-chunk cannot be expressed with one base pointer unless n == m or nref == 1 */

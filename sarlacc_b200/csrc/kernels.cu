@@ -60,23 +60,42 @@ __device__ __forceinline__ void update_best(double s, int id, double& best, doub
     }
 }
 
-template <int C, bool TRACE, bool ALT>
+/* Column layout of the wavefront kernel.  G lanes x C slots >= L columns; the pad = G*C - L (< G) surplus
+ * slots are slot 0 of lanes 0..pad-1 ("dummy" slots that pass their left boundary through), so that the last
+ * reference column always sits in slot C-1 of lane G-1: the one column with special vertical penalties
+ * (src/reference_align.cpp:120-121) then needs per-lane, not per-slot, constants. */
+__host__ __device__ __forceinline__ int wf_first_col(int j, int C, int pad) {   /* 1-based DP column of lane j's first real slot */
+    return j * C - (j < pad ? j : pad) + 1;
+}
+
+__host__ __device__ __forceinline__ void wf_locate(int c, int C, int pad, int* j, int* k) {   /* DP column -> (lane, slot) */
+    const int short_cols = pad * (C - 1);
+    if (c <= short_cols) {
+        *j = (c - 1) / (C - 1);
+        *k = (c - 1) % (C - 1) + 1;
+    } else {
+        const int c2 = c - short_cols - 1;
+        *j = pad + c2 / C;
+        *k = c2 % C;
+    }
+}
+
+constexpr int kCostEntries = 7;   /* A, C, G, T, two-fold code, three-fold code, N */
+
+template <int C, bool TRACE>
 __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(const __grid_constant__ AlignArgs A)
 {
     using WT = typename FlagWord<C>::type;
     extern __shared__ double smem_d[];
     const int L = A.L, nref = A.nref, encn = A.enc_n;
-    double* row0s = smem_d;                 /* [L+1]            */
-    double* costs = row0s + (L + 1);        /* [3][encn]: match1, mismatch1, alt */
-    uint8_t* refm = reinterpret_cast<uint8_t*>(costs + 3 * encn);   /* [nref][L] */
-    uint8_t* refk = refm + (size_t)nref * L;                        /* [nref][L] */
+    double* row0s = smem_d;                                   /* [L+1]                         */
+    double* costs = row0s + (L + 1);                          /* [5][encn], layout of AlignArgs::cost */
+    double* lanetab = costs + 5 * encn;                       /* [warps][kCostEntries][32] lane-private cost entries */
+    uint8_t* refm = reinterpret_cast<uint8_t*>(lanetab + (kBlock / 32) * kCostEntries * 32);   /* [nref][L] */
+    uint8_t* refk = refm + (size_t)nref * L;                                                    /* [nref][L] */
 
     for (int x = threadIdx.x; x <= L; x += blockDim.x) row0s[x] = A.row0[x];
-    for (int x = threadIdx.x; x < encn; x += blockDim.x) {
-        costs[x] = A.cost[x];
-        costs[encn + x] = A.cost[encn + x];
-        costs[2 * encn + x] = ALT ? A.cost[(size_t)A.alt_row * encn + x] : 0.0;
-    }
+    for (int x = threadIdx.x; x < 5 * encn; x += blockDim.x) costs[x] = A.cost[x];
     for (int x = threadIdx.x; x < nref * L; x += blockDim.x) {
         refm[x] = A.refmask[x];
         refk[x] = A.refkind[x];
@@ -90,32 +109,35 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
     const long long warp_global = (long long)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
     const long long gidx = warp_global * gpw + lane / G;
     const long long NG = (long long)gridDim.x * (kBlock / 32) * gpw;
-    const int c0 = j * C;                       /* this lane owns DP columns c0+1 .. c0+C */
-    const int jl = (L - 1) / C, kl = (L - 1) % C;   /* owner of the last column */
-    const double gop = A.gop, ge = A.ge, ngop = -A.gop, nge = -A.ge;
+    const int pad = G * C - L;
+    const bool skip0 = j < pad;                     /* slot 0 of this lane is a dummy */
+    const int cfirst = wf_first_col(j, C, pad);     /* DP column of the first real slot */
+    const double gop = A.gop, ge = A.ge;
     const int local = A.local;
+    const int kinds = A.kinds;
     const double NEG = neg_inf();
     const bool first_lane = (j == 0);
+    /* vertical penalties of slot C-1: zero for the last reference column in local mode (:120-121) */
+    const double vo_last = (local && j == G - 1) ? 0.0 : gop;
+    const double ve_last = (local && j == G - 1) ? 0.0 : ge;
 
-    /* Per-slot constants.  one[k] = 0 only for the last reference column in local mode, where vertical
-     * gaps are free (src/reference_align.cpp:120-121): fma(-gop, 0, x) == x - 0 == x exactly. */
-    double one[C];
-    uint32_t refpack[(C + 7) / 8];
-    uint32_t altmask = 0;
-#pragma unroll
-    for (int k = 0; k < C; ++k) one[k] = (local && c0 + k == L - 1) ? 0.0 : 1.0;
-
+    /* This lane's private table of the current row's possible costs: entry e at mytab[e*32].  Slot k reads
+     * the entry of its reference base: ACGT -> (obs == base ? match1 : mismatch1)[q], IUPAC classes ->
+     * mismatch2 / match3 / match4 [q] regardless of obs (src/reference_align.cpp:184-212). */
+    double* mytab = lanetab + (threadIdx.x >> 5) * kCostEntries * 32 + lane;
+    const double* slotp[C];
     auto load_slots = [&](int b) {
 #pragma unroll
-        for (int w = 0; w < (C + 7) / 8; ++w) refpack[w] = 0;
-        altmask = 0;
-#pragma unroll
         for (int k = 0; k < C; ++k) {
-            const int c = c0 + k;
-            if (c < L) {
-                refpack[k >> 3] |= (uint32_t)refm[(size_t)b * L + c] << (4 * (k & 7));
-                if (refk[(size_t)b * L + c] != COL_ACGT) altmask |= 1u << k;
+            const int c = cfirst + k - (skip0 ? 1 : 0);   /* DP column of slot k (dummy slot 0 aliases column cfirst-1) */
+            int e = 0;
+            if (c >= 1 && c <= L) {
+                const unsigned kind = refk[(size_t)b * L + c - 1];
+                const unsigned mask = refm[(size_t)b * L + c - 1];
+                e = (kind == COL_ACGT) ? (mask == 1 ? 0 : (mask == 2 ? 1 : (mask == 4 ? 2 : 3))) : 3 + (int)kind;
+                if (kind == COL_ACGT && mask == 0) e = 0;   /* unrecognized base: host raises before results are used */
             }
+            slotp[k] = mytab + e * 32;
         }
     };
     load_slots(0);
@@ -137,39 +159,44 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
     auto row_step = [&](double Sl, double El, bool live) {
         const unsigned rw = rowp[i - 1];
         const unsigned q = rw & 0xffu;
-        const unsigned obsrep = (rw >> 8) * 0x11111111u;
-        const double mq = costs[q], xq = costs[encn + q];
-        double aq = 0.0;
-        if (ALT) aq = costs[2 * encn + q];
+        const unsigned obs = rw >> 8;
+        {
+            const double mq = costs[q], xq = costs[encn + q];
+            mytab[0 * 32] = (obs & 1u) ? mq : xq;
+            mytab[1 * 32] = (obs & 2u) ? mq : xq;
+            mytab[2 * 32] = (obs & 4u) ? mq : xq;
+            mytab[3 * 32] = (obs & 8u) ? mq : xq;
+            if (kinds & 2) mytab[4 * 32] = costs[2 * encn + q];
+            if (kinds & 4) mytab[5 * 32] = costs[3 * encn + q];
+            if (kinds & 8) mytab[6 * 32] = costs[4 * encn + q];
+        }
         if (first_lane) {   /* column 0: src/reference_align.cpp:64-78 */
             Sl = col0_value(local, gop, ge, i);
             El = NEG;
         }
+        const double Sl_in = Sl, El_in = El;
         uint32_t flo = 0, fhi = 0;
         /* Phase 1 (independent of this row's left-to-right chain): for every owned column the vertical
-         * candidate v = max(F[i-1][c]-ve, H[i-1][c]-vo) (:145-155; free in the last local column) and the
-         * (mis)match candidate m = H[i-1][c-1] + cost (:159, :184-225).  F is updated in place, m kept. */
+         * candidate v = max(F[i-1][c]-ve, H[i-1][c]-vo) (:145-155) and the (mis)match candidate
+         * m = H[i-1][c-1] + cost (:159).  F is updated in place, m kept for phase 2. */
         double m[C];
         {
             double diag = diag0;
 #pragma unroll
             for (int k = 0; k < C; ++k) {
-                const double vO = __fma_rn(ngop, one[k], S[k]);
-                const double Fe = __fma_rn(nge, one[k], F[k]);
+                const double vO = __dsub_rn(S[k], (k == C - 1) ? vo_last : gop);
+                const double Fe = __dsub_rn(F[k], (k == C - 1) ? ve_last : ge);
                 const bool p2 = Fe > vO;
                 F[k] = p2 ? Fe : vO;
-                const bool pm = (obsrep & refpack[k >> 3] & (0xFu << (4 * (k & 7)))) != 0;
-                double cost = pm ? mq : xq;
-                if (ALT) cost = (altmask & (1u << k)) ? aq : cost;
-                m[k] = __dadd_rn(diag, cost);
-                diag = S[k];
+                m[k] = __dadd_rn(diag, *slotp[k]);
+                diag = (k == 0 && skip0) ? diag0 : S[k];
                 if (TRACE) {
                     uint32_t& f = (k < 8) ? flo : fhi;
                     if (p2) f |= 8u << (4 * (k & 7));
                 }
             }
         }
-        diag0 = Sl;
+        diag0 = Sl_in;
         /* Phase 2 (the serial chain along the row): horizontal candidate h = max(E[i][c-1]-ge, H[i][c-1]-go')
          * (:129-140; when the left cell itself chose "left", H == E bitwise and go' >= ge makes the max the
          * reference's value), then the choice (:164-174): diag only if strictly best, horizontal only if
@@ -188,6 +215,10 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
             S[k] = Sn;
             Sl = Sn;
             El = h;
+            if (k == 0) {   /* a dummy slot hands its left boundary on unchanged */
+                Sl = skip0 ? Sl_in : Sl;
+                El = skip0 ? El_in : El;
+            }
             if (TRACE) {
                 uint32_t& f = (k < 8) ? flo : fhi;
                 const int sh = 4 * (k & 7);
@@ -228,10 +259,11 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
                 if (TRACE) flagp = reinterpret_cast<WT*>(A.flags) + a * A.fstride;
 #pragma unroll
                 for (int k = 0; k < C; ++k) {
-                    S[k] = (c0 + k + 1 <= L) ? row0s[c0 + k + 1] : 0.0;   /* H[0][c] */
-                    F[k] = NEG;                                            /* up_jump_score, :122 */
+                    const int c = cfirst + k - (skip0 ? 1 : 0);
+                    S[k] = (c >= 0 && c <= L) ? row0s[c] : 0.0;   /* H[0][c] */
+                    F[k] = NEG;                                   /* up_jump_score, :122 */
                 }
-                diag0 = row0s[c0 < L ? c0 : L];                            /* H[0][c0] */
+                diag0 = row0s[cfirst - 1];                        /* H[0][cfirst-1] */
                 if (nref > 1) {
                     load_slots(b);
                     if (b == 0) { best = NEG; nextb = NEG; bid = 0; }
@@ -261,10 +293,8 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
         }
         if (!act) { rowp = keep_rowp; i = keep_i; }
 
-        if (act && i == len && j == jl) {
-            double s = S[0];
-#pragma unroll
-            for (int k = 1; k < C; ++k) s = (k == kl) ? S[k] : s;
+        if (act && i == len && j == G - 1) {
+            const double s = S[C - 1];
             if (A.score) A.score[(long long)b * A.n + a] = s;
             if (nref > 1) {
                 update_best(s, b + 1, best, nextb, bid);
@@ -407,7 +437,8 @@ struct FlagReader {
     int len;
     __device__ unsigned get(int i, int c) const {
         if (T.layout == 0) {
-            const int j = (c - 1) / T.C, k = (c - 1) % T.C;
+            int j, k;
+            wf_locate(c, T.C, T.G * T.C - T.L, &j, &k);
             const long long w = a * T.fstride + (long long)(i + j) * T.G + j;
             if (T.wordbytes == 4) {
                 return (reinterpret_cast<const uint32_t*>(T.flags)[w] >> (4 * k)) & 15u;
@@ -508,9 +539,9 @@ __global__ void __launch_bounds__(128) traceback(const TraceArgs T)
     }
 }
 
-template <int C, bool TRACE, bool ALT>
+template <int C, bool TRACE>
 const char* launch_wf(const AlignArgs& a, int grid, cudaStream_t st, size_t smem) {
-    auto kern = wf_forward<C, TRACE, ALT>;
+    auto kern = wf_forward<C, TRACE>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (grid <= 0) {
         int dev = 0, sms = 0, per = 0;
@@ -525,21 +556,20 @@ const char* launch_wf(const AlignArgs& a, int grid, cudaStream_t st, size_t smem
     const long long need = (a.n + groups_per_block - 1) / groups_per_block;
     if (need < grid) grid = (int)(need > 0 ? need : 1);
     kern<<<grid, kBlock, smem, st>>>(a);
-    return TRACE ? (ALT ? "wf_forward<trace,alt>" : "wf_forward<trace>") : (ALT ? "wf_forward<alt>" : "wf_forward<>");
+    return TRACE ? "wf_forward<trace>" : "wf_forward<score>";
 }
 
 template <int C>
 const char* dispatch_flags(const AlignArgs& a, bool trace, bool alt, int grid, cudaStream_t st, size_t smem) {
-    if (trace) {
-        return alt ? launch_wf<C, true, true>(a, grid, st, smem) : launch_wf<C, true, false>(a, grid, st, smem);
-    }
-    return alt ? launch_wf<C, false, true>(a, grid, st, smem) : launch_wf<C, false, false>(a, grid, st, smem);
+    (void)alt;
+    return trace ? launch_wf<C, true>(a, grid, st, smem) : launch_wf<C, false>(a, grid, st, smem);
 }
 
 }  // namespace
 
 size_t wavefront_smem_bytes(const AlignArgs& a) {
-    return sizeof(double) * ((size_t)a.L + 1 + 3 * (size_t)a.enc_n) + 2 * (size_t)a.nref * a.L;
+    return sizeof(double) * ((size_t)a.L + 1 + 5 * (size_t)a.enc_n + (size_t)(kBlock / 32) * kCostEntries * 32) +
+           2 * (size_t)a.nref * a.L;
 }
 
 int wavefront_block_threads() { return kBlock; }

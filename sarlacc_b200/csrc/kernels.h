@@ -47,7 +47,7 @@ struct AlignArgs {
     const double* row0;       /* [L+1] H[0][c] (row 0 chain of src/reference_align.cpp:116-117) */
     const double* cost;       /* [5][enc_n]: match1, mismatch1, mismatch2, match3, match4 */
     int enc_n;
-    int alt_row;              /* which row of `cost` the single non-ACGT class of the reference uses (2..4), wavefront only */
+    int kinds;                /* bit k set if some reference column has ColKind k */
     /* wavefront geometry */
     int G, C;
     /* outputs */

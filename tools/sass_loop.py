@@ -1,9 +1,9 @@
 """Print the instruction mix of the innermost loop (the DP row loop) of one wf_forward variant.
-usage: python tools/sass_loop.py C trace alt [--dump]"""
+usage: python tools/sass_loop.py C trace [--dump]"""
 import re, subprocess, sys, collections
-C, tr, alt = sys.argv[1], sys.argv[2], sys.argv[3]
+C, tr = sys.argv[1], sys.argv[2]
 out = subprocess.run(["cuobjdump", "-sass", "sarlacc_b200/libsarlacc_b200.so"], capture_output=True, text=True).stdout
-pat = "wf_forwardILi%sELb%sELb%sE" % (C, tr, alt)
+pat = "wf_forwardILi%sELb%sEEE" % (C, tr)
 lines = out.splitlines()
 st = next(i for i, l in enumerate(lines) if "Function :" in l and pat in l)
 en = next((i for i in range(st + 1, len(lines)) if "Function :" in lines[i]), len(lines))
