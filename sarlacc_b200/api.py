@@ -1,0 +1,475 @@
+"""Host-side mirror of the reference's R drivers around the adaptor-alignment hot path.
+
+Same names, arguments, defaults, return columns and quirks as the R functions they mirror, so that the
+parity tests read like the reference's own tests:
+
+    adaptorAlign           R/adaptorAlign.R:7-78
+    getAdaptorThresholds   R/getAdaptorThresholds.R:6-66
+    barcodeAlign           R/barcodeAlign.R:4-40
+    tuneAlignment          R/tuneAlignment.R:6-76          (caller of the same entry points)
+    qualityAlign           R/qualityAlign.R                (general_align wrapper)
+    helpers: _setup_subseqs (:136-143), _get_front_and_back (:86-95), _resolve_strand (:112-122),
+             _parallelize (:126-134), _align_and_extract (:150-176), _align_AA_internal (:178-199),
+             _scramble_input (getAdaptorThresholds.R:68-92), _compute_threshold (:94-103),
+             _tied_overlap (tuneAlignment.R:78-86), _create_encoding_vector (qualityMask.R:19-27)
+
+All alignment arithmetic happens in the CUDA library (sarlacc_b200.native); this module only does what
+the R code does around the `.Call`s.  R data structures map to: QualityScaledDNAStringSet -> ReadSet,
+DataFrame -> Frame (ordered columns + metadata + rownames), NA_integer_ -> 0 for barcode ids.
+"""
+import re
+
+import numpy as np
+
+from . import native
+from .reads import ReadSet, read_fastq
+
+
+# --------------------------------------------------------------------------------------------------
+# A minimal DataFrame
+# --------------------------------------------------------------------------------------------------
+class Frame:
+    """Ordered named columns of equal length (numpy arrays, ReadSets or nested Frames) + metadata + rownames."""
+
+    def __init__(self, columns=None, nrows=None, rownames=None, metadata=None):
+        self.columns = dict(columns or {})
+        self._nrows = nrows
+        self.rownames = rownames
+        self.metadata = dict(metadata or {})
+
+    def __len__(self):
+        if self._nrows is not None:
+            return self._nrows
+        for v in self.columns.values():
+            return len(v)
+        return 0
+
+    def __getitem__(self, key):
+        return self.columns[key]
+
+    def __setitem__(self, key, value):
+        self.columns[key] = value
+
+    def __contains__(self, key):
+        return key in self.columns
+
+    def __getattr__(self, key):
+        cols = self.__dict__.get("columns", {})
+        if key in cols:
+            return cols[key]
+        raise AttributeError(key)
+
+    def names(self):
+        return list(self.columns)
+
+    def assign_rows(self, mask, other):
+        """self[mask,] <- other[mask,] for every column (R/adaptorAlign.R:195-196), nested frames included."""
+        mask = np.asarray(mask, dtype=bool)
+        for k, v in self.columns.items():
+            o = other.columns[k]
+            if isinstance(v, Frame):
+                v.assign_rows(mask, o)
+            elif isinstance(v, ReadSet):
+                self.columns[k] = _readset_where(mask, o, v)
+            else:
+                v = v.copy()
+                v[mask] = o[mask]
+                self.columns[k] = v
+
+    @staticmethod
+    def rbind(frames):
+        frames = list(frames)
+        first = frames[0]
+        out = Frame(nrows=sum(len(f) for f in frames), metadata=first.metadata)
+        for k, v in first.columns.items():
+            parts = [f.columns[k] for f in frames]
+            if isinstance(v, Frame):
+                out.columns[k] = Frame.rbind(parts)
+            elif isinstance(v, ReadSet):
+                out.columns[k] = ReadSet.concat(parts)
+            else:
+                out.columns[k] = np.concatenate(parts)
+        if all(f.rownames is not None for f in frames):
+            out.rownames = [x for f in frames for x in f.rownames]
+        return out
+
+
+def _readset_where(mask, a, b):
+    """Element-wise ifelse(mask, a, b) for two ReadSets of equal length."""
+    n = len(a)
+    both = ReadSet.concat([a, b])
+    idx = np.where(mask, np.arange(n), n + np.arange(n))
+    return both[idx]
+
+
+# --------------------------------------------------------------------------------------------------
+# helpers (dot-prefixed internals of the R package)
+# --------------------------------------------------------------------------------------------------
+def _qual2class(qual_type):
+    # R/adaptorAlign.R:97-99
+    return qual_type[:1].upper() + qual_type[1:] + "Quality"
+
+
+_QUAL_ENCODINGS = {
+    # Biostrings::encoding(): offset character and score range of each quality class
+    "PhredQuality": (33, 0, 93, "phred"),
+    "IlluminaQuality": (64, 0, 62, "phred"),
+    "SolexaQuality": (59, -5, 62, "solexa"),
+}
+
+
+def _create_encoding_vector(qual_class="PhredQuality"):
+    """R/qualityMask.R:19-27: names = the encoding characters, values = their error probabilities
+    (Phred: 10^(-q/10); Solexa: 1/(1+10^(q/10)) ... expressed as an error probability)."""
+    offset, lo, hi, kind = _QUAL_ENCODINGS[qual_class]
+    qs = np.arange(lo, hi + 1)
+    names = [chr(offset + int(q)) for q in qs]
+    if kind == "phred":
+        err = 10.0 ** (-qs / 10.0)
+    else:
+        err = 1.0 - 1.0 / (1.0 + 10.0 ** (-qs / 10.0))
+    return names, err.astype(np.float64)
+
+
+def _setup_subseqs(adaptor):
+    """R/adaptorAlign.R:136-143: 1-based starts/ends of the runs of non-ACGT characters."""
+    starts, ends = [], []
+    for m in re.finditer("[^ACTG]+", adaptor):
+        starts.append(m.start() + 1)
+        ends.append(m.end())
+    return {"starts": np.array(starts, dtype=np.int32), "ends": np.array(ends, dtype=np.int32)}
+
+
+def _get_front_and_back(reads, tolerance):
+    """R/adaptorAlign.R:86-95: first `tolerance` bases, and the reverse complement of the last `tolerance` bases."""
+    w = reads.width()
+    tol = np.minimum(np.int64(tolerance), w)
+    front = reads.subseq(start=np.ones(len(reads), np.int64), width=tol)
+    back = reads.subseq(end=w, width=tol).reverse_complement()
+    back.names = reads.names
+    return {"front": front, "back": back}
+
+
+def _resolve_strand(start_score, end_score, rc_start_score, rc_end_score):
+    """R/adaptorAlign.R:112-122."""
+    fscore = np.maximum(start_score, 0) + np.maximum(end_score, 0)
+    rscore = np.maximum(rc_start_score, 0) + np.maximum(rc_end_score, 0)
+    is_reverse = fscore < rscore
+    return {"reversed": is_reverse, "scores": np.where(is_reverse, rscore, fscore)}
+
+
+def _parallelize(n, n_workers):
+    """R/adaptorAlign.R:126-134: contiguous split of seq_len(n) into n_workers chunks; returns index arrays.
+    (The GPU library shards by the same rule internally; this is kept for API parity and the gloo tests.)"""
+    if n == 0:
+        return []
+    bounds = np.linspace(1, n, n_workers + 1)[:-1]
+    ids = np.searchsorted(bounds, np.arange(1, n + 1), side="right")
+    return [np.nonzero(ids == k)[0] for k in np.unique(ids)]
+
+
+def _align_and_extract(adaptor, reads, gap_opening, gap_extension, subseq_starts, subseq_ends, encoding=None):
+    """R/adaptorAlign.R:150-176."""
+    enc = encoding or native.phred_encoding()
+    out = native.adaptor_align(reads, enc, gap_opening, gap_extension, adaptor,
+                               np.asarray(subseq_starts, dtype=np.int32) - 1, subseq_ends)
+    output = Frame({"score": out[0], "start": out[1], "end": out[2]})
+    segments = Frame(nrows=len(reads))
+    for i in range(len(out[3])):
+        segments["Sub%d" % (i + 1)] = reads.subseq(start=out[3][i], width=out[4][i])
+    output["subseq"] = segments
+    return output
+
+
+def _align_AA_internal(reads, adaptor1, adaptor2, tolerance, subseq1, subseq2, gap_opening, gap_extension, encoding=None):
+    """R/adaptorAlign.R:178-199."""
+    w = _get_front_and_back(reads, tolerance)
+    args = dict(gap_opening=gap_opening, gap_extension=gap_extension, encoding=encoding)
+    cur_starts = _align_and_extract(adaptor1, w["front"], subseq_starts=subseq1["starts"], subseq_ends=subseq1["ends"], **args)
+    cur_ends = _align_and_extract(adaptor2, w["back"], subseq_starts=subseq2["starts"], subseq_ends=subseq2["ends"], **args)
+    cur_rc_starts = _align_and_extract(adaptor1, w["back"], subseq_starts=subseq1["starts"], subseq_ends=subseq1["ends"], **args)
+    cur_rc_ends = _align_and_extract(adaptor2, w["front"], subseq_starts=subseq2["starts"], subseq_ends=subseq2["ends"], **args)
+    strand = _resolve_strand(cur_starts["score"], cur_ends["score"], cur_rc_starts["score"], cur_rc_ends["score"])
+    is_reverse = strand["reversed"]
+    cur_starts.assign_rows(is_reverse, cur_rc_starts)
+    cur_ends.assign_rows(is_reverse, cur_rc_ends)
+    return {"names": reads.names, "width": reads.width(), "start": cur_starts, "end": cur_ends, "reversed": is_reverse}
+
+
+def _stream(source, number):
+    """FastqStreamer(filepath, n=number) + yield (R/adaptorAlign.R:26,36), or chunks of an in-memory ReadSet."""
+    number = int(number)
+    if isinstance(source, ReadSet):
+        n = len(source)
+        for lo in range(0, n, number):
+            idx = np.arange(lo, min(n, lo + number))
+            yield source[idx]
+    else:
+        yield from read_fastq(source, number)
+
+
+# --------------------------------------------------------------------------------------------------
+# exported functions
+# --------------------------------------------------------------------------------------------------
+def adaptorAlign(adaptor1, adaptor2, filepath, tolerance=250, gapOpening=5, gapExtension=1,
+                 qual_type="phred", number=1e5):
+    """R/adaptorAlign.R:7-78.  `filepath` is a FASTQ path or an in-memory ReadSet (names required for
+    getAdaptorThresholds).  Returns a Frame with read.width, adaptor1, adaptor2, reversed and the same metadata."""
+    adaptor1 = str(adaptor1).upper()
+    adaptor2 = str(adaptor2).upper()
+    if qual_type not in ("phred", "solexa", "illumina"):
+        raise ValueError("'arg' should be one of 'phred', 'solexa', 'illumina'")
+    enc = _create_encoding_vector(_qual2class(qual_type))
+    all_args = dict(adaptor1=adaptor1, adaptor2=adaptor2, tolerance=tolerance,
+                    subseq1=_setup_subseqs(adaptor1), subseq2=_setup_subseqs(adaptor2),
+                    gap_opening=gapOpening, gap_extension=gapExtension, encoding=enc)
+    names, widths, starts, ends, revs = [], [], [], [], []
+    for reads in _stream(filepath, number):
+        out = _align_AA_internal(reads, **all_args)
+        names.append(out["names"] if out["names"] is not None else [None] * len(reads))
+        widths.append(out["width"])
+        starts.append(out["start"])
+        ends.append(out["end"])
+        revs.append(out["reversed"])
+    if not starts:
+        out = _align_AA_internal(ReadSet.empty(), **all_args)   # guarantee some value is returned (:47-55)
+        names, widths, starts, ends, revs = [[]], [out["width"]], [out["start"]], [out["end"]], [out["reversed"]]
+    align_start = Frame.rbind(starts)
+    align_end = Frame.rbind(ends)
+    details = {"gapOpening": gapOpening, "gapExtension": gapExtension}
+    align_start.metadata = dict(sequence=adaptor1, **details)
+    align_end.metadata = dict(sequence=adaptor2, **details)
+    all_widths = np.concatenate(widths).astype(np.int64)
+    # Adjusting the reverse coordinates for the read length (:66-71)
+    align_end["start"] = (all_widths - align_end["start"] + 1).astype(np.int64)
+    align_end["end"] = (all_widths - align_end["end"] + 1).astype(np.int64)
+    all_names = [x for chunk in names for x in chunk]
+    align_start.rownames = align_end.rownames = all_names
+    output = Frame({"read.width": all_widths, "adaptor1": align_start, "adaptor2": align_end,
+                    "reversed": np.concatenate(revs)}, rownames=all_names,
+                   metadata={"filepath": filepath, "qual.type": qual_type, "tolerance": tolerance})
+    return output
+
+
+def _mix64(x):
+    """splitmix64 finaliser (vectorised): the counter-based hash behind the scramble permutation."""
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+def _scramble_input(seqs, has_qual=True, seed=0, first_index=0, stream=0):
+    """R/getAdaptorThresholds.R:68-92: one uniform random permutation per sequence, applied to bases and
+    qualities alike.  R's sample() stream cannot be reproduced outside R; the permutation here sorts
+    counter-based hash keys of (seed, global read index, stream, position), so it does not depend on
+    chunking, sharding or device count."""
+    n = len(seqs)
+    w = seqs.width()
+    total = int(w.sum())
+    with np.errstate(over="ignore"):
+        rid = np.repeat(np.arange(first_index, first_index + n, dtype=np.uint64), w)
+        off = np.zeros(n, dtype=np.int64)
+        np.cumsum(w[:-1], out=off[1:])
+        pos = (np.arange(total, dtype=np.int64) - np.repeat(off, w)).astype(np.uint64)
+        key = _mix64(_mix64(rid * np.uint64(0x9E3779B97F4A7C15) + np.uint64(seed)) ^ (pos * np.uint64(0xD1B54A32D192ED03) + np.uint64(stream) * np.uint64(0x8CB92BA72F3D8DD7)))
+    order = np.lexsort((key, np.repeat(np.arange(n), w)))
+    base = seqs.seq_off[0]
+    sp = seqs.seq_pool[base + order]
+    qp = None
+    if has_qual:
+        qp = seqs.qual_pool[seqs.qual_off[0] + order]
+    o = seqs.seq_off - base
+    return ReadSet(sp, o, qp, o if qp is not None else None, seqs.names)
+
+
+def _compute_threshold(real, scrambled, error):
+    """R/getAdaptorThresholds.R:94-103, IEEE semantics included (x/0 -> Inf/NaN, dropped by which())."""
+    real = np.sort(np.asarray(real, dtype=np.float64))
+    scrambled = np.sort(np.asarray(scrambled, dtype=np.float64))
+    found = np.searchsorted(scrambled, real, side="right")          # findInterval(real, scrambled)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        fdr = (len(scrambled) - found) / (len(real) - np.arange(1, len(real) + 1, dtype=np.float64))
+    ok = np.nonzero(fdr <= error)[0]
+    if len(ok) == 0:
+        return float("nan")                                         # real[min(integer(0))] -> NA
+    return float(real[ok[0]])
+
+
+def _get_alignment_scores(reads_start, reads_end, adaptor1, adaptor2, gap_opening, gap_extension, encoding=None):
+    """R/tuneAlignment.R:99-112."""
+    enc = encoding or native.phred_encoding()
+
+    def fun(r, a):
+        return native.adaptor_align_score_only(r, enc, gap_opening, gap_extension, a)
+
+    return {"START": fun(reads_start, adaptor1), "END": fun(reads_end, adaptor2),
+            "RSTART": fun(reads_end, adaptor1), "REND": fun(reads_start, adaptor2)}
+
+
+def _align_AT_internal(reads, adaptor1, adaptor2, tolerance, gap_opening, gap_extension, encoding=None, seed=0, first_index=0):
+    """R/getAdaptorThresholds.R:105-128."""
+    w = _get_front_and_back(reads, tolerance)
+    scr_start = _scramble_input(w["front"], True, seed, first_index, 0)
+    scr_end = _scramble_input(w["back"], True, seed, first_index, 1)
+    sc = _get_alignment_scores(scr_start, scr_end, adaptor1, adaptor2, gap_opening, gap_extension, encoding)
+    is_reverse = _resolve_strand(sc["START"], sc["END"], sc["RSTART"], sc["REND"])["reversed"]
+    return {"adaptor1": np.where(is_reverse, sc["RSTART"], sc["START"]),
+            "adaptor2": np.where(is_reverse, sc["REND"], sc["END"])}
+
+
+def getAdaptorThresholds(aligned, error=0.01, number=1e5, seed=0):
+    """R/getAdaptorThresholds.R:6-66."""
+    go = aligned["adaptor1"].metadata["gapOpening"]
+    ge = aligned["adaptor1"].metadata["gapExtension"]
+    adaptor1 = aligned["adaptor1"].metadata["sequence"]
+    adaptor2 = aligned["adaptor2"].metadata["sequence"]
+    tolerance = aligned.metadata["tolerance"]
+    filepath = aligned.metadata["filepath"]
+    enc = _create_encoding_vector(_qual2class(aligned.metadata["qual.type"]))
+    wanted = {nm: k for k, nm in enumerate(aligned.rownames)}
+    scr1, scr2, used = [], [], []
+    seen = 0
+    for reads in _stream(filepath, number):
+        keep = np.array([nm in wanted for nm in reads.names], dtype=bool)
+        first_index = seen
+        seen += len(reads)
+        idx = np.nonzero(keep)[0]
+        sub = reads[idx]
+        used.extend(sub.names)
+        if len(sub) == 0:
+            continue
+        # the scramble is keyed by the read's position in the file, so dropping reads does not shift others
+        w = _get_front_and_back(sub, tolerance)
+        scr_start = _scramble_by_index(w["front"], seed, first_index + idx, 0)
+        scr_end = _scramble_by_index(w["back"], seed, first_index + idx, 1)
+        sc = _get_alignment_scores(scr_start, scr_end, adaptor1, adaptor2, go, ge, enc)
+        is_reverse = _resolve_strand(sc["START"], sc["END"], sc["RSTART"], sc["REND"])["reversed"]
+        scr1.append(np.where(is_reverse, sc["RSTART"], sc["START"]))
+        scr2.append(np.where(is_reverse, sc["REND"], sc["END"]))
+    scram1 = np.concatenate(scr1) if scr1 else np.zeros(0)
+    scram2 = np.concatenate(scr2) if scr2 else np.zeros(0)
+    m = np.array([wanted[nm] for nm in used], dtype=np.int64)
+    real1 = aligned["adaptor1"]["score"][m]
+    real2 = aligned["adaptor2"]["score"][m]
+    return {"threshold1": _compute_threshold(real1, scram1, error),
+            "threshold2": _compute_threshold(real2, scram2, error),
+            "scores1": {"reads": real1, "scrambled": scram1},
+            "scores2": {"reads": real2, "scrambled": scram2}}
+
+
+def _scramble_by_index(seqs, seed, read_index, stream):
+    """_scramble_input with an explicit global index per read."""
+    n = len(seqs)
+    w = seqs.width()
+    total = int(w.sum())
+    with np.errstate(over="ignore"):
+        rid = np.repeat(np.asarray(read_index, dtype=np.uint64), w)
+        off = np.zeros(n, dtype=np.int64)
+        if n:
+            np.cumsum(w[:-1], out=off[1:])
+        pos = (np.arange(total, dtype=np.int64) - np.repeat(off, w)).astype(np.uint64)
+        key = _mix64(_mix64(rid * np.uint64(0x9E3779B97F4A7C15) + np.uint64(seed)) ^ (pos * np.uint64(0xD1B54A32D192ED03) + np.uint64(stream) * np.uint64(0x8CB92BA72F3D8DD7)))
+    order = np.lexsort((key, np.repeat(np.arange(n), w)))
+    base = seqs.seq_off[0]
+    sp = seqs.seq_pool[base + order]
+    qp = seqs.qual_pool[seqs.qual_off[0] + order] if seqs.has_quality else None
+    o = seqs.seq_off - base
+    return ReadSet(sp, o, qp, o if qp is not None else None, seqs.names)
+
+
+def barcodeAlign(sequences, barcodes, gapOpening=5, gapExtension=1, qual_type="phred"):
+    """R/barcodeAlign.R:4-40, with the per-barcode loop fused into one device pass.  Quirk kept: the barcodes are
+    passed to the aligner as given (the reference computes toupper() at :21 but passes barcodes[b] at :23)."""
+    enc = _create_encoding_vector(_qual2class(qual_type))
+    barcodes = [str(b) for b in barcodes]
+    if len({len(b) for b in barcodes}) <= 1:
+        bid, best, nxt = native.barcode_align_multi(sequences, enc, gapOpening, gapExtension, barcodes)
+    else:
+        # barcodes of different lengths cannot share one pass; fall back to the reference's own loop (:20-35)
+        n = len(sequences)
+        best = np.full(n, -np.inf)
+        nxt = np.full(n, -np.inf)
+        bid = np.zeros(n, np.int32)
+        for b, bc in enumerate(barcodes):
+            scores = native.barcode_align(sequences, enc, gapOpening, gapExtension, bc)
+            keep = scores > best
+            second = ~keep & (scores > nxt)
+            bid[keep] = b + 1
+            nxt[keep] = best[keep]
+            best[keep] = scores[keep]
+            nxt[second] = scores[second]
+    with np.errstate(invalid="ignore"):
+        gap = best - nxt
+    return Frame({"barcode": bid, "score": best, "gap": gap},
+                 metadata={"gapOpening": gapOpening, "gapExtension": gapExtension, "barcodes": barcodes})
+
+
+def _tied_overlap(real, fake):
+    """R/tuneAlignment.R:78-86."""
+    real = np.asarray(real, dtype=np.float64)
+    fake = np.sort(np.asarray(fake, dtype=np.float64))
+    upper = np.searchsorted(fake, real, side="right")
+    lower = np.searchsorted(fake, real, side="left")
+    return float(np.sum((upper + lower) / 2.0) / (len(real) * len(fake)))
+
+
+def tuneAlignment(adaptor1, adaptor2, filepath, tolerance=200, number=10000, gapOp_range=(4, 10), gapExt_range=(1, 5),
+                  qual_type="phred", seed=0):
+    """R/tuneAlignment.R:6-76.  The reference samples `number` reads with FastqSampler (R's RNG); here the first
+    `number` reads of the stream are used.  Windows and their scrambled versions are packed once and stay
+    resident in HBM across the 35-point grid."""
+    adaptor1 = str(adaptor1).upper()
+    adaptor2 = str(adaptor2).upper()
+    enc = _create_encoding_vector(_qual2class(qual_type))
+    reads = None
+    for chunk in _stream(filepath, number):
+        reads = chunk
+        break
+    if reads is None or len(reads) == 0:
+        return {"parameters": {"gapOpening": None, "gapExtension": None},
+                "scores": {"reads": np.zeros(0), "scrambled": np.zeros(0)}}
+    w = _get_front_and_back(reads, tolerance)
+    scr_start = _scramble_input(w["front"], True, seed, 0, 0)
+    scr_end = _scramble_input(w["back"], True, seed, 0, 1)
+    res = {k: native.Resident(v, enc) for k, v in
+           dict(start=w["front"], end=w["back"], sstart=scr_start, send=scr_end).items()}
+    go_r = np.maximum.accumulate(np.asarray(gapOp_range, dtype=int))
+    ge_r = np.maximum.accumulate(np.asarray(gapExt_range, dtype=int))
+    max_score, final = 0.0, None
+
+    def scores(rs, re_, go, ge):
+        out = {}
+        for key, r, a in (("START", rs, adaptor1), ("END", re_, adaptor2), ("RSTART", re_, adaptor1), ("REND", rs, adaptor2)):
+            r.align(r.MODE_SCORE_LOCAL, go, ge, a)
+            out[key] = r.fetch()
+        return _resolve_strand(out["START"], out["END"], out["RSTART"], out["REND"])["scores"]
+
+    try:
+        for go in range(int(go_r[0]), int(go_r[1]) + 1):
+            for ge in range(int(ge_r[0]), int(ge_r[1]) + 1):
+                read_scores = scores(res["start"], res["end"], go, ge)
+                scr_scores = scores(res["sstart"], res["send"], go, ge)
+                cur = _tied_overlap(read_scores, scr_scores)
+                if max_score < cur:
+                    max_score = cur
+                    final = (go, ge, read_scores, scr_scores)
+    finally:
+        for r in res.values():
+            r.close()
+    if final is None:
+        return {"parameters": {"gapOpening": None, "gapExtension": None}, "scores": {"reads": None, "scrambled": None}}
+    return {"parameters": {"gapOpening": final[0], "gapExtension": final[1]},
+            "scores": {"reads": final[2], "scrambled": final[3]}}
+
+
+def qualityAlign(sequences, reference, gapOpening=5, gapExtension=1, edit_only=False, qual_type="phred"):
+    """R/qualityAlign.R: global quality-aware alignment of every sequence to one reference (cxx_general_align)."""
+    enc = _create_encoding_vector(_qual2class(qual_type))
+    ref = str(reference).upper()
+    out = native.general_align(sequences, enc, gapOpening, gapExtension, ref, edit_only)
+    f = Frame({"score": out[0], "edit": out[1]},
+              metadata={"gapOpening": gapOpening, "gapExtension": gapExtension, "reference": reference})
+    if not edit_only:
+        f["reference"] = np.array(out[2], dtype=object)
+        f["query"] = np.array(out[3], dtype=object)
+    return f

@@ -1,0 +1,183 @@
+"""GPU: the host-side mirror of the R drivers (adaptorAlign / getAdaptorThresholds / barcodeAlign / tuneAlignment /
+qualityAlign) through the CUDA library, against the loop restatement on the CPU oracle."""
+import numpy as np
+import pytest
+
+from conftest import VIGNETTE_A1, VIGNETTE_A2
+
+pytestmark = pytest.mark.gpu
+
+
+def compare_adaptor_align(out, exp):
+    assert len(out) == len(exp)
+    for side in ("adaptor1", "adaptor2"):
+        f = out[side]
+        assert np.array_equal(f["score"], np.array([e[side]["score"] for e in exp]))
+        assert f["start"].tolist() == [e[side]["start"] for e in exp]
+        assert f["end"].tolist() == [e[side]["end"] for e in exp]
+        nsub = len(exp[0][side]["subseq"]) if exp else 0
+        for k in range(nsub):
+            sub = f["subseq"]["Sub%d" % (k + 1)]
+            assert sub.seq_strings() == [e[side]["subseq"][k][0] for e in exp]
+            assert sub.qual_strings() == [e[side]["subseq"][k][1] for e in exp]
+    assert out["reversed"].tolist() == [e["reversed"] for e in exp]
+    assert out["read.width"].tolist() == [e["read.width"] for e in exp]
+
+
+def test_adaptor_align_known_answer(port, enc):
+    """tests/testthat/test-adaptor-align.R:186-206."""
+    from sarlacc_b200 import api, ReadSet
+    from oracle import r_level as R
+    read = "AACGTAACGTACGTACGTGGGGGGG"
+    rs = ReadSet.from_strings([read, R.revcomp(read)], ["5" * 25, "5" * 25], ["fwd", "rev"])
+    out = api.adaptorAlign("AANNNAA", "CCCCCCC", rs)
+    assert out["reversed"].tolist() == [False, True]
+    assert out["adaptor1"]["start"].tolist() == [1, 1] and out["adaptor1"]["end"].tolist() == [7, 7]
+    assert out["adaptor2"]["start"].tolist() == [25, 25] and out["adaptor2"]["end"].tolist() == [19, 19]
+    assert out["adaptor1"]["subseq"]["Sub1"].seq_strings() == ["CGT", "CGT"]
+    assert out["adaptor1"]["score"][0] == out["adaptor1"]["score"][1]
+    assert out.rownames == ["fwd", "rev"] and out.metadata["tolerance"] == 250
+    assert out["adaptor1"].metadata == {"sequence": "AANNNAA", "gapOpening": 5, "gapExtension": 1}
+    # empty input -> 0-row result (:209-211)
+    empty = api.adaptorAlign("AANNNAA", "CCCCCCC", ReadSet.empty())
+    assert len(empty["read.width"]) == 0 and len(empty["adaptor1"]["score"]) == 0
+
+
+def test_adaptor_align_mock_reads(port, enc, tmp_path):
+    """configs[0] in miniature: mockReads-style whole reads through a FASTQ file, chunked streaming, both
+    strands, vignette adaptors with UMI/barcode N-runs."""
+    from sarlacc_b200 import api, synth, write_fastq
+    from oracle import r_level as R
+    reads = synth.mock_reads(240, VIGNETTE_A1, VIGNETTE_A2, seed=1000)
+    path = str(tmp_path / "mock.fastq")
+    write_fastq(path, reads)
+    out = api.adaptorAlign(VIGNETTE_A1, VIGNETTE_A2, path, number=100)
+    exp = R.adaptor_align_R(port, enc, VIGNETTE_A1, VIGNETTE_A2, reads.seq_strings(), reads.qual_strings())
+    compare_adaptor_align(out, exp)
+    assert out.rownames == reads.names
+    assert 0.2 < out["reversed"].mean() < 0.8
+    # most reads carry both adaptors: scores well above zero, 12-base barcode and 4-base UMI extracted
+    assert np.median(out["adaptor1"]["score"]) > 20
+    assert np.median(out["adaptor1"]["subseq"]["Sub2"].width()) == 4
+    # other tolerance / penalties, in-memory input
+    out2 = api.adaptorAlign(VIGNETTE_A1, VIGNETTE_A2, reads, tolerance=120, gapOpening=4, gapExtension=2, number=77)
+    exp2 = R.adaptor_align_R(port, enc, VIGNETTE_A1, VIGNETTE_A2, reads.seq_strings(), reads.qual_strings(), tolerance=120, go=4, ge=2)
+    compare_adaptor_align(out2, exp2)
+
+
+def test_get_adaptor_thresholds(port, enc):
+    from sarlacc_b200 import api, synth
+    from oracle import r_level as R
+    reads = synth.mock_reads(150, VIGNETTE_A1, VIGNETTE_A2, seed=5)
+    aligned = api.adaptorAlign(VIGNETTE_A1, VIGNETTE_A2, reads, number=60)
+    th = api.getAdaptorThresholds(aligned, error=0.01, number=50, seed=3)
+    # identity is defined from the scrambled windows onwards: rebuild them with the same keyed permutation
+    w = api._get_front_and_back(reads, 250)
+    sf = api._scramble_input(w["front"], True, 3, 0, 0)
+    sb = api._scramble_input(w["back"], True, 3, 0, 1)
+    t1, t2, s1, s2 = R.adaptor_thresholds_R(port, enc, VIGNETTE_A1, VIGNETTE_A2,
+                                            list(zip(sf.seq_strings(), sf.qual_strings())), list(zip(sb.seq_strings(), sb.qual_strings())),
+                                            aligned["adaptor1"]["score"].tolist(), aligned["adaptor2"]["score"].tolist(), 5, 1, 0.01)
+    assert np.array_equal(th["scores1"]["scrambled"], np.array(s1)) and np.array_equal(th["scores2"]["scrambled"], np.array(s2))
+    assert (np.isnan(t1) and np.isnan(th["threshold1"])) or t1 == th["threshold1"]
+    assert (np.isnan(t2) and np.isnan(th["threshold2"])) or t2 == th["threshold2"]
+    assert np.array_equal(th["scores1"]["reads"], aligned["adaptor1"]["score"])
+    # real adaptors score far above scrambled windows
+    assert np.median(th["scores1"]["reads"]) > np.max(th["scores1"]["scrambled"])
+    # chunking must not change anything
+    th2 = api.getAdaptorThresholds(aligned, error=0.01, number=1000, seed=3)
+    assert np.array_equal(th2["scores1"]["scrambled"], th["scores1"]["scrambled"]) and th2["threshold2"] == th["threshold2"] or np.isnan(th["threshold2"])
+
+
+def test_barcode_align(port, enc):
+    from sarlacc_b200 import api, synth
+    from oracle import r_level as R
+    barcodes = synth.random_barcodes(12, 24, 8, seed=3000)
+    seqs, pick = synth.mock_barcode_sequences(400, barcodes, seed=3000)
+    out = api.barcodeAlign(seqs, barcodes)
+    cid, cur, gap = R.barcode_align_R(port, enc, seqs.seq_strings(), seqs.qual_strings(), barcodes)
+    assert out["barcode"].tolist() == cid and np.array_equal(out["score"], np.array(cur)) and np.array_equal(out["gap"], np.array(gap))
+    assert np.mean(out["barcode"] - 1 == pick) > 0.95
+    one = api.barcodeAlign(seqs, barcodes[:1])
+    assert np.all(np.isinf(one["gap"])) and set(one["barcode"].tolist()) == {1}
+    # barcodes of different lengths take the reference's own loop
+    mixed = barcodes[:3] + [barcodes[3][:20]]
+    out = api.barcodeAlign(seqs, mixed)
+    cid, cur, gap = R.barcode_align_R(port, enc, seqs.seq_strings(), seqs.qual_strings(), mixed)
+    assert out["barcode"].tolist() == cid and np.array_equal(out["score"], np.array(cur))
+
+
+def test_tune_alignment(port, enc):
+    """tests/testthat/test-tuning.R:26-42 (the pairwiseAlignment comparison is replaced by the oracle)."""
+    from sarlacc_b200 import api, ReadSet
+    from oracle import r_level as R
+    a1, a2 = "CGTACGACGAT", "TCGAGCGTTAC"
+    reads = ["CGTACGACGATGACTGATCGATCGTAGTTCATCGACGATGTAACGCTCGA", "CGTCGACGATGACTGATCGATCGTAGTTCATCGACGATGTAACGCTCGA",
+             "CGTACGACGATGACTGATCGATCGTAGTTCATCGACGATGTAACGCCGA", "CGTACGACGATGACTGATCGATCGTAGTTCATCGACGATGTAACGCTCGA",
+             "CGCTACGACGATGACTGATCGATCGTAGTTCATCGACGATGTAACGGTCGA", "GTACGACGATTTACTGATCGATCGTAGTTCATCGACGATGTAACGCTCGA",
+             "CGTCGACGATGACTGGGCGATCGTAGTTCATCGACGATGTAACGCTCGA", "TACGACGATGACTGATCATCGTAAAAATTCATCGATGTAACGCCGA",
+             "CGTACGACGATGACTGATCGATCGTAGTTCACCCCGATGTAACGCTCGA", "CGCTACGACGATGACTGCGATCGTAGTTCATAAAAATGTAACGGTCGA"]
+    rs = ReadSet.from_strings(reads, ["~" * len(r) for r in reads], ["READ_%d" % (i + 1) for i in range(len(reads))])
+    out = api.tuneAlignment(a1, a2, rs, gapOp_range=(4, 5), gapExt_range=(1, 2))
+    go, ge = out["parameters"]["gapOpening"], out["parameters"]["gapExtension"]
+    assert go in (4, 5) and ge in (1, 2)
+    assert out["scores"]["reads"].min() > out["scores"]["scrambled"].max()
+    quals = ["~" * len(r) for r in reads]
+    front, back = R.get_front_and_back(reads, quals, 200)
+    sc = lambda w, a: port.align_score_only([x[0] for x in w], [x[1] for x in w], enc, go, ge, a)
+    _, final = R.resolve_strand(sc(front, a1), sc(back, a2), sc(back, a1), sc(front, a2))
+    assert np.array_equal(out["scores"]["reads"], np.array(final))
+    none = api.tuneAlignment(a1, a2, ReadSet.empty())
+    assert none["parameters"] == {"gapOpening": None, "gapExtension": None} and len(none["scores"]["reads"]) == 0
+
+
+def test_quality_align(port, enc):
+    from sarlacc_b200 import api, ReadSet
+    from conftest import random_windows
+    rng = np.random.default_rng(8)
+    ref = "aaggaattaaggccttacgt"
+    seqs, quals = random_windows(rng, 120, ref.upper(), 5, 40)
+    out = api.qualityAlign(ReadSet.from_strings(seqs, quals), ref, gapOpening=4, gapExtension=1)
+    exp = port.general_align(seqs, quals, enc, 4, 1, ref.upper())
+    assert np.array_equal(out["score"], exp[0]) and np.array_equal(out["edit"], exp[1])
+    assert out["reference"].tolist() == exp[2] and out["query"].tolist() == exp[3]
+    # batching invariance (tests/testthat/test-general-align.R:81-93)
+    half = api.qualityAlign(ReadSet.from_strings(seqs[:60], quals[:60]), ref, gapOpening=4, gapExtension=1)
+    assert np.array_equal(half["score"], out["score"][:60])
+
+
+def test_full_size_properties(port, enc):
+    """At production scale the oracle cannot check everything; check size-independent properties on 200k reads
+    (2 x 200k windows x 4 alignments) and a strided sample against the oracle."""
+    from sarlacc_b200 import native, synth
+    n = 200000
+    front, back, widths, flips = synth.mock_windows(n, VIGNETTE_A1, VIGNETTE_A2, seed=2000)
+    ss, se = [16, 42], [28, 46]
+    a = native.adaptor_align(front, enc, 5, 1, VIGNETTE_A1, ss, se)
+    # (1) score-only pass, resident pass and host-buffer pass agree bit for bit (batching / path invariance)
+    assert np.array_equal(native.adaptor_align_score_only(front, enc, 5, 1, VIGNETTE_A1), a[0])
+    r = native.Resident(front, enc)
+    r.align(r.MODE_TRACE_LOCAL, 5, 1, VIGNETTE_A1, ss, se)
+    b = r.fetch()
+    r.close()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    for s in range(2):
+        assert np.array_equal(a[3][s], b[3][s]) and np.array_equal(a[4][s], b[4][s])
+    # (2) coordinate invariants: 1 <= start <= end <= 250 when aligned; sections lie inside the window and are ordered
+    ok = a[1] > 0
+    assert np.all(a[1][ok] <= a[2][ok]) and np.all(a[2] <= 250)
+    for s in range(2):
+        assert np.all(a[3][s] >= 1) and np.all(a[3][s] - 1 + a[4][s] <= 250) and np.all(a[4][s] >= 0)
+    assert np.all(a[3][0] - 1 + a[4][0] <= a[3][1] - 1 + np.maximum(a[4][1], 0) + 250 * 0 + 250)  # barcode run ends before the window does
+    # (3) un-flipped reads carry adaptor1 at the front: high score, start near 1, 12-base barcode, 4-base UMI mostly
+    fwd = ~flips
+    assert np.median(a[0][fwd]) > 40 and np.median(a[1][fwd]) == 1
+    assert np.mean(a[4][0][fwd] == 12) > 0.7 and np.mean(a[4][1][fwd] == 4) > 0.8
+    assert np.median(a[0][flips]) < 10
+    # (4) strided sample against the oracle
+    idx = np.arange(0, n, 97)
+    sub = front[idx]
+    exp = port.adaptor_align(sub.seq_strings(), sub.qual_strings(), enc, 5, 1, VIGNETTE_A1, ss, se, nthreads=8)
+    assert np.array_equal(a[0][idx], exp[0]) and np.array_equal(a[1][idx], exp[1]) and np.array_equal(a[2][idx], exp[2])
+    for s in range(2):
+        assert np.array_equal(a[3][s][idx], exp[3][s]) and np.array_equal(a[4][s][idx], exp[4][s])

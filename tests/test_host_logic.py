@@ -1,0 +1,158 @@
+"""CPU-only: the host-side mirror of the R drivers (sarlacc_b200/api.py, reads.py, synth.py) against the loop
+restatement in oracle/r_level.py and the reference tests' literal answers.  Nothing here launches a kernel."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import VIGNETTE_A1, VIGNETTE_A2
+
+
+def test_setup_subseqs():
+    from sarlacc_b200 import api
+    # tests/testthat/test-adaptor-align.R:125-127
+    for ad, st, en in [("AAAAGGNNNNCCTTTT", [7], [10]), ("AAAAGGYYYYCCTTTT", [7], [10]), ("AAAAGGNNNNCCRRRR", [7, 13], [10, 16]), ("ACGT", [], [])]:
+        out = api._setup_subseqs(ad)
+        assert out["starts"].tolist() == st and out["ends"].tolist() == en
+    out = api._setup_subseqs(VIGNETTE_A1)
+    assert out["starts"].tolist() == [17, 43] and out["ends"].tolist() == [28, 46]
+
+
+def test_front_and_back_windows():
+    """tests/testthat/test-adaptor-align.R:130-139 incl. tolerance > read length."""
+    from sarlacc_b200 import api, ReadSet
+    from oracle import r_level as R
+    rng = np.random.default_rng(1)
+    seqs = ["".join(rng.choice(list("ACGTN"), size=int(n))) for n in rng.integers(0, 60, size=50)]
+    quals = ["".join(chr(33 + int(q)) for q in rng.integers(0, 60, size=len(s))) for s in seqs]
+    rs = ReadSet.from_strings(seqs, quals, ["r%d" % i for i in range(len(seqs))])
+    for tol in (5, 20, 100):
+        w = api._get_front_and_back(rs, tol)
+        f, b = R.get_front_and_back(seqs, quals, tol)
+        assert w["front"].seq_strings() == [x[0] for x in f] and w["front"].qual_strings() == [x[1] for x in f]
+        assert w["back"].seq_strings() == [x[0] for x in b] and w["back"].qual_strings() == [x[1] for x in b]
+
+
+def test_readset_ops():
+    from sarlacc_b200 import ReadSet
+    from sarlacc_b200.api import _readset_where
+    a = ReadSet.from_strings(["ACGT", "", "GGGTTT"], ["1234", "", "abcdef"], ["x", "y", "z"])
+    assert a.width().tolist() == [4, 0, 6]
+    assert a.reverse_complement().seq_strings() == ["ACGT", "", "AAACCC"]
+    assert a.reverse_complement().qual_strings() == ["4321", "", "fedcba"]
+    s = a.subseq(start=[2, 1, 3], width=[2, 0, 4])
+    assert s.seq_strings() == ["CG", "", "GTTT"] and s.qual_strings() == ["23", "", "cdef"]
+    assert a.subseq(end=[4, 0, 6], width=[1, 0, 2]).seq_strings() == ["T", "", "TT"]
+    with pytest.raises(ValueError):
+        a.subseq(start=[1, 1, 1], width=[5, 0, 1])
+    sub = a[np.array([True, False, True])]
+    assert sub.seq_strings() == ["ACGT", "GGGTTT"] and sub.names == ["x", "z"]
+    b = ReadSet.from_strings(["TT", "A", "C"], ["!!", "#", "$"])
+    w = _readset_where(np.array([True, False, True]), a, b)
+    assert w.seq_strings() == ["ACGT", "A", "GGGTTT"] and w.qual_strings() == ["1234", "#", "abcdef"]
+    c = ReadSet.concat([a, b])
+    assert c.seq_strings() == ["ACGT", "", "GGGTTT", "TT", "A", "C"]
+    assert len(ReadSet.empty()) == 0
+
+
+def test_fastq_round_trip(tmp_path):
+    from sarlacc_b200 import ReadSet, read_fastq, write_fastq
+    a = ReadSet.from_strings(["ACGT", "GGGTTT", "A"], ["1234", "abcdef", "~"], ["r1", "r2 extra", "r3"])
+    p = str(tmp_path / "x.fastq")
+    write_fastq(p, a)
+    chunks = list(read_fastq(p, number=2))
+    assert [len(c) for c in chunks] == [2, 1]
+    back = ReadSet.concat(chunks)
+    assert back.seq_strings() == a.seq_strings() and back.qual_strings() == a.qual_strings() and back.names == a.names
+    open(str(tmp_path / "empty.fastq"), "w").close()
+    assert list(read_fastq(str(tmp_path / "empty.fastq"), 10)) == []
+
+
+def test_resolve_strand_and_thresholds():
+    from sarlacc_b200 import api
+    from oracle import r_level as R
+    rng = np.random.default_rng(3)
+    s = [rng.normal(5, 10, size=200) for _ in range(4)]
+    s[2][:50] = s[0][:50]
+    s[3][:50] = s[1][:50]          # exact ties: fscore == rscore -> not reversed (strict <)
+    out = api._resolve_strand(*s)
+    rev, final = R.resolve_strand(*s)
+    assert out["reversed"].tolist() == rev and np.array_equal(out["scores"], np.array(final))
+    assert not out["reversed"][:50].any()
+    for trial in range(30):
+        real = np.round(rng.normal(30, 10, size=int(rng.integers(1, 80))), 1)
+        scr = np.round(rng.normal(10, 8, size=int(rng.integers(1, 80))), 1)
+        for err in (0.0, 0.01, 0.2, 1.0):
+            a = api._compute_threshold(real, scr, err)
+            b = R.compute_threshold(real.tolist(), scr.tolist(), err)
+            assert (np.isnan(a) and np.isnan(b)) or a == b
+    assert np.isnan(api._compute_threshold([1.0], [5.0], 0.01))
+
+
+def test_tied_overlap_known_answers():
+    """tests/testthat/test-tuning.R:53-59."""
+    from sarlacc_b200.api import _tied_overlap
+    x = np.arange(1, 11, dtype=float)
+    assert _tied_overlap(x, x - 10) == 1
+    assert _tied_overlap(x, x) == 0.5
+    assert _tied_overlap(x, x - 0.5) == pytest.approx(0.55)
+    assert _tied_overlap(x, x + 0.5) == pytest.approx(0.45)
+    assert _tied_overlap(x, x + 10) == 0
+
+
+def test_parallelize_matches_r_rule():
+    """R/adaptorAlign.R:126-134: bounds <- seq(1, n, length.out=w+1); ids <- findInterval(seq_len(n), head(bounds,-1))."""
+    from sarlacc_b200.api import _parallelize
+    for n, w in [(10, 1), (10, 3), (7, 4), (100, 8), (3, 8)]:
+        chunks = _parallelize(n, w)
+        flat = np.concatenate(chunks)
+        assert flat.tolist() == list(range(n))
+        bounds = np.linspace(1, n, w + 1)[:-1]
+        ids = [int(np.sum(bounds <= i)) for i in range(1, n + 1)]
+        assert [len(c) for c in chunks] == [ids.count(k) for k in sorted(set(ids))]
+    assert _parallelize(0, 4) == []
+
+
+def test_scramble_is_a_joint_permutation_and_shard_independent():
+    from sarlacc_b200 import api, ReadSet
+    rng = np.random.default_rng(5)
+    seqs = ["".join(rng.choice(list("ACGT"), size=int(n))) for n in rng.integers(0, 80, size=40)]
+    quals = ["".join(chr(40 + (i % 50)) for i in range(len(s))) for s in seqs]
+    rs = ReadSet.from_strings(seqs, quals)
+    a = api._scramble_input(rs, True, seed=7, first_index=100, stream=0)
+    for s, q, s2, q2 in zip(seqs, quals, a.seq_strings(), a.qual_strings()):
+        assert sorted(zip(s, q)) == sorted(zip(s2, q2))          # bases and qualities move together
+    assert a.seq_strings() != seqs
+    b = api._scramble_input(rs, True, seed=7, first_index=100, stream=0)
+    assert a.seq_strings() == b.seq_strings()
+    # chunk [10:30) scrambled on its own with the right first_index gives the same strings
+    part = api._scramble_input(rs[np.arange(10, 30)], True, seed=7, first_index=110, stream=0)
+    assert part.seq_strings() == a.seq_strings()[10:30] and part.qual_strings() == a.qual_strings()[10:30]
+    assert api._scramble_input(rs, True, seed=8, first_index=100).seq_strings() != a.seq_strings()
+    assert api._scramble_by_index(rs, 7, 100 + np.arange(len(rs)), 0).seq_strings() == a.seq_strings()
+
+
+def test_synthetic_reads_are_shard_independent_and_shaped_like_mockreads():
+    from sarlacc_b200 import synth
+    f, b, w, fl = synth.mock_windows(3000, VIGNETTE_A1, VIGNETTE_A2, seed=2000, block=1000)
+    assert len(f) == 3000 and set(f.width().tolist()) == {250} and set(b.width().tolist()) == {250}
+    f2, b2, w2, fl2 = synth.mock_windows(1000, VIGNETTE_A1, VIGNETTE_A2, seed=2000, first_index=1000, block=1000)
+    assert f2.seq_strings() == f.seq_strings()[1000:2000] and b2.qual_strings() == b.qual_strings()[1000:2000]
+    assert 0.4 < fl.mean() < 0.6
+    q = f.qual_pool.astype(int) - 33
+    assert q.min() >= 12 and q.max() <= 93                       # -10 log10 U(0, 0.06) >= 12.2
+    # un-flipped reads start with adaptor1 (up to 5% substitutions / 1% indels): the constant prefix mostly survives
+    s = f.seq_strings()
+    hits = sum(1 for i in range(3000) if not fl[i] and s[i].startswith("ACGCAG"))
+    assert hits > 0.6 * (~fl).sum()
+    assert abs(w.mean() - (70 + 4908 + 22) * 1.018) < 10
+    r = synth.mock_reads(20, VIGNETTE_A1, VIGNETTE_A2, seed=1)
+    assert len(r) == 20 and r.width().min() > 400
+
+
+def test_encoding_vector():
+    from sarlacc_b200 import api
+    names, err = api._create_encoding_vector("PhredQuality")
+    assert names[0] == "!" and names[-1] == "~" and len(names) == 94
+    assert err[20] == 10.0 ** -2.0 and np.all(np.diff(err) <= 0)
+    assert api._qual2class("phred") == "PhredQuality" and api._qual2class("solexa") == "SolexaQuality"
