@@ -124,11 +124,13 @@ def _create_encoding_vector(qual_class="PhredQuality"):
     offset, lo, hi, kind = _QUAL_ENCODINGS[qual_class]
     qs = np.arange(lo, hi + 1)
     names = [chr(offset + int(q)) for q in qs]
+    # scalar libm pow per entry (not numpy's vectorised pow, which may differ in the last bit): the table must be
+    # the same numbers whoever builds it, since scores are compared bit for bit
     if kind == "phred":
-        err = 10.0 ** (-qs / 10.0)
+        err = np.array([10.0 ** (-int(q) / 10.0) for q in qs], dtype=np.float64)
     else:
-        err = 1.0 - 1.0 / (1.0 + 10.0 ** (-qs / 10.0))
-    return names, err.astype(np.float64)
+        err = np.array([1.0 - 1.0 / (1.0 + 10.0 ** (-int(q) / 10.0)) for q in qs], dtype=np.float64)
+    return names, err
 
 
 def _setup_subseqs(adaptor):

@@ -264,10 +264,8 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
                     F[k] = NEG;                                   /* up_jump_score, :122 */
                 }
                 diag0 = row0s[cfirst - 1];                        /* H[0][cfirst-1] */
-                if (nref > 1) {
-                    load_slots(b);
-                    if (b == 0) { best = NEG; nextb = NEG; bid = 0; }
-                }
+                if (nref > 1) load_slots(b);
+                if (b == 0) { best = NEG; nextb = NEG; bid = 0; }
             }
         }
 
@@ -296,9 +294,9 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
         if (act && i == len && j == G - 1) {
             const double s = S[C - 1];
             if (A.score) A.score[(long long)b * A.n + a] = s;
-            if (nref > 1) {
+            if (A.best_id) {
                 update_best(s, b + 1, best, nextb, bid);
-                if (b == nref - 1 && A.best_id) {
+                if (b == nref - 1) {
                     A.best_id[a] = bid;
                     A.best[a] = best;
                     A.next_best[a] = nextb;
@@ -394,9 +392,9 @@ __global__ void __launch_bounds__(128) generic_forward(const AlignArgs A, const 
             }
             const double s = gS[(long long)len * T];
             if (A.score) A.score[(long long)b * A.n + a] = s;
-            if (A.nref > 1) update_best(s, b + 1, best, nextb, bid);
+            if (A.best_id) update_best(s, b + 1, best, nextb, bid);
         }
-        if (A.nref > 1 && A.best_id) {
+        if (A.best_id) {
             A.best_id[a] = bid;
             A.best[a] = best;
             A.next_best[a] = nextb;
@@ -414,10 +412,10 @@ __global__ void fill_empty(const AlignArgs A)
     for (int b = 0; b < A.nref; ++b) {
         if (A.score) A.score[(long long)b * A.n + a] = s;
     }
-    if (A.nref > 1 && A.best_id) {
+    if (A.best_id) {
         A.best_id[a] = 1;
         A.best[a] = s;
-        A.next_best[a] = s;   /* second barcode ties: not > best, but > -Inf */
+        A.next_best[a] = A.nref > 1 ? s : neg_inf();   /* a second barcode ties: not > best, but > -Inf */
     }
 }
 
