@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsarlacc_b200.so")
+LIB_PATH = os.environ.get("SARLACC_LIB") or os.path.join(HERE, "libsarlacc_b200.so")   # override: A/B builds of the same library
 
 SEQ_ASCII = 0
 SEQ_BIOSTRINGS = 1

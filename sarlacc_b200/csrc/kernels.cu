@@ -44,9 +44,19 @@ struct FlagWord {
     using type = typename std::conditional<(C <= 8), uint32_t, unsigned long long>::type;
 };
 
+#ifndef SARLACC_WF_STEP_UNROLL
+#define SARLACC_WF_STEP_UNROLL 4   /* rows per trip of the inner loop: lets ptxas rename loop-carried state instead of moving it (profiles/) */
+#endif
+constexpr int kStepUnroll = SARLACC_WF_STEP_UNROLL;
+#ifndef SARLACC_WF_BLOCKS_SMALL
+#define SARLACC_WF_BLOCKS_SMALL 4   /* resident 128-thread blocks per SM for C <= 9 (register cap 128) */
+#endif
+#ifndef SARLACC_WF_BLOCKS_LARGE
+#define SARLACC_WF_BLOCKS_LARGE 4   /* C >= 10: 4 blocks (cap 128 registers) measured faster than 3 (cap 168) */
+#endif
 template <int C>
 struct WfBounds {
-    static constexpr int min_blocks = (C <= 9) ? 4 : 3;
+    static constexpr int min_blocks = (C <= 9) ? SARLACC_WF_BLOCKS_SMALL : SARLACC_WF_BLOCKS_LARGE;
 };
 
 /* R/barcodeAlign.R:28-34: strict `>` for best, then strict `>` for next best. */
@@ -281,7 +291,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
         const uint16_t* keep_rowp = rowp;
         const int keep_i = i;
         if (!act) { rowp = A.rows; i = 1; }
-#pragma unroll 1
+#pragma unroll kStepUnroll
         for (int s = 0; s < steps; ++s) {
             /* Left boundary of this row: what lane j-1 produced one step ago. */
             const double Sl = __shfl_up_sync(FULL, outS, 1, G);
@@ -433,15 +443,15 @@ struct FlagReader {
     const TraceArgs& T;
     long long a;
     int len;
+    const int* colinfo;   /* wavefront layout: per DP column, (word offset j*(G+1)) << 8 | (bit shift 4k) */
     __device__ unsigned get(int i, int c) const {
         if (T.layout == 0) {
-            int j, k;
-            wf_locate(c, T.C, T.G * T.C - T.L, &j, &k);
-            const long long w = a * T.fstride + (long long)(i + j) * T.G + j;
+            const int ci = colinfo[c];
+            const long long w = a * T.fstride + (long long)i * T.G + (ci >> 8);
             if (T.wordbytes == 4) {
-                return (reinterpret_cast<const uint32_t*>(T.flags)[w] >> (4 * k)) & 15u;
+                return (reinterpret_cast<const uint32_t*>(T.flags)[w] >> (ci & 0xff)) & 15u;
             }
-            return (unsigned)((reinterpret_cast<const unsigned long long*>(T.flags)[w] >> (4 * k)) & 15ull);
+            return (unsigned)((reinterpret_cast<const unsigned long long*>(T.flags)[w] >> (ci & 0xff)) & 15ull);
         }
         return reinterpret_cast<const uint8_t*>(T.flags)[a * T.fstride + (long long)(c - 1) * len + (i - 1)];
     }
@@ -455,12 +465,22 @@ struct FlagReader {
 
 __global__ void __launch_bounds__(128) traceback(const TraceArgs T)
 {
+    extern __shared__ int tb_colinfo[];
+    if (T.layout == 0) {
+        const int pad = T.G * T.C - T.L;
+        for (int c = 1 + threadIdx.x; c <= T.L; c += blockDim.x) {
+            int j, k;
+            wf_locate(c, T.C, pad, &j, &k);
+            tb_colinfo[c] = ((j * (T.G + 1)) << 8) | (4 * k);
+        }
+        __syncthreads();
+    }
     const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= T.n) return;
     const int L = T.L;
     const int len = T.lens[a];
     const long long n = T.n;
-    FlagReader R{T, a, len};
+    FlagReader R{T, a, len, tb_colinfo};
     int32_t* map = T.map + a;        /* map[c*n]: (row << 1) | is_match, fill_map's mapping (:280-305) */
     uint8_t* ops = T.ops ? T.ops + a * T.ops_stride : nullptr;
     int nops = 0;
@@ -601,7 +621,7 @@ const char* launch_generic(const AlignArgs& a, bool trace, int grid, cudaStream_
 void launch_traceback(const TraceArgs& t, cudaStream_t st) {
     const int block = 128;
     const int grid = (int)((t.n + block - 1) / block);
-    if (grid > 0) traceback<<<grid, block, 0, st>>>(t);
+    if (grid > 0) traceback<<<grid, block, sizeof(int) * ((size_t)t.L + 1), st>>>(t);
 }
 
 void launch_fill_empty(const AlignArgs& a, cudaStream_t st) {
