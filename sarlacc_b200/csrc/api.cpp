@@ -702,6 +702,49 @@ OutLayout make_layout(Mode mode, long long n, int nref_scores, int nsec, int max
     return o;
 }
 
+/* Per-device resources kept between host-buffer calls.  One call at a time per device (the R boundary is
+ * single-threaded; concurrent callers serialise on the device's mutex). */
+struct DeviceCache {
+    std::mutex busy;
+    bool ready = false;
+    Slot slots[2];
+    DevPlan plan;
+
+    static DeviceCache& acquire(int device) {
+        static std::mutex table_mutex;
+        static std::vector<std::unique_ptr<DeviceCache> > table;
+        DeviceCache* c = nullptr;
+        {
+            std::lock_guard<std::mutex> lock(table_mutex);
+            if ((int)table.size() <= device) table.resize(device + 1);
+            if (!table[device]) table[device].reset(new DeviceCache());
+            c = table[device].get();
+        }
+        c->busy.lock();
+        if (!c->ready) {
+            try {
+                c->slots[0].init();
+                c->slots[1].init();
+            } catch (...) {
+                c->busy.unlock();
+                throw;
+            }
+            c->ready = true;
+        }
+        c->slots[0].busy = false;
+        c->slots[1].busy = false;
+        return *c;
+    }
+    void release() {
+        /* make sure nothing of this call is still in flight before another call reuses the buffers */
+        if (ready) {
+            cudaStreamSynchronize(slots[0].st);
+            cudaStreamSynchronize(slots[1].st);
+        }
+        busy.unlock();
+    }
+};
+
 /* Runs [lo,hi) of the reads on one device with a two-slot pipeline: pack chunk k+1 on the host while the
  * device works on chunk k. */
 struct DeviceJob {
@@ -738,14 +781,15 @@ struct DeviceJob {
         const int nsec = (int)P.sec_starts.size();
         const int nref_scores = (mode == MODE_MULTI_GLOBAL) ? (want_all_scores ? P.nref : 0) : 1;
 
-        Slot slots[2];
-        DevPlan D;
-        struct Cleanup {
-            Slot* s; DevPlan* d;
-            ~Cleanup() { s[0].destroy(); s[1].destroy(); d->buf.release(); }
-        } cleanup{slots, &D};
-        slots[0].init();
-        slots[1].init();
+        /* Streams, pinned staging, device buffers and scratch are cached per device across calls
+         * (cudaMallocHost / cudaMalloc / cudaFree of hundreds of MB per call would dominate short calls). */
+        DeviceCache& cache = DeviceCache::acquire(device);
+        struct Release {
+            DeviceCache& c;
+            ~Release() { c.release(); }
+        } release{cache};
+        Slot* slots = cache.slots;
+        DevPlan& D = cache.plan;
         D.upload(P, slots[0].st);
 
         /* chunk size: bounded so that staging stays modest and the trace scratch fits its budget */
