@@ -485,33 +485,55 @@ __global__ void __launch_bounds__(128) traceback(const TraceArgs T)
     uint8_t* ops = T.ops ? T.ops + a * T.ops_stride : nullptr;
     int nops = 0;
 
-    int i = len, c = L;
+    /* Flat three-state walk, one record read and one move per iteration (keeps the warp's lanes in step):
+     *   ST_H  look at the cell's own choice;
+     *   ST_E  inside a horizontal run: the move into this cell was "left", and whether the run continues was
+     *         decided by the p1 bit of the cell we came from AND this cell not having chosen "left" itself
+     *         (then its own choice says "left" again anyway) -- resolved when this cell's record is read;
+     *   ST_F  same for vertical runs with p2 / "up". */
+    enum { ST_H = 0, ST_E = 1, ST_F = 2 };
+    int i = len, c = L, state = ST_H;
+    bool pending = false;   /* p1 (in ST_E) / p2 (in ST_F) of the cell the current run came from */
     while (c > 0) {
-        const int ch = R.choice(i, c);
-        if (ch == CH_DIAG) {
+        unsigned f;
+        int ch;
+        if (i == 0) {          /* row 0: +1 (:118), never an extension */
+            f = 0;
+            ch = CH_LEFT;
+        } else {
+            f = R.get(i, c);
+            ch = (f & 1u) ? CH_DIAG : ((f & 2u) ? CH_LEFT : CH_UP);
+        }
+        int move;
+        if (i == 0) {
+            move = CH_LEFT;    /* the reference's runs stop at row 0 / column 0 regardless of the extend bit */
+        } else if (state == ST_E && pending && ch != CH_LEFT) {
+            move = CH_LEFT;    /* the horizontal run passes through this cell whatever it chose */
+        } else if (state == ST_F && pending && ch != CH_UP) {
+            move = CH_UP;
+        } else {
+            move = ch;
+        }
+        if (move == CH_DIAG) {
             map[(long long)c * n] = (i << 1) | 1;
             if (ops) ops[nops] = 'M';
             ++nops;
             --i;
             --c;
-        } else if (ch == CH_LEFT) {
-            for (;;) {
-                map[(long long)c * n] = ((i + 1) << 1);
-                if (ops) ops[nops] = 'D';
-                ++nops;
-                bool ext = false;
-                if (i > 0) ext = (R.get(i, c) & 4u) && R.choice(i, c - 1) != CH_LEFT;
-                --c;
-                if (!ext || c == 0) break;
-            }
+            state = ST_H;
+        } else if (move == CH_LEFT) {
+            map[(long long)c * n] = ((i + 1) << 1);
+            if (ops) ops[nops] = 'D';
+            ++nops;
+            pending = (f & 4u) != 0;
+            --c;
+            state = ST_E;
         } else {
-            for (;;) {
-                if (ops) ops[nops] = 'I';
-                ++nops;
-                const bool ext = (R.get(i, c) & 8u) && R.choice(i - 1, c) != CH_UP;
-                --i;
-                if (!ext || i == 0) break;
-            }
+            if (ops) ops[nops] = 'I';
+            ++nops;
+            pending = (f & 8u) != 0;
+            --i;
+            state = ST_F;
         }
     }
     while (i > 0) {   /* leading read bases, consumed at column 0 (:273-276) */
