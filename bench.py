@@ -266,13 +266,19 @@ def main():
         sub_b = back if ne == n else back[np.arange(ne)]
         _lib.lib.sarlacc_set_devices((_lib.C.c_int * 1)(dev), 1)
 
+        sub_w = widths[:ne].astype(np.int32)
+
         def e2e_step():
+            # .align_AA_internal + adaptor2 flip in one C-ABI call: windows packed and uploaded once, four alignments
+            # with traceback, strand resolution and row selection on the device, selected rows copied back
+            return native.adaptor_align_windows(sub_f, sub_b, enc, GO, GE, A1, A2, (s1, e1), (s2, e2), read_width=sub_w)
+
+        def e2e_step_unfused():
             a = native.adaptor_align(sub_f, enc, GO, GE, A1, s1, e1)
             b = native.adaptor_align(sub_b, enc, GO, GE, A2, s2, e2)
             c = native.adaptor_align(sub_b, enc, GO, GE, A1, s1, e1)
             d = native.adaptor_align(sub_f, enc, GO, GE, A2, s2, e2)
-            rev = resolve_strand(a[0], b[0], c[0], d[0])
-            return rev
+            return resolve_strand(a[0], b[0], c[0], d[0])
 
         e2e_step()
         barrier()
@@ -284,11 +290,18 @@ def main():
         torch.cuda.synchronize()
         dt = max_over_ranks((time.perf_counter() - t0) / reps)
         stride = (TOL + 8) & ~7
-        h2d = 4 * (ne * stride * 2 + ne * 4)
-        d2h = 2 * ne * (8 + 4 + 4 + 8 * len(s1)) + 2 * ne * (8 + 4 + 4 + 8 * len(s2))
+        h2d = 2 * (ne * stride * 2 + ne * 4) + ne * 4
+        d2h = ne * (1 + (8 + 4 + 4 + 8 * len(s1)) + (8 + 4 + 4 + 8 * len(s2)))
+        t0 = time.perf_counter()
+        e2e_step_unfused()
+        torch.cuda.synchronize()
+        dt_unfused = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": world * ne / dt, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "reads_per_step": ne, "ms_per_step": dt * 1000.0,
-               "path": "4 x sarlacc_adaptor_align (host CSR buffers -> pack -> pinned -> H2D -> kernels -> D2H) + .resolve_strand"}
+               "path": "sarlacc_adaptor_align_windows: host CSR buffers -> pack -> pinned -> H2D -> 4 alignments + traceback + "
+                       "strand resolution/selection on device -> D2H of the kept rows",
+               "unfused_reads_per_s": world * ne / dt_unfused,
+               "unfused_path": "4 x sarlacc_adaptor_align (the reference's four .Calls) + .resolve_strand on the host"}
 
     # ------------------------------------------------------------------ cpu baseline (rank 0, N = 1 only)
     cpu = None

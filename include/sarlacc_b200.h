@@ -117,6 +117,22 @@ int sarlacc_barcode_align_multi(const sarlacc_reads* reads, const sarlacc_encodi
         double gapopen, double gapext, const char* const* barcodes, int nbarcodes,
         int32_t* best_id, double* best, double* next_best, double* all_scores);
 
+/* ---- fused extension: both adaptors on both read ends ---------------------------------------------
+ * Replaces the body of .align_AA_internal (R/adaptorAlign.R:178-199: four adaptor_align calls -- (adaptor1, front),
+ * (adaptor2, back), (adaptor1, back), (adaptor2, front) --, .resolve_strand (:112-122) and the per-row selection
+ * cur.starts[rev,] <- cur.rc.starts[rev,]) plus adaptorAlign's adaptor2 coordinate flip width - x + 1 (:66-71,
+ * applied when read_width != NULL).  `front` / `back` are the windows .get_front_and_back (:86-95) produced (the
+ * back one already reverse-complemented), element i of both belonging to read i.  Outputs are the rows R keeps:
+ * reversed[n] (0/1), and for adaptor k the score / start / end / [nsec_k][n] section starts and widths of the
+ * alignment on the selected window.  Results are identical to composing the four calls (tests/test_gpu_api.py). */
+int sarlacc_adaptor_align_windows(const sarlacc_reads* front, const sarlacc_reads* back, const sarlacc_encoding* encoding,
+        double gapopen, double gapext, const char* adaptor1, const char* adaptor2,
+        int nsec1, const int32_t* sec_starts1, const int32_t* sec_ends1,
+        int nsec2, const int32_t* sec_starts2, const int32_t* sec_ends2,
+        const int32_t* read_width, uint8_t* reversed,
+        double* score1, int32_t* start1, int32_t* end1, int32_t* sec_start1, int32_t* sec_width1,
+        double* score2, int32_t* start2, int32_t* end2, int32_t* sec_start2, int32_t* sec_width2);
+
 /* ---- resident read windows -----------------------------------------------------------------------
  * Packs the reads once (2 bytes per base: quality index + one-hot base), uploads them and keeps them
  * in HBM.  The *_resident calls then run on that copy; results stay on the device until fetched.

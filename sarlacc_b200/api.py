@@ -198,6 +198,29 @@ def _align_AA_internal(reads, adaptor1, adaptor2, tolerance, subseq1, subseq2, g
     return {"names": reads.names, "width": reads.width(), "start": cur_starts, "end": cur_ends, "reversed": is_reverse}
 
 
+def _align_AA_internal_fused(reads, adaptor1, adaptor2, tolerance, subseq1, subseq2, gap_opening, gap_extension, encoding=None):
+    """_align_AA_internal with the four .Calls, .resolve_strand and the row selection done in one device pass
+    (sarlacc_adaptor_align_windows).  Same return value."""
+    enc = encoding or native.phred_encoding()
+    w = _get_front_and_back(reads, tolerance)
+    rev, r1, r2 = native.adaptor_align_windows(
+        w["front"], w["back"], enc, gap_opening, gap_extension, adaptor1, adaptor2,
+        (np.asarray(subseq1["starts"], dtype=np.int32) - 1, subseq1["ends"]),
+        (np.asarray(subseq2["starts"], dtype=np.int32) - 1, subseq2["ends"]))
+    # the sections were located on the window that was kept: front for adaptor1 / back for adaptor2, swapped if reversed
+    src = (_readset_where(rev, w["back"], w["front"]) if len(r1[3]) else None,
+           _readset_where(rev, w["front"], w["back"]) if len(r2[3]) else None)
+    frames = []
+    for out, windows in ((r1, src[0]), (r2, src[1])):
+        f = Frame({"score": out[0], "start": out[1], "end": out[2]})
+        seg = Frame(nrows=len(reads))
+        for i in range(len(out[3])):
+            seg["Sub%d" % (i + 1)] = windows.subseq(start=out[3][i], width=out[4][i])
+        f["subseq"] = seg
+        frames.append(f)
+    return {"names": reads.names, "width": reads.width(), "start": frames[0], "end": frames[1], "reversed": rev}
+
+
 def _stream(source, number):
     """FastqStreamer(filepath, n=number) + yield (R/adaptorAlign.R:26,36), or chunks of an in-memory ReadSet."""
     number = int(number)
@@ -214,9 +237,11 @@ def _stream(source, number):
 # exported functions
 # --------------------------------------------------------------------------------------------------
 def adaptorAlign(adaptor1, adaptor2, filepath, tolerance=250, gapOpening=5, gapExtension=1,
-                 qual_type="phred", number=1e5):
+                 qual_type="phred", number=1e5, fused=True):
     """R/adaptorAlign.R:7-78.  `filepath` is a FASTQ path or an in-memory ReadSet (names required for
-    getAdaptorThresholds).  Returns a Frame with read.width, adaptor1, adaptor2, reversed and the same metadata."""
+    getAdaptorThresholds).  Returns a Frame with read.width, adaptor1, adaptor2, reversed and the same metadata.
+    fused=True runs .align_AA_internal's four alignments + strand resolution in one device pass
+    (sarlacc_adaptor_align_windows); fused=False issues the reference's four .Calls.  Results are identical."""
     adaptor1 = str(adaptor1).upper()
     adaptor2 = str(adaptor2).upper()
     if qual_type not in ("phred", "solexa", "illumina"):
@@ -226,8 +251,9 @@ def adaptorAlign(adaptor1, adaptor2, filepath, tolerance=250, gapOpening=5, gapE
                     subseq1=_setup_subseqs(adaptor1), subseq2=_setup_subseqs(adaptor2),
                     gap_opening=gapOpening, gap_extension=gapExtension, encoding=enc)
     names, widths, starts, ends, revs = [], [], [], [], []
+    internal = _align_AA_internal_fused if fused else _align_AA_internal
     for reads in _stream(filepath, number):
-        out = _align_AA_internal(reads, **all_args)
+        out = internal(reads, **all_args)
         names.append(out["names"] if out["names"] is not None else [None] * len(reads))
         widths.append(out["width"])
         starts.append(out["start"])

@@ -652,6 +652,8 @@ struct Slot {
     cudaEvent_t done = nullptr;
     PinBuf h_rows, h_lens, h_out;
     DevBuf d_rows, d_lens, d_out;
+    PinBuf h_rows2, h_lens2, h_width;     /* second window set + read widths of the fused both-ends entry */
+    DevBuf d_rows2, d_lens2, d_width, d_tmp;
     Scratch scratch;
     long long n = 0;        /* reads in flight */
     int64_t lo = 0;
@@ -663,6 +665,8 @@ struct Slot {
     void destroy() {
         h_rows.release(); h_lens.release(); h_out.release();
         d_rows.release(); d_lens.release(); d_out.release();
+        h_rows2.release(); h_lens2.release(); h_width.release();
+        d_rows2.release(); d_lens2.release(); d_width.release(); d_tmp.release();
         scratch.release();
         if (done) cudaEventDestroy(done);
         if (st) cudaStreamDestroy(st);
@@ -923,6 +927,35 @@ double col0_host(bool local, double gop, double ge, int64_t i) {
     return -gop - ge * (double)(i - 1);
 }
 
+/* Unrecognized reference bases (src/reference_align.cpp:211) surface at the first read that has any base:
+ * column by column, so a bad quality in that read wins unless the very first column is the bad one
+ * (:184-217).  With several references the unfused R loop runs one .Call per barcode, so read errors (raised
+ * in the first call) win over a bad later barcode. */
+void apply_reference_errors(FirstError& err, const ReadView& V, int64_t n, const Plan& P, int nref) {
+    int bfirst = -1;
+    for (int b = 0; b < nref; ++b) {
+        if (P.bad_col[b] >= 0) { bfirst = b; break; }
+    }
+    if (bfirst < 0) return;
+    int64_t i0 = -1;
+    for (int64_t i = 0; i < n; ++i) {
+        if (V.seq_len(i) != V.qual_len(i)) break;
+        if (V.seq_len(i) > 0) { i0 = i; break; }
+    }
+    if (i0 < 0) return;
+    if (bfirst == 0) {
+        if (err.kind == ERR_NONE || err.at > i0) {
+            err.at = i0;
+            err.kind = ERR_REF;
+        } else if (err.at == i0 && P.bad_col[0] == 0) {
+            err.kind = ERR_REF;
+        }
+    } else if (err.kind == ERR_NONE) {
+        err.at = i0;
+        err.kind = ERR_REF;
+    }
+}
+
 /* Shared driver of all host-buffer entry points. */
 int run_host(const sarlacc_reads* reads, const sarlacc_encoding* encoding, double go, double ge,
         const char* const* refs, int nref, Mode mode, int nsec, const int32_t* sec_starts, const int32_t* sec_ends,
@@ -1012,39 +1045,218 @@ int run_host(const sarlacc_reads* reads, const sarlacc_encoding* encoding, doubl
     FirstError err;
     for (int d = 0; d < nd; ++d) err.merge(jobs[d].err);
 
-    /* Unrecognized reference bases (src/reference_align.cpp:211) surface at the first read that has any
-     * base: column by column, so a bad quality in that read wins unless the very first column is the bad
-     * one (:184-217).  With several references the unfused R loop runs one .Call per barcode, so read
-     * errors (raised in the first call) win over a bad later barcode. */
-    {
-        int bfirst = -1;
-        for (int b = 0; b < nref; ++b) {
-            if (P.bad_col[b] >= 0) { bfirst = b; break; }
-        }
-        if (bfirst >= 0) {
-            int64_t i0 = -1;
-            for (int64_t i = 0; i < n; ++i) {
-                if (V.seq_len(i) != V.qual_len(i)) break;
-                if (V.seq_len(i) > 0) { i0 = i; break; }
-            }
-            if (i0 >= 0) {
-                if (bfirst == 0) {
-                    if (err.kind == ERR_NONE || err.at > i0) {
-                        err.at = i0;
-                        err.kind = ERR_REF;
-                    } else if (err.at == i0 && P.bad_col[0] == 0) {
-                        err.kind = ERR_REF;
-                    }
-                } else if (err.kind == ERR_NONE) {
-                    err.at = i0;
-                    err.kind = ERR_REF;
-                }
-            }
-        }
-    }
+    apply_reference_errors(err, V, n, P, nref);
     if (err.kind != ERR_NONE) return fail(err_text(err.kind));
     return 0;
 }
+
+/* ---- fused both-ends entry ----------------------------------------------------------------------
+ * What .align_AA_internal (R/adaptorAlign.R:178-199) does with four .Calls -- (adaptor1, front), (adaptor2, back),
+ * (adaptor1, back), (adaptor2, front) -- plus .resolve_strand, the row selection and adaptorAlign's adaptor2
+ * coordinate flip (:66-71), in one pass: both window sets are packed and uploaded once, the four alignments run
+ * back to back on the device, and only the selected rows come back. */
+struct PairOutputs {
+    uint8_t* reversed;
+    double* score[2];
+    int32_t* start[2];
+    int32_t* end[2];
+    int32_t* sec_start[2];
+    int32_t* sec_width[2];
+};
+
+struct TmpLayout {   /* four result sets: a1/front, a2/back, a1/back, a2/front */
+    size_t o_score[4], o_start[4], o_end[4], o_ss[4], o_sw[4], total;
+};
+
+struct FinalLayout {
+    size_t o_rev, o_score[2], o_start[2], o_end[2], o_ss[2], o_sw[2], total;
+};
+
+struct PairJob {
+    int device = 0;
+    int64_t lo = 0, hi = 0, n_total = 0;
+    const sarlacc_reads* front = nullptr;
+    const sarlacc_reads* back = nullptr;
+    const Plan* plan[2] = {nullptr, nullptr};   /* adaptor1, adaptor2 */
+    const int32_t* width = nullptr;
+    PairOutputs out;
+    int nthreads = 1;
+    FirstError err_front, err_back;
+    std::string cuda_error;
+
+    void run() {
+        try {
+            run_inner();
+        } catch (CudaError& e) {
+            cuda_error = e.msg;
+        } catch (std::exception& e) {
+            cuda_error = std::string("internal error: ") + e.what();
+        }
+    }
+
+    void run_inner() {
+        CUDA_CHECK(cudaSetDevice(device));
+        const int sms = device_sm_count(device);
+        ReadView VF{front}, VB{back};
+        PackTables PF, PB;
+        build_pack_tables(PF, front->seq_encoding, *plan[0]->enc);
+        build_pack_tables(PB, back->seq_encoding, *plan[0]->enc);
+        const int nsec[2] = {(int)plan[0]->sec_starts.size(), (int)plan[1]->sec_starts.size()};
+        DeviceCache& cache = DeviceCache::acquire(device);
+        struct Release {
+            DeviceCache& c;
+            ~Release() { c.release(); }
+        } release{cache};
+        Slot* slots = cache.slots;
+        DevPlan D[2];
+        struct FreePlans {
+            DevPlan* d;
+            ~FreePlans() { d[0].buf.release(); d[1].buf.release(); }
+        } free_plans{D};
+        D[0].upload(*plan[0], slots[0].st);
+        D[1].upload(*plan[1], slots[0].st);
+
+        long long chunk = 1 << 17;
+        const char* ce = std::getenv("SARLACC_CHUNK");
+        if (ce && std::atoll(ce) > 0) chunk = std::atoll(ce);
+        auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        FinalLayout lay[2];
+        int which = 0;
+
+        auto drain = [&](Slot& s, const FinalLayout& o) {
+            if (!s.busy) return;
+            CUDA_CHECK(cudaEventSynchronize(s.done));
+            const uint8_t* h = s.h_out.as<uint8_t>();
+            const long long m = s.n;
+            const int64_t g0 = s.lo;
+            std::memcpy(out.reversed + g0, h + o.o_rev, (size_t)m);
+            for (int k = 0; k < 2; ++k) {
+                std::memcpy(out.score[k] + g0, h + o.o_score[k], sizeof(double) * m);
+                std::memcpy(out.start[k] + g0, h + o.o_start[k], sizeof(int32_t) * m);
+                std::memcpy(out.end[k] + g0, h + o.o_end[k], sizeof(int32_t) * m);
+                for (int sct = 0; sct < nsec[k]; ++sct) {
+                    std::memcpy(out.sec_start[k] + (size_t)sct * n_total + g0, h + o.o_ss[k] + sizeof(int32_t) * (size_t)sct * m, sizeof(int32_t) * m);
+                    std::memcpy(out.sec_width[k] + (size_t)sct * n_total + g0, h + o.o_sw[k] + sizeof(int32_t) * (size_t)sct * m, sizeof(int32_t) * m);
+                }
+            }
+            s.busy = false;
+        };
+
+        for (int64_t c0 = lo; c0 < hi;) {
+            Slot& s = slots[which];
+            drain(s, lay[which]);
+            int64_t c1 = std::min<int64_t>(hi, c0 + chunk);
+            s.h_lens.reserve(sizeof(int32_t) * (size_t)(c1 - c0));
+            s.h_lens2.reserve(sizeof(int32_t) * (size_t)(c1 - c0));
+            int maxf = 0, maxb = 0;
+            scan_lengths(VF, c0, c1, s.h_lens.as<int32_t>(), nthreads, err_front, maxf);
+            scan_lengths(VB, c0, c1, s.h_lens2.as<int32_t>(), nthreads, err_back, maxb);
+            {
+                const int mx = std::max(maxf, maxb);
+                const long long fit = std::min(sub_chunk(*plan[0], mx, true, c1 - c0), sub_chunk(*plan[1], mx, true, c1 - c0));
+                if (fit < c1 - c0) {
+                    c1 = c0 + fit;
+                    maxf = maxb = 0;
+                    for (int64_t i = 0; i < c1 - c0; ++i) {
+                        maxf = std::max(maxf, (int)s.h_lens.as<int32_t>()[i]);
+                        maxb = std::max(maxb, (int)s.h_lens2.as<int32_t>()[i]);
+                    }
+                }
+            }
+            const long long m = c1 - c0;
+            const int stride_f = std::max(8, (maxf + 8) & ~7), stride_b = std::max(8, (maxb + 8) & ~7);
+            s.h_rows.reserve(sizeof(uint16_t) * (size_t)m * stride_f);
+            s.h_rows2.reserve(sizeof(uint16_t) * (size_t)m * stride_b);
+            pack_rows(VF, c0, c1, PF, s.h_lens.as<int32_t>(), stride_f, s.h_rows.as<uint16_t>(), nthreads, true, err_front);
+            pack_rows(VB, c0, c1, PB, s.h_lens2.as<int32_t>(), stride_b, s.h_rows2.as<uint16_t>(), nthreads, true, err_back);
+            if ((err_front.kind != ERR_NONE && err_front.at < c1) || (err_back.kind != ERR_NONE && err_back.at < c1)) break;
+
+            /* device buffers */
+            s.d_rows.reserve(sizeof(uint16_t) * (size_t)m * stride_f);
+            s.d_rows2.reserve(sizeof(uint16_t) * (size_t)m * stride_b);
+            s.d_lens.reserve(sizeof(int32_t) * (size_t)m);
+            s.d_lens2.reserve(sizeof(int32_t) * (size_t)m);
+            TmpLayout T;
+            size_t at = 0;
+            for (int r = 0; r < 4; ++r) {
+                const int ns = nsec[(r == 0 || r == 2) ? 0 : 1];
+                T.o_score[r] = at; at += al(sizeof(double) * m);
+                T.o_start[r] = at; at += al(sizeof(int32_t) * m);
+                T.o_end[r] = at; at += al(sizeof(int32_t) * m);
+                T.o_ss[r] = at; at += al(sizeof(int32_t) * m * std::max(1, ns));
+                T.o_sw[r] = at; at += al(sizeof(int32_t) * m * std::max(1, ns));
+            }
+            T.total = at;
+            FinalLayout F;
+            at = 0;
+            F.o_rev = at; at += al((size_t)m);
+            for (int k = 0; k < 2; ++k) {
+                F.o_score[k] = at; at += al(sizeof(double) * m);
+                F.o_start[k] = at; at += al(sizeof(int32_t) * m);
+                F.o_end[k] = at; at += al(sizeof(int32_t) * m);
+                F.o_ss[k] = at; at += al(sizeof(int32_t) * m * std::max(1, nsec[k]));
+                F.o_sw[k] = at; at += al(sizeof(int32_t) * m * std::max(1, nsec[k]));
+            }
+            F.total = at;
+            lay[which] = F;
+            s.d_tmp.reserve(T.total);
+            s.d_out.reserve(F.total);
+            s.h_out.reserve(F.total);
+            CUDA_CHECK(cudaMemcpyAsync(s.d_rows.p, s.h_rows.p, sizeof(uint16_t) * (size_t)m * stride_f, cudaMemcpyHostToDevice, s.st));
+            CUDA_CHECK(cudaMemcpyAsync(s.d_rows2.p, s.h_rows2.p, sizeof(uint16_t) * (size_t)m * stride_b, cudaMemcpyHostToDevice, s.st));
+            CUDA_CHECK(cudaMemcpyAsync(s.d_lens.p, s.h_lens.p, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
+            CUDA_CHECK(cudaMemcpyAsync(s.d_lens2.p, s.h_lens2.p, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
+            if (width) {
+                s.h_width.reserve(sizeof(int32_t) * (size_t)m);
+                s.d_width.reserve(sizeof(int32_t) * (size_t)m);
+                std::memcpy(s.h_width.p, width + c0, sizeof(int32_t) * (size_t)m);
+                CUDA_CHECK(cudaMemcpyAsync(s.d_width.p, s.h_width.p, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
+            }
+            uint8_t* t = s.d_tmp.as<uint8_t>();
+            ResultSet rs[4];
+            for (int r = 0; r < 4; ++r) {
+                const int a = (r == 0 || r == 2) ? 0 : 1;             /* adaptor */
+                const bool on_front = (r == 0 || r == 3);              /* window set */
+                Outputs dev;
+                dev.score = reinterpret_cast<double*>(t + T.o_score[r]);
+                dev.start = reinterpret_cast<int32_t*>(t + T.o_start[r]);
+                dev.end = reinterpret_cast<int32_t*>(t + T.o_end[r]);
+                dev.sec_start = reinterpret_cast<int32_t*>(t + T.o_ss[r]);
+                dev.sec_width = reinterpret_cast<int32_t*>(t + T.o_sw[r]);
+                run_device(*plan[a], D[a], s.scratch, s.st,
+                           on_front ? s.d_rows.as<uint16_t>() : s.d_rows2.as<uint16_t>(),
+                           on_front ? s.d_lens.as<int32_t>() : s.d_lens2.as<int32_t>(), m,
+                           on_front ? stride_f : stride_b, on_front ? maxf : maxb, true, dev, sms);
+                rs[r] = ResultSet{dev.score, dev.start, dev.end, dev.sec_start, dev.sec_width};
+            }
+            uint8_t* d = s.d_out.as<uint8_t>();
+            SelectArgs S;
+            std::memset(&S, 0, sizeof(S));
+            S.n = m;
+            S.a1_front = rs[0]; S.a2_back = rs[1]; S.a1_back = rs[2]; S.a2_front = rs[3];
+            S.nsec1 = nsec[0]; S.nsec2 = nsec[1];
+            S.width = width ? s.d_width.as<int32_t>() : nullptr;
+            S.reversed = d + F.o_rev;
+            S.score1 = reinterpret_cast<double*>(d + F.o_score[0]); S.score2 = reinterpret_cast<double*>(d + F.o_score[1]);
+            S.start1 = reinterpret_cast<int32_t*>(d + F.o_start[0]); S.start2 = reinterpret_cast<int32_t*>(d + F.o_start[1]);
+            S.end1 = reinterpret_cast<int32_t*>(d + F.o_end[0]); S.end2 = reinterpret_cast<int32_t*>(d + F.o_end[1]);
+            S.sec_start1 = reinterpret_cast<int32_t*>(d + F.o_ss[0]); S.sec_start2 = reinterpret_cast<int32_t*>(d + F.o_ss[1]);
+            S.sec_width1 = reinterpret_cast<int32_t*>(d + F.o_sw[0]); S.sec_width2 = reinterpret_cast<int32_t*>(d + F.o_sw[1]);
+            launch_resolve_select(S, s.st);
+            g_launches += 1;
+            CUDA_CHECK(cudaGetLastError());
+            CUDA_CHECK(cudaMemcpyAsync(s.h_out.p, s.d_out.p, F.total, cudaMemcpyDeviceToHost, s.st));
+            CUDA_CHECK(cudaEventRecord(s.done, s.st));
+            s.n = m;
+            s.lo = c0;
+            s.busy = true;
+            which ^= 1;
+            c0 = c1;
+        }
+        drain(slots[which], lay[which]);
+        drain(slots[which ^ 1], lay[which ^ 1]);
+    }
+};
 
 }  // namespace
 
@@ -1186,6 +1398,120 @@ int sarlacc_general_align(const sarlacc_reads* reads, const sarlacc_encoding* en
             ref_aln[i * aln_stride + (int64_t)nop] = '\0';
             query_aln[i * aln_stride + (int64_t)nop] = '\0';
         }
+    }
+    return 0;
+}
+
+int sarlacc_adaptor_align_windows(const sarlacc_reads* front, const sarlacc_reads* back, const sarlacc_encoding* encoding,
+        double gapopen, double gapext, const char* adaptor1, const char* adaptor2,
+        int nsec1, const int32_t* sec_starts1, const int32_t* sec_ends1,
+        int nsec2, const int32_t* sec_starts2, const int32_t* sec_ends2,
+        const int32_t* read_width, uint8_t* reversed,
+        double* score1, int32_t* start1, int32_t* end1, int32_t* sec_start1, int32_t* sec_width1,
+        double* score2, int32_t* start2, int32_t* end2, int32_t* sec_start2, int32_t* sec_width2)
+{
+    if (!front || !back) return fail("reads must not be NULL");
+    if (!adaptor1 || !adaptor2) return fail("adaptor sequence should be a string");
+    if (front->n != back->n) return fail("front and back windows should have the same length");
+    if (nsec1 < 0 || nsec2 < 0) return fail("section starts and ends should have the same length");
+    Encoding enc;
+    const char* msg = build_encoding(encoding, enc);
+    if (msg) return fail(msg);
+    const int64_t n = front->n;
+    const int L1 = (int)std::strlen(adaptor1), L2 = (int)std::strlen(adaptor2);
+    if (n == 0) return 0;
+    if (L1 == 0 || L2 == 0) {
+        /* degenerate adaptors: compose the four reference calls on the host side of the ABI */
+        std::vector<double> sc[4];
+        std::vector<int32_t> st[4], en[4], ss[4], sw[4];
+        const sarlacc_reads* rd[4] = {front, back, back, front};
+        const char* ad[4] = {adaptor1, adaptor2, adaptor1, adaptor2};
+        const int ns[4] = {nsec1, nsec2, nsec1, nsec2};
+        const int32_t* s0[4] = {sec_starts1, sec_starts2, sec_starts1, sec_starts2};
+        const int32_t* e0[4] = {sec_ends1, sec_ends2, sec_ends1, sec_ends2};
+        for (int r = 0; r < 4; ++r) {
+            sc[r].resize(n); st[r].resize(n); en[r].resize(n);
+            ss[r].resize((size_t)std::max(1, ns[r]) * n); sw[r].resize((size_t)std::max(1, ns[r]) * n);
+            int rc = sarlacc_adaptor_align(rd[r], encoding, gapopen, gapext, ad[r], ns[r], s0[r], e0[r],
+                                           sc[r].data(), st[r].data(), en[r].data(), ss[r].data(), sw[r].data());
+            if (rc) return rc;
+        }
+        for (int64_t i = 0; i < n; ++i) {
+            const double f = std::max(sc[0][i], 0.0) + std::max(sc[1][i], 0.0);
+            const double r = std::max(sc[2][i], 0.0) + std::max(sc[3][i], 0.0);
+            const bool rev = f < r;
+            reversed[i] = rev ? 1 : 0;
+            const int a = rev ? 2 : 0, b = rev ? 3 : 1;
+            score1[i] = sc[a][i]; start1[i] = st[a][i]; end1[i] = en[a][i];
+            for (int s = 0; s < nsec1; ++s) { sec_start1[(size_t)s * n + i] = ss[a][(size_t)s * n + i]; sec_width1[(size_t)s * n + i] = sw[a][(size_t)s * n + i]; }
+            score2[i] = sc[b][i];
+            int x = st[b][i], y = en[b][i];
+            if (read_width) { x = read_width[i] - x + 1; y = read_width[i] - y + 1; }
+            start2[i] = x; end2[i] = y;
+            for (int s = 0; s < nsec2; ++s) { sec_start2[(size_t)s * n + i] = ss[b][(size_t)s * n + i]; sec_width2[(size_t)s * n + i] = sw[b][(size_t)s * n + i]; }
+        }
+        return 0;
+    }
+    Plan P[2];
+    const char* r1[1] = {adaptor1};
+    const char* r2[1] = {adaptor2};
+    build_plan(P[0], enc, r1, 1, L1, true, gapopen, gapext);
+    build_plan(P[1], enc, r2, 1, L2, true, gapopen, gapext);
+    const int nsecs[2] = {nsec1, nsec2};
+    const int32_t* sst[2] = {sec_starts1, sec_starts2};
+    const int32_t* sen[2] = {sec_ends1, sec_ends2};
+    const int Ls[2] = {L1, L2};
+    for (int k = 0; k < 2; ++k) {
+        if (nsecs[k] > 0) {
+            P[k].sec_starts.assign(sst[k], sst[k] + nsecs[k]);
+            P[k].sec_ends.assign(sen[k], sen[k] + nsecs[k]);
+            for (int s = 0; s < nsecs[k]; ++s) {
+                if (sst[k][s] < 0 || sst[k][s] > Ls[k] || sen[k][s] < 0 || sen[k][s] > Ls[k]) return fail("section bounds outside the adaptor");
+            }
+        }
+    }
+    if (require_device()) return 1;
+    std::vector<int> devs = configured_devices();
+    if ((int64_t)devs.size() > n) devs.resize((size_t)std::max<int64_t>(1, n));
+    const int nd = (int)devs.size();
+    std::vector<PairJob> jobs(nd);
+    for (int d = 0; d < nd; ++d) {
+        PairJob& J = jobs[d];
+        J.device = devs[d];
+        J.lo = n * d / nd;
+        J.hi = n * (d + 1) / nd;
+        J.n_total = n;
+        J.front = front;
+        J.back = back;
+        J.plan[0] = &P[0];
+        J.plan[1] = &P[1];
+        J.width = read_width;
+        J.out.reversed = reversed;
+        J.out.score[0] = score1; J.out.start[0] = start1; J.out.end[0] = end1; J.out.sec_start[0] = sec_start1; J.out.sec_width[0] = sec_width1;
+        J.out.score[1] = score2; J.out.start[1] = start2; J.out.end[1] = end2; J.out.sec_start[1] = sec_start2; J.out.sec_width[1] = sec_width2;
+        J.nthreads = host_threads_for(nd);
+    }
+    if (nd == 1) {
+        jobs[0].run();
+    } else {
+        std::vector<std::thread> pool;
+        for (int d = 0; d < nd; ++d) pool.emplace_back([&jobs, d] { jobs[d].run(); });
+        for (auto& t : pool) t.join();
+    }
+    for (int d = 0; d < nd; ++d) {
+        if (!jobs[d].cuda_error.empty()) return fail(jobs[d].cuda_error);
+    }
+    /* error precedence of the four reference calls, in their order (R/adaptorAlign.R:186-189) */
+    FirstError ef, eb;
+    for (int d = 0; d < nd; ++d) { ef.merge(jobs[d].err_front); eb.merge(jobs[d].err_back); }
+    ReadView VF{front}, VB{back};
+    const FirstError* base[4] = {&ef, &eb, &eb, &ef};
+    const ReadView* views[4] = {&VF, &VB, &VB, &VF};
+    const Plan* plans[4] = {&P[0], &P[1], &P[0], &P[1]};
+    for (int r = 0; r < 4; ++r) {
+        FirstError e = *base[r];
+        apply_reference_errors(e, *views[r], n, *plans[r], 1);
+        if (e.kind != ERR_NONE) return fail(err_text(e.kind));
     }
     return 0;
 }

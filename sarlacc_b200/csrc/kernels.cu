@@ -579,6 +579,41 @@ __global__ void __launch_bounds__(128) traceback(const TraceArgs T)
     }
 }
 
+/* .resolve_strand (R/adaptorAlign.R:112-122): fscore = pmax(s_a1_front,0) + pmax(s_a2_back,0), rscore likewise on
+ * the swapped windows, reversed = fscore < rscore (strict); then cur.starts[rev,] <- cur.rc.starts[rev,] (:195-196)
+ * and adaptor2's start/end flipped into read coordinates, width - x + 1 (:66-71; unaligned 0 -> width + 1). */
+__global__ void resolve_select(const SelectArgs S)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.n) return;
+    const double f = __dadd_rn(fmax(S.a1_front.score[i], 0.0), fmax(S.a2_back.score[i], 0.0));
+    const double r = __dadd_rn(fmax(S.a1_back.score[i], 0.0), fmax(S.a2_front.score[i], 0.0));
+    const bool rev = f < r;
+    S.reversed[i] = rev ? 1 : 0;
+    const ResultSet& A = rev ? S.a1_back : S.a1_front;
+    const ResultSet& B = rev ? S.a2_front : S.a2_back;
+    S.score1[i] = A.score[i];
+    S.start1[i] = A.start[i];
+    S.end1[i] = A.end[i];
+    for (int s = 0; s < S.nsec1; ++s) {
+        S.sec_start1[(long long)s * S.n + i] = A.sec_start[(long long)s * S.n + i];
+        S.sec_width1[(long long)s * S.n + i] = A.sec_width[(long long)s * S.n + i];
+    }
+    S.score2[i] = B.score[i];
+    int st = B.start[i], en = B.end[i];
+    if (S.width) {
+        const int w = S.width[i];
+        st = w - st + 1;
+        en = w - en + 1;
+    }
+    S.start2[i] = st;
+    S.end2[i] = en;
+    for (int s = 0; s < S.nsec2; ++s) {
+        S.sec_start2[(long long)s * S.n + i] = B.sec_start[(long long)s * S.n + i];
+        S.sec_width2[(long long)s * S.n + i] = B.sec_width[(long long)s * S.n + i];
+    }
+}
+
 template <int C, bool TRACE>
 const char* launch_wf(const AlignArgs& a, int grid, cudaStream_t st, size_t smem) {
     auto kern = wf_forward<C, TRACE>;
@@ -644,6 +679,12 @@ void launch_traceback(const TraceArgs& t, cudaStream_t st) {
     const int block = 128;
     const int grid = (int)((t.n + block - 1) / block);
     if (grid > 0) traceback<<<grid, block, sizeof(int) * ((size_t)t.L + 1), st>>>(t);
+}
+
+void launch_resolve_select(const SelectArgs& s, cudaStream_t st) {
+    const int block = 256;
+    const int grid = (int)((s.n + block - 1) / block);
+    if (grid > 0) resolve_select<<<grid, block, 0, st>>>(s);
 }
 
 void launch_fill_empty(const AlignArgs& a, cudaStream_t st) {

@@ -54,6 +54,7 @@ def test_adaptor_align_mock_reads(port, enc, tmp_path):
     out = api.adaptorAlign(VIGNETTE_A1, VIGNETTE_A2, path, number=100)
     exp = R.adaptor_align_R(port, enc, VIGNETTE_A1, VIGNETTE_A2, reads.seq_strings(), reads.qual_strings())
     compare_adaptor_align(out, exp)
+    compare_adaptor_align(api.adaptorAlign(VIGNETTE_A1, VIGNETTE_A2, path, number=100, fused=False), exp)
     assert out.rownames == reads.names
     assert 0.2 < out["reversed"].mean() < 0.8
     # most reads carry both adaptors: scores well above zero, 12-base barcode and 4-base UMI extracted
@@ -63,6 +64,37 @@ def test_adaptor_align_mock_reads(port, enc, tmp_path):
     out2 = api.adaptorAlign(VIGNETTE_A1, VIGNETTE_A2, reads, tolerance=120, gapOpening=4, gapExtension=2, number=77)
     exp2 = R.adaptor_align_R(port, enc, VIGNETTE_A1, VIGNETTE_A2, reads.seq_strings(), reads.qual_strings(), tolerance=120, go=4, ge=2)
     compare_adaptor_align(out2, exp2)
+
+
+def test_fused_windows_entry(port, enc, monkeypatch):
+    """sarlacc_adaptor_align_windows == the four reference calls + .resolve_strand + selection + flip."""
+    from sarlacc_b200 import native, synth, SarlaccError
+    from oracle import r_level as R
+    n = 3000
+    front, back, widths, _ = synth.mock_windows(n, VIGNETTE_A1, VIGNETTE_A2, seed=77)
+    s1, e1 = [16, 42], [28, 46]
+    monkeypatch.setenv("SARLACC_CHUNK", "700")
+    rev, r1, r2 = native.adaptor_align_windows(front, back, enc, 5, 1, VIGNETTE_A1, VIGNETTE_A2, (s1, e1), ((), ()), read_width=widths)
+    a = native.adaptor_align(front, enc, 5, 1, VIGNETTE_A1, s1, e1)
+    b = native.adaptor_align(back, enc, 5, 1, VIGNETTE_A2)
+    c = native.adaptor_align(back, enc, 5, 1, VIGNETTE_A1, s1, e1)
+    d = native.adaptor_align(front, enc, 5, 1, VIGNETTE_A2)
+    exp_rev, _ = R.resolve_strand(a[0], b[0], c[0], d[0])
+    exp_rev = np.array(exp_rev)
+    assert np.array_equal(rev, exp_rev) and 0.3 < rev.mean() < 0.7
+    for k in range(3):
+        assert np.array_equal(r1[k], np.where(exp_rev, c[k], a[k]))
+    for s in range(2):
+        assert np.array_equal(r1[3][s], np.where(exp_rev, c[3][s], a[3][s])) and np.array_equal(r1[4][s], np.where(exp_rev, c[4][s], a[4][s]))
+    assert np.array_equal(r2[0], np.where(exp_rev, d[0], b[0]))
+    assert np.array_equal(r2[1], widths - np.where(exp_rev, d[1], b[1]) + 1) and np.array_equal(r2[2], widths - np.where(exp_rev, d[2], b[2]) + 1)
+    # degenerate adaptor and error paths go through the same entry
+    rev0, q1, q2 = native.adaptor_align_windows(front[np.arange(50)], back[np.arange(50)], enc, 5, 1, "", VIGNETTE_A2)
+    assert np.all(q1[0] == 0) and np.array_equal(q2[0], np.where(rev0, d[0][:50], b[0][:50]))
+    with pytest.raises(SarlaccError, match="unrecognized base in reference sequence"):
+        native.adaptor_align_windows(front[np.arange(5)], back[np.arange(5)], enc, 5, 1, VIGNETTE_A1, "ACXT")
+    with pytest.raises(SarlaccError, match="front and back windows should have the same length"):
+        native.adaptor_align_windows(front[np.arange(5)], back[np.arange(4)], enc, 5, 1, VIGNETTE_A1, VIGNETTE_A2)
 
 
 def test_get_adaptor_thresholds(port, enc):
