@@ -519,8 +519,13 @@ struct FwdTimer {
 /* Enqueue forward (+ traceback) for device-resident packed reads [0,n).  Sub-chunks by scratch budget. */
 const char* run_device(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t st,
         const uint16_t* d_rows, const int32_t* d_lens, long long n, int stride, int maxlen,
-        bool trace, const Outputs& out, int sms, FwdTimer* timer = nullptr)
+        bool trace, const Outputs& out, int sms, FwdTimer* timer = nullptr,
+        cudaStream_t tb_stream = nullptr, cudaEvent_t fwd_done = nullptr, cudaEvent_t tb_done = nullptr)
 {
+    /* With tb_stream set, the traceback of this range runs on that stream after fwd_done (recorded on `st`), and
+     * tb_done is recorded behind it: the memory-bound traceback then overlaps the next range's ALU-bound forward pass
+     * (it fits beside the forward kernel's resident blocks: 32 registers per thread).  The caller owns the waits that
+     * protect the scratch buffers. */
     const char* name = "";
     if (n == 0) return name;
     const long long cn = sub_chunk(P, maxlen, trace, n);
@@ -608,7 +613,14 @@ const char* run_device(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t
             T.ops = out.ops ? out.ops + off * out.ops_stride : nullptr;
             T.nops = out.nops ? out.nops + off : nullptr;
             T.ops_stride = out.ops_stride;
-            launch_traceback(T, st);
+            if (tb_stream) {
+                CUDA_CHECK(cudaEventRecord(fwd_done, st));
+                CUDA_CHECK(cudaStreamWaitEvent(tb_stream, fwd_done, 0));
+                launch_traceback(T, tb_stream);
+                CUDA_CHECK(cudaEventRecord(tb_done, tb_stream));
+            } else {
+                launch_traceback(T, st);
+            }
             g_launches += 1;
         }
         CUDA_CHECK(cudaGetLastError());
@@ -1526,8 +1538,12 @@ struct sarlacc_resident {
     int64_t total_len = 0;
     Encoding enc;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t tb_stream = nullptr;            /* tracebacks of sub-range k overlap the forward pass of k+1 */
+    cudaEvent_t fwd_done[2] = {nullptr, nullptr};
+    cudaEvent_t tb_done[2] = {nullptr, nullptr};
+    bool tb_pending[2] = {false, false};
     DevBuf d_rows, d_lens, d_out;
-    Scratch scratch;
+    Scratch scratch, scratch2;
     /* plans (host tables + their device copy) are cached per (reference, penalties, mode, sections) so that the
      * steady state of adaptorAlign -> getAdaptorThresholds style re-use enqueues kernels only */
     struct CachedPlan {
@@ -1546,6 +1562,7 @@ struct sarlacc_resident {
     std::vector<int32_t> h_lens;
     FwdTimer timer;
     bool timing = false;
+    long long sub = 0;     /* alignments per sub-range of the last run */
 };
 
 sarlacc_resident* sarlacc_resident_create(const sarlacc_reads* reads, const sarlacc_encoding* encoding, int device) {
@@ -1560,6 +1577,11 @@ sarlacc_resident* sarlacc_resident_create(const sarlacc_reads* reads, const sarl
         r->sms = device_sm_count(device);
         r->n = reads->n;
         CUDA_CHECK(cudaStreamCreateWithFlags(&r->own_stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&r->tb_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            CUDA_CHECK(cudaEventCreateWithFlags(&r->fwd_done[k], cudaEventDisableTiming));
+            CUDA_CHECK(cudaEventCreateWithFlags(&r->tb_done[k], cudaEventDisableTiming));
+        }
         ReadView V{reads};
         PackTables PT;
         build_pack_tables(PT, reads->seq_encoding, r->enc);
@@ -1618,6 +1640,12 @@ void sarlacc_resident_free(sarlacc_resident* r) {
     r->d_lens.release();
     r->d_out.release();
     r->scratch.release();
+    r->scratch2.release();
+    for (int k = 0; k < 2; ++k) {
+        if (r->fwd_done[k]) cudaEventDestroy(r->fwd_done[k]);
+        if (r->tb_done[k]) cudaEventDestroy(r->tb_done[k]);
+    }
+    if (r->tb_stream) cudaStreamDestroy(r->tb_stream);
     for (auto& p : r->plans) p->d.buf.release();
     r->plans.clear();
     r->timer.release();
@@ -1692,24 +1720,45 @@ int sarlacc_resident_align(sarlacc_resident* r, int mode, double gapopen, double
         uint8_t* d = r->d_out.as<uint8_t>();
         /* Sub-chunks (scratch budget) write straight into the full-size output block: sections are laid out
          * [nsec][n] so each sub-chunk gets its own launch set with per-section base pointers. */
-        const long long cn = sub_chunk(cp->plan, r->maxlen, trace, std::max<int64_t>(r->n, 1));
+        /* two scratch sets: each sub-range gets half of the budget so that traceback(k) and forward(k+1) overlap */
+        long long cn = sub_chunk(cp->plan, r->maxlen, trace, std::max<int64_t>(r->n, 1));
+        const bool overlap = trace && std::getenv("SARLACC_NO_OVERLAP") == nullptr;
+        if (overlap && cn >= r->n && r->n >= 65536) cn = (r->n + 1) / 2;          /* at least two ranges to overlap */
+        else if (overlap && cn < r->n) cn = std::max<long long>(1, cn / 2);
+        r->sub = cn;
         const char* name = "";
         r->timer.used = 0;
-        for (long long off = 0; off < r->n; off += cn) {
+        int k = 0;
+        for (long long off = 0; off < r->n; off += cn, ++k) {
             const long long m = std::min<long long>(cn, r->n - off);
+            const int b = k & 1;
             Outputs dev;
             dev.score = reinterpret_cast<double*>(d + r->lay.o_score) + off;
             if (trace) {
                 dev.start = reinterpret_cast<int32_t*>(d + r->lay.o_start) + off;
                 dev.end = reinterpret_cast<int32_t*>(d + r->lay.o_end) + off;
-                /* section matrices are re-based per sub-chunk below: run_device sees n = m, so give it a
-                 * compact [nsec][m] staging area and scatter afterwards when the run is split */
+                /* section matrices: one run -> [nsec][n]; split run -> consecutive compact [nsec][m] blocks,
+                 * scattered by sarlacc_resident_fetch */
                 dev.sec_start = reinterpret_cast<int32_t*>(d + r->lay.o_ss) + (cn >= r->n ? 0 : off * (long long)std::max(1, r->nsec));
                 dev.sec_width = reinterpret_cast<int32_t*>(d + r->lay.o_sw) + (cn >= r->n ? 0 : off * (long long)std::max(1, r->nsec));
             }
-            name = run_device(cp->plan, cp->d, r->scratch, st, r->d_rows.as<uint16_t>() + (size_t)off * r->stride,
+            if (overlap && r->tb_pending[b]) {
+                /* the forward pass of this range overwrites the records traceback(k-2) may still be reading */
+                CUDA_CHECK(cudaStreamWaitEvent(st, r->tb_done[b], 0));
+                r->tb_pending[b] = false;
+            }
+            name = run_device(cp->plan, cp->d, b ? r->scratch2 : r->scratch, st, r->d_rows.as<uint16_t>() + (size_t)off * r->stride,
                               r->d_lens.as<int32_t>() + off, m, r->stride, r->maxlen, trace, dev, r->sms,
-                              r->timing ? &r->timer : nullptr);
+                              r->timing ? &r->timer : nullptr,
+                              overlap ? r->tb_stream : nullptr, r->fwd_done[b], r->tb_done[b]);
+            if (overlap) r->tb_pending[b] = true;
+        }
+        /* the caller's stream sees the run as complete only when the tracebacks are */
+        for (int b = 0; b < 2; ++b) {
+            if (r->tb_pending[b]) {
+                CUDA_CHECK(cudaStreamWaitEvent(st, r->tb_done[b], 0));
+                r->tb_pending[b] = false;
+            }
         }
         r->last_kernel = std::string(name) + " G=" + std::to_string(cp->plan.G) + " C=" + std::to_string(cp->plan.C);
         r->has_result = true;
@@ -1734,7 +1783,7 @@ int sarlacc_resident_fetch(sarlacc_resident* r, double* score, int32_t* start, i
         if (r->mode == MODE_TRACE_LOCAL) {
             if (start) CUDA_CHECK(cudaMemcpyAsync(start, d + r->lay.o_start, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
             if (end) CUDA_CHECK(cudaMemcpyAsync(end, d + r->lay.o_end, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-            const long long cn = sub_chunk(r->cur->plan, r->maxlen, true, (long long)n);
+            const long long cn = r->sub > 0 ? r->sub : (long long)n;
             if (r->nsec > 0 && (sec_start || sec_width)) {
                 if (cn >= (long long)n) {
                     if (sec_start) CUDA_CHECK(cudaMemcpyAsync(sec_start, d + r->lay.o_ss, sizeof(int32_t) * n * r->nsec, cudaMemcpyDeviceToHost, st));
