@@ -247,9 +247,11 @@ def main():
     # dominant kernel, timed alone with events inside the library (same stream), outside the timed region so that
     # the event synchronisation does not serialise it
     fwd_ms = []
+    os.environ["SARLACC_NO_OVERLAP"] = "1"     # time the kernel alone: no traceback of the previous sub-range beside it
     for _ in range(max(3, args.steps)):
         fwd_ms.append(step(timing=True))
     torch.cuda.synchronize()
+    del os.environ["SARLACC_NO_OVERLAP"]
     rf.align(T, GO, GE, A1, s1, e1, stream=stream)
     dom_kernel = rf.last_kernel()
     fwd = statistics.median(fwd_ms)
@@ -345,7 +347,10 @@ def main():
                 "peak_at_measured_clock": peak_gcups_at_clock,
                 "frac_at_measured_clock": (achieved / peak_gcups_at_clock) if achieved else None,
                 "how": "cells = n*250*70 per launch / CUDA-event duration of the forward launch; peak = %d SMs * 64 FP64 lanes * f / 10 FP64 ops per cell, f = clocks.max.sm" % sms,
-                "launch_ms": fwd, "traffic": None,
+                "launch_ms": fwd,
+                # dram__bytes_read+write of this kernel per alignment in profiles/r01_ncu_summary_*.txt (100 k alignments:
+                # 0.088 GB read + 1.56 GB written) scaled to the alignments of one bench pass
+                "traffic": 16520.0 * n, "traffic_algorithmic": alg_bytes,
                 "hbm": {"achieved": alg_bytes / (fwd / 1000.0) / 1e9 if fwd > 0 else None, "peak": hbm_peak, "unit": "GB/s",
                         "frac": (alg_bytes / (fwd / 1000.0) / 1e9 / hbm_peak) if fwd > 0 else None,
                         "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},

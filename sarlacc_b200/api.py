@@ -7,6 +7,7 @@ parity tests read like the reference's own tests:
     getAdaptorThresholds   R/getAdaptorThresholds.R:6-66
     barcodeAlign           R/barcodeAlign.R:4-40
     tuneAlignment          R/tuneAlignment.R:6-76          (caller of the same entry points)
+    extractSubseq          R/extractSubseq.R:5-117         (caller; re-aligns and re-checks the stored scores)
     qualityAlign           R/qualityAlign.R                (general_align wrapper)
     helpers: _setup_subseqs (:136-143), _get_front_and_back (:86-95), _resolve_strand (:112-122),
              _parallelize (:126-134), _align_and_extract (:150-176), _align_AA_internal (:178-199),
@@ -488,6 +489,62 @@ def tuneAlignment(adaptor1, adaptor2, filepath, tolerance=200, number=10000, gap
         return {"parameters": {"gapOpening": None, "gapExtension": None}, "scores": {"reads": None, "scrambled": None}}
     return {"parameters": {"gapOpening": final[0], "gapExtension": final[1]},
             "scores": {"reads": final[2], "scrambled": final[3]}}
+
+
+def _extract_internal(reads, flipped, adaptor1, adaptor2, tolerance, subseq1, subseq2, gap_opening, gap_extension, encoding=None):
+    """R/extractSubseq.R:89-117: re-align only the window the stored orientation points at."""
+    w = _get_front_and_back(reads, tolerance)
+    flipped = np.asarray(flipped, dtype=bool)
+    actual_starts = _readset_where(flipped, w["back"], w["front"])
+    actual_ends = _readset_where(flipped, w["front"], w["back"])
+    args = dict(gap_opening=gap_opening, gap_extension=gap_extension, encoding=encoding)
+    a1 = a2 = None
+    if len(subseq1["starts"]) or len(subseq1["ends"]):
+        a1 = _align_and_extract(adaptor1, actual_starts, subseq_starts=subseq1["starts"], subseq_ends=subseq1["ends"], **args)
+    if len(subseq2["starts"]) or len(subseq2["ends"]):
+        a2 = _align_and_extract(adaptor2, actual_ends, subseq_starts=subseq2["starts"], subseq_ends=subseq2["ends"], **args)
+    return a1, a2
+
+
+def extractSubseq(aligned, subseq1=None, subseq2=None, number=1e5):
+    """R/extractSubseq.R:5-87: arbitrary adaptor sub-ranges (dicts with 1-based "starts"/"ends"), obtained by
+    re-aligning and checked against the stored scores -- which is why the device path has to be deterministic and
+    independent of chunking / device count.  The reference tests the scores with all.equal; here they are identical."""
+    if subseq1 is None and subseq2 is None:
+        raise ValueError("at least one of 'subseq1' and 'subseq2' should be specified")
+    empty = {"starts": np.zeros(0, np.int32), "ends": np.zeros(0, np.int32)}
+    do1, do2 = subseq1 is not None, subseq2 is not None
+    subseq1 = subseq1 if do1 else empty
+    subseq2 = subseq2 if do2 else empty
+    go = aligned["adaptor1"].metadata["gapOpening"]
+    ge = aligned["adaptor1"].metadata["gapExtension"]
+    adaptor1 = aligned["adaptor1"].metadata["sequence"]
+    adaptor2 = aligned["adaptor2"].metadata["sequence"]
+    tolerance = aligned.metadata["tolerance"]
+    enc = _create_encoding_vector(_qual2class(aligned.metadata["qual.type"]))
+    wanted = {nm: k for k, nm in enumerate(aligned.rownames)}
+    all1, all2 = [], []
+    for reads in _stream(aligned.metadata["filepath"], number):
+        keep = np.array([nm in wanted for nm in reads.names], dtype=bool)
+        reads = reads[np.nonzero(keep)[0]]
+        if len(reads) == 0:
+            continue
+        m = np.array([wanted[nm] for nm in reads.names], dtype=np.int64)
+        a1, a2 = _extract_internal(reads, aligned["reversed"][m], adaptor1, adaptor2, tolerance, subseq1, subseq2, go, ge, enc)
+        if do1:
+            if a1 is not None and not np.allclose(a1["score"], aligned["adaptor1"]["score"][m], rtol=1.5e-8, atol=0):
+                raise RuntimeError("score mismatch from 'aligned' for adaptor 1")
+            all1.append(a1["subseq"] if a1 is not None else Frame(nrows=len(reads)))
+        if do2:
+            if a2 is not None and not np.allclose(a2["score"], aligned["adaptor2"]["score"][m], rtol=1.5e-8, atol=0):
+                raise RuntimeError("score mismatch from 'aligned' for adaptor 2")
+            all2.append(a2["subseq"] if a2 is not None else Frame(nrows=len(reads)))
+    out = {}
+    if do1:
+        out["adaptor1"] = Frame.rbind(all1) if all1 else Frame(nrows=0)
+    if do2:
+        out["adaptor2"] = Frame.rbind(all2) if all2 else Frame(nrows=0)
+    return out
 
 
 def qualityAlign(sequences, reference, gapOpening=5, gapExtension=1, edit_only=False, qual_type="phred"):

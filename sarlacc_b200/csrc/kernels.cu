@@ -180,9 +180,11 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
             if (kinds & 4) mytab[5 * 32] = costs[3 * encn + q];
             if (kinds & 8) mytab[6 * 32] = costs[4 * encn + q];
         }
-        if (first_lane) {   /* column 0: src/reference_align.cpp:64-78 */
-            Sl = col0_value(local, gop, ge, i);
-            El = NEG;
+        {   /* column 0 feeds the first lane: src/reference_align.cpp:64-78 (0 in local mode; uniform branch otherwise) */
+            double c0v = 0.0;
+            if (!local) c0v = col0_value(0, gop, ge, i);
+            Sl = first_lane ? c0v : Sl;
+            El = first_lane ? NEG : El;
         }
         const double Sl_in = Sl, El_in = El;
         uint32_t flo = 0, fhi = 0;

@@ -139,6 +139,35 @@ def test_barcode_align(port, enc):
     assert out["barcode"].tolist() == cid and np.array_equal(out["score"], np.array(cur))
 
 
+def test_extract_subseq(port, enc):
+    """R/extractSubseq.R: arbitrary sub-ranges by re-alignment; the stored scores must be reproduced exactly."""
+    from sarlacc_b200 import api, synth
+    from oracle import r_level as R
+    reads = synth.mock_reads(120, VIGNETTE_A1, VIGNETTE_A2, seed=9)
+    aligned = api.adaptorAlign(VIGNETTE_A1, VIGNETTE_A2, reads, number=50)
+    sub1 = {"starts": np.array([1, 17, 30]), "ends": np.array([16, 28, 70])}
+    sub2 = {"starts": np.array([5]), "ends": np.array([10])}
+    out = api.extractSubseq(aligned, sub1, sub2, number=37)
+    seqs, quals = reads.seq_strings(), reads.qual_strings()
+    front, back = R.get_front_and_back(seqs, quals, 250)
+    rev = aligned["reversed"]
+    w1 = [back[i] if rev[i] else front[i] for i in range(len(seqs))]
+    w2 = [front[i] if rev[i] else back[i] for i in range(len(seqs))]
+    e1 = R.align_and_extract(port, enc, VIGNETTE_A1, w1, 5, 1, sub1["starts"].tolist(), sub1["ends"].tolist())
+    e2 = R.align_and_extract(port, enc, VIGNETTE_A2, w2, 5, 1, sub2["starts"].tolist(), sub2["ends"].tolist())
+    for k in range(3):
+        assert out["adaptor1"]["Sub%d" % (k + 1)].seq_strings() == [e["subseq"][k][0] for e in e1]
+    assert out["adaptor2"]["Sub1"].seq_strings() == [e["subseq"][0][0] for e in e2]
+    # the barcode section asked for again equals what adaptorAlign stored
+    assert out["adaptor1"]["Sub2"].seq_strings() == aligned["adaptor1"]["subseq"]["Sub1"].seq_strings()
+    only2 = api.extractSubseq(aligned, subseq2=sub2)
+    assert "adaptor1" not in only2 and only2["adaptor2"]["Sub1"].seq_strings() == out["adaptor2"]["Sub1"].seq_strings()
+    # a tampered score is caught like in the reference
+    aligned["adaptor1"]["score"] = aligned["adaptor1"]["score"] + 1.0
+    with pytest.raises(RuntimeError, match="score mismatch from 'aligned' for adaptor 1"):
+        api.extractSubseq(aligned, sub1)
+
+
 def test_tune_alignment(port, enc):
     """tests/testthat/test-tuning.R:26-42 (the pairwiseAlignment comparison is replaced by the oracle)."""
     from sarlacc_b200 import api, ReadSet

@@ -4,6 +4,8 @@ import os
 import sys
 import time
 
+os.environ.setdefault("SARLACC_NO_OVERLAP", "1")   # time the forward kernel alone (no traceback of the previous sub-range beside it)
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sarlacc_b200 import native, synth  # noqa: E402
 

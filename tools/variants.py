@@ -56,10 +56,12 @@ for flags in sys.argv[2:]:
         print(flags, "FAILED", r.stderr[-400:])
         continue
     regs = {}
-    for m in re.finditer(r"Compiling entry function '([^']+)'.*?\n.*?Function properties.*?\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\n.*?Used (\d+) registers", r.stderr):
-        mm = re.search(r"wf_forwardILi(\d+)ELb([01])E", m.group(1))
-        if mm:
-            regs[int(mm.group(2))] = (m.group(5), m.group(3))
+    for block in r.stderr.split("Compiling entry function")[1:]:
+        mm = re.search(r"wf_forwardILi(\d+)ELb([01])E", block)
+        sp = re.search(r"(\d+) bytes spill stores", block)
+        rg = re.search(r"Used (\d+) registers", block)
+        if mm and sp and rg:
+            regs[int(mm.group(2))] = (rg.group(1), sp.group(1))
     for trace in (1, 0):
         per, rows, top = analyse(cubin, trace)
         print("%-46s trace=%d  %.2f instr/cell (x%d rows)  regs=%s spill=%s | %s" % (flags or "(base)", trace, per, rows, regs[trace][0], regs[trace][1], top))
