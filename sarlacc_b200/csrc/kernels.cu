@@ -653,6 +653,9 @@ int wavefront_block_threads() { return kBlock; }
 
 const char* launch_wavefront(const AlignArgs& a, bool trace, bool has_alt, int grid, cudaStream_t st) {
     const size_t smem = wavefront_smem_bytes(a);
+#ifdef SARLACC_ONLY_C   /* tuning builds: instantiate one geometry only (tools/variants.py) */
+    if (a.C == SARLACC_ONLY_C) return dispatch_flags<SARLACC_ONLY_C>(a, trace, has_alt, grid, st, smem);
+#else
     switch (a.C) {
         case 1: return dispatch_flags<1>(a, trace, has_alt, grid, st, smem);
         case 2: return dispatch_flags<2>(a, trace, has_alt, grid, st, smem);
@@ -667,6 +670,7 @@ const char* launch_wavefront(const AlignArgs& a, bool trace, bool has_alt, int g
         case 11: return dispatch_flags<11>(a, trace, has_alt, grid, st, smem);
         case 12: return dispatch_flags<12>(a, trace, has_alt, grid, st, smem);
     }
+#endif
     return nullptr;
 }
 

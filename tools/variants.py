@@ -61,7 +61,8 @@ for flags in sys.argv[2:]:
         sp = re.search(r"(\d+) bytes spill stores", block)
         rg = re.search(r"Used (\d+) registers", block)
         if mm and sp and rg:
-            regs[int(mm.group(2))] = (rg.group(1), sp.group(1))
+            if int(mm.group(1)) == C:
+                regs[int(mm.group(2))] = (rg.group(1), sp.group(1))
     for trace in (1, 0):
         per, rows, top = analyse(cubin, trace)
         print("%-46s trace=%d  %.2f instr/cell (x%d rows)  regs=%s spill=%s | %s" % (flags or "(base)", trace, per, rows, regs[trace][0], regs[trace][1], top))
