@@ -141,6 +141,14 @@ int sarlacc_adaptor_align_windows(const sarlacc_reads* front, const sarlacc_read
 typedef struct sarlacc_resident sarlacc_resident;
 
 sarlacc_resident* sarlacc_resident_create(const sarlacc_reads* reads, const sarlacc_encoding* encoding, int device);
+/* Device-side .scramble_input (R/getAdaptorThresholds.R:68-92): a new resident object whose window i is a uniform
+ * random permutation of window i of `src` (bases and qualities move together).  The permutation is a pure function of
+ * (seed, read index, stream_id, length): read index = read_index[i] if given, else first_index + i -- so it does not
+ * depend on chunking, sharding or device count, and sarlacc_b200/api.py reproduces it on the host for parity. */
+sarlacc_resident* sarlacc_resident_scrambled(const sarlacc_resident* src, uint64_t seed, uint64_t first_index,
+        const uint64_t* read_index, int stream_id);
+/* Copies the packed rows (uint16[n][stride]: quality index | one-hot base << 8) and lengths back (tests). */
+int     sarlacc_resident_rows(sarlacc_resident* r, uint16_t* rows, int32_t* lens, int* stride);
 void    sarlacc_resident_free(sarlacc_resident* r);
 int64_t sarlacc_resident_n(const sarlacc_resident* r);
 int64_t sarlacc_resident_cells(const sarlacc_resident* r, int rlen);   /* sum(len_i) * rlen: DP cells of one pass */

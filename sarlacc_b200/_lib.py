@@ -48,6 +48,7 @@ EXPORTS = [
     "sarlacc_resident_bytes", "sarlacc_resident_align", "sarlacc_resident_fetch",
     "sarlacc_resident_scores_device", "sarlacc_resident_last_kernel",
     "sarlacc_resident_set_timing", "sarlacc_resident_forward_ms",
+    "sarlacc_resident_scrambled", "sarlacc_resident_rows",
 ]
 
 
@@ -63,6 +64,9 @@ def _load():
     lib.sarlacc_kernel_launches.argtypes = [C.c_int]
     lib.sarlacc_resident_create.restype = C.c_void_p
     lib.sarlacc_resident_create.argtypes = [C.POINTER(_Reads), C.POINTER(_Encoding), C.c_int]
+    lib.sarlacc_resident_scrambled.restype = C.c_void_p
+    lib.sarlacc_resident_scrambled.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int]
+    lib.sarlacc_resident_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.sarlacc_resident_free.argtypes = [C.c_void_p]
     lib.sarlacc_resident_free.restype = None
     for name in ("sarlacc_resident_n", "sarlacc_resident_bytes"):

@@ -346,8 +346,29 @@ def _align_AT_internal(reads, adaptor1, adaptor2, tolerance, gap_opening, gap_ex
             "adaptor2": np.where(is_reverse, sc["REND"], sc["END"])}
 
 
-def getAdaptorThresholds(aligned, error=0.01, number=1e5, seed=0):
-    """R/getAdaptorThresholds.R:6-66."""
+def _scrambled_scores_device(front, back, adaptor1, adaptor2, go, ge, enc, seed, read_index):
+    """.align_AT_internal's scramble + four score-only alignments with the windows resident in HBM: packed once,
+    permuted on the device (sarlacc_resident_scrambled), scored four times."""
+    rf = native.Resident(front, enc)
+    rb = native.Resident(back, enc)
+    sf = rf.scrambled(seed, read_index=read_index, stream_id=0)
+    sb = rb.scrambled(seed, read_index=read_index, stream_id=1)
+    rf.close()
+    rb.close()
+    out = {}
+    try:
+        for key, r, a in (("START", sf, adaptor1), ("END", sb, adaptor2), ("RSTART", sb, adaptor1), ("REND", sf, adaptor2)):
+            r.align(r.MODE_SCORE_LOCAL, go, ge, a)
+            out[key] = r.fetch()
+    finally:
+        sf.close()
+        sb.close()
+    return out
+
+
+def getAdaptorThresholds(aligned, error=0.01, number=1e5, seed=0, device_scramble=True):
+    """R/getAdaptorThresholds.R:6-66.  device_scramble=True permutes the windows on the GPU; False builds the same
+    keyed permutation with numpy and goes through the reference's four score-only .Calls.  Identical results."""
     go = aligned["adaptor1"].metadata["gapOpening"]
     ge = aligned["adaptor1"].metadata["gapExtension"]
     adaptor1 = aligned["adaptor1"].metadata["sequence"]
@@ -369,9 +390,12 @@ def getAdaptorThresholds(aligned, error=0.01, number=1e5, seed=0):
             continue
         # the scramble is keyed by the read's position in the file, so dropping reads does not shift others
         w = _get_front_and_back(sub, tolerance)
-        scr_start = _scramble_by_index(w["front"], seed, first_index + idx, 0)
-        scr_end = _scramble_by_index(w["back"], seed, first_index + idx, 1)
-        sc = _get_alignment_scores(scr_start, scr_end, adaptor1, adaptor2, go, ge, enc)
+        if device_scramble:
+            sc = _scrambled_scores_device(w["front"], w["back"], adaptor1, adaptor2, go, ge, enc, seed, first_index + idx)
+        else:
+            scr_start = _scramble_by_index(w["front"], seed, first_index + idx, 0)
+            scr_end = _scramble_by_index(w["back"], seed, first_index + idx, 1)
+            sc = _get_alignment_scores(scr_start, scr_end, adaptor1, adaptor2, go, ge, enc)
         is_reverse = _resolve_strand(sc["START"], sc["END"], sc["RSTART"], sc["REND"])["reversed"]
         scr1.append(np.where(is_reverse, sc["RSTART"], sc["START"]))
         scr2.append(np.where(is_reverse, sc["REND"], sc["END"]))

@@ -1633,6 +1633,68 @@ sarlacc_resident* sarlacc_resident_create(const sarlacc_reads* reads, const sarl
     return r.release();
 }
 
+sarlacc_resident* sarlacc_resident_scrambled(const sarlacc_resident* src, uint64_t seed, uint64_t first_index,
+        const uint64_t* read_index, int stream_id)
+{
+    if (!src) { fail("resident handle is NULL"); return nullptr; }
+    std::unique_ptr<sarlacc_resident> r(new sarlacc_resident());
+    try {
+        CUDA_CHECK(cudaSetDevice(src->device));
+        r->device = src->device;
+        r->sms = src->sms;
+        r->n = src->n;
+        r->stride = src->stride;
+        r->maxlen = src->maxlen;
+        r->total_len = src->total_len;
+        r->enc = src->enc;
+        r->h_lens = src->h_lens;
+        CUDA_CHECK(cudaStreamCreateWithFlags(&r->own_stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&r->tb_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            CUDA_CHECK(cudaEventCreateWithFlags(&r->fwd_done[k], cudaEventDisableTiming));
+            CUDA_CHECK(cudaEventCreateWithFlags(&r->tb_done[k], cudaEventDisableTiming));
+        }
+        const size_t nn = (size_t)std::max<int64_t>(r->n, 1);
+        r->d_rows.reserve(sizeof(uint16_t) * nn * r->stride);
+        r->d_lens.reserve(sizeof(int32_t) * nn);
+        CUDA_CHECK(cudaMemsetAsync(r->d_rows.p, 0, sizeof(uint16_t) * nn * r->stride, r->own_stream));
+        if (r->n > 0) {
+            CUDA_CHECK(cudaMemcpyAsync(r->d_lens.p, src->d_lens.p, sizeof(int32_t) * (size_t)r->n, cudaMemcpyDeviceToDevice, r->own_stream));
+        }
+        DevBuf idx;
+        if (read_index && r->n > 0) {
+            idx.reserve(sizeof(uint64_t) * (size_t)r->n);
+            CUDA_CHECK(cudaMemcpyAsync(idx.p, read_index, sizeof(uint64_t) * (size_t)r->n, cudaMemcpyHostToDevice, r->own_stream));
+        }
+        /* the source may still be busy on its own stream */
+        CUDA_CHECK(cudaStreamSynchronize(src->own_stream));
+        launch_scramble(src->d_rows.as<uint16_t>(), r->d_rows.as<uint16_t>(), r->d_lens.as<int32_t>(), r->n, r->stride,
+                        seed, first_index, read_index ? idx.as<unsigned long long>() : nullptr, (unsigned long long)stream_id, r->own_stream);
+        g_launches += 1;
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaStreamSynchronize(r->own_stream));
+        idx.release();
+    } catch (CudaError& e) {
+        fail(e.msg);
+        sarlacc_resident_free(r.release());
+        return nullptr;
+    }
+    return r.release();
+}
+
+int sarlacc_resident_rows(sarlacc_resident* r, uint16_t* rows, int32_t* lens, int* stride) {
+    if (!r) return fail("resident handle is NULL");
+    try {
+        CUDA_CHECK(cudaSetDevice(r->device));
+        if (stride) *stride = r->stride;
+        if (r->n > 0 && rows) CUDA_CHECK(cudaMemcpy(rows, r->d_rows.p, sizeof(uint16_t) * (size_t)r->n * r->stride, cudaMemcpyDeviceToHost));
+        if (r->n > 0 && lens) CUDA_CHECK(cudaMemcpy(lens, r->d_lens.p, sizeof(int32_t) * (size_t)r->n, cudaMemcpyDeviceToHost));
+    } catch (CudaError& e) {
+        return fail(e.msg);
+    }
+    return 0;
+}
+
 void sarlacc_resident_free(sarlacc_resident* r) {
     if (!r) return;
     cudaSetDevice(r->device);

@@ -616,6 +616,42 @@ __global__ void resolve_select(const SelectArgs S)
     }
 }
 
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {   /* splitmix64 finaliser */
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+
+/* One warp per window: keys in shared memory, rank by counting (len <= a few hundred, so O(len^2 / 32) per lane). */
+__global__ void __launch_bounds__(128) scramble_rows(const uint16_t* in, uint16_t* out, const int32_t* lens, long long n, int stride,
+        unsigned long long seed, unsigned long long first_index, const unsigned long long* read_index, unsigned long long stream_id)
+{
+    extern __shared__ unsigned long long sk[];   /* [warps][stride] */
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long* keys = sk + (size_t)warp * stride;
+    for (long long a = (long long)blockIdx.x * (blockDim.x >> 5) + warp; a < n; a += (long long)gridDim.x * (blockDim.x >> 5)) {
+        const int len = lens[a];
+        const unsigned long long rid = read_index ? read_index[a] : first_index + (unsigned long long)a;
+        const unsigned long long base = mix64(rid * 0x9E3779B97F4A7C15ULL + seed);
+        for (int i = lane; i < len; i += 32) {
+            keys[i] = mix64(base ^ ((unsigned long long)i * 0xD1B54A32D192ED03ULL + stream_id * 0x8CB92BA72F3D8DD7ULL));
+        }
+        __syncwarp();
+        const uint16_t* src = in + a * (long long)stride;
+        uint16_t* dst = out + a * (long long)stride;
+        for (int i = lane; i < len; i += 32) {
+            const unsigned long long ki = keys[i];
+            int rank = 0;
+            for (int j = 0; j < len; ++j) {
+                const unsigned long long kj = keys[j];
+                rank += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
+            }
+            dst[rank] = src[i];
+        }
+        __syncwarp();
+    }
+}
+
 template <int C, bool TRACE>
 const char* launch_wf(const AlignArgs& a, int grid, cudaStream_t st, size_t smem) {
     auto kern = wf_forward<C, TRACE>;
@@ -685,6 +721,19 @@ void launch_traceback(const TraceArgs& t, cudaStream_t st) {
     const int block = 128;
     const int grid = (int)((t.n + block - 1) / block);
     if (grid > 0) traceback<<<grid, block, sizeof(int) * ((size_t)t.L + 1), st>>>(t);
+}
+
+void launch_scramble(const uint16_t* in, uint16_t* out, const int32_t* lens, long long n, int stride,
+                     unsigned long long seed, unsigned long long first_index, const unsigned long long* read_index,
+                     unsigned long long stream_id, cudaStream_t st)
+{
+    if (n <= 0) return;
+    const int block = 128;
+    const size_t smem = sizeof(unsigned long long) * (size_t)(block / 32) * stride;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(scramble_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    long long grid = (n + (block / 32) - 1) / (block / 32);
+    if (grid > 148 * 64) grid = 148 * 64;
+    scramble_rows<<<(int)grid, block, smem, st>>>(in, out, lens, n, stride, seed, first_index, read_index, stream_id);
 }
 
 void launch_resolve_select(const SelectArgs& s, cudaStream_t st) {

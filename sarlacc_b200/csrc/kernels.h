@@ -107,6 +107,13 @@ struct SelectArgs {
 };
 void launch_resolve_select(const SelectArgs& s, cudaStream_t st);
 
+/* .scramble_input (R/getAdaptorThresholds.R:68-92) on packed rows: out[a][rank(i)] = in[a][i], where rank orders the
+ * counter-based keys mix64(mix64(index_a * K1 + seed) ^ (i * K2 + stream * K3)) (ties by position) -- the same
+ * permutation sarlacc_b200/api.py:_scramble_input builds on the host. */
+void launch_scramble(const uint16_t* in, uint16_t* out, const int32_t* lens, long long n, int stride,
+                     unsigned long long seed, unsigned long long first_index, const unsigned long long* read_index,
+                     unsigned long long stream_id, cudaStream_t st);
+
 /* Launchers (return the kernel's name for reporting; throw nothing, errors via cudaGetLastError). */
 const char* launch_wavefront(const AlignArgs& a, bool trace, bool has_alt, int grid, cudaStream_t st);
 const char* launch_generic(const AlignArgs& a, bool trace, int grid, cudaStream_t st);

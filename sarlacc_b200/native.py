@@ -209,7 +209,12 @@ class Resident:
 
     MODE_SCORE_LOCAL, MODE_TRACE_LOCAL, MODE_SCORE_GLOBAL = 0, 1, 2
 
-    def __init__(self, reads, encoding, device=0, views=False, seq_encoding=SEQ_ASCII):
+    def __init__(self, reads, encoding, device=0, views=False, seq_encoding=SEQ_ASCII, _handle=None):
+        if _handle is not None:
+            self.handle = _handle
+            self.n = int(_lib.lib.sarlacc_resident_n(self.handle))
+            self.nsec = 0
+            return
         ra = _reads_arg(reads, views, seq_encoding)
         ea = _encoding_arg(encoding)
         self.handle = _lib.lib.sarlacc_resident_create(ra.ref(), ea.ref(), C.c_int(device))
@@ -224,6 +229,23 @@ class Resident:
             self.handle = None
 
     __del__ = close
+
+    def scrambled(self, seed=0, first_index=0, read_index=None, stream_id=0):
+        """Device-side .scramble_input: a new Resident whose windows are keyed random permutations of this one's."""
+        idx = None if read_index is None else np.ascontiguousarray(read_index, dtype=np.uint64)
+        h = _lib.lib.sarlacc_resident_scrambled(self.handle, C.c_uint64(int(seed)), C.c_uint64(int(first_index)), _lib._ptr(idx), C.c_int(int(stream_id)))
+        if not h:
+            raise SarlaccError(_lib.last_error())
+        return Resident(None, None, _handle=h)
+
+    def rows(self):
+        """Packed rows (uint16[n][stride]) and lengths, downloaded (tests)."""
+        stride = C.c_int(0)
+        _lib.check(_lib.lib.sarlacc_resident_rows(self.handle, None, None, C.byref(stride)))
+        rows = np.zeros((max(self.n, 1), stride.value), np.uint16)
+        lens = np.zeros(max(self.n, 1), np.int32)
+        _lib.check(_lib.lib.sarlacc_resident_rows(self.handle, _lib._ptr(rows), _lib._ptr(lens), C.byref(stride)))
+        return rows[:self.n], lens[:self.n]
 
     def cells(self, rlen):
         return int(_lib.lib.sarlacc_resident_cells(self.handle, C.c_int(rlen)))

@@ -116,9 +116,40 @@ def test_get_adaptor_thresholds(port, enc):
     assert np.array_equal(th["scores1"]["reads"], aligned["adaptor1"]["score"])
     # real adaptors score far above scrambled windows
     assert np.median(th["scores1"]["reads"]) > np.max(th["scores1"]["scrambled"])
+    # the host (numpy) scramble + four reference-style calls give the same numbers as the device scramble
+    th_host = api.getAdaptorThresholds(aligned, error=0.01, number=50, seed=3, device_scramble=False)
+    assert np.array_equal(th_host["scores1"]["scrambled"], th["scores1"]["scrambled"])
+    assert np.array_equal(th_host["scores2"]["scrambled"], th["scores2"]["scrambled"])
     # chunking must not change anything
     th2 = api.getAdaptorThresholds(aligned, error=0.01, number=1000, seed=3)
     assert np.array_equal(th2["scores1"]["scrambled"], th["scores1"]["scrambled"]) and th2["threshold2"] == th["threshold2"] or np.isnan(th["threshold2"])
+
+
+def test_device_scramble_matches_host_permutation(enc):
+    """sarlacc_resident_scrambled == api._scramble_input row for row (same keyed permutation), ragged lengths included."""
+    from sarlacc_b200 import api, native, ReadSet
+    from conftest import random_windows
+    rng = np.random.default_rng(12)
+    seqs, quals = random_windows(rng, 300, VIGNETTE_A2, 0, 260, 0, 60)
+    rs = ReadSet.from_strings(seqs, quals)
+    r = native.Resident(rs, enc)
+    for seed, first, stream in [(0, 0, 0), (7, 1000, 1), (2 ** 40 + 5, 123456789, 0)]:
+        d = r.scrambled(seed, first_index=first, stream_id=stream)
+        rows, lens = d.rows()
+        h = native.Resident(api._scramble_input(rs, True, seed, first, stream), enc)
+        hrows, hlens = h.rows()
+        assert np.array_equal(lens, hlens)
+        for i in range(len(rs)):
+            assert np.array_equal(rows[i, :lens[i]], hrows[i, :lens[i]]), (seed, i)
+        d.close()
+        h.close()
+    idx = rng.permutation(5000)[:300].astype(np.uint64)
+    d = r.scrambled(9, read_index=idx, stream_id=1)
+    h = native.Resident(api._scramble_by_index(rs, 9, idx, 1), enc)
+    a, la = d.rows()
+    b, lb = h.rows()
+    assert all(np.array_equal(a[i, :la[i]], b[i, :lb[i]]) for i in range(len(rs)))
+    r.close()
 
 
 def test_barcode_align(port, enc):
