@@ -273,3 +273,54 @@ def test_full_size_properties(port, enc):
     assert np.array_equal(a[0][idx], exp[0]) and np.array_equal(a[1][idx], exp[1]) and np.array_equal(a[2][idx], exp[2])
     for s in range(2):
         assert np.array_equal(a[3][s][idx], exp[3][s]) and np.array_equal(a[4][s][idx], exp[4][s])
+
+
+def test_multi_device_sharding_in_one_process(port, enc):
+    """sarlacc_set_devices: contiguous read-index shards over every visible GPU, results identical to one device
+    (and to the oracle).  With a single GPU this degenerates to listing device 0 twice-over shards."""
+    import ctypes
+    from sarlacc_b200 import native, _lib
+    from conftest import random_windows
+    ndev = _lib.lib.sarlacc_device_count()
+    rng = np.random.default_rng(21)
+    seqs, quals = random_windows(rng, 1500, VIGNETTE_A2, 5, 120)
+    exp = port.adaptor_align(seqs, quals, enc, 5, 1, "AAGGCCTTNNNNCGACTCATGAA", [8], [12], nthreads=4)
+    devs = list(range(ndev))
+    try:
+        _lib.check(_lib.lib.sarlacc_set_devices((ctypes.c_int * len(devs))(*devs), len(devs)))
+        got = native.adaptor_align((seqs, quals), enc, 5, 1, "AAGGCCTTNNNNCGACTCATGAA", [8], [12])
+        assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1]) and np.array_equal(got[2], exp[2])
+        assert np.array_equal(got[3][0], exp[3][0]) and np.array_equal(got[4][0], exp[4][0])
+        bid, best, nxt = native.barcode_align_multi((seqs, quals), enc, 5, 1, ["AAGGCCTTTTCCGACTCATGAA", "AAGGCCTTTTCCGACTCATGTT"])
+        e0 = port.align_score_only(seqs, quals, enc, 5, 1, "AAGGCCTTTTCCGACTCATGAA", local=False)
+        e1 = port.align_score_only(seqs, quals, enc, 5, 1, "AAGGCCTTTTCCGACTCATGTT", local=False)
+        assert np.array_equal(best, np.maximum(e0, e1)) and np.array_equal(bid, np.where(e1 > e0, 2, 1))
+        with pytest.raises(native.SarlaccError, match="device index out of range"):
+            _lib.check(_lib.lib.sarlacc_set_devices((ctypes.c_int * 1)(ndev + 3), 1))
+    finally:
+        _lib.check(_lib.lib.sarlacc_set_devices((ctypes.c_int * 1)(0), 1))
+
+
+def test_long_reads_and_long_references(port, enc):
+    """Rows stream through the wavefront, so read length is unbounded; references up to 256 columns use it too,
+    longer ones the literal kernel.  (qualityAlign-style global alignment of kilobase sequences.)"""
+    from sarlacc_b200 import native
+    rng = np.random.default_rng(33)
+    ref = "".join(rng.choice(list("ACGT"), size=200))
+    seqs, quals = [], []
+    for _ in range(40):
+        n = int(rng.integers(1500, 3000))
+        s = rng.choice(list("ACGT"), size=n).tolist()
+        p = int(rng.integers(0, n - 250))
+        s[p:p + 200] = list(ref)
+        seqs.append("".join(s))
+        quals.append("".join(chr(33 + int(q)) for q in rng.integers(5, 40, size=n)))
+    got = native.adaptor_align((seqs, quals), enc, 5, 1, ref, [10, 100], [20, 150])
+    exp = port.adaptor_align(seqs, quals, enc, 5, 1, ref, [10, 100], [20, 150], nthreads=8)
+    for a, b in zip(got[:3], exp[:3]):
+        assert np.array_equal(a, b)
+    for s in range(2):
+        assert np.array_equal(got[3][s], exp[3][s]) and np.array_equal(got[4][s], exp[4][s])
+    g = native.general_align((seqs[:10], quals[:10]), enc, 4, 1, ref)
+    e = port.general_align(seqs[:10], quals[:10], enc, 4, 1, ref)
+    assert np.array_equal(g[0], e[0]) and np.array_equal(g[1], e[1]) and g[2] == e[2] and g[3] == e[3]
