@@ -133,6 +133,18 @@ int sarlacc_adaptor_align_windows(const sarlacc_reads* front, const sarlacc_read
         double* score1, int32_t* start1, int32_t* end1, int32_t* sec_start1, int32_t* sec_width1,
         double* score2, int32_t* start2, int32_t* end2, int32_t* sec_start2, int32_t* sec_width2);
 
+/* The same with WHOLE reads in and .get_front_and_back (R/adaptorAlign.R:86-95) done by the packer: front window =
+ * first min(tolerance, width) bases, back window = reverse complement of the last min(tolerance, width) bases, cut
+ * and complemented on the fly while packing (never materialised on the host).  read_width[n] receives width(reads);
+ * adaptor2's start/end are always flipped into read coordinates (width - x + 1).  Needs two non-empty adaptors. */
+int sarlacc_adaptor_align_reads(const sarlacc_reads* reads, int tolerance, const sarlacc_encoding* encoding,
+        double gapopen, double gapext, const char* adaptor1, const char* adaptor2,
+        int nsec1, const int32_t* sec_starts1, const int32_t* sec_ends1,
+        int nsec2, const int32_t* sec_starts2, const int32_t* sec_ends2,
+        int32_t* read_width, uint8_t* reversed,
+        double* score1, int32_t* start1, int32_t* end1, int32_t* sec_start1, int32_t* sec_width1,
+        double* score2, int32_t* start2, int32_t* end2, int32_t* sec_start2, int32_t* sec_width2);
+
 /* ---- resident read windows -----------------------------------------------------------------------
  * Packs the reads once (2 bytes per base: quality index + one-hot base), uploads them and keeps them
  * in HBM.  The *_resident calls then run on that copy; results stay on the device until fetched.

@@ -43,7 +43,7 @@ EXPORTS = [
     "sarlacc_last_error", "sarlacc_device_count", "sarlacc_set_devices", "sarlacc_set_host_threads",
     "sarlacc_version", "sarlacc_kernel_launches",
     "sarlacc_adaptor_align", "sarlacc_adaptor_align_score_only", "sarlacc_barcode_align", "sarlacc_general_align",
-    "sarlacc_barcode_align_multi", "sarlacc_adaptor_align_windows",
+    "sarlacc_barcode_align_multi", "sarlacc_adaptor_align_windows", "sarlacc_adaptor_align_reads",
     "sarlacc_resident_create", "sarlacc_resident_free", "sarlacc_resident_n", "sarlacc_resident_cells",
     "sarlacc_resident_bytes", "sarlacc_resident_align", "sarlacc_resident_fetch",
     "sarlacc_resident_scores_device", "sarlacc_resident_last_kernel",

@@ -199,27 +199,40 @@ def _align_AA_internal(reads, adaptor1, adaptor2, tolerance, subseq1, subseq2, g
     return {"names": reads.names, "width": reads.width(), "start": cur_starts, "end": cur_ends, "reversed": is_reverse}
 
 
+def _window_subseq(reads, use_back, start, width):
+    """subseq(window, start, width) without materialising the windows of .get_front_and_back: rows with use_back
+    take it from the reverse-complemented tail of the read (window position p <-> read position W - p + 1)."""
+    W = reads.width()
+    start = np.asarray(start, dtype=np.int64)
+    width = np.asarray(width, dtype=np.int64)
+    fwd = reads.subseq(start=np.where(use_back, 1, start), width=np.where(use_back, 0, width))
+    bstart = np.where(use_back, W - start - width + 2, 1)
+    bwd = reads.subseq(start=bstart, width=np.where(use_back, width, 0)).reverse_complement()
+    return _readset_where(use_back, bwd, fwd)
+
+
 def _align_AA_internal_fused(reads, adaptor1, adaptor2, tolerance, subseq1, subseq2, gap_opening, gap_extension, encoding=None):
-    """_align_AA_internal with the four .Calls, .resolve_strand and the row selection done in one device pass
-    (sarlacc_adaptor_align_windows).  Same return value."""
+    """_align_AA_internal with window cutting, the four .Calls, .resolve_strand and the row selection done in one
+    library call (sarlacc_adaptor_align_reads).  Same return value, except that adaptor2's start/end are already in
+    read coordinates (flagged by "flipped")."""
     enc = encoding or native.phred_encoding()
-    w = _get_front_and_back(reads, tolerance)
-    rev, r1, r2 = native.adaptor_align_windows(
-        w["front"], w["back"], enc, gap_opening, gap_extension, adaptor1, adaptor2,
+    if len(adaptor1) == 0 or len(adaptor2) == 0 or len(reads) == 0:
+        return _align_AA_internal(reads, adaptor1, adaptor2, tolerance, subseq1, subseq2, gap_opening, gap_extension, encoding)
+    width, rev, r1, r2 = native.adaptor_align_reads(
+        reads, tolerance, enc, gap_opening, gap_extension, adaptor1, adaptor2,
         (np.asarray(subseq1["starts"], dtype=np.int32) - 1, subseq1["ends"]),
         (np.asarray(subseq2["starts"], dtype=np.int32) - 1, subseq2["ends"]))
-    # the sections were located on the window that was kept: front for adaptor1 / back for adaptor2, swapped if reversed
-    src = (_readset_where(rev, w["back"], w["front"]) if len(r1[3]) else None,
-           _readset_where(rev, w["front"], w["back"]) if len(r2[3]) else None)
     frames = []
-    for out, windows in ((r1, src[0]), (r2, src[1])):
+    # the sections were located on the window that was kept: front for adaptor1 / back for adaptor2, swapped if reversed
+    for out, use_back in ((r1, rev), (r2, ~rev)):
         f = Frame({"score": out[0], "start": out[1], "end": out[2]})
         seg = Frame(nrows=len(reads))
         for i in range(len(out[3])):
-            seg["Sub%d" % (i + 1)] = windows.subseq(start=out[3][i], width=out[4][i])
+            seg["Sub%d" % (i + 1)] = _window_subseq(reads, use_back, out[3][i], out[4][i])
         f["subseq"] = seg
         frames.append(f)
-    return {"names": reads.names, "width": reads.width(), "start": frames[0], "end": frames[1], "reversed": rev}
+    return {"names": reads.names, "width": width.astype(np.int64), "start": frames[0], "end": frames[1], "reversed": rev,
+            "flipped": True}
 
 
 def _stream(source, number):
@@ -255,6 +268,11 @@ def adaptorAlign(adaptor1, adaptor2, filepath, tolerance=250, gapOpening=5, gapE
     internal = _align_AA_internal_fused if fused else _align_AA_internal
     for reads in _stream(filepath, number):
         out = internal(reads, **all_args)
+        if out.get("flipped"):
+            # undo the library's adaptor2 flip so that the single flip below (R/adaptorAlign.R:66-71) applies to every chunk
+            w = out["width"]
+            out["end"]["start"] = (w - out["end"]["start"] + 1).astype(np.int32)
+            out["end"]["end"] = (w - out["end"]["end"] + 1).astype(np.int32)
         names.append(out["names"] if out["names"] is not None else [None] * len(reads))
         widths.append(out["width"])
         starts.append(out["start"])

@@ -218,16 +218,35 @@ void build_plan(Plan& P, const Encoding& enc, const char* const* refs, int nref,
 
 /* ---- read access + packing --------------------------------------------------------------------- */
 
+/* A view of the reads, optionally restricted to the window .get_front_and_back (R/adaptorAlign.R:86-95) would cut:
+ * tol > 0, back == false: the first min(tol, width) bases; back == true: the reverse complement of the last
+ * min(tol, width) bases (qualities reversed with them) -- produced on the fly by the packer, never materialised. */
 struct ReadView {
     const sarlacc_reads* R;
-    inline int64_t seq_len(int64_t i) const { return R->seq ? R->seq_len[i] : R->seq_off[i + 1] - R->seq_off[i]; }
-    inline int64_t qual_len(int64_t i) const { return R->seq ? R->qual_len[i] : R->qual_off[i + 1] - R->qual_off[i]; }
-    inline const uint8_t* seq(int64_t i) const { return R->seq ? R->seq[i] : R->seq_pool + R->seq_off[i]; }
-    inline const uint8_t* qual(int64_t i) const { return R->seq ? R->qual[i] : R->qual_pool + R->qual_off[i]; }
+    int tol = 0;
+    bool back = false;
+    inline int64_t full_seq_len(int64_t i) const { return R->seq ? R->seq_len[i] : R->seq_off[i + 1] - R->seq_off[i]; }
+    inline int64_t full_qual_len(int64_t i) const { return R->seq ? R->qual_len[i] : R->qual_off[i + 1] - R->qual_off[i]; }
+    inline int64_t clip(int64_t n) const { return (tol > 0 && n > tol) ? tol : n; }
+    inline int64_t seq_len(int64_t i) const { return clip(full_seq_len(i)); }
+    inline int64_t qual_len(int64_t i) const {
+        /* a length mismatch of the whole read must stay visible after clipping */
+        const int64_t s = full_seq_len(i), q = full_qual_len(i);
+        return (s == q) ? clip(q) : (clip(s) == clip(q) ? clip(q) + 1 : clip(q));
+    }
+    inline const uint8_t* seq(int64_t i) const {
+        const uint8_t* p = R->seq ? R->seq[i] : R->seq_pool + R->seq_off[i];
+        return back ? p + (full_seq_len(i) - seq_len(i)) : p;
+    }
+    inline const uint8_t* qual(int64_t i) const {
+        const uint8_t* p = R->seq ? R->qual[i] : R->qual_pool + R->qual_off[i];
+        return back ? p + (full_qual_len(i) - clip(full_qual_len(i))) : p;
+    }
 };
 
 struct PackTables {
     uint8_t base[256];
+    uint8_t base_rc[256];   /* one-hot code of the complement (A<->T, C<->G); 0 for everything else */
     /* quality byte -> index, or 0xFFFF when below the offset (signed char comparison, :215) */
     uint16_t qidx[256];
 };
@@ -240,6 +259,8 @@ void build_pack_tables(PackTables& T, int seq_encoding, const Encoding& enc) {
         T.base[(unsigned char)'A'] = 1; T.base[(unsigned char)'C'] = 2;
         T.base[(unsigned char)'G'] = 4; T.base[(unsigned char)'T'] = 8;
     }
+    static const uint8_t comp[16] = {0, 8, 4, 0, 2, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0};
+    for (int b = 0; b < 256; ++b) T.base_rc[b] = comp[T.base[b] & 15];
     for (int b = 0; b < 256; ++b) {
         const char q = (char)(unsigned char)b;
         if (q < enc.offset) {
@@ -338,10 +359,18 @@ void pack_rows(const ReadView& V, int64_t lo, int64_t hi, const PackTables& T, c
             const uint8_t* s = V.seq(i);
             const uint8_t* q = V.qual(i);
             unsigned bad = 0;
-            for (int r = 0; r < len; ++r) {
-                const unsigned qi = T.qidx[q[r]];
-                bad |= qi;
-                out[r] = (uint16_t)((qi & 0xFFu) | ((unsigned)T.base[s[r]] << 8));
+            if (!V.back) {
+                for (int r = 0; r < len; ++r) {
+                    const unsigned qi = T.qidx[q[r]];
+                    bad |= qi;
+                    out[r] = (uint16_t)((qi & 0xFFu) | ((unsigned)T.base[s[r]] << 8));
+                }
+            } else {
+                for (int r = 0; r < len; ++r) {
+                    const unsigned qi = T.qidx[q[len - 1 - r]];
+                    bad |= qi;
+                    out[r] = (uint16_t)((qi & 0xFFu) | ((unsigned)T.base_rc[s[len - 1 - r]] << 8));
+                }
             }
             if (check_qual && (bad & 0xFF00u)) errs[t].offer(i, ERR_QUAL);
         }
@@ -1091,6 +1120,8 @@ struct PairJob {
     const sarlacc_reads* back = nullptr;
     const Plan* plan[2] = {nullptr, nullptr};   /* adaptor1, adaptor2 */
     const int32_t* width = nullptr;
+    int tolerance = 0;          /* > 0: `front` holds WHOLE reads; both windows are cut (and the back one reverse-complemented) by the packer */
+    int32_t* width_out = nullptr;
     PairOutputs out;
     int nthreads = 1;
     FirstError err_front, err_back;
@@ -1110,9 +1141,13 @@ struct PairJob {
         CUDA_CHECK(cudaSetDevice(device));
         const int sms = device_sm_count(device);
         ReadView VF{front}, VB{back};
+        if (tolerance > 0) {
+            VF.tol = tolerance;
+            VB = ReadView{front, tolerance, true};
+        }
         PackTables PF, PB;
         build_pack_tables(PF, front->seq_encoding, *plan[0]->enc);
-        build_pack_tables(PB, back->seq_encoding, *plan[0]->enc);
+        build_pack_tables(PB, VB.R->seq_encoding, *plan[0]->enc);
         const int nsec[2] = {(int)plan[0]->sec_starts.size(), (int)plan[1]->sec_starts.size()};
         DeviceCache& cache = DeviceCache::acquire(device);
         struct Release {
@@ -1218,10 +1253,18 @@ struct PairJob {
             CUDA_CHECK(cudaMemcpyAsync(s.d_rows2.p, s.h_rows2.p, sizeof(uint16_t) * (size_t)m * stride_b, cudaMemcpyHostToDevice, s.st));
             CUDA_CHECK(cudaMemcpyAsync(s.d_lens.p, s.h_lens.p, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
             CUDA_CHECK(cudaMemcpyAsync(s.d_lens2.p, s.h_lens2.p, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
-            if (width) {
+            if (width || tolerance > 0) {
                 s.h_width.reserve(sizeof(int32_t) * (size_t)m);
                 s.d_width.reserve(sizeof(int32_t) * (size_t)m);
-                std::memcpy(s.h_width.p, width + c0, sizeof(int32_t) * (size_t)m);
+                if (tolerance > 0) {
+                    int32_t* hw = s.h_width.as<int32_t>();
+                    for (int64_t i = 0; i < m; ++i) {
+                        hw[i] = (int32_t)VF.full_seq_len(c0 + i);
+                        if (width_out) width_out[c0 + i] = hw[i];
+                    }
+                } else {
+                    std::memcpy(s.h_width.p, width + c0, sizeof(int32_t) * (size_t)m);
+                }
                 CUDA_CHECK(cudaMemcpyAsync(s.d_width.p, s.h_width.p, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
             }
             uint8_t* t = s.d_tmp.as<uint8_t>();
@@ -1247,7 +1290,7 @@ struct PairJob {
             S.n = m;
             S.a1_front = rs[0]; S.a2_back = rs[1]; S.a1_back = rs[2]; S.a2_front = rs[3];
             S.nsec1 = nsec[0]; S.nsec2 = nsec[1];
-            S.width = width ? s.d_width.as<int32_t>() : nullptr;
+            S.width = (width || tolerance > 0) ? s.d_width.as<int32_t>() : nullptr;
             S.reversed = d + F.o_rev;
             S.score1 = reinterpret_cast<double*>(d + F.o_score[0]); S.score2 = reinterpret_cast<double*>(d + F.o_score[1]);
             S.start1 = reinterpret_cast<int32_t*>(d + F.o_start[0]); S.start2 = reinterpret_cast<int32_t*>(d + F.o_start[1]);
@@ -1414,11 +1457,11 @@ int sarlacc_general_align(const sarlacc_reads* reads, const sarlacc_encoding* en
     return 0;
 }
 
-int sarlacc_adaptor_align_windows(const sarlacc_reads* front, const sarlacc_reads* back, const sarlacc_encoding* encoding,
+static int align_pair(const sarlacc_reads* front, const sarlacc_reads* back, int tolerance, const sarlacc_encoding* encoding,
         double gapopen, double gapext, const char* adaptor1, const char* adaptor2,
         int nsec1, const int32_t* sec_starts1, const int32_t* sec_ends1,
         int nsec2, const int32_t* sec_starts2, const int32_t* sec_ends2,
-        const int32_t* read_width, uint8_t* reversed,
+        const int32_t* read_width, int32_t* width_out, uint8_t* reversed,
         double* score1, int32_t* start1, int32_t* end1, int32_t* sec_start1, int32_t* sec_width1,
         double* score2, int32_t* start2, int32_t* end2, int32_t* sec_start2, int32_t* sec_width2)
 {
@@ -1432,6 +1475,7 @@ int sarlacc_adaptor_align_windows(const sarlacc_reads* front, const sarlacc_read
     const int64_t n = front->n;
     const int L1 = (int)std::strlen(adaptor1), L2 = (int)std::strlen(adaptor2);
     if (n == 0) return 0;
+    if ((L1 == 0 || L2 == 0) && tolerance > 0) return fail("the fused whole-read entry needs two non-empty adaptors");
     if (L1 == 0 || L2 == 0) {
         /* degenerate adaptors: compose the four reference calls on the host side of the ABI */
         std::vector<double> sc[4];
@@ -1498,6 +1542,8 @@ int sarlacc_adaptor_align_windows(const sarlacc_reads* front, const sarlacc_read
         J.plan[0] = &P[0];
         J.plan[1] = &P[1];
         J.width = read_width;
+        J.tolerance = tolerance;
+        J.width_out = width_out;
         J.out.reversed = reversed;
         J.out.score[0] = score1; J.out.start[0] = start1; J.out.end[0] = end1; J.out.sec_start[0] = sec_start1; J.out.sec_width[0] = sec_width1;
         J.out.score[1] = score2; J.out.start[1] = start2; J.out.end[1] = end2; J.out.sec_start[1] = sec_start2; J.out.sec_width[1] = sec_width2;
@@ -1517,6 +1563,10 @@ int sarlacc_adaptor_align_windows(const sarlacc_reads* front, const sarlacc_read
     FirstError ef, eb;
     for (int d = 0; d < nd; ++d) { ef.merge(jobs[d].err_front); eb.merge(jobs[d].err_back); }
     ReadView VF{front}, VB{back};
+    if (tolerance > 0) {
+        VF.tol = tolerance;
+        VB = ReadView{front, tolerance, true};
+    }
     const FirstError* base[4] = {&ef, &eb, &eb, &ef};
     const ReadView* views[4] = {&VF, &VB, &VB, &VF};
     const Plan* plans[4] = {&P[0], &P[1], &P[0], &P[1]};
@@ -1526,6 +1576,33 @@ int sarlacc_adaptor_align_windows(const sarlacc_reads* front, const sarlacc_read
         if (e.kind != ERR_NONE) return fail(err_text(e.kind));
     }
     return 0;
+}
+
+int sarlacc_adaptor_align_windows(const sarlacc_reads* front, const sarlacc_reads* back, const sarlacc_encoding* encoding,
+        double gapopen, double gapext, const char* adaptor1, const char* adaptor2,
+        int nsec1, const int32_t* sec_starts1, const int32_t* sec_ends1,
+        int nsec2, const int32_t* sec_starts2, const int32_t* sec_ends2,
+        const int32_t* read_width, uint8_t* reversed,
+        double* score1, int32_t* start1, int32_t* end1, int32_t* sec_start1, int32_t* sec_width1,
+        double* score2, int32_t* start2, int32_t* end2, int32_t* sec_start2, int32_t* sec_width2)
+{
+    return align_pair(front, back, 0, encoding, gapopen, gapext, adaptor1, adaptor2, nsec1, sec_starts1, sec_ends1,
+                      nsec2, sec_starts2, sec_ends2, read_width, nullptr, reversed,
+                      score1, start1, end1, sec_start1, sec_width1, score2, start2, end2, sec_start2, sec_width2);
+}
+
+int sarlacc_adaptor_align_reads(const sarlacc_reads* reads, int tolerance, const sarlacc_encoding* encoding,
+        double gapopen, double gapext, const char* adaptor1, const char* adaptor2,
+        int nsec1, const int32_t* sec_starts1, const int32_t* sec_ends1,
+        int nsec2, const int32_t* sec_starts2, const int32_t* sec_ends2,
+        int32_t* read_width, uint8_t* reversed,
+        double* score1, int32_t* start1, int32_t* end1, int32_t* sec_start1, int32_t* sec_width1,
+        double* score2, int32_t* start2, int32_t* end2, int32_t* sec_start2, int32_t* sec_width2)
+{
+    if (tolerance <= 0) return fail("tolerance should be a positive integer");
+    return align_pair(reads, reads, tolerance, encoding, gapopen, gapext, adaptor1, adaptor2, nsec1, sec_starts1, sec_ends1,
+                      nsec2, sec_starts2, sec_ends2, nullptr, read_width, reversed,
+                      score1, start1, end1, sec_start1, sec_width1, score2, start2, end2, sec_start2, sec_width2);
 }
 
 /* ---- resident windows ------------------------------------------------------------------------- */

@@ -204,6 +204,43 @@ def adaptor_align_windows(front, back, encoding, gapopen, gapext, adaptor1, adap
     return rev[:n].astype(bool), res[0], res[1]
 
 
+def adaptor_align_reads(reads, tolerance, encoding, gapopen, gapext, adaptor1, adaptor2, sec1=((), ()), sec2=((), ()),
+                        views=False, seq_encoding=SEQ_ASCII):
+    """Whole reads in: windows cut / reverse-complemented by the packer (sarlacc_adaptor_align_reads).  Returns
+    read_width, reversed and the two result lists (adaptor2 coordinates already flipped into read coordinates)."""
+    a1 = _string(adaptor1, "adaptor sequence")
+    a2 = _string(adaptor2, "adaptor sequence")
+    go = _numeric_scalar(gapopen, "gap opening penalty")
+    ge = _numeric_scalar(gapext, "gap extension penalty")
+    rr = _reads_arg(reads, views, seq_encoding)
+    ea = _encoding_arg(encoding)
+    n = rr.n
+    secs = []
+    for st, en in (sec1, sec2):
+        ss = np.ascontiguousarray(st, dtype=np.int32).reshape(-1)
+        se = np.ascontiguousarray(en, dtype=np.int32).reshape(-1)
+        if len(ss) != len(se):
+            raise SarlaccError("section starts and ends should have the same length")
+        secs.append((ss, se))
+    width = np.zeros(max(n, 1), np.int32)
+    rev = np.zeros(max(n, 1), np.uint8)
+    outs = []
+    for ss, se in secs:
+        outs.append([np.zeros(n, np.float64), np.zeros(n, np.int32), np.zeros(n, np.int32),
+                     np.zeros((max(len(ss), 1), max(n, 1)), np.int32), np.zeros((max(len(ss), 1), max(n, 1)), np.int32)])
+    _lib.check(_lib.lib.sarlacc_adaptor_align_reads(
+        rr.ref(), C.c_int(int(tolerance)), ea.ref(), C.c_double(go), C.c_double(ge), a1.encode("latin-1"), a2.encode("latin-1"),
+        C.c_int(len(secs[0][0])), _lib._ptr(secs[0][0]), _lib._ptr(secs[0][1]),
+        C.c_int(len(secs[1][0])), _lib._ptr(secs[1][0]), _lib._ptr(secs[1][1]),
+        _lib._ptr(width), _lib._ptr(rev),
+        *[_lib._ptr(x) for x in outs[0]], *[_lib._ptr(x) for x in outs[1]]))
+    res = []
+    for k, (ss, se) in enumerate(secs):
+        o = outs[k]
+        res.append([o[0], o[1], o[2], [o[3][i, :n].copy() for i in range(len(ss))], [o[4][i, :n].copy() for i in range(len(ss))]])
+    return width[:n], rev[:n].astype(bool), res[0], res[1]
+
+
 class Resident:
     """Read windows packed once and kept in HBM (sarlacc_resident_*)."""
 

@@ -97,6 +97,35 @@ def test_fused_windows_entry(port, enc, monkeypatch):
         native.adaptor_align_windows(front[np.arange(5)], back[np.arange(4)], enc, 5, 1, VIGNETTE_A1, VIGNETTE_A2)
 
 
+def test_fused_whole_read_entry(port, enc):
+    """sarlacc_adaptor_align_reads: windows cut and reverse-complemented by the packer == .get_front_and_back + the
+    four calls, for reads shorter and longer than the tolerance, odd characters and Biostrings byte codes."""
+    from sarlacc_b200 import api, native, synth, ReadSet, SEQ_BIOSTRINGS
+    from oracle import r_level as R
+    reads = synth.mock_reads(150, VIGNETTE_A1, VIGNETTE_A2, seed=41, insert_range=(10, 900))
+    seqs, quals = reads.seq_strings(), reads.qual_strings()
+    seqs[3] = seqs[3][:40] + "NNRYK" + seqs[3][45:]          # IUPAC codes in a read: never match, complement irrelevant
+    seqs[5], quals[5] = "", ""
+    rs = ReadSet.from_strings(seqs, quals, reads.names)
+    for tol in (250, 60):
+        width, rev, r1, r2 = native.adaptor_align_reads(rs, tol, enc, 5, 1, VIGNETTE_A1, VIGNETTE_A2, ([16, 42], [28, 46]), ((), ()))
+        exp = R.adaptor_align_R(port, enc, VIGNETTE_A1, VIGNETTE_A2, seqs, quals, tolerance=tol)
+        assert width.tolist() == [len(x) for x in seqs] and rev.tolist() == [e["reversed"] for e in exp]
+        assert np.array_equal(r1[0], np.array([e["adaptor1"]["score"] for e in exp]))
+        assert r1[1].tolist() == [e["adaptor1"]["start"] for e in exp] and r1[2].tolist() == [e["adaptor1"]["end"] for e in exp]
+        assert np.array_equal(r2[0], np.array([e["adaptor2"]["score"] for e in exp]))
+        assert r2[1].tolist() == [e["adaptor2"]["start"] for e in exp] and r2[2].tolist() == [e["adaptor2"]["end"] for e in exp]
+        out = api.adaptorAlign(VIGNETTE_A1, VIGNETTE_A2, rs, tolerance=tol, number=64)
+        compare_adaptor_align(out, exp)
+    code = {"A": 1, "C": 2, "G": 4, "T": 8, "N": 15, "R": 5, "Y": 10, "K": 12}
+    coded = ReadSet.from_strings([bytes(code[c] for c in s) for s in seqs], quals)
+    w2, rev2, q1, q2 = native.adaptor_align_reads(coded, 250, enc, 5, 1, VIGNETTE_A1, VIGNETTE_A2, seq_encoding=SEQ_BIOSTRINGS)
+    width, rev, r1, r2 = native.adaptor_align_reads(rs, 250, enc, 5, 1, VIGNETTE_A1, VIGNETTE_A2)
+    assert np.array_equal(rev2, rev) and np.array_equal(q1[0], r1[0]) and np.array_equal(q2[1], r2[1])
+    with pytest.raises(native.SarlaccError, match="two non-empty adaptors"):
+        native.adaptor_align_reads(rs, 250, enc, 5, 1, "", VIGNETTE_A2)
+
+
 def test_get_adaptor_thresholds(port, enc):
     from sarlacc_b200 import api, synth
     from oracle import r_level as R
