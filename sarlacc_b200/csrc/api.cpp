@@ -17,10 +17,14 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
+#include <functional>
 #include <limits>
 #include <memory>
 #include <mutex>
@@ -306,6 +310,88 @@ int host_threads_for(int ndev) {
     return t;
 }
 
+/* Persistent worker pool for the packer (thread creation per chunk showed up in the end-to-end profile). */
+class WorkerPool {
+public:
+    static WorkerPool& instance() {
+        static WorkerPool pool;
+        return pool;
+    }
+    /* Runs fn(k) for k in [0, ntasks) on the pool (the caller takes part) and returns when all are done. */
+    void run(int ntasks, const std::function<void(int)>& fn) {
+        if (ntasks <= 1) {
+            if (ntasks == 1) fn(0);
+            return;
+        }
+        auto job = std::make_shared<Job>();
+        job->fn = &fn;
+        job->total = ntasks;
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            grow(ntasks - 1);
+            queue_.push_back(job);
+        }
+        cv_.notify_all();
+        work_on(*job);
+        std::unique_lock<std::mutex> lock(job->m);
+        job->cv.wait(lock, [&] { return job->done == job->total; });
+    }
+
+private:
+    struct Job {
+        const std::function<void(int)>* fn = nullptr;
+        int total = 0;
+        std::atomic<int> next{0};
+        int done = 0;
+        std::mutex m;
+        std::condition_variable cv;
+    };
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<std::shared_ptr<Job> > queue_;
+    std::vector<std::thread> threads_;
+    bool stop_ = false;
+
+    WorkerPool() {}
+    ~WorkerPool() {
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    void grow(int want) {   /* m_ held */
+        want = std::min(want, 64);
+        while ((int)threads_.size() < want) threads_.emplace_back([this] { loop(); });
+    }
+    static void work_on(Job& job) {
+        for (;;) {
+            const int k = job.next.fetch_add(1);
+            if (k >= job.total) break;
+            (*job.fn)(k);
+            std::lock_guard<std::mutex> lock(job.m);
+            if (++job.done == job.total) job.cv.notify_all();
+        }
+    }
+    void loop() {
+        for (;;) {
+            std::shared_ptr<Job> job;
+            {
+                std::unique_lock<std::mutex> lock(m_);
+                cv_.wait(lock, [&] { return stop_ || !queue_.empty(); });
+                if (stop_) return;
+                job = queue_.front();
+                if (job->next.load() >= job->total) {
+                    queue_.pop_front();
+                    continue;
+                }
+            }
+            work_on(*job);
+        }
+    }
+};
+
 template <class F>
 void parallel_for(int64_t lo, int64_t hi, int nthreads, F body) {
     const int64_t n = hi - lo;
@@ -315,12 +401,11 @@ void parallel_for(int64_t lo, int64_t hi, int nthreads, F body) {
         body(lo, hi, 0);
         return;
     }
-    std::vector<std::thread> pool;
-    for (int t = 0; t < nthreads; ++t) {
+    const std::function<void(int)> task = [&](int t) {
         const int64_t a = lo + n * t / nthreads, b = lo + n * (t + 1) / nthreads;
-        pool.emplace_back([=] { body(a, b, t); });
-    }
-    for (auto& th : pool) th.join();
+        body(a, b, t);
+    };
+    WorkerPool::instance().run(nthreads, task);
 }
 
 /* Pass 1 over [lo,hi): lengths, length-mismatch errors, max length. */
@@ -1189,9 +1274,15 @@ struct PairJob {
             s.busy = false;
         };
 
+        const bool dbg = std::getenv("SARLACC_DEBUG_TIMING") != nullptr;
+        double t_drain = 0, t_pack = 0, t_enq = 0;
+        auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         for (int64_t c0 = lo; c0 < hi;) {
             Slot& s = slots[which];
+            double t0 = now();
             drain(s, lay[which]);
+            t_drain += now() - t0;
+            t0 = now();
             int64_t c1 = std::min<int64_t>(hi, c0 + chunk);
             s.h_lens.reserve(sizeof(int32_t) * (size_t)(c1 - c0));
             s.h_lens2.reserve(sizeof(int32_t) * (size_t)(c1 - c0));
@@ -1217,6 +1308,8 @@ struct PairJob {
             pack_rows(VF, c0, c1, PF, s.h_lens.as<int32_t>(), stride_f, s.h_rows.as<uint16_t>(), nthreads, true, err_front);
             pack_rows(VB, c0, c1, PB, s.h_lens2.as<int32_t>(), stride_b, s.h_rows2.as<uint16_t>(), nthreads, true, err_back);
             if ((err_front.kind != ERR_NONE && err_front.at < c1) || (err_back.kind != ERR_NONE && err_back.at < c1)) break;
+            t_pack += now() - t0;
+            t0 = now();
 
             /* device buffers */
             s.d_rows.reserve(sizeof(uint16_t) * (size_t)m * stride_f);
@@ -1307,9 +1400,13 @@ struct PairJob {
             s.busy = true;
             which ^= 1;
             c0 = c1;
+            t_enq += now() - t0;
         }
+        double t0 = now();
         drain(slots[which], lay[which]);
         drain(slots[which ^ 1], lay[which ^ 1]);
+        t_drain += now() - t0;
+        if (dbg) std::fprintf(stderr, "[sarlacc] pair job dev %d: pack %.1f ms, enqueue %.1f ms, wait+copy-out %.1f ms\n", device, t_pack * 1e3, t_enq * 1e3, t_drain * 1e3);
     }
 };
 
