@@ -153,37 +153,44 @@ struct Plan {
     int alt_row = 4;
     int kinds = 1;
     int G = 1, C = 1;
+    bool wide_ok = false;     /* score-only runs may use 14-18 columns per lane */
     std::vector<int32_t> sec_starts, sec_ends;
 };
 
-void choose_geometry(Plan& P) {
+bool choose_geometry(Plan& P) {
     const char* force = std::getenv("SARLACC_FORCE_GC");
     if (force) {
         int g = 0, c = 0;
-        if (std::sscanf(force, "%d,%d", &g, &c) == 2 && g >= 1 && g <= 32 && (g & (g - 1)) == 0 && c >= 1 && c <= kMaxC &&
+        if (std::sscanf(force, "%d,%d", &g, &c) == 2 && g >= 1 && g <= 32 && (g & (g - 1)) == 0 && c >= 1 && c <= kMaxC && (c <= 12 || !(c & 1)) &&
             g * c >= P.L && g * c - P.L < g) {   /* at most one dummy slot per lane */
             P.G = g;
             P.C = c;
-            return;
+            return true;
         }
     }
     double best = 1e300;
     for (int g = 1; g <= kMaxGroup; g *= 2) {
         const int c = (P.L + g - 1) / g;
-        if (c > kMaxC) continue;
+        if (c > kMaxC || (c > 12 && (c & 1))) continue;   /* instantiated: 1..12, 14, 16, 18 */
+        if (c > 12 && !P.wide_ok) continue;   /* 14-18 columns per lane (3 resident blocks): measured faster only without trace records */
         const double util = (double)P.L / ((double)g * c);
-        double est = (26.0 + 14.0 / c) / util;     /* issue slots per DP cell, see DESIGN.md */
-        if (c > 9) est *= 1.10;                      /* 3 instead of 4 resident blocks per SM */
+        /* issue slots per DP cell: ~19 for the cell itself + ~86 per row spread over the lane's c columns
+         * (profiles/r01_ncu_summary_v2.txt), corrected for the resident warps the register budget allows */
+        double est = (19.0 + 86.0 / c) / util;
+        if (c > 12) est *= 1.12;                     /* 3 resident blocks per SM */
+        else if (c > 9) est *= 1.03;                 /* 4 blocks, but the register cap costs a few spills */
         if (est < best) {
             best = est;
             P.G = g;
             P.C = c;
         }
     }
+    return best < 1e300;   /* false: no instantiated geometry covers L (the literal kernel takes it) */
 }
 
-void build_plan(Plan& P, const Encoding& enc, const char* const* refs, int nref, int L, bool local, double go, double ge) {
+void build_plan(Plan& P, const Encoding& enc, const char* const* refs, int nref, int L, bool local, double go, double ge, bool trace = true) {
     P.enc = &enc;
+    P.wide_ok = !trace && std::getenv("SARLACC_NO_WIDE_C") == nullptr;
     P.L = L;
     P.nref = nref;
     P.local = local;
@@ -217,7 +224,7 @@ void build_plan(Plan& P, const Encoding& enc, const char* const* refs, int nref,
      * gap_open >= gap_ext, i.e. go >= 0 (see kernels.cu).  Anything else takes the literal kernel. */
     P.fast = L >= 1 && L <= kMaxFastL && finite && go >= 0.0 && enc.n <= 256 &&
              std::getenv("SARLACC_FORCE_GENERIC") == nullptr;
-    if (P.fast) choose_geometry(P);
+    if (P.fast) P.fast = choose_geometry(P);
 }
 
 /* ---- read access + packing --------------------------------------------------------------------- */
@@ -581,7 +588,7 @@ long long sub_chunk(const Plan& P, int maxlen, bool trace, long long n) {
     size_t per = 0;
     if (trace) {
         if (P.fast) {
-            per += (size_t)(maxlen + P.G) * P.G * (P.C <= 8 ? 4 : 8);
+            per += (size_t)(maxlen + P.G) * P.G * (P.C <= 8 ? 4 : (P.C <= 16 ? 8 : 16));
         } else {
             per += (size_t)std::max(1, maxlen) * P.L;
         }
@@ -674,7 +681,7 @@ const char* run_device(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t
         std::memset(&T, 0, sizeof(T));
         if (trace) {
             if (P.fast) {
-                const int wb = P.C <= 8 ? 4 : 8;
+                const int wb = P.C <= 8 ? 4 : (P.C <= 16 ? 8 : 16);
                 A.fstride = (long long)(maxlen + P.G) * P.G;
                 S.flags.reserve((size_t)A.fstride * wb * m);
                 T.layout = 0;
@@ -1101,7 +1108,7 @@ int run_host(const sarlacc_reads* reads, const sarlacc_encoding* encoding, doubl
         }
     }
     Plan P;
-    build_plan(P, enc, refs, nref, L, local, go, ge);
+    build_plan(P, enc, refs, nref, L, local, go, ge, mode == MODE_TRACE_LOCAL || mode == MODE_OPS_GLOBAL);
     if (nsec > 0) {
         P.sec_starts.assign(sec_starts, sec_starts + nsec);
         P.sec_ends.assign(sec_ends, sec_ends + nsec);
@@ -1916,6 +1923,7 @@ int sarlacc_resident_align(sarlacc_resident* r, int mode, double gapopen, double
         key.append(reinterpret_cast<const char*>(&gapopen), sizeof(double));
         key.append(reinterpret_cast<const char*>(&gapext), sizeof(double));
         key += local ? 'L' : 'G';
+        key += trace ? 'T' : 'S';
         if (trace) {
             if (nsec < 0 || (nsec > 0 && (!sec_starts || !sec_ends))) return fail("section starts and ends should have the same length");
             key.append(reinterpret_cast<const char*>(sec_starts), sizeof(int32_t) * nsec);
@@ -1935,7 +1943,7 @@ int sarlacc_resident_align(sarlacc_resident* r, int mode, double gapopen, double
             std::unique_ptr<sarlacc_resident::CachedPlan> np(new sarlacc_resident::CachedPlan());
             np->key = key;
             const char* refs[1] = {reference};
-            build_plan(np->plan, r->enc, refs, 1, L, local, gapopen, gapext);
+            build_plan(np->plan, r->enc, refs, 1, L, local, gapopen, gapext, trace);
             if (trace && nsec > 0) {
                 np->plan.sec_starts.assign(sec_starts, sec_starts + nsec);
                 np->plan.sec_ends.assign(sec_ends, sec_ends + nsec);

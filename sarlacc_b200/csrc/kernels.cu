@@ -40,8 +40,9 @@ __device__ __forceinline__ double col0_value(int local, double gop, double ge, i
 }
 
 template <int C>
-struct FlagWord {
-    using type = typename std::conditional<(C <= 8), uint32_t, unsigned long long>::type;
+struct FlagWord {   /* 4 bits per owned column: 32-bit word up to C = 8, 64-bit up to 16, 128-bit (uint4) beyond */
+    using type = typename std::conditional<(C <= 8), uint32_t,
+                 typename std::conditional<(C <= 16), unsigned long long, uint4>::type>::type;
 };
 
 #ifndef SARLACC_WF_STEP_UNROLL
@@ -54,9 +55,12 @@ constexpr int kStepUnroll = SARLACC_WF_STEP_UNROLL;
 #ifndef SARLACC_WF_BLOCKS_LARGE
 #define SARLACC_WF_BLOCKS_LARGE 4   /* C >= 10: 4 blocks (cap 128 registers) measured faster than 3 (cap 168) */
 #endif
+#ifndef SARLACC_WF_BLOCKS_XL
+#define SARLACC_WF_BLOCKS_XL 3      /* C = 14, 16, 18 (register cap 168): fewer, fatter lanes; pays off without trace records */
+#endif
 template <int C>
 struct WfBounds {
-    static constexpr int min_blocks = (C <= 9) ? SARLACC_WF_BLOCKS_SMALL : SARLACC_WF_BLOCKS_LARGE;
+    static constexpr int min_blocks = (C <= 9) ? SARLACC_WF_BLOCKS_SMALL : ((C <= 12) ? SARLACC_WF_BLOCKS_LARGE : SARLACC_WF_BLOCKS_XL);
 };
 
 /* R/barcodeAlign.R:28-34: strict `>` for best, then strict `>` for next best. */
@@ -87,6 +91,17 @@ __host__ __device__ __forceinline__ void wf_locate(int c, int C, int pad, int* j
         const int c2 = c - short_cols - 1;
         *j = pad + c2 / C;
         *k = c2 % C;
+    }
+}
+
+template <int C>
+__device__ __forceinline__ void store_flags(typename FlagWord<C>::type* dst, const uint32_t* fw) {
+    if constexpr (C <= 8) {
+        *dst = fw[0];
+    } else if constexpr (C <= 16) {
+        *dst = ((unsigned long long)fw[1] << 32) | fw[0];
+    } else {
+        *dst = make_uint4(fw[0], fw[1], fw[2], 0u);
     }
 }
 
@@ -187,7 +202,9 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
             El = first_lane ? NEG : El;
         }
         const double Sl_in = Sl, El_in = El;
-        uint32_t flo = 0, fhi = 0;
+        uint32_t fw[(C + 7) / 8];
+#pragma unroll
+        for (int x = 0; x < (C + 7) / 8; ++x) fw[x] = 0;
         /* Phase 1 (independent of this row's left-to-right chain): for every owned column the vertical
          * candidate v = max(F[i-1][c]-ve, H[i-1][c]-vo) (:145-155) and the (mis)match candidate
          * m = H[i-1][c-1] + cost (:159).  F is updated in place, m kept for phase 2. */
@@ -203,7 +220,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
                 m[k] = __dadd_rn(diag, *slotp[k]);
                 diag = (k == 0 && skip0) ? diag0 : S[k];
                 if (TRACE) {
-                    uint32_t& f = (k < 8) ? flo : fhi;
+                    uint32_t& f = fw[k >> 3];
                     if (p2) f |= 8u << (4 * (k & 7));
                 }
             }
@@ -232,7 +249,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
                 El = skip0 ? El_in : El;
             }
             if (TRACE) {
-                uint32_t& f = (k < 8) ? flo : fhi;
+                uint32_t& f = fw[k >> 3];
                 const int sh = 4 * (k & 7);
                 if (pd) f |= 1u << sh;
                 if (p5) f |= 2u << sh;
@@ -243,9 +260,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
         outE = El;
         if (TRACE) {
             if (live) {
-                WT w;
-                if (sizeof(WT) == 4) w = (WT)flo; else w = (WT)(((unsigned long long)fhi << 32) | flo);
-                flagp[(long long)(i + j) * G + j] = w;
+                store_flags<C>(flagp + (long long)(i + j) * G + j, fw);
             }
         }
     };
@@ -450,10 +465,10 @@ struct FlagReader {
         if (T.layout == 0) {
             const int ci = colinfo[c];
             const long long w = a * T.fstride + (long long)i * T.G + (ci >> 8);
-            if (T.wordbytes == 4) {
-                return (reinterpret_cast<const uint32_t*>(T.flags)[w] >> (ci & 0xff)) & 15u;
-            }
-            return (unsigned)((reinterpret_cast<const unsigned long long*>(T.flags)[w] >> (ci & 0xff)) & 15ull);
+            /* the word of (row, lane) is wordbytes wide; slot k lives in its 32-bit part k/8 */
+            const uint32_t* base = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(T.flags) + w * T.wordbytes);
+            const int sh = ci & 0xff;
+            return (base[sh >> 5] >> (sh & 31)) & 15u;
         }
         return reinterpret_cast<const uint8_t*>(T.flags)[a * T.fstride + (long long)(c - 1) * len + (i - 1)];
     }
@@ -705,6 +720,9 @@ const char* launch_wavefront(const AlignArgs& a, bool trace, bool has_alt, int g
         case 10: return dispatch_flags<10>(a, trace, has_alt, grid, st, smem);
         case 11: return dispatch_flags<11>(a, trace, has_alt, grid, st, smem);
         case 12: return dispatch_flags<12>(a, trace, has_alt, grid, st, smem);
+        case 14: return dispatch_flags<14>(a, trace, has_alt, grid, st, smem);
+        case 16: return dispatch_flags<16>(a, trace, has_alt, grid, st, smem);
+        case 18: return dispatch_flags<18>(a, trace, has_alt, grid, st, smem);
     }
 #endif
     return nullptr;

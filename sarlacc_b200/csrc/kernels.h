@@ -18,7 +18,7 @@
 
 namespace sarlacc {
 
-constexpr int kMaxC = 12;        /* adaptor columns per lane in the wavefront kernel */
+constexpr int kMaxC = 18;        /* adaptor columns per lane in the wavefront kernel (instantiated: 1..12, 14, 16, 18) */
 constexpr int kMaxGroup = 32;    /* lanes per alignment */
 constexpr int kMaxFastL = kMaxC * kMaxGroup;
 

@@ -118,6 +118,19 @@ def test_every_geometry(port, enc, monkeypatch, force):
     check_adaptor(native, port, enc, seqs, quals, adaptor, 5, 1)
 
 
+@pytest.mark.parametrize("force,L", [("4,18", 70), ("2,18", 35), ("2,16", 31), ("4,14", 55), ("1,18", 18), ("8,16", 125)])
+def test_wide_geometries(port, enc, monkeypatch, force, L):
+    """14-18 columns per lane (128-bit trace words beyond 16): used for score-only runs, forced here for both."""
+    from sarlacc_b200 import native
+    monkeypatch.setenv("SARLACC_FORCE_GC", force)
+    rng = np.random.default_rng(L)
+    adaptor = "".join(rng.choice(list("ACGTN"), size=L, p=[0.22, 0.22, 0.22, 0.22, 0.12]))
+    seqs, quals = random_windows(rng, 250, adaptor, 1, 200)
+    check_adaptor(native, port, enc, seqs, quals, adaptor, 5, 1)
+    got = native.barcode_align((seqs, quals), enc, 4, 1, adaptor)
+    assert np.array_equal(got, port.align_score_only(seqs, quals, enc, 4, 1, adaptor, local=False))
+
+
 def test_barcode_align(port, enc):
     from sarlacc_b200 import native
     rng = np.random.default_rng(23)
