@@ -183,6 +183,16 @@ const char* sarlacc_resident_last_kernel(const sarlacc_resident* r);
 void   sarlacc_resident_set_timing(sarlacc_resident* r, int on);
 double sarlacc_resident_forward_ms(sarlacc_resident* r);
 
+/* ---- FASTQ ingest (host side; stands in for ShortRead::FastqStreamer + .FASTQ2QSDS, R/adaptorAlign.R:26,36,104-110) --
+ * Buffered reader of plain-text 4-line FASTQ records yielding chunks as CSR pools that can be handed straight back as a
+ * sarlacc_reads (CSR layout).  Names exclude the leading '@'.  Pointers stay valid until the next call on the handle. */
+typedef struct sarlacc_fastq sarlacc_fastq;
+sarlacc_fastq* sarlacc_fastq_open(const char* path);
+int64_t sarlacc_fastq_next(sarlacc_fastq* f, int64_t max_reads,
+        const uint8_t** seq_pool, const int64_t** seq_off, const uint8_t** qual_pool, const int64_t** qual_off,
+        const uint8_t** name_pool, const int64_t** name_off);   /* reads returned; 0 at end of file; -1 on a malformed record */
+void sarlacc_fastq_close(sarlacc_fastq* f);
+
 #ifdef __cplusplus
 }
 #endif

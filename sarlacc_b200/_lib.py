@@ -49,6 +49,7 @@ EXPORTS = [
     "sarlacc_resident_scores_device", "sarlacc_resident_last_kernel",
     "sarlacc_resident_set_timing", "sarlacc_resident_forward_ms",
     "sarlacc_resident_scrambled", "sarlacc_resident_rows",
+    "sarlacc_fastq_open", "sarlacc_fastq_next", "sarlacc_fastq_close",
 ]
 
 
@@ -67,6 +68,12 @@ def _load():
     lib.sarlacc_resident_scrambled.restype = C.c_void_p
     lib.sarlacc_resident_scrambled.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int]
     lib.sarlacc_resident_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sarlacc_fastq_open.restype = C.c_void_p
+    lib.sarlacc_fastq_open.argtypes = [C.c_char_p]
+    lib.sarlacc_fastq_close.restype = None
+    lib.sarlacc_fastq_close.argtypes = [C.c_void_p]
+    lib.sarlacc_fastq_next.restype = C.c_int64
+    lib.sarlacc_fastq_next.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
     lib.sarlacc_resident_free.argtypes = [C.c_void_p]
     lib.sarlacc_resident_free.restype = None
     for name in ("sarlacc_resident_n", "sarlacc_resident_bytes"):

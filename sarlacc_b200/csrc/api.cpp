@@ -1709,6 +1709,109 @@ int sarlacc_adaptor_align_reads(const sarlacc_reads* reads, int tolerance, const
                       score1, start1, end1, sec_start1, sec_width1, score2, start2, end2, sec_start2, sec_width2);
 }
 
+/* ---- FASTQ ingest ----------------------------------------------------------------
+ * Stands in for ShortRead::FastqStreamer + .FASTQ2QSDS (R/adaptorAlign.R:26,36,104-110) on the host side of the
+ * ABI: a buffered reader of 4-line FASTQ records that yields chunks of reads as CSR pools (names, sequences,
+ * qualities), ready to be passed back in as a sarlacc_reads.  Plain text only; host code, excluded from timings. */
+struct sarlacc_fastq {
+    FILE* fh = nullptr;
+    std::vector<char> buf;
+    size_t pos = 0, end = 0;
+    bool eof = false;
+    std::vector<uint8_t> seq_pool, qual_pool, name_pool;
+    std::vector<int64_t> seq_off, qual_off, name_off;
+
+    bool fill() {
+        if (eof) return false;
+        if (pos > 0) {
+            std::memmove(buf.data(), buf.data() + pos, end - pos);
+            end -= pos;
+            pos = 0;
+        }
+        if (end == buf.size()) buf.resize(buf.size() * 2);
+        const size_t got = std::fread(buf.data() + end, 1, buf.size() - end, fh);
+        if (got == 0) { eof = true; return false; }
+        end += got;
+        return true;
+    }
+    /* next line [b, e) without the terminator; false at end of file */
+    bool line(size_t& b, size_t& e) {
+        for (;;) {
+            const char* nl = (const char*)std::memchr(buf.data() + pos, '\n', end - pos);
+            if (nl) {
+                b = pos;
+                e = (size_t)(nl - buf.data());
+                pos = e + 1;
+                if (e > b && buf[e - 1] == '\r') --e;
+                return true;
+            }
+            if (!fill()) {
+                if (pos < end) {   /* last line without newline */
+                    b = pos;
+                    e = end;
+                    pos = end;
+                    return true;
+                }
+                return false;
+            }
+        }
+    }
+};
+
+sarlacc_fastq* sarlacc_fastq_open(const char* path) {
+    if (!path) { fail("path must not be NULL"); return nullptr; }
+    FILE* fh = std::fopen(path, "rb");
+    if (!fh) { fail(std::string("cannot open FASTQ file: ") + path); return nullptr; }
+    sarlacc_fastq* f = new sarlacc_fastq();
+    f->fh = fh;
+    f->buf.resize(1 << 22);
+    return f;
+}
+
+void sarlacc_fastq_close(sarlacc_fastq* f) {
+    if (!f) return;
+    if (f->fh) std::fclose(f->fh);
+    delete f;
+}
+
+/* Reads up to max_reads records.  Returns the number read (0 at end of file), or -1 on a malformed record.  The
+ * pointers stay valid until the next call on this handle. */
+int64_t sarlacc_fastq_next(sarlacc_fastq* f, int64_t max_reads,
+        const uint8_t** seq_pool, const int64_t** seq_off, const uint8_t** qual_pool, const int64_t** qual_off,
+        const uint8_t** name_pool, const int64_t** name_off)
+{
+    if (!f) { fail("FASTQ handle is NULL"); return -1; }
+    f->seq_pool.clear(); f->qual_pool.clear(); f->name_pool.clear();
+    f->seq_off.assign(1, 0); f->qual_off.assign(1, 0); f->name_off.assign(1, 0);
+    int64_t n = 0;
+    size_t b, e;
+    while (n < max_reads) {
+        if (!f->line(b, e)) break;
+        if (e == b) continue;                       /* blank line between records */
+        if (f->buf[b] != '@') { fail("malformed FASTQ record: header does not start with '@'"); return -1; }
+        f->name_pool.insert(f->name_pool.end(), f->buf.begin() + b + 1, f->buf.begin() + e);
+        f->name_off.push_back((int64_t)f->name_pool.size());
+        if (!f->line(b, e)) { fail("malformed FASTQ record: missing sequence line"); return -1; }
+        f->seq_pool.insert(f->seq_pool.end(), f->buf.begin() + b, f->buf.begin() + e);
+        f->seq_off.push_back((int64_t)f->seq_pool.size());
+        if (!f->line(b, e) || e == b || f->buf[b] != '+') { fail("malformed FASTQ record: missing '+' line"); return -1; }
+        if (!f->line(b, e)) { fail("malformed FASTQ record: missing quality line"); return -1; }
+        f->qual_pool.insert(f->qual_pool.end(), f->buf.begin() + b, f->buf.begin() + e);
+        f->qual_off.push_back((int64_t)f->qual_pool.size());
+        ++n;
+    }
+    if (f->seq_pool.empty()) f->seq_pool.push_back(0);
+    if (f->qual_pool.empty()) f->qual_pool.push_back(0);
+    if (f->name_pool.empty()) f->name_pool.push_back(0);
+    if (seq_pool) *seq_pool = f->seq_pool.data();
+    if (seq_off) *seq_off = f->seq_off.data();
+    if (qual_pool) *qual_pool = f->qual_pool.data();
+    if (qual_off) *qual_off = f->qual_off.data();
+    if (name_pool) *name_pool = f->name_pool.data();
+    if (name_off) *name_off = f->name_off.data();
+    return n;
+}
+
 /* ---- resident windows ------------------------------------------------------------------------- */
 
 struct sarlacc_resident {

@@ -170,9 +170,44 @@ class ReadSet:
         return ReadSet(sp, so, qp, so if qp is not None else None, names)
 
 
+def _read_fastq_native(path, number):
+    """Plain-text FASTQ through the library's buffered reader (sarlacc_fastq_*)."""
+    import ctypes as C
+    from . import _lib
+    h = _lib.lib.sarlacc_fastq_open(str(path).encode())
+    if not h:
+        raise _lib.SarlaccError(_lib.last_error())
+    try:
+        ptrs = [C.c_void_p() for _ in range(6)]
+        while True:
+            n = _lib.lib.sarlacc_fastq_next(h, C.c_int64(int(number) if number else 1 << 62), *[C.byref(p) for p in ptrs])
+            if n < 0:
+                raise _lib.SarlaccError(_lib.last_error())
+            if n == 0:
+                return
+
+            def arr(ptr, count, dtype):
+                ctype = C.c_uint8 if dtype == np.uint8 else C.c_int64
+                return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(max(count, 1),))[:count].copy()
+
+            so = arr(ptrs[1], n + 1, np.int64)
+            qo = arr(ptrs[3], n + 1, np.int64)
+            no = arr(ptrs[5], n + 1, np.int64)
+            sp = arr(ptrs[0], int(so[-1]), np.uint8)
+            qp = arr(ptrs[2], int(qo[-1]), np.uint8)
+            nb = arr(ptrs[4], int(no[-1]), np.uint8).tobytes()
+            names = [nb[no[i]:no[i + 1]].decode("latin-1") for i in range(n)]
+            yield ReadSet(sp, so, qp, qo, names)
+    finally:
+        _lib.lib.sarlacc_fastq_close(h)
+
+
 def read_fastq(path, number=None, skip=0):
-    """Minimal 4-line FASTQ reader standing in for ShortRead::FastqStreamer + .FASTQ2QSDS
-    (R/adaptorAlign.R:26,36,104-110).  Yields ReadSets of at most `number` reads."""
+    """FASTQ reader standing in for ShortRead::FastqStreamer + .FASTQ2QSDS (R/adaptorAlign.R:26,36,104-110).
+    Yields ReadSets of at most `number` reads; plain text goes through the library's reader, .gz through Python."""
+    if not str(path).endswith(".gz"):
+        yield from _read_fastq_native(path, number)
+        return
     opener = gzip.open if str(path).endswith(".gz") else open
     with opener(path, "rb") as fh:
         names, seqs, quals = [], [], []

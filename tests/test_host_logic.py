@@ -66,6 +66,23 @@ def test_fastq_round_trip(tmp_path):
     assert back.seq_strings() == a.seq_strings() and back.qual_strings() == a.qual_strings() and back.names == a.names
     open(str(tmp_path / "empty.fastq"), "w").close()
     assert list(read_fastq(str(tmp_path / "empty.fastq"), 10)) == []
+    # CRLF line ends, a missing final newline, an empty read, and the gzip path (Python reader)
+    with open(str(tmp_path / "crlf.fastq"), "wb") as fh:
+        fh.write(b"@a\r\nACGT\r\n+\r\n!!!!\r\n@b\n\n+\n\n@c\nGG\n+c\n##")
+    got = ReadSet.concat(list(read_fastq(str(tmp_path / "crlf.fastq"), 2)))
+    assert got.seq_strings() == ["ACGT", "", "GG"] and got.qual_strings() == ["!!!!", "", "##"] and got.names == ["a", "b", "c"]
+    import gzip
+    with gzip.open(str(tmp_path / "x.fastq.gz"), "wb") as fh:
+        fh.write(open(p, "rb").read())
+    gz = ReadSet.concat(list(read_fastq(str(tmp_path / "x.fastq.gz"), 2)))
+    assert gz.seq_strings() == a.seq_strings() and gz.names == a.names
+    with open(str(tmp_path / "bad.fastq"), "wb") as fh:
+        fh.write(b"@a\nACGT\nIIII\n")
+    from sarlacc_b200 import SarlaccError
+    with pytest.raises(SarlaccError, match="malformed FASTQ record"):
+        list(read_fastq(str(tmp_path / "bad.fastq"), 10))
+    with pytest.raises(SarlaccError, match="cannot open FASTQ file"):
+        list(read_fastq(str(tmp_path / "missing.fastq"), 10))
 
 
 def test_resolve_strand_and_thresholds():
