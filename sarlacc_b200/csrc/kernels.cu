@@ -116,7 +116,10 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
     double* row0s = smem_d;                                   /* [L+1]                         */
     double* costs = row0s + (L + 1);                          /* [5][encn], layout of AlignArgs::cost */
     double* lanetab = costs + 5 * encn;                       /* [warps][kCostEntries][32] lane-private cost entries */
-    uint8_t* refm = reinterpret_cast<uint8_t*>(lanetab + (kBlock / 32) * kCostEntries * 32);   /* [nref][L] */
+    /* pre[q][o][e]: cost of reference base e (A,C,G,T) against an observed base o (0 = other, 1..4 = A,C,G,T) of quality
+     * index q: match1[q] if o-1 == e else mismatch1[q] -- one 32-byte record per (q, o), read with two LDS.128 per row */
+    double2* pre = reinterpret_cast<double2*>(smem_d + (((size_t)(L + 1) + 5 * encn + (kBlock / 32) * kCostEntries * 32 + 1) & ~(size_t)1));   /* 16-byte aligned */
+    uint8_t* refm = reinterpret_cast<uint8_t*>(pre + (size_t)encn * 5 * 2);   /* [nref][L] */
     uint8_t* refk = refm + (size_t)nref * L;                                                    /* [nref][L] */
 
     for (int x = threadIdx.x; x <= L; x += blockDim.x) row0s[x] = A.row0[x];
@@ -124,6 +127,11 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
     for (int x = threadIdx.x; x < nref * L; x += blockDim.x) {
         refm[x] = A.refmask[x];
         refk[x] = A.refkind[x];
+    }
+    for (int x = threadIdx.x; x < encn * 5 * 2; x += blockDim.x) {
+        const int q = x / 10, o = (x / 2) % 5, half = x & 1;     /* half 0: entries A,C; half 1: entries G,T */
+        const double mq = A.cost[q], xq = A.cost[encn + q];
+        pre[x] = make_double2((o - 1 == 2 * half) ? mq : xq, (o - 1 == 2 * half + 1) ? mq : xq);
     }
     __syncthreads();
 
@@ -182,15 +190,16 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
 
     /* One DP row of this lane's C columns.  `live` gates the only side effect (the trace store). */
     auto row_step = [&](double Sl, double El, bool live) {
-        const unsigned rw = rowp[i - 1];
+        const unsigned rw = *rowp;
         const unsigned q = rw & 0xffu;
         const unsigned obs = rw >> 8;
         {
-            const double mq = costs[q], xq = costs[encn + q];
-            mytab[0 * 32] = (obs & 1u) ? mq : xq;
-            mytab[1 * 32] = (obs & 2u) ? mq : xq;
-            mytab[2 * 32] = (obs & 4u) ? mq : xq;
-            mytab[3 * 32] = (obs & 8u) ? mq : xq;
+            const int o = __ffs(obs);                       /* one-hot A=1,C=2,G=4,T=8 -> 1..4; 0 for anything else */
+            const double2 ac = pre[(q * 5 + o) * 2], gt = pre[(q * 5 + o) * 2 + 1];
+            mytab[0 * 32] = ac.x;
+            mytab[1 * 32] = ac.y;
+            mytab[2 * 32] = gt.x;
+            mytab[3 * 32] = gt.y;
             if (kinds & 2) mytab[4 * 32] = costs[2 * encn + q];
             if (kinds & 4) mytab[5 * 32] = costs[3 * encn + q];
             if (kinds & 8) mytab[6 * 32] = costs[4 * encn + q];
@@ -260,7 +269,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
         outE = El;
         if (TRACE) {
             if (live) {
-                store_flags<C>(flagp + (long long)(i + j) * G + j, fw);
+                store_flags<C>(flagp, fw);
             }
         }
     };
@@ -282,8 +291,8 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
                 act = false;
             } else {
                 i = 0;
-                rowp = A.rows + a * (long long)A.stride;
-                if (TRACE) flagp = reinterpret_cast<WT*>(A.flags) + a * A.fstride;
+                rowp = A.rows + a * (long long)A.stride - 1;                                   /* advanced to row i before use */
+                if (TRACE) flagp = reinterpret_cast<WT*>(A.flags) + a * A.fstride + (long long)j * (G + 1);   /* word (i + j) * G + j */
 #pragma unroll
                 for (int k = 0; k < C; ++k) {
                     const int c = cfirst + k - (skip0 ? 1 : 0);
@@ -305,18 +314,20 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
         const int steps = __reduce_min_sync(FULL, room);
         if (steps == 0x7fffffff) break;
         const int inc = act ? 1 : 0;
+        const long long finc = act ? G : 0;
         const uint16_t* keep_rowp = rowp;
-        const int keep_i = i;
-        if (!act) { rowp = A.rows; i = 1; }
+        if (!act) rowp = A.rows;
 #pragma unroll kStepUnroll
         for (int s = 0; s < steps; ++s) {
             /* Left boundary of this row: what lane j-1 produced one step ago. */
             const double Sl = __shfl_up_sync(FULL, outS, 1, G);
             const double El = __shfl_up_sync(FULL, outE, 1, G);
             i += inc;
+            rowp += inc;
+            if (TRACE) flagp += finc;
             row_step(Sl, El, act);
         }
-        if (!act) { rowp = keep_rowp; i = keep_i; }
+        if (!act) rowp = keep_rowp;
 
         if (act && i == len && j == G - 1) {
             const double s = S[C - 1];
@@ -696,7 +707,8 @@ const char* dispatch_flags(const AlignArgs& a, bool trace, bool alt, int grid, c
 }  // namespace
 
 size_t wavefront_smem_bytes(const AlignArgs& a) {
-    return sizeof(double) * ((size_t)a.L + 1 + 5 * (size_t)a.enc_n + (size_t)(kBlock / 32) * kCostEntries * 32) +
+    return sizeof(double) * ((((size_t)a.L + 1 + 5 * (size_t)a.enc_n + (size_t)(kBlock / 32) * kCostEntries * 32 + 1) & ~(size_t)1) +
+                             (size_t)a.enc_n * 5 * 4) +
            2 * (size_t)a.nref * a.L;
 }
 
