@@ -219,7 +219,12 @@ void build_plan(Plan& P, const Encoding& enc, const char* const* refs, int nref,
     P.has_alt = nalt > 0;
     P.alt_row = kinds[COL_TWO] ? 2 : (kinds[COL_THREE] ? 3 : 4);
     P.kinds = (kinds[COL_ACGT] ? 1 : 0) | (kinds[COL_TWO] ? 2 : 0) | (kinds[COL_THREE] ? 4 : 0) | (kinds[COL_N] ? 8 : 0);
-    const bool finite = std::isfinite(go) && std::isfinite(ge);
+    bool finite = std::isfinite(go) && std::isfinite(ge);
+    /* cost tables: -Inf is legitimate (Phred 0: log2(0)) and harmless; NaN / +Inf (malformed error probabilities) would
+     * break the max() reformulation, so such encodings take the literal kernel */
+    for (double c : enc.cost) {
+        if (std::isnan(c) || (std::isinf(c) && c > 0)) finite = false;
+    }
     /* The wavefront kernel folds "left/up neighbour already chose a gap" into a max(), which needs
      * gap_open >= gap_ext, i.e. go >= 0 (see kernels.cu).  Anything else takes the literal kernel. */
     P.fast = L >= 1 && L <= kMaxFastL && finite && go >= 0.0 && enc.n <= 256 &&

@@ -62,6 +62,24 @@ def test_adaptor_align_random(port, enc, adaptor, go, ge):
     check_adaptor(native, port, enc, seqs, quals, adaptor, go, ge)
 
 
+def test_unusual_penalties_and_encodings(port, enc):
+    """Zero and negative extension penalties stay on the wavefront kernel (it only needs go >= 0); Phred 0 gives a -Inf
+    match cost; error probabilities above 1 give NaN costs and take the literal kernel.  All must equal the oracle."""
+    from sarlacc_b200 import native
+    rng = np.random.default_rng(101)
+    seqs, quals = random_windows(rng, 200, VIGNETTE_A2, 1, 90, qlo=0, qhi=3)      # lots of '!' (Q0)
+    for go, ge in [(0, 0), (3, -0.25), (0, 2), (1e-3, 1e-3), (50, 0)]:
+        check_adaptor(native, port, enc, seqs, quals, VIGNETTE_A2, go, ge)
+        got = native.barcode_align((seqs, quals), enc, go, ge, VIGNETTE_A2)
+        assert np.array_equal(got, port.align_score_only(seqs, quals, enc, go, ge, VIGNETTE_A2, local=False))
+    names, err = enc
+    weird = (names, np.concatenate([[3.0, 2.0], err[2:]]))                         # log of a negative number -> NaN
+    seqs, quals = random_windows(rng, 100, VIGNETTE_A2, 1, 60, qlo=0, qhi=10)
+    got = native.adaptor_align((seqs, quals), weird, 5, 1, VIGNETTE_A2)
+    exp = port.adaptor_align(seqs, quals, weird, 5, 1, VIGNETTE_A2)
+    assert np.array_equal(got[0], exp[0], equal_nan=True) and np.array_equal(got[1], exp[1]) and np.array_equal(got[2], exp[2])
+
+
 def test_adaptor_align_ties(port, enc):
     """Uniform qualities and repetitive sequence: co-optimal paths everywhere, tie-breaking must match."""
     from sarlacc_b200 import native
