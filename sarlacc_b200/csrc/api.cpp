@@ -593,7 +593,7 @@ long long sub_chunk(const Plan& P, int maxlen, bool trace, long long n) {
     size_t per = 0;
     if (trace) {
         if (P.fast) {
-            per += (size_t)(maxlen + P.G) * P.G * (P.C <= 8 ? 4 : (P.C <= 16 ? 8 : 16));
+            per += (size_t)(maxlen + kSkew * P.G) * P.G * (P.C <= 8 ? 4 : (P.C <= 16 ? 8 : 16));
         } else {
             per += (size_t)std::max(1, maxlen) * P.L;
         }
@@ -687,7 +687,7 @@ const char* run_device(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t
         if (trace) {
             if (P.fast) {
                 const int wb = P.C <= 8 ? 4 : (P.C <= 16 ? 8 : 16);
-                A.fstride = (long long)(maxlen + P.G) * P.G;
+                A.fstride = (long long)(maxlen + kSkew * P.G) * P.G;
                 S.flags.reserve((size_t)A.fstride * wb * m);
                 T.layout = 0;
                 T.wordbytes = wb;

@@ -179,9 +179,10 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
 #pragma unroll
     for (int k = 0; k < C; ++k) { S[k] = 0.0; F[k] = NEG; }
     double outS = 0.0, outE = NEG, diag0 = 0.0;
+    double outS2 = 0.0, outE2 = NEG;   /* kSkew == 2: what this lane produced one row earlier */
     long long a = gidx - NG;
     int b = nref - 1;
-    int i = 0, len = 0, delay = j;
+    int i = 0, len = 0, delay = kSkew * j;
     bool done = false;
     const uint16_t* rowp = A.rows;
     WT* flagp = reinterpret_cast<WT*>(A.flags);
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
             } else {
                 i = 0;
                 rowp = A.rows + a * (long long)A.stride - 1;                                   /* advanced to row i before use */
-                if (TRACE) flagp = reinterpret_cast<WT*>(A.flags) + a * A.fstride + (long long)j * (G + 1);   /* word (i + j) * G + j */
+                if (TRACE) flagp = reinterpret_cast<WT*>(A.flags) + a * A.fstride + (long long)j * (kSkew * G + 1);   /* word (i + kSkew * j) * G + j */
 #pragma unroll
                 for (int k = 0; k < C; ++k) {
                     const int c = cfirst + k - (skip0 ? 1 : 0);
@@ -320,8 +321,12 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
 #pragma unroll kStepUnroll
         for (int s = 0; s < steps; ++s) {
             /* Left boundary of this row: what lane j-1 produced one step ago. */
-            const double Sl = __shfl_up_sync(FULL, outS, 1, G);
-            const double El = __shfl_up_sync(FULL, outE, 1, G);
+            /* With kSkew == 2 lane j lags lane j-1 by two rows, so the boundary of the row it is about to process was
+             * produced two steps ago: the serial chains of consecutive rows of one lane then do not depend on each
+             * other through the neighbour and ptxas can interleave them (two chains in flight per warp). */
+            const double Sl = __shfl_up_sync(FULL, kSkew == 2 ? outS2 : outS, 1, G);
+            const double El = __shfl_up_sync(FULL, kSkew == 2 ? outE2 : outE, 1, G);
+            if (kSkew == 2) { outS2 = outS; outE2 = outE; }
             i += inc;
             rowp += inc;
             if (TRACE) flagp += finc;
@@ -499,7 +504,7 @@ __global__ void __launch_bounds__(128) traceback(const TraceArgs T)
         for (int c = 1 + threadIdx.x; c <= T.L; c += blockDim.x) {
             int j, k;
             wf_locate(c, T.C, pad, &j, &k);
-            tb_colinfo[c] = ((j * (T.G + 1)) << 8) | (4 * k);
+            tb_colinfo[c] = ((j * (kSkew * T.G + 1)) << 8) | (4 * k);
         }
         __syncthreads();
     }

@@ -20,6 +20,10 @@ namespace sarlacc {
 
 constexpr int kMaxC = 18;        /* adaptor columns per lane in the wavefront kernel (instantiated: 1..12, 14, 16, 18) */
 constexpr int kMaxGroup = 32;    /* lanes per alignment */
+#ifndef SARLACC_WF_SKEW
+#define SARLACC_WF_SKEW 2
+#endif
+constexpr int kSkew = SARLACC_WF_SKEW;   /* rows by which lane j+1 lags lane j (see kernels.cu) */
 constexpr int kMaxFastL = kMaxC * kMaxGroup;
 
 /* Column classes of a reference position (src/reference_align.cpp:184-212). */
