@@ -459,14 +459,14 @@ void pack_rows(const ReadView& V, int64_t lo, int64_t hi, const PackTables& T, c
             if (!V.back) {
                 for (int r = 0; r < len; ++r) {
                     const unsigned qi = T.qidx[q[r]];
-                    bad |= qi;
-                    out[r] = (uint16_t)((qi & 0xFFu) | ((unsigned)T.base[s[r]] << 8));
+                    bad |= qi;   /* 0xFFFF marks a quality below the offset: the call fails; pack index 0 so no kernel reads out of its tables */
+                    out[r] = (uint16_t)(((qi & 0xFF00u) ? 0u : qi) | ((unsigned)T.base[s[r]] << 8));
                 }
             } else {
                 for (int r = 0; r < len; ++r) {
                     const unsigned qi = T.qidx[q[len - 1 - r]];
                     bad |= qi;
-                    out[r] = (uint16_t)((qi & 0xFFu) | ((unsigned)T.base_rc[s[len - 1 - r]] << 8));
+                    out[r] = (uint16_t)(((qi & 0xFF00u) ? 0u : qi) | ((unsigned)T.base_rc[s[len - 1 - r]] << 8));
                 }
             }
             if (check_qual && (bad & 0xFF00u)) errs[t].offer(i, ERR_QUAL);
@@ -676,6 +676,7 @@ const char* run_device(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t
         A.kinds = P.kinds;
         A.G = P.G;
         A.C = P.C;
+        A.pair_rows = std::getenv("SARLACC_PAIR") ? std::atoi(std::getenv("SARLACC_PAIR")) : 1;   /* 0 selects the single-row kernel (A/B tests) */
         /* [nref][n] outputs of a sub-chunk cannot be expressed with one base pointer unless n == m or nref == 1 */
         A.score = out.score ? out.score + off : nullptr;
         A.best_id = out.best_id ? out.best_id + off : nullptr;

@@ -49,6 +49,10 @@ struct FlagWord {   /* 4 bits per owned column: 32-bit word up to C = 8, 64-bit 
 #define SARLACC_WF_STEP_UNROLL 4   /* rows per trip of the inner loop: lets ptxas rename loop-carried state instead of moving it (profiles/) */
 #endif
 constexpr int kStepUnroll = SARLACC_WF_STEP_UNROLL;
+#ifndef SARLACC_WF_PAIR_UNROLL
+#define SARLACC_WF_PAIR_UNROLL 2
+#endif
+constexpr int kPairUnroll = SARLACC_WF_PAIR_UNROLL;
 #ifndef SARLACC_WF_BLOCKS_SMALL
 #define SARLACC_WF_BLOCKS_SMALL 4   /* resident 128-thread blocks per SM for C <= 9 (register cap 128) */
 #endif
@@ -331,6 +335,300 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
             rowp += inc;
             if (TRACE) flagp += finc;
             row_step(Sl, El, act);
+        }
+        if (!act) rowp = keep_rowp;
+
+        if (act && i == len && j == G - 1) {
+            const double s = S[C - 1];
+            if (A.score) A.score[(long long)b * A.n + a] = s;
+            if (A.best_id) {
+                update_best(s, b + 1, best, nextb, bid);
+                if (b == nref - 1) {
+                    A.best_id[a] = bid;
+                    A.best[a] = best;
+                    A.next_best[a] = nextb;
+                }
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * wf_forward2: the same wavefront, but a lane takes TWO read rows per step and lags its left neighbour by one such
+ * step.  Cell (r+1, k-1) depends on row r only through cells the lane has already finished, so the serial chains of
+ * the two rows are independent and are written interleaved: cell A(k) of row r next to cell B(k-1) of row r+1.  That
+ * gives every warp two dependency chains in flight (the single-row kernel's top stall is `wait`, the fixed-latency
+ * dependency of its one chain, profiles/).  An odd last row runs the same code with row B masked off.
+ */
+template <int C, bool TRACE>
+__global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(const __grid_constant__ AlignArgs A)
+{
+    using WT = typename FlagWord<C>::type;
+    extern __shared__ double smem_d[];
+    const int L = A.L, nref = A.nref, encn = A.enc_n;
+    double* row0s = smem_d;                                   /* [L+1]                         */
+    double* costs = row0s + (L + 1);                          /* [5][encn], layout of AlignArgs::cost */
+    double* lanetab = costs + 5 * encn;                       /* [warps][2 rows][kCostEntries][32] lane-private cost entries */
+    double2* pre = reinterpret_cast<double2*>(smem_d + (((size_t)(L + 1) + 5 * encn + (kBlock / 32) * 2 * kCostEntries * 32 + 1) & ~(size_t)1));
+    uint8_t* refm = reinterpret_cast<uint8_t*>(pre + (size_t)encn * 5 * 2);   /* [nref][L] */
+    uint8_t* refk = refm + (size_t)nref * L;                                   /* [nref][L] */
+
+    for (int x = threadIdx.x; x <= L; x += blockDim.x) row0s[x] = A.row0[x];
+    for (int x = threadIdx.x; x < 5 * encn; x += blockDim.x) costs[x] = A.cost[x];
+    for (int x = threadIdx.x; x < nref * L; x += blockDim.x) {
+        refm[x] = A.refmask[x];
+        refk[x] = A.refkind[x];
+    }
+    for (int x = threadIdx.x; x < encn * 5 * 2; x += blockDim.x) {
+        const int q = x / 10, o = (x / 2) % 5, half = x & 1;
+        const double mq = A.cost[q], xq = A.cost[encn + q];
+        pre[x] = make_double2((o - 1 == 2 * half) ? mq : xq, (o - 1 == 2 * half + 1) ? mq : xq);
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int G = A.G;
+    const int j = lane & (G - 1);
+    const int gpw = 32 / G;
+    const long long warp_global = (long long)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+    const long long gidx = warp_global * gpw + lane / G;
+    const long long NG = (long long)gridDim.x * (kBlock / 32) * gpw;
+    const int pad = G * C - L;
+    const bool skip0 = j < pad;
+    const int cfirst = wf_first_col(j, C, pad);
+    const double gop = A.gop, ge = A.ge;
+    const int local = A.local;
+    const int kinds = A.kinds;
+    const double NEG = neg_inf();
+    const bool first_lane = (j == 0);
+    const double vo_last = (local && j == G - 1) ? 0.0 : gop;
+    const double ve_last = (local && j == G - 1) ? 0.0 : ge;
+
+    constexpr int kTab = kCostEntries * 32;                   /* doubles between the tables of row A and row B */
+    double* mytab = lanetab + (threadIdx.x >> 5) * 2 * kTab + lane;
+    const double* slotp[C];
+    auto load_slots = [&](int b) {
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const int c = cfirst + k - (skip0 ? 1 : 0);
+            int e = 0;
+            if (c >= 1 && c <= L) {
+                const unsigned kind = refk[(size_t)b * L + c - 1];
+                const unsigned mask = refm[(size_t)b * L + c - 1];
+                e = (kind == COL_ACGT) ? (mask == 1 ? 0 : (mask == 2 ? 1 : (mask == 4 ? 2 : 3))) : 3 + (int)kind;
+                if (kind == COL_ACGT && mask == 0) e = 0;
+            }
+            slotp[k] = mytab + e * 32;
+        }
+    };
+    load_slots(0);
+
+    double S[C], F[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) { S[k] = 0.0; F[k] = NEG; }
+    double outSA = 0.0, outEA = NEG, outSB = 0.0, outEB = NEG, diag0 = 0.0;
+    long long a = gidx - NG;
+    int b = nref - 1;
+    int i = 0, len = 0, delay = j;
+    bool done = false;
+    const uint16_t* rowp = A.rows;          /* points at the next unprocessed row */
+    WT* flagp = reinterpret_cast<WT*>(A.flags);   /* word of the next unprocessed row for this lane */
+    double best = NEG, nextb = NEG;
+    int bid = 0;
+
+    auto fill_table = [&](double* tab, unsigned rw) {
+        const unsigned q = rw & 0xffu;
+        const int o = __ffs(rw >> 8);
+        const double2 ac = pre[(q * 5 + o) * 2], gt = pre[(q * 5 + o) * 2 + 1];
+        tab[0 * 32] = ac.x;
+        tab[1 * 32] = ac.y;
+        tab[2 * 32] = gt.x;
+        tab[3 * 32] = gt.y;
+        if (kinds & 2) tab[4 * 32] = costs[2 * encn + q];
+        if (kinds & 4) tab[5 * 32] = costs[3 * encn + q];
+        if (kinds & 8) tab[6 * 32] = costs[4 * encn + q];
+    };
+
+    /* Rows i+1 (A) and i+2 (B) of this lane's C columns.  MASKED: row B may not exist (hasB false) and then must leave no
+     * trace in the state.  `live` gates the trace stores. */
+    auto pair_step = [&](auto masked_tag, double SlA, double ElA, double SlB, double ElB, bool live, bool hasB) {
+        constexpr bool MASKED = decltype(masked_tag)::value;
+        fill_table(mytab, rowp[0]);
+        fill_table(mytab + kTab, rowp[1]);
+        {   /* column 0 feeds the first lane: src/reference_align.cpp:64-78 */
+            double c0a = 0.0, c0b = 0.0;
+            if (!local) { c0a = col0_value(0, gop, ge, i + 1); c0b = col0_value(0, gop, ge, i + 2); }
+            SlA = first_lane ? c0a : SlA;
+            ElA = first_lane ? NEG : ElA;
+            SlB = first_lane ? c0b : SlB;
+            ElB = first_lane ? NEG : ElB;
+        }
+        const double SlA_in = SlA, ElA_in = ElA, SlB_in = SlB, ElB_in = ElB;
+        uint32_t fa[(C + 7) / 8], fb[(C + 7) / 8];
+#pragma unroll
+        for (int x = 0; x < (C + 7) / 8; ++x) { fa[x] = 0; fb[x] = 0; }
+        /* row A, phase 1: vertical and (mis)match candidates of every column (:145-159); F updated in place */
+        double mA[C];
+        {
+            double diag = diag0;
+#pragma unroll
+            for (int k = 0; k < C; ++k) {
+                const double vO = __dsub_rn(S[k], (k == C - 1) ? vo_last : gop);
+                const double Fe = __dsub_rn(F[k], (k == C - 1) ? ve_last : ge);
+                const bool p2 = Fe > vO;
+                F[k] = p2 ? Fe : vO;
+                mA[k] = __dadd_rn(diag, *slotp[k]);
+                diag = (k == 0 && skip0) ? diag0 : S[k];
+                if (TRACE) { if (p2) fa[k >> 3] |= 8u << (4 * (k & 7)); }
+            }
+        }
+        /* the two serial chains, interleaved: A(k) and B(k-1) */
+        double dB = SlA_in;               /* H[A][column left of slot 0]: diagonal of B's slot 0 */
+#pragma unroll
+        for (int k = 0; k <= C; ++k) {
+            if (k < C) {
+                const double hO = __dsub_rn(SlA, gop);
+                const double Ee = __dsub_rn(ElA, ge);
+                const bool p1 = Ee > hO;
+                const double h = p1 ? Ee : hO;
+                const double v = F[k];
+                const bool p5 = h > v;
+                const double t = p5 ? h : v;
+                const bool pd = mA[k] > t;
+                const double Sn = pd ? mA[k] : t;
+                S[k] = Sn;
+                SlA = Sn;
+                ElA = h;
+                if (k == 0) {
+                    SlA = skip0 ? SlA_in : SlA;
+                    ElA = skip0 ? ElA_in : ElA;
+                }
+                if (TRACE) {
+                    const int sh = 4 * (k & 7);
+                    if (pd) fa[k >> 3] |= 1u << sh;
+                    if (p5) fa[k >> 3] |= 2u << sh;
+                    if (p1) fa[k >> 3] |= 4u << sh;
+                }
+            }
+            if (k >= 1) {
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int kk = k - 1;
+                const double SA = S[kk], FA = F[kk];          /* row A's results in this column */
+                const double vO = __dsub_rn(SA, (kk == C - 1) ? vo_last : gop);
+                const double Fe = __dsub_rn(FA, (kk == C - 1) ? ve_last : ge);
+                const bool p2 = Fe > vO;
+                const double vB = p2 ? Fe : vO;
+                const double mB = __dadd_rn(dB, slotp[kk][kTab]);
+                dB = (kk == 0 && skip0) ? dB : SA;
+                const double hO = __dsub_rn(SlB, gop);
+                const double Ee = __dsub_rn(ElB, ge);
+                const bool p1 = Ee > hO;
+                const double h = p1 ? Ee : hO;
+                const bool p5 = h > vB;
+                const double t = p5 ? h : vB;
+                const bool pd = mB > t;
+                const double Sn = pd ? mB : t;
+                if (MASKED) {
+                    S[kk] = hasB ? Sn : SA;
+                    F[kk] = hasB ? vB : FA;
+                } else {
+                    S[kk] = Sn;
+                    F[kk] = vB;
+                }
+                SlB = Sn;
+                ElB = h;
+                if (kk == 0) {
+                    SlB = skip0 ? SlB_in : SlB;
+                    ElB = skip0 ? ElB_in : ElB;
+                }
+                if (TRACE) {
+                    const int sh = 4 * (kk & 7);
+                    if (p2) fb[kk >> 3] |= 8u << sh;
+                    if (pd) fb[kk >> 3] |= 1u << sh;
+                    if (p5) fb[kk >> 3] |= 2u << sh;
+                    if (p1) fb[kk >> 3] |= 4u << sh;
+                }
+            }
+        }
+        outSA = SlA;
+        outEA = ElA;
+        outSB = SlB;
+        outEB = ElB;
+        if (MASKED) diag0 = hasB ? SlB_in : SlA_in;
+        else diag0 = SlB_in;
+        if (TRACE) {
+            if (live) {
+                store_flags<C>(flagp, fa);
+                if (!MASKED || hasB) store_flags<C>(flagp + G, fb);
+            }
+        }
+    };
+
+    while (__any_sync(FULL, !done)) {
+        /* ---- bookkeeping: pipeline start-up and switches to the next chained alignment ---- */
+        bool act = !done;
+        if (delay > 0) { --delay; act = false; }
+        if (act && i == len) {
+            ++b;
+            if (b == nref) {
+                b = 0;
+                a += NG;
+                while (a < A.n && (len = A.lens[a]) == 0) a += NG;
+            }
+            if (a >= A.n) {
+                done = true;
+                act = false;
+            } else {
+                i = 0;
+                rowp = A.rows + a * (long long)A.stride;
+                if (TRACE) flagp = reinterpret_cast<WT*>(A.flags) + a * A.fstride + (long long)(1 + 2 * j) * G + j;   /* word (i + 2j) * G + j, i = 1 */
+#pragma unroll
+                for (int k = 0; k < C; ++k) {
+                    const int c = cfirst + k - (skip0 ? 1 : 0);
+                    S[k] = (c >= 0 && c <= L) ? row0s[c] : 0.0;
+                    F[k] = NEG;
+                }
+                diag0 = row0s[cfirst - 1];
+                if (nref > 1) load_slots(b);
+                if (b == 0) { best = NEG; nextb = NEG; bid = 0; }
+            }
+        }
+
+        /* ---- DP rows, two per step.  Unmasked steps run while every lane of the warp still has a whole pair of rows
+         * before its next event; otherwise one masked step (odd last row, start-up) is taken. ---- */
+        int room;
+        if (act) room = (len - i) >> 1;
+        else room = done ? 0x7fffffff : 0;
+        const int steps = __reduce_min_sync(FULL, room);
+        if (steps == 0x7fffffff) break;
+        const uint16_t* keep_rowp = rowp;
+        if (!act) rowp = A.rows;
+        if (steps > 0) {
+            const int inc = act ? 2 : 0;
+            const long long finc = act ? 2 * G : 0;
+#pragma unroll kPairUnroll
+            for (int s = 0; s < steps; ++s) {
+                const double SlA = __shfl_up_sync(FULL, outSA, 1, G);
+                const double ElA = __shfl_up_sync(FULL, outEA, 1, G);
+                const double SlB = __shfl_up_sync(FULL, outSB, 1, G);
+                const double ElB = __shfl_up_sync(FULL, outEB, 1, G);
+                pair_step(std::false_type(), SlA, ElA, SlB, ElB, act, true);
+                i += inc;
+                rowp += inc;
+                if (TRACE) flagp += finc;
+            }
+        } else {
+            const double SlA = __shfl_up_sync(FULL, outSA, 1, G);
+            const double ElA = __shfl_up_sync(FULL, outEA, 1, G);
+            const double SlB = __shfl_up_sync(FULL, outSB, 1, G);
+            const double ElB = __shfl_up_sync(FULL, outEB, 1, G);
+            const bool hasB = act && (len - i) >= 2;
+            pair_step(std::true_type(), SlA, ElA, SlB, ElB, act, hasB);
+            const int inc = act ? (hasB ? 2 : 1) : 0;
+            i += inc;
+            rowp += inc;
+            if (TRACE) flagp += (long long)inc * G;
         }
         if (!act) rowp = keep_rowp;
 
@@ -685,7 +983,8 @@ __global__ void __launch_bounds__(128) scramble_rows(const uint16_t* in, uint16_
 
 template <int C, bool TRACE>
 const char* launch_wf(const AlignArgs& a, int grid, cudaStream_t st, size_t smem) {
-    auto kern = wf_forward<C, TRACE>;
+    const bool pair = a.pair_rows != 0;
+    auto kern = pair ? wf_forward2<C, TRACE> : wf_forward<C, TRACE>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (grid <= 0) {
         int dev = 0, sms = 0, per = 0;
@@ -700,7 +999,7 @@ const char* launch_wf(const AlignArgs& a, int grid, cudaStream_t st, size_t smem
     const long long need = (a.n + groups_per_block - 1) / groups_per_block;
     if (need < grid) grid = (int)(need > 0 ? need : 1);
     kern<<<grid, kBlock, smem, st>>>(a);
-    return TRACE ? "wf_forward<trace>" : "wf_forward<score>";
+    return pair ? (TRACE ? "wf_forward2<trace>" : "wf_forward2<score>") : (TRACE ? "wf_forward<trace>" : "wf_forward<score>");
 }
 
 template <int C>
@@ -712,7 +1011,7 @@ const char* dispatch_flags(const AlignArgs& a, bool trace, bool alt, int grid, c
 }  // namespace
 
 size_t wavefront_smem_bytes(const AlignArgs& a) {
-    return sizeof(double) * ((((size_t)a.L + 1 + 5 * (size_t)a.enc_n + (size_t)(kBlock / 32) * kCostEntries * 32 + 1) & ~(size_t)1) +
+    return sizeof(double) * ((((size_t)a.L + 1 + 5 * (size_t)a.enc_n + (size_t)(kBlock / 32) * 2 * kCostEntries * 32 + 1) & ~(size_t)1) +
                              (size_t)a.enc_n * 5 * 4) +
            2 * (size_t)a.nref * a.L;
 }

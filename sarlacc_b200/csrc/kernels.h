@@ -54,6 +54,7 @@ struct AlignArgs {
     int kinds;                /* bit k set if some reference column has ColKind k */
     /* wavefront geometry */
     int G, C;
+    int pair_rows;            /* 1: wf_forward2 (two rows per lane step) */
     /* outputs */
     double* score;            /* [nref][n] (may be null when nref > 1 and only the reduction is wanted) */
     int32_t* best_id;         /* [n] multi-reference running best (R/barcodeAlign.R:28-34), nref > 1 only */
