@@ -190,7 +190,8 @@ bool choose_geometry(Plan& P) {
 
 void build_plan(Plan& P, const Encoding& enc, const char* const* refs, int nref, int L, bool local, double go, double ge, bool trace = true) {
     P.enc = &enc;
-    P.wide_ok = !trace && std::getenv("SARLACC_NO_WIDE_C") == nullptr;
+    (void)trace;   /* with two rows per step the 14-18 column geometries win with and without trace records (profiles/) */
+    P.wide_ok = std::getenv("SARLACC_NO_WIDE_C") == nullptr;
     P.L = L;
     P.nref = nref;
     P.local = local;

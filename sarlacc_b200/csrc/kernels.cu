@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
         if (steps > 0) {
             const int inc = act ? 2 : 0;
             const long long finc = act ? 2 * G : 0;
-#pragma unroll kPairUnroll
+#pragma unroll (C > 12 ? 1 : kPairUnroll)
             for (int s = 0; s < steps; ++s) {
                 const double SlA = __shfl_up_sync(FULL, outSA, 1, G);
                 const double ElA = __shfl_up_sync(FULL, outEA, 1, G);
