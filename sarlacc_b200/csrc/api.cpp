@@ -575,8 +575,8 @@ struct Outputs {   /* device pointers; any may be null */
 
 /* Scratch for one in-flight run on one stream. */
 struct Scratch {
-    DevBuf flags, map, gS, gE, gC;
-    void release() { flags.release(); map.release(); gS.release(); gE.release(); gC.release(); }
+    DevBuf flags, map, endrow, gS, gE, gC;
+    void release() { flags.release(); map.release(); endrow.release(); gS.release(); gE.release(); gC.release(); }
 };
 
 size_t scratch_budget_bytes() {
@@ -598,7 +598,7 @@ long long sub_chunk(const Plan& P, int maxlen, bool trace, long long n) {
         } else {
             per += (size_t)std::max(1, maxlen) * P.L;
         }
-        per += sizeof(int32_t) * ((size_t)P.L + 1);
+        per += sizeof(int32_t) * ((size_t)P.L + 2);
     }
     if (per == 0) return n;
     long long cn = (long long)(scratch_budget_bytes() / per);
@@ -691,6 +691,8 @@ const char* run_device(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t
                 const int wb = P.C <= 8 ? 4 : (P.C <= 16 ? 8 : 16);
                 A.fstride = (long long)(maxlen + kSkew * P.G) * P.G;
                 S.flags.reserve((size_t)A.fstride * wb * m);
+                S.endrow.reserve(sizeof(int32_t) * (size_t)m);
+                A.endrow = std::getenv("SARLACC_NO_ENDROW") ? nullptr : S.endrow.as<int32_t>();   /* A/B switch for profiles */
                 T.layout = 0;
                 T.wordbytes = wb;
             } else {
@@ -728,6 +730,7 @@ const char* run_device(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t
             T.C = P.C;
             T.flags = A.flags;
             T.fstride = A.fstride;
+            T.endrow = A.endrow;
             T.nsec = (int)P.sec_starts.size();
             T.sec_starts = D.sec_starts;
             T.sec_ends = D.sec_ends;

@@ -109,6 +109,20 @@ __device__ __forceinline__ void store_flags(typename FlagWord<C>::type* dst, con
     }
 }
 
+/* Where the traceback's climb up one column lands.  The walk of `traceback` below, arriving at row i of a column
+ * in state F with `pending` = p, moves up again iff (p && choice != up) || choice == up, carrying p2(i); otherwise it
+ * takes the cell's own diag/left move.  With LF1(i) / LF0(i) = landing row when arriving with pending true / false:
+ *   LF1(i) = p2(i) ? LF1(i-1) : LF0(i-1),   LF0(i) = (choice(i) == up) ? LF1(i) : i,   LF0(0) = LF1(0) = 0.
+ * The forward kernels keep this for the LAST reference column (slot C-1 of lane G-1): in local mode its vertical gaps
+ * are free (src/reference_align.cpp:120-121), so the reference's backtrack<> starts with one jump over the whole
+ * unaligned read tail, and LF0(len) lets the traceback kernel start where that jump lands instead of reading one
+ * record per tail row. */
+__device__ __forceinline__ void land_step(int& lf0, int& lf1, bool pd, bool p5, bool p2, int row) {
+    const int n1 = p2 ? lf1 : lf0;
+    lf1 = n1;
+    lf0 = (pd || p5) ? row : n1;
+}
+
 constexpr int kCostEntries = 7;   /* A, C, G, T, two-fold code, three-fold code, N */
 
 template <int C, bool TRACE>
@@ -192,6 +206,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
     WT* flagp = reinterpret_cast<WT*>(A.flags);
     double best = NEG, nextb = NEG;
     int bid = 0;
+    int lf0 = 0, lf1 = 0;   /* last slot: where the traceback's climb from this row lands (see land_step) */
 
     /* One DP row of this lane's C columns.  `live` gates the only side effect (the trace store). */
     auto row_step = [&](double Sl, double El, bool live) {
@@ -223,6 +238,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
          * candidate v = max(F[i-1][c]-ve, H[i-1][c]-vo) (:145-155) and the (mis)match candidate
          * m = H[i-1][c-1] + cost (:159).  F is updated in place, m kept for phase 2. */
         double m[C];
+        bool p2last = false;
         {
             double diag = diag0;
 #pragma unroll
@@ -233,6 +249,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
                 F[k] = p2 ? Fe : vO;
                 m[k] = __dadd_rn(diag, *slotp[k]);
                 diag = (k == 0 && skip0) ? diag0 : S[k];
+                if (k == C - 1) p2last = p2;
                 if (TRACE) {
                     uint32_t& f = fw[k >> 3];
                     if (p2) f |= 8u << (4 * (k & 7));
@@ -268,6 +285,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
                 if (pd) f |= 1u << sh;
                 if (p5) f |= 2u << sh;
                 if (p1) f |= 4u << sh;
+                if (k == C - 1) land_step(lf0, lf1, pd, p5, p2last, i);
             }
         }
         outS = Sl;
@@ -305,6 +323,8 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
                     F[k] = NEG;                                   /* up_jump_score, :122 */
                 }
                 diag0 = row0s[cfirst - 1];                        /* H[0][cfirst-1] */
+                lf0 = 0;
+                lf1 = 0;
                 if (nref > 1) load_slots(b);
                 if (b == 0) { best = NEG; nextb = NEG; bid = 0; }
             }
@@ -341,6 +361,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
         if (act && i == len && j == G - 1) {
             const double s = S[C - 1];
             if (A.score) A.score[(long long)b * A.n + a] = s;
+            if (TRACE) { if (A.endrow) A.endrow[a] = lf0; }
             if (A.best_id) {
                 update_best(s, b + 1, best, nextb, bid);
                 if (b == nref - 1) {
@@ -435,6 +456,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
     WT* flagp = reinterpret_cast<WT*>(A.flags);   /* word of the next unprocessed row for this lane */
     double best = NEG, nextb = NEG;
     int bid = 0;
+    int lf0 = 0, lf1 = 0;   /* last slot: landing row of the traceback's climb (land_step) */
 
     auto fill_table = [&](double* tab, unsigned rw) {
         const unsigned q = rw & 0xffu;
@@ -469,6 +491,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
         for (int x = 0; x < (C + 7) / 8; ++x) { fa[x] = 0; fb[x] = 0; }
         /* row A, phase 1: vertical and (mis)match candidates of every column (:145-159); F updated in place */
         double mA[C];
+        bool p2lastA = false;
         {
             double diag = diag0;
 #pragma unroll
@@ -479,6 +502,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
                 F[k] = p2 ? Fe : vO;
                 mA[k] = __dadd_rn(diag, *slotp[k]);
                 diag = (k == 0 && skip0) ? diag0 : S[k];
+                if (k == C - 1) p2lastA = p2;
                 if (TRACE) { if (p2) fa[k >> 3] |= 8u << (4 * (k & 7)); }
             }
         }
@@ -508,6 +532,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
                     if (pd) fa[k >> 3] |= 1u << sh;
                     if (p5) fa[k >> 3] |= 2u << sh;
                     if (p1) fa[k >> 3] |= 4u << sh;
+                    if (k == C - 1) land_step(lf0, lf1, pd, p5, p2lastA, i + 1);
                 }
             }
             if (k >= 1) {
@@ -548,6 +573,16 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
                     if (pd) fb[kk >> 3] |= 1u << sh;
                     if (p5) fb[kk >> 3] |= 2u << sh;
                     if (p1) fb[kk >> 3] |= 4u << sh;
+                    if (kk == C - 1) {
+                        if (MASKED) {
+                            int t0 = lf0, t1 = lf1;
+                            land_step(t0, t1, pd, p5, p2, i + 2);
+                            lf0 = hasB ? t0 : lf0;
+                            lf1 = hasB ? t1 : lf1;
+                        } else {
+                            land_step(lf0, lf1, pd, p5, p2, i + 2);
+                        }
+                    }
                 }
             }
         }
@@ -590,6 +625,8 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
                     F[k] = NEG;
                 }
                 diag0 = row0s[cfirst - 1];
+                lf0 = 0;
+                lf1 = 0;
                 if (nref > 1) load_slots(b);
                 if (b == 0) { best = NEG; nextb = NEG; bid = 0; }
             }
@@ -635,6 +672,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
         if (act && i == len && j == G - 1) {
             const double s = S[C - 1];
             if (A.score) A.score[(long long)b * A.n + a] = s;
+            if (TRACE) { if (A.endrow) A.endrow[a] = lf0; }
             if (A.best_id) {
                 update_best(s, b + 1, best, nextb, bid);
                 if (b == nref - 1) {
@@ -825,6 +863,14 @@ __global__ void __launch_bounds__(128) traceback(const TraceArgs T)
     enum { ST_H = 0, ST_E = 1, ST_F = 2 };
     int i = len, c = L, state = ST_H;
     bool pending = false;   /* p1 (in ST_E) / p2 (in ST_F) of the cell the current run came from */
+    if (T.endrow && len > 0 && L > 0) {
+        /* the forward kernel already followed the climb up the last column (land_step): skip those up-moves */
+        i = T.endrow[a];
+        for (int x = i; x < len; ++x) {
+            if (ops) ops[nops] = 'I';
+            ++nops;
+        }
+    }
     while (c > 0) {
         unsigned f;
         int ch;

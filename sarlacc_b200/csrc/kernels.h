@@ -63,6 +63,7 @@ struct AlignArgs {
     /* traceback records */
     void* flags;
     long long fstride;        /* per alignment, in flag words (wavefront) or bytes (generic) */
+    int32_t* endrow;          /* [n] wavefront + trace: row where the traceback's climb up the last column lands (optional) */
     /* generic kernel scratch: [maxlen+1][nthreads] doubles each */
     double* gS;
     double* gE;
@@ -78,6 +79,7 @@ struct TraceArgs {
     int G, C, wordbytes;
     const void* flags;
     long long fstride;
+    const int32_t* endrow;      /* [n] optional: start the walk at (endrow[a], L) instead of (len, L) */
     int nsec;
     const int32_t* sec_starts;  /* device, 0-based */
     const int32_t* sec_ends;    /* device, 1-based */

@@ -3,7 +3,8 @@ usage: python tools/sass_loop.py C trace [--dump]"""
 import re, subprocess, sys, collections
 C, tr = sys.argv[1], sys.argv[2]
 out = subprocess.run(["cuobjdump", "-sass", "sarlacc_b200/libsarlacc_b200.so"], capture_output=True, text=True).stdout
-pat = "wf_forwardILi%sELb%sEEE" % (C, tr)
+name = sys.argv[3] if len(sys.argv) > 3 and not sys.argv[3].startswith("--") else "wf_forward2"
+pat = "%sILi%sELb%sEEE" % (name, C, tr)
 lines = out.splitlines()
 st = next(i for i, l in enumerate(lines) if "Function :" in l and pat in l)
 en = next((i for i in range(st + 1, len(lines)) if "Function :" in lines[i]), len(lines))
