@@ -317,7 +317,10 @@ int host_threads_for(int ndev) {
     if (t <= 0) {
         t = (int)std::thread::hardware_concurrency();
         if (t <= 0) t = 4;
-        t = std::max(1, t / std::max(1, ndev));
+        /* one process per GPU (torchrun): the ranks of a node share its cores */
+        const char* lws = std::getenv("LOCAL_WORLD_SIZE");
+        const int ranks = lws ? std::max(1, std::atoi(lws)) : 1;
+        t = std::max(1, t / (std::max(1, ndev) * ranks));
         t = std::min(t, 32);
     }
     return t;
@@ -608,6 +611,45 @@ long long sub_chunk(const Plan& P, int maxlen, bool trace, long long n) {
 
 const char* g_last_kernel = "";
 
+int pair_rows_default() {   /* SARLACC_PAIR=0 selects the single-row kernel (A/B tests) */
+    const char* e = std::getenv("SARLACC_PAIR");
+    return e ? std::atoi(e) : 1;
+}
+
+/* Alignment groups in one full grid of the plan's forward kernel (0 for the literal kernel). */
+long long plan_groups(const Plan& P, bool trace) {
+    if (!P.fast) return 0;
+    AlignArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.L = P.L;
+    A.nref = P.nref;
+    A.enc_n = P.enc->n;
+    A.G = P.G;
+    A.C = P.C;
+    A.pair_rows = pair_rows_default();
+    return wavefront_groups(A, trace);
+}
+
+/* Every group walks its alignments back to back, so a launch over a whole number of grid-fulls of (equal-length)
+ * alignments has no tail round: 131 072 windows on 14 208 groups would run 10 rounds for 9.2 rounds of work. */
+long long whole_rounds(long long cn, long long groups) {
+    if (groups <= 0 || cn < groups) return cn;
+    return cn / groups * groups;
+}
+
+/* Reads per pipeline chunk near `target` that is a whole number of rounds for both plans if possible, else for the first. */
+long long chunk_for(long long target, long long g1, long long g2) {
+    if (g1 <= 0 && g2 <= 0) return target;
+    if (g1 <= 0) std::swap(g1, g2);
+    if (g2 > 0) {
+        long long a = g1, b = g2;
+        while (b) { const long long t = a % b; a = b; b = t; }
+        const long long l = g1 / a * g2;
+        if (l <= 2 * target) return std::max<long long>(1, (target + l / 2) / l) * l;
+    }
+    return std::max<long long>(1, (target + g1 / 2) / g1) * g1;
+}
+
 /* Optional CUDA-event bracket around the forward kernel launches of one run (roofline accounting). */
 struct FwdTimer {
     std::vector<cudaEvent_t> ev;   /* pairs */
@@ -655,7 +697,8 @@ const char* run_device(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t
      * protect the scratch buffers. */
     const char* name = "";
     if (n == 0) return name;
-    const long long cn = sub_chunk(P, maxlen, trace, n);
+    long long cn = sub_chunk(P, maxlen, trace, n);
+    if (cn < n) cn = whole_rounds(cn, plan_groups(P, trace));
     for (long long off = 0; off < n; off += cn) {
         const long long m = std::min(cn, n - off);
         AlignArgs A;
@@ -677,7 +720,7 @@ const char* run_device(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t
         A.kinds = P.kinds;
         A.G = P.G;
         A.C = P.C;
-        A.pair_rows = std::getenv("SARLACC_PAIR") ? std::atoi(std::getenv("SARLACC_PAIR")) : 1;   /* 0 selects the single-row kernel (A/B tests) */
+        A.pair_rows = pair_rows_default();
         /* [nref][n] outputs of a sub-chunk cannot be expressed with one base pointer unless n == m or nref == 1 */
         A.score = out.score ? out.score + off : nullptr;
         A.best_id = out.best_id ? out.best_id + off : nullptr;
@@ -793,6 +836,7 @@ struct HostOutputs {
 struct Slot {
     cudaStream_t st = nullptr;
     cudaEvent_t done = nullptr;
+    cudaEvent_t t_begin = nullptr, t_h2d = nullptr, t_end = nullptr;   /* SARLACC_DEBUG_TIMING: per-chunk device phases */
     PinBuf h_rows, h_lens, h_out;
     DevBuf d_rows, d_lens, d_out;
     PinBuf h_rows2, h_lens2, h_width;     /* second window set + read widths of the fused both-ends entry */
@@ -804,6 +848,9 @@ struct Slot {
     void init() {
         CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         CUDA_CHECK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreate(&t_begin));
+        CUDA_CHECK(cudaEventCreate(&t_h2d));
+        CUDA_CHECK(cudaEventCreate(&t_end));
     }
     void destroy() {
         h_rows.release(); h_lens.release(); h_out.release();
@@ -812,6 +859,10 @@ struct Slot {
         d_rows2.release(); d_lens2.release(); d_width.release(); d_tmp.release();
         scratch.release();
         if (done) cudaEventDestroy(done);
+        if (t_begin) cudaEventDestroy(t_begin);
+        if (t_h2d) cudaEventDestroy(t_h2d);
+        if (t_end) cudaEventDestroy(t_end);
+        t_begin = t_h2d = t_end = nullptr;
         if (st) cudaStreamDestroy(st);
         done = nullptr;
         st = nullptr;
@@ -851,10 +902,15 @@ OutLayout make_layout(Mode mode, long long n, int nref_scores, int nsec, int max
 
 /* Per-device resources kept between host-buffer calls.  One call at a time per device (the R boundary is
  * single-threaded; concurrent callers serialise on the device's mutex). */
+constexpr int kSlots = 3;
+
 struct DeviceCache {
     std::mutex busy;
     bool ready = false;
-    Slot slots[2];
+    /* three slots: while the device runs chunk k and chunk k+1's upload is in flight, the host packs chunk k+2
+     * (with two, the upload of k+1 could only start after k-1 had finished and k+1 been packed: the device idled
+     * ~2 ms of every 7.5 ms chunk period) */
+    Slot slots[kSlots];
     DevPlan plan;
 
     static DeviceCache& acquire(int device) {
@@ -870,23 +926,20 @@ struct DeviceCache {
         c->busy.lock();
         if (!c->ready) {
             try {
-                c->slots[0].init();
-                c->slots[1].init();
+                for (int k = 0; k < kSlots; ++k) c->slots[k].init();
             } catch (...) {
                 c->busy.unlock();
                 throw;
             }
             c->ready = true;
         }
-        c->slots[0].busy = false;
-        c->slots[1].busy = false;
+        for (int k = 0; k < kSlots; ++k) c->slots[k].busy = false;
         return *c;
     }
     void release() {
         /* make sure nothing of this call is still in flight before another call reuses the buffers */
         if (ready) {
-            cudaStreamSynchronize(slots[0].st);
-            cudaStreamSynchronize(slots[1].st);
+            for (int k = 0; k < kSlots; ++k) cudaStreamSynchronize(slots[k].st);
         }
         busy.unlock();
     }
@@ -939,12 +992,15 @@ struct DeviceJob {
         DevPlan& D = cache.plan;
         D.upload(P, slots[0].st);
 
-        /* chunk size: bounded so that staging stays modest and the trace scratch fits its budget */
-        long long chunk = 1 << 17;
+        /* chunk size: bounded so that staging stays modest and the trace scratch fits its budget; a whole number of
+         * grid-fulls of alignments (no tail round), and a smaller first chunk so that the device starts early */
+        const long long groups = plan_groups(P, trace);
+        long long chunk = chunk_for(1 << 17, groups, 0);
+        long long first_chunk = (hi - lo > chunk && groups > 0) ? std::max<long long>(1, whole_rounds(chunk / 4, groups)) : chunk;
         const char* ce = std::getenv("SARLACC_CHUNK");
-        if (ce && std::atoll(ce) > 0) chunk = std::atoll(ce);
+        if (ce && std::atoll(ce) > 0) first_chunk = chunk = std::atoll(ce);
 
-        OutLayout lay[2];
+        OutLayout lay[kSlots];
         int which = 0;
         auto drain = [&](Slot& s, const OutLayout& o) {
             if (!s.busy) return;
@@ -986,7 +1042,7 @@ struct DeviceJob {
             Slot& s = slots[which];
             drain(s, lay[which]);
             /* size the chunk: the trace scratch budget may force fewer reads than `chunk` */
-            int64_t c1 = std::min<int64_t>(hi, c0 + chunk);
+            int64_t c1 = std::min<int64_t>(hi, c0 + (c0 == lo ? first_chunk : chunk));
             s.h_lens.reserve(sizeof(int32_t) * (size_t)(c1 - c0));
             int maxlen = 0;
             scan_lengths(V, c0, c1, s.h_lens.as<int32_t>(), nthreads, err, maxlen);
@@ -1038,11 +1094,10 @@ struct DeviceJob {
             s.n = m;
             s.lo = c0;
             s.busy = true;
-            which ^= 1;
+            which = (which + 1) % kSlots;
             c0 = c1;
         }
-        drain(slots[which], lay[which]);
-        drain(slots[which ^ 1], lay[which ^ 1]);
+        for (int k = 0; k < kSlots; ++k) drain(slots[(which + k) % kSlots], lay[(which + k) % kSlots]);   /* oldest first */
     }
 };
 
@@ -1265,16 +1320,30 @@ struct PairJob {
         D[0].upload(*plan[0], slots[0].st);
         D[1].upload(*plan[1], slots[0].st);
 
-        long long chunk = 1 << 17;
+        /* chunk = a whole number of grid-fulls for both adaptors' kernels (no tail round); the first chunk is a quarter
+         * of that so that the device starts early */
+        const long long g_a1 = plan_groups(*plan[0], true), g_a2 = plan_groups(*plan[1], true);
+        long long chunk = chunk_for(1 << 17, g_a1, g_a2);
+        long long first_chunk = (hi - lo > chunk) ? std::max<long long>(1, whole_rounds(chunk / 4, std::max(g_a1, g_a2) > 0 ? (g_a1 > 0 ? g_a1 : g_a2) : 0)) : chunk;
         const char* ce = std::getenv("SARLACC_CHUNK");
-        if (ce && std::atoll(ce) > 0) chunk = std::atoll(ce);
+        if (ce && std::atoll(ce) > 0) first_chunk = chunk = std::atoll(ce);
         auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-        FinalLayout lay[2];
+        FinalLayout lay[kSlots];
         int which = 0;
 
+        const bool dbg = std::getenv("SARLACC_DEBUG_TIMING") != nullptr;
+        auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double t_start = now();
         auto drain = [&](Slot& s, const FinalLayout& o) {
             if (!s.busy) return;
             CUDA_CHECK(cudaEventSynchronize(s.done));
+            if (dbg) {
+                float a = 0, b = 0;
+                cudaEventElapsedTime(&a, s.t_begin, s.t_h2d);
+                cudaEventElapsedTime(&b, s.t_h2d, s.t_end);
+                std::fprintf(stderr, "[sarlacc]   chunk at %lld (%lld reads): H2D %.2f ms, kernels + D2H %.2f ms, host clock %.1f ms\n",
+                             (long long)s.lo, s.n, a, b, (now() - t_start) * 1e3);
+            }
             const uint8_t* h = s.h_out.as<uint8_t>();
             const long long m = s.n;
             const int64_t g0 = s.lo;
@@ -1291,16 +1360,14 @@ struct PairJob {
             s.busy = false;
         };
 
-        const bool dbg = std::getenv("SARLACC_DEBUG_TIMING") != nullptr;
         double t_drain = 0, t_pack = 0, t_enq = 0;
-        auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         for (int64_t c0 = lo; c0 < hi;) {
             Slot& s = slots[which];
             double t0 = now();
             drain(s, lay[which]);
             t_drain += now() - t0;
             t0 = now();
-            int64_t c1 = std::min<int64_t>(hi, c0 + chunk);
+            int64_t c1 = std::min<int64_t>(hi, c0 + (c0 == lo ? first_chunk : chunk));
             s.h_lens.reserve(sizeof(int32_t) * (size_t)(c1 - c0));
             s.h_lens2.reserve(sizeof(int32_t) * (size_t)(c1 - c0));
             int maxf = 0, maxb = 0;
@@ -1359,6 +1426,7 @@ struct PairJob {
             s.d_tmp.reserve(T.total);
             s.d_out.reserve(F.total);
             s.h_out.reserve(F.total);
+            if (dbg) CUDA_CHECK(cudaEventRecord(s.t_begin, s.st));
             CUDA_CHECK(cudaMemcpyAsync(s.d_rows.p, s.h_rows.p, sizeof(uint16_t) * (size_t)m * stride_f, cudaMemcpyHostToDevice, s.st));
             CUDA_CHECK(cudaMemcpyAsync(s.d_rows2.p, s.h_rows2.p, sizeof(uint16_t) * (size_t)m * stride_b, cudaMemcpyHostToDevice, s.st));
             CUDA_CHECK(cudaMemcpyAsync(s.d_lens.p, s.h_lens.p, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
@@ -1377,6 +1445,7 @@ struct PairJob {
                 }
                 CUDA_CHECK(cudaMemcpyAsync(s.d_width.p, s.h_width.p, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
             }
+            if (dbg) CUDA_CHECK(cudaEventRecord(s.t_h2d, s.st));
             uint8_t* t = s.d_tmp.as<uint8_t>();
             ResultSet rs[4];
             for (int r = 0; r < 4; ++r) {
@@ -1411,17 +1480,17 @@ struct PairJob {
             g_launches += 1;
             CUDA_CHECK(cudaGetLastError());
             CUDA_CHECK(cudaMemcpyAsync(s.h_out.p, s.d_out.p, F.total, cudaMemcpyDeviceToHost, s.st));
+            if (dbg) CUDA_CHECK(cudaEventRecord(s.t_end, s.st));
             CUDA_CHECK(cudaEventRecord(s.done, s.st));
             s.n = m;
             s.lo = c0;
             s.busy = true;
-            which ^= 1;
+            which = (which + 1) % kSlots;
             c0 = c1;
             t_enq += now() - t0;
         }
         double t0 = now();
-        drain(slots[which], lay[which]);
-        drain(slots[which ^ 1], lay[which ^ 1]);
+        for (int k = 0; k < kSlots; ++k) drain(slots[(which + k) % kSlots], lay[(which + k) % kSlots]);   /* oldest first */
         t_drain += now() - t0;
         if (dbg) std::fprintf(stderr, "[sarlacc] pair job dev %d: pack %.1f ms, enqueue %.1f ms, wait+copy-out %.1f ms\n", device, t_pack * 1e3, t_enq * 1e3, t_drain * 1e3);
     }
@@ -2082,6 +2151,7 @@ int sarlacc_resident_align(sarlacc_resident* r, int mode, double gapopen, double
         const bool overlap = trace && std::getenv("SARLACC_NO_OVERLAP") == nullptr;
         if (overlap && cn >= r->n && r->n >= 65536) cn = (r->n + 1) / 2;          /* at least two ranges to overlap */
         else if (overlap && cn < r->n) cn = std::max<long long>(1, cn / 2);
+        if (cn < r->n) cn = whole_rounds(cn, plan_groups(cp->plan, trace));
         r->sub = cn;
         const char* name = "";
         r->timer.used = 0;

@@ -453,6 +453,12 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
     int i = 0, len = 0, delay = j;
     bool done = false;
     const uint16_t* rowp = A.rows;          /* points at the next unprocessed row */
+    unsigned cur = 0;                        /* rows i+1, i+2 (two 16-bit entries), loaded one step ahead */
+    /* the next step's two rows, requested before this step's arithmetic; i stays even until the last row, so the
+     * 32-bit load is aligned, and stride >= len + 1 keeps an odd last row's partner inside the window's slot */
+    auto prefetch = [&](bool act_) -> unsigned {
+        return (act_ && i + 2 < len) ? *reinterpret_cast<const unsigned*>(rowp + 2) : 0u;
+    };
     WT* flagp = reinterpret_cast<WT*>(A.flags);   /* word of the next unprocessed row for this lane */
     double best = NEG, nextb = NEG;
     int bid = 0;
@@ -473,10 +479,10 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
 
     /* Rows i+1 (A) and i+2 (B) of this lane's C columns.  MASKED: row B may not exist (hasB false) and then must leave no
      * trace in the state.  `live` gates the trace stores. */
-    auto pair_step = [&](auto masked_tag, double SlA, double ElA, double SlB, double ElB, bool live, bool hasB) {
+    auto pair_step = [&](auto masked_tag, unsigned rw2, double SlA, double ElA, double SlB, double ElB, bool live, bool hasB) {
         constexpr bool MASKED = decltype(masked_tag)::value;
-        fill_table(mytab, rowp[0]);
-        fill_table(mytab + kTab, rowp[1]);
+        fill_table(mytab, rw2 & 0xffffu);
+        fill_table(mytab + kTab, rw2 >> 16);
         {   /* column 0 feeds the first lane: src/reference_align.cpp:64-78 */
             double c0a = 0.0, c0b = 0.0;
             if (!local) { c0a = col0_value(0, gop, ge, i + 1); c0b = col0_value(0, gop, ge, i + 2); }
@@ -617,6 +623,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
             } else {
                 i = 0;
                 rowp = A.rows + a * (long long)A.stride;
+                cur = *reinterpret_cast<const unsigned*>(rowp);
                 if (TRACE) flagp = reinterpret_cast<WT*>(A.flags) + a * A.fstride + (long long)(1 + 2 * j) * G + j;   /* word (i + 2j) * G + j, i = 1 */
 #pragma unroll
                 for (int k = 0; k < C; ++k) {
@@ -639,8 +646,6 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
         else room = done ? 0x7fffffff : 0;
         const int steps = __reduce_min_sync(FULL, room);
         if (steps == 0x7fffffff) break;
-        const uint16_t* keep_rowp = rowp;
-        if (!act) rowp = A.rows;
         if (steps > 0) {
             const int inc = act ? 2 : 0;
             const long long finc = act ? 2 * G : 0;
@@ -650,7 +655,9 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
                 const double ElA = __shfl_up_sync(FULL, outEA, 1, G);
                 const double SlB = __shfl_up_sync(FULL, outSB, 1, G);
                 const double ElB = __shfl_up_sync(FULL, outEB, 1, G);
-                pair_step(std::false_type(), SlA, ElA, SlB, ElB, act, true);
+                const unsigned nxt = prefetch(act);
+                pair_step(std::false_type(), cur, SlA, ElA, SlB, ElB, act, true);
+                cur = nxt;
                 i += inc;
                 rowp += inc;
                 if (TRACE) flagp += finc;
@@ -661,13 +668,14 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
             const double SlB = __shfl_up_sync(FULL, outSB, 1, G);
             const double ElB = __shfl_up_sync(FULL, outEB, 1, G);
             const bool hasB = act && (len - i) >= 2;
-            pair_step(std::true_type(), SlA, ElA, SlB, ElB, act, hasB);
+            const unsigned nxt = prefetch(act);
+            pair_step(std::true_type(), act ? (hasB ? cur : (cur & 0xffffu)) : 0u, SlA, ElA, SlB, ElB, act, hasB);   /* a missing row B reads as entry 0, never as whatever follows the window */
+            cur = nxt;
             const int inc = act ? (hasB ? 2 : 1) : 0;
             i += inc;
             rowp += inc;
             if (TRACE) flagp += (long long)inc * G;
         }
-        if (!act) rowp = keep_rowp;
 
         if (act && i == len && j == G - 1) {
             const double s = S[C - 1];
@@ -1028,17 +1036,25 @@ __global__ void __launch_bounds__(128) scramble_rows(const uint16_t* in, uint16_
 }
 
 template <int C, bool TRACE>
+int wf_resident_blocks(bool pair, size_t smem) {
+    auto kern = pair ? wf_forward2<C, TRACE> : wf_forward<C, TRACE>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, kBlock, smem);
+    return per < 1 ? 1 : per;
+}
+
+template <int C, bool TRACE>
 const char* launch_wf(const AlignArgs& a, int grid, cudaStream_t st, size_t smem) {
     const bool pair = a.pair_rows != 0;
     auto kern = pair ? wf_forward2<C, TRACE> : wf_forward<C, TRACE>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (grid <= 0) {
-        int dev = 0, sms = 0, per = 0;
+        int dev = 0, sms = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, kBlock, smem);
-        if (per < 1) per = 1;
-        grid = sms * per;
+        grid = sms * wf_resident_blocks<C, TRACE>(pair, smem);
+    } else if (smem > 48 * 1024) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
     /* never more groups than alignments */
     const long long groups_per_block = (long long)(kBlock / 32) * (32 / a.G);
@@ -1048,10 +1064,22 @@ const char* launch_wf(const AlignArgs& a, int grid, cudaStream_t st, size_t smem
     return pair ? (TRACE ? "wf_forward2<trace>" : "wf_forward2<score>") : (TRACE ? "wf_forward<trace>" : "wf_forward<score>");
 }
 
-template <int C>
-const char* dispatch_flags(const AlignArgs& a, bool trace, bool alt, int grid, cudaStream_t st, size_t smem) {
-    (void)alt;
-    return trace ? launch_wf<C, true>(a, grid, st, smem) : launch_wf<C, false>(a, grid, st, smem);
+/* Calls f(std::integral_constant<int, C>) for an instantiated geometry; false if a.C is not one. */
+template <class F>
+bool for_geometry(int C, F&& f) {
+#ifdef SARLACC_ONLY_C   /* tuning builds: instantiate one geometry only (tools/variants.py) */
+    if (C == SARLACC_ONLY_C) { f(std::integral_constant<int, SARLACC_ONLY_C>()); return true; }
+    return false;
+#else
+    switch (C) {
+#define SARLACC_GEOM(N) case N: f(std::integral_constant<int, N>()); return true;
+        SARLACC_GEOM(1) SARLACC_GEOM(2) SARLACC_GEOM(3) SARLACC_GEOM(4) SARLACC_GEOM(5) SARLACC_GEOM(6)
+        SARLACC_GEOM(7) SARLACC_GEOM(8) SARLACC_GEOM(9) SARLACC_GEOM(10) SARLACC_GEOM(11) SARLACC_GEOM(12)
+        SARLACC_GEOM(14) SARLACC_GEOM(16) SARLACC_GEOM(18)
+#undef SARLACC_GEOM
+    }
+    return false;
+#endif
 }
 
 }  // namespace
@@ -1065,29 +1093,28 @@ size_t wavefront_smem_bytes(const AlignArgs& a) {
 int wavefront_block_threads() { return kBlock; }
 
 const char* launch_wavefront(const AlignArgs& a, bool trace, bool has_alt, int grid, cudaStream_t st) {
+    (void)has_alt;
     const size_t smem = wavefront_smem_bytes(a);
-#ifdef SARLACC_ONLY_C   /* tuning builds: instantiate one geometry only (tools/variants.py) */
-    if (a.C == SARLACC_ONLY_C) return dispatch_flags<SARLACC_ONLY_C>(a, trace, has_alt, grid, st, smem);
-#else
-    switch (a.C) {
-        case 1: return dispatch_flags<1>(a, trace, has_alt, grid, st, smem);
-        case 2: return dispatch_flags<2>(a, trace, has_alt, grid, st, smem);
-        case 3: return dispatch_flags<3>(a, trace, has_alt, grid, st, smem);
-        case 4: return dispatch_flags<4>(a, trace, has_alt, grid, st, smem);
-        case 5: return dispatch_flags<5>(a, trace, has_alt, grid, st, smem);
-        case 6: return dispatch_flags<6>(a, trace, has_alt, grid, st, smem);
-        case 7: return dispatch_flags<7>(a, trace, has_alt, grid, st, smem);
-        case 8: return dispatch_flags<8>(a, trace, has_alt, grid, st, smem);
-        case 9: return dispatch_flags<9>(a, trace, has_alt, grid, st, smem);
-        case 10: return dispatch_flags<10>(a, trace, has_alt, grid, st, smem);
-        case 11: return dispatch_flags<11>(a, trace, has_alt, grid, st, smem);
-        case 12: return dispatch_flags<12>(a, trace, has_alt, grid, st, smem);
-        case 14: return dispatch_flags<14>(a, trace, has_alt, grid, st, smem);
-        case 16: return dispatch_flags<16>(a, trace, has_alt, grid, st, smem);
-        case 18: return dispatch_flags<18>(a, trace, has_alt, grid, st, smem);
-    }
-#endif
-    return nullptr;
+    const char* name = nullptr;
+    for_geometry(a.C, [&](auto ctag) {
+        constexpr int C = decltype(ctag)::value;
+        name = trace ? launch_wf<C, true>(a, grid, st, smem) : launch_wf<C, false>(a, grid, st, smem);
+    });
+    return name;
+}
+
+long long wavefront_groups(const AlignArgs& a, bool trace) {
+    const size_t smem = wavefront_smem_bytes(a);
+    int per = 0;
+    for_geometry(a.C, [&](auto ctag) {
+        constexpr int C = decltype(ctag)::value;
+        per = trace ? wf_resident_blocks<C, true>(a.pair_rows != 0, smem) : wf_resident_blocks<C, false>(a.pair_rows != 0, smem);
+    });
+    if (per == 0) return 0;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (long long)sms * per * (kBlock / 32) * (32 / a.G);
 }
 
 const char* launch_generic(const AlignArgs& a, bool trace, int grid, cudaStream_t st) {

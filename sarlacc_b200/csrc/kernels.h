@@ -127,6 +127,9 @@ const char* launch_generic(const AlignArgs& a, bool trace, int grid, cudaStream_
 void launch_traceback(const TraceArgs& t, cudaStream_t st);
 void launch_fill_empty(const AlignArgs& a, cudaStream_t st);
 size_t wavefront_smem_bytes(const AlignArgs& a);
+/* Alignment groups of one full grid of the wavefront kernel on the current device (0: geometry not instantiated).
+ * Every group walks its alignments back to back, so a launch over k * groups equal-length alignments has no tail. */
+long long wavefront_groups(const AlignArgs& a, bool trace);
 int wavefront_block_threads();
 
 }

@@ -186,11 +186,11 @@ def adaptor_align_windows(front, back, encoding, gapopen, gapext, adaptor1, adap
             raise SarlaccError("section starts and ends should have the same length")
         secs.append((ss, se))
     width = None if read_width is None else np.ascontiguousarray(read_width, dtype=np.int32)
-    rev = np.zeros(max(n, 1), np.uint8)
+    rev = np.empty(max(n, 1), np.uint8)      # every element is written by the call (n > 0) -- no zero fill, no copies below
     outs = []
     for ss, se in secs:
-        outs.append([np.zeros(n, np.float64), np.zeros(n, np.int32), np.zeros(n, np.int32),
-                     np.zeros((max(len(ss), 1), max(n, 1)), np.int32), np.zeros((max(len(ss), 1), max(n, 1)), np.int32)])
+        outs.append([np.empty(n, np.float64), np.empty(n, np.int32), np.empty(n, np.int32),
+                     np.empty((max(len(ss), 1), max(n, 1)), np.int32), np.empty((max(len(ss), 1), max(n, 1)), np.int32)])
     _lib.check(_lib.lib.sarlacc_adaptor_align_windows(
         rf.ref(), rb.ref(), ea.ref(), C.c_double(go), C.c_double(ge), a1.encode("latin-1"), a2.encode("latin-1"),
         C.c_int(len(secs[0][0])), _lib._ptr(secs[0][0]), _lib._ptr(secs[0][1]),
@@ -200,8 +200,8 @@ def adaptor_align_windows(front, back, encoding, gapopen, gapext, adaptor1, adap
     res = []
     for k, (ss, se) in enumerate(secs):
         o = outs[k]
-        res.append([o[0], o[1], o[2], [o[3][i, :n].copy() for i in range(len(ss))], [o[4][i, :n].copy() for i in range(len(ss))]])
-    return rev[:n].astype(bool), res[0], res[1]
+        res.append([o[0], o[1], o[2], [o[3][i, :n] for i in range(len(ss))], [o[4][i, :n] for i in range(len(ss))]])
+    return rev[:n].view(np.bool_), res[0], res[1]
 
 
 def adaptor_align_reads(reads, tolerance, encoding, gapopen, gapext, adaptor1, adaptor2, sec1=((), ()), sec2=((), ()),
@@ -223,11 +223,11 @@ def adaptor_align_reads(reads, tolerance, encoding, gapopen, gapext, adaptor1, a
             raise SarlaccError("section starts and ends should have the same length")
         secs.append((ss, se))
     width = np.zeros(max(n, 1), np.int32)
-    rev = np.zeros(max(n, 1), np.uint8)
+    rev = np.empty(max(n, 1), np.uint8)      # every element is written by the call (n > 0) -- no zero fill, no copies below
     outs = []
     for ss, se in secs:
-        outs.append([np.zeros(n, np.float64), np.zeros(n, np.int32), np.zeros(n, np.int32),
-                     np.zeros((max(len(ss), 1), max(n, 1)), np.int32), np.zeros((max(len(ss), 1), max(n, 1)), np.int32)])
+        outs.append([np.empty(n, np.float64), np.empty(n, np.int32), np.empty(n, np.int32),
+                     np.empty((max(len(ss), 1), max(n, 1)), np.int32), np.empty((max(len(ss), 1), max(n, 1)), np.int32)])
     _lib.check(_lib.lib.sarlacc_adaptor_align_reads(
         rr.ref(), C.c_int(int(tolerance)), ea.ref(), C.c_double(go), C.c_double(ge), a1.encode("latin-1"), a2.encode("latin-1"),
         C.c_int(len(secs[0][0])), _lib._ptr(secs[0][0]), _lib._ptr(secs[0][1]),
@@ -237,8 +237,8 @@ def adaptor_align_reads(reads, tolerance, encoding, gapopen, gapext, adaptor1, a
     res = []
     for k, (ss, se) in enumerate(secs):
         o = outs[k]
-        res.append([o[0], o[1], o[2], [o[3][i, :n].copy() for i in range(len(ss))], [o[4][i, :n].copy() for i in range(len(ss))]])
-    return width[:n], rev[:n].astype(bool), res[0], res[1]
+        res.append([o[0], o[1], o[2], [o[3][i, :n] for i in range(len(ss))], [o[4][i, :n] for i in range(len(ss))]])
+    return width[:n], rev[:n].view(np.bool_), res[0], res[1]
 
 
 class Resident:
