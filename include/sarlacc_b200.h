@@ -183,6 +183,16 @@ const char* sarlacc_resident_last_kernel(const sarlacc_resident* r);
 void   sarlacc_resident_set_timing(sarlacc_resident* r, int on);
 double sarlacc_resident_forward_ms(sarlacc_resident* r);
 
+/* ---- host packer, exposed for tests (no device involved) ------------------------------------------
+ * Packs reads [0, n) the way every entry point above does before upload: rows[i*stride + r] = quality index
+ * (min(qual - offset, |enc| - 1), src/reference_align.cpp:218-221) | one-hot base << 8 (src/DNA_input.cpp:64-75
+ * folded in).  tolerance > 0 cuts the window .get_front_and_back would (R/adaptorAlign.R:86-95): the first
+ * min(tolerance, width) bases, or with back != 0 the reverse complement of the last ones.  force_scalar != 0 bypasses
+ * the vector packer.  lens[i] receives the window length (0 for a sequence/quality length mismatch); stride must be
+ * >= the longest window.  Returns 0, or 1 with sarlacc_last_error() set (the reference's messages). */
+int sarlacc_pack_rows(const sarlacc_reads* reads, const sarlacc_encoding* encoding, int tolerance, int back,
+                      int stride, uint16_t* rows, int32_t* lens, int force_scalar);
+
 /* ---- FASTQ ingest (host side; stands in for ShortRead::FastqStreamer + .FASTQ2QSDS, R/adaptorAlign.R:26,36,104-110) --
  * Buffered reader of plain-text 4-line FASTQ records yielding chunks as CSR pools that can be handed straight back as a
  * sarlacc_reads (CSR layout).  Names exclude the leading '@'.  Pointers stay valid until the next call on the handle. */

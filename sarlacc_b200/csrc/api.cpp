@@ -266,6 +266,11 @@ struct PackTables {
     uint8_t base_rc[256];   /* one-hot code of the complement (A<->T, C<->G); 0 for everything else */
     /* quality byte -> index, or 0xFFFF when below the offset (signed char comparison, :215) */
     uint16_t qidx[256];
+    /* the same mapping in closed form for the vector packer */
+    uint8_t code[4];
+    int8_t offset;
+    uint8_t clamp;
+    bool simd_ok;
 };
 
 void build_pack_tables(PackTables& T, int seq_encoding, const Encoding& enc) {
@@ -276,6 +281,14 @@ void build_pack_tables(PackTables& T, int seq_encoding, const Encoding& enc) {
         T.base[(unsigned char)'A'] = 1; T.base[(unsigned char)'C'] = 2;
         T.base[(unsigned char)'G'] = 4; T.base[(unsigned char)'T'] = 8;
     }
+    if (seq_encoding == SARLACC_SEQ_BIOSTRINGS) {
+        T.code[0] = 1; T.code[1] = 2; T.code[2] = 4; T.code[3] = 8;
+    } else {
+        T.code[0] = 'A'; T.code[1] = 'C'; T.code[2] = 'G'; T.code[3] = 'T';
+    }
+    T.offset = (int8_t)enc.offset;
+    T.clamp = (uint8_t)std::min(enc.n - 1, 255);
+    T.simd_ok = enc.n >= 1;
     static const uint8_t comp[16] = {0, 8, 4, 0, 2, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0};
     for (int b = 0; b < 256; ++b) T.base_rc[b] = comp[T.base[b] & 15];
     for (int b = 0; b < 256; ++b) {
@@ -447,18 +460,93 @@ void scan_lengths(const ReadView& V, int64_t lo, int64_t hi, int32_t* lens, int 
     }
 }
 
+/* AVX2 packer (chosen at run time): 32 bases per iteration.  one-hot base = OR of four byte compares against the
+ * encoding's A/C/G/T codes; quality index = min(q - offset, |enc| - 1) with the reference's signed `q < offset` test
+ * (src/reference_align.cpp:215-221); the two byte vectors are interleaved into the uint16 rows.  The tail re-does the
+ * last 32 bases of the window (overlapping stores of identical values) instead of a scalar loop. */
+#if defined(__x86_64__) && defined(__GNUC__)
+#define SARLACC_HAVE_AVX2_PACK 1
+#include <immintrin.h>
+
+struct PackConsts {
+    uint8_t code[4];      /* input bytes of A, C, G, T */
+    int8_t offset;        /* smallest encoded quality (signed char, like the reference) */
+    uint8_t clamp;        /* min(|enc| - 1, 255) */
+};
+
+__attribute__((target("avx2"))) static inline void pack32_avx2(__m256i x, __m256i qv, const PackConsts& K, bool rc, uint16_t* out, __m256i& bad_acc) {
+    const __m256i b0 = _mm256_and_si256(_mm256_cmpeq_epi8(x, _mm256_set1_epi8((char)K.code[0])), _mm256_set1_epi8(rc ? 8 : 1));
+    const __m256i b1 = _mm256_and_si256(_mm256_cmpeq_epi8(x, _mm256_set1_epi8((char)K.code[1])), _mm256_set1_epi8(rc ? 4 : 2));
+    const __m256i b2 = _mm256_and_si256(_mm256_cmpeq_epi8(x, _mm256_set1_epi8((char)K.code[2])), _mm256_set1_epi8(rc ? 2 : 4));
+    const __m256i b3 = _mm256_and_si256(_mm256_cmpeq_epi8(x, _mm256_set1_epi8((char)K.code[3])), _mm256_set1_epi8(rc ? 1 : 8));
+    const __m256i base = _mm256_or_si256(_mm256_or_si256(b0, b1), _mm256_or_si256(b2, b3));
+    const __m256i offv = _mm256_set1_epi8((char)K.offset);
+    const __m256i bad = _mm256_cmpgt_epi8(offv, qv);                                /* signed q < offset */
+    bad_acc = _mm256_or_si256(bad_acc, bad);
+    __m256i qi = _mm256_min_epu8(_mm256_sub_epi8(qv, offv), _mm256_set1_epi8((char)K.clamp));
+    qi = _mm256_andnot_si256(bad, qi);                                              /* failing reads pack index 0 */
+    const __m256i lo = _mm256_unpacklo_epi8(qi, base);                              /* elements 0-7 | 16-23 */
+    const __m256i hi = _mm256_unpackhi_epi8(qi, base);                              /* elements 8-15 | 24-31 */
+    _mm256_storeu_si256(reinterpret_cast<__m256i*>(out), _mm256_permute2x128_si256(lo, hi, 0x20));
+    _mm256_storeu_si256(reinterpret_cast<__m256i*>(out + 16), _mm256_permute2x128_si256(lo, hi, 0x31));
+}
+
+__attribute__((target("avx2"))) static inline __m256i reverse32_avx2(__m256i v) {
+    const __m256i idx = _mm256_setr_epi8(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
+    return _mm256_permute2x128_si256(_mm256_shuffle_epi8(v, idx), _mm256_shuffle_epi8(v, idx), 0x01);
+}
+
+/* One window of len >= 32 bases; returns true if some quality was below the offset. */
+__attribute__((target("avx2"))) static bool pack_window_avx2(const uint8_t* s, const uint8_t* q, int len, bool back, const PackConsts& K, uint16_t* out) {
+    __m256i bad = _mm256_setzero_si256();
+    for (int r = 0;; r += 32) {
+        if (r + 32 > len) r = len - 32;      /* last block: overlap */
+        if (!back) {
+            pack32_avx2(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + r)),
+                        _mm256_loadu_si256(reinterpret_cast<const __m256i*>(q + r)), K, false, out + r, bad);
+        } else {
+            /* out[r .. r+31] come from positions len-1-r down to len-32-r */
+            pack32_avx2(reverse32_avx2(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + len - 32 - r))),
+                        reverse32_avx2(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(q + len - 32 - r))), K, true, out + r, bad);
+        }
+        if (r + 32 >= len) break;
+    }
+    return !_mm256_testz_si256(bad, bad);
+}
+
+static bool have_avx2() {
+    static const bool ok = __builtin_cpu_supports("avx2") && std::getenv("SARLACC_NO_AVX2") == nullptr;
+    return ok;
+}
+#endif
+
 /* Pass 2: rows[(i-lo)*stride + r] = qidx | base << 8.  Quality errors only matter when a cost would have been
  * computed for that read, i.e. L > 0 (src/reference_align.cpp:184-225 is only reached from align_column). */
 void pack_rows(const ReadView& V, int64_t lo, int64_t hi, const PackTables& T, const int32_t* lens, int stride,
-        uint16_t* rows, int nthreads, bool check_qual, FirstError& err)
+        uint16_t* rows, int nthreads, bool check_qual, FirstError& err, bool force_scalar = false)
 {
     std::vector<FirstError> errs(nthreads + 1);
+#ifdef SARLACC_HAVE_AVX2_PACK
+    PackConsts K;
+    bool simd = have_avx2() && T.simd_ok && !force_scalar;
+    if (simd) {
+        std::memcpy(K.code, T.code, 4);
+        K.offset = T.offset;
+        K.clamp = T.clamp;
+    }
+#endif
     parallel_for(lo, hi, nthreads, [&](int64_t a, int64_t b, int t) {
         for (int64_t i = a; i < b; ++i) {
             const int len = lens[i - lo];
             uint16_t* out = rows + (size_t)(i - lo) * stride;
             const uint8_t* s = V.seq(i);
             const uint8_t* q = V.qual(i);
+#ifdef SARLACC_HAVE_AVX2_PACK
+            if (simd && len >= 32) {
+                if (pack_window_avx2(s, q, len, V.back, K, out) && check_qual) errs[t].offer(i, ERR_QUAL);
+                continue;
+            }
+#endif
             unsigned bad = 0;
             if (!V.back) {
                 for (int r = 0; r < len; ++r) {
@@ -1786,6 +1874,26 @@ int sarlacc_adaptor_align_reads(const sarlacc_reads* reads, int tolerance, const
     return align_pair(reads, reads, tolerance, encoding, gapopen, gapext, adaptor1, adaptor2, nsec1, sec_starts1, sec_ends1,
                       nsec2, sec_starts2, sec_ends2, nullptr, read_width, reversed,
                       score1, start1, end1, sec_start1, sec_width1, score2, start2, end2, sec_start2, sec_width2);
+}
+
+int sarlacc_pack_rows(const sarlacc_reads* reads, const sarlacc_encoding* encoding, int tolerance, int back,
+                      int stride, uint16_t* rows, int32_t* lens, int force_scalar)
+{
+    if (!reads || !rows || !lens) return fail("reads must not be NULL");
+    Encoding enc;
+    const char* msg = build_encoding(encoding, enc);
+    if (msg) return fail(msg);
+    ReadView V{reads, tolerance > 0 ? tolerance : 0, tolerance > 0 && back != 0};
+    PackTables T;
+    build_pack_tables(T, reads->seq_encoding, enc);
+    FirstError err;
+    int maxlen = 0;
+    const int nt = host_threads_for(1);
+    scan_lengths(V, 0, reads->n, lens, nt, err, maxlen);
+    if (maxlen > stride) return fail("stride is shorter than the longest window");
+    pack_rows(V, 0, reads->n, T, lens, stride, rows, nt, true, err, force_scalar != 0);
+    if (err.kind != ERR_NONE) return fail(err_text(err.kind));
+    return 0;
 }
 
 /* ---- FASTQ ingest ----------------------------------------------------------------

@@ -173,3 +173,77 @@ def test_encoding_vector():
     assert names[0] == "!" and names[-1] == "~" and len(names) == 94
     assert err[20] == 10.0 ** -2.0 and np.all(np.diff(err) <= 0)
     assert api._qual2class("phred") == "PhredQuality" and api._qual2class("solexa") == "SolexaQuality"
+
+
+def _pack(rs_args, enc, tolerance, back, stride, force_scalar, seq_encoding=0):
+    import ctypes as C
+    from sarlacc_b200 import _lib
+    ra = _lib.ReadsArg(*rs_args, seq_encoding, False)
+    ea = _lib.EncodingArg(*enc)
+    rows = np.full((ra.n, stride), 0xABCD, np.uint16)
+    lens = np.zeros(ra.n, np.int32)
+    rc = _lib.lib.sarlacc_pack_rows(ra.ref(), ea.ref(), C.c_int(tolerance), C.c_int(back), C.c_int(stride),
+                                    _lib._ptr(rows), _lib._ptr(lens), C.c_int(force_scalar))
+    return rc, rows, lens
+
+
+def test_vector_packer_matches_scalar_and_numpy():
+    """The AVX2 packer, the table packer and a numpy restatement of DNA_input decode + the quality clamp
+    (src/DNA_input.cpp:64-75, src/reference_align.cpp:215-221, R/adaptorAlign.R:86-95) agree on every entry."""
+    from sarlacc_b200 import _lib
+    from sarlacc_b200.native import phred_encoding
+    rng = np.random.default_rng(7)
+    n = 300
+    lens_true = rng.integers(0, 400, size=n)
+    lens_true[:8] = [0, 1, 31, 32, 33, 63, 64, 65]
+    alphabet = np.frombuffer(b"ACGTNacgtRYKM-", np.uint8)
+    off = np.concatenate([[0], np.cumsum(lens_true)]).astype(np.int64)
+    seq = alphabet[rng.integers(0, len(alphabet), size=off[-1])]
+    qual = rng.integers(33, 127, size=off[-1]).astype(np.uint8)
+    onehot = np.zeros(256, np.uint16)
+    for ch, v in zip(b"ACGT", (1, 2, 4, 8)):
+        onehot[ch] = v
+    comp = np.zeros(256, np.uint16)
+    for ch, v in zip(b"ACGT", (8, 4, 2, 1)):
+        comp[ch] = v
+    for nenc in (94, 42):       # 42: qualities above the table are clamped to its last entry
+        enc = phred_encoding(nenc)
+        for tol, back in ((0, 0), (250, 0), (250, 1), (40, 1), (31, 1)):
+            stride = 400
+            rc_v, rows_v, lens_v = _pack((seq, off, qual, off), enc, tol, back, stride, 0)
+            rc_s, rows_s, lens_s = _pack((seq, off, qual, off), enc, tol, back, stride, 1)
+            assert rc_v == 0 and rc_s == 0
+            assert np.array_equal(lens_v, lens_s)
+            for i in range(n):
+                ln = int(lens_true[i]) if tol == 0 else min(tol, int(lens_true[i]))
+                assert lens_v[i] == ln
+                s = seq[off[i]:off[i + 1]]
+                q = qual[off[i]:off[i + 1]]
+                if back:
+                    s, q = s[len(s) - ln:][::-1], q[len(q) - ln:][::-1]
+                    base = comp[s]
+                else:
+                    s, q = s[:ln], q[:ln]
+                    base = onehot[s]
+                want = np.minimum(q.astype(np.int32) - 33, nenc - 1).astype(np.uint16) | (base << 8)
+                assert np.array_equal(rows_s[i, :ln], want), (nenc, tol, back, i)
+                assert np.array_equal(rows_v[i, :ln], want), (nenc, tol, back, i)
+                assert (rows_v[i, ln:] == 0xABCD).all()      # nothing written past the window
+    # Biostrings byte codes (A=1, C=2, G=4, T=8; IUPAC = OR; gaps >= 16)
+    codes = np.array([1, 2, 4, 8, 15, 3, 5, 16, 32], np.uint8)
+    seq_b = codes[rng.integers(0, len(codes), size=off[-1])]
+    for back in (0, 1):
+        rc_v, rows_v, _ = _pack((seq_b, off, qual, off), phred_encoding(), 100, back, 128, 0, seq_encoding=_lib.SEQ_BIOSTRINGS)
+        rc_s, rows_s, lens_s = _pack((seq_b, off, qual, off), phred_encoding(), 100, back, 128, 1, seq_encoding=_lib.SEQ_BIOSTRINGS)
+        assert rc_v == 0 and rc_s == 0
+        for i in range(n):
+            assert np.array_equal(rows_v[i, :lens_s[i]], rows_s[i, :lens_s[i]])
+    # a quality below the offset fails with the reference's message on both paths, wherever it sits in the window
+    for pos in (0, 5, 31, 32, 100, 249):
+        q2 = qual.copy()
+        q2[off[20] + pos] = 32      # read 20 is longer than 250? make sure below
+        if lens_true[20] <= pos:
+            continue
+        for fs in (0, 1):
+            rc, _, _ = _pack((seq, off, q2, off), phred_encoding(), 0, 0, 400, fs)
+            assert rc != 0 and "quality cannot be lower than smallest encoded value" in _lib.last_error()
