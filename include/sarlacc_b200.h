@@ -183,6 +183,31 @@ const char* sarlacc_resident_last_kernel(const sarlacc_resident* r);
 void   sarlacc_resident_set_timing(sarlacc_resident* r, int on);
 double sarlacc_resident_forward_ms(sarlacc_resident* r);
 
+/* ---- UMI grouping ----------------------------------------------------------------
+ * Replaces SEXP umi_group(umi1, thresh1, umi2, thresh2, pregroup) (src/umi_group.cpp:14-117, registered at
+ * src/init.cpp:22) together with unlist(out, recursive=FALSE) of R/umiGroup.R:22: the bounded masked-Levenshtein
+ * neighbour search of src/sorted_trie.cpp runs as an all-pairs pass on the device, the greedy clustering of
+ * src/cluster_umis.cpp on the host.  UMIs are ASCII (the decoded form process_DNA_input yields, src/DNA_input.cpp:64-88)
+ * as one pool + n+1 offsets; umi2_pool may be NULL (one UMI).  Pre-groups are given like R's by.group list: ngroups+1
+ * offsets into 1-based read indices.  The result is a list of integer vectors (1-based read indices per cluster, in
+ * the reference's order), held by a handle:
+ *     count  = number of vectors,  values = total length;  fetch copies count+1 offsets and the values.
+ * Returns NULL with sarlacc_last_error() set on failure; the reference's messages are kept ("single-read groups
+ * should contain only the read itself", "zero length read group", "'umi1' and 'umi2' should have the same length").
+ * sarlacc_umi_neighbors returns the neighbour lists themselves (one vector per read of every pre-group, in group
+ * order) -- with a single pre-group 1..n that is fast_levdist_test(seqs, limit, TRUE) (src/sorted_trie.cpp:307-337). */
+typedef struct sarlacc_lists sarlacc_lists;
+sarlacc_lists* sarlacc_umi_group(const uint8_t* umi1_pool, const int64_t* umi1_off, int64_t n, int threshold1,
+                                 const uint8_t* umi2_pool, const int64_t* umi2_off, int threshold2,
+                                 const int64_t* group_off, const int32_t* group_members, int64_t ngroups, int device);
+sarlacc_lists* sarlacc_umi_neighbors(const uint8_t* umi1_pool, const int64_t* umi1_off, int64_t n, int threshold1,
+                                     const uint8_t* umi2_pool, const int64_t* umi2_off, int threshold2,
+                                     const int64_t* group_off, const int32_t* group_members, int64_t ngroups, int device);
+int64_t sarlacc_lists_count(const sarlacc_lists* r);
+int64_t sarlacc_lists_values(const sarlacc_lists* r);
+int     sarlacc_lists_fetch(const sarlacc_lists* r, int64_t* off, int32_t* values);
+void    sarlacc_lists_free(sarlacc_lists* r);
+
 /* ---- host packer, exposed for tests (no device involved) ------------------------------------------
  * Packs reads [0, n) the way every entry point above does before upload: rows[i*stride + r] = quality index
  * (min(qual - offset, |enc| - 1), src/reference_align.cpp:218-221) | one-hot base << 8 (src/DNA_input.cpp:64-75

@@ -92,6 +92,18 @@ def _load():
     lib.sarlacc_resident_align.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_char_p,
                                            C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.sarlacc_resident_fetch.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+    for name in ("sarlacc_umi_group", "sarlacc_umi_neighbors"):
+        getattr(lib, name).restype = C.c_void_p
+        getattr(lib, name).argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+    lib.sarlacc_lists_count.restype = C.c_int64
+    lib.sarlacc_lists_count.argtypes = [C.c_void_p]
+    lib.sarlacc_lists_values.restype = C.c_int64
+    lib.sarlacc_lists_values.argtypes = [C.c_void_p]
+    lib.sarlacc_lists_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sarlacc_lists_free.restype = None
+    lib.sarlacc_lists_free.argtypes = [C.c_void_p]
+    lib.sarlacc_pack_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     return lib
 
 

@@ -9,6 +9,7 @@ parity tests read like the reference's own tests:
     tuneAlignment          R/tuneAlignment.R:6-76          (caller of the same entry points)
     extractSubseq          R/extractSubseq.R:5-117         (caller; re-aligns and re-checks the stored scores)
     qualityAlign           R/qualityAlign.R                (general_align wrapper)
+    umiGroup, qualityMask  R/umiGroup.R:2-23, R/qualityMask.R:5-15   (neighbour search on the device)
     helpers: _setup_subseqs (:136-143), _get_front_and_back (:86-95), _resolve_strand (:112-122),
              _parallelize (:126-134), _align_and_extract (:150-176), _align_AA_internal (:178-199),
              _scramble_input (getAdaptorThresholds.R:68-92), _compute_threshold (:94-103),
@@ -600,3 +601,48 @@ def qualityAlign(sequences, reference, gapOpening=5, gapExtension=1, edit_only=F
         f["reference"] = np.array(out[2], dtype=object)
         f["query"] = np.array(out[3], dtype=object)
     return f
+
+
+# --------------------------------------------------------------------------------------------------
+# umiGroup (R/umiGroup.R) -- SURVEY 8f-4
+# --------------------------------------------------------------------------------------------------
+def qualityMask(seq, max_err=None, qual_type="phred"):
+    """R/qualityMask.R:5-15 + mask_bad_bases (src/mask_bad_bases.cpp:10-50): bases whose error probability exceeds
+    max_err become 'N'.  max_err None (R's NA) or a ReadSet without qualities: sequences unchanged.  Returns a
+    quality-less ReadSet (the R function returns a DNAStringSet / character vector)."""
+    if not isinstance(seq, ReadSet):
+        seq = ReadSet.from_strings(list(seq))
+    if max_err is None or not seq.has_quality:
+        return ReadSet(seq.seq_pool, seq.seq_off, names=seq.names)
+    names, err = _create_encoding_vector(_qual2class(qual_type))
+    if not np.array_equal(seq.seq_off, seq.qual_off):
+        raise native.SarlaccError("sequence and quality strings should have the same length")
+    offset = ord(names[0])
+    q = seq.qual_pool[:seq.qual_off[-1]].astype(np.int64) - offset
+    if (q < 0).any():
+        raise native.SarlaccError("quality cannot be lower than smallest encoded value")
+    q = np.minimum(q, len(err) - 1)                       # quality_encoding::to_error clamps like precomputed_cost
+    pool = seq.seq_pool[:seq.seq_off[-1]].copy()
+    pool[np.asarray(err)[q] > max_err] = ord("N")
+    return ReadSet(pool, seq.seq_off, names=seq.names)
+
+
+def umiGroup(UMI1, threshold1=3, UMI2=None, threshold2=None, max_err=None, groups=None, device=0):
+    """R/umiGroup.R:2-23.  groups: None, a vector of group labels (split() semantics: groups ordered by sorted label,
+    members in input order) or a list of 1-based index vectors.  Returns a list of int32 arrays (1-based indices)."""
+    if threshold2 is None:
+        threshold2 = threshold1
+    u1 = qualityMask(UMI1, max_err)
+    u2 = qualityMask(UMI2, max_err) if UMI2 is not None else None
+    n = len(u1)
+    if groups is None:
+        by_group = [np.arange(1, n + 1, dtype=np.int32)]
+    elif isinstance(groups, (list, tuple)) and (len(groups) == 0 or isinstance(groups[0], (list, tuple, np.ndarray))):
+        by_group = [np.asarray(g, np.int32) for g in groups]
+    else:
+        labels = np.asarray(groups)
+        uniq, inv = np.unique(labels, return_inverse=True)
+        order = np.argsort(inv, kind="stable")
+        bounds = np.searchsorted(inv[order], np.arange(len(uniq) + 1))
+        by_group = [(order[bounds[k]:bounds[k + 1]] + 1).astype(np.int32) for k in range(len(uniq))]
+    return native.umi_group(u1, threshold1, u2, threshold2, by_group, device=device)

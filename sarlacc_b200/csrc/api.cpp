@@ -49,6 +49,15 @@ int fail(const std::string& msg) {
 
 struct CudaError { std::string msg; };
 
+}  // namespace
+
+namespace sarlacc {   /* for the other translation units of the library (umi.cu) */
+int set_error(const std::string& msg) { return fail(msg); }
+void count_launches(int n) { g_launches += n; }
+}
+
+namespace {
+
 #define CUDA_CHECK(expr)                                                                       \
     do {                                                                                       \
         cudaError_t e_ = (expr);                                                               \

@@ -53,6 +53,10 @@ constexpr int kStepUnroll = SARLACC_WF_STEP_UNROLL;
 #define SARLACC_WF_PAIR_UNROLL 2
 #endif
 constexpr int kPairUnroll = SARLACC_WF_PAIR_UNROLL;
+#ifndef SARLACC_WF_PAIR_UNROLL_XL
+#define SARLACC_WF_PAIR_UNROLL_XL 1   /* C > 12 */
+#endif
+constexpr int kPairUnrollXL = SARLACC_WF_PAIR_UNROLL_XL;
 #ifndef SARLACC_WF_BLOCKS_SMALL
 #define SARLACC_WF_BLOCKS_SMALL 4   /* resident 128-thread blocks per SM for C <= 9 (register cap 128) */
 #endif
@@ -649,7 +653,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
         if (steps > 0) {
             const int inc = act ? 2 : 0;
             const long long finc = act ? 2 * G : 0;
-#pragma unroll (C > 12 ? 1 : kPairUnroll)
+#pragma unroll (C > 12 ? kPairUnrollXL : kPairUnroll)
             for (int s = 0; s < steps; ++s) {
                 const double SlA = __shfl_up_sync(FULL, outSA, 1, G);
                 const double ElA = __shfl_up_sync(FULL, outEA, 1, G);

@@ -1,0 +1,434 @@
+/* UMI grouping on the device: replaces umi_group (src/umi_group.cpp:14-117) -- the trie-based
+ * bounded Levenshtein search of src/sorted_trie.cpp and the greedy clustering of src/cluster_umis.cpp.
+ *
+ * What the reference computes, per pre-group of reads:
+ *   1. for every UMI s, the stored UMIs t with lev2(s, t) <= 2 * threshold, where lev2 is the edit distance with
+ *      indel = mismatch = 2 and "N against anything" = 1 (get_edit_score, src/sorted_trie.cpp:15-21), listed in the
+ *      order the trie walk meets them: sorted by (sequence under A<C<G<T<N, shorter prefix first, insertion index)
+ *      (src/sorted_trie.cpp:175-208); with two UMIs, the UMI2 list filtered by membership in the UMI1 list
+ *      (src/umi_group.cpp:63-101);
+ *   2. greedy clustering of those lists (cluster_umis, src/cluster_umis.cpp:7-112).
+ *
+ * Here step 1 is an all-pairs pass on the GPU: the reads of every pre-group are sorted once into trie order on the
+ * host, one thread takes one query UMI and walks its group's candidates in that order, running the reference's DP
+ * row by row in registers (row = one candidate base, columns = query positions) with the trie's own pruning rule
+ * as early exit (a row whose minimum exceeds the limit cannot come back, src/sorted_trie.cpp:182-201).  Two passes:
+ * count, exclusive scan on the host, fill -- so the lists come out dense, in order, without atomics.
+ * Step 2 is inherently sequential (each pick changes the counts the next pick depends on) and stays on the host,
+ * with a lazy max-heap instead of the reference's O(n) scan per cluster; ties resolve identically (largest index).
+ */
+#include "sarlacc_b200.h"
+#include "kernels.h"
+
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <queue>
+#include <string>
+#include <vector>
+
+namespace sarlacc {
+int set_error(const std::string& msg);
+void count_launches(int n);
+}
+
+namespace {
+
+constexpr int kUmiBlock = 128;
+
+struct UmiArgs {
+    const uint8_t* seq1;      /* [E][W1] candidate/query bytes, zero padded */
+    const uint8_t* seq2;      /* [E][W2] or null */
+    const uint8_t* len1;      /* [E] */
+    const uint8_t* len2;
+    const uint8_t* flags;     /* bit 0: UMI1 is in the trie (ACGTN only), bit 1: UMI2 is */
+    const int32_t* gstart;    /* [E] candidate range of the entry's pre-group, in sorted positions */
+    const int32_t* gend;
+    const int32_t* local;     /* [E] index within the pre-group (what the reference stores in its lists) */
+    int W1, W2;
+    int limit1, limit2;       /* already doubled: 2 * threshold */
+    long long E;
+    int32_t* count;           /* pass 1 out */
+    const long long* offset;  /* pass 2 in */
+    int32_t* neighbors;       /* pass 2 out */
+};
+
+/* lev2(query, cand) <= limit ?  Query bytes sit in registers (MAXQ / 4 words), the DP row too. */
+template <int MAXQ>
+__device__ __forceinline__ bool within(const uint32_t* qw, int lq, const uint8_t* cand, int lt, int limit) {
+    const int dl = lq > lt ? lq - lt : lt - lq;
+    if (2 * dl > limit) return false;
+    int row[MAXQ + 1];
+#pragma unroll
+    for (int i = 0; i <= MAXQ; ++i) row[i] = 2 * i;                       /* src/sorted_trie.cpp:220-226 */
+    for (int d = 0; d < lt; ++d) {
+        const unsigned tb = cand[d];
+        const bool tn = tb == 'N';
+        int diag = row[0];
+        row[0] = diag + 2;                                                 /* :124 */
+        int rmin = row[0];
+#pragma unroll
+        for (int i = 1; i <= MAXQ; ++i) {
+            const unsigned qb = (qw[(i - 1) >> 2] >> (8 * ((i - 1) & 3))) & 0xffu;
+            const int sc = (tn || qb == 'N') ? 1 : (qb == tb ? 0 : 2);    /* get_edit_score, :15-21 */
+            const int up = row[i];
+            const int v = min(min(up + 2, row[i - 1] + 2), diag + sc);    /* :149-153 */
+            diag = up;
+            row[i] = v;
+            rmin = min(rmin, v);
+        }
+        /* cells past the query's end only ever derive from real ones plus costs, so a row minimum above the limit
+         * is final (the trie's pruning rule, :182-201) */
+        if (rmin > limit) return false;
+    }
+    int res = 0;
+#pragma unroll
+    for (int i = 0; i <= MAXQ; ++i) res = (i == lq) ? row[i] : res;
+    return res <= limit;
+}
+
+template <int MAXQ1, int MAXQ2, bool FILL>
+__global__ void __launch_bounds__(kUmiBlock) umi_neighbors(const UmiArgs A) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= A.E) return;
+    uint32_t q1[MAXQ1 / 4], q2[MAXQ2 / 4];
+#pragma unroll
+    for (int w = 0; w < MAXQ1 / 4; ++w) q1[w] = (4 * w < A.W1) ? reinterpret_cast<const uint32_t*>(A.seq1 + e * A.W1)[w] : 0u;
+    const int l1 = A.len1[e];
+    int l2 = 0;
+    if (A.seq2) {
+#pragma unroll
+        for (int w = 0; w < MAXQ2 / 4; ++w) q2[w] = (4 * w < A.W2) ? reinterpret_cast<const uint32_t*>(A.seq2 + e * A.W2)[w] : 0u;
+        l2 = A.len2[e];
+    }
+    const int need = A.seq2 ? 3 : 1;
+    int n = 0;
+    int32_t* out = FILL ? A.neighbors + A.offset[e] : nullptr;
+    const int gs = A.gstart[e], ge = A.gend[e];
+    for (int j = gs; j < ge; ++j) {
+        if ((A.flags[j] & need) != need) continue;          /* never inserted into the trie (src/sorted_trie.cpp:56-72) */
+        /* the cheaper / more selective test first: UMI2 when present (its list drives the order, UMI1 filters) */
+        if (A.seq2 && !within<MAXQ2>(q2, l2, A.seq2 + (long long)j * A.W2, A.len2[j], A.limit2)) continue;
+        if (!within<MAXQ1>(q1, l1, A.seq1 + (long long)j * A.W1, A.len1[j], A.limit1)) continue;
+        if (FILL) out[n] = A.local[j];
+        ++n;
+    }
+    if (!FILL) A.count[e] = n;
+}
+
+template <int M1, int M2>
+void launch_pair(const UmiArgs& a, bool fill, cudaStream_t st) {
+    const int grid = (int)((a.E + kUmiBlock - 1) / kUmiBlock);
+    if (grid <= 0) return;
+    if (fill) umi_neighbors<M1, M2, true><<<grid, kUmiBlock, 0, st>>>(a);
+    else umi_neighbors<M1, M2, false><<<grid, kUmiBlock, 0, st>>>(a);
+}
+
+template <int M1>
+bool launch_m2(const UmiArgs& a, bool fill, cudaStream_t st) {
+    if (!a.seq2) { launch_pair<M1, 4>(a, fill, st); return true; }
+    if (a.W2 <= 16) { launch_pair<M1, 16>(a, fill, st); return true; }
+    if (a.W2 <= 32) { launch_pair<M1, 32>(a, fill, st); return true; }
+    if (a.W2 <= 64) { launch_pair<M1, 64>(a, fill, st); return true; }
+    return false;
+}
+
+bool launch_umi(const UmiArgs& a, bool fill, cudaStream_t st) {
+    if (a.W1 <= 16) return launch_m2<16>(a, fill, st);
+    if (a.W1 <= 32) return launch_m2<32>(a, fill, st);
+    if (a.W1 <= 64) return launch_m2<64>(a, fill, st);
+    return false;
+}
+
+struct Lists {   /* a list of integer vectors, flattened */
+    std::vector<int64_t> off{0};
+    std::vector<int32_t> values;
+    void push(const std::vector<int32_t>& v) {
+        values.insert(values.end(), v.begin(), v.end());
+        off.push_back((int64_t)values.size());
+    }
+};
+
+inline int trie_rank(uint8_t c) {   /* children order of the trie: src/sorted_trie.cpp:10,56-72 */
+    switch (c) {
+        case 'A': return 0;
+        case 'C': return 1;
+        case 'G': return 2;
+        case 'T': return 3;
+        case 'N': return 4;
+        default: return 5;
+    }
+}
+
+struct Seqs {
+    const uint8_t* pool;
+    const int64_t* off;
+    const uint8_t* ptr(int64_t i) const { return pool + off[i]; }
+    int64_t len(int64_t i) const { return off[i + 1] - off[i]; }
+    bool storable(int64_t i) const {
+        for (int64_t k = off[i]; k < off[i + 1]; ++k) if (trie_rank(pool[k]) == 5) return false;
+        return true;
+    }
+    /* order of sorted_trie's walk: (sequence under ACGTN, prefix first) */
+    bool less(int64_t a, int64_t b) const {
+        const int64_t la = len(a), lb = len(b), m = std::min(la, lb);
+        const uint8_t* pa = ptr(a);
+        const uint8_t* pb = ptr(b);
+        for (int64_t k = 0; k < m; ++k) {
+            const int ra = trie_rank(pa[k]), rb = trie_rank(pb[k]);
+            if (ra != rb) return ra < rb;
+        }
+        return la < lb;
+    }
+};
+
+/* cluster_umis (src/cluster_umis.cpp:7-112) over CSR lists of group-local indices.  Returns false with `msg` set on
+ * the reference's two error conditions. */
+bool cluster_lists(const long long* off, const int32_t* nb, int n, std::vector<std::vector<int32_t> >& out, const char** msg) {
+    std::vector<int64_t> remaining((size_t)n);
+    std::vector<char> in_play((size_t)n, 0);
+    typedef std::pair<int64_t, int32_t> Key;   /* (remaining, index): the reference's max_element order, :58-66 */
+    std::priority_queue<Key> heap;
+    for (int a = 0; a < n; ++a) {
+        const int64_t cur = off[a + 1] - off[a];
+        remaining[a] = cur;
+        if (cur > 1) {
+            in_play[a] = 1;
+            heap.push(Key(cur, a));
+        } else if (cur == 1) {                                            /* :24-38 */
+            if (nb[off[a]] != a) { *msg = "single-read groups should contain only the read itself"; return false; }
+            out.push_back(std::vector<int32_t>(1, a));
+        } else {
+            *msg = "zero length read group";                              /* :39-41 */
+            return false;
+        }
+    }
+    while (!heap.empty()) {
+        const Key top = heap.top();
+        heap.pop();
+        const int32_t v = top.second;
+        if (!in_play[v] || remaining[v] != top.first) continue;           /* stale entry */
+        if (top.first == 0) continue;                                     /* wiped-out node, :47-56 */
+        in_play[v] = 0;                                                   /* pop_back of :70-71 */
+        std::vector<int32_t> cluster;
+        for (long long k = off[v]; k < off[v + 1]; ++k) {                 /* :74-97 */
+            const int32_t w = nb[k];
+            if (remaining[w] == 0) continue;
+            cluster.push_back(w);
+            remaining[w] = 0;
+            for (long long k2 = off[w]; k2 < off[w + 1]; ++k2) {
+                const int32_t x = nb[k2];
+                if (remaining[x] > 0) {
+                    --remaining[x];
+                    if (in_play[x]) heap.push(Key(remaining[x], x));
+                }
+            }
+        }
+        out.push_back(std::move(cluster));
+    }
+    return true;
+}
+
+struct DevMem {
+    void* p = nullptr;
+    ~DevMem() { if (p) cudaFree(p); }
+    bool alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1) == cudaSuccess; }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct sarlacc_lists {
+    Lists L;
+};
+
+extern "C" {
+
+int64_t sarlacc_lists_count(const sarlacc_lists* r) { return r ? (int64_t)r->L.off.size() - 1 : 0; }
+int64_t sarlacc_lists_values(const sarlacc_lists* r) { return r ? (int64_t)r->L.values.size() : 0; }
+int sarlacc_lists_fetch(const sarlacc_lists* r, int64_t* off, int32_t* values) {
+    if (!r) return sarlacc::set_error("list handle is NULL");
+    std::memcpy(off, r->L.off.data(), sizeof(int64_t) * r->L.off.size());
+    if (!r->L.values.empty()) std::memcpy(values, r->L.values.data(), sizeof(int32_t) * r->L.values.size());
+    return 0;
+}
+void sarlacc_lists_free(sarlacc_lists* r) { delete r; }
+
+/* mode 0: umi_group; mode 1: neighbour lists only (fast_levdist_test(sorted=TRUE) when there is one group) */
+static sarlacc_lists* umi_run(int mode, const uint8_t* pool1, const int64_t* off1, int64_t n, int threshold1,
+        const uint8_t* pool2, const int64_t* off2, int threshold2,
+        const int64_t* group_off, const int32_t* members, int64_t ngroups, int device)
+{
+    if (!pool1 || !off1 || (ngroups > 0 && (!group_off || !members))) { sarlacc::set_error("UMI buffers must not be NULL"); return nullptr; }
+    const bool two = pool2 != nullptr;
+    if (two && !off2) { sarlacc::set_error("'umi1' and 'umi2' should have the same length"); return nullptr; }
+    Seqs S1{pool1, off1}, S2{pool2, off2};
+    /* entries = members of pre-groups with more than one read (src/umi_group.cpp:37-40), sorted per group */
+    std::vector<int64_t> ent;            /* 0-based read index */
+    std::vector<int32_t> local, gstart, gend;
+    int64_t maxl1 = 0, maxl2 = 0;
+    for (int64_t g = 0; g < ngroups; ++g) {
+        const int64_t a = group_off[g], b = group_off[g + 1];
+        for (int64_t k = a; k < b; ++k) {
+            if (members[k] < 1 || members[k] > n) { sarlacc::set_error("pre-group index out of range"); return nullptr; }
+        }
+        if (b - a == 0 || (mode == 0 && b - a < 2)) continue;
+        const size_t base = ent.size();
+        std::vector<int32_t> ord((size_t)(b - a));
+        for (size_t k = 0; k < ord.size(); ++k) ord[k] = (int32_t)k;
+        const Seqs& So = two ? S2 : S1;   /* with two UMIs the UMI2 trie drives the order (:86-100) */
+        std::sort(ord.begin(), ord.end(), [&](int32_t x, int32_t y) {
+            const int64_t rx = members[a + x] - 1, ry = members[a + y] - 1;
+            if (So.less(rx, ry)) return true;
+            if (So.less(ry, rx)) return false;
+            return x < y;
+        });
+        for (size_t k = 0; k < ord.size(); ++k) {
+            const int64_t r = members[a + ord[k]] - 1;
+            ent.push_back(r);
+            local.push_back(ord[k]);
+            gstart.push_back((int32_t)base);
+            gend.push_back((int32_t)(base + ord.size()));
+            maxl1 = std::max(maxl1, S1.len(r));
+            if (two) maxl2 = std::max(maxl2, S2.len(r));
+        }
+    }
+    const long long E = (long long)ent.size();
+    std::vector<long long> offs((size_t)E + 1, 0);
+    std::vector<int32_t> nbrs;
+    if (E > 0) {
+        if (E > 0x7fffffffLL) { sarlacc::set_error("too many reads in multi-read pre-groups for one device pass"); return nullptr; }
+        if (maxl1 > 64 || maxl2 > 64) { sarlacc::set_error("UMIs longer than 64 bases are outside the device kernel's envelope"); return nullptr; }
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { sarlacc::set_error("no CUDA device available (this library has no CPU fallback)"); return nullptr; }
+        if (device < 0 || device >= ndev) { sarlacc::set_error("device index out of range"); return nullptr; }
+        cudaSetDevice(device);
+        const int W1 = std::max<int>(4, (int)((maxl1 + 3) & ~3LL)), W2 = two ? std::max<int>(4, (int)((maxl2 + 3) & ~3LL)) : 0;
+        std::vector<uint8_t> h1((size_t)E * W1, 0), h2((size_t)E * std::max(W2, 1), 0), hl1((size_t)E), hl2((size_t)E, 0), hf((size_t)E);
+        for (long long e = 0; e < E; ++e) {
+            const int64_t r = ent[(size_t)e];
+            std::memcpy(&h1[(size_t)e * W1], S1.ptr(r), (size_t)S1.len(r));
+            hl1[(size_t)e] = (uint8_t)S1.len(r);
+            uint8_t f = S1.storable(r) ? 1 : 0;
+            if (two) {
+                std::memcpy(&h2[(size_t)e * W2], S2.ptr(r), (size_t)S2.len(r));
+                hl2[(size_t)e] = (uint8_t)S2.len(r);
+                if (S2.storable(r)) f |= 2;
+            }
+            hf[(size_t)e] = f;
+        }
+        DevMem d1, d2, dl1, dl2, df, dgs, dge, dloc, dcnt, doff, dnb;
+        bool ok = d1.alloc(h1.size()) && d2.alloc(h2.size()) && dl1.alloc(E) && dl2.alloc(E) && df.alloc(E) &&
+                  dgs.alloc(sizeof(int32_t) * E) && dge.alloc(sizeof(int32_t) * E) && dloc.alloc(sizeof(int32_t) * E) &&
+                  dcnt.alloc(sizeof(int32_t) * E) && doff.alloc(sizeof(long long) * (E + 1));
+        if (!ok) { sarlacc::set_error("CUDA error: out of device memory in the UMI pass"); return nullptr; }
+        cudaStream_t st = nullptr;
+        cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        auto up = [&](DevMem& d, const void* h, size_t bytes) { cudaMemcpyAsync(d.p, h, bytes, cudaMemcpyHostToDevice, st); };
+        up(d1, h1.data(), h1.size());
+        if (two) up(d2, h2.data(), h2.size());
+        up(dl1, hl1.data(), (size_t)E);
+        up(dl2, hl2.data(), (size_t)E);
+        up(df, hf.data(), (size_t)E);
+        up(dgs, gstart.data(), sizeof(int32_t) * E);
+        up(dge, gend.data(), sizeof(int32_t) * E);
+        up(dloc, local.data(), sizeof(int32_t) * E);
+        UmiArgs A;
+        std::memset(&A, 0, sizeof(A));
+        A.seq1 = d1.as<uint8_t>();
+        A.seq2 = two ? d2.as<uint8_t>() : nullptr;
+        A.len1 = dl1.as<uint8_t>();
+        A.len2 = dl2.as<uint8_t>();
+        A.flags = df.as<uint8_t>();
+        A.gstart = dgs.as<int32_t>();
+        A.gend = dge.as<int32_t>();
+        A.local = dloc.as<int32_t>();
+        A.W1 = W1;
+        A.W2 = W2;
+        A.limit1 = 2 * threshold1;       /* limit *= MULT, src/sorted_trie.cpp:227 */
+        A.limit2 = 2 * threshold2;
+        A.E = E;
+        A.count = dcnt.as<int32_t>();
+        bool launched = launch_umi(A, false, st);
+        std::vector<int32_t> cnt((size_t)E);
+        cudaMemcpyAsync(cnt.data(), dcnt.p, sizeof(int32_t) * E, cudaMemcpyDeviceToHost, st);
+        cudaError_t ce = cudaStreamSynchronize(st);
+        if (launched && ce == cudaSuccess) {
+            for (long long e = 0; e < E; ++e) offs[(size_t)e + 1] = offs[(size_t)e] + cnt[(size_t)e];
+            nbrs.resize((size_t)offs[(size_t)E]);
+            if (!dnb.alloc(sizeof(int32_t) * nbrs.size())) { cudaStreamDestroy(st); sarlacc::set_error("CUDA error: out of device memory for the UMI neighbour lists"); return nullptr; }
+            up(doff, offs.data(), sizeof(long long) * (E + 1));
+            A.offset = doff.as<long long>();
+            A.neighbors = dnb.as<int32_t>();
+            launch_umi(A, true, st);
+            if (!nbrs.empty()) cudaMemcpyAsync(nbrs.data(), dnb.p, sizeof(int32_t) * nbrs.size(), cudaMemcpyDeviceToHost, st);
+            ce = cudaStreamSynchronize(st);
+            sarlacc::count_launches(2);
+        }
+        cudaStreamDestroy(st);
+        if (!launched) { sarlacc::set_error("no UMI kernel for this width"); return nullptr; }
+        if (ce != cudaSuccess || (ce = cudaGetLastError()) != cudaSuccess) {
+            sarlacc::set_error(std::string("CUDA error: ") + cudaGetErrorString(ce) + " in the UMI neighbour pass");
+            return nullptr;
+        }
+    }
+
+    /* back to pre-group order: lists indexed by the read's position in its group */
+    std::unique_ptr<sarlacc_lists> res(new sarlacc_lists());
+    long long e0 = 0;
+    for (int64_t g = 0; g < ngroups; ++g) {
+        const int64_t a = group_off[g], b = group_off[g + 1];
+        const int cur = (int)(b - a);
+        if (cur == 0) continue;                     /* an empty pre-group yields an empty list: nothing after unlist() */
+        if (cur == 1 && mode == 0) {                /* src/umi_group.cpp:37-40 */
+            res->L.push(std::vector<int32_t>(1, members[a]));
+            continue;
+        }
+        /* CSR by local index */
+        std::vector<long long> loff((size_t)cur + 1, 0);
+        std::vector<long long> where((size_t)cur);
+        for (int k = 0; k < cur; ++k) {
+            const long long e = e0 + k;
+            where[(size_t)local[(size_t)e]] = e;
+        }
+        for (int s = 0; s < cur; ++s) loff[(size_t)s + 1] = loff[(size_t)s] + (offs[(size_t)where[(size_t)s] + 1] - offs[(size_t)where[(size_t)s]]);
+        std::vector<int32_t> lnb((size_t)loff[(size_t)cur]);
+        for (int s = 0; s < cur; ++s) {
+            const long long e = where[(size_t)s];
+            std::copy(nbrs.begin() + offs[(size_t)e], nbrs.begin() + offs[(size_t)e + 1], lnb.begin() + loff[(size_t)s]);
+        }
+        if (mode == 1) {
+            for (int s = 0; s < cur; ++s) {
+                std::vector<int32_t> v(lnb.begin() + loff[(size_t)s], lnb.begin() + loff[(size_t)s + 1]);
+                for (auto& x : v) x = members[a + x];
+                res->L.push(v);
+            }
+        } else {
+            std::vector<std::vector<int32_t> > clusters;
+            const char* msg = nullptr;
+            if (!cluster_lists(loff.data(), lnb.data(), cur, clusters, &msg)) { sarlacc::set_error(msg); return nullptr; }
+            for (auto& c : clusters) {
+                for (auto& x : c) x = members[a + x];                     /* src/umi_group.cpp:105-109 */
+                res->L.push(c);
+            }
+        }
+        e0 += cur;
+    }
+    return res.release();
+}
+
+sarlacc_lists* sarlacc_umi_group(const uint8_t* umi1_pool, const int64_t* umi1_off, int64_t n, int threshold1,
+        const uint8_t* umi2_pool, const int64_t* umi2_off, int threshold2,
+        const int64_t* group_off, const int32_t* group_members, int64_t ngroups, int device)
+{
+    return umi_run(0, umi1_pool, umi1_off, n, threshold1, umi2_pool, umi2_off, threshold2, group_off, group_members, ngroups, device);
+}
+
+sarlacc_lists* sarlacc_umi_neighbors(const uint8_t* umi1_pool, const int64_t* umi1_off, int64_t n, int threshold1,
+        const uint8_t* umi2_pool, const int64_t* umi2_off, int threshold2,
+        const int64_t* group_off, const int32_t* group_members, int64_t ngroups, int device)
+{
+    return umi_run(1, umi1_pool, umi1_off, n, threshold1, umi2_pool, umi2_off, threshold2, group_off, group_members, ngroups, device);
+}
+
+}

@@ -241,6 +241,60 @@ def adaptor_align_reads(reads, tolerance, encoding, gapopen, gapext, adaptor1, a
     return width[:n], rev[:n].view(np.bool_), res[0], res[1]
 
 
+def _string_pool(strings):
+    if isinstance(strings, ReadSet):
+        return np.ascontiguousarray(strings.seq_pool, np.uint8), np.ascontiguousarray(strings.seq_off, np.int64)
+    if isinstance(strings, tuple):
+        return np.ascontiguousarray(strings[0], np.uint8), np.ascontiguousarray(strings[1], np.int64)
+    rs = ReadSet.from_strings(list(strings))
+    return np.ascontiguousarray(rs.seq_pool, np.uint8), np.ascontiguousarray(rs.seq_off, np.int64)
+
+
+def _umi_call(fn, umi1, threshold1, umi2, threshold2, groups, device):
+    p1, o1 = _string_pool(umi1)
+    n = len(o1) - 1
+    if p1.size == 0:
+        p1 = np.zeros(1, np.uint8)
+    p2 = o2 = None
+    if umi2 is not None:
+        p2, o2 = _string_pool(umi2)
+        if len(o2) - 1 != n:
+            raise SarlaccError("'umi1' and 'umi2' should have the same length")     # src/umi_group.cpp:27-29
+        if p2.size == 0:
+            p2 = np.zeros(1, np.uint8)
+    if groups is None:
+        groups = [np.arange(1, n + 1, dtype=np.int32)]
+    goff = np.zeros(len(groups) + 1, np.int64)
+    if len(groups):
+        goff[1:] = np.cumsum([len(g) for g in groups])
+    gmem = np.ascontiguousarray(np.concatenate([np.asarray(g, np.int32).reshape(-1) for g in groups] + [np.zeros(1, np.int32)]))
+    h = fn(_lib._ptr(p1), _lib._ptr(o1), C.c_int64(n), C.c_int(int(threshold1)), _lib._ptr(p2), _lib._ptr(o2), C.c_int(int(threshold2)),
+           _lib._ptr(goff), _lib._ptr(gmem), C.c_int64(len(groups)), C.c_int(int(device)))
+    if not h:
+        raise SarlaccError(_lib.last_error())
+    try:
+        nl, nv = _lib.lib.sarlacc_lists_count(h), _lib.lib.sarlacc_lists_values(h)
+        off = np.zeros(nl + 1, np.int64)
+        vals = np.zeros(max(nv, 1), np.int32)
+        _lib.check(_lib.lib.sarlacc_lists_fetch(h, _lib._ptr(off), _lib._ptr(vals)))
+    finally:
+        _lib.lib.sarlacc_lists_free(h)
+    return [vals[off[i]:off[i + 1]] for i in range(nl)]
+
+
+def umi_group(umi1, threshold1, umi2=None, threshold2=None, groups=None, device=0):
+    """.Call(cxx_umi_group, UMI1, threshold1, UMI2, threshold2, by.group) + unlist(recursive=FALSE)
+    (src/umi_group.cpp:14-117, R/umiGroup.R:21-22): list of int32 arrays of 1-based read indices, one per cluster.
+    groups: list of 1-based index vectors (R's by.group); default one group of all reads."""
+    return _umi_call(_lib.lib.sarlacc_umi_group, umi1, threshold1, umi2, threshold1 if threshold2 is None else threshold2, groups, device)
+
+
+def umi_neighbors(umi1, threshold1, umi2=None, threshold2=None, groups=None, device=0):
+    """The neighbour lists umi_group clusters (1-based, trie order); with the default single group this is
+    .Call(cxx_fast_levdist_test, seqs, limit, TRUE) (src/sorted_trie.cpp:307-337)."""
+    return _umi_call(_lib.lib.sarlacc_umi_neighbors, umi1, threshold1, umi2, threshold1 if threshold2 is None else threshold2, groups, device)
+
+
 class Resident:
     """Read windows packed once and kept in HBM (sarlacc_resident_*)."""
 
