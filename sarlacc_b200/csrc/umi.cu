@@ -21,6 +21,9 @@
 #include "kernels.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <queue>
@@ -49,6 +52,7 @@ struct UmiArgs {
     int limit1, limit2;       /* already doubled: 2 * threshold */
     long long E;
     int32_t* count;           /* pass 1 out */
+    int32_t* first;           /* pass 1 out: [E][kUmiCap] the first matches of every read */
     const long long* offset;  /* pass 2 in */
     int32_t* neighbors;       /* pass 2 out */
 };
@@ -87,6 +91,68 @@ __device__ __forceinline__ bool within(const uint32_t* qw, int lq, const uint8_t
     return res <= limit;
 }
 
+/* The same decision inside the Ukkonen band |i - d| <= K, K = threshold: a cell further from the diagonal has paid more
+ * than K indels of cost 2 and is already over the limit, so leaving it at "infinity" changes no answer.  The band of
+ * the previous row sits in 2K+1 registers; the query, shifted by one base per candidate base, in MAXQ/4 + 2 words, so
+ * that every index is a compile-time constant. */
+template <int MAXQ, int K>
+__device__ __forceinline__ bool within_band(const uint32_t* qw, int lq, const uint8_t* cand, int lt, int limit) {
+    const int dl = lq > lt ? lq - lt : lt - lq;
+    if (2 * dl > limit) return false;
+    constexpr int INF = 1 << 20;
+    constexpr int NQ = MAXQ / 4;
+    constexpr int NW = NQ + 2;
+    /* s = K zero bytes, the query, zeros: byte m of s is the query base of band slot m in the row being computed */
+    uint32_t sreg[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        const uint32_t lo = (w - K / 4 - 1 >= 0 && w - K / 4 - 1 < NQ) ? qw[w - K / 4 - 1] : 0u;
+        const uint32_t hi = (w - K / 4 >= 0 && w - K / 4 < NQ) ? qw[w - K / 4] : 0u;
+        sreg[w] = (K % 4 == 0) ? hi : __funnelshift_l(lo, hi, 8 * (K % 4));
+    }
+    int band[2 * K + 1];
+#pragma unroll
+    for (int m = 0; m <= 2 * K; ++m) band[m] = (m >= K) ? 2 * (m - K) : INF;     /* row 0: cell (0, i) = 2i */
+    for (int d = 0; d < lt; ++d) {
+        const unsigned tb = cand[d];
+        const bool tn = tb == 'N';
+        int left = INF, rmin = INF;
+#pragma unroll
+        for (int m = 0; m <= 2 * K; ++m) {
+            const unsigned qb = (sreg[m >> 2] >> (8 * (m & 3))) & 0xffu;
+            const int sc = (tn || qb == 'N') ? 1 : (qb == tb ? 0 : 2);
+            const int diag = band[m];
+            const int up = (m < 2 * K) ? band[m + 1] : INF;
+            const int v = min(min(up + 2, left + 2), diag + sc);
+            band[m] = v;
+            left = v;
+            rmin = min(rmin, v);
+        }
+        if (rmin > limit) return false;
+#pragma unroll
+        for (int w = 0; w < NW - 1; ++w) sreg[w] = __funnelshift_r(sreg[w], sreg[w + 1], 8);
+        sreg[NW - 1] >>= 8;
+    }
+    int res = INF;
+#pragma unroll
+    for (int m = 0; m <= 2 * K; ++m) res = (m - K == lq - lt) ? band[m] : res;
+    return res <= limit;
+}
+
+template <int MAXQ>
+__device__ __forceinline__ bool within_any(const uint32_t* qw, int lq, const uint8_t* cand, int lt, int limit) {
+    switch (limit >> 1) {     /* limit = 2 * threshold */
+        case 0: return within_band<MAXQ, 0>(qw, lq, cand, lt, limit);
+        case 1: return within_band<MAXQ, 1>(qw, lq, cand, lt, limit);
+        case 2: return within_band<MAXQ, 2>(qw, lq, cand, lt, limit);
+        case 3: return within_band<MAXQ, 3>(qw, lq, cand, lt, limit);
+        case 4: return within_band<MAXQ, 4>(qw, lq, cand, lt, limit);
+        default: return within<MAXQ>(qw, lq, cand, lt, limit);
+    }
+}
+
+constexpr int kUmiCap = 16;   /* matches kept by the counting pass; only reads with more are walked a second time */
+
 template <int MAXQ1, int MAXQ2, bool FILL>
 __global__ void __launch_bounds__(kUmiBlock) umi_neighbors(const UmiArgs A) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -103,14 +169,21 @@ __global__ void __launch_bounds__(kUmiBlock) umi_neighbors(const UmiArgs A) {
     }
     const int need = A.seq2 ? 3 : 1;
     int n = 0;
-    int32_t* out = FILL ? A.neighbors + A.offset[e] : nullptr;
+    int32_t* out = FILL ? A.neighbors + A.offset[e] : A.first + e * kUmiCap;
+    if (FILL) {
+        const int have = A.count[e];
+        if (have <= kUmiCap) {       /* the counting pass already holds this read's whole list */
+            for (int k = 0; k < have; ++k) out[k] = A.first[e * kUmiCap + k];
+            return;
+        }
+    }
     const int gs = A.gstart[e], ge = A.gend[e];
     for (int j = gs; j < ge; ++j) {
         if ((A.flags[j] & need) != need) continue;          /* never inserted into the trie (src/sorted_trie.cpp:56-72) */
-        /* the cheaper / more selective test first: UMI2 when present (its list drives the order, UMI1 filters) */
-        if (A.seq2 && !within<MAXQ2>(q2, l2, A.seq2 + (long long)j * A.W2, A.len2[j], A.limit2)) continue;
-        if (!within<MAXQ1>(q1, l1, A.seq1 + (long long)j * A.W1, A.len1[j], A.limit1)) continue;
-        if (FILL) out[n] = A.local[j];
+        /* UMI2 first when present (its list drives the order, UMI1 filters) */
+        if (A.seq2 && !within_any<MAXQ2>(q2, l2, A.seq2 + (long long)j * A.W2, A.len2[j], A.limit2)) continue;
+        if (!within_any<MAXQ1>(q1, l1, A.seq1 + (long long)j * A.W1, A.len1[j], A.limit1)) continue;
+        if (FILL || n < kUmiCap) out[n] = A.local[j];
         ++n;
     }
     if (!FILL) A.count[e] = n;
@@ -263,6 +336,10 @@ static sarlacc_lists* umi_run(int mode, const uint8_t* pool1, const int64_t* off
     const bool two = pool2 != nullptr;
     if (two && !off2) { sarlacc::set_error("'umi1' and 'umi2' should have the same length"); return nullptr; }
     Seqs S1{pool1, off1}, S2{pool2, off2};
+    const bool dbg = std::getenv("SARLACC_DEBUG_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    double t_sorted = t_begin, t_device = t_begin;
     /* entries = members of pre-groups with more than one read (src/umi_group.cpp:37-40), sorted per group */
     std::vector<int64_t> ent;            /* 0-based read index */
     std::vector<int32_t> local, gstart, gend;
@@ -275,14 +352,31 @@ static sarlacc_lists* umi_run(int mode, const uint8_t* pool1, const int64_t* off
         if (b - a == 0 || (mode == 0 && b - a < 2)) continue;
         const size_t base = ent.size();
         std::vector<int32_t> ord((size_t)(b - a));
-        for (size_t k = 0; k < ord.size(); ++k) ord[k] = (int32_t)k;
         const Seqs& So = two ? S2 : S1;   /* with two UMIs the UMI2 trie drives the order (:86-100) */
-        std::sort(ord.begin(), ord.end(), [&](int32_t x, int32_t y) {
-            const int64_t rx = members[a + x] - 1, ry = members[a + y] - 1;
-            if (So.less(rx, ry)) return true;
-            if (So.less(ry, rx)) return false;
-            return x < y;
-        });
+        bool short_keys = true;
+        for (int64_t k = a; k < b && short_keys; ++k) short_keys = So.len(members[k] - 1) <= 21;
+        if (short_keys) {
+            /* up to 21 bases: the walk order is the order of 3-bit digits (rank + 1, 0 = end) packed into one word */
+            std::vector<std::pair<uint64_t, int32_t> > keyed((size_t)(b - a));
+            for (int64_t k = a; k < b; ++k) {
+                const int64_t r = members[k] - 1;
+                const uint8_t* p = So.ptr(r);
+                const int64_t len = So.len(r);
+                uint64_t key = 0;
+                for (int64_t x = 0; x < 21; ++x) key = (key << 3) | (x < len ? (uint64_t)(trie_rank(p[x]) + 1) : 0u);
+                keyed[(size_t)(k - a)] = std::make_pair(key, (int32_t)(k - a));
+            }
+            std::sort(keyed.begin(), keyed.end());
+            for (size_t k = 0; k < ord.size(); ++k) ord[k] = keyed[k].second;
+        } else {
+            for (size_t k = 0; k < ord.size(); ++k) ord[k] = (int32_t)k;
+            std::sort(ord.begin(), ord.end(), [&](int32_t x, int32_t y) {
+                const int64_t rx = members[a + x] - 1, ry = members[a + y] - 1;
+                if (So.less(rx, ry)) return true;
+                if (So.less(ry, rx)) return false;
+                return x < y;
+            });
+        }
         for (size_t k = 0; k < ord.size(); ++k) {
             const int64_t r = members[a + ord[k]] - 1;
             ent.push_back(r);
@@ -294,6 +388,7 @@ static sarlacc_lists* umi_run(int mode, const uint8_t* pool1, const int64_t* off
         }
     }
     const long long E = (long long)ent.size();
+    t_sorted = now();
     std::vector<long long> offs((size_t)E + 1, 0);
     std::vector<int32_t> nbrs;
     if (E > 0) {
@@ -317,10 +412,11 @@ static sarlacc_lists* umi_run(int mode, const uint8_t* pool1, const int64_t* off
             }
             hf[(size_t)e] = f;
         }
-        DevMem d1, d2, dl1, dl2, df, dgs, dge, dloc, dcnt, doff, dnb;
+        DevMem d1, d2, dl1, dl2, df, dgs, dge, dloc, dcnt, doff, dnb, dfirst;
         bool ok = d1.alloc(h1.size()) && d2.alloc(h2.size()) && dl1.alloc(E) && dl2.alloc(E) && df.alloc(E) &&
                   dgs.alloc(sizeof(int32_t) * E) && dge.alloc(sizeof(int32_t) * E) && dloc.alloc(sizeof(int32_t) * E) &&
-                  dcnt.alloc(sizeof(int32_t) * E) && doff.alloc(sizeof(long long) * (E + 1));
+                  dcnt.alloc(sizeof(int32_t) * E) && doff.alloc(sizeof(long long) * (E + 1)) &&
+                  dfirst.alloc(sizeof(int32_t) * (size_t)E * kUmiCap);
         if (!ok) { sarlacc::set_error("CUDA error: out of device memory in the UMI pass"); return nullptr; }
         cudaStream_t st = nullptr;
         cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
@@ -349,6 +445,7 @@ static sarlacc_lists* umi_run(int mode, const uint8_t* pool1, const int64_t* off
         A.limit2 = 2 * threshold2;
         A.E = E;
         A.count = dcnt.as<int32_t>();
+        A.first = dfirst.as<int32_t>();
         bool launched = launch_umi(A, false, st);
         std::vector<int32_t> cnt((size_t)E);
         cudaMemcpyAsync(cnt.data(), dcnt.p, sizeof(int32_t) * E, cudaMemcpyDeviceToHost, st);
@@ -373,6 +470,7 @@ static sarlacc_lists* umi_run(int mode, const uint8_t* pool1, const int64_t* off
         }
     }
 
+    t_device = now();
     /* back to pre-group order: lists indexed by the read's position in its group */
     std::unique_ptr<sarlacc_lists> res(new sarlacc_lists());
     long long e0 = 0;
@@ -414,6 +512,8 @@ static sarlacc_lists* umi_run(int mode, const uint8_t* pool1, const int64_t* off
         }
         e0 += cur;
     }
+    if (dbg) std::fprintf(stderr, "[sarlacc] umi: sort %.1f ms, pack + device passes %.1f ms, lists + clustering %.1f ms (%lld reads in multi-read groups, %zu neighbours)\n",
+                          (t_sorted - t_begin) * 1e3, (t_device - t_sorted) * 1e3, (now() - t_device) * 1e3, E, nbrs.size());
     return res.release();
 }
 
