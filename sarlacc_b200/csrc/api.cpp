@@ -708,9 +708,13 @@ long long sub_chunk(const Plan& P, int maxlen, bool trace, long long n) {
 
 const char* g_last_kernel = "";
 
-int pair_rows_default() {   /* SARLACC_PAIR=0 selects the single-row kernel (A/B tests) */
+/* Two rows per lane step (wf_forward2) pay off on long windows; on barcode-length reads (a couple of dozen rows per
+ * alignment, lanes of a warp at different phases of different alignments) nearly every step is the masked one and the
+ * single-row kernel is ~2x faster (1 M x 96 barcodes: 0.11 s vs 0.20 s).  SARLACC_PAIR=0/1 forces either (A/B tests). */
+int pair_rows_default(int maxlen = 1 << 30) {
     const char* e = std::getenv("SARLACC_PAIR");
-    return e ? std::atoi(e) : 1;
+    if (e) return std::atoi(e);
+    return maxlen >= 48 ? 1 : 0;
 }
 
 /* Alignment groups in one full grid of the plan's forward kernel (0 for the literal kernel). */
@@ -817,7 +821,7 @@ const char* run_device(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t
         A.kinds = P.kinds;
         A.G = P.G;
         A.C = P.C;
-        A.pair_rows = pair_rows_default();
+        A.pair_rows = pair_rows_default(maxlen);
         /* [nref][n] outputs of a sub-chunk cannot be expressed with one base pointer unless n == m or nref == 1 */
         A.score = out.score ? out.score + off : nullptr;
         A.best_id = out.best_id ? out.best_id + off : nullptr;

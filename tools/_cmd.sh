@@ -1,4 +1,7 @@
 exec > gpurun_out/run.log 2>&1
-python -m pytest tests/test_gpu_umi.py -x -q 2>&1 | tail -15
-SARLACC_DEBUG_TIMING=1 python tools/bench_umi.py 400000 2000 2>&1 | tail -12
-SARLACC_DEBUG_TIMING=1 python tools/bench_umi.py 100000 100000 2>&1 | grep -v reference | tail -6
+echo default; python tools/bench_extra.py 2>&1 | head -2
+echo again; python tools/bench_extra.py 2>&1 | head -1
+echo CHUNK131072; SARLACC_CHUNK=131072 python tools/bench_extra.py 2>&1 | head -1
+echo NOAVX; SARLACC_NO_AVX2=1 python tools/bench_extra.py 2>&1 | head -1
+echo PAIR0; SARLACC_PAIR=0 python tools/bench_extra.py 2>&1 | head -1
+echo THREADS8; SARLACC_HOST_THREADS=8 python tools/bench_extra.py 2>&1 | head -1

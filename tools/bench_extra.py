@@ -13,6 +13,9 @@ from sarlacc_b200 import api, native, synth  # noqa: E402
 A1 = "ACGCAGATCGATCGATNNNNNNNNNNNNCGCGCGAGCTGACTNNNNGCACGACTCTGGTTTTTTTTTTTT"
 A2 = "AAGGCCTTTTCCGACTCATGAA"
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
+if os.environ.get("SARLACC_HOST_THREADS"):
+    from sarlacc_b200 import _lib
+    _lib.lib.sarlacc_set_host_threads(int(os.environ["SARLACC_HOST_THREADS"]))
 enc = native.phred_encoding()
 
 # ---- configs[3]: barcodeAlign --------------------------------------------------------------------------------
