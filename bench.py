@@ -329,7 +329,7 @@ def main():
         peak_gcups_at_clock = sms * FP64_LANES_PER_SM * cur_mhz * 1e6 / FP64_OPS_PER_CELL / 1e9
         achieved = cells_a1 / (fwd / 1000.0) / 1e9 if fwd > 0 else None
         # HBM side of the same kernel: rows read once (2 B/base) + 4-bit records written (8-byte word per lane-row)
-        alg_bytes = rf.nbytes() + n * (TOL + 8) * 8 * 8 + n * 8
+        alg_bytes = rf.nbytes() + n * (TOL + 8) * 4 * 16 + n * 12   # rows read once; 4 lanes x 16-byte trace word per row slot; score + endrow
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         line = {
             "metric": "adaptorAlign reads/s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
@@ -348,9 +348,9 @@ def main():
                 "frac_at_measured_clock": (achieved / peak_gcups_at_clock) if achieved else None,
                 "how": "cells = n*250*70 per launch / CUDA-event duration of the forward launch; peak = %d SMs * 64 FP64 lanes * f / 10 FP64 ops per cell, f = clocks.max.sm" % sms,
                 "launch_ms": fwd,
-                # dram__bytes_read+write of this kernel per alignment in profiles/r01_ncu_summary_*.txt (100 k alignments:
-                # 0.088 GB read + 1.56 GB written) scaled to the alignments of one bench pass
-                "traffic": 16520.0 * n, "traffic_algorithmic": alg_bytes,
+                # dram__bytes_read+write of this kernel per alignment in profiles/r01_ncu_summary_v4.txt (100 k alignments:
+                # 0.082 GB read + 1.568 GB written) scaled to the alignments of one bench pass
+                "traffic": 16503.0 * n, "traffic_algorithmic": alg_bytes,
                 "hbm": {"achieved": alg_bytes / (fwd / 1000.0) / 1e9 if fwd > 0 else None, "peak": hbm_peak, "unit": "GB/s",
                         "frac": (alg_bytes / (fwd / 1000.0) / 1e9 / hbm_peak) if fwd > 0 else None,
                         "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
