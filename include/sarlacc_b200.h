@@ -227,6 +227,16 @@ int64_t sarlacc_fastq_next(sarlacc_fastq* f, int64_t max_reads,
         const uint8_t** seq_pool, const int64_t** seq_off, const uint8_t** qual_pool, const int64_t** qual_off,
         const uint8_t** name_pool, const int64_t** name_off);   /* reads returned; 0 at end of file; -1 on a malformed record */
 void sarlacc_fastq_close(sarlacc_fastq* f);
+/* Parallel, condensed variant for the adaptor path: the file is mapped and parsed by `nthreads` threads (0 = auto), and
+ * of every read only its name, its length (`width`) and its first and last `keep` bases + qualities are kept (the whole
+ * read when it is no longer than 2*keep) -- all .get_front_and_back (R/adaptorAlign.R:86-95) ever looks at for
+ * tolerance <= keep.  The condensed reads come back as CSR pools like sarlacc_fastq_next's and can be handed to
+ * sarlacc_adaptor_align_reads unchanged: their windows are the original read's windows; only adaptor2's coordinate flip
+ * needs the true width (R/adaptorAlign.R:66-71).  Do not mix with sarlacc_fastq_next on one handle.  Records whose
+ * sequence and quality lengths differ are rejected as malformed. */
+int64_t sarlacc_fastq_next_condensed(sarlacc_fastq* f, int64_t max_reads, int keep, int nthreads,
+        const uint8_t** seq_pool, const int64_t** seq_off, const uint8_t** qual_pool, const int64_t** qual_off,
+        const uint8_t** name_pool, const int64_t** name_off, const int32_t** width);
 
 #ifdef __cplusplus
 }

@@ -74,6 +74,8 @@ def _load():
     lib.sarlacc_fastq_close.argtypes = [C.c_void_p]
     lib.sarlacc_fastq_next.restype = C.c_int64
     lib.sarlacc_fastq_next.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
+    lib.sarlacc_fastq_next_condensed.restype = C.c_int64
+    lib.sarlacc_fastq_next_condensed.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int] + [C.c_void_p] * 7
     lib.sarlacc_resident_free.argtypes = [C.c_void_p]
     lib.sarlacc_resident_free.restype = None
     for name in ("sarlacc_resident_n", "sarlacc_resident_bytes"):

@@ -24,7 +24,7 @@ import re
 import numpy as np
 
 from . import native
-from .reads import ReadSet, read_fastq
+from .reads import ReadSet, read_fastq, read_fastq_condensed
 
 
 # --------------------------------------------------------------------------------------------------
@@ -236,16 +236,22 @@ def _align_AA_internal_fused(reads, adaptor1, adaptor2, tolerance, subseq1, subs
             "flipped": True}
 
 
-def _stream(source, number):
-    """FastqStreamer(filepath, n=number) + yield (R/adaptorAlign.R:26,36), or chunks of an in-memory ReadSet."""
+def _stream(source, number, keep=None):
+    """FastqStreamer(filepath, n=number) + yield (R/adaptorAlign.R:26,36), or chunks of an in-memory ReadSet.
+    Yields (reads, true widths or None).  With `keep` set, plain-text FASTQ goes through the parallel condensed ingest:
+    only the first and last `keep` bases of every read are materialised (all the alignment looks at), widths carry
+    the real read lengths."""
     number = int(number)
     if isinstance(source, ReadSet):
         n = len(source)
         for lo in range(0, n, number):
             idx = np.arange(lo, min(n, lo + number))
-            yield source[idx]
+            yield source[idx], None
+    elif keep is not None and not str(source).endswith(".gz"):
+        yield from read_fastq_condensed(source, keep, number)
     else:
-        yield from read_fastq(source, number)
+        for reads in read_fastq(source, number):
+            yield reads, None
 
 
 # --------------------------------------------------------------------------------------------------
@@ -267,7 +273,7 @@ def adaptorAlign(adaptor1, adaptor2, filepath, tolerance=250, gapOpening=5, gapE
                     gap_opening=gapOpening, gap_extension=gapExtension, encoding=enc)
     names, widths, starts, ends, revs = [], [], [], [], []
     internal = _align_AA_internal_fused if fused else _align_AA_internal
-    for reads in _stream(filepath, number):
+    for reads, true_width in _stream(filepath, number, keep=int(tolerance)):
         out = internal(reads, **all_args)
         if out.get("flipped"):
             # undo the library's adaptor2 flip so that the single flip below (R/adaptorAlign.R:66-71) applies to every chunk
@@ -275,7 +281,8 @@ def adaptorAlign(adaptor1, adaptor2, filepath, tolerance=250, gapOpening=5, gapE
             out["end"]["start"] = (w - out["end"]["start"] + 1).astype(np.int32)
             out["end"]["end"] = (w - out["end"]["end"] + 1).astype(np.int32)
         names.append(out["names"] if out["names"] is not None else [None] * len(reads))
-        widths.append(out["width"])
+        # condensed ingest: the windows are the real read's windows, the width is not
+        widths.append(out["width"] if true_width is None else true_width.astype(np.int64))
         starts.append(out["start"])
         ends.append(out["end"])
         revs.append(out["reversed"])
@@ -398,7 +405,7 @@ def getAdaptorThresholds(aligned, error=0.01, number=1e5, seed=0, device_scrambl
     wanted = {nm: k for k, nm in enumerate(aligned.rownames)}
     scr1, scr2, used = [], [], []
     seen = 0
-    for reads in _stream(filepath, number):
+    for reads, _ in _stream(filepath, number, keep=int(tolerance)):     # thresholds only look at the windows
         keep = np.array([nm in wanted for nm in reads.names], dtype=bool)
         first_index = seen
         seen += len(reads)
@@ -494,7 +501,7 @@ def tuneAlignment(adaptor1, adaptor2, filepath, tolerance=200, number=10000, gap
     adaptor2 = str(adaptor2).upper()
     enc = _create_encoding_vector(_qual2class(qual_type))
     reads = None
-    for chunk in _stream(filepath, number):
+    for chunk, _ in _stream(filepath, number, keep=int(tolerance)):
         reads = chunk
         break
     if reads is None or len(reads) == 0:
@@ -567,7 +574,7 @@ def extractSubseq(aligned, subseq1=None, subseq2=None, number=1e5):
     enc = _create_encoding_vector(_qual2class(aligned.metadata["qual.type"]))
     wanted = {nm: k for k, nm in enumerate(aligned.rownames)}
     all1, all2 = [], []
-    for reads in _stream(aligned.metadata["filepath"], number):
+    for reads, _ in _stream(aligned.metadata["filepath"], number):
         keep = np.array([nm in wanted for nm in reads.names], dtype=bool)
         reads = reads[np.nonzero(keep)[0]]
         if len(reads) == 0:

@@ -202,6 +202,42 @@ def _read_fastq_native(path, number):
         _lib.lib.sarlacc_fastq_close(h)
 
 
+def read_fastq_condensed(path, keep, number=None, nthreads=0):
+    """Parallel FASTQ ingest for the adaptor path (sarlacc_fastq_next_condensed): yields (ReadSet, widths) where every
+    read is cut down to its first and last `keep` bases (whole if no longer than 2*keep) and `widths` holds the true
+    read lengths.  For tolerance <= keep the condensed reads have exactly the windows .get_front_and_back
+    (R/adaptorAlign.R:86-95) cuts from the full reads."""
+    import ctypes as C
+    from . import _lib
+    h = _lib.lib.sarlacc_fastq_open(str(path).encode())
+    if not h:
+        raise _lib.SarlaccError(_lib.last_error())
+    try:
+        ptrs = [C.c_void_p() for _ in range(7)]
+        while True:
+            n = _lib.lib.sarlacc_fastq_next_condensed(h, C.c_int64(int(number) if number else 1 << 62), C.c_int(int(keep)), C.c_int(int(nthreads)),
+                                                      *[C.byref(p) for p in ptrs])
+            if n < 0:
+                raise _lib.SarlaccError(_lib.last_error())
+            if n == 0:
+                return
+
+            def arr(ptr, count, ctype):
+                return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(max(count, 1),))[:count].copy()
+
+            so = arr(ptrs[1], n + 1, C.c_int64)
+            qo = arr(ptrs[3], n + 1, C.c_int64)
+            no = arr(ptrs[5], n + 1, C.c_int64)
+            sp = arr(ptrs[0], int(so[-1]), C.c_uint8)
+            qp = arr(ptrs[2], int(qo[-1]), C.c_uint8)
+            nb = arr(ptrs[4], int(no[-1]), C.c_uint8).tobytes()
+            widths = arr(ptrs[6], n, C.c_int32)
+            names = [nb[no[i]:no[i + 1]].decode("latin-1") for i in range(n)]
+            yield ReadSet(sp, so, qp, qo, names), widths
+    finally:
+        _lib.lib.sarlacc_fastq_close(h)
+
+
 def read_fastq(path, number=None, skip=0):
     """FASTQ reader standing in for ShortRead::FastqStreamer + .FASTQ2QSDS (R/adaptorAlign.R:26,36,104-110).
     Yields ReadSets of at most `number` reads; plain text goes through the library's reader, .gz through Python."""

@@ -97,6 +97,45 @@ def test_fused_windows_entry(port, enc, monkeypatch):
         native.adaptor_align_windows(front[np.arange(5)], back[np.arange(4)], enc, 5, 1, VIGNETTE_A1, VIGNETTE_A2)
 
 
+def test_pair_pipeline_default_chunking(enc):
+    """The host-buffer pipeline at a size that needs several default chunks (quarter-size first chunk, whole grid-fulls
+    after it, three slots in rotation): sarlacc_adaptor_align_windows over 300 k reads == four resident passes +
+    .resolve_strand + selection, and == itself with a different chunking."""
+    import os
+    from sarlacc_b200 import native, synth
+    from oracle import r_level as R
+    n = 300000
+    front, back, widths, _ = synth.mock_windows(n, VIGNETTE_A1, VIGNETTE_A2, seed=31)
+    s1, e1 = [16, 42], [28, 46]
+    rev, r1, r2 = native.adaptor_align_windows(front, back, enc, 5, 1, VIGNETTE_A1, VIGNETTE_A2, (s1, e1), ((), ()), read_width=widths)
+    res = {}
+    for key, rs, ad, sec in (("a", front, VIGNETTE_A1, (s1, e1)), ("b", back, VIGNETTE_A2, ((), ())),
+                             ("c", back, VIGNETTE_A1, (s1, e1)), ("d", front, VIGNETTE_A2, ((), ()))):
+        r = native.Resident(rs, enc)
+        r.align(r.MODE_TRACE_LOCAL, 5, 1, ad, *sec)
+        res[key] = r.fetch()
+        r.close()
+    a, b, c, d = res["a"], res["b"], res["c"], res["d"]
+    f = np.maximum(a[0], 0) + np.maximum(b[0], 0)
+    rr = np.maximum(c[0], 0) + np.maximum(d[0], 0)
+    exp_rev = f < rr                                              # R/adaptorAlign.R:112-122
+    assert np.array_equal(rev, exp_rev)
+    for k in range(3):
+        assert np.array_equal(r1[k], np.where(exp_rev, c[k], a[k]))
+    for s in range(2):
+        assert np.array_equal(r1[3][s], np.where(exp_rev, c[3][s], a[3][s])) and np.array_equal(r1[4][s], np.where(exp_rev, c[4][s], a[4][s]))
+    assert np.array_equal(r2[0], np.where(exp_rev, d[0], b[0]))
+    assert np.array_equal(r2[1], widths - np.where(exp_rev, d[1], b[1]) + 1) and np.array_equal(r2[2], widths - np.where(exp_rev, d[2], b[2]) + 1)
+    os.environ["SARLACC_CHUNK"] = "50001"
+    try:
+        rev2, q1, q2 = native.adaptor_align_windows(front, back, enc, 5, 1, VIGNETTE_A1, VIGNETTE_A2, (s1, e1), ((), ()), read_width=widths)
+    finally:
+        del os.environ["SARLACC_CHUNK"]
+    assert np.array_equal(rev, rev2)
+    for k in range(3):
+        assert np.array_equal(r1[k], q1[k]) and np.array_equal(r2[k], q2[k])
+
+
 def test_fused_whole_read_entry(port, enc):
     """sarlacc_adaptor_align_reads: windows cut and reverse-complemented by the packer == .get_front_and_back + the
     four calls, for reads shorter and longer than the tolerance, odd characters and Biostrings byte codes."""

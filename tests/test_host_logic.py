@@ -247,3 +247,58 @@ def test_vector_packer_matches_scalar_and_numpy():
         for fs in (0, 1):
             rc, _, _ = _pack((seq, off, q2, off), phred_encoding(), 0, 0, 400, fs)
             assert rc != 0 and "quality cannot be lower than smallest encoded value" in _lib.last_error()
+
+
+def test_condensed_fastq_ingest(tmp_path):
+    """sarlacc_fastq_next_condensed (parallel, windows only) against the sequential whole-read reader: same names,
+    widths and first/last `keep` bases for any thread count and chunk size; quality lines that start with '@' or '+',
+    CRLF line ends, blank lines, a missing final newline; malformed records are reported."""
+    from sarlacc_b200 import read_fastq, read_fastq_condensed, SarlaccError
+    rng = np.random.default_rng(12)
+    n = 3000
+    recs = []
+    for i in range(n):
+        ln = int(rng.integers(0, 1500)) if i % 50 else int(rng.integers(0, 12))
+        s = "".join(rng.choice(list("ACGTN"), ln))
+        q = "".join(chr(int(c)) for c in rng.integers(33, 127, ln))
+        if ln and i % 7 == 0:
+            q = "@" + q[1:]                       # a quality line that looks like a header
+        if ln and i % 11 == 0:
+            q = "+" + q[1:]
+        recs.append(("read_%d some comment" % i, s, q))
+    for crlf, final_nl in ((False, True), (True, True), (False, False)):
+        nl = "\r\n" if crlf else "\n"
+        text = "".join("@%s%s%s%s+%s%s%s" % (h, nl, s, nl, nl, q, nl) + ("\n" if k % 500 == 499 else "") for k, (h, s, q) in enumerate(recs))
+        if not final_nl:
+            text = text.rstrip("\r\n")
+        path = tmp_path / ("x_%d_%d.fastq" % (crlf, final_nl))
+        path.write_bytes(text.encode("latin-1"))
+        whole = list(read_fastq(str(path)))
+        assert sum(len(c) for c in whole) == n
+        names = [x for c in whole for x in c.names]
+        seqs = [x for c in whole for x in c.seq_strings()]
+        quals = [x for c in whole for x in c.qual_strings()]
+        assert names == [h for h, _, _ in recs] and seqs == [s for _, s, _ in recs] and quals == [q for _, _, q in recs]
+        for keep, number, threads in ((250, None, 1), (250, None, 5), (40, 777, 3), (5, 64, 8), (250, 1, 2)):
+            if number == 1 and (crlf or not final_nl):
+                continue
+            got_n, got_s, got_q, got_w = [], [], [], []
+            for rs, w in read_fastq_condensed(str(path), keep, number, nthreads=threads):
+                assert number is None or len(rs) <= number
+                got_n += rs.names
+                got_s += rs.seq_strings()
+                got_q += rs.qual_strings()
+                got_w += w.tolist()
+            cond = lambda x: x if len(x) <= 2 * keep else x[:keep] + x[-keep:]   # noqa: E731
+            assert got_n == names and got_w == [len(s) for s in seqs]
+            assert got_s == [cond(s) for s in seqs] and got_q == [cond(q) for q in quals]
+    bad = tmp_path / "bad.fastq"
+    bad.write_bytes(b"@r1\nACGT\n+\n!!!!\n@r2\nACGT\n+\n!!!\n")
+    with pytest.raises(SarlaccError, match="sequence and quality lengths differ"):
+        list(read_fastq_condensed(str(bad), 10))
+    bad.write_bytes(b"@r1\nACGT\n+\n!!!!\nr2\nACGT\n+\n!!!!\n")
+    with pytest.raises(SarlaccError, match="header does not start with '@'"):
+        list(read_fastq_condensed(str(bad), 10))
+    empty = tmp_path / "empty.fastq"
+    empty.write_bytes(b"")
+    assert list(read_fastq_condensed(str(empty), 10)) == []

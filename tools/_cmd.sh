@@ -1,7 +1,6 @@
-exec > gpurun_out/run.log 2>&1
-echo default; python tools/bench_extra.py 2>&1 | head -2
-echo again; python tools/bench_extra.py 2>&1 | head -1
-echo CHUNK131072; SARLACC_CHUNK=131072 python tools/bench_extra.py 2>&1 | head -1
-echo NOAVX; SARLACC_NO_AVX2=1 python tools/bench_extra.py 2>&1 | head -1
-echo PAIR0; SARLACC_PAIR=0 python tools/bench_extra.py 2>&1 | head -1
-echo THREADS8; SARLACC_HOST_THREADS=8 python tools/bench_extra.py 2>&1 | head -1
+exec > gpurun_out/run2.log 2>&1
+python -m pytest tests/test_gpu_api.py -x -q -k "pipeline or sharding or fused" 2>&1 | tail -3
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --impl reference --steps 2 --warmup 1
+nproc
+python tools/bench_extra.py 2>&1 | head -2
