@@ -236,6 +236,52 @@ def _align_AA_internal_fused(reads, adaptor1, adaptor2, tolerance, subseq1, subs
             "flipped": True}
 
 
+def _prefetch(gen, depth=2):
+    """Runs a generator in a background thread, `depth` items ahead: the next chunk is parsed (in C, GIL released)
+    while the device works on the current one.  Closing the consumer early (tuneAlignment takes one chunk) stops
+    the producer and closes the underlying generator."""
+    import queue
+    import threading
+    q = queue.Queue(maxsize=depth)
+    done = object()
+    stop = threading.Event()
+
+    def put(item):
+        while not stop.is_set():
+            try:
+                q.put(item, timeout=0.05)
+                return True
+            except queue.Full:
+                continue
+        return False
+
+    def work():
+        try:
+            for item in gen:
+                if not put(item):
+                    break
+            else:
+                put(done)
+        except BaseException as e:      # surfaced in the consumer
+            put(e)
+        finally:
+            gen.close()
+
+    t = threading.Thread(target=work, daemon=True)
+    t.start()
+    try:
+        while True:
+            item = q.get()
+            if item is done:
+                return
+            if isinstance(item, BaseException):
+                raise item
+            yield item
+    finally:
+        stop.set()
+        t.join(timeout=5)
+
+
 def _stream(source, number, keep=None):
     """FastqStreamer(filepath, n=number) + yield (R/adaptorAlign.R:26,36), or chunks of an in-memory ReadSet.
     Yields (reads, true widths or None).  With `keep` set, plain-text FASTQ goes through the parallel condensed ingest:
@@ -248,7 +294,7 @@ def _stream(source, number, keep=None):
             idx = np.arange(lo, min(n, lo + number))
             yield source[idx], None
     elif keep is not None and not str(source).endswith(".gz"):
-        yield from read_fastq_condensed(source, keep, number)
+        yield from _prefetch(read_fastq_condensed(source, keep, number))
     else:
         for reads in read_fastq(source, number):
             yield reads, None
