@@ -265,7 +265,8 @@ def _prefetch(gen, depth=2):
         except BaseException as e:      # surfaced in the consumer
             put(e)
         finally:
-            gen.close()
+            if hasattr(gen, "close"):
+                gen.close()
 
     t = threading.Thread(target=work, daemon=True)
     t.start()
