@@ -127,6 +127,35 @@ __device__ __forceinline__ void land_step(int& lf0, int& lf1, bool pd, bool p5, 
     lf0 = (pd || p5) ? row : n1;
 }
 
+/* The three-way choice of src/reference_align.cpp:164-174 -- diagonal only if strictly best, horizontal only if strictly
+ * greater than vertical -- as value + the two recorded predicates.
+ * SARLACC_WF_SHORT_CHAIN: max(m, v) does not depend on this row's left-to-right chain, so it is taken first and the
+ * chain only carries max(h, mv): one compare + select less between H[i][c-1] and H[i][c].  The value is the same
+ * maximum; pd = (m > v) && (m > h) is the same predicate; p5 is recorded as (m > v) || (h > mv), which equals (h > v)
+ * whenever pd is false -- the only case in which the traceback (and land_step) read it: if m <= v then mv = v, and if
+ * m > v but the diagonal lost, h >= m > v. */
+#ifndef SARLACC_WF_SHORT_CHAIN
+#define SARLACC_WF_SHORT_CHAIN 0   /* measured: no gain without trace records (a1 1192 -> 1160, a2 1099 -> 1114 GCUPS), -12 % with (predicates spill into SELs) */
+#endif
+#ifndef SARLACC_WF_JIT_M
+#define SARLACC_WF_JIT_M 0
+#endif
+__device__ __forceinline__ double pick_move(double h, double m, double v, bool& pd, bool& p5) {
+#if SARLACC_WF_SHORT_CHAIN
+    const bool pmv = m > v;
+    const double mv = pmv ? m : v;
+    const bool q = h > mv;
+    pd = pmv && (m > h);
+    p5 = pmv || q;
+    return q ? h : mv;
+#else
+    p5 = h > v;
+    const double t = p5 ? h : v;
+    pd = m > t;
+    return pd ? m : t;
+#endif
+}
+
 constexpr int kCostEntries = 7;   /* A, C, G, T, two-fold code, three-fold code, N */
 
 template <int C, bool TRACE>
@@ -499,9 +528,13 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
         uint32_t fa[(C + 7) / 8], fb[(C + 7) / 8];
 #pragma unroll
         for (int x = 0; x < (C + 7) / 8; ++x) { fa[x] = 0; fb[x] = 0; }
-        /* row A, phase 1: vertical and (mis)match candidates of every column (:145-159); F updated in place */
+        /* row A, phase 1: vertical and (mis)match candidates of every column (:145-159); F updated in place.
+         * SARLACC_WF_JIT_M: computed per column inside the chain loop instead (no m[] array: fewer live registers). */
+#if !SARLACC_WF_JIT_M
         double mA[C];
+#endif
         bool p2lastA = false;
+#if !SARLACC_WF_JIT_M
         {
             double diag = diag0;
 #pragma unroll
@@ -516,20 +549,32 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
                 if (TRACE) { if (p2) fa[k >> 3] |= 8u << (4 * (k & 7)); }
             }
         }
+#else
+        double diagA = diag0;
+#endif
         /* the two serial chains, interleaved: A(k) and B(k-1) */
         double dB = SlA_in;               /* H[A][column left of slot 0]: diagonal of B's slot 0 */
 #pragma unroll
         for (int k = 0; k <= C; ++k) {
             if (k < C) {
+#if SARLACC_WF_JIT_M
+                const double vO = __dsub_rn(S[k], (k == C - 1) ? vo_last : gop);
+                const double Fe = __dsub_rn(F[k], (k == C - 1) ? ve_last : ge);
+                const bool p2A = Fe > vO;
+                F[k] = p2A ? Fe : vO;
+                const double mAk = __dadd_rn(diagA, *slotp[k]);
+                diagA = (k == 0 && skip0) ? diag0 : S[k];
+                if (k == C - 1) p2lastA = p2A;
+                if (TRACE) { if (p2A) fa[k >> 3] |= 8u << (4 * (k & 7)); }
+#else
+                const double mAk = mA[k];
+#endif
                 const double hO = __dsub_rn(SlA, gop);
                 const double Ee = __dsub_rn(ElA, ge);
                 const bool p1 = Ee > hO;
                 const double h = p1 ? Ee : hO;
-                const double v = F[k];
-                const bool p5 = h > v;
-                const double t = p5 ? h : v;
-                const bool pd = mA[k] > t;
-                const double Sn = pd ? mA[k] : t;
+                bool pd, p5;
+                const double Sn = pick_move(h, mAk, F[k], pd, p5);
                 S[k] = Sn;
                 SlA = Sn;
                 ElA = h;
@@ -560,10 +605,8 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
                 const double Ee = __dsub_rn(ElB, ge);
                 const bool p1 = Ee > hO;
                 const double h = p1 ? Ee : hO;
-                const bool p5 = h > vB;
-                const double t = p5 ? h : vB;
-                const bool pd = mB > t;
-                const double Sn = pd ? mB : t;
+                bool pd, p5;
+                const double Sn = pick_move(h, mB, vB, pd, p5);
                 if (MASKED) {
                     S[kk] = hasB ? Sn : SA;
                     F[kk] = hasB ? vB : FA;

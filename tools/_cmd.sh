@@ -1,4 +1,2 @@
-exec > gpurun_out/run3.log 2>&1
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python tools/bench_extra.py 2>&1 | head -3
-python tools/bench_fastq.py 200000 5000
+exec > gpurun_out/run5.log 2>&1
+for v in J3 J4; do echo $v; for m in trace score; do SARLACC_LIB=scratch/lib_$v.so python tools/profile_forward.py 200000 a1 $m 3 | tail -1; done; done
