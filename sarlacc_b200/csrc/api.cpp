@@ -937,22 +937,157 @@ struct HostOutputs {
     std::vector<std::vector<uint8_t> >* ops = nullptr;
 };
 
+/* Raw staging of one window set of one chunk: the windows' sequence and quality bytes go to the device as they are and
+ * are packed there (kernels.cu: pack_rows_kernel), so the host only moves bytes.  On a box with few cores per GPU (the
+ * 8-GPU node has 4) the host packer, not the device, set the end-to-end rate.
+ *   - CSR input, whole entries (no window cutting), pools in pinned host memory: no staging at all, the chunk's byte
+ *     range is DMA'd straight from the caller's pool;
+ *   - otherwise the windows are gathered into pinned staging (one memcpy per window, or one per thread range when the
+ *     chunk is a contiguous run of a CSR pool). */
+struct RawStage {
+    PinBuf h_seq, h_qual, h_soff, h_qoff, h_bad;
+    DevBuf d_seq, d_qual, d_soff, d_qoff, d_bad;
+    bool bad_pending = false;
+    void release() {
+        h_seq.release(); h_qual.release(); h_soff.release(); h_qoff.release(); h_bad.release();
+        d_seq.release(); d_qual.release(); d_soff.release(); d_qoff.release(); d_bad.release();
+    }
+    /* after the slot's `done` event: index (within the chunk) of the first window with a quality below the offset, or -1 */
+    long long first_bad() {
+        if (!bad_pending) return -1;
+        bad_pending = false;
+        const long long v = *h_bad.as<long long>();
+        return v == std::numeric_limits<long long>::max() ? -1 : v;
+    }
+};
+
+bool pointer_is_pinned(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+/* Enqueues on `st`: upload of the raw bytes of windows [c0, c1) of V + the device packer writing d_rows. */
+void stage_and_pack(const ReadView& V, int64_t c0, int64_t c1, const PackTables& T, const int32_t* h_lens, const int32_t* d_lens,
+        int stride, uint16_t* d_rows, bool check_qual, bool pools_pinned, RawStage& R, cudaStream_t st, int nthreads)
+{
+    const long long m = c1 - c0;
+    if (m <= 0) return;
+    R.h_soff.reserve(sizeof(long long) * (size_t)m);
+    R.h_qoff.reserve(sizeof(long long) * (size_t)m);
+    long long* soff = R.h_soff.as<long long>();
+    long long* qoff = R.h_qoff.as<long long>();
+    const sarlacc_reads* S = V.R;
+    const bool csr_whole = !S->seq && V.tol == 0;
+    const uint8_t* src_seq = nullptr;
+    const uint8_t* src_qual = nullptr;
+    size_t nseq = 0, nqual = 0;
+    if (csr_whole) {
+        /* the chunk is one contiguous byte range of each pool; a window's offsets are its entry's */
+        const int64_t s0 = S->seq_off[c0], q0 = S->qual_off[c0];
+        for (long long i = 0; i < m; ++i) {
+            soff[i] = S->seq_off[c0 + i] - s0;
+            qoff[i] = S->qual_off[c0 + i] - q0;
+        }
+        nseq = (size_t)(S->seq_off[c1] - s0);
+        nqual = (size_t)(S->qual_off[c1] - q0);
+        if (pools_pinned) {
+            src_seq = S->seq_pool + s0;
+            src_qual = S->qual_pool + q0;
+        } else {
+            R.h_seq.reserve(nseq);
+            R.h_qual.reserve(nqual);
+            uint8_t* hs = R.h_seq.as<uint8_t>();
+            uint8_t* hq = R.h_qual.as<uint8_t>();
+            parallel_for(0, m, nthreads, [&](int64_t a, int64_t b, int) {
+                std::memcpy(hs + soff[a], S->seq_pool + s0 + soff[a], (size_t)(S->seq_off[c0 + b] - S->seq_off[c0 + a]));
+                std::memcpy(hq + qoff[a], S->qual_pool + q0 + qoff[a], (size_t)(S->qual_off[c0 + b] - S->qual_off[c0 + a]));
+            });
+            src_seq = hs;
+            src_qual = hq;
+        }
+    } else {
+        /* views and cut windows: gather the windows back to back (same offsets for bases and qualities) */
+        long long at = 0;
+        for (long long i = 0; i < m; ++i) {
+            soff[i] = qoff[i] = at;
+            at += h_lens[i];
+        }
+        nseq = nqual = (size_t)at;
+        R.h_seq.reserve(nseq);
+        R.h_qual.reserve(nqual);
+        uint8_t* hs = R.h_seq.as<uint8_t>();
+        uint8_t* hq = R.h_qual.as<uint8_t>();
+        parallel_for(0, m, nthreads, [&](int64_t a, int64_t b, int) {
+            for (int64_t i = a; i < b; ++i) {
+                const int len = h_lens[i];
+                if (len <= 0) continue;
+                std::memcpy(hs + soff[i], V.seq(c0 + i), (size_t)len);
+                std::memcpy(hq + qoff[i], V.qual(c0 + i), (size_t)len);
+            }
+        });
+        src_seq = hs;
+        src_qual = hq;
+    }
+    R.d_seq.reserve(nseq);
+    R.d_qual.reserve(nqual);
+    R.d_soff.reserve(sizeof(long long) * (size_t)m);
+    R.d_qoff.reserve(sizeof(long long) * (size_t)m);
+    R.d_bad.reserve(sizeof(long long));
+    R.h_bad.reserve(sizeof(long long));
+    if (nseq) CUDA_CHECK(cudaMemcpyAsync(R.d_seq.p, src_seq, nseq, cudaMemcpyHostToDevice, st));
+    if (nqual) CUDA_CHECK(cudaMemcpyAsync(R.d_qual.p, src_qual, nqual, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(R.d_soff.p, soff, sizeof(long long) * (size_t)m, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(R.d_qoff.p, qoff, sizeof(long long) * (size_t)m, cudaMemcpyHostToDevice, st));
+    *R.h_bad.as<long long>() = std::numeric_limits<long long>::max();
+    CUDA_CHECK(cudaMemcpyAsync(R.d_bad.p, R.h_bad.p, sizeof(long long), cudaMemcpyHostToDevice, st));
+    PackArgs A;
+    A.seq = R.d_seq.as<uint8_t>();
+    A.qual = R.d_qual.as<uint8_t>();
+    A.soff = R.d_soff.as<long long>();
+    A.qoff = R.d_qoff.as<long long>();
+    A.lens = d_lens;
+    A.n = m;
+    A.stride = stride;
+    A.back = V.back ? 1 : 0;
+    A.rows = d_rows;
+    A.first_bad = check_qual ? R.d_bad.as<long long>() : nullptr;
+    std::memcpy(A.base, T.base, 256);
+    std::memcpy(A.base_rc, T.base_rc, 256);
+    std::memcpy(A.qidx, T.qidx, 512);
+    launch_pack_rows(A, st);
+    g_launches += 1;
+    CUDA_CHECK(cudaMemcpyAsync(R.h_bad.p, R.d_bad.p, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    R.bad_pending = check_qual;
+}
+
 /* One pipeline slot: pinned staging + device buffers for a chunk of reads. */
 struct Slot {
     cudaStream_t st = nullptr;
     cudaEvent_t done = nullptr;
     cudaEvent_t t_begin = nullptr, t_h2d = nullptr, t_end = nullptr;   /* SARLACC_DEBUG_TIMING: per-chunk device phases */
+    /* recorded behind the chunk's alignment kernels: the next chunk's kernels (on another slot's stream) wait for it.
+     * Uploads and result copies of neighbouring chunks still overlap, but two grid-filling forward kernels never share
+     * the device -- concurrently they finish three chunks in the time of 3.4 (measured with pinned inputs, when the
+     * host no longer paces the enqueues). */
+    cudaEvent_t gate = nullptr;
     PinBuf h_rows, h_lens, h_out;
     DevBuf d_rows, d_lens, d_out;
     PinBuf h_rows2, h_lens2, h_width;     /* second window set + read widths of the fused both-ends entry */
     DevBuf d_rows2, d_lens2, d_width, d_tmp;
     Scratch scratch;
+    RawStage raw, raw2;     /* raw bytes of the (first, second) window set on their way to the device packer */
     long long n = 0;        /* reads in flight */
     int64_t lo = 0;
     bool busy = false;
     void init() {
         CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         CUDA_CHECK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&gate, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreate(&t_begin));
         CUDA_CHECK(cudaEventCreate(&t_h2d));
         CUDA_CHECK(cudaEventCreate(&t_end));
@@ -963,7 +1098,11 @@ struct Slot {
         h_rows2.release(); h_lens2.release(); h_width.release();
         d_rows2.release(); d_lens2.release(); d_width.release(); d_tmp.release();
         scratch.release();
+        raw.release();
+        raw2.release();
         if (done) cudaEventDestroy(done);
+        if (gate) cudaEventDestroy(gate);
+        gate = nullptr;
         if (t_begin) cudaEventDestroy(t_begin);
         if (t_h2d) cudaEventDestroy(t_h2d);
         if (t_end) cudaEventDestroy(t_end);
@@ -1110,6 +1249,10 @@ struct DeviceJob {
         auto drain = [&](Slot& s, const OutLayout& o) {
             if (!s.busy) return;
             CUDA_CHECK(cudaEventSynchronize(s.done));
+            {
+                const long long fb = s.raw.first_bad();      /* quality below the offset, found by the device packer */
+                if (fb >= 0) err.offer(s.lo + fb, ERR_QUAL);
+            }
             const uint8_t* h = s.h_out.as<uint8_t>();
             const long long m = s.n;
             const int64_t g0 = s.lo;   /* global index of the slot's first read */
@@ -1143,9 +1286,13 @@ struct DeviceJob {
             s.busy = false;
         };
 
+        cudaEvent_t prev_gate = nullptr;
+        const bool host_pack = std::getenv("SARLACC_HOST_PACK") != nullptr;     /* A/B: pack on the host as before */
+        const bool pools_pinned = !reads->seq && pointer_is_pinned(reads->seq_pool) && pointer_is_pinned(reads->qual_pool);
         for (int64_t c0 = lo; c0 < hi;) {
             Slot& s = slots[which];
             drain(s, lay[which]);
+            if (err.kind != ERR_NONE && err.at < c0) break;   /* found while draining: a serial run would have stopped there */
             /* size the chunk: the trace scratch budget may force fewer reads than `chunk` */
             int64_t c1 = std::min<int64_t>(hi, c0 + (c0 == lo ? first_chunk : chunk));
             s.h_lens.reserve(sizeof(int32_t) * (size_t)(c1 - c0));
@@ -1162,8 +1309,10 @@ struct DeviceJob {
             }
             const long long m = c1 - c0;
             const int stride = std::max(8, (maxlen + 8) & ~7);   /* >= maxlen+1, multiple of 8 */
-            s.h_rows.reserve(sizeof(uint16_t) * (size_t)m * stride);
-            pack_rows(V, c0, c1, PT, s.h_lens.as<int32_t>(), stride, s.h_rows.as<uint16_t>(), nthreads, P.L > 0, err);
+            if (host_pack) {
+                s.h_rows.reserve(sizeof(uint16_t) * (size_t)m * stride);
+                pack_rows(V, c0, c1, PT, s.h_lens.as<int32_t>(), stride, s.h_rows.as<uint16_t>(), nthreads, P.L > 0, err);
+            }
             if (err.kind != ERR_NONE && err.at < c1) break;   /* a serial run would have stopped here */
 
             const OutLayout o = make_layout(mode, m, nref_scores, nsec, maxlen, P.L);
@@ -1172,8 +1321,13 @@ struct DeviceJob {
             s.d_lens.reserve(sizeof(int32_t) * (size_t)m);
             s.d_out.reserve(o.total);
             s.h_out.reserve(o.total);
-            CUDA_CHECK(cudaMemcpyAsync(s.d_rows.p, s.h_rows.p, sizeof(uint16_t) * (size_t)m * stride, cudaMemcpyHostToDevice, s.st));
             CUDA_CHECK(cudaMemcpyAsync(s.d_lens.p, s.h_lens.p, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
+            if (host_pack) {
+                CUDA_CHECK(cudaMemcpyAsync(s.d_rows.p, s.h_rows.p, sizeof(uint16_t) * (size_t)m * stride, cudaMemcpyHostToDevice, s.st));
+            } else {
+                stage_and_pack(V, c0, c1, PT, s.h_lens.as<int32_t>(), s.d_lens.as<int32_t>(), stride, s.d_rows.as<uint16_t>(), P.L > 0,
+                               pools_pinned, s.raw, s.st, nthreads);
+            }
             uint8_t* d = s.d_out.as<uint8_t>();
             Outputs dev;
             dev.score = (mode == MODE_MULTI_GLOBAL && !want_all_scores) ? nullptr : reinterpret_cast<double*>(d + o.o_score);
@@ -1193,7 +1347,10 @@ struct DeviceJob {
                 dev.ops = d + o.o_ops;
                 dev.ops_stride = o.ops_stride;
             }
+            if (prev_gate) CUDA_CHECK(cudaStreamWaitEvent(s.st, prev_gate, 0));
             run_device(P, D, s.scratch, s.st, s.d_rows.as<uint16_t>(), s.d_lens.as<int32_t>(), m, stride, maxlen, trace, dev, sms);
+            CUDA_CHECK(cudaEventRecord(s.gate, s.st));
+            prev_gate = s.gate;
             CUDA_CHECK(cudaMemcpyAsync(s.h_out.p, s.d_out.p, o.total, cudaMemcpyDeviceToHost, s.st));
             CUDA_CHECK(cudaEventRecord(s.done, s.st));
             s.n = m;
@@ -1442,6 +1599,11 @@ struct PairJob {
         auto drain = [&](Slot& s, const FinalLayout& o) {
             if (!s.busy) return;
             CUDA_CHECK(cudaEventSynchronize(s.done));
+            {
+                const long long fb = s.raw.first_bad(), fb2 = s.raw2.first_bad();
+                if (fb >= 0) err_front.offer(s.lo + fb, ERR_QUAL);
+                if (fb2 >= 0) err_back.offer(s.lo + fb2, ERR_QUAL);
+            }
             if (dbg) {
                 float a = 0, b = 0;
                 cudaEventElapsedTime(&a, s.t_begin, s.t_h2d);
@@ -1466,11 +1628,16 @@ struct PairJob {
         };
 
         double t_drain = 0, t_pack = 0, t_enq = 0;
+        cudaEvent_t prev_gate = nullptr;
+        const bool host_pack = std::getenv("SARLACC_HOST_PACK") != nullptr;     /* A/B: pack on the host as before */
+        const bool pinned_f = !VF.R->seq && pointer_is_pinned(VF.R->seq_pool) && pointer_is_pinned(VF.R->qual_pool);
+        const bool pinned_b = !VB.R->seq && pointer_is_pinned(VB.R->seq_pool) && pointer_is_pinned(VB.R->qual_pool);
         for (int64_t c0 = lo; c0 < hi;) {
             Slot& s = slots[which];
             double t0 = now();
             drain(s, lay[which]);
             t_drain += now() - t0;
+            if ((err_front.kind != ERR_NONE && err_front.at < c0) || (err_back.kind != ERR_NONE && err_back.at < c0)) break;
             t0 = now();
             int64_t c1 = std::min<int64_t>(hi, c0 + (c0 == lo ? first_chunk : chunk));
             s.h_lens.reserve(sizeof(int32_t) * (size_t)(c1 - c0));
@@ -1492,10 +1659,12 @@ struct PairJob {
             }
             const long long m = c1 - c0;
             const int stride_f = std::max(8, (maxf + 8) & ~7), stride_b = std::max(8, (maxb + 8) & ~7);
-            s.h_rows.reserve(sizeof(uint16_t) * (size_t)m * stride_f);
-            s.h_rows2.reserve(sizeof(uint16_t) * (size_t)m * stride_b);
-            pack_rows(VF, c0, c1, PF, s.h_lens.as<int32_t>(), stride_f, s.h_rows.as<uint16_t>(), nthreads, true, err_front);
-            pack_rows(VB, c0, c1, PB, s.h_lens2.as<int32_t>(), stride_b, s.h_rows2.as<uint16_t>(), nthreads, true, err_back);
+            if (host_pack) {
+                s.h_rows.reserve(sizeof(uint16_t) * (size_t)m * stride_f);
+                s.h_rows2.reserve(sizeof(uint16_t) * (size_t)m * stride_b);
+                pack_rows(VF, c0, c1, PF, s.h_lens.as<int32_t>(), stride_f, s.h_rows.as<uint16_t>(), nthreads, true, err_front);
+                pack_rows(VB, c0, c1, PB, s.h_lens2.as<int32_t>(), stride_b, s.h_rows2.as<uint16_t>(), nthreads, true, err_back);
+            }
             if ((err_front.kind != ERR_NONE && err_front.at < c1) || (err_back.kind != ERR_NONE && err_back.at < c1)) break;
             t_pack += now() - t0;
             t0 = now();
@@ -1532,10 +1701,17 @@ struct PairJob {
             s.d_out.reserve(F.total);
             s.h_out.reserve(F.total);
             if (dbg) CUDA_CHECK(cudaEventRecord(s.t_begin, s.st));
-            CUDA_CHECK(cudaMemcpyAsync(s.d_rows.p, s.h_rows.p, sizeof(uint16_t) * (size_t)m * stride_f, cudaMemcpyHostToDevice, s.st));
-            CUDA_CHECK(cudaMemcpyAsync(s.d_rows2.p, s.h_rows2.p, sizeof(uint16_t) * (size_t)m * stride_b, cudaMemcpyHostToDevice, s.st));
             CUDA_CHECK(cudaMemcpyAsync(s.d_lens.p, s.h_lens.p, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
             CUDA_CHECK(cudaMemcpyAsync(s.d_lens2.p, s.h_lens2.p, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
+            if (host_pack) {
+                CUDA_CHECK(cudaMemcpyAsync(s.d_rows.p, s.h_rows.p, sizeof(uint16_t) * (size_t)m * stride_f, cudaMemcpyHostToDevice, s.st));
+                CUDA_CHECK(cudaMemcpyAsync(s.d_rows2.p, s.h_rows2.p, sizeof(uint16_t) * (size_t)m * stride_b, cudaMemcpyHostToDevice, s.st));
+            } else {
+                stage_and_pack(VF, c0, c1, PF, s.h_lens.as<int32_t>(), s.d_lens.as<int32_t>(), stride_f, s.d_rows.as<uint16_t>(), true,
+                               pinned_f, s.raw, s.st, nthreads);
+                stage_and_pack(VB, c0, c1, PB, s.h_lens2.as<int32_t>(), s.d_lens2.as<int32_t>(), stride_b, s.d_rows2.as<uint16_t>(), true,
+                               pinned_b, s.raw2, s.st, nthreads);
+            }
             if (width || tolerance > 0) {
                 s.h_width.reserve(sizeof(int32_t) * (size_t)m);
                 s.d_width.reserve(sizeof(int32_t) * (size_t)m);
@@ -1551,6 +1727,7 @@ struct PairJob {
                 CUDA_CHECK(cudaMemcpyAsync(s.d_width.p, s.h_width.p, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
             }
             if (dbg) CUDA_CHECK(cudaEventRecord(s.t_h2d, s.st));
+            if (prev_gate) CUDA_CHECK(cudaStreamWaitEvent(s.st, prev_gate, 0));
             uint8_t* t = s.d_tmp.as<uint8_t>();
             ResultSet rs[4];
             for (int r = 0; r < 4; ++r) {
@@ -1568,6 +1745,8 @@ struct PairJob {
                            on_front ? stride_f : stride_b, on_front ? maxf : maxb, true, dev, sms);
                 rs[r] = ResultSet{dev.score, dev.start, dev.end, dev.sec_start, dev.sec_width};
             }
+            CUDA_CHECK(cudaEventRecord(s.gate, s.st));
+            prev_gate = s.gate;
             uint8_t* d = s.d_out.as<uint8_t>();
             SelectArgs S;
             std::memset(&S, 0, sizeof(S));

@@ -1082,6 +1082,35 @@ __global__ void __launch_bounds__(128) scramble_rows(const uint16_t* in, uint16_
     }
 }
 
+/* One warp per window, lanes across its bases: coalesced byte loads, 64-byte row stores; tables in shared memory. */
+__global__ void __launch_bounds__(256) pack_rows_kernel(const __grid_constant__ PackArgs A)
+{
+    __shared__ uint8_t sbase[256];
+    __shared__ uint16_t sq[256];
+    const uint8_t* bt = A.back ? A.base_rc : A.base;
+    for (int x = threadIdx.x; x < 256; x += blockDim.x) {
+        sbase[x] = bt[x];
+        sq[x] = A.qidx[x];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < A.n; i += warps) {
+        const int len = A.lens[i];
+        const uint8_t* s = A.seq + A.soff[i];
+        const uint8_t* q = A.qual + A.qoff[i];
+        uint16_t* out = A.rows + i * (long long)A.stride;
+        bool bad = false;
+        for (int r = lane; r < len; r += 32) {
+            const int src = A.back ? len - 1 - r : r;
+            unsigned qi = sq[q[src]];
+            if (qi & 0xFF00u) { bad = true; qi = 0; }
+            out[r] = (uint16_t)(qi | ((unsigned)sbase[s[src]] << 8));
+        }
+        if (A.first_bad && __any_sync(FULL, bad) && lane == 0) atomicMin(A.first_bad, i);
+    }
+}
+
 template <int C, bool TRACE>
 int wf_resident_blocks(bool pair, size_t smem) {
     auto kern = pair ? wf_forward2<C, TRACE> : wf_forward<C, TRACE>;
@@ -1188,6 +1217,13 @@ void launch_scramble(const uint16_t* in, uint16_t* out, const int32_t* lens, lon
     long long grid = (n + (block / 32) - 1) / (block / 32);
     if (grid > 148 * 64) grid = 148 * 64;
     scramble_rows<<<(int)grid, block, smem, st>>>(in, out, lens, n, stride, seed, first_index, read_index, stream_id);
+}
+
+void launch_pack_rows(const PackArgs& a, cudaStream_t st) {
+    if (a.n <= 0) return;
+    long long grid = (a.n + 7) / 8;
+    if (grid > 148 * 16) grid = 148 * 16;
+    pack_rows_kernel<<<(int)grid, 256, 0, st>>>(a);
 }
 
 void launch_resolve_select(const SelectArgs& s, cudaStream_t st) {

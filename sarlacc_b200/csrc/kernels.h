@@ -121,6 +121,28 @@ void launch_scramble(const uint16_t* in, uint16_t* out, const int32_t* lens, lon
                      unsigned long long seed, unsigned long long first_index, const unsigned long long* read_index,
                      unsigned long long stream_id, cudaStream_t st);
 
+/* Device packer: raw sequence / quality bytes (as the caller holds them: ASCII or Biostrings codes, any quality
+ * encoding) -> the uint16 rows above.  Window i is seq[soff[i] .. soff[i] + lens[i]) and qual[qoff[i] ..); back != 0
+ * packs its reverse complement (qualities reversed with it, R/adaptorAlign.R:86-95).  The 256-entry tables are the host
+ * packer's (api.cpp: build_pack_tables), so both packers are the same function of the input bytes.  A quality below
+ * the encoding's offset (src/reference_align.cpp:215-217) packs index 0 and reports its window: atomicMin(first_bad, i). */
+struct PackArgs {
+    const uint8_t* seq;
+    const uint8_t* qual;
+    const long long* soff;
+    const long long* qoff;
+    const int32_t* lens;
+    long long n;
+    int stride;
+    int back;
+    uint16_t* rows;
+    long long* first_bad;      /* initialised to LLONG_MAX by the caller; may be null */
+    uint8_t base[256];
+    uint8_t base_rc[256];
+    uint16_t qidx[256];        /* 0xFFFF: below the offset */
+};
+void launch_pack_rows(const PackArgs& a, cudaStream_t st);
+
 /* Launchers (return the kernel's name for reporting; throw nothing, errors via cudaGetLastError). */
 const char* launch_wavefront(const AlignArgs& a, bool trace, bool has_alt, int grid, cudaStream_t st);
 const char* launch_generic(const AlignArgs& a, bool trace, int grid, cudaStream_t st);

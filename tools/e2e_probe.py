@@ -18,6 +18,13 @@ w = widths.astype(np.int32)
 print("host cores", os.cpu_count(), "threads env", os.environ.get("SARLACC_HOST_THREADS"))
 if os.environ.get("SARLACC_HOST_THREADS"):
     _lib.lib.sarlacc_set_host_threads(int(os.environ["SARLACC_HOST_THREADS"]))
+if os.environ.get("PROBE_PINNED"):
+    import torch
+    from sarlacc_b200 import ReadSet
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()   # noqa: E731
+    front = ReadSet(pin(front.seq_pool), front.seq_off, pin(front.qual_pool), front.qual_off, front.names)
+    back = ReadSet(pin(back.seq_pool), back.seq_off, pin(back.qual_pool), back.qual_off, back.names)
+    print("inputs pinned")
 for r in range(reps):
     t0 = time.perf_counter()
     native.adaptor_align_windows(front, back, enc, 5.0, 1.0, A1, A2, (s1, e1), ([], []), read_width=w)
