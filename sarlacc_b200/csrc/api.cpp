@@ -1079,7 +1079,9 @@ struct Slot {
     DevBuf d_rows, d_lens, d_out;
     PinBuf h_rows2, h_lens2, h_width;     /* second window set + read widths of the fused both-ends entry */
     DevBuf d_rows2, d_lens2, d_width, d_tmp;
-    Scratch scratch;
+    Scratch scratch, scratch_b;   /* the fused both-ends entry alternates them so that traceback(r) overlaps forward(r+1) */
+    cudaStream_t tb = nullptr;    /* tracebacks of the fused entry */
+    cudaEvent_t fwd_ev[4] = {nullptr, nullptr, nullptr, nullptr}, tb_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     RawStage raw, raw2;     /* raw bytes of the (first, second) window set on their way to the device packer */
     long long n = 0;        /* reads in flight */
     int64_t lo = 0;
@@ -1088,6 +1090,11 @@ struct Slot {
         CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         CUDA_CHECK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&gate, cudaEventDisableTiming));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&tb, cudaStreamNonBlocking));
+        for (int k = 0; k < 4; ++k) {
+            CUDA_CHECK(cudaEventCreateWithFlags(&fwd_ev[k], cudaEventDisableTiming));
+            CUDA_CHECK(cudaEventCreateWithFlags(&tb_ev[k], cudaEventDisableTiming));
+        }
         CUDA_CHECK(cudaEventCreate(&t_begin));
         CUDA_CHECK(cudaEventCreate(&t_h2d));
         CUDA_CHECK(cudaEventCreate(&t_end));
@@ -1103,6 +1110,14 @@ struct Slot {
         if (done) cudaEventDestroy(done);
         if (gate) cudaEventDestroy(gate);
         gate = nullptr;
+        for (int k = 0; k < 4; ++k) {
+            if (fwd_ev[k]) cudaEventDestroy(fwd_ev[k]);
+            if (tb_ev[k]) cudaEventDestroy(tb_ev[k]);
+            fwd_ev[k] = tb_ev[k] = nullptr;
+        }
+        if (tb) cudaStreamDestroy(tb);
+        tb = nullptr;
+        scratch_b.release();
         if (t_begin) cudaEventDestroy(t_begin);
         if (t_h2d) cudaEventDestroy(t_h2d);
         if (t_end) cudaEventDestroy(t_end);
@@ -1739,14 +1754,18 @@ struct PairJob {
                 dev.end = reinterpret_cast<int32_t*>(t + T.o_end[r]);
                 dev.sec_start = reinterpret_cast<int32_t*>(t + T.o_ss[r]);
                 dev.sec_width = reinterpret_cast<int32_t*>(t + T.o_sw[r]);
-                run_device(*plan[a], D[a], s.scratch, s.st,
+                /* forward(r) reuses the records traceback(r-2) reads; traceback(r-1) runs beside it on the slot's second stream */
+                if (r >= 2) CUDA_CHECK(cudaStreamWaitEvent(s.st, s.tb_ev[r - 2], 0));
+                run_device(*plan[a], D[a], (r & 1) ? s.scratch_b : s.scratch, s.st,
                            on_front ? s.d_rows.as<uint16_t>() : s.d_rows2.as<uint16_t>(),
                            on_front ? s.d_lens.as<int32_t>() : s.d_lens2.as<int32_t>(), m,
-                           on_front ? stride_f : stride_b, on_front ? maxf : maxb, true, dev, sms);
+                           on_front ? stride_f : stride_b, on_front ? maxf : maxb, true, dev, sms,
+                           nullptr, s.tb, s.fwd_ev[r], s.tb_ev[r]);
                 rs[r] = ResultSet{dev.score, dev.start, dev.end, dev.sec_start, dev.sec_width};
             }
-            CUDA_CHECK(cudaEventRecord(s.gate, s.st));
+            CUDA_CHECK(cudaEventRecord(s.gate, s.st));     /* behind the fourth forward pass; the last tracebacks run beside the next chunk */
             prev_gate = s.gate;
+            CUDA_CHECK(cudaStreamWaitEvent(s.st, s.tb_ev[3], 0));   /* the traceback stream is in order: [3] covers all four */
             uint8_t* d = s.d_out.as<uint8_t>();
             SelectArgs S;
             std::memset(&S, 0, sizeof(S));
