@@ -136,6 +136,37 @@ def test_pair_pipeline_default_chunking(enc):
         assert np.array_equal(r1[k], q1[k]) and np.array_equal(r2[k], q2[k])
 
 
+def test_pinned_inputs_take_the_zero_copy_path(enc):
+    """Pools in pinned host memory are DMA'd straight to the device packer (no staging copy): identical results to
+    pageable pools, for the fused entry and the single-adaptor entries, including a quality error found on the device."""
+    import torch
+    from sarlacc_b200 import native, synth, ReadSet, SarlaccError
+    n = 150000
+    front, back, widths, _ = synth.mock_windows(n, VIGNETTE_A1, VIGNETTE_A2, seed=55)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()   # noqa: E731
+    pf = ReadSet(pin(front.seq_pool), front.seq_off, pin(front.qual_pool), front.qual_off, front.names)
+    pb = ReadSet(pin(back.seq_pool), back.seq_off, pin(back.qual_pool), back.qual_off, back.names)
+    s1, e1 = [16, 42], [28, 46]
+    a = native.adaptor_align_windows(front, back, enc, 5, 1, VIGNETTE_A1, VIGNETTE_A2, (s1, e1), ((), ()), read_width=widths)
+    b = native.adaptor_align_windows(pf, pb, enc, 5, 1, VIGNETTE_A1, VIGNETTE_A2, (s1, e1), ((), ()), read_width=widths)
+    assert np.array_equal(a[0], b[0])
+    for x, y in ((a[1], b[1]), (a[2], b[2])):
+        for k in range(3):
+            assert np.array_equal(x[k], y[k])
+        for k in range(len(x[3])):
+            assert np.array_equal(x[3][k], y[3][k]) and np.array_equal(x[4][k], y[4][k])
+    c = native.adaptor_align(front, enc, 5, 1, VIGNETTE_A1, s1, e1)
+    d = native.adaptor_align(pf, enc, 5, 1, VIGNETTE_A1, s1, e1)
+    assert all(np.array_equal(c[k], d[k]) for k in range(3))
+    assert np.array_equal(native.adaptor_align_score_only(pb, enc, 5, 1, VIGNETTE_A2), native.adaptor_align_score_only(back, enc, 5, 1, VIGNETTE_A2))
+    # a quality below the offset somewhere in the middle: reported by the device packer, same message
+    pf.qual_pool[pf.qual_off[120000] + 17] = 32
+    with pytest.raises(SarlaccError, match="quality cannot be lower than smallest encoded value"):
+        native.adaptor_align(pf, enc, 5, 1, VIGNETTE_A1, s1, e1)
+    with pytest.raises(SarlaccError, match="quality cannot be lower than smallest encoded value"):
+        native.adaptor_align_windows(pf, pb, enc, 5, 1, VIGNETTE_A1, VIGNETTE_A2, (s1, e1), ((), ()), read_width=widths)
+
+
 def test_fused_whole_read_entry(port, enc):
     """sarlacc_adaptor_align_reads: windows cut and reverse-complemented by the packer == .get_front_and_back + the
     four calls, for reads shorter and longer than the tolerance, odd characters and Biostrings byte codes."""

@@ -1,4 +1,2 @@
-exec > gpurun_out/run10.log 2>&1
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-echo "--- pinned"; PROBE_PINNED=1 SARLACC_DEBUG_TIMING=1 python tools/e2e_probe.py 1000000 3 2>&1 | tail -4
-echo "--- pageable, 16 threads"; python tools/e2e_probe.py 1000000 3 2>&1 | tail -1
+exec > gpurun_out/run11.log 2>&1
+python -m pytest tests/test_gpu_api.py -x -q -k "pinned or errors" 2>&1 | tail -8
