@@ -356,20 +356,29 @@ class Resident:
             reference.encode("latin-1"), C.c_int(len(ss)), _lib._ptr(ss), _lib._ptr(se),
             C.c_void_p(stream) if stream else None))
 
-    def fetch(self, stream=None):
+    def fetch(self, stream=None, pinned=False):
+        """Copies the last run's results to the host.  pinned=True puts them in page-locked memory (torch allocator):
+        the device-to-host copy then runs at PCIe speed instead of through the driver's bounce buffers."""
         n, nsec = self.n, self.nsec
-        score = np.zeros(n, np.float64)
+
+        def alloc(shape, dtype):
+            if pinned:
+                import torch
+                return torch.empty(shape, dtype={np.float64: torch.float64, np.int32: torch.int32}[dtype], pin_memory=True).numpy()
+            return np.empty(shape, dtype)
+
+        score = alloc(n, np.float64)
         trace = self.mode == self.MODE_TRACE_LOCAL
-        start = np.zeros(n, np.int32) if trace else None
-        end = np.zeros(n, np.int32) if trace else None
-        sst = np.zeros((max(nsec, 1), max(n, 1)), np.int32) if trace else None
-        swd = np.zeros((max(nsec, 1), max(n, 1)), np.int32) if trace else None
+        start = alloc(n, np.int32) if trace else None
+        end = alloc(n, np.int32) if trace else None
+        sst = alloc((max(nsec, 1), max(n, 1)), np.int32) if trace else None
+        swd = alloc((max(nsec, 1), max(n, 1)), np.int32) if trace else None
         _lib.check(_lib.lib.sarlacc_resident_fetch(
             self.handle, _lib._ptr(score), _lib._ptr(start), _lib._ptr(end), _lib._ptr(sst), _lib._ptr(swd),
             C.c_void_p(stream) if stream else None))
         if not trace:
             return score
-        return [score, start, end, [sst[i, :n].copy() for i in range(nsec)], [swd[i, :n].copy() for i in range(nsec)]]
+        return [score, start, end, [sst[i, :n] for i in range(nsec)], [swd[i, :n] for i in range(nsec)]]
 
     def set_timing(self, on=True):
         _lib.lib.sarlacc_resident_set_timing(self.handle, C.c_int(1 if on else 0))

@@ -1,2 +1,2 @@
-exec > gpurun_out/run11.log 2>&1
-python -m pytest tests/test_gpu_api.py -x -q -k "pinned or errors" 2>&1 | tail -8
+exec > gpurun_out/run12.log 2>&1
+python tools/run_c5.py --share 2500000 --batch 1250000
