@@ -295,6 +295,14 @@ def umi_neighbors(umi1, threshold1, umi2=None, threshold2=None, groups=None, dev
     return _umi_call(_lib.lib.sarlacc_umi_neighbors, umi1, threshold1, umi2, threshold1 if threshold2 is None else threshold2, groups, device)
 
 
+class _Fetched(list):
+    """[score, start, end, [section starts], [section widths]] that remembers its buffers for reuse by Resident.fetch."""
+
+
+class _FetchedScores(np.ndarray):
+    """Score vector that remembers its buffers for reuse by Resident.fetch."""
+
+
 class Resident:
     """Read windows packed once and kept in HBM (sarlacc_resident_*)."""
 
@@ -356,10 +364,12 @@ class Resident:
             reference.encode("latin-1"), C.c_int(len(ss)), _lib._ptr(ss), _lib._ptr(se),
             C.c_void_p(stream) if stream else None))
 
-    def fetch(self, stream=None, pinned=False):
+    def fetch(self, stream=None, pinned=False, out=None):
         """Copies the last run's results to the host.  pinned=True puts them in page-locked memory (torch allocator):
-        the device-to-host copy then runs at PCIe speed instead of through the driver's bounce buffers."""
+        the device-to-host copy then runs at PCIe speed instead of through the driver's bounce buffers.  out = the
+        object returned by an earlier fetch of the same shape: its buffers are reused (page-locking is slow)."""
         n, nsec = self.n, self.nsec
+        trace = self.mode == self.MODE_TRACE_LOCAL
 
         def alloc(shape, dtype):
             if pinned:
@@ -367,18 +377,21 @@ class Resident:
                 return torch.empty(shape, dtype={np.float64: torch.float64, np.int32: torch.int32}[dtype], pin_memory=True).numpy()
             return np.empty(shape, dtype)
 
-        score = alloc(n, np.float64)
-        trace = self.mode == self.MODE_TRACE_LOCAL
-        start = alloc(n, np.int32) if trace else None
-        end = alloc(n, np.int32) if trace else None
-        sst = alloc((max(nsec, 1), max(n, 1)), np.int32) if trace else None
-        swd = alloc((max(nsec, 1), max(n, 1)), np.int32) if trace else None
+        bufs = getattr(out, "_buffers", None) if out is not None else None
+        if bufs is not None and bufs[0].shape == (n,) and (bufs[3] is None) == (not trace) and (not trace or bufs[3].shape == (max(nsec, 1), max(n, 1))):
+            score, start, end, sst, swd = bufs
+        else:
+            score = alloc(n, np.float64)
+            start = alloc(n, np.int32) if trace else None
+            end = alloc(n, np.int32) if trace else None
+            sst = alloc((max(nsec, 1), max(n, 1)), np.int32) if trace else None
+            swd = alloc((max(nsec, 1), max(n, 1)), np.int32) if trace else None
         _lib.check(_lib.lib.sarlacc_resident_fetch(
             self.handle, _lib._ptr(score), _lib._ptr(start), _lib._ptr(end), _lib._ptr(sst), _lib._ptr(swd),
             C.c_void_p(stream) if stream else None))
-        if not trace:
-            return score
-        return [score, start, end, [sst[i, :n] for i in range(nsec)], [swd[i, :n] for i in range(nsec)]]
+        res = _Fetched([score, start, end, [sst[i, :n] for i in range(nsec)], [swd[i, :n] for i in range(nsec)]]) if trace else score.view(_FetchedScores)
+        res._buffers = (score, start, end, sst, swd)
+        return res
 
     def set_timing(self, on=True):
         _lib.lib.sarlacc_resident_set_timing(self.handle, C.c_int(1 if on else 0))

@@ -44,12 +44,17 @@ t_align = t_thr = t_gen = 0.0
 real1, real2, scr1, scr2 = [], [], [], []
 checked = 0
 stream = torch.cuda.Stream(device=local)
-for b0 in range(0, args.share, args.batch):
+bufs = {}
+# one untimed warm-up batch first (module load, page-locked result buffers), then the share in batches
+for bi, b0 in enumerate([-1] + list(range(0, args.share, args.batch))):
+    warm = b0 < 0
+    b0 = max(b0, 0)
     m = min(args.batch, args.share - b0)
     first = rank * args.share + b0
     t0 = time.perf_counter()
     front, back, widths, _ = synth.mock_windows(m, A1, A2, seed=5000, first_index=first)
-    t_gen += time.perf_counter() - t0
+    if not warm:
+        t_gen += time.perf_counter() - t0
     rf, rb = native.Resident(front, enc, device=local), native.Resident(back, enc, device=local)
     torch.cuda.synchronize()
     # ---- adaptorAlign: .align_AA_internal's four alignments with traceback + strand resolution
@@ -57,12 +62,13 @@ for b0 in range(0, args.share, args.batch):
     res = {}
     for key, r, a, sec in (("a", rf, A1, (s1, e1)), ("b", rb, A2, ((), ())), ("c", rb, A1, (s1, e1)), ("d", rf, A2, ((), ()))):
         r.align(r.MODE_TRACE_LOCAL, 5, 1, a, *sec, stream=stream.cuda_stream)
-        res[key] = r.fetch(stream=stream.cuda_stream, pinned=True)
+        res[key] = bufs[key] = r.fetch(stream=stream.cuda_stream, pinned=True, out=bufs.get(key))
     torch.cuda.synchronize()
     rev = api._resolve_strand(res["a"][0], res["b"][0], res["c"][0], res["d"][0])["reversed"]
-    t_align += time.perf_counter() - t0
-    real1.append(np.where(rev, res["c"][0], res["a"][0]))
-    real2.append(np.where(rev, res["d"][0], res["b"][0]))
+    if not warm:
+        t_align += time.perf_counter() - t0
+        real1.append(np.where(rev, res["c"][0], res["a"][0]))
+        real2.append(np.where(rev, res["d"][0], res["b"][0]))
     # ---- getAdaptorThresholds: scramble on the device (keyed by global read index), four score-only alignments
     t0 = time.perf_counter()
     idx = np.arange(first, first + m, dtype=np.uint64)
@@ -70,14 +76,15 @@ for b0 in range(0, args.share, args.batch):
     sc = {}
     for key, r, a in (("S", sf, A1), ("E", sb, A2), ("RS", sb, A1), ("RE", sf, A2)):
         r.align(r.MODE_SCORE_LOCAL, 5, 1, a, stream=stream.cuda_stream)
-        sc[key] = r.fetch(stream=stream.cuda_stream, pinned=True)
+        sc[key] = bufs[key] = r.fetch(stream=stream.cuda_stream, pinned=True, out=bufs.get(key))
     torch.cuda.synchronize()
     srev = api._resolve_strand(sc["S"], sc["E"], sc["RS"], sc["RE"])["reversed"]
-    t_thr += time.perf_counter() - t0
-    scr1.append(np.where(srev, sc["RS"], sc["S"]))
-    scr2.append(np.where(srev, sc["RE"], sc["E"]))
+    if not warm:
+        t_thr += time.perf_counter() - t0
+        scr1.append(np.where(srev, sc["RS"], sc["S"]))
+        scr2.append(np.where(srev, sc["RE"], sc["E"]))
     # ---- parity on a strided sample: the reference's own C++ on the same windows
-    if oracle is not None:
+    if oracle is not None and not warm:
         pick = np.arange(0, m, args.check_stride)
         sub = front[pick]
         exp = oracle.adaptor_align((sub.seq_pool, sub.seq_off), (sub.qual_pool, sub.qual_off), enc, 5, 1, A1, s1, e1, nthreads=os.cpu_count() or 1)
