@@ -77,6 +77,9 @@ int  sarlacc_set_host_threads(int nthreads);    /* packer threads per device (de
 const char* sarlacc_version(void);
 /* Launch accounting for bench.py's "gpu_launches": kernels launched by this library since the last reset. */
 int64_t sarlacc_kernel_launches(int reset);
+/* Device buffers released by the library are kept for reuse (SARLACC_POOL_MB, default 24576; 0 = off); this hands them
+ * back to the driver. */
+void sarlacc_trim_device_memory(void);
 
 /* ---- the four reference entry points (host buffers in, host buffers out) ------------------------- */
 

@@ -582,20 +582,93 @@ void pack_rows(const ReadView& V, int64_t lo, int64_t hi, const PackTables& T, c
 
 /* ---- device-side resources ------------------------------------------------------------------- */
 
+/* Freed device buffers are kept for reuse (per device, best fit) instead of going back to the driver: building and
+ * dropping resident objects per batch otherwise spends more time in cudaMalloc / cudaFree of multi-GB trace scratch than
+ * in the kernels.  A buffer enters the pool only after its device has been synchronised -- the guarantee cudaFree gave.
+ * SARLACC_POOL_MB bounds what is kept (default 24576; 0 disables the pool); sarlacc_trim_device_memory() empties it. */
+class DevPool {
+public:
+    static DevPool& instance() {
+        static DevPool* pool = new DevPool();     /* never destroyed: no CUDA calls during process teardown */
+        return *pool;
+    }
+    void* take(size_t bytes, int dev, size_t* cap) {
+        std::lock_guard<std::mutex> lock(m_);
+        int best = -1;
+        for (size_t i = 0; i < free_.size(); ++i) {
+            const Block& b = free_[i];
+            if (b.dev != dev || b.cap < bytes || b.cap > 2 * bytes + (1u << 20)) continue;
+            if (best < 0 || b.cap < free_[(size_t)best].cap) best = (int)i;
+        }
+        if (best < 0) return nullptr;
+        void* p = free_[(size_t)best].p;
+        *cap = free_[(size_t)best].cap;
+        cached_ -= *cap;
+        free_.erase(free_.begin() + best);
+        return p;
+    }
+    /* returns false if the block was not kept (the caller frees it) */
+    bool give(void* p, size_t cap, int dev) {
+        std::lock_guard<std::mutex> lock(m_);
+        if (limit_ == 0 || cap > limit_) return false;
+        while (cached_ + cap > limit_ && !free_.empty()) {      /* make room: drop the oldest blocks */
+            cudaFree(free_.front().p);
+            cached_ -= free_.front().cap;
+            free_.erase(free_.begin());
+        }
+        free_.push_back(Block{p, cap, dev});
+        cached_ += cap;
+        return true;
+    }
+    void trim() {
+        std::lock_guard<std::mutex> lock(m_);
+        for (auto& b : free_) cudaFree(b.p);
+        free_.clear();
+        cached_ = 0;
+    }
+
+private:
+    struct Block { void* p; size_t cap; int dev; };
+    DevPool() {
+        const char* e = std::getenv("SARLACC_POOL_MB");
+        long mb = 24576;
+        if (e) mb = std::atol(e);
+        limit_ = mb <= 0 ? 0 : (size_t)mb << 20;
+    }
+    std::mutex m_;
+    std::vector<Block> free_;
+    size_t cached_ = 0, limit_ = 0;
+};
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    int dev = 0;
     void reserve(size_t bytes) {
         if (bytes <= cap) return;
-        if (p) CUDA_CHECK(cudaFree(p));
-        p = nullptr;
-        cap = 0;
+        release();
+        CUDA_CHECK(cudaGetDevice(&dev));
         const size_t want = bytes + bytes / 8 + 256;
-        CUDA_CHECK(cudaMalloc(&p, want));
+        p = DevPool::instance().take(want, dev, &cap);
+        if (p) return;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {          /* the pool may be what fills the device: empty it and try once more */
+            cudaGetLastError();
+            DevPool::instance().trim();
+            p = nullptr;
+            CUDA_CHECK(cudaMalloc(&p, want));
+        }
         cap = want;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            int cur = 0;
+            cudaGetDevice(&cur);
+            if (cur != dev) cudaSetDevice(dev);
+            cudaDeviceSynchronize();     /* nothing in flight may still touch the block when someone else takes it */
+            if (!DevPool::instance().give(p, cap, dev)) cudaFree(p);
+            if (cur != dev) cudaSetDevice(cur);
+        }
         p = nullptr;
         cap = 0;
     }
@@ -1836,6 +1909,8 @@ int sarlacc_set_host_threads(int nthreads) {
     g_host_threads = nthreads;
     return 0;
 }
+
+void sarlacc_trim_device_memory(void) { DevPool::instance().trim(); }
 
 int64_t sarlacc_kernel_launches(int reset) {
     const long long v = g_launches.load();
