@@ -1,3 +1,4 @@
-exec > gpurun_out/run13.log 2>&1
-python -m pytest tests -m gpu -x -q -k "full_size or pipeline or resident or tune or thresholds" 2>&1 | tail -3
+exec > gpurun_out/run14.log 2>&1
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 python tools/run_c5.py --share 1250000 --batch 625000
+python bench.py --no-cpu | cut -c1-1500
