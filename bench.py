@@ -276,7 +276,11 @@ def main():
             pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()   # noqa: E731
             return ReadSet(pin(rs.seq_pool), rs.seq_off, pin(rs.qual_pool), rs.qual_off, rs.names)
 
-        sub_f, sub_b = pinned(sub_f), pinned(sub_b)
+        inputs_pinned = True
+        try:
+            sub_f, sub_b = pinned(sub_f), pinned(sub_b)
+        except RuntimeError:          # page-locking refused (memlock limit): the library stages the bytes itself
+            inputs_pinned = False
 
         sub_w = widths[:ne].astype(np.int32)
 
@@ -319,7 +323,7 @@ def main():
                "reads_per_step": ne, "ms_per_step": dt * 1000.0,
                "path": "sarlacc_adaptor_align_windows: pinned host CSR buffers -> H2D of the raw bytes -> device packer -> 4 alignments + "
                        "traceback + strand resolution/selection on device -> D2H of the kept rows",
-               "pageable_inputs_reads_per_s": world * ne / dt_pageable, "host_threads_per_rank": max(1, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))),
+               "inputs_pinned": inputs_pinned, "pageable_inputs_reads_per_s": world * ne / dt_pageable, "host_threads_per_rank": max(1, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))),
                "unfused_reads_per_s": world * ne / dt_unfused,
                "unfused_path": "4 x sarlacc_adaptor_align (the reference's four .Calls) + .resolve_strand on the host"}
 
