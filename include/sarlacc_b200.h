@@ -206,6 +206,9 @@ sarlacc_lists* sarlacc_umi_group(const uint8_t* umi1_pool, const int64_t* umi1_o
 sarlacc_lists* sarlacc_umi_neighbors(const uint8_t* umi1_pool, const int64_t* umi1_off, int64_t n, int threshold1,
                                      const uint8_t* umi2_pool, const int64_t* umi2_off, int threshold2,
                                      const int64_t* group_off, const int32_t* group_members, int64_t ngroups, int device);
+/* The clustering step alone, on the host -- SEXP cluster_umis_test(links) (src/cluster_umis_test.cpp:8-29, registered at
+ * src/init.cpp:24): n lists of 1-based neighbour indices (n+1 offsets), 1-based clusters out.  No device involved. */
+sarlacc_lists* sarlacc_cluster_umis(const int64_t* link_off, const int32_t* links, int64_t n);
 int64_t sarlacc_lists_count(const sarlacc_lists* r);
 int64_t sarlacc_lists_values(const sarlacc_lists* r);
 int     sarlacc_lists_fetch(const sarlacc_lists* r, int64_t* off, int32_t* values);

@@ -98,6 +98,8 @@ def _load():
         getattr(lib, name).restype = C.c_void_p
         getattr(lib, name).argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                        C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+    lib.sarlacc_cluster_umis.restype = C.c_void_p
+    lib.sarlacc_cluster_umis.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     lib.sarlacc_lists_count.restype = C.c_int64
     lib.sarlacc_lists_count.argtypes = [C.c_void_p]
     lib.sarlacc_lists_values.restype = C.c_int64

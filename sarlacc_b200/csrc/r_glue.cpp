@@ -1,5 +1,5 @@
-/* R-side glue: the four hot-path `.Call` entry points of sarlacc, re-implemented as thin SEXP unpackers over
- * the C ABI in include/sarlacc_b200.h.  Drop this file into the package's src/ in place of
+/* R-side glue: the four hot-path `.Call` entry points of sarlacc (and, at the end of the file, umi_group and
+ * cluster_umis_test), re-implemented as thin SEXP unpackers over the C ABI in include/sarlacc_b200.h.  Drop this file into the package's src/ in place of
  * adaptor_align.cpp, barcode_align.cpp, general_align.cpp and reference_align.{h,cpp}; src/init.cpp keeps its
  * registration table (src/init.cpp:9-35) unchanged, because the symbols, arities and return shapes are the
  * same.  NOT compiled in this repository (no R / Rcpp / Biostrings headers in the image) -- it depends only on
@@ -169,6 +169,111 @@ SEXP general_align(SEXP inputseq, SEXP inputqual, SEXP encoding, SEXP gapopen, S
     }
     UNPROTECT(1);
     return out;
+}
+
+}
+
+/* ---- UMI grouping: SEXP umi_group(umi1, thresh1, umi2, thresh2, pregroup) (src/umi_group.cpp:14-117, src/init.cpp:22)
+ * and SEXP cluster_umis_test(links) (src/cluster_umis_test.cpp:8-29, src/init.cpp:24).  Replaces src/umi_group.cpp and
+ * src/cluster_umis_test.cpp; R/umiGroup.R:21-22 keeps working unchanged because the result is nested per pre-group
+ * exactly like the reference's (a list of lists of integer vectors, unlisted one level by the R code). */
+namespace {
+
+struct UmiPool {   /* decoded ASCII, what process_DNA_input()->get_persistent yields (src/DNA_input.cpp:28-88) */
+    std::vector<uint8_t> pool;
+    std::vector<int64_t> off;
+    int64_t n = 0;
+    explicit UmiPool(SEXP x) {
+        off.push_back(0);
+        if (IS_S4_OBJECT(x)) {
+            XStringSet_holder h = hold_XStringSet(x);
+            n = get_length_from_XStringSet_holder(&h);
+            for (int64_t i = 0; i < n; ++i) {
+                Chars_holder e = get_elt_from_XStringSet_holder(&h, (int)i);
+                for (int k = 0; k < e.length; ++k) pool.push_back((uint8_t)DNAdecode(e.ptr[k]));
+                off.push_back((int64_t)pool.size());
+            }
+        } else {
+            n = LENGTH(x);
+            for (int64_t i = 0; i < n; ++i) {
+                SEXP e = STRING_ELT(x, i);
+                pool.insert(pool.end(), CHAR(e), CHAR(e) + LENGTH(e));
+                off.push_back((int64_t)pool.size());
+            }
+        }
+        if (pool.empty()) pool.push_back(0);
+    }
+};
+
+int integer_scalar(SEXP x, const char* what) {   /* check_integer_scalar, src/utils.cpp:14-16 */
+    if (!Rf_isInteger(x) || LENGTH(x) != 1) Rf_error("%s should be an integer scalar", what);
+    return INTEGER(x)[0];
+}
+
+/* sarlacc_lists -> VECSXP of INTSXP; frees the handle */
+SEXP lists_to_sexp(sarlacc_lists* h, int64_t from, int64_t to, const std::vector<int64_t>& off, const std::vector<int32_t>& val) {
+    (void)h;
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, (R_xlen_t)(to - from)));
+    for (int64_t c = from; c < to; ++c) {
+        SEXP v = Rf_allocVector(INTSXP, (R_xlen_t)(off[c + 1] - off[c]));
+        SET_VECTOR_ELT(out, (R_xlen_t)(c - from), v);
+        if (off[c + 1] > off[c]) std::memcpy(INTEGER(v), val.data() + off[c], sizeof(int32_t) * (size_t)(off[c + 1] - off[c]));
+    }
+    UNPROTECT(1);
+    return out;
+}
+
+void fetch_lists(sarlacc_lists* h, std::vector<int64_t>& off, std::vector<int32_t>& val) {
+    if (!h) Rf_error("%s", sarlacc_last_error());
+    off.assign((size_t)sarlacc_lists_count(h) + 1, 0);
+    val.assign((size_t)sarlacc_lists_values(h) + 1, 0);
+    sarlacc_lists_fetch(h, off.data(), val.data());
+    sarlacc_lists_free(h);
+}
+
+}
+
+extern "C" {
+
+SEXP umi_group(SEXP umi1, SEXP thresh1, SEXP umi2, SEXP thresh2, SEXP pregroup) {
+    UmiPool u1(umi1);
+    const int t1 = integer_scalar(thresh1, "threshold 1");
+    const bool two = umi2 != R_NilValue;
+    UmiPool u2(two ? umi2 : umi1);
+    if (two && u1.n != u2.n) Rf_error("'umi1' and 'umi2' should have the same length");   /* src/umi_group.cpp:27-29 */
+    const int t2 = integer_scalar(thresh2, "threshold 2");
+    const R_xlen_t ng = Rf_xlength(pregroup);
+    /* one library call per pre-group keeps the reference's nesting (a list per group) without a second index */
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, ng));
+    for (R_xlen_t g = 0; g < ng; ++g) {
+        SEXP cur = VECTOR_ELT(pregroup, g);
+        const int64_t goff[2] = {0, (int64_t)LENGTH(cur)};
+        std::vector<int64_t> off;
+        std::vector<int32_t> val;
+        fetch_lists(sarlacc_umi_group(u1.pool.data(), u1.off.data(), u1.n, t1, two ? u2.pool.data() : NULL, u2.off.data(), t2,
+                                      goff, INTEGER(cur), 1, /*device*/ 0), off, val);
+        SET_VECTOR_ELT(out, g, lists_to_sexp(NULL, 0, (int64_t)off.size() - 1, off, val));
+    }
+    UNPROTECT(1);
+    return out;
+}
+/* (With many small pre-groups, pass them all in ONE call -- group_off / members as CSR -- and re-nest by counting the
+ *  clusters per group: the device pass then covers every group at once.  sarlacc_b200/native.py: umi_group does that.) */
+
+SEXP cluster_umis_test(SEXP links) {
+    const R_xlen_t n = Rf_xlength(links);
+    std::vector<int64_t> loff(1, 0);
+    std::vector<int32_t> lval;
+    for (R_xlen_t i = 0; i < n; ++i) {
+        SEXP cur = VECTOR_ELT(links, i);
+        lval.insert(lval.end(), INTEGER(cur), INTEGER(cur) + LENGTH(cur));
+        loff.push_back((int64_t)lval.size());
+    }
+    if (lval.empty()) lval.push_back(0);
+    std::vector<int64_t> off;
+    std::vector<int32_t> val;
+    fetch_lists(sarlacc_cluster_umis(loff.data(), lval.data(), (int64_t)n), off, val);
+    return lists_to_sexp(NULL, 0, (int64_t)off.size() - 1, off, val);
 }
 
 }

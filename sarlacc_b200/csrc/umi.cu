@@ -517,6 +517,30 @@ static sarlacc_lists* umi_run(int mode, const uint8_t* pool1, const int64_t* off
     return res.release();
 }
 
+/* cluster_umis_test (src/cluster_umis_test.cpp:8-29): the host clustering alone, 1-based links in, 1-based clusters out */
+sarlacc_lists* sarlacc_cluster_umis(const int64_t* link_off, const int32_t* links, int64_t n)
+{
+    if (n < 0 || !link_off || (n > 0 && link_off[n] > 0 && !links)) { sarlacc::set_error("link lists must not be NULL"); return nullptr; }
+    if (n > 0x7fffffffLL) { sarlacc::set_error("too many reads"); return nullptr; }
+    std::vector<long long> off((size_t)n + 1);
+    for (int64_t i = 0; i <= n; ++i) off[(size_t)i] = link_off[i] - link_off[0];
+    std::vector<int32_t> nb((size_t)off[(size_t)n]);
+    for (size_t k = 0; k < nb.size(); ++k) {
+        const int32_t v = links[link_off[0] + (int64_t)k];
+        if (v < 1 || v > n) { sarlacc::set_error("link index out of range"); return nullptr; }
+        nb[k] = v - 1;
+    }
+    std::vector<std::vector<int32_t> > clusters;
+    const char* msg = nullptr;
+    if (!cluster_lists(off.data(), nb.data(), (int)n, clusters, &msg)) { sarlacc::set_error(msg); return nullptr; }
+    std::unique_ptr<sarlacc_lists> res(new sarlacc_lists());
+    for (auto& c : clusters) {
+        for (auto& x : c) ++x;
+        res->L.push(c);
+    }
+    return res.release();
+}
+
 sarlacc_lists* sarlacc_umi_group(const uint8_t* umi1_pool, const int64_t* umi1_off, int64_t n, int threshold1,
         const uint8_t* umi2_pool, const int64_t* umi2_off, int threshold2,
         const int64_t* group_off, const int32_t* group_members, int64_t ngroups, int device)

@@ -282,6 +282,29 @@ def _umi_call(fn, umi1, threshold1, umi2, threshold2, groups, device):
     return [vals[off[i]:off[i + 1]] for i in range(nl)]
 
 
+def _fetch_lists(h):
+    if not h:
+        raise SarlaccError(_lib.last_error())
+    try:
+        nl, nv = _lib.lib.sarlacc_lists_count(h), _lib.lib.sarlacc_lists_values(h)
+        off = np.zeros(nl + 1, np.int64)
+        vals = np.zeros(max(nv, 1), np.int32)
+        _lib.check(_lib.lib.sarlacc_lists_fetch(h, _lib._ptr(off), _lib._ptr(vals)))
+    finally:
+        _lib.lib.sarlacc_lists_free(h)
+    return [vals[off[i]:off[i + 1]] for i in range(nl)]
+
+
+def cluster_umis(links):
+    """.Call(cxx_cluster_umis_test, links) (src/cluster_umis_test.cpp:8-29): greedy clustering of 1-based neighbour lists
+    on the host (no device needed).  Returns a list of int32 arrays of 1-based indices."""
+    off = np.zeros(len(links) + 1, np.int64)
+    if len(links):
+        off[1:] = np.cumsum([len(x) for x in links])
+    vals = np.ascontiguousarray(np.concatenate([np.asarray(x, np.int32).reshape(-1) for x in links] + [np.zeros(1, np.int32)]))
+    return _fetch_lists(_lib.lib.sarlacc_cluster_umis(_lib._ptr(off), _lib._ptr(vals), C.c_int64(len(links))))
+
+
 def umi_group(umi1, threshold1, umi2=None, threshold2=None, groups=None, device=0):
     """.Call(cxx_umi_group, UMI1, threshold1, UMI2, threshold2, by.group) + unlist(recursive=FALSE)
     (src/umi_group.cpp:14-117, R/umiGroup.R:21-22): list of int32 arrays of 1-based read indices, one per cluster.

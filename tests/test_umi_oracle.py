@@ -104,3 +104,27 @@ def test_clustering_against_the_reference_tests_slow_version(umiref):
         key = lambda cl: sorted(tuple(sorted(c)) for c in cl)   # noqa: E731
         assert key(port) == key(ref) == key(real)
         assert port == real          # and the exact order, which only the C++ defines
+
+
+def test_host_clustering_entry_matches_the_reference(umiref):
+    """sarlacc_cluster_umis (the library's host clustering, no device) == the reference's cluster_umis_test on random
+    symmetric link sets (tests/testthat/test-umicluster.R:33-43), on asymmetric ones, and on its two error conditions."""
+    from sarlacc_b200 import native, SarlaccError
+    rng = np.random.default_rng(17)
+    for nn, dens, symmetric in ((20, 0.05, True), (50, 0.2, True), (50, 0.4, True), (200, 0.03, True), (300, 0.0, True), (60, 0.1, False)):
+        m = rng.random((nn, nn)) < dens / 2
+        if symmetric:
+            m = m | m.T
+        np.fill_diagonal(m, True)
+        links = [(np.nonzero(m[:, j])[0] + 1).tolist() for j in range(nn)]
+        for l in links:
+            rng.shuffle(l)                      # list order decides the order inside a cluster
+        got = [c.tolist() for c in native.cluster_umis(links)]
+        assert got == umiref.cluster(links)
+    assert native.cluster_umis([]) == []
+    with pytest.raises(SarlaccError, match="zero length read group"):
+        native.cluster_umis([[1, 2], []])
+    with pytest.raises(SarlaccError, match="single-read groups should contain only the read itself"):
+        native.cluster_umis([[1, 2], [1]])
+    with pytest.raises(SarlaccError, match="out of range"):
+        native.cluster_umis([[1, 3], [2]])
