@@ -253,6 +253,7 @@ struct Seqs {
         }
         return la < lb;
     }
+    bool same(int64_t a, int64_t b) const { return len(a) == len(b) && std::memcmp(ptr(a), ptr(b), (size_t)len(a)) == 0; }
 };
 
 /* cluster_umis (src/cluster_umis.cpp:7-112) over CSR lists of group-local indices.  Returns false with `msg` set on
@@ -388,6 +389,21 @@ static sarlacc_lists* umi_run(int mode, const uint8_t* pool1, const int64_t* off
         }
     }
     const long long E = (long long)ent.size();
+    /* Identical UMIs (PCR duplicates -- the reason UMIs exist) have identical neighbour lists, the reference's own
+     * shortcut in sorted_trie::find (src/sorted_trie.cpp:258-262).  With one UMI the sorted order makes them adjacent,
+     * so the device pass runs over the distinct sequences of each group and the lists are expanded on the host:
+     * a matched sequence contributes all its reads, in index order -- exactly the walk order.  (With two UMIs the
+     * order is (UMI2, index), which interleaves different UMI1s: no collapsing there.) */
+    const bool collapse = !two && std::getenv("SARLACC_UMI_NO_COLLAPSE") == nullptr;
+    std::vector<long long> ufirst;           /* entry index of every distinct sequence's first read (+ sentinel) */
+    std::vector<int32_t> uniq_of((size_t)E);
+    for (long long e = 0; e < E; ++e) {
+        const bool fresh = e == gstart[(size_t)e] || !collapse || !S1.same(ent[(size_t)e], ent[(size_t)e - 1]);
+        if (fresh) ufirst.push_back(e);
+        uniq_of[(size_t)e] = (int32_t)ufirst.size() - 1;
+    }
+    const long long U = (long long)ufirst.size();
+    ufirst.push_back(E);
     t_sorted = now();
     std::vector<long long> offs((size_t)E + 1, 0);
     std::vector<int32_t> nbrs;
@@ -399,36 +415,41 @@ static sarlacc_lists* umi_run(int mode, const uint8_t* pool1, const int64_t* off
         if (device < 0 || device >= ndev) { sarlacc::set_error("device index out of range"); return nullptr; }
         cudaSetDevice(device);
         const int W1 = std::max<int>(4, (int)((maxl1 + 3) & ~3LL)), W2 = two ? std::max<int>(4, (int)((maxl2 + 3) & ~3LL)) : 0;
-        std::vector<uint8_t> h1((size_t)E * W1, 0), h2((size_t)E * std::max(W2, 1), 0), hl1((size_t)E), hl2((size_t)E, 0), hf((size_t)E);
-        for (long long e = 0; e < E; ++e) {
+        std::vector<uint8_t> h1((size_t)U * W1, 0), h2((size_t)U * std::max(W2, 1), 0), hl1((size_t)U), hl2((size_t)U, 0), hf((size_t)U);
+        std::vector<int32_t> ugs((size_t)U), uge((size_t)U), uid((size_t)U);
+        for (long long u = 0; u < U; ++u) {
+            const long long e = ufirst[(size_t)u];
             const int64_t r = ent[(size_t)e];
-            std::memcpy(&h1[(size_t)e * W1], S1.ptr(r), (size_t)S1.len(r));
-            hl1[(size_t)e] = (uint8_t)S1.len(r);
+            std::memcpy(&h1[(size_t)u * W1], S1.ptr(r), (size_t)S1.len(r));
+            hl1[(size_t)u] = (uint8_t)S1.len(r);
             uint8_t f = S1.storable(r) ? 1 : 0;
             if (two) {
-                std::memcpy(&h2[(size_t)e * W2], S2.ptr(r), (size_t)S2.len(r));
-                hl2[(size_t)e] = (uint8_t)S2.len(r);
+                std::memcpy(&h2[(size_t)u * W2], S2.ptr(r), (size_t)S2.len(r));
+                hl2[(size_t)u] = (uint8_t)S2.len(r);
                 if (S2.storable(r)) f |= 2;
             }
-            hf[(size_t)e] = f;
+            hf[(size_t)u] = f;
+            ugs[(size_t)u] = uniq_of[(size_t)gstart[(size_t)e]];
+            uge[(size_t)u] = uniq_of[(size_t)gend[(size_t)e] - 1] + 1;
+            uid[(size_t)u] = (int32_t)u;
         }
         DevMem d1, d2, dl1, dl2, df, dgs, dge, dloc, dcnt, doff, dnb, dfirst;
-        bool ok = d1.alloc(h1.size()) && d2.alloc(h2.size()) && dl1.alloc(E) && dl2.alloc(E) && df.alloc(E) &&
-                  dgs.alloc(sizeof(int32_t) * E) && dge.alloc(sizeof(int32_t) * E) && dloc.alloc(sizeof(int32_t) * E) &&
-                  dcnt.alloc(sizeof(int32_t) * E) && doff.alloc(sizeof(long long) * (E + 1)) &&
-                  dfirst.alloc(sizeof(int32_t) * (size_t)E * kUmiCap);
+        bool ok = d1.alloc(h1.size()) && d2.alloc(h2.size()) && dl1.alloc(U) && dl2.alloc(U) && df.alloc(U) &&
+                  dgs.alloc(sizeof(int32_t) * U) && dge.alloc(sizeof(int32_t) * U) && dloc.alloc(sizeof(int32_t) * U) &&
+                  dcnt.alloc(sizeof(int32_t) * U) && doff.alloc(sizeof(long long) * (U + 1)) &&
+                  dfirst.alloc(sizeof(int32_t) * (size_t)U * kUmiCap);
         if (!ok) { sarlacc::set_error("CUDA error: out of device memory in the UMI pass"); return nullptr; }
         cudaStream_t st = nullptr;
         cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
         auto up = [&](DevMem& d, const void* h, size_t bytes) { cudaMemcpyAsync(d.p, h, bytes, cudaMemcpyHostToDevice, st); };
         up(d1, h1.data(), h1.size());
         if (two) up(d2, h2.data(), h2.size());
-        up(dl1, hl1.data(), (size_t)E);
-        up(dl2, hl2.data(), (size_t)E);
-        up(df, hf.data(), (size_t)E);
-        up(dgs, gstart.data(), sizeof(int32_t) * E);
-        up(dge, gend.data(), sizeof(int32_t) * E);
-        up(dloc, local.data(), sizeof(int32_t) * E);
+        up(dl1, hl1.data(), (size_t)U);
+        up(dl2, hl2.data(), (size_t)U);
+        up(df, hf.data(), (size_t)U);
+        up(dgs, ugs.data(), sizeof(int32_t) * U);
+        up(dge, uge.data(), sizeof(int32_t) * U);
+        up(dloc, uid.data(), sizeof(int32_t) * U);
         UmiArgs A;
         std::memset(&A, 0, sizeof(A));
         A.seq1 = d1.as<uint8_t>();
@@ -438,27 +459,29 @@ static sarlacc_lists* umi_run(int mode, const uint8_t* pool1, const int64_t* off
         A.flags = df.as<uint8_t>();
         A.gstart = dgs.as<int32_t>();
         A.gend = dge.as<int32_t>();
-        A.local = dloc.as<int32_t>();
+        A.local = dloc.as<int32_t>();      /* the lists name distinct sequences; reads are filled in below */
         A.W1 = W1;
         A.W2 = W2;
         A.limit1 = 2 * threshold1;       /* limit *= MULT, src/sorted_trie.cpp:227 */
         A.limit2 = 2 * threshold2;
-        A.E = E;
+        A.E = U;
         A.count = dcnt.as<int32_t>();
         A.first = dfirst.as<int32_t>();
         bool launched = launch_umi(A, false, st);
-        std::vector<int32_t> cnt((size_t)E);
-        cudaMemcpyAsync(cnt.data(), dcnt.p, sizeof(int32_t) * E, cudaMemcpyDeviceToHost, st);
+        std::vector<int32_t> cnt((size_t)U);
+        std::vector<long long> uoffs((size_t)U + 1, 0);
+        std::vector<int32_t> unbrs;
+        cudaMemcpyAsync(cnt.data(), dcnt.p, sizeof(int32_t) * U, cudaMemcpyDeviceToHost, st);
         cudaError_t ce = cudaStreamSynchronize(st);
         if (launched && ce == cudaSuccess) {
-            for (long long e = 0; e < E; ++e) offs[(size_t)e + 1] = offs[(size_t)e] + cnt[(size_t)e];
-            nbrs.resize((size_t)offs[(size_t)E]);
-            if (!dnb.alloc(sizeof(int32_t) * nbrs.size())) { cudaStreamDestroy(st); sarlacc::set_error("CUDA error: out of device memory for the UMI neighbour lists"); return nullptr; }
-            up(doff, offs.data(), sizeof(long long) * (E + 1));
+            for (long long u = 0; u < U; ++u) uoffs[(size_t)u + 1] = uoffs[(size_t)u] + cnt[(size_t)u];
+            unbrs.resize((size_t)uoffs[(size_t)U]);
+            if (!dnb.alloc(sizeof(int32_t) * unbrs.size())) { cudaStreamDestroy(st); sarlacc::set_error("CUDA error: out of device memory for the UMI neighbour lists"); return nullptr; }
+            up(doff, uoffs.data(), sizeof(long long) * (U + 1));
             A.offset = doff.as<long long>();
             A.neighbors = dnb.as<int32_t>();
             launch_umi(A, true, st);
-            if (!nbrs.empty()) cudaMemcpyAsync(nbrs.data(), dnb.p, sizeof(int32_t) * nbrs.size(), cudaMemcpyDeviceToHost, st);
+            if (!unbrs.empty()) cudaMemcpyAsync(unbrs.data(), dnb.p, sizeof(int32_t) * unbrs.size(), cudaMemcpyDeviceToHost, st);
             ce = cudaStreamSynchronize(st);
             sarlacc::count_launches(2);
         }
@@ -467,6 +490,25 @@ static sarlacc_lists* umi_run(int mode, const uint8_t* pool1, const int64_t* off
         if (ce != cudaSuccess || (ce = cudaGetLastError()) != cudaSuccess) {
             sarlacc::set_error(std::string("CUDA error: ") + cudaGetErrorString(ce) + " in the UMI neighbour pass");
             return nullptr;
+        }
+        /* from distinct sequences back to reads: every read of a matched sequence, in entry (= index) order */
+        for (long long e = 0; e < E; ++e) {
+            const long long u = uniq_of[(size_t)e];
+            long long c = 0;
+            for (long long k = uoffs[(size_t)u]; k < uoffs[(size_t)u + 1]; ++k) {
+                const long long v = unbrs[(size_t)k];
+                c += ufirst[(size_t)v + 1] - ufirst[(size_t)v];
+            }
+            offs[(size_t)e + 1] = offs[(size_t)e] + c;
+        }
+        nbrs.resize((size_t)offs[(size_t)E]);
+        for (long long e = 0; e < E; ++e) {
+            const long long u = uniq_of[(size_t)e];
+            long long at = offs[(size_t)e];
+            for (long long k = uoffs[(size_t)u]; k < uoffs[(size_t)u + 1]; ++k) {
+                const long long v = unbrs[(size_t)k];
+                for (long long e2 = ufirst[(size_t)v]; e2 < ufirst[(size_t)v + 1]; ++e2) nbrs[(size_t)at++] = local[(size_t)e2];
+            }
         }
     }
 
@@ -512,8 +554,8 @@ static sarlacc_lists* umi_run(int mode, const uint8_t* pool1, const int64_t* off
         }
         e0 += cur;
     }
-    if (dbg) std::fprintf(stderr, "[sarlacc] umi: sort %.1f ms, pack + device passes %.1f ms, lists + clustering %.1f ms (%lld reads in multi-read groups, %zu neighbours)\n",
-                          (t_sorted - t_begin) * 1e3, (t_device - t_sorted) * 1e3, (now() - t_device) * 1e3, E, nbrs.size());
+    if (dbg) std::fprintf(stderr, "[sarlacc] umi: sort %.1f ms, pack + device passes %.1f ms, lists + clustering %.1f ms (%lld reads in multi-read groups, %lld distinct sequences, %zu neighbours)\n",
+                          (t_sorted - t_begin) * 1e3, (t_device - t_sorted) * 1e3, (now() - t_device) * 1e3, E, U, nbrs.size());
     return res.release();
 }
 
