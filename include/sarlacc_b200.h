@@ -10,9 +10,15 @@
  *     barcode_align            src/barcode_align.cpp:10-44      sarlacc_barcode_align
  *     general_align            src/general_align.cpp:10-62      sarlacc_general_align
  *
- * plus one fused entry that folds the per-barcode R loop of R/barcodeAlign.R:20-35 into one launch
- * (sarlacc_barcode_align_multi) and a "resident" variant of the same calls that keeps packed read
- * windows in HBM between calls (what adaptorAlign -> getAdaptorThresholds -> tuneAlignment re-use).
+ *     umi_group                src/umi_group.cpp:14-117         sarlacc_umi_group          (init.cpp:23)
+ *     cluster_umis_test        src/cluster_umis_test.cpp:8-29   sarlacc_cluster_umis       (init.cpp:25)
+ *     fast_levdist_test        src/sorted_trie.cpp:307-337      sarlacc_umi_neighbors      (init.cpp:24)
+ *
+ * plus fused entries that fold R-level loops into one device pass -- sarlacc_barcode_align_multi (the per-barcode
+ * loop of R/barcodeAlign.R:20-35), sarlacc_adaptor_align_windows / sarlacc_adaptor_align_reads (.align_AA_internal,
+ * R/adaptorAlign.R:178-199) --, a "resident" variant of the same calls that keeps packed read windows in HBM between
+ * calls (what adaptorAlign -> getAdaptorThresholds -> tuneAlignment re-use), and host-side helpers: FASTQ ingest
+ * (sarlacc_fastq_*, standing in for ShortRead::FastqStreamer, R/adaptorAlign.R:26,36) and the packer test hook.
  *
  * Plain pointers and sizes only: no R, Rcpp, torch or CUDA types appear in any signature.  The R-side
  * glue a maintainer would add (SEXP unpacking -> these calls) is shown in INTEGRATION.md and kept as
@@ -188,7 +194,7 @@ double sarlacc_resident_forward_ms(sarlacc_resident* r);
 
 /* ---- UMI grouping ----------------------------------------------------------------
  * Replaces SEXP umi_group(umi1, thresh1, umi2, thresh2, pregroup) (src/umi_group.cpp:14-117, registered at
- * src/init.cpp:22) together with unlist(out, recursive=FALSE) of R/umiGroup.R:22: the bounded masked-Levenshtein
+ * src/init.cpp:23) together with unlist(out, recursive=FALSE) of R/umiGroup.R:22: the bounded masked-Levenshtein
  * neighbour search of src/sorted_trie.cpp runs as an all-pairs pass on the device, the greedy clustering of
  * src/cluster_umis.cpp on the host.  UMIs are ASCII (the decoded form process_DNA_input yields, src/DNA_input.cpp:64-88)
  * as one pool + n+1 offsets; umi2_pool may be NULL (one UMI).  Pre-groups are given like R's by.group list: ngroups+1
@@ -207,7 +213,7 @@ sarlacc_lists* sarlacc_umi_neighbors(const uint8_t* umi1_pool, const int64_t* um
                                      const uint8_t* umi2_pool, const int64_t* umi2_off, int threshold2,
                                      const int64_t* group_off, const int32_t* group_members, int64_t ngroups, int device);
 /* The clustering step alone, on the host -- SEXP cluster_umis_test(links) (src/cluster_umis_test.cpp:8-29, registered at
- * src/init.cpp:24): n lists of 1-based neighbour indices (n+1 offsets), 1-based clusters out.  No device involved. */
+ * src/init.cpp:25): n lists of 1-based neighbour indices (n+1 offsets), 1-based clusters out.  No device involved. */
 sarlacc_lists* sarlacc_cluster_umis(const int64_t* link_off, const int32_t* links, int64_t n);
 int64_t sarlacc_lists_count(const sarlacc_lists* r);
 int64_t sarlacc_lists_values(const sarlacc_lists* r);

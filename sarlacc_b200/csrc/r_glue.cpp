@@ -173,8 +173,8 @@ SEXP general_align(SEXP inputseq, SEXP inputqual, SEXP encoding, SEXP gapopen, S
 
 }
 
-/* ---- UMI grouping: SEXP umi_group(umi1, thresh1, umi2, thresh2, pregroup) (src/umi_group.cpp:14-117, src/init.cpp:22)
- * and SEXP cluster_umis_test(links) (src/cluster_umis_test.cpp:8-29, src/init.cpp:24).  Replaces src/umi_group.cpp and
+/* ---- UMI grouping: SEXP umi_group(umi1, thresh1, umi2, thresh2, pregroup) (src/umi_group.cpp:14-117, src/init.cpp:23)
+ * and SEXP cluster_umis_test(links) (src/cluster_umis_test.cpp:8-29, src/init.cpp:25).  Replaces src/umi_group.cpp and
  * src/cluster_umis_test.cpp; R/umiGroup.R:21-22 keeps working unchanged because the result is nested per pre-group
  * exactly like the reference's (a list of lists of integer vectors, unlisted one level by the R code). */
 namespace {
