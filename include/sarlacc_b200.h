@@ -12,7 +12,7 @@
  *
  *     umi_group                src/umi_group.cpp:14-117         sarlacc_umi_group          (init.cpp:23)
  *     cluster_umis_test        src/cluster_umis_test.cpp:8-29   sarlacc_cluster_umis       (init.cpp:25)
- *     fast_levdist_test        src/sorted_trie.cpp:307-337      sarlacc_umi_neighbors      (init.cpp:24)
+ *     fast_levdist_test        src/sorted_trie.cpp:302-332      sarlacc_umi_neighbors      (init.cpp:24)
  *
  * plus fused entries that fold R-level loops into one device pass -- sarlacc_barcode_align_multi (the per-barcode
  * loop of R/barcodeAlign.R:20-35), sarlacc_adaptor_align_windows / sarlacc_adaptor_align_reads (.align_AA_internal,
@@ -204,7 +204,7 @@ double sarlacc_resident_forward_ms(sarlacc_resident* r);
  * Returns NULL with sarlacc_last_error() set on failure; the reference's messages are kept ("single-read groups
  * should contain only the read itself", "zero length read group", "'umi1' and 'umi2' should have the same length").
  * sarlacc_umi_neighbors returns the neighbour lists themselves (one vector per read of every pre-group, in group
- * order) -- with a single pre-group 1..n that is fast_levdist_test(seqs, limit, TRUE) (src/sorted_trie.cpp:307-337). */
+ * order) -- with a single pre-group 1..n that is fast_levdist_test(seqs, limit, TRUE) (src/sorted_trie.cpp:302-332). */
 typedef struct sarlacc_lists sarlacc_lists;
 sarlacc_lists* sarlacc_umi_group(const uint8_t* umi1_pool, const int64_t* umi1_off, int64_t n, int threshold1,
                                  const uint8_t* umi2_pool, const int64_t* umi2_off, int threshold2,

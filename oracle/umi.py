@@ -89,7 +89,7 @@ class UmiRef:
 
 
 # ---------------------------------------------------------------------------------------------- restatement
-TRIE_ALPHABET = "ACGTN"      # src/sorted_trie.cpp:10 (children are visited in this order, :203-208)
+TRIE_ALPHABET = "ACGTN"      # src/sorted_trie.cpp:10 (children are visited in this order, :178-183)
 
 
 def edit_score(a, b):
@@ -100,10 +100,10 @@ def edit_score(a, b):
 
 
 def lev2(s, t):
-    """Twice the masked Levenshtein distance: the DP of src/sorted_trie.cpp:149-153 (indel = mismatch = 2)."""
-    prev = [2 * i for i in range(len(s) + 1)]                       # :220-226
+    """Twice the masked Levenshtein distance: the DP of src/sorted_trie.cpp:134-138 (indel = mismatch = 2)."""
+    prev = [2 * i for i in range(len(s) + 1)]                       # :196-202
     for d, tb in enumerate(t, 1):
-        cur = [prev[0] + 2] + [0] * len(s)                          # :124
+        cur = [prev[0] + 2] + [0] * len(s)                          # :111
         for i in range(1, len(s) + 1):
             cur[i] = min(prev[i] + 2, cur[i - 1] + 2, prev[i - 1] + edit_score(s[i - 1], tb))
         prev = cur
@@ -117,17 +117,17 @@ def trie_key(s):
 def port_levdist(seqs, limit):
     """What sorted_trie::find returns for every sequence (0-based lists): the stored sequences within `limit`, in the
     order the trie walk meets them -- a node's own indices (insertion order) before its children, children in ACGTN
-    order (src/sorted_trie.cpp:175-208), i.e. sorted by (sequence under ACGTN, index).  Sequences with any other
-    character are never stored (the switch of :56-72 has no default) but can still be queried."""
+    order (src/sorted_trie.cpp:152-185), i.e. sorted by (sequence under ACGTN, index).  Sequences with any other
+    character are never stored (the switch of :53-69 has no default) but can still be queried."""
     stored = [i for i, s in enumerate(seqs) if all(c in TRIE_ALPHABET for c in s)]
     stored.sort(key=lambda i: (trie_key(seqs[i]), i))
     return [[j for j in stored if lev2(seqs[i], seqs[j]) <= 2 * limit] for i in range(len(seqs))]
 
 
 def port_cluster(storage):
-    """cluster_umis, src/cluster_umis.cpp:7-112, 0-based.  Solo reads first (:20-42), then repeatedly the node with
-    the most unclaimed neighbours, LAST index on ties (:58-66), absorbing its unclaimed neighbours in list order and
-    decrementing the counts of their neighbours (:76-97)."""
+    """cluster_umis, src/cluster_umis.cpp:7-112, 0-based.  Solo reads first (:20-45), then repeatedly the node with
+    the most unclaimed neighbours, LAST index on ties (:62-69), absorbing its unclaimed neighbours in list order and
+    decrementing the counts of their neighbours (:76-100)."""
     n = len(storage)
     remaining = [len(x) for x in storage]
     out = []
@@ -172,14 +172,14 @@ def port_umi_group(umi1, threshold1=3, umi2=None, threshold2=None, groups=None):
         groups = [list(range(1, n + 1))]
     out = []
     for g in groups:
-        if len(g) == 1:                                             # :37-40
+        if len(g) == 1:                                             # :39-42
             out.append(list(g))
             continue
         s1 = [umi1[i - 1] for i in g]
         m1 = port_levdist(s1, threshold1)
         if umi2 is None:
             storage = m1
-        else:                                                       # :63-101: trie2 order, kept if also a UMI1 match
+        else:                                                       # :65-101: trie2 order, kept if also a UMI1 match
             s2 = [umi2[i - 1] for i in g]
             m2 = port_levdist(s2, threshold2)
             storage = [[x for x in m2[k] if x in set(m1[k])] for k in range(len(g))]

@@ -1,7 +1,7 @@
 /* TEST INFRASTRUCTURE ONLY -- not part of the product.
  *
  * Calls the reference's OWN UMI-grouping entry points -- umi_group (src/umi_group.cpp:14-117), fast_levdist_test
- * (src/sorted_trie.cpp:307-337) and cluster_umis_test (src/cluster_umis_test.cpp:8-29) -- compiled verbatim from
+ * (src/sorted_trie.cpp:302-332) and cluster_umis_test (src/cluster_umis_test.cpp:8-29) -- compiled verbatim from
  * /root/reference/src against the toy R object model of oracle/rshim/.  Nothing is restated here: this file only
  * builds the argument objects and flattens the returned list of integer vectors.
  * Results are kept in a static holder and fetched with a second call (sizes are not known up front).  Not thread-safe.

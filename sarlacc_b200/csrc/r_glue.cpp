@@ -240,7 +240,7 @@ SEXP umi_group(SEXP umi1, SEXP thresh1, SEXP umi2, SEXP thresh2, SEXP pregroup) 
     const int t1 = integer_scalar(thresh1, "threshold 1");
     const bool two = umi2 != R_NilValue;
     UmiPool u2(two ? umi2 : umi1);
-    if (two && u1.n != u2.n) Rf_error("'umi1' and 'umi2' should have the same length");   /* src/umi_group.cpp:27-29 */
+    if (two && u1.n != u2.n) Rf_error("'umi1' and 'umi2' should have the same length");   /* src/umi_group.cpp:25-29 */
     const int t2 = integer_scalar(thresh2, "threshold 2");
     const R_xlen_t ng = Rf_xlength(pregroup);
     /* one library call per pre-group keeps the reference's nesting (a list per group) without a second index */

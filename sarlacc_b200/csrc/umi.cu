@@ -5,14 +5,14 @@
  *   1. for every UMI s, the stored UMIs t with lev2(s, t) <= 2 * threshold, where lev2 is the edit distance with
  *      indel = mismatch = 2 and "N against anything" = 1 (get_edit_score, src/sorted_trie.cpp:15-21), listed in the
  *      order the trie walk meets them: sorted by (sequence under A<C<G<T<N, shorter prefix first, insertion index)
- *      (src/sorted_trie.cpp:175-208); with two UMIs, the UMI2 list filtered by membership in the UMI1 list
- *      (src/umi_group.cpp:63-101);
+ *      (src/sorted_trie.cpp:152-185); with two UMIs, the UMI2 list filtered by membership in the UMI1 list
+ *      (src/umi_group.cpp:65-101);
  *   2. greedy clustering of those lists (cluster_umis, src/cluster_umis.cpp:7-112).
  *
  * Here step 1 is an all-pairs pass on the GPU: the reads of every pre-group are sorted once into trie order on the
  * host, one thread takes one query UMI and walks its group's candidates in that order, running the reference's DP
  * row by row in registers (row = one candidate base, columns = query positions) with the trie's own pruning rule
- * as early exit (a row whose minimum exceeds the limit cannot come back, src/sorted_trie.cpp:182-201).  Two passes:
+ * as early exit (a row whose minimum exceeds the limit cannot come back, src/sorted_trie.cpp:160-176).  Two passes:
  * count, exclusive scan on the host, fill -- so the lists come out dense, in order, without atomics.
  * Step 2 is inherently sequential (each pick changes the counts the next pick depends on) and stays on the host,
  * with a lazy max-heap instead of the reference's O(n) scan per cluster; ties resolve identically (largest index).
@@ -64,25 +64,25 @@ __device__ __forceinline__ bool within(const uint32_t* qw, int lq, const uint8_t
     if (2 * dl > limit) return false;
     int row[MAXQ + 1];
 #pragma unroll
-    for (int i = 0; i <= MAXQ; ++i) row[i] = 2 * i;                       /* src/sorted_trie.cpp:220-226 */
+    for (int i = 0; i <= MAXQ; ++i) row[i] = 2 * i;                       /* src/sorted_trie.cpp:196-202 */
     for (int d = 0; d < lt; ++d) {
         const unsigned tb = cand[d];
         const bool tn = tb == 'N';
         int diag = row[0];
-        row[0] = diag + 2;                                                 /* :124 */
+        row[0] = diag + 2;                                                 /* :111 */
         int rmin = row[0];
 #pragma unroll
         for (int i = 1; i <= MAXQ; ++i) {
             const unsigned qb = (qw[(i - 1) >> 2] >> (8 * ((i - 1) & 3))) & 0xffu;
             const int sc = (tn || qb == 'N') ? 1 : (qb == tb ? 0 : 2);    /* get_edit_score, :15-21 */
             const int up = row[i];
-            const int v = min(min(up + 2, row[i - 1] + 2), diag + sc);    /* :149-153 */
+            const int v = min(min(up + 2, row[i - 1] + 2), diag + sc);    /* :134-138 */
             diag = up;
             row[i] = v;
             rmin = min(rmin, v);
         }
         /* cells past the query's end only ever derive from real ones plus costs, so a row minimum above the limit
-         * is final (the trie's pruning rule, :182-201) */
+         * is final (the trie's pruning rule, :160-176) */
         if (rmin > limit) return false;
     }
     int res = 0;
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kUmiBlock) umi_neighbors(const UmiArgs A) {
     }
     const int gs = A.gstart[e], ge = A.gend[e];
     for (int j = gs; j < ge; ++j) {
-        if ((A.flags[j] & need) != need) continue;          /* never inserted into the trie (src/sorted_trie.cpp:56-72) */
+        if ((A.flags[j] & need) != need) continue;          /* never inserted into the trie (src/sorted_trie.cpp:53-69) */
         /* UMI2 first when present (its list drives the order, UMI1 filters) */
         if (A.seq2 && !within_any<MAXQ2>(q2, l2, A.seq2 + (long long)j * A.W2, A.len2[j], A.limit2)) continue;
         if (!within_any<MAXQ1>(q1, l1, A.seq1 + (long long)j * A.W1, A.len1[j], A.limit1)) continue;
@@ -222,7 +222,7 @@ struct Lists {   /* a list of integer vectors, flattened */
     }
 };
 
-inline int trie_rank(uint8_t c) {   /* children order of the trie: src/sorted_trie.cpp:10,56-72 */
+inline int trie_rank(uint8_t c) {   /* children order of the trie: src/sorted_trie.cpp:10,53-69 */
     switch (c) {
         case 'A': return 0;
         case 'C': return 1;
@@ -261,7 +261,7 @@ struct Seqs {
 bool cluster_lists(const long long* off, const int32_t* nb, int n, std::vector<std::vector<int32_t> >& out, const char** msg) {
     std::vector<int64_t> remaining((size_t)n);
     std::vector<char> in_play((size_t)n, 0);
-    typedef std::pair<int64_t, int32_t> Key;   /* (remaining, index): the reference's max_element order, :58-66 */
+    typedef std::pair<int64_t, int32_t> Key;   /* (remaining, index): the reference's max_element order, :62-69 */
     std::priority_queue<Key> heap;
     for (int a = 0; a < n; ++a) {
         const int64_t cur = off[a + 1] - off[a];
@@ -269,11 +269,11 @@ bool cluster_lists(const long long* off, const int32_t* nb, int n, std::vector<s
         if (cur > 1) {
             in_play[a] = 1;
             heap.push(Key(cur, a));
-        } else if (cur == 1) {                                            /* :24-38 */
+        } else if (cur == 1) {                                            /* :26-37 */
             if (nb[off[a]] != a) { *msg = "single-read groups should contain only the read itself"; return false; }
             out.push_back(std::vector<int32_t>(1, a));
         } else {
-            *msg = "zero length read group";                              /* :39-41 */
+            *msg = "zero length read group";                              /* :38-40 */
             return false;
         }
     }
@@ -282,10 +282,10 @@ bool cluster_lists(const long long* off, const int32_t* nb, int n, std::vector<s
         heap.pop();
         const int32_t v = top.second;
         if (!in_play[v] || remaining[v] != top.first) continue;           /* stale entry */
-        if (top.first == 0) continue;                                     /* wiped-out node, :47-56 */
-        in_play[v] = 0;                                                   /* pop_back of :70-71 */
+        if (top.first == 0) continue;                                     /* wiped-out node, :50-56 */
+        in_play[v] = 0;                                                   /* pop_back of :73-74 */
         std::vector<int32_t> cluster;
-        for (long long k = off[v]; k < off[v + 1]; ++k) {                 /* :74-97 */
+        for (long long k = off[v]; k < off[v + 1]; ++k) {                 /* :76-100 */
             const int32_t w = nb[k];
             if (remaining[w] == 0) continue;
             cluster.push_back(w);
@@ -341,7 +341,7 @@ static sarlacc_lists* umi_run(int mode, const uint8_t* pool1, const int64_t* off
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now();
     double t_sorted = t_begin, t_device = t_begin;
-    /* entries = members of pre-groups with more than one read (src/umi_group.cpp:37-40), sorted per group */
+    /* entries = members of pre-groups with more than one read (src/umi_group.cpp:39-42), sorted per group */
     std::vector<int64_t> ent;            /* 0-based read index */
     std::vector<int32_t> local, gstart, gend;
     int64_t maxl1 = 0, maxl2 = 0;
@@ -353,7 +353,7 @@ static sarlacc_lists* umi_run(int mode, const uint8_t* pool1, const int64_t* off
         if (b - a == 0 || (mode == 0 && b - a < 2)) continue;
         const size_t base = ent.size();
         std::vector<int32_t> ord((size_t)(b - a));
-        const Seqs& So = two ? S2 : S1;   /* with two UMIs the UMI2 trie drives the order (:86-100) */
+        const Seqs& So = two ? S2 : S1;   /* with two UMIs the UMI2 trie drives the order (umi_group.cpp:82-101) */
         bool short_keys = true;
         for (int64_t k = a; k < b && short_keys; ++k) short_keys = So.len(members[k] - 1) <= 21;
         if (short_keys) {
@@ -390,7 +390,7 @@ static sarlacc_lists* umi_run(int mode, const uint8_t* pool1, const int64_t* off
     }
     const long long E = (long long)ent.size();
     /* Identical UMIs (PCR duplicates -- the reason UMIs exist) have identical neighbour lists, the reference's own
-     * shortcut in sorted_trie::find (src/sorted_trie.cpp:258-262).  With one UMI the sorted order makes them adjacent,
+     * shortcut in sorted_trie::find (src/sorted_trie.cpp:253-257).  With one UMI the sorted order makes them adjacent,
      * so the device pass runs over the distinct sequences of each group and the lists are expanded on the host:
      * a matched sequence contributes all its reads, in index order -- exactly the walk order.  (With two UMIs the
      * order is (UMI2, index), which interleaves different UMI1s: no collapsing there.) */
@@ -462,7 +462,7 @@ static sarlacc_lists* umi_run(int mode, const uint8_t* pool1, const int64_t* off
         A.local = dloc.as<int32_t>();      /* the lists name distinct sequences; reads are filled in below */
         A.W1 = W1;
         A.W2 = W2;
-        A.limit1 = 2 * threshold1;       /* limit *= MULT, src/sorted_trie.cpp:227 */
+        A.limit1 = 2 * threshold1;       /* limit *= MULT, src/sorted_trie.cpp:203 */
         A.limit2 = 2 * threshold2;
         A.E = U;
         A.count = dcnt.as<int32_t>();
@@ -520,7 +520,7 @@ static sarlacc_lists* umi_run(int mode, const uint8_t* pool1, const int64_t* off
         const int64_t a = group_off[g], b = group_off[g + 1];
         const int cur = (int)(b - a);
         if (cur == 0) continue;                     /* an empty pre-group yields an empty list: nothing after unlist() */
-        if (cur == 1 && mode == 0) {                /* src/umi_group.cpp:37-40 */
+        if (cur == 1 && mode == 0) {                /* src/umi_group.cpp:39-42 */
             res->L.push(std::vector<int32_t>(1, members[a]));
             continue;
         }

@@ -259,7 +259,7 @@ def _umi_call(fn, umi1, threshold1, umi2, threshold2, groups, device):
     if umi2 is not None:
         p2, o2 = _string_pool(umi2)
         if len(o2) - 1 != n:
-            raise SarlaccError("'umi1' and 'umi2' should have the same length")     # src/umi_group.cpp:27-29
+            raise SarlaccError("'umi1' and 'umi2' should have the same length")     # src/umi_group.cpp:25-29
         if p2.size == 0:
             p2 = np.zeros(1, np.uint8)
     if groups is None:
@@ -314,7 +314,7 @@ def umi_group(umi1, threshold1, umi2=None, threshold2=None, groups=None, device=
 
 def umi_neighbors(umi1, threshold1, umi2=None, threshold2=None, groups=None, device=0):
     """The neighbour lists umi_group clusters (1-based, trie order); with the default single group this is
-    .Call(cxx_fast_levdist_test, seqs, limit, TRUE) (src/sorted_trie.cpp:307-337)."""
+    .Call(cxx_fast_levdist_test, seqs, limit, TRUE) (src/sorted_trie.cpp:302-332)."""
     return _umi_call(_lib.lib.sarlacc_umi_neighbors, umi1, threshold1, umi2, threshold1 if threshold2 is None else threshold2, groups, device)
 
 

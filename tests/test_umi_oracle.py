@@ -1,7 +1,7 @@
 """CPU-only: pins the UMI-grouping oracles.  oracle/_ref/libsarlacc_umi_ref.so is the reference's own
 umi_group / sorted_trie / cluster_umis compiled verbatim; oracle/umi.py:port_* is the restatement.  Checked here:
 restatement == reference on seeded inputs, both == the committed golden vectors, and the reference tests' own slow R
-check (tests/testthat/test-umicluster.R:4-31) restated."""
+check (tests/testthat/test-umicluster.R:4-29) restated."""
 import json
 import os
 
@@ -62,7 +62,7 @@ def test_known_answers(umiref):
     # N is half a mismatch against anything, N itself included (src/sorted_trie.cpp:15-21)
     assert U.lev2("ACGT", "ACGT") == 0 and U.lev2("ACGT", "ACGA") == 2 and U.lev2("ACNT", "ACGT") == 1
     assert U.lev2("NNNN", "NNNN") == 4 and U.lev2("ACGT", "ACG") == 2 and U.lev2("", "AC") == 4
-    # trie order: ACGA < ACGT(1) < ACGT(4); the solo read comes first (src/cluster_umis.cpp:20-42)
+    # trie order: ACGA < ACGT(1) < ACGT(4); the solo read comes first (src/cluster_umis.cpp:20-45)
     for f in (umiref.umi_group, U.port_umi_group):
         assert f(["ACGT", "ACGA", "TTTT", "ACGT"], 1) == [[3], [2, 1, 4]]
     # a read masked so heavily that it is not within the limit of itself
@@ -74,7 +74,7 @@ def test_known_answers(umiref):
 
 
 def test_clustering_against_the_reference_tests_slow_version(umiref):
-    """tests/testthat/test-umicluster.R:4-31 (REF) and :33-43 (MOCKUP), compared as sets like COMPARE (:45-51)."""
+    """tests/testthat/test-umicluster.R:4-29 (REF) and :32-41 (MOCKUP), compared as sets like COMPARE (:43-49)."""
     from oracle import umi as U
     rng = np.random.default_rng(5)
 
@@ -108,7 +108,7 @@ def test_clustering_against_the_reference_tests_slow_version(umiref):
 
 def test_host_clustering_entry_matches_the_reference(umiref):
     """sarlacc_cluster_umis (the library's host clustering, no device) == the reference's cluster_umis_test on random
-    symmetric link sets (tests/testthat/test-umicluster.R:33-43), on asymmetric ones, and on its two error conditions."""
+    symmetric link sets (tests/testthat/test-umicluster.R:32-41), on asymmetric ones, and on its two error conditions."""
     from sarlacc_b200 import native, SarlaccError
     rng = np.random.default_rng(17)
     for nn, dens, symmetric in ((20, 0.05, True), (50, 0.2, True), (50, 0.4, True), (200, 0.03, True), (300, 0.0, True), (60, 0.1, False)):

@@ -1,5 +1,5 @@
 """Seeded UMI test inputs shared by the CPU oracle tests, the golden generator and the GPU parity tests.
-SEQSIM follows tests/testthat/test-umicluster.R:86-96 (a random reference, 10 % substitutions per copy), extended with
+SEQSIM follows tests/testthat/test-umicluster.R:94-104 (a random reference, 10 % substitutions per copy), extended with
 indels, N masking and junk characters to reach the corners of src/sorted_trie.cpp."""
 import numpy as np
 
