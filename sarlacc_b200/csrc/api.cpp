@@ -165,13 +165,15 @@ struct Plan {
     bool has_alt = false;
     int alt_row = 4;
     int kinds = 1;
-    int G = 1, C = 1;
+    int G = 1, C = 1;         /* lanes per alignment x columns per lane of the wavefront kernels */
+    bool solo = false;        /* windows of 48+ rows run one thread per alignment (G = 1, C = L) instead: references of 20-24 bases */
     bool wide_ok = false;     /* score-only runs may use 14-18 columns per lane */
     std::vector<int32_t> sec_starts, sec_ends;
 };
 
 bool choose_geometry(Plan& P) {
     const char* force = std::getenv("SARLACC_FORCE_GC");
+    P.solo = false;
     if (force) {
         int g = 0, c = 0;
         if (std::sscanf(force, "%d,%d", &g, &c) == 2 && g >= 1 && g <= 32 && (g & (g - 1)) == 0 && c >= 1 && c <= kMaxC && (c <= 12 || !(c & 1)) &&
@@ -181,6 +183,9 @@ bool choose_geometry(Plan& P) {
             return true;
         }
     }
+    /* 20-24 columns: one thread per alignment, all columns in its registers -- no shuffles, no boundary selects, the
+     * row overhead spread over twice the columns of the two-lane split (profiles/r02_history.md) */
+    P.solo = P.L >= kSoloMinC && P.L <= kSoloMaxC && P.nref == 1 && std::getenv("SARLACC_NO_SOLO") == nullptr;
     double best = 1e300;
     for (int g = 1; g <= kMaxGroup; g *= 2) {
         const int c = (P.L + g - 1) / g;
@@ -766,12 +771,31 @@ size_t scratch_budget_bytes() {
     return mb << 20;
 }
 
+/* Two rows per lane step (wf_forward2) pay off on long windows; on barcode-length reads (a couple of dozen rows per
+ * alignment, lanes of a warp at different phases of different alignments) nearly every step is the masked one and the
+ * single-row kernel is ~2x faster (1 M x 96 barcodes: 0.11 s vs 0.20 s).  SARLACC_PAIR=0/1 forces either (A/B tests). */
+int pair_rows_default(int maxlen = 1 << 30) {
+    const char* e = std::getenv("SARLACC_PAIR");
+    if (e) return std::atoi(e);
+    return maxlen >= 48 ? 1 : 0;
+}
+
+/* The geometry a run over windows of at most `maxlen` rows uses: the solo kernel is a row-pair kernel whose lanes are
+ * independent alignments, so it wants windows long enough to stay in step (the same bound as pair_rows_default). */
+struct Geometry { int G, C; bool solo; int pair; };
+Geometry geometry_for(const Plan& P, int maxlen = 1 << 30) {
+    if (P.solo && pair_rows_default(maxlen)) return Geometry{1, P.L, true, 1};
+    return Geometry{P.G, P.C, false, pair_rows_default(maxlen)};
+}
+
 /* How many alignments of at most `maxlen` rows one sub-launch may cover under the scratch budget. */
 long long sub_chunk(const Plan& P, int maxlen, bool trace, long long n) {
     size_t per = 0;
     if (trace) {
         if (P.fast) {
-            per += (size_t)(maxlen + kSkew * P.G) * P.G * (P.C <= 8 ? 4 : (P.C <= 16 ? 8 : 16));
+            const Geometry g = geometry_for(P, maxlen);
+            const size_t wb = (size_t)trace_word_bytes(g.C) + (size_t)trace_hi_bytes(g.C, g.solo);
+            per += g.solo ? (size_t)(maxlen + 1) * wb : (size_t)(maxlen + kSkew * g.G) * g.G * wb;
         } else {
             per += (size_t)std::max(1, maxlen) * P.L;
         }
@@ -785,26 +809,19 @@ long long sub_chunk(const Plan& P, int maxlen, bool trace, long long n) {
 
 const char* g_last_kernel = "";
 
-/* Two rows per lane step (wf_forward2) pay off on long windows; on barcode-length reads (a couple of dozen rows per
- * alignment, lanes of a warp at different phases of different alignments) nearly every step is the masked one and the
- * single-row kernel is ~2x faster (1 M x 96 barcodes: 0.11 s vs 0.20 s).  SARLACC_PAIR=0/1 forces either (A/B tests). */
-int pair_rows_default(int maxlen = 1 << 30) {
-    const char* e = std::getenv("SARLACC_PAIR");
-    if (e) return std::atoi(e);
-    return maxlen >= 48 ? 1 : 0;
-}
-
 /* Alignment groups in one full grid of the plan's forward kernel (0 for the literal kernel). */
 long long plan_groups(const Plan& P, bool trace) {
     if (!P.fast) return 0;
+    const Geometry g = geometry_for(P);
     AlignArgs A;
     std::memset(&A, 0, sizeof(A));
     A.L = P.L;
     A.nref = P.nref;
     A.enc_n = P.enc->n;
-    A.G = P.G;
-    A.C = P.C;
-    A.pair_rows = pair_rows_default();
+    A.G = g.G;
+    A.C = g.C;
+    A.solo = g.solo ? 1 : 0;
+    A.pair_rows = g.pair;
     return wavefront_groups(A, trace);
 }
 
@@ -896,9 +913,11 @@ const char* run_device(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t
         A.cost = D.cost;
         A.enc_n = P.enc->n;
         A.kinds = P.kinds;
-        A.G = P.G;
-        A.C = P.C;
-        A.pair_rows = pair_rows_default(maxlen);
+        const Geometry geo = geometry_for(P, maxlen);
+        A.G = geo.G;
+        A.C = geo.C;
+        A.solo = geo.solo ? 1 : 0;
+        A.pair_rows = geo.pair;
         /* [nref][n] outputs of a sub-chunk cannot be expressed with one base pointer unless n == m or nref == 1 */
         A.score = out.score ? out.score + off : nullptr;
         A.best_id = out.best_id ? out.best_id + off : nullptr;
@@ -909,13 +928,19 @@ const char* run_device(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t
         std::memset(&T, 0, sizeof(T));
         if (trace) {
             if (P.fast) {
-                const int wb = P.C <= 8 ? 4 : (P.C <= 16 ? 8 : 16);
-                A.fstride = (long long)(maxlen + kSkew * P.G) * P.G;
-                S.flags.reserve((size_t)A.fstride * wb * m);
+                const int wb = trace_word_bytes(geo.C), hb = trace_hi_bytes(geo.C, geo.solo);
+                /* record words of this sub-launch: wavefront [alignment][row slot][lane]; solo [32 alignments][row][lane] */
+                A.fstride = geo.solo ? (long long)(maxlen + 1) : (long long)(maxlen + kSkew * geo.G) * geo.G;
+                const size_t words = geo.solo ? (size_t)((m + 31) / 32) * 32 * (size_t)A.fstride : (size_t)A.fstride * (size_t)m;
+                const size_t lo_bytes = (words * wb + 255) & ~(size_t)255;
+                S.flags.reserve(lo_bytes + words * hb);
                 S.endrow.reserve(sizeof(int32_t) * (size_t)m);
                 A.endrow = std::getenv("SARLACC_NO_ENDROW") ? nullptr : S.endrow.as<int32_t>();   /* A/B switch for profiles */
-                T.layout = 0;
+                A.flags_hi = hb ? S.flags.as<uint8_t>() + lo_bytes : nullptr;
+                T.layout = geo.solo ? 2 : 0;
                 T.wordbytes = wb;
+                T.hi_bytes = hb;
+                T.flags_hi = A.flags_hi;
             } else {
                 A.fstride = (long long)std::max(1, maxlen) * P.L;
                 S.flags.reserve((size_t)A.fstride * m);
@@ -947,8 +972,8 @@ const char* run_device(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t
             T.lens = A.lens;
             T.n = m;
             T.L = P.L;
-            T.G = P.G;
-            T.C = P.C;
+            T.G = geo.G;
+            T.C = geo.C;
             T.flags = A.flags;
             T.fstride = A.fstride;
             T.endrow = A.endrow;
@@ -2768,7 +2793,10 @@ int sarlacc_resident_align(sarlacc_resident* r, int mode, double gapopen, double
                 r->tb_pending[b] = false;
             }
         }
-        r->last_kernel = std::string(name) + " G=" + std::to_string(cp->plan.G) + " C=" + std::to_string(cp->plan.C);
+        {
+            const Geometry g = geometry_for(cp->plan, r->maxlen);
+            r->last_kernel = std::string(name) + " G=" + std::to_string(g.G) + " C=" + std::to_string(g.C);
+        }
         r->has_result = true;
     } catch (CudaError& e) {
         return fail(e.msg);

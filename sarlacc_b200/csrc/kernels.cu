@@ -41,9 +41,12 @@ __device__ __forceinline__ double col0_value(int local, double gop, double ge, i
 }
 
 template <int C>
-struct FlagWord {   /* 4 bits per owned column: 32-bit word up to C = 8, 64-bit up to 16, 128-bit (uint4) beyond */
-    using type = typename std::conditional<(C <= 8), uint32_t,
-                 typename std::conditional<(C <= 16), unsigned long long, uint4>::type>::type;
+struct FlagWord {   /* 4 bits per owned column: the low word holds the first 8 (32-bit) or 16 (64-bit) columns ... */
+    using type = typename std::conditional<(C <= 8), uint32_t, unsigned long long>::type;
+};
+template <int C, bool SOLO>
+struct FlagHi {     /* ... columns 16.. go to a second plane indexed alike: one byte (C = 17, 18) or one 32-bit word (solo) */
+    using type = typename std::conditional<SOLO, uint32_t, uint8_t>::type;
 };
 
 #ifndef SARLACC_WF_STEP_UNROLL
@@ -67,9 +70,12 @@ constexpr int kPairUnrollXL = SARLACC_WF_PAIR_UNROLL_XL;
 #ifndef SARLACC_WF_BLOCKS_XL
 #define SARLACC_WF_BLOCKS_XL 3      /* C = 14, 16, 18 (register cap 168): fewer, fatter lanes; pays off without trace records */
 #endif
+#ifndef SARLACC_WF_BLOCKS_SOLO
+#define SARLACC_WF_BLOCKS_SOLO 3    /* C = 20..24, one thread per alignment */
+#endif
 template <int C>
 struct WfBounds {
-    static constexpr int min_blocks = (C <= 9) ? SARLACC_WF_BLOCKS_SMALL : ((C <= 12) ? SARLACC_WF_BLOCKS_LARGE : SARLACC_WF_BLOCKS_XL);
+    static constexpr int min_blocks = (C <= 9) ? SARLACC_WF_BLOCKS_SMALL : ((C <= 12) ? SARLACC_WF_BLOCKS_LARGE : ((C <= 18) ? SARLACC_WF_BLOCKS_XL : SARLACC_WF_BLOCKS_SOLO));
 };
 
 /* R/barcodeAlign.R:28-34: strict `>` for best, then strict `>` for next best. */
@@ -103,14 +109,13 @@ __host__ __device__ __forceinline__ void wf_locate(int c, int C, int pad, int* j
     }
 }
 
-template <int C>
-__device__ __forceinline__ void store_flags(typename FlagWord<C>::type* dst, const uint32_t* fw) {
+template <int C, bool SOLO>
+__device__ __forceinline__ void store_flags(typename FlagWord<C>::type* lo, typename FlagHi<C, SOLO>::type* hi, long long at, const uint32_t* fw) {
     if constexpr (C <= 8) {
-        *dst = fw[0];
-    } else if constexpr (C <= 16) {
-        *dst = ((unsigned long long)fw[1] << 32) | fw[0];
+        lo[at] = fw[0];
     } else {
-        *dst = make_uint4(fw[0], fw[1], fw[2], 0u);
+        lo[at] = ((unsigned long long)fw[1] << 32) | fw[0];
+        if constexpr (C > 16) hi[at] = (typename FlagHi<C, SOLO>::type)fw[2];
     }
 }
 
@@ -237,7 +242,9 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
     int i = 0, len = 0, delay = kSkew * j;
     bool done = false;
     const uint16_t* rowp = A.rows;
-    WT* flagp = reinterpret_cast<WT*>(A.flags);
+    WT* const flo = reinterpret_cast<WT*>(A.flags);
+    typename FlagHi<C, false>::type* const fhi = reinterpret_cast<typename FlagHi<C, false>::type*>(A.flags_hi);
+    long long fidx = 0;     /* record word of the current row for this lane */
     double best = NEG, nextb = NEG;
     int bid = 0;
     int lf0 = 0, lf1 = 0;   /* last slot: where the traceback's climb from this row lands (see land_step) */
@@ -326,7 +333,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
         outE = El;
         if (TRACE) {
             if (live) {
-                store_flags<C>(flagp, fw);
+                store_flags<C, false>(flo, fhi, fidx, fw);
             }
         }
     };
@@ -349,7 +356,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
             } else {
                 i = 0;
                 rowp = A.rows + a * (long long)A.stride - 1;                                   /* advanced to row i before use */
-                if (TRACE) flagp = reinterpret_cast<WT*>(A.flags) + a * A.fstride + (long long)j * (kSkew * G + 1);   /* word (i + kSkew * j) * G + j */
+                if (TRACE) fidx = a * A.fstride + (long long)j * (kSkew * G + 1);   /* word (i + kSkew * j) * G + j */
 #pragma unroll
                 for (int k = 0; k < C; ++k) {
                     const int c = cfirst + k - (skip0 ? 1 : 0);
@@ -387,7 +394,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
             if (kSkew == 2) { outS2 = outS; outE2 = outE; }
             i += inc;
             rowp += inc;
-            if (TRACE) flagp += finc;
+            if (TRACE) fidx += finc;
             row_step(Sl, El, act);
         }
         if (!act) rowp = keep_rowp;
@@ -415,9 +422,11 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
  * gives every warp two dependency chains in flight (the single-row kernel's top stall is `wait`, the fixed-latency
  * dependency of its one chain, profiles/).  An odd last row runs the same code with row B masked off.
  */
-template <int C, bool TRACE>
+template <int C, bool TRACE, bool SOLO>
 __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(const __grid_constant__ AlignArgs A)
 {
+    /* SOLO: one thread owns one alignment and all C = L columns (G = 1): no shuffles, no first-lane or dummy-slot
+     * selects, column 0 is a constant boundary -- the geometry for 20-24 bp references (adaptor2, barcodes). */
     using WT = typename FlagWord<C>::type;
     extern __shared__ double smem_d[];
     const int L = A.L, nref = A.nref, encn = A.enc_n;
@@ -442,22 +451,23 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
-    const int G = A.G;
-    const int j = lane & (G - 1);
+    const int G = SOLO ? 1 : A.G;
+    const int j = SOLO ? 0 : (lane & (G - 1));
     const int gpw = 32 / G;
     const long long warp_global = (long long)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
     const long long gidx = warp_global * gpw + lane / G;
     const long long NG = (long long)gridDim.x * (kBlock / 32) * gpw;
-    const int pad = G * C - L;
-    const bool skip0 = j < pad;
-    const int cfirst = wf_first_col(j, C, pad);
+    const int pad = SOLO ? 0 : (G * C - L);
+    const bool skip0 = SOLO ? false : (j < pad);
+    const int cfirst = SOLO ? 1 : wf_first_col(j, C, pad);
     const double gop = A.gop, ge = A.ge;
     const int local = A.local;
     const int kinds = A.kinds;
     const double NEG = neg_inf();
-    const bool first_lane = (j == 0);
+    const bool first_lane = SOLO ? true : (j == 0);
     const double vo_last = (local && j == G - 1) ? 0.0 : gop;
     const double ve_last = (local && j == G - 1) ? 0.0 : ge;
+    const int rstep = SOLO ? 32 : G;          /* record words between consecutive rows of one lane */
 
     constexpr int kTab = kCostEntries * 32;                   /* doubles between the tables of row A and row B */
     double* mytab = lanetab + (threadIdx.x >> 5) * 2 * kTab + lane;
@@ -484,7 +494,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
     double outSA = 0.0, outEA = NEG, outSB = 0.0, outEB = NEG, diag0 = 0.0;
     long long a = gidx - NG;
     int b = nref - 1;
-    int i = 0, len = 0, delay = j;
+    int i = 0, len = 0, delay = SOLO ? 0 : j;
     bool done = false;
     const uint16_t* rowp = A.rows;          /* points at the next unprocessed row */
     unsigned cur = 0;                        /* rows i+1, i+2 (two 16-bit entries), loaded one step ahead */
@@ -493,7 +503,9 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
     auto prefetch = [&](bool act_) -> unsigned {
         return (act_ && i + 2 < len) ? *reinterpret_cast<const unsigned*>(rowp + 2) : 0u;
     };
-    WT* flagp = reinterpret_cast<WT*>(A.flags);   /* word of the next unprocessed row for this lane */
+    WT* const flo = reinterpret_cast<WT*>(A.flags);
+    typename FlagHi<C, SOLO>::type* const fhi = reinterpret_cast<typename FlagHi<C, SOLO>::type*>(A.flags_hi);
+    long long fidx = 0;      /* record word of the next unprocessed row for this lane */
     double best = NEG, nextb = NEG;
     int bid = 0;
     int lf0 = 0, lf1 = 0;   /* last slot: landing row of the traceback's climb (land_step) */
@@ -648,8 +660,8 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
         else diag0 = SlB_in;
         if (TRACE) {
             if (live) {
-                store_flags<C>(flagp, fa);
-                if (!MASKED || hasB) store_flags<C>(flagp + G, fb);
+                store_flags<C, SOLO>(flo, fhi, fidx, fa);
+                if (!MASKED || hasB) store_flags<C, SOLO>(flo, fhi, fidx + rstep, fb);
             }
         }
     };
@@ -672,7 +684,10 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
                 i = 0;
                 rowp = A.rows + a * (long long)A.stride;
                 cur = *reinterpret_cast<const unsigned*>(rowp);
-                if (TRACE) flagp = reinterpret_cast<WT*>(A.flags) + a * A.fstride + (long long)(1 + 2 * j) * G + j;   /* word (i + 2j) * G + j, i = 1 */
+                if (TRACE) {
+                    if (SOLO) fidx = ((a >> 5) * A.fstride + 1) * 32 + (a & 31);     /* [32 alignments][row][lane], row = 1 */
+                    else fidx = a * A.fstride + (long long)(1 + 2 * j) * G + j;      /* word (i + 2j) * G + j, i = 1 */
+                }
 #pragma unroll
                 for (int k = 0; k < C; ++k) {
                     const int c = cfirst + k - (skip0 ? 1 : 0);
@@ -696,25 +711,31 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
         if (steps == 0x7fffffff) break;
         if (steps > 0) {
             const int inc = act ? 2 : 0;
-            const long long finc = act ? 2 * G : 0;
+            const long long finc = act ? 2 * rstep : 0;
 #pragma unroll (C > 12 ? kPairUnrollXL : kPairUnroll)
             for (int s = 0; s < steps; ++s) {
-                const double SlA = __shfl_up_sync(FULL, outSA, 1, G);
-                const double ElA = __shfl_up_sync(FULL, outEA, 1, G);
-                const double SlB = __shfl_up_sync(FULL, outSB, 1, G);
-                const double ElB = __shfl_up_sync(FULL, outEB, 1, G);
+                double SlA = 0.0, ElA = 0.0, SlB = 0.0, ElB = 0.0;     /* SOLO: column 0 is set inside pair_step */
+                if (!SOLO) {
+                    SlA = __shfl_up_sync(FULL, outSA, 1, G);
+                    ElA = __shfl_up_sync(FULL, outEA, 1, G);
+                    SlB = __shfl_up_sync(FULL, outSB, 1, G);
+                    ElB = __shfl_up_sync(FULL, outEB, 1, G);
+                }
                 const unsigned nxt = prefetch(act);
                 pair_step(std::false_type(), cur, SlA, ElA, SlB, ElB, act, true);
                 cur = nxt;
                 i += inc;
                 rowp += inc;
-                if (TRACE) flagp += finc;
+                if (TRACE) fidx += finc;
             }
         } else {
-            const double SlA = __shfl_up_sync(FULL, outSA, 1, G);
-            const double ElA = __shfl_up_sync(FULL, outEA, 1, G);
-            const double SlB = __shfl_up_sync(FULL, outSB, 1, G);
-            const double ElB = __shfl_up_sync(FULL, outEB, 1, G);
+            double SlA = 0.0, ElA = 0.0, SlB = 0.0, ElB = 0.0;
+            if (!SOLO) {
+                SlA = __shfl_up_sync(FULL, outSA, 1, G);
+                ElA = __shfl_up_sync(FULL, outEA, 1, G);
+                SlB = __shfl_up_sync(FULL, outSB, 1, G);
+                ElB = __shfl_up_sync(FULL, outEB, 1, G);
+            }
             const bool hasB = act && (len - i) >= 2;
             const unsigned nxt = prefetch(act);
             pair_step(std::true_type(), act ? (hasB ? cur : (cur & 0xffffu)) : 0u, SlA, ElA, SlB, ElB, act, hasB);   /* a missing row B reads as entry 0, never as whatever follows the window */
@@ -722,7 +743,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
             const int inc = act ? (hasB ? 2 : 1) : 0;
             i += inc;
             rowp += inc;
-            if (TRACE) flagp += (long long)inc * G;
+            if (TRACE) fidx += (long long)inc * rstep;
         }
 
         if (act && i == len && j == G - 1) {
@@ -868,30 +889,31 @@ struct FlagReader {
     const TraceArgs& T;
     long long a;
     int len;
-    const int* colinfo;   /* wavefront layout: per DP column, (word offset j*(G+1)) << 8 | (bit shift 4k) */
+    const int* colinfo;   /* wavefront / solo layouts: per DP column, (word offset j*(kSkew*G+1)) << 8 | (bit shift 4k) */
     __device__ unsigned get(int i, int c) const {
-        if (T.layout == 0) {
+        if (T.layout != 1) {
             const int ci = colinfo[c];
-            const long long w = a * T.fstride + (long long)i * T.G + (ci >> 8);
-            /* the word of (row, lane) is wordbytes wide; slot k lives in its 32-bit part k/8 */
-            const uint32_t* base = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(T.flags) + w * T.wordbytes);
+            /* wavefront: word (i + kSkew*j)*G + j of the alignment; solo: [32 alignments][row][lane] */
+            const long long w = (T.layout == 0) ? a * T.fstride + (long long)i * T.G + (ci >> 8)
+                                                : ((a >> 5) * T.fstride + i) * 32 + (a & 31);
             const int sh = ci & 0xff;
+            if (sh >= 64) {       /* columns 16.. of the lane live in the second plane */
+                const unsigned v = (T.hi_bytes == 1) ? (unsigned)reinterpret_cast<const uint8_t*>(T.flags_hi)[w]
+                                                     : reinterpret_cast<const uint32_t*>(T.flags_hi)[w];
+                return (v >> (sh - 64)) & 15u;
+            }
+            /* the low word is wordbytes wide; slot k lives in its 32-bit part k/8 */
+            const uint32_t* base = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(T.flags) + w * T.wordbytes);
             return (base[sh >> 5] >> (sh & 31)) & 15u;
         }
         return reinterpret_cast<const uint8_t*>(T.flags)[a * T.fstride + (long long)(c - 1) * len + (i - 1)];
-    }
-    __device__ int choice(int i, int c) const {
-        if (c == 0) return CH_UP;      /* column 0: -1 (:64) */
-        if (i == 0) return CH_LEFT;    /* row 0: +1 (:118) */
-        const unsigned f = get(i, c);
-        return (f & 1u) ? CH_DIAG : ((f & 2u) ? CH_LEFT : CH_UP);
     }
 };
 
 __global__ void __launch_bounds__(128) traceback(const TraceArgs T)
 {
     extern __shared__ int tb_colinfo[];
-    if (T.layout == 0) {
+    if (T.layout != 1) {
         const int pad = T.G * T.C - T.L;
         for (int c = 1 + threadIdx.x; c <= T.L; c += blockDim.x) {
             int j, k;
@@ -902,6 +924,7 @@ __global__ void __launch_bounds__(128) traceback(const TraceArgs T)
     }
     const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= T.n) return;
+    if (T.skip && T.skip[a] == T.skip_if) return;   /* the strand .resolve_strand dropped: nobody reads these coordinates */
     const int L = T.L;
     const int len = T.lens[a];
     const long long n = T.n;
@@ -1158,24 +1181,33 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const __grid_constant__ 
     }
 }
 
-template <int C, bool TRACE>
+template <int C, bool TRACE, bool SOLO>
+auto wf_kernel(bool pair) -> void (*)(const AlignArgs) {
+    if constexpr (SOLO) {
+        return wf_forward2<C, TRACE, true>;      /* the solo geometry exists as a row-pair kernel only */
+    } else {
+        return pair ? wf_forward2<C, TRACE, false> : wf_forward<C, TRACE>;
+    }
+}
+
+template <int C, bool TRACE, bool SOLO>
 int wf_resident_blocks(bool pair, size_t smem) {
-    auto kern = pair ? wf_forward2<C, TRACE> : wf_forward<C, TRACE>;
+    auto kern = wf_kernel<C, TRACE, SOLO>(pair);
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, kBlock, smem);
     return per < 1 ? 1 : per;
 }
 
-template <int C, bool TRACE>
+template <int C, bool TRACE, bool SOLO>
 const char* launch_wf(const AlignArgs& a, int grid, cudaStream_t st, size_t smem) {
-    const bool pair = a.pair_rows != 0;
-    auto kern = pair ? wf_forward2<C, TRACE> : wf_forward<C, TRACE>;
+    const bool pair = SOLO || a.pair_rows != 0;
+    auto kern = wf_kernel<C, TRACE, SOLO>(pair);
     if (grid <= 0) {
         int dev = 0, sms = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        grid = sms * wf_resident_blocks<C, TRACE>(pair, smem);
+        grid = sms * wf_resident_blocks<C, TRACE, SOLO>(pair, smem);
     } else if (smem > 48 * 1024) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
@@ -1184,18 +1216,34 @@ const char* launch_wf(const AlignArgs& a, int grid, cudaStream_t st, size_t smem
     const long long need = (a.n + groups_per_block - 1) / groups_per_block;
     if (need < grid) grid = (int)(need > 0 ? need : 1);
     kern<<<grid, kBlock, smem, st>>>(a);
+    if (SOLO) return TRACE ? "solo_forward2<trace>" : "solo_forward2<score>";
     return pair ? (TRACE ? "wf_forward2<trace>" : "wf_forward2<score>") : (TRACE ? "wf_forward<trace>" : "wf_forward<score>");
 }
 
-/* Calls f(std::integral_constant<int, C>) for an instantiated geometry; false if a.C is not one. */
+/* Calls f(std::integral_constant<int, C>, std::integral_constant<bool, SOLO>) for an instantiated geometry; false if
+ * (C, solo) is not one. */
 template <class F>
-bool for_geometry(int C, F&& f) {
+bool for_geometry(int C, bool solo, F&& f) {
 #ifdef SARLACC_ONLY_C   /* tuning builds: instantiate one geometry only (tools/variants.py) */
-    if (C == SARLACC_ONLY_C) { f(std::integral_constant<int, SARLACC_ONLY_C>()); return true; }
+    if (C == SARLACC_ONLY_C) {
+        if (solo) {
+            if constexpr (SARLACC_ONLY_C >= kSoloMinC && SARLACC_ONLY_C <= kSoloMaxC) { f(std::integral_constant<int, SARLACC_ONLY_C>(), std::true_type()); return true; }
+        } else {
+            if constexpr (SARLACC_ONLY_C <= kMaxC) { f(std::integral_constant<int, SARLACC_ONLY_C>(), std::false_type()); return true; }
+        }
+    }
     return false;
 #else
+    if (solo) {
+        switch (C) {
+#define SARLACC_GEOM(N) case N: f(std::integral_constant<int, N>(), std::true_type()); return true;
+            SARLACC_GEOM(20) SARLACC_GEOM(21) SARLACC_GEOM(22) SARLACC_GEOM(23) SARLACC_GEOM(24)
+#undef SARLACC_GEOM
+        }
+        return false;
+    }
     switch (C) {
-#define SARLACC_GEOM(N) case N: f(std::integral_constant<int, N>()); return true;
+#define SARLACC_GEOM(N) case N: f(std::integral_constant<int, N>(), std::false_type()); return true;
         SARLACC_GEOM(1) SARLACC_GEOM(2) SARLACC_GEOM(3) SARLACC_GEOM(4) SARLACC_GEOM(5) SARLACC_GEOM(6)
         SARLACC_GEOM(7) SARLACC_GEOM(8) SARLACC_GEOM(9) SARLACC_GEOM(10) SARLACC_GEOM(11) SARLACC_GEOM(12)
         SARLACC_GEOM(14) SARLACC_GEOM(16) SARLACC_GEOM(18)
@@ -1219,9 +1267,10 @@ const char* launch_wavefront(const AlignArgs& a, bool trace, bool has_alt, int g
     (void)has_alt;
     const size_t smem = wavefront_smem_bytes(a);
     const char* name = nullptr;
-    for_geometry(a.C, [&](auto ctag) {
+    for_geometry(a.C, a.solo != 0, [&](auto ctag, auto stag) {
         constexpr int C = decltype(ctag)::value;
-        name = trace ? launch_wf<C, true>(a, grid, st, smem) : launch_wf<C, false>(a, grid, st, smem);
+        constexpr bool SOLO = decltype(stag)::value;
+        name = trace ? launch_wf<C, true, SOLO>(a, grid, st, smem) : launch_wf<C, false, SOLO>(a, grid, st, smem);
     });
     return name;
 }
@@ -1229,9 +1278,11 @@ const char* launch_wavefront(const AlignArgs& a, bool trace, bool has_alt, int g
 long long wavefront_groups(const AlignArgs& a, bool trace) {
     const size_t smem = wavefront_smem_bytes(a);
     int per = 0;
-    for_geometry(a.C, [&](auto ctag) {
+    for_geometry(a.C, a.solo != 0, [&](auto ctag, auto stag) {
         constexpr int C = decltype(ctag)::value;
-        per = trace ? wf_resident_blocks<C, true>(a.pair_rows != 0, smem) : wf_resident_blocks<C, false>(a.pair_rows != 0, smem);
+        constexpr bool SOLO = decltype(stag)::value;
+        const bool pair = SOLO || a.pair_rows != 0;
+        per = trace ? wf_resident_blocks<C, true, SOLO>(pair, smem) : wf_resident_blocks<C, false, SOLO>(pair, smem);
     });
     if (per == 0) return 0;
     int dev = 0, sms = 0;

@@ -19,6 +19,8 @@
 namespace sarlacc {
 
 constexpr int kMaxC = 18;        /* adaptor columns per lane in the wavefront kernel (instantiated: 1..12, 14, 16, 18) */
+constexpr int kSoloMinC = 20;    /* one-thread-per-alignment geometry ("solo", G = 1, C = L): instantiated for L = 20..24 */
+constexpr int kSoloMaxC = 24;
 constexpr int kMaxGroup = 32;    /* lanes per alignment */
 #ifndef SARLACC_WF_SKEW
 #define SARLACC_WF_SKEW 2
@@ -60,9 +62,13 @@ struct AlignArgs {
     int32_t* best_id;         /* [n] multi-reference running best (R/barcodeAlign.R:28-34), nref > 1 only */
     double* best;
     double* next_best;
-    /* traceback records */
+    /* traceback records: 4 bits per cell.  Wavefront layout: word (row slot, lane) holds the lane's first 8 (C <= 8) or 16
+     * columns in `flags` (32- / 64-bit words) and columns 16.. in `flags_hi` (one byte per word for C = 17, 18; one
+     * 32-bit word in the solo geometry), both indexed alike -- no padding bits are written (C = 18: 9 bytes per lane-row). */
     void* flags;
-    long long fstride;        /* per alignment, in flag words (wavefront) or bytes (generic) */
+    void* flags_hi;
+    long long fstride;        /* per alignment, in flag words (wavefront), row slots (solo) or bytes (generic) */
+    int solo;                 /* 1: one thread per alignment (G = 1, C = L), records laid out [32 alignments][row][lane] */
     int32_t* endrow;          /* [n] wavefront + trace: row where the traceback's climb up the last column lands (optional) */
     /* generic kernel scratch: [maxlen+1][nthreads] doubles each */
     double* gS;
@@ -75,11 +81,15 @@ struct TraceArgs {
     const int32_t* lens;
     long long n;
     int L;
-    int layout;               /* 0: wavefront words, 1: generic bytes */
-    int G, C, wordbytes;
+    int layout;               /* 0: wavefront words, 1: generic bytes, 2: solo planes */
+    int G, C, wordbytes;      /* wordbytes: 4 or 8 (the low word) */
+    int hi_bytes;             /* 0, 1 or 4: element size of flags_hi (columns 16.. of a lane) */
     const void* flags;
+    const void* flags_hi;
     long long fstride;
     const int32_t* endrow;      /* [n] optional: start the walk at (endrow[a], L) instead of (len, L) */
+    const uint8_t* skip;        /* [n] optional: alignments with skip[a] == skip_if are not walked (the strand .resolve_strand dropped) */
+    int skip_if;
     int nsec;
     const int32_t* sec_starts;  /* device, 0-based */
     const int32_t* sec_ends;    /* device, 1-based */
@@ -149,6 +159,10 @@ const char* launch_generic(const AlignArgs& a, bool trace, int grid, cudaStream_
 void launch_traceback(const TraceArgs& t, cudaStream_t st);
 void launch_fill_empty(const AlignArgs& a, cudaStream_t st);
 size_t wavefront_smem_bytes(const AlignArgs& a);
+/* Trace record geometry of the wavefront kernels: bytes of the low word, bytes of the high element (0: none). */
+inline int trace_word_bytes(int C) { return C <= 8 ? 4 : 8; }
+inline int trace_hi_bytes(int C, bool solo) { return C <= 16 ? 0 : (solo ? 4 : 1); }
+inline bool solo_geometry(int G, int C) { return G == 1 && C >= kSoloMinC && C <= kSoloMaxC; }
 /* Alignment groups of one full grid of the wavefront kernel on the current device (0: geometry not instantiated).
  * Every group walks its alignments back to back, so a launch over k * groups equal-length alignments has no tail. */
 long long wavefront_groups(const AlignArgs& a, bool trace);

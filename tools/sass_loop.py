@@ -1,10 +1,20 @@
-"""Print the instruction mix of the innermost loop (the DP row loop) of one wf_forward variant.
-usage: python tools/sass_loop.py C trace [--dump]"""
-import re, subprocess, sys, collections
-C, tr = sys.argv[1], sys.argv[2]
-out = subprocess.run(["cuobjdump", "-sass", "sarlacc_b200/libsarlacc_b200.so"], capture_output=True, text=True).stdout
-name = sys.argv[3] if len(sys.argv) > 3 and not sys.argv[3].startswith("--") else "wf_forward2"
-pat = "%sILi%sELb%sEEE" % (name, C, tr)
+"""Print the instruction mix of the unmasked DP row loop of one forward-kernel variant (static SASS count).
+usage: python tools/sass_loop.py C trace [kernel=wf_forward2] [solo=0|1] [--dump] [--lib path]
+The row loop is the smallest backward-branch body that holds at least 4*C DSETP (one row of C cells has 4 FP64 compares)."""
+import collections
+import re
+import subprocess
+import sys
+
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+C, tr = args[0], args[1]
+name = args[2] if len(args) > 2 else "wf_forward2"
+solo = args[3] if len(args) > 3 else "0"
+lib = "sarlacc_b200/libsarlacc_b200.so"
+if "--lib" in sys.argv:
+    lib = sys.argv[sys.argv.index("--lib") + 1]
+out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+pat = "%sILi%sELb%sE" % (name, C, tr) + ("Lb%sE" % solo if name == "wf_forward2" else "") + "EE"
 lines = out.splitlines()
 st = next(i for i, l in enumerate(lines) if "Function :" in l and pat in l)
 en = next((i for i in range(st + 1, len(lines)) if "Function :" in lines[i]), len(lines))
@@ -13,7 +23,6 @@ for l in lines[st:en]:
     m = re.match(r"\s+/\*([0-9a-f]{4,5})\*/\s+(.*?);", l)
     if m:
         ins.append((int(m.group(1), 16), m.group(2).strip()))
-# find backward branches; the innermost loop = the backward branch with the largest body containing SHFL and DSETP
 best = None
 for idx, (addr, txt) in enumerate(ins):
     m = re.search(r"BRA(?:\.U)?\s+(?:!?U?P\d,\s*)?0x([0-9a-f]+)", txt)
@@ -21,14 +30,16 @@ for idx, (addr, txt) in enumerate(ins):
         tgt = int(m.group(1), 16)
         if tgt < addr:
             body = [t for a, t in ins if tgt <= a <= addr]
-            if any("SHFL" in t for t in body) and any("DSETP" in t for t in body):
+            if sum("DSETP" in t for t in body) >= 4 * int(C):
                 if best is None or len(body) < len(best):
                     best = body
 cnt = collections.Counter()
 for t in best:
     t = re.sub(r"^@!?U?P\d+\s+", "", t)
     cnt[t.split()[0].split(".")[0]] += 1
-print("loop instructions: %d  (%.1f per cell at C=%s)" % (len(best), len(best) / int(C), C))
+rows = max(1, round(cnt["DSETP"] / (4.0 * int(C))))
+print("%s<C=%s, trace=%s, solo=%s>: loop instructions %d = %d rows x %s columns -> %.2f per cell" %
+      (name, C, tr, solo, len(best), rows, C, len(best) / (rows * int(C))))
 print(sorted(cnt.items(), key=lambda kv: -kv[1]))
 if "--dump" in sys.argv:
     print("\n".join(best))
