@@ -353,35 +353,84 @@ def adaptorAlign(adaptor1, adaptor2, filepath, tolerance=250, gapOpening=5, gapE
     return output
 
 
-def _mix64(x):
-    """splitmix64 finaliser (vectorised): the counter-based hash behind the scramble permutation."""
-    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-    return x ^ (x >> np.uint64(31))
+_U32 = np.uint32
+
+
+def _hash32(x):
+    """kernels.cu: hash32 (two 32-bit multiplies), on uint32 arrays."""
+    x = np.asarray(x, dtype=np.uint32).copy()
+    with np.errstate(over="ignore"):
+        x ^= x >> _U32(16)
+        x *= _U32(0x21F0AAAD)
+        x ^= x >> _U32(15)
+        x *= _U32(0x735A2D97)
+        x ^= x >> _U32(15)
+    return x
+
+
+def _stream_key(seed, index, field):
+    """kernels.cu: stream_key -- the 32-bit key of the stream (seed, global read index, field); index may be an array."""
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    index = np.asarray(index, dtype=np.uint64)
+    k = _hash32(_U32((seed & 0xFFFFFFFF) ^ 0x243F6A88))
+    k = _hash32(k ^ _U32(seed >> 32))
+    k = _hash32(k ^ (index & np.uint64(0xFFFFFFFF)).astype(np.uint32))
+    k = _hash32(k ^ (index >> np.uint64(32)).astype(np.uint32))
+    with np.errstate(over="ignore"):
+        f = _U32((int(field) * 0x85EBCA6B + 0xC2B2AE35) & 0xFFFFFFFF)
+    return _hash32(k ^ f)
+
+
+def _stream_word(key, p):
+    """kernels.cu: stream_word -- word p of the stream with that key (broadcasts)."""
+    with np.errstate(over="ignore"):
+        return _hash32(np.asarray(key, np.uint32) ^ (np.asarray(p, np.uint32) * _U32(0x9E3779B1) + _U32(0x7F4A7C15)))
+
+
+def _scramble_by_index(seqs, seed, read_index, stream):
+    """R/getAdaptorThresholds.R:68-92: one uniform random permutation per sequence, applied to bases and qualities
+    alike.  R's sample() stream cannot be reproduced outside R; here it is a Fisher-Yates shuffle -- for i = len-1 .. 1:
+    j = floor(word_i * (i + 1) / 2^32), swap(i, j) -- driven by the counter-based stream of (seed, global read index,
+    field 16 + stream), so it does not depend on chunking, sharding or device count.  kernels.cu: scramble_rows_fy is the
+    same function on the device."""
+    n = len(seqs)
+    w = seqs.width().astype(np.int64)
+    maxw = int(w.max()) if n else 0
+    key = _stream_key(seed, np.asarray(read_index, dtype=np.uint64), 16 + int(stream))
+    perm = np.tile(np.arange(max(maxw, 1), dtype=np.int64), (n, 1))        # perm[r, i] = source position of output i
+    rows = np.arange(n)
+    for i in range(maxw - 1, 0, -1):
+        live = w > i
+        if not live.any():
+            continue
+        j = ((_stream_word(key, i).astype(np.uint64) * np.uint64(i + 1)) >> np.uint64(32)).astype(np.int64)
+        r = rows[live]
+        jj = j[live]
+        a, b = perm[r, i].copy(), perm[r, jj].copy()
+        perm[r, i] = b
+        perm[r, jj] = a
+    off = np.zeros(n, dtype=np.int64)
+    if n:
+        np.cumsum(w[:-1], out=off[1:])
+    total = int(w.sum())
+    pos = np.arange(total, dtype=np.int64) - np.repeat(off, w)
+    src = np.repeat(seqs.seq_off[:-1] if n else np.zeros(0, np.int64), w) + perm[np.repeat(rows, w), pos]
+    sp = seqs.seq_pool[src]
+    qp = None
+    if seqs.has_quality:
+        qsrc = np.repeat(seqs.qual_off[:-1] if n else np.zeros(0, np.int64), w) + perm[np.repeat(rows, w), pos]
+        qp = seqs.qual_pool[qsrc]
+    o = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(w, out=o[1:])
+    return ReadSet(sp, o, qp, o if qp is not None else None, seqs.names)
 
 
 def _scramble_input(seqs, has_qual=True, seed=0, first_index=0, stream=0):
-    """R/getAdaptorThresholds.R:68-92: one uniform random permutation per sequence, applied to bases and
-    qualities alike.  R's sample() stream cannot be reproduced outside R; the permutation here sorts
-    counter-based hash keys of (seed, global read index, stream, position), so it does not depend on
-    chunking, sharding or device count."""
-    n = len(seqs)
-    w = seqs.width()
-    total = int(w.sum())
-    with np.errstate(over="ignore"):
-        rid = np.repeat(np.arange(first_index, first_index + n, dtype=np.uint64), w)
-        off = np.zeros(n, dtype=np.int64)
-        np.cumsum(w[:-1], out=off[1:])
-        pos = (np.arange(total, dtype=np.int64) - np.repeat(off, w)).astype(np.uint64)
-        key = _mix64(_mix64(rid * np.uint64(0x9E3779B97F4A7C15) + np.uint64(seed)) ^ (pos * np.uint64(0xD1B54A32D192ED03) + np.uint64(stream) * np.uint64(0x8CB92BA72F3D8DD7)))
-    order = np.lexsort((key, np.repeat(np.arange(n), w)))
-    base = seqs.seq_off[0]
-    sp = seqs.seq_pool[base + order]
-    qp = None
-    if has_qual:
-        qp = seqs.qual_pool[seqs.qual_off[0] + order]
-    o = seqs.seq_off - base
-    return ReadSet(sp, o, qp, o if qp is not None else None, seqs.names)
+    """_scramble_by_index for reads first_index, first_index + 1, ... (has_qual=False drops the qualities)."""
+    out = _scramble_by_index(seqs, seed, np.arange(first_index, first_index + len(seqs), dtype=np.uint64), stream)
+    if not has_qual and out.has_quality:
+        out = ReadSet(out.seq_pool, out.seq_off, None, None, out.names)
+    return out
 
 
 def _compute_threshold(real, scrambled, error):
@@ -481,26 +530,6 @@ def getAdaptorThresholds(aligned, error=0.01, number=1e5, seed=0, device_scrambl
             "threshold2": _compute_threshold(real2, scram2, error),
             "scores1": {"reads": real1, "scrambled": scram1},
             "scores2": {"reads": real2, "scrambled": scram2}}
-
-
-def _scramble_by_index(seqs, seed, read_index, stream):
-    """_scramble_input with an explicit global index per read."""
-    n = len(seqs)
-    w = seqs.width()
-    total = int(w.sum())
-    with np.errstate(over="ignore"):
-        rid = np.repeat(np.asarray(read_index, dtype=np.uint64), w)
-        off = np.zeros(n, dtype=np.int64)
-        if n:
-            np.cumsum(w[:-1], out=off[1:])
-        pos = (np.arange(total, dtype=np.int64) - np.repeat(off, w)).astype(np.uint64)
-        key = _mix64(_mix64(rid * np.uint64(0x9E3779B97F4A7C15) + np.uint64(seed)) ^ (pos * np.uint64(0xD1B54A32D192ED03) + np.uint64(stream) * np.uint64(0x8CB92BA72F3D8DD7)))
-    order = np.lexsort((key, np.repeat(np.arange(n), w)))
-    base = seqs.seq_off[0]
-    sp = seqs.seq_pool[base + order]
-    qp = seqs.qual_pool[seqs.qual_off[0] + order] if seqs.has_quality else None
-    o = seqs.seq_off - base
-    return ReadSet(sp, o, qp, o if qp is not None else None, seqs.names)
 
 
 def barcodeAlign(sequences, barcodes, gapOpening=5, gapExtension=1, qual_type="phred"):

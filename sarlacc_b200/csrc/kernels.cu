@@ -164,6 +164,16 @@ __device__ __forceinline__ double pick_move(double h, double m, double v, bool& 
 
 constexpr int kCostEntries = 7;   /* A, C, G, T, two-fold code, three-fold code, N */
 
+/* Element x = ((q * 5 + o) * 4 + part) of the pre-tabulated cost records (see wf_forward): part 0 = entries A,C;
+ * 1 = G,T; 2 = two-fold, three-fold; 3 = N, unused.  cost = AlignArgs::cost, [5][encn]. */
+__device__ __forceinline__ double2 pre_record(const double* cost, int encn, int x) {
+    const int q = x / 20, o = (x / 4) % 5, part = x & 3;
+    const double mq = cost[q], xq = cost[encn + q];
+    if (part < 2) return make_double2((o - 1 == 2 * part) ? mq : xq, (o - 1 == 2 * part + 1) ? mq : xq);
+    if (part == 2) return make_double2(cost[2 * encn + q], cost[3 * encn + q]);
+    return make_double2(cost[4 * encn + q], 0.0);
+}
+
 template <int C, bool TRACE>
 __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(const __grid_constant__ AlignArgs A)
 {
@@ -171,25 +181,21 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
     extern __shared__ double smem_d[];
     const int L = A.L, nref = A.nref, encn = A.enc_n;
     double* row0s = smem_d;                                   /* [L+1]                         */
-    double* costs = row0s + (L + 1);                          /* [5][encn], layout of AlignArgs::cost */
-    double* lanetab = costs + 5 * encn;                       /* [warps][kCostEntries][32] lane-private cost entries */
-    /* pre[q][o][e]: cost of reference base e (A,C,G,T) against an observed base o (0 = other, 1..4 = A,C,G,T) of quality
-     * index q: match1[q] if o-1 == e else mismatch1[q] -- one 32-byte record per (q, o), read with two LDS.128 per row */
-    double2* pre = reinterpret_cast<double2*>(smem_d + (((size_t)(L + 1) + 5 * encn + (kBlock / 32) * kCostEntries * 32 + 1) & ~(size_t)1));   /* 16-byte aligned */
-    uint8_t* refm = reinterpret_cast<uint8_t*>(pre + (size_t)encn * 5 * 2);   /* [nref][L] */
+    double* lanetab = row0s + (L + 1);                        /* [warps][kCostEntries][32] lane-private cost entries */
+    /* pre[q][o][e]: the row's possible costs given its quality index q and observed base o (0 = other, 1..4 = A,C,G,T):
+     * e = 0..3 reference A,C,G,T -> match1[q] if o-1 == e else mismatch1[q]; e = 4,5,6 two-fold / three-fold code / N ->
+     * mismatch2[q], match3[q], match4[q] whatever was observed (src/reference_align.cpp:184-212); e = 7 unused.  One
+     * 64-byte record per (q, o), read with four LDS.128 per row -- no branches on which classes the reference has. */
+    double2* pre = reinterpret_cast<double2*>(smem_d + (((size_t)(L + 1) + (kBlock / 32) * kCostEntries * 32 + 1) & ~(size_t)1));   /* 16-byte aligned */
+    uint8_t* refm = reinterpret_cast<uint8_t*>(pre + (size_t)encn * 5 * 4);   /* [nref][L] */
     uint8_t* refk = refm + (size_t)nref * L;                                                    /* [nref][L] */
 
     for (int x = threadIdx.x; x <= L; x += blockDim.x) row0s[x] = A.row0[x];
-    for (int x = threadIdx.x; x < 5 * encn; x += blockDim.x) costs[x] = A.cost[x];
     for (int x = threadIdx.x; x < nref * L; x += blockDim.x) {
         refm[x] = A.refmask[x];
         refk[x] = A.refkind[x];
     }
-    for (int x = threadIdx.x; x < encn * 5 * 2; x += blockDim.x) {
-        const int q = x / 10, o = (x / 2) % 5, half = x & 1;     /* half 0: entries A,C; half 1: entries G,T */
-        const double mq = A.cost[q], xq = A.cost[encn + q];
-        pre[x] = make_double2((o - 1 == 2 * half) ? mq : xq, (o - 1 == 2 * half + 1) ? mq : xq);
-    }
+    for (int x = threadIdx.x; x < encn * 5 * 4; x += blockDim.x) pre[x] = pre_record(A.cost, encn, x);
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
@@ -204,12 +210,14 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
     const int cfirst = wf_first_col(j, C, pad);     /* DP column of the first real slot */
     const double gop = A.gop, ge = A.ge;
     const int local = A.local;
-    const int kinds = A.kinds;
     const double NEG = neg_inf();
     const bool first_lane = (j == 0);
     /* vertical penalties of slot C-1: zero for the last reference column in local mode (:120-121) */
     const double vo_last = (local && j == G - 1) ? 0.0 : gop;
     const double ve_last = (local && j == G - 1) ? 0.0 : ge;
+    /* column 0, rows i >= 1 (src/reference_align.cpp:65-74): 0 in local mode, -gap_open - gap_ext * (i - 1) otherwise --
+     * one expression for both (0 - 0 * x == 0), so the row loop has no branch on the mode */
+    const double c0base = local ? 0.0 : -gop, c0step = local ? 0.0 : ge;
 
     /* This lane's private table of the current row's possible costs: entry e at mytab[e*32].  Slot k reads
      * the entry of its reference base: ACGT -> (obs == base ? match1 : mismatch1)[q], IUPAC classes ->
@@ -256,18 +264,18 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
         const unsigned obs = rw >> 8;
         {
             const int o = __ffs(obs);                       /* one-hot A=1,C=2,G=4,T=8 -> 1..4; 0 for anything else */
-            const double2 ac = pre[(q * 5 + o) * 2], gt = pre[(q * 5 + o) * 2 + 1];
+            const double2* rec = pre + (q * 5 + o) * 4;
+            const double2 ac = rec[0], gt = rec[1], iu = rec[2], nn = rec[3];
             mytab[0 * 32] = ac.x;
             mytab[1 * 32] = ac.y;
             mytab[2 * 32] = gt.x;
             mytab[3 * 32] = gt.y;
-            if (kinds & 2) mytab[4 * 32] = costs[2 * encn + q];
-            if (kinds & 4) mytab[5 * 32] = costs[3 * encn + q];
-            if (kinds & 8) mytab[6 * 32] = costs[4 * encn + q];
+            mytab[4 * 32] = iu.x;
+            mytab[5 * 32] = iu.y;
+            mytab[6 * 32] = nn.x;
         }
         {   /* column 0 feeds the first lane: src/reference_align.cpp:64-78 (0 in local mode; uniform branch otherwise) */
-            double c0v = 0.0;
-            if (!local) c0v = col0_value(0, gop, ge, i);
+            const double c0v = __dsub_rn(c0base, __dmul_rn(c0step, (double)(i - 1)));   /* H[i][0], i >= 1 */
             Sl = first_lane ? c0v : Sl;
             El = first_lane ? NEG : El;
         }
@@ -431,23 +439,17 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
     extern __shared__ double smem_d[];
     const int L = A.L, nref = A.nref, encn = A.enc_n;
     double* row0s = smem_d;                                   /* [L+1]                         */
-    double* costs = row0s + (L + 1);                          /* [5][encn], layout of AlignArgs::cost */
-    double* lanetab = costs + 5 * encn;                       /* [warps][2 rows][kCostEntries][32] lane-private cost entries */
-    double2* pre = reinterpret_cast<double2*>(smem_d + (((size_t)(L + 1) + 5 * encn + (kBlock / 32) * 2 * kCostEntries * 32 + 1) & ~(size_t)1));
-    uint8_t* refm = reinterpret_cast<uint8_t*>(pre + (size_t)encn * 5 * 2);   /* [nref][L] */
+    double* lanetab = row0s + (L + 1);                        /* [warps][2 rows][kCostEntries][32] lane-private cost entries */
+    double2* pre = reinterpret_cast<double2*>(smem_d + (((size_t)(L + 1) + (kBlock / 32) * 2 * kCostEntries * 32 + 1) & ~(size_t)1));   /* see wf_forward */
+    uint8_t* refm = reinterpret_cast<uint8_t*>(pre + (size_t)encn * 5 * 4);   /* [nref][L] */
     uint8_t* refk = refm + (size_t)nref * L;                                   /* [nref][L] */
 
     for (int x = threadIdx.x; x <= L; x += blockDim.x) row0s[x] = A.row0[x];
-    for (int x = threadIdx.x; x < 5 * encn; x += blockDim.x) costs[x] = A.cost[x];
     for (int x = threadIdx.x; x < nref * L; x += blockDim.x) {
         refm[x] = A.refmask[x];
         refk[x] = A.refkind[x];
     }
-    for (int x = threadIdx.x; x < encn * 5 * 2; x += blockDim.x) {
-        const int q = x / 10, o = (x / 2) % 5, half = x & 1;
-        const double mq = A.cost[q], xq = A.cost[encn + q];
-        pre[x] = make_double2((o - 1 == 2 * half) ? mq : xq, (o - 1 == 2 * half + 1) ? mq : xq);
-    }
+    for (int x = threadIdx.x; x < encn * 5 * 4; x += blockDim.x) pre[x] = pre_record(A.cost, encn, x);
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
@@ -462,11 +464,13 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
     const int cfirst = SOLO ? 1 : wf_first_col(j, C, pad);
     const double gop = A.gop, ge = A.ge;
     const int local = A.local;
-    const int kinds = A.kinds;
     const double NEG = neg_inf();
     const bool first_lane = SOLO ? true : (j == 0);
     const double vo_last = (local && j == G - 1) ? 0.0 : gop;
     const double ve_last = (local && j == G - 1) ? 0.0 : ge;
+    /* column 0, rows i >= 1 (src/reference_align.cpp:65-74): 0 in local mode, -gap_open - gap_ext * (i - 1) otherwise --
+     * one expression for both (0 - 0 * x == 0), so the row loop has no branch on the mode */
+    const double c0base = local ? 0.0 : -gop, c0step = local ? 0.0 : ge;
     const int rstep = SOLO ? 32 : G;          /* record words between consecutive rows of one lane */
 
     constexpr int kTab = kCostEntries * 32;                   /* doubles between the tables of row A and row B */
@@ -513,14 +517,15 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
     auto fill_table = [&](double* tab, unsigned rw) {
         const unsigned q = rw & 0xffu;
         const int o = __ffs(rw >> 8);
-        const double2 ac = pre[(q * 5 + o) * 2], gt = pre[(q * 5 + o) * 2 + 1];
+        const double2* rec = pre + (q * 5 + o) * 4;
+        const double2 ac = rec[0], gt = rec[1], iu = rec[2], nn = rec[3];
         tab[0 * 32] = ac.x;
         tab[1 * 32] = ac.y;
         tab[2 * 32] = gt.x;
         tab[3 * 32] = gt.y;
-        if (kinds & 2) tab[4 * 32] = costs[2 * encn + q];
-        if (kinds & 4) tab[5 * 32] = costs[3 * encn + q];
-        if (kinds & 8) tab[6 * 32] = costs[4 * encn + q];
+        tab[4 * 32] = iu.x;
+        tab[5 * 32] = iu.y;
+        tab[6 * 32] = nn.x;
     };
 
     /* Rows i+1 (A) and i+2 (B) of this lane's C columns.  MASKED: row B may not exist (hasB false) and then must leave no
@@ -530,8 +535,8 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
         fill_table(mytab, rw2 & 0xffffu);
         fill_table(mytab + kTab, rw2 >> 16);
         {   /* column 0 feeds the first lane: src/reference_align.cpp:64-78 */
-            double c0a = 0.0, c0b = 0.0;
-            if (!local) { c0a = col0_value(0, gop, ge, i + 1); c0b = col0_value(0, gop, ge, i + 2); }
+            const double c0a = __dsub_rn(c0base, __dmul_rn(c0step, (double)i));           /* H[i+1][0] */
+            const double c0b = __dsub_rn(c0base, __dmul_rn(c0step, (double)(i + 1)));     /* H[i+2][0] */
             SlA = first_lane ? c0a : SlA;
             ElA = first_lane ? NEG : ElA;
             SlB = first_lane ? c0b : SlB;
@@ -543,12 +548,15 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
         for (int x = 0; x < (C + 7) / 8; ++x) { fa[x] = 0; fb[x] = 0; }
         /* row A, phase 1: vertical and (mis)match candidates of every column (:145-159); F updated in place.
          * SARLACC_WF_JIT_M: computed per column inside the chain loop instead (no m[] array: fewer live registers). */
-#if !SARLACC_WF_JIT_M
-        double mA[C];
-#endif
+        /* JIT: m is computed per column inside the chain loop instead (no m[] array).  Chosen per instantiation by what
+         * ptxas 12.9 makes of it: with the other form it runs out of predicate registers in the row loop of solo C = 20..22
+         * (and with this form in C = 23, 24) and spills them through P2R / LOP3 / ISETP, +10 instructions per cell
+         * (tests/test_abi.py::test_no_predicate_spills_in_row_loops watches the built library for that). */
+        constexpr bool JIT = (SOLO && C <= 22) || (SARLACC_WF_JIT_M != 0);
+        double mA[JIT ? 1 : C];
         bool p2lastA = false;
-#if !SARLACC_WF_JIT_M
-        {
+        double diagA = diag0;
+        if constexpr (!JIT) {
             double diag = diag0;
 #pragma unroll
             for (int k = 0; k < C; ++k) {
@@ -562,26 +570,24 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
                 if (TRACE) { if (p2) fa[k >> 3] |= 8u << (4 * (k & 7)); }
             }
         }
-#else
-        double diagA = diag0;
-#endif
         /* the two serial chains, interleaved: A(k) and B(k-1) */
         double dB = SlA_in;               /* H[A][column left of slot 0]: diagonal of B's slot 0 */
 #pragma unroll
         for (int k = 0; k <= C; ++k) {
             if (k < C) {
-#if SARLACC_WF_JIT_M
-                const double vO = __dsub_rn(S[k], (k == C - 1) ? vo_last : gop);
-                const double Fe = __dsub_rn(F[k], (k == C - 1) ? ve_last : ge);
-                const bool p2A = Fe > vO;
-                F[k] = p2A ? Fe : vO;
-                const double mAk = __dadd_rn(diagA, *slotp[k]);
-                diagA = (k == 0 && skip0) ? diag0 : S[k];
-                if (k == C - 1) p2lastA = p2A;
-                if (TRACE) { if (p2A) fa[k >> 3] |= 8u << (4 * (k & 7)); }
-#else
-                const double mAk = mA[k];
-#endif
+                double mAk;
+                if constexpr (JIT) {
+                    const double vO = __dsub_rn(S[k], (k == C - 1) ? vo_last : gop);
+                    const double Fe = __dsub_rn(F[k], (k == C - 1) ? ve_last : ge);
+                    const bool p2A = Fe > vO;
+                    F[k] = p2A ? Fe : vO;
+                    mAk = __dadd_rn(diagA, *slotp[k]);
+                    diagA = (k == 0 && skip0) ? diag0 : S[k];
+                    if (k == C - 1) p2lastA = p2A;
+                    if (TRACE) { if (p2A) fa[k >> 3] |= 8u << (4 * (k & 7)); }
+                } else {
+                    mAk = mA[k];
+                }
                 const double hO = __dsub_rn(SlA, gop);
                 const double Ee = __dsub_rn(ElA, ge);
                 const bool p1 = Ee > hO;
@@ -890,6 +896,8 @@ struct FlagReader {
     long long a;
     int len;
     const int* colinfo;   /* wavefront / solo layouts: per DP column, (word offset j*(kSkew*G+1)) << 8 | (bit shift 4k) */
+    const void* flags;    /* the record planes of the source this alignment reads (TraceArgs::sel) */
+    const void* flags_hi;
     __device__ unsigned get(int i, int c) const {
         if (T.layout != 1) {
             const int ci = colinfo[c];
@@ -898,15 +906,15 @@ struct FlagReader {
                                                 : ((a >> 5) * T.fstride + i) * 32 + (a & 31);
             const int sh = ci & 0xff;
             if (sh >= 64) {       /* columns 16.. of the lane live in the second plane */
-                const unsigned v = (T.hi_bytes == 1) ? (unsigned)reinterpret_cast<const uint8_t*>(T.flags_hi)[w]
-                                                     : reinterpret_cast<const uint32_t*>(T.flags_hi)[w];
+                const unsigned v = (T.hi_bytes == 1) ? (unsigned)reinterpret_cast<const uint8_t*>(flags_hi)[w]
+                                                     : reinterpret_cast<const uint32_t*>(flags_hi)[w];
                 return (v >> (sh - 64)) & 15u;
             }
             /* the low word is wordbytes wide; slot k lives in its 32-bit part k/8 */
-            const uint32_t* base = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(T.flags) + w * T.wordbytes);
+            const uint32_t* base = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(flags) + w * T.wordbytes);
             return (base[sh >> 5] >> (sh & 31)) & 15u;
         }
-        return reinterpret_cast<const uint8_t*>(T.flags)[a * T.fstride + (long long)(c - 1) * len + (i - 1)];
+        return reinterpret_cast<const uint8_t*>(flags)[a * T.fstride + (long long)(c - 1) * len + (i - 1)];
     }
 };
 
@@ -924,11 +932,15 @@ __global__ void __launch_bounds__(128) traceback(const TraceArgs T)
     }
     const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= T.n) return;
-    if (T.skip && T.skip[a] == T.skip_if) return;   /* the strand .resolve_strand dropped: nobody reads these coordinates */
+    /* fused both-ends runs: the records of (adaptor, front window) and (adaptor, back window) are both on the device and
+     * only the strand .resolve_strand kept is walked (sel[a] != 0: the second source) */
+    const bool alt = T.sel != nullptr && T.sel[a] != 0;
     const int L = T.L;
-    const int len = T.lens[a];
+    const int len = alt ? T.lens2[a] : T.lens[a];
+    const int32_t* endrow = alt ? T.endrow2 : T.endrow;
     const long long n = T.n;
-    FlagReader R{T, a, len, tb_colinfo};
+    const long long pitch = T.out_pitch > 0 ? T.out_pitch : n;
+    FlagReader R{T, a, len, tb_colinfo, alt ? T.flags2 : T.flags, alt ? T.flags_hi2 : T.flags_hi};
     int32_t* map = T.map + a;        /* map[c*n]: (row << 1) | is_match, fill_map's mapping (:280-305) */
     uint8_t* ops = T.ops ? T.ops + a * T.ops_stride : nullptr;
     int nops = 0;
@@ -942,9 +954,9 @@ __global__ void __launch_bounds__(128) traceback(const TraceArgs T)
     enum { ST_H = 0, ST_E = 1, ST_F = 2 };
     int i = len, c = L, state = ST_H;
     bool pending = false;   /* p1 (in ST_E) / p2 (in ST_F) of the cell the current run came from */
-    if (T.endrow && len > 0 && L > 0) {
+    if (endrow && len > 0 && L > 0) {
         /* the forward kernel already followed the climb up the last column (land_step): skip those up-moves */
-        i = T.endrow[a];
+        i = endrow[a];
         for (int x = i; x < len; ++x) {
             if (ops) ops[nops] = 'I';
             ++nops;
@@ -1006,13 +1018,18 @@ __global__ void __launch_bounds__(128) traceback(const TraceArgs T)
         const int m1 = map[n], mL = map[(long long)L * n];
         const int first = (m1 >> 1) - 1;
         const int second = (mL >> 1) + (mL & 1) - 1;
+        int st = 0, en = 0;
         if (first < second) {
-            T.start[a] = first + 1;
-            T.end[a] = second;
-        } else {
-            T.start[a] = 0;
-            T.end[a] = 0;
+            st = first + 1;
+            en = second;
         }
+        if (T.width) {     /* adaptor2 into read coordinates: width - x + 1 (R/adaptorAlign.R:66-71; unaligned 0 -> width + 1) */
+            const int w = T.width[a];
+            st = w - st + 1;
+            en = w - en + 1;
+        }
+        T.start[a] = st;
+        T.end[a] = en;
     }
     for (int s = 0; s < T.nsec; ++s) {
         const int rs = T.sec_starts[s];
@@ -1030,8 +1047,8 @@ __global__ void __launch_bounds__(128) traceback(const TraceArgs T)
         } else {
             curend = map[(long long)re * n] >> 1;
         }
-        T.sec_start[(long long)s * n + a] = curstart;            /* (curstart-1) + 1 */
-        T.sec_width[(long long)s * n + a] = curend - curstart;
+        T.sec_start[(long long)s * pitch + a] = curstart;        /* (curstart-1) + 1 */
+        T.sec_width[(long long)s * pitch + a] = curend - curstart;
     }
 }
 
@@ -1070,85 +1087,200 @@ __global__ void resolve_select(const SelectArgs S)
     }
 }
 
-__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {   /* splitmix64 finaliser */
-    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
-    return x ^ (x >> 31);
+/* .resolve_strand alone (R/adaptorAlign.R:112-122), on four score vectors: reversed = fscore < rscore (strict), and
+ * the two scores R keeps (ifelse(is.reverse, revcomp, forward), R/getAdaptorThresholds.R:123-127 / R/adaptorAlign.R:192-196).
+ * Run between the forward passes and the tracebacks of a fused both-ends run, so that only the kept strand is walked. */
+__global__ void resolve_strand(const StrandArgs S)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.n) return;
+    const double s1 = S.a1_front[i], s2 = S.a2_back[i], r1 = S.a1_back[i], r2 = S.a2_front[i];
+    const double f = __dadd_rn(fmax(s1, 0.0), fmax(s2, 0.0));
+    const double r = __dadd_rn(fmax(r1, 0.0), fmax(r2, 0.0));
+    const bool rev = f < r;
+    if (S.reversed) S.reversed[i] = rev ? 1 : 0;
+    S.score1[i] = rev ? r1 : s1;
+    S.score2[i] = rev ? r2 : s2;
 }
 
-/* One warp per window: keys in shared memory, rank by counting (len <= a few hundred, so O(len^2 / 32) per lane). */
-__global__ void __launch_bounds__(128) scramble_rows(const uint16_t* in, uint16_t* out, const int32_t* lens, long long n, int stride,
-        unsigned long long seed, unsigned long long first_index, const unsigned long long* read_index, unsigned long long stream_id)
+/* ---- counter-based randomness shared by the scramble and the synthetic-read generator ----------------------------
+ * 32-bit integer hashing only (two multiplies per word), so that sarlacc_b200/synth.py and api.py reproduce every draw
+ * bit for bit with numpy uint32 arithmetic.  A stream is keyed by (seed, global read index, field); word p of it is
+ * hash32(key ^ (p * 0x9E3779B1 + 0x7F4A7C15)). */
+__host__ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x21F0AAADu;
+    x ^= x >> 15;
+    x *= 0x735A2D97u;
+    x ^= x >> 15;
+    return x;
+}
+
+__host__ __device__ __forceinline__ uint32_t stream_key(unsigned long long seed, unsigned long long index, uint32_t field) {
+    uint32_t k = hash32((uint32_t)seed ^ 0x243F6A88u);
+    k = hash32(k ^ (uint32_t)(seed >> 32));
+    k = hash32(k ^ (uint32_t)index);
+    k = hash32(k ^ (uint32_t)(index >> 32));
+    return hash32(k ^ (field * 0x85EBCA6Bu + 0xC2B2AE35u));
+}
+
+__host__ __device__ __forceinline__ uint32_t stream_word(uint32_t key, uint32_t p) {
+    return hash32(key ^ (p * 0x9E3779B1u + 0x7F4A7C15u));
+}
+
+/* .scramble_input (R/getAdaptorThresholds.R:68-92) on packed rows: a Fisher-Yates shuffle of the window, bases and
+ * qualities moving together (one 16-bit entry each).  for i = len-1 .. 1: j = floor(word_i * (i + 1) / 2^32); swap(i, j),
+ * words from the stream keyed by (seed, read index, field 16 + stream_id): a uniform random permutation that depends on
+ * nothing but those, so chunking, sharding and device count do not change it (api.py: _scramble_input is the host
+ * mirror).  One thread per window, the window in shared memory as [entry][thread] (pitch TPB + 2 entries: the transposing
+ * loads and stores of a warp then hit 32 different banks). */
+template <int TPB>
+__global__ void __launch_bounds__(TPB) scramble_rows_fy(const uint16_t* in, uint16_t* out, const int32_t* lens, long long n, int stride,
+        unsigned long long seed, unsigned long long first_index, const unsigned long long* read_index, unsigned stream_id)
 {
-    extern __shared__ unsigned long long sk[];   /* [warps][stride] */
+    extern __shared__ uint16_t swin[];          /* [stride][TPB + 2] */
+    constexpr int P = TPB + 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned long long* keys = sk + (size_t)warp * stride;
-    for (long long a = (long long)blockIdx.x * (blockDim.x >> 5) + warp; a < n; a += (long long)gridDim.x * (blockDim.x >> 5)) {
-        const int len = lens[a];
-        const unsigned long long rid = read_index ? read_index[a] : first_index + (unsigned long long)a;
-        const unsigned long long base = mix64(rid * 0x9E3779B97F4A7C15ULL + seed);
-        for (int i = lane; i < len; i += 32) {
-            keys[i] = mix64(base ^ ((unsigned long long)i * 0xD1B54A32D192ED03ULL + stream_id * 0x8CB92BA72F3D8DD7ULL));
+    for (long long base = (long long)blockIdx.x * TPB; base < n; base += (long long)gridDim.x * TPB) {
+        /* load: each warp brings in its own 32 windows, 32 consecutive entries of one window per instruction */
+        for (int w = 0; w < 32; ++w) {
+            const long long a = base + warp * 32 + w;
+            if (a >= n) break;
+            const int len = lens[a];
+            const uint16_t* src = in + a * (long long)stride;
+            for (int e = lane; e < len; e += 32) swin[e * P + warp * 32 + w] = src[e];
         }
         __syncwarp();
-        const uint16_t* src = in + a * (long long)stride;
-        uint16_t* dst = out + a * (long long)stride;
-        for (int i = lane; i < len; i += 32) {
-            const unsigned long long ki = keys[i];
-            int rank = 0;
-            for (int j = 0; j < len; ++j) {
-                const unsigned long long kj = keys[j];
-                rank += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
+        {
+            const long long a = base + threadIdx.x;
+            if (a < n) {
+                const int len = lens[a];
+                const unsigned long long rid = read_index ? read_index[a] : first_index + (unsigned long long)a;
+                const uint32_t key = stream_key(seed, rid, 16u + stream_id);
+                uint16_t* mine = swin + threadIdx.x;
+                for (int i = len - 1; i >= 1; --i) {
+                    const uint32_t j = __umulhi(stream_word(key, (uint32_t)i), (uint32_t)(i + 1));
+                    const uint16_t x = mine[i * P], y = mine[j * P];
+                    mine[i * P] = y;
+                    mine[j * P] = x;
+                }
             }
-            dst[rank] = src[i];
+        }
+        __syncwarp();
+        for (int w = 0; w < 32; ++w) {
+            const long long a = base + warp * 32 + w;
+            if (a >= n) break;
+            const int len = lens[a];
+            uint16_t* dst = out + a * (long long)stride;
+            for (int e = lane; e < stride; e += 32) dst[e] = e < len ? swin[e * P + warp * 32 + w] : (uint16_t)0;
         }
         __syncwarp();
     }
 }
 
-/* The same permutation by sorting: one warp sorts the window's (key, position) pairs with a bitonic network in shared
- * memory (NP = window slots rounded up to a power of two, pads sort last), then slot p of the output takes the element
- * whose pair landed at p -- rank(i) of the counting kernel above, in log^2 instead of len compare steps per element
- * (250-base windows: 36 x 4 compare-exchanges per lane instead of 8 x 250 comparisons). */
-template <int NP>
-__global__ void __launch_bounds__(128) scramble_rows_sorted(const uint16_t* in, uint16_t* out, const int32_t* lens, long long n, int stride,
-        unsigned long long seed, unsigned long long first_index, const unsigned long long* read_index, unsigned long long stream_id)
+/* The same shuffle in place in global memory, for windows too long for the shared-memory kernel. */
+__global__ void __launch_bounds__(128) scramble_rows_fy_global(const uint16_t* in, uint16_t* out, const int32_t* lens, long long n, int stride,
+        unsigned long long seed, unsigned long long first_index, const unsigned long long* read_index, unsigned stream_id)
 {
-    __shared__ unsigned long long skeys[4][NP];
-    __shared__ uint16_t sidx[4][NP];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned long long* keys = skeys[warp];
-    uint16_t* idx = sidx[warp];
-    for (long long a = (long long)blockIdx.x * 4 + warp; a < n; a += (long long)gridDim.x * 4) {
-        const int len = lens[a];
-        const unsigned long long rid = read_index ? read_index[a] : first_index + (unsigned long long)a;
-        const unsigned long long base = mix64(rid * 0x9E3779B97F4A7C15ULL + seed);
-        for (int i = lane; i < NP; i += 32) {
-            keys[i] = i < len ? mix64(base ^ ((unsigned long long)i * 0xD1B54A32D192ED03ULL + stream_id * 0x8CB92BA72F3D8DD7ULL)) : ~0ULL;
-            idx[i] = (uint16_t)i;
+    const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const int len = lens[a];
+    const uint16_t* src = in + a * (long long)stride;
+    uint16_t* dst = out + a * (long long)stride;
+    for (int e = 0; e < stride; ++e) dst[e] = e < len ? src[e] : (uint16_t)0;
+    const unsigned long long rid = read_index ? read_index[a] : first_index + (unsigned long long)a;
+    const uint32_t key = stream_key(seed, rid, 16u + stream_id);
+    for (int i = len - 1; i >= 1; --i) {
+        const uint32_t j = __umulhi(stream_word(key, (uint32_t)i), (uint32_t)(i + 1));
+        const uint16_t x = dst[i], y = dst[j];
+        dst[i] = y;
+        dst[j] = x;
+    }
+}
+
+/* ---- synthetic reads on the device: the mockReads generator (R/mockReads.R:58-92) ------------------------------------
+ * One thread per (read, end).  The front window of an unflipped read is the first `tol` bases of the mutated molecule
+ * adaptor1 (first N-run <- one random base repeated, :50, or a barcode; other ambiguous positions <- random bases) +
+ * random insert; its back window (already reverse-complemented, as .get_front_and_back hands it over) is the first `tol`
+ * bases of mutated adaptor2 + random insert (:58-64).  Per molecule base: substituted by a uniform base w.p. sub_rate
+ * (:73-74), then w.p. indel_rate replaced by 0 or 2..max_insert copies of itself (:77-79).  Qualities are iid Phred of
+ * U(0, max_err) through an integer threshold table built on the host (:82); half of the reads are flipped (:91-92), which
+ * swaps the two windows.  Every draw is stream_word(stream_key(seed, read index, field), position): the read depends on
+ * (seed, index) only -- sarlacc_b200/synth.py: mock_windows is the numpy mirror, bit for bit.
+ * Fields: 0/4 molecule fill (front/back molecule), 1/5 mutation, 2/6 count choice, 3/7 quality, 8 flip, 9 width. */
+__device__ __forceinline__ unsigned mock_quality(uint32_t h, const MockArgs& M) {
+    unsigned q = M.qmin;
+    while (q < 93u && h < M.qthr[q + 1]) ++q;      /* P(Q >= k) falls by 10^-0.1 per step: ~4 iterations on average */
+    return q;
+}
+
+__global__ void __launch_bounds__(128) mock_windows_kernel(const __grid_constant__ MockArgs M)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * M.n) return;
+    const long long r = t >> 1;
+    const int mol = (int)(t & 1);                           /* 0: adaptor1 molecule, 1: adaptor2 molecule */
+    const unsigned long long rid = M.first_index + (unsigned long long)r;
+    const bool flip = (stream_word(stream_key(M.seed, rid, 8u), 0u) >> 31) != 0u;
+    const bool to_front = (mol == 0) != flip;
+    uint16_t* row = (to_front ? M.front : M.back) + r * (long long)M.stride;
+    const char* ad = mol == 0 ? M.adaptor1 : M.adaptor2;
+    const int alen = mol == 0 ? M.len1 : M.len2;
+    const int run0 = mol == 0 ? M.run0_start : -1, run1 = mol == 0 ? M.run0_end : -1;
+    const uint32_t kfill = stream_key(M.seed, rid, 0u + 4u * mol), kmut = stream_key(M.seed, rid, 1u + 4u * mol);
+    const uint32_t kcnt = stream_key(M.seed, rid, 2u + 4u * mol), kq = stream_key(M.seed, rid, 3u + 4u * mol);
+    const unsigned barcode_base = stream_word(kfill, 0xFFFFFFFFu) & 3u;
+    const unsigned barcode_pick = M.nbarcodes > 0 ? stream_word(kfill, 0xFFFFFFFEu) % (unsigned)M.nbarcodes : 0u;
+    int emitted = 0;
+    uint32_t acc[4] = {0u, 0u, 0u, 0u};                     /* eight 16-bit entries per 128-bit store */
+    for (uint32_t p = 0; emitted < M.tol; ++p) {
+        unsigned b;
+        const char c = p < (uint32_t)alen ? ad[p] : 'N';
+        if (c == 'A') b = 0; else if (c == 'C') b = 1; else if (c == 'G') b = 2; else if (c == 'T') b = 3;
+        else if ((int)p >= run0 && (int)p < run1) b = M.nbarcodes > 0 ? (unsigned)M.barcodes[barcode_pick * (run1 - run0) + ((int)p - run0)] : barcode_base;
+        else b = stream_word(kfill, p) & 3u;
+        const uint32_t u = stream_word(kmut, p);
+        if ((u >> 16) < M.sub_thr) b = (u >> 2) & 3u;       /* substitution: a uniform base (may be the same one) */
+        int copies = 1;
+        if ((u & 0xFFFFu) < M.indel_thr) {                  /* indel: 0 or 2..max_insert copies */
+            const uint32_t k = stream_word(kcnt, p) % (uint32_t)M.max_insert;
+            copies = k == 0 ? 0 : (int)k + 1;
         }
-        __syncwarp();
-        for (int k = 2; k <= NP; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int t = lane; t < NP / 2; t += 32) {
-                    const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));     /* t-th index with bit j clear */
-                    const int hi = lo | j;
-                    const bool up = (lo & k) == 0;
-                    const unsigned long long ka = keys[lo], kb = keys[hi];
-                    const unsigned ia = idx[lo], ib = idx[hi];
-                    const bool gt = ka > kb || (ka == kb && ia > ib);           /* (key, position): ties by position */
-                    if (gt == up) {
-                        keys[lo] = kb; keys[hi] = ka;
-                        idx[lo] = (uint16_t)ib; idx[hi] = (uint16_t)ia;
-                    }
-                }
-                __syncwarp();
+        for (int x = 0; x < copies && emitted < M.tol; ++x) {
+            const unsigned q = mock_quality(stream_word(kq, (uint32_t)emitted), M);
+            const uint32_t entry = ((1u << b) << 8) | q;
+            acc[(emitted & 7) >> 1] |= entry << (16 * (emitted & 1));
+            ++emitted;
+            if ((emitted & 7) == 0) {
+                *reinterpret_cast<uint4*>(row + emitted - 8) = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+                acc[0] = acc[1] = acc[2] = acc[3] = 0u;
             }
         }
-        const uint16_t* src = in + a * (long long)stride;
-        uint16_t* dst = out + a * (long long)stride;
-        for (int p = lane; p < len; p += 32) dst[p] = src[idx[p]];
-        __syncwarp();
+    }
+    /* tail of the last 8-entry group and zero padding up to the row stride */
+    for (int e = emitted & ~7; e < M.stride; e += 8) {
+        *reinterpret_cast<uint4*>(row + e) = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+        acc[0] = acc[1] = acc[2] = acc[3] = 0u;
+    }
+    if (mol == 0) {
+        M.lens_front[r] = M.tol;
+        M.lens_back[r] = M.tol;
+        /* read width = mutated length of adaptor1 + insert + adaptor2: every base independently an indel w.p. indel_rate,
+         * changing the length by -1 or +1..max_insert-1; four bases per stream word (16-bit fields) */
+        const uint32_t kw = stream_key(M.seed, rid, 9u);
+        int width = M.molecule_len;
+        for (int p4 = 0; p4 * 4 < M.molecule_len; ++p4) {
+            const uint32_t lo = stream_word(kw, 2u * p4), hi = stream_word(kw, 2u * p4 + 1u);
+            const uint32_t f[4] = {lo & 0xFFFFu, lo >> 16, hi & 0xFFFFu, hi >> 16};
+            for (int x = 0; x < 4 && p4 * 4 + x < M.molecule_len; ++x) {
+                if (f[x] < M.indel_thr) {
+                    const uint32_t k = stream_word(kw, 0x80000000u + (uint32_t)(p4 * 4 + x)) % (uint32_t)M.max_insert;
+                    width += k == 0 ? -1 : (int)k;
+                }
+            }
+        }
+        M.width[r] = width;
+        if (M.flipped) M.flipped[r] = flip ? 1 : 0;
     }
 }
 
@@ -1256,8 +1388,9 @@ bool for_geometry(int C, bool solo, F&& f) {
 }  // namespace
 
 size_t wavefront_smem_bytes(const AlignArgs& a) {
-    return sizeof(double) * ((((size_t)a.L + 1 + 5 * (size_t)a.enc_n + (size_t)(kBlock / 32) * 2 * kCostEntries * 32 + 1) & ~(size_t)1) +
-                             (size_t)a.enc_n * 5 * 4) +
+    /* row-0 chain + lane-private tables (two rows' worth: the row-pair kernel) + 64-byte cost records + reference columns */
+    return sizeof(double) * ((((size_t)a.L + 1 + (size_t)(kBlock / 32) * 2 * kCostEntries * 32 + 1) & ~(size_t)1) +
+                             (size_t)a.enc_n * 5 * 8) +
            2 * (size_t)a.nref * a.L;
 }
 
@@ -1309,27 +1442,45 @@ void launch_scramble(const uint16_t* in, uint16_t* out, const int32_t* lens, lon
                      unsigned long long stream_id, cudaStream_t st)
 {
     if (n <= 0) return;
-    {
-        long long g = (n + 3) / 4;
-        if (g > 148 * 64) g = 148 * 64;
-        if (std::getenv("SARLACC_SCRAMBLE_COUNTING") == nullptr) {     /* A/B: the rank-counting kernel */
-            if (stride <= 256) { scramble_rows_sorted<256><<<(int)g, 128, 0, st>>>(in, out, lens, n, stride, seed, first_index, read_index, stream_id); return; }
-            if (stride <= 512) { scramble_rows_sorted<512><<<(int)g, 128, 0, st>>>(in, out, lens, n, stride, seed, first_index, read_index, stream_id); return; }
-            if (stride <= 1024) { scramble_rows_sorted<1024><<<(int)g, 128, 0, st>>>(in, out, lens, n, stride, seed, first_index, read_index, stream_id); return; }
-        }
-    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    auto launch = [&](auto tag) {
+        constexpr int TPB = decltype(tag)::value;
+        const size_t smem = sizeof(uint16_t) * (size_t)stride * (TPB + 2);
+        cudaFuncSetAttribute(scramble_rows_fy<TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int per = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, scramble_rows_fy<TPB>, TPB, smem);
+        long long grid = (n + TPB - 1) / TPB;
+        if (grid > (long long)sms * (per < 1 ? 1 : per)) grid = (long long)sms * (per < 1 ? 1 : per);
+        scramble_rows_fy<TPB><<<(int)grid, TPB, smem, st>>>(in, out, lens, n, stride, seed, first_index, read_index, (unsigned)stream_id);
+    };
+    const size_t budget = 200u << 10;
+    if (sizeof(uint16_t) * (size_t)stride * (128 + 2) <= budget / 2) launch(std::integral_constant<int, 128>());      /* two blocks per SM */
+    else if (sizeof(uint16_t) * (size_t)stride * (64 + 2) <= budget) launch(std::integral_constant<int, 64>());
+    else if (sizeof(uint16_t) * (size_t)stride * (32 + 2) <= budget) launch(std::integral_constant<int, 32>());
+    else scramble_rows_fy_global<<<(int)((n + 127) / 128), 128, 0, st>>>(in, out, lens, n, stride, seed, first_index, read_index, (unsigned)stream_id);
+}
+
+void launch_resolve_strand(const StrandArgs& s, cudaStream_t st) {
+    const int block = 256;
+    const int grid = (int)((s.n + block - 1) / block);
+    if (grid > 0) resolve_strand<<<grid, block, 0, st>>>(s);
+}
+
+void launch_mock_windows(const MockArgs& m, cudaStream_t st) {
+    if (m.n <= 0) return;
     const int block = 128;
-    const size_t smem = sizeof(unsigned long long) * (size_t)(block / 32) * stride;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(scramble_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    long long grid = (n + (block / 32) - 1) / (block / 32);
-    if (grid > 148 * 64) grid = 148 * 64;
-    scramble_rows<<<(int)grid, block, smem, st>>>(in, out, lens, n, stride, seed, first_index, read_index, stream_id);
+    mock_windows_kernel<<<(int)((2 * m.n + block - 1) / block), block, 0, st>>>(m);
 }
 
 void launch_pack_rows(const PackArgs& a, cudaStream_t st) {
     if (a.n <= 0) return;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     long long grid = (a.n + 7) / 8;
-    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid > (long long)sms * 16) grid = (long long)sms * 16;
     pack_rows_kernel<<<(int)grid, 256, 0, st>>>(a);
 }
 

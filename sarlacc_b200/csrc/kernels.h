@@ -88,8 +88,15 @@ struct TraceArgs {
     const void* flags_hi;
     long long fstride;
     const int32_t* endrow;      /* [n] optional: start the walk at (endrow[a], L) instead of (len, L) */
-    const uint8_t* skip;        /* [n] optional: alignments with skip[a] == skip_if are not walked (the strand .resolve_strand dropped) */
-    int skip_if;
+    /* fused both-ends runs: a second source (the same adaptor on the other window set) and, per alignment, which of the
+     * two .resolve_strand kept (0: lens/flags/endrow, 1: lens2/flags2/endrow2; sel == null: always the first) */
+    const uint8_t* sel;
+    const int32_t* lens2;
+    const void* flags2;
+    const void* flags_hi2;
+    const int32_t* endrow2;
+    const int32_t* width;       /* optional read widths: start/end are flipped to width - x + 1 (R/adaptorAlign.R:66-71) */
+    long long out_pitch;        /* row pitch of sec_start / sec_width (0: n) */
     int nsec;
     const int32_t* sec_starts;  /* device, 0-based */
     const int32_t* sec_ends;    /* device, 1-based */
@@ -124,9 +131,39 @@ struct SelectArgs {
 };
 void launch_resolve_select(const SelectArgs& s, cudaStream_t st);
 
-/* .scramble_input (R/getAdaptorThresholds.R:68-92) on packed rows: out[a][rank(i)] = in[a][i], where rank orders the
- * counter-based keys mix64(mix64(index_a * K1 + seed) ^ (i * K2 + stream * K3)) (ties by position) -- the same
- * permutation sarlacc_b200/api.py:_scramble_input builds on the host. */
+/* .resolve_strand on four device score vectors (R/adaptorAlign.R:112-122): reversed (may be null) and the two kept scores. */
+struct StrandArgs {
+    long long n;
+    const double* a1_front; const double* a2_back; const double* a1_back; const double* a2_front;
+    uint8_t* reversed;
+    double* score1; double* score2;
+};
+void launch_resolve_strand(const StrandArgs& s, cudaStream_t st);
+
+/* Synthetic mockReads-style windows generated on the device (R/mockReads.R:58-92; kernels.cu: mock_windows_kernel). */
+struct MockArgs {
+    long long n;
+    unsigned long long seed, first_index;
+    int tol, stride;
+    uint16_t* front; uint16_t* back;       /* packed rows [n][stride] */
+    int32_t* lens_front; int32_t* lens_back; int32_t* width;
+    uint8_t* flipped;                      /* optional */
+    int len1, len2;                        /* adaptor lengths (<= 128) */
+    int run0_start, run0_end;              /* adaptor1's first N-run (the barcode slot); -1, -1 if none */
+    int nbarcodes;                         /* 0: the slot holds one random base repeated (R/mockReads.R:50) */
+    const uint8_t* barcodes;               /* device: [nbarcodes][run0_end - run0_start] base codes 0..3 */
+    int molecule_len;                      /* adaptor1 + insert + adaptor2 before mutation */
+    int max_insert;
+    uint32_t sub_thr, indel_thr;           /* 16-bit thresholds: floor(rate * 65536) */
+    uint32_t qmin;                         /* smallest quality that can occur */
+    uint32_t qthr[95];                     /* quality >= k  <=>  word < qthr[k]  (k = 0..93; qthr[94] = 0) */
+    char adaptor1[128]; char adaptor2[128];
+};
+void launch_mock_windows(const MockArgs& m, cudaStream_t st);
+
+/* .scramble_input (R/getAdaptorThresholds.R:68-92) on packed rows: a Fisher-Yates shuffle per window driven by the
+ * counter-based stream of (seed, read index, stream_id) (kernels.cu: scramble_rows_fy) -- the same permutation
+ * sarlacc_b200/api.py:_scramble_input builds on the host. */
 void launch_scramble(const uint16_t* in, uint16_t* out, const int32_t* lens, long long n, int stride,
                      unsigned long long seed, unsigned long long first_index, const unsigned long long* read_index,
                      unsigned long long stream_id, cudaStream_t st);

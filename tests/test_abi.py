@@ -93,3 +93,24 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cpp", ".cu", ".h", ".cuh")) or f == "Makefile":
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in text.lower(), os.path.join(dirpath, f)
+
+
+def test_no_predicate_spills_in_row_loops():
+    """ptxas sometimes runs out of predicate registers in the unrolled row loop of a forward kernel and spills them
+    through P2R + LOP3 + ISETP (ten extra instructions per DP cell, sarlacc_b200/csrc/kernels.cu: JIT).  A healthy
+    instantiation has a handful of P2R outside the loop; this watches the built library for the pathology."""
+    import collections
+    import subprocess
+    from sarlacc_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    cur, count = None, collections.Counter()
+    for line in out.stdout.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip()
+        elif " P2R " in line and cur and "wf_forward" in cur:
+            count[cur] += 1
+    assert count, "no forward kernels found in the library"
+    bad = {k: v for k, v in count.items() if v > 16}
+    assert not bad, bad

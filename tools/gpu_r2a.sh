@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call A: parity suite on the new record layout + solo geometry, A/B of the a2 kernels
-tag=r2a
+tag=${1:-r2b}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$tag.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_$tag.log
