@@ -192,6 +192,64 @@ const char* sarlacc_resident_last_kernel(const sarlacc_resident* r);
 void   sarlacc_resident_set_timing(sarlacc_resident* r, int on);
 double sarlacc_resident_forward_ms(sarlacc_resident* r);
 
+/* ---- chunks: device-resident reads, re-loaded in place (BASELINE.json configs[2] and configs[4]) -----
+ * One chunk is to this library what one FastqStreamer yield() is to the R drivers (R/adaptorAlign.R:26-48,
+ * R/getAdaptorThresholds.R:35-48): up to `capacity` reads whose front and back windows (.get_front_and_back,
+ * R/adaptorAlign.R:86-95) sit packed in HBM.  Loading replaces the contents in place; the two passes below are the
+ * bodies of the per-chunk workers:
+ *     sarlacc_chunk_adaptor_align     .align_AA_internal (R/adaptorAlign.R:178-199) + adaptor2's coordinate flip (:66-71)
+ *     sarlacc_chunk_scrambled_scores  .align_AT_internal (R/getAdaptorThresholds.R:105-128)
+ * Every call only ENQUEUES work on the chunk's streams; outputs may be host (ideally page-locked) or device pointers and
+ * are complete when sarlacc_chunk_sync returns, so the copy-out of one chunk overlaps the alignment of the next.  Output
+ * pointers may be NULL.  Section matrices are [nsec][out_pitch] (out_pitch >= reads in the chunk: the caller may point
+ * into the columns of one big result table).  Results are those of composing the four reference calls
+ * (tests/test_gpu_chunk.py): only the strand .resolve_strand keeps is ever walked back, which the R code computes and
+ * then discards. */
+typedef struct sarlacc_chunk sarlacc_chunk;
+sarlacc_chunk* sarlacc_chunk_create(int device, int64_t capacity, int tolerance, const sarlacc_encoding* encoding);
+void    sarlacc_chunk_free(sarlacc_chunk* c);
+int64_t sarlacc_chunk_n(const sarlacc_chunk* c);
+/* Host reads in.  tolerance == 0: `front` / `back` are the windows as .get_front_and_back made them (back already
+ * reverse-complemented) and `width` the read widths or NULL (then adaptor2's coordinates stay window-relative);
+ * tolerance > 0: `front` holds WHOLE reads, `back` must be NULL, both windows are cut by the packer.  Returns the
+ * reference's per-read errors ("sequence and quality strings should have the same length", "quality cannot be lower
+ * than smallest encoded value") before anything is aligned. */
+int sarlacc_chunk_load_reads(sarlacc_chunk* c, const sarlacc_reads* front, const sarlacc_reads* back, int tolerance, const int32_t* width);
+/* Synthetic reads generated on the device: the mockReads recipe (R/mockReads.R:58-92) with a counter-based generator
+ * keyed by (seed, first_index + i), so read i of a run is the same whatever the chunking, sharding or device count;
+ * sarlacc_b200/synth.py: mock_windows is its host mirror, bit for bit.  barcodes may be NULL (the barcode slot -- adaptor1's
+ * first N run -- then holds one random base repeated, :50).  Only the two windows and the read width are materialised. */
+int sarlacc_chunk_load_mock(sarlacc_chunk* c, int64_t n, uint64_t first_index, uint64_t seed,
+        const char* adaptor1, const char* adaptor2, int insert_len, const char* const* barcodes, int nbarcodes,
+        double sub_rate, double indel_rate, int max_insert);
+int sarlacc_chunk_adaptor_align(sarlacc_chunk* c, double gapopen, double gapext, const char* adaptor1, const char* adaptor2,
+        int nsec1, const int32_t* sec_starts1, const int32_t* sec_ends1,
+        int nsec2, const int32_t* sec_starts2, const int32_t* sec_ends2,
+        int64_t out_pitch, int32_t* read_width, uint8_t* reversed,
+        double* score1, int32_t* start1, int32_t* end1, int32_t* sec_start1, int32_t* sec_width1,
+        double* score2, int32_t* start2, int32_t* end2, int32_t* sec_start2, int32_t* sec_width2);
+/* scramble != 0: both windows of every read are permuted first (.scramble_input, R/getAdaptorThresholds.R:68-92; the
+ * permutation of read i depends on (seed, read_index[i] or first_index + i) only -- sarlacc_b200/api.py: _scramble_by_index
+ * is the host mirror); scramble == 0 scores the windows as loaded (.get_alignment_scores, R/tuneAlignment.R:99-112).
+ * score1 / score2 receive ifelse(is.reverse, revcomp score, forward score) per adaptor. */
+int sarlacc_chunk_scrambled_scores(sarlacc_chunk* c, double gapopen, double gapext, const char* adaptor1, const char* adaptor2,
+        uint64_t seed, uint64_t first_index, const uint64_t* read_index, int scramble, double* score1, double* score2);
+int sarlacc_chunk_sync(sarlacc_chunk* c);
+/* Tests / reports: packed rows (uint16[n][stride]) of window set `which` (0 front, 1 back, 2 scrambled front,
+ * 3 scrambled back), window lengths, read widths, strand flips of the generator; any pointer may be NULL. */
+int sarlacc_chunk_rows(sarlacc_chunk* c, int which, uint16_t* rows, int32_t* lens, int* stride, int32_t* width, uint8_t* flipped);
+/* Phase accounting with CUDA events on the chunk's compute stream: ms4 = {load / generate, adaptor_align forward passes,
+ * scramble, score-only passes} summed since timing was switched on. */
+void sarlacc_chunk_set_timing(sarlacc_chunk* c, int on);
+int  sarlacc_chunk_phase_ms(sarlacc_chunk* c, double* ms4);
+const char* sarlacc_chunk_last_kernel(const sarlacc_chunk* c, int adaptor);   /* forward kernel of adaptor 0 / 1 in the last adaptor_align */
+
+/* .compute_threshold (R/getAdaptorThresholds.R:94-103): both vectors sorted (device radix sort), fdr_k = (n_scr -
+ * #{scrambled <= real_k}) / (n_real - k), threshold = real[min(which(fdr <= error))]; NaN where R returns NA.  The
+ * vectors may live on the host or on `device` (e.g. gathered from all ranks); they are not modified. */
+int sarlacc_compute_threshold(const double* real, int64_t nreal, const double* scrambled, int64_t nscr, double error,
+                              int device, double* threshold);
+
 /* ---- UMI grouping ----------------------------------------------------------------
  * Replaces SEXP umi_group(umi1, thresh1, umi2, thresh2, pregroup) (src/umi_group.cpp:14-117, registered at
  * src/init.cpp:23) together with unlist(out, recursive=FALSE) of R/umiGroup.R:22: the bounded masked-Levenshtein

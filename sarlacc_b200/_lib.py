@@ -108,6 +108,28 @@ def _load():
     lib.sarlacc_lists_free.restype = None
     lib.sarlacc_lists_free.argtypes = [C.c_void_p]
     lib.sarlacc_pack_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    lib.sarlacc_chunk_create.restype = C.c_void_p
+    lib.sarlacc_chunk_create.argtypes = [C.c_int, C.c_int64, C.c_int, C.POINTER(_Encoding)]
+    lib.sarlacc_chunk_free.restype = None
+    lib.sarlacc_chunk_free.argtypes = [C.c_void_p]
+    lib.sarlacc_chunk_n.restype = C.c_int64
+    lib.sarlacc_chunk_n.argtypes = [C.c_void_p]
+    lib.sarlacc_chunk_load_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.sarlacc_chunk_load_mock.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.c_uint64, C.c_char_p, C.c_char_p, C.c_int,
+                                            C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int]
+    lib.sarlacc_chunk_adaptor_align.argtypes = ([C.c_void_p, C.c_double, C.c_double, C.c_char_p, C.c_char_p,
+                                                 C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64] +
+                                                [C.c_void_p] * 12)
+    lib.sarlacc_chunk_scrambled_scores.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_char_p, C.c_char_p,
+                                                   C.c_uint64, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.sarlacc_chunk_sync.argtypes = [C.c_void_p]
+    lib.sarlacc_chunk_rows.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
+    lib.sarlacc_chunk_set_timing.restype = None
+    lib.sarlacc_chunk_set_timing.argtypes = [C.c_void_p, C.c_int]
+    lib.sarlacc_chunk_phase_ms.argtypes = [C.c_void_p, C.c_void_p]
+    lib.sarlacc_chunk_last_kernel.restype = C.c_char_p
+    lib.sarlacc_chunk_last_kernel.argtypes = [C.c_void_p, C.c_int]
+    lib.sarlacc_compute_threshold.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_void_p]
     return lib
 
 

@@ -880,7 +880,114 @@ struct FwdTimer {
     }
 };
 
-/* Enqueue forward (+ traceback) for device-resident packed reads [0,n).  Sub-chunks by scratch budget. */
+/* One forward launch over device-resident packed windows [0, m) (+ the scores of empty windows), with traceback records
+ * into S when `trace`.  Returns what a traceback of these records needs. */
+struct FwdRec {
+    AlignArgs A;
+    Geometry geo;
+    int layout = 0, wordbytes = 0, hi_bytes = 0;
+    const char* name = "";
+};
+
+FwdRec forward_once(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t st,
+        const uint16_t* d_rows, const int32_t* d_lens, long long m, int stride, int maxlen,
+        bool trace, const Outputs& out, int sms, FwdTimer* timer = nullptr)
+{
+    FwdRec R;
+    AlignArgs& A = R.A;
+    std::memset(&A, 0, sizeof(A));
+    A.rows = d_rows;
+    A.lens = d_lens;
+    A.n = m;
+    A.stride = stride;
+    A.L = P.L;
+    A.nref = P.nref;
+    A.refmask = D.refmask;
+    A.refkind = D.refkind;
+    A.local = P.local ? 1 : 0;
+    A.gop = P.gop;
+    A.ge = P.ge;
+    A.row0 = D.row0;
+    A.cost = D.cost;
+    A.enc_n = P.enc->n;
+    A.kinds = P.kinds;
+    const Geometry geo = geometry_for(P, maxlen);
+    R.geo = geo;
+    A.G = geo.G;
+    A.C = geo.C;
+    A.solo = geo.solo ? 1 : 0;
+    A.pair_rows = geo.pair;
+    A.score = out.score;
+    A.best_id = out.best_id;
+    A.best = out.best;
+    A.next_best = out.next_best;
+    if (trace) {
+        if (P.fast) {
+            const int wb = trace_word_bytes(geo.C), hb = trace_hi_bytes(geo.C, geo.solo);
+            /* record words of this launch: wavefront [alignment][row slot][lane]; solo [32 alignments][row][lane] */
+            A.fstride = geo.solo ? (long long)(maxlen + 1) : (long long)(maxlen + kSkew * geo.G) * geo.G;
+            const size_t words = geo.solo ? (size_t)((m + 31) / 32) * 32 * (size_t)A.fstride : (size_t)A.fstride * (size_t)m;
+            const size_t lo_bytes = (words * wb + 255) & ~(size_t)255;
+            S.flags.reserve(lo_bytes + words * hb);
+            S.endrow.reserve(sizeof(int32_t) * (size_t)m);
+            A.endrow = std::getenv("SARLACC_NO_ENDROW") ? nullptr : S.endrow.as<int32_t>();   /* A/B switch for profiles */
+            A.flags_hi = hb ? S.flags.as<uint8_t>() + lo_bytes : nullptr;
+            R.layout = geo.solo ? 2 : 0;
+            R.wordbytes = wb;
+            R.hi_bytes = hb;
+        } else {
+            A.fstride = (long long)std::max(1, maxlen) * P.L;
+            S.flags.reserve((size_t)A.fstride * m);
+            R.layout = 1;
+            R.wordbytes = 1;
+        }
+        A.flags = S.flags.p;
+    }
+    if (timer) timer->begin(st);
+    if (P.fast) {
+        R.name = launch_wavefront(A, trace, P.has_alt, 0, st);
+    } else {
+        long long threads = std::min<long long>(m, (long long)sms * 1024);
+        threads = (threads + 127) / 128 * 128;
+        A.gthreads = threads;
+        S.gS.reserve(sizeof(double) * (size_t)(maxlen + 1) * threads);
+        S.gE.reserve(sizeof(double) * (size_t)(maxlen + 1) * threads);
+        S.gC.reserve((size_t)(maxlen + 1) * threads);
+        A.gS = S.gS.as<double>();
+        A.gE = S.gE.as<double>();
+        A.gChoice = S.gC.as<uint8_t>();
+        R.name = launch_generic(A, trace, 0, st);
+    }
+    if (timer) timer->end(st);
+    launch_fill_empty(A, st);
+    g_launches += 2;
+    return R;
+}
+
+/* The traceback arguments that read the records of one forward launch (outputs still to be filled in). */
+TraceArgs trace_args_for(const Plan& P, const DevPlan& D, const FwdRec& R) {
+    TraceArgs T;
+    std::memset(&T, 0, sizeof(T));
+    T.lens = R.A.lens;
+    T.n = R.A.n;
+    T.L = P.L;
+    T.layout = R.layout;
+    T.G = R.geo.G;
+    T.C = R.geo.C;
+    T.wordbytes = R.wordbytes;
+    T.hi_bytes = R.hi_bytes;
+    T.flags = R.A.flags;
+    T.flags_hi = R.A.flags_hi;
+    T.fstride = R.A.fstride;
+    T.endrow = R.A.endrow;
+    T.nsec = (int)P.sec_starts.size();
+    T.sec_starts = D.sec_starts;
+    T.sec_ends = D.sec_ends;
+    return T;
+}
+
+/* Enqueue forward (+ traceback) for device-resident packed reads [0,n).  The caller hands over a range one launch can
+ * take (sub_chunk() under the scratch budget): the [nref][n] / [nsec][n] output matrices have row pitch n. */
 const char* run_device(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t st,
         const uint16_t* d_rows, const int32_t* d_lens, long long n, int stride, int maxlen,
         bool trace, const Outputs& out, int sms, FwdTimer* timer = nullptr,
@@ -890,120 +997,127 @@ const char* run_device(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t
      * tb_done is recorded behind it: the memory-bound traceback then overlaps the next range's ALU-bound forward pass
      * (it fits beside the forward kernel's resident blocks: 32 registers per thread).  The caller owns the waits that
      * protect the scratch buffers. */
-    const char* name = "";
-    if (n == 0) return name;
-    long long cn = sub_chunk(P, maxlen, trace, n);
-    if (cn < n) cn = whole_rounds(cn, plan_groups(P, trace));
-    for (long long off = 0; off < n; off += cn) {
-        const long long m = std::min(cn, n - off);
-        AlignArgs A;
-        std::memset(&A, 0, sizeof(A));
-        A.rows = d_rows + off * (long long)stride;
-        A.lens = d_lens + off;
-        A.n = m;
-        A.stride = stride;
-        A.L = P.L;
-        A.nref = P.nref;
-        A.refmask = D.refmask;
-        A.refkind = D.refkind;
-        A.local = P.local ? 1 : 0;
-        A.gop = P.gop;
-        A.ge = P.ge;
-        A.row0 = D.row0;
-        A.cost = D.cost;
-        A.enc_n = P.enc->n;
-        A.kinds = P.kinds;
-        const Geometry geo = geometry_for(P, maxlen);
-        A.G = geo.G;
-        A.C = geo.C;
-        A.solo = geo.solo ? 1 : 0;
-        A.pair_rows = geo.pair;
-        /* [nref][n] outputs of a sub-chunk cannot be expressed with one base pointer unless n == m or nref == 1 */
-        A.score = out.score ? out.score + off : nullptr;
-        A.best_id = out.best_id ? out.best_id + off : nullptr;
-        A.best = out.best ? out.best + off : nullptr;
-        A.next_best = out.next_best ? out.next_best + off : nullptr;
-
-        TraceArgs T;
-        std::memset(&T, 0, sizeof(T));
-        if (trace) {
-            if (P.fast) {
-                const int wb = trace_word_bytes(geo.C), hb = trace_hi_bytes(geo.C, geo.solo);
-                /* record words of this sub-launch: wavefront [alignment][row slot][lane]; solo [32 alignments][row][lane] */
-                A.fstride = geo.solo ? (long long)(maxlen + 1) : (long long)(maxlen + kSkew * geo.G) * geo.G;
-                const size_t words = geo.solo ? (size_t)((m + 31) / 32) * 32 * (size_t)A.fstride : (size_t)A.fstride * (size_t)m;
-                const size_t lo_bytes = (words * wb + 255) & ~(size_t)255;
-                S.flags.reserve(lo_bytes + words * hb);
-                S.endrow.reserve(sizeof(int32_t) * (size_t)m);
-                A.endrow = std::getenv("SARLACC_NO_ENDROW") ? nullptr : S.endrow.as<int32_t>();   /* A/B switch for profiles */
-                A.flags_hi = hb ? S.flags.as<uint8_t>() + lo_bytes : nullptr;
-                T.layout = geo.solo ? 2 : 0;
-                T.wordbytes = wb;
-                T.hi_bytes = hb;
-                T.flags_hi = A.flags_hi;
-            } else {
-                A.fstride = (long long)std::max(1, maxlen) * P.L;
-                S.flags.reserve((size_t)A.fstride * m);
-                T.layout = 1;
-                T.wordbytes = 1;
-            }
-            A.flags = S.flags.p;
-            S.map.reserve(sizeof(int32_t) * ((size_t)P.L + 1) * m);
-        }
-        if (timer) timer->begin(st);
-        if (P.fast) {
-            name = launch_wavefront(A, trace, P.has_alt, 0, st);
+    if (n == 0) return "";
+    if (sub_chunk(P, maxlen, trace, n) < n) throw CudaError{"internal error: run_device was handed more alignments than its scratch budget covers"};
+    const FwdRec R = forward_once(P, D, S, st, d_rows, d_lens, n, stride, maxlen, trace, out, sms, timer);
+    if (trace) {
+        TraceArgs T = trace_args_for(P, D, R);
+        S.map.reserve(sizeof(int32_t) * ((size_t)P.L + 1) * (size_t)n);
+        T.map = S.map.as<int32_t>();
+        T.start = out.start;
+        T.end = out.end;
+        T.sec_start = out.sec_start;
+        T.sec_width = out.sec_width;
+        T.ops = out.ops;
+        T.nops = out.nops;
+        T.ops_stride = out.ops_stride;
+        if (tb_stream) {
+            CUDA_CHECK(cudaEventRecord(fwd_done, st));
+            CUDA_CHECK(cudaStreamWaitEvent(tb_stream, fwd_done, 0));
+            launch_traceback(T, tb_stream);
+            CUDA_CHECK(cudaEventRecord(tb_done, tb_stream));
         } else {
-            long long threads = std::min<long long>(m, (long long)sms * 1024);
-            threads = (threads + 127) / 128 * 128;
-            A.gthreads = threads;
-            S.gS.reserve(sizeof(double) * (size_t)(maxlen + 1) * threads);
-            S.gE.reserve(sizeof(double) * (size_t)(maxlen + 1) * threads);
-            S.gC.reserve((size_t)(maxlen + 1) * threads);
-            A.gS = S.gS.as<double>();
-            A.gE = S.gE.as<double>();
-            A.gChoice = S.gC.as<uint8_t>();
-            name = launch_generic(A, trace, 0, st);
+            launch_traceback(T, st);
         }
-        if (timer) timer->end(st);
-        launch_fill_empty(A, st);
-        g_launches += 2;
-        if (trace) {
-            T.lens = A.lens;
-            T.n = m;
-            T.L = P.L;
-            T.G = geo.G;
-            T.C = geo.C;
-            T.flags = A.flags;
-            T.fstride = A.fstride;
-            T.endrow = A.endrow;
-            T.nsec = (int)P.sec_starts.size();
-            T.sec_starts = D.sec_starts;
-            T.sec_ends = D.sec_ends;
-            T.map = S.map.as<int32_t>();
-            T.start = out.start ? out.start + off : nullptr;
-            T.end = out.end ? out.end + off : nullptr;
-            /* section outputs are [nsec][n_total]: the kernel indexes s*n + a with n = m, so sub-chunks
-             * of a larger run are only valid when they cover it entirely or nsec <= 1 */
-            T.sec_start = out.sec_start ? out.sec_start + off : nullptr;
-            T.sec_width = out.sec_width ? out.sec_width + off : nullptr;
-            T.ops = out.ops ? out.ops + off * out.ops_stride : nullptr;
-            T.nops = out.nops ? out.nops + off : nullptr;
-            T.ops_stride = out.ops_stride;
-            if (tb_stream) {
-                CUDA_CHECK(cudaEventRecord(fwd_done, st));
-                CUDA_CHECK(cudaStreamWaitEvent(tb_stream, fwd_done, 0));
-                launch_traceback(T, tb_stream);
-                CUDA_CHECK(cudaEventRecord(tb_done, tb_stream));
-            } else {
-                launch_traceback(T, st);
-            }
-            g_launches += 1;
-        }
-        CUDA_CHECK(cudaGetLastError());
+        g_launches += 1;
     }
-    g_last_kernel = name;
-    return name;
+    CUDA_CHECK(cudaGetLastError());
+    g_last_kernel = R.name;
+    return R.name;
+}
+
+/* ---- both adaptors on both window sets of device-resident reads ---------------------------------------------------
+ * .align_AA_internal (R/adaptorAlign.R:178-199) without the work R throws away: the four forward passes -- (adaptor1,
+ * front), (adaptor2, back), (adaptor1, back), (adaptor2, front) -- keep their traceback records, .resolve_strand
+ * (:112-122) runs on the four score vectors, and then ONE traceback per adaptor walks, for every read, the records of
+ * the strand that was kept (cur.starts[rev,] <- cur.rc.starts[rev,], :195-196), writing the final columns directly
+ * (adaptor2's start/end flipped into read coordinates when widths are given, :66-71).  Half the traceback work of four
+ * separate adaptor_align calls, and no per-strand result sets to select from afterwards. */
+struct PairScratch {
+    Scratch s[4];
+    DevBuf map[2];
+    void release() {
+        for (auto& x : s) x.release();
+        map[0].release();
+        map[1].release();
+    }
+};
+
+struct PairDeviceOut {      /* device pointers: [m] vectors, [nsec][pitch] section matrices */
+    uint8_t* reversed = nullptr;
+    double* score[2] = {nullptr, nullptr};
+    int32_t* start[2] = {nullptr, nullptr};
+    int32_t* end[2] = {nullptr, nullptr};
+    int32_t* sec_start[2] = {nullptr, nullptr};
+    int32_t* sec_width[2] = {nullptr, nullptr};
+    long long pitch = 0;
+};
+
+/* Scratch bytes per read of one run_pair_device range (four record sets + two column maps). */
+size_t pair_scratch_per_read(const Plan& P1, const Plan& P2, int maxlen) {
+    auto rec = [&](const Plan& P) -> size_t {
+        if (!P.fast) return (size_t)std::max(1, maxlen) * P.L + 4;
+        const Geometry g = geometry_for(P, maxlen);
+        const size_t wb = (size_t)trace_word_bytes(g.C) + (size_t)trace_hi_bytes(g.C, g.solo);
+        return (g.solo ? (size_t)(maxlen + 1) * wb : (size_t)(maxlen + kSkew * g.G) * g.G * wb) + 4;
+    };
+    return 2 * rec(P1) + 2 * rec(P2) + sizeof(int32_t) * ((size_t)P1.L + P2.L + 2);
+}
+
+/* Enqueues on `st` the four forward passes + strand resolution and on `tb` (behind fwd_done) the two tracebacks;
+ * tb_done is recorded behind those.  The caller makes `st` wait for the previous user of S before calling. */
+const char* run_pair_device(const Plan* const plan[2], const DevPlan* const D[2], PairScratch& S, cudaStream_t st, cudaStream_t tb,
+        cudaEvent_t fwd_done, cudaEvent_t tb_done,
+        const uint16_t* rows_f, const int32_t* lens_f, int stride_f, const uint16_t* rows_b, const int32_t* lens_b, int stride_b,
+        long long m, int maxlen, const int32_t* width, double* tmp_scores, const PairDeviceOut& out, int sms, FwdTimer* timer = nullptr)
+{
+    if (m <= 0) return "";
+    FwdRec rec[4];
+    for (int r = 0; r < 4; ++r) {
+        const int a = (r == 0 || r == 2) ? 0 : 1;          /* adaptor */
+        const bool on_front = (r == 0 || r == 3);           /* window set */
+        Outputs dev;
+        dev.score = tmp_scores + (size_t)r * m;
+        rec[r] = forward_once(*plan[a], *D[a], S.s[r], st, on_front ? rows_f : rows_b, on_front ? lens_f : lens_b, m,
+                              on_front ? stride_f : stride_b, maxlen, true, dev, sms, r == 0 ? timer : nullptr);
+    }
+    StrandArgs SA;
+    SA.n = m;
+    SA.a1_front = tmp_scores;
+    SA.a2_back = tmp_scores + (size_t)m;
+    SA.a1_back = tmp_scores + (size_t)2 * m;
+    SA.a2_front = tmp_scores + (size_t)3 * m;
+    SA.reversed = out.reversed;
+    SA.score1 = out.score[0];
+    SA.score2 = out.score[1];
+    launch_resolve_strand(SA, st);
+    g_launches += 1;
+    CUDA_CHECK(cudaEventRecord(fwd_done, st));
+    CUDA_CHECK(cudaStreamWaitEvent(tb, fwd_done, 0));
+    for (int a = 0; a < 2; ++a) {
+        const FwdRec& fwd = rec[a == 0 ? 0 : 1];     /* forward strand: (adaptor1, front) / (adaptor2, back) */
+        const FwdRec& rev = rec[a == 0 ? 2 : 3];     /* reverse strand: (adaptor1, back) / (adaptor2, front) */
+        TraceArgs T = trace_args_for(*plan[a], *D[a], fwd);
+        T.sel = out.reversed;
+        T.lens2 = rev.A.lens;
+        T.flags2 = rev.A.flags;
+        T.flags_hi2 = rev.A.flags_hi;
+        T.endrow2 = rev.A.endrow;
+        S.map[a].reserve(sizeof(int32_t) * ((size_t)plan[a]->L + 1) * (size_t)m);
+        T.map = S.map[a].as<int32_t>();
+        T.start = out.start[a];
+        T.end = out.end[a];
+        T.sec_start = out.sec_start[a];
+        T.sec_width = out.sec_width[a];
+        T.out_pitch = out.pitch;
+        T.width = a == 1 ? width : nullptr;
+        launch_traceback(T, tb);
+        g_launches += 1;
+    }
+    CUDA_CHECK(cudaEventRecord(tb_done, tb));
+    CUDA_CHECK(cudaGetLastError());
+    g_last_kernel = rec[0].name;
+    return rec[0].name;
 }
 
 }  // namespace
@@ -1177,7 +1291,8 @@ struct Slot {
     DevBuf d_rows, d_lens, d_out;
     PinBuf h_rows2, h_lens2, h_width;     /* second window set + read widths of the fused both-ends entry */
     DevBuf d_rows2, d_lens2, d_width, d_tmp;
-    Scratch scratch, scratch_b;   /* the fused both-ends entry alternates them so that traceback(r) overlaps forward(r+1) */
+    Scratch scratch;
+    PairScratch pair;             /* the fused both-ends entry: four record sets, so that only the kept strand is walked */
     cudaStream_t tb = nullptr;    /* tracebacks of the fused entry */
     cudaEvent_t fwd_ev[4] = {nullptr, nullptr, nullptr, nullptr}, tb_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     RawStage raw, raw2;     /* raw bytes of the (first, second) window set on their way to the device packer */
@@ -1215,7 +1330,7 @@ struct Slot {
         }
         if (tb) cudaStreamDestroy(tb);
         tb = nullptr;
-        scratch_b.release();
+        pair.release();
         if (t_begin) cudaEventDestroy(t_begin);
         if (t_h2d) cudaEventDestroy(t_h2d);
         if (t_end) cudaEventDestroy(t_end);
@@ -1637,10 +1752,6 @@ struct PairOutputs {
     int32_t* sec_width[2];
 };
 
-struct TmpLayout {   /* four result sets: a1/front, a2/back, a1/back, a2/front */
-    size_t o_score[4], o_start[4], o_end[4], o_ss[4], o_sw[4], total;
-};
-
 struct FinalLayout {
     size_t o_rev, o_score[2], o_start[2], o_end[2], o_ss[2], o_sw[2], total;
 };
@@ -1760,7 +1871,7 @@ struct PairJob {
             scan_lengths(VB, c0, c1, s.h_lens2.as<int32_t>(), nthreads, err_back, maxb);
             {
                 const int mx = std::max(maxf, maxb);
-                const long long fit = std::min(sub_chunk(*plan[0], mx, true, c1 - c0), sub_chunk(*plan[1], mx, true, c1 - c0));
+                const long long fit = std::max<long long>(1, (long long)(2 * scratch_budget_bytes() / pair_scratch_per_read(*plan[0], *plan[1], mx)));
                 if (fit < c1 - c0) {
                     c1 = c0 + fit;
                     maxf = maxb = 0;
@@ -1787,17 +1898,7 @@ struct PairJob {
             s.d_rows2.reserve(sizeof(uint16_t) * (size_t)m * stride_b);
             s.d_lens.reserve(sizeof(int32_t) * (size_t)m);
             s.d_lens2.reserve(sizeof(int32_t) * (size_t)m);
-            TmpLayout T;
             size_t at = 0;
-            for (int r = 0; r < 4; ++r) {
-                const int ns = nsec[(r == 0 || r == 2) ? 0 : 1];
-                T.o_score[r] = at; at += al(sizeof(double) * m);
-                T.o_start[r] = at; at += al(sizeof(int32_t) * m);
-                T.o_end[r] = at; at += al(sizeof(int32_t) * m);
-                T.o_ss[r] = at; at += al(sizeof(int32_t) * m * std::max(1, ns));
-                T.o_sw[r] = at; at += al(sizeof(int32_t) * m * std::max(1, ns));
-            }
-            T.total = at;
             FinalLayout F;
             at = 0;
             F.o_rev = at; at += al((size_t)m);
@@ -1810,7 +1911,7 @@ struct PairJob {
             }
             F.total = at;
             lay[which] = F;
-            s.d_tmp.reserve(T.total);
+            s.d_tmp.reserve(sizeof(double) * 4 * (size_t)m);      /* the four forward passes' scores */
             s.d_out.reserve(F.total);
             s.h_out.reserve(F.total);
             if (dbg) CUDA_CHECK(cudaEventRecord(s.t_begin, s.st));
@@ -1841,45 +1942,26 @@ struct PairJob {
             }
             if (dbg) CUDA_CHECK(cudaEventRecord(s.t_h2d, s.st));
             if (prev_gate) CUDA_CHECK(cudaStreamWaitEvent(s.st, prev_gate, 0));
-            uint8_t* t = s.d_tmp.as<uint8_t>();
-            ResultSet rs[4];
-            for (int r = 0; r < 4; ++r) {
-                const int a = (r == 0 || r == 2) ? 0 : 1;             /* adaptor */
-                const bool on_front = (r == 0 || r == 3);              /* window set */
-                Outputs dev;
-                dev.score = reinterpret_cast<double*>(t + T.o_score[r]);
-                dev.start = reinterpret_cast<int32_t*>(t + T.o_start[r]);
-                dev.end = reinterpret_cast<int32_t*>(t + T.o_end[r]);
-                dev.sec_start = reinterpret_cast<int32_t*>(t + T.o_ss[r]);
-                dev.sec_width = reinterpret_cast<int32_t*>(t + T.o_sw[r]);
-                /* forward(r) reuses the records traceback(r-2) reads; traceback(r-1) runs beside it on the slot's second stream */
-                if (r >= 2) CUDA_CHECK(cudaStreamWaitEvent(s.st, s.tb_ev[r - 2], 0));
-                run_device(*plan[a], D[a], (r & 1) ? s.scratch_b : s.scratch, s.st,
-                           on_front ? s.d_rows.as<uint16_t>() : s.d_rows2.as<uint16_t>(),
-                           on_front ? s.d_lens.as<int32_t>() : s.d_lens2.as<int32_t>(), m,
-                           on_front ? stride_f : stride_b, on_front ? maxf : maxb, true, dev, sms,
-                           nullptr, s.tb, s.fwd_ev[r], s.tb_ev[r]);
-                rs[r] = ResultSet{dev.score, dev.start, dev.end, dev.sec_start, dev.sec_width};
-            }
-            CUDA_CHECK(cudaEventRecord(s.gate, s.st));     /* behind the fourth forward pass; the last tracebacks run beside the next chunk */
-            prev_gate = s.gate;
-            CUDA_CHECK(cudaStreamWaitEvent(s.st, s.tb_ev[3], 0));   /* the traceback stream is in order: [3] covers all four */
             uint8_t* d = s.d_out.as<uint8_t>();
-            SelectArgs S;
-            std::memset(&S, 0, sizeof(S));
-            S.n = m;
-            S.a1_front = rs[0]; S.a2_back = rs[1]; S.a1_back = rs[2]; S.a2_front = rs[3];
-            S.nsec1 = nsec[0]; S.nsec2 = nsec[1];
-            S.width = (width || tolerance > 0) ? s.d_width.as<int32_t>() : nullptr;
-            S.reversed = d + F.o_rev;
-            S.score1 = reinterpret_cast<double*>(d + F.o_score[0]); S.score2 = reinterpret_cast<double*>(d + F.o_score[1]);
-            S.start1 = reinterpret_cast<int32_t*>(d + F.o_start[0]); S.start2 = reinterpret_cast<int32_t*>(d + F.o_start[1]);
-            S.end1 = reinterpret_cast<int32_t*>(d + F.o_end[0]); S.end2 = reinterpret_cast<int32_t*>(d + F.o_end[1]);
-            S.sec_start1 = reinterpret_cast<int32_t*>(d + F.o_ss[0]); S.sec_start2 = reinterpret_cast<int32_t*>(d + F.o_ss[1]);
-            S.sec_width1 = reinterpret_cast<int32_t*>(d + F.o_sw[0]); S.sec_width2 = reinterpret_cast<int32_t*>(d + F.o_sw[1]);
-            launch_resolve_select(S, s.st);
-            g_launches += 1;
-            CUDA_CHECK(cudaGetLastError());
+            PairDeviceOut po;
+            po.reversed = d + F.o_rev;
+            for (int k = 0; k < 2; ++k) {
+                po.score[k] = reinterpret_cast<double*>(d + F.o_score[k]);
+                po.start[k] = reinterpret_cast<int32_t*>(d + F.o_start[k]);
+                po.end[k] = reinterpret_cast<int32_t*>(d + F.o_end[k]);
+                po.sec_start[k] = reinterpret_cast<int32_t*>(d + F.o_ss[k]);
+                po.sec_width[k] = reinterpret_cast<int32_t*>(d + F.o_sw[k]);
+            }
+            po.pitch = m;
+            const DevPlan* Dp[2] = {&D[0], &D[1]};
+            /* the slot's previous tracebacks finished before its results were drained, so its record sets are free */
+            run_pair_device(plan, Dp, s.pair, s.st, s.tb, s.fwd_ev[0], s.tb_ev[0],
+                            s.d_rows.as<uint16_t>(), s.d_lens.as<int32_t>(), stride_f, s.d_rows2.as<uint16_t>(), s.d_lens2.as<int32_t>(), stride_b,
+                            m, std::max(maxf, maxb), (width || tolerance > 0) ? s.d_width.as<int32_t>() : nullptr,
+                            s.d_tmp.as<double>(), po, sms);
+            CUDA_CHECK(cudaEventRecord(s.gate, s.st));     /* behind the fourth forward pass; the tracebacks run beside the next chunk */
+            prev_gate = s.gate;
+            CUDA_CHECK(cudaStreamWaitEvent(s.st, s.tb_ev[0], 0));
             CUDA_CHECK(cudaMemcpyAsync(s.h_out.p, s.d_out.p, F.total, cudaMemcpyDeviceToHost, s.st));
             if (dbg) CUDA_CHECK(cudaEventRecord(s.t_end, s.st));
             CUDA_CHECK(cudaEventRecord(s.done, s.st));
@@ -2864,6 +2946,608 @@ double sarlacc_resident_forward_ms(sarlacc_resident* r) {
         fail(e.msg);
         return -1.0;
     }
+}
+
+
+/* ---- chunks: device-resident reads that are re-loaded in place ---------------------------------------------------
+ * One chunk = what one FastqStreamer yield() is to the R drivers (R/adaptorAlign.R:26-48, R/getAdaptorThresholds.R:35-48):
+ * up to `capacity` reads whose front and back windows sit packed in HBM.  Loading replaces the contents in place (no
+ * allocation in steady state); sarlacc_chunk_adaptor_align is .align_AA_internal + adaptorAlign's adaptor2 flip,
+ * sarlacc_chunk_scrambled_scores is .align_AT_internal.  Every call only enqueues work (compute, traceback and copy
+ * streams of the chunk) and results land in caller memory -- host or device -- by the time sarlacc_chunk_sync returns,
+ * so the copy-out of chunk k overlaps the alignment of chunk k+1. */
+struct sarlacc_chunk {
+    int device = 0, sms = 0;
+    int64_t capacity = 0, n = 0;
+    int tol = 0, stride = 0, maxlen = 0;
+    bool has_width = false;
+    Encoding enc;
+    int seq_encoding = SARLACC_SEQ_ASCII;
+    cudaStream_t st = nullptr, tb = nullptr, cp = nullptr;
+    DevBuf rows_f, rows_b, lens_f, lens_b, width, flipped, srows_f, srows_b, barcodes;
+    RawStage raw_f, raw_b;
+    PinBuf h_lens_f, h_lens_b, h_width;
+    struct CachedPlan { std::string key; Plan plan; DevPlan d; };
+    std::vector<std::unique_ptr<CachedPlan> > plans;
+    PairScratch pair[2];
+    Scratch score_scratch;
+    cudaEvent_t fwd_done[2] = {nullptr, nullptr}, tb_done[2] = {nullptr, nullptr};
+    bool tb_pending[2] = {false, false};
+    int parity = 0;
+    DevBuf tmp;                     /* [4][capacity] forward scores */
+    DevBuf out[2];                  /* final columns of the last two adaptor_align calls */
+    DevBuf sout[2];                 /* kept scrambled scores of the last two scrambled_scores calls */
+    cudaEvent_t out_ready = nullptr, out_copied[2] = {nullptr, nullptr}, sout_copied[2] = {nullptr, nullptr};
+    bool out_pending[2] = {false, false}, sout_pending[2] = {false, false};
+    int out_which = 0, sout_which = 0;
+    /* phase timing (sarlacc_chunk_set_timing): CUDA events on the compute stream around load / align / scramble / score */
+    bool timing = false;
+    std::vector<cudaEvent_t> tev;   /* pairs, tagged by phase */
+    std::vector<int> tphase;
+    double phase_ms[4] = {0, 0, 0, 0};
+    std::string last_kernel[2];
+};
+
+namespace {
+
+void chunk_mark(sarlacc_chunk* c, int phase, bool begin) {
+    if (!c->timing) return;
+    cudaEvent_t e;
+    CUDA_CHECK(cudaEventCreate(&e));
+    CUDA_CHECK(cudaEventRecord(e, c->st));
+    c->tev.push_back(e);
+    if (begin) c->tphase.push_back(phase);
+}
+
+void chunk_collect_timing(sarlacc_chunk* c) {
+    for (size_t i = 0; i + 1 < c->tev.size(); i += 2) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->tev[i], c->tev[i + 1]) == cudaSuccess) c->phase_ms[c->tphase[i / 2]] += ms;
+    }
+    for (auto e : c->tev) cudaEventDestroy(e);
+    c->tev.clear();
+    c->tphase.clear();
+}
+
+sarlacc_chunk::CachedPlan* chunk_plan(sarlacc_chunk* c, const char* reference, double go, double ge, bool trace,
+                                      int nsec, const int32_t* ss, const int32_t* se) {
+    std::string key(reference);
+    key += '|';
+    key.append(reinterpret_cast<const char*>(&go), sizeof(double));
+    key.append(reinterpret_cast<const char*>(&ge), sizeof(double));
+    key += trace ? 'T' : 'S';
+    if (trace && nsec > 0) {
+        key.append(reinterpret_cast<const char*>(ss), sizeof(int32_t) * nsec);
+        key += '|';
+        key.append(reinterpret_cast<const char*>(se), sizeof(int32_t) * nsec);
+    }
+    for (auto& p : c->plans) {
+        if (p->key == key) return p.get();
+    }
+    if (c->plans.size() >= 128) {      /* bounded (tuneAlignment walks 35 penalty pairs x 2 adaptors): start over once idle */
+        CUDA_CHECK(cudaDeviceSynchronize());
+        for (auto& p : c->plans) p->d.buf.release();
+        c->plans.clear();
+    }
+    std::unique_ptr<sarlacc_chunk::CachedPlan> np(new sarlacc_chunk::CachedPlan());
+    np->key = key;
+    const char* refs[1] = {reference};
+    build_plan(np->plan, c->enc, refs, 1, (int)std::strlen(reference), true, go, ge, trace);
+    if (trace && nsec > 0) {
+        np->plan.sec_starts.assign(ss, ss + nsec);
+        np->plan.sec_ends.assign(se, se + nsec);
+    }
+    np->d.upload(np->plan, c->st);
+    c->plans.push_back(std::move(np));
+    return c->plans.back().get();
+}
+
+/* Copies a device vector to caller memory (host or device) on the chunk's copy stream. */
+void chunk_copy_out(sarlacc_chunk* c, void* dst, const void* src, size_t bytes) {
+    if (!dst || bytes == 0) return;
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, c->cp));
+}
+
+void chunk_wait_tracebacks(sarlacc_chunk* c, cudaStream_t on) {
+    for (int b = 0; b < 2; ++b) {
+        if (c->tb_pending[b]) CUDA_CHECK(cudaStreamWaitEvent(on, c->tb_done[b], 0));
+    }
+}
+
+int chunk_check_loaded(sarlacc_chunk* c) {
+    if (!c) return fail("chunk handle is NULL");
+    if (c->n <= 0) return fail("the chunk holds no reads");
+    return 0;
+}
+
+}  // namespace
+
+void sarlacc_chunk_free(sarlacc_chunk* c);
+
+sarlacc_chunk* sarlacc_chunk_create(int device, int64_t capacity, int tolerance, const sarlacc_encoding* encoding) {
+    if (capacity <= 0) { fail("chunk capacity must be positive"); return nullptr; }
+    if (tolerance <= 0) { fail("tolerance should be a positive integer"); return nullptr; }
+    if (require_device()) return nullptr;
+    std::unique_ptr<sarlacc_chunk> c(new sarlacc_chunk());
+    const char* msg = build_encoding(encoding, c->enc);
+    if (msg) { fail(msg); return nullptr; }
+    try {
+        CUDA_CHECK(cudaSetDevice(device));
+        c->device = device;
+        c->sms = device_sm_count(device);
+        c->capacity = capacity;
+        c->tol = tolerance;
+        c->stride = std::max(8, (tolerance + 8) & ~7);
+        CUDA_CHECK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&c->tb, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&c->cp, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            CUDA_CHECK(cudaEventCreateWithFlags(&c->fwd_done[k], cudaEventDisableTiming));
+            CUDA_CHECK(cudaEventCreateWithFlags(&c->tb_done[k], cudaEventDisableTiming));
+            CUDA_CHECK(cudaEventCreateWithFlags(&c->out_copied[k], cudaEventDisableTiming));
+            CUDA_CHECK(cudaEventCreateWithFlags(&c->sout_copied[k], cudaEventDisableTiming));
+        }
+        CUDA_CHECK(cudaEventCreateWithFlags(&c->out_ready, cudaEventDisableTiming));
+        const size_t cap = (size_t)capacity;
+        c->rows_f.reserve(sizeof(uint16_t) * cap * c->stride);
+        c->rows_b.reserve(sizeof(uint16_t) * cap * c->stride);
+        c->lens_f.reserve(sizeof(int32_t) * cap);
+        c->lens_b.reserve(sizeof(int32_t) * cap);
+        c->width.reserve(sizeof(int32_t) * cap);
+        c->flipped.reserve(cap);
+        c->tmp.reserve(sizeof(double) * 4 * cap);
+    } catch (CudaError& e) {
+        fail(e.msg);
+        sarlacc_chunk_free(c.release());
+        return nullptr;
+    }
+    return c.release();
+}
+
+void sarlacc_chunk_free(sarlacc_chunk* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (DevBuf* b : {&c->rows_f, &c->rows_b, &c->lens_f, &c->lens_b, &c->width, &c->flipped, &c->srows_f, &c->srows_b, &c->barcodes,
+                      &c->tmp, &c->out[0], &c->out[1], &c->sout[0], &c->sout[1]}) b->release();
+    c->raw_f.release();
+    c->raw_b.release();
+    c->h_lens_f.release();
+    c->h_lens_b.release();
+    c->h_width.release();
+    c->pair[0].release();
+    c->pair[1].release();
+    c->score_scratch.release();
+    for (auto& p : c->plans) p->d.buf.release();
+    for (int k = 0; k < 2; ++k) {
+        if (c->fwd_done[k]) cudaEventDestroy(c->fwd_done[k]);
+        if (c->tb_done[k]) cudaEventDestroy(c->tb_done[k]);
+        if (c->out_copied[k]) cudaEventDestroy(c->out_copied[k]);
+        if (c->sout_copied[k]) cudaEventDestroy(c->sout_copied[k]);
+    }
+    if (c->out_ready) cudaEventDestroy(c->out_ready);
+    for (auto e : c->tev) cudaEventDestroy(e);
+    if (c->st) cudaStreamDestroy(c->st);
+    if (c->tb) cudaStreamDestroy(c->tb);
+    if (c->cp) cudaStreamDestroy(c->cp);
+    delete c;
+}
+
+int64_t sarlacc_chunk_n(const sarlacc_chunk* c) { return c ? c->n : 0; }
+
+int sarlacc_chunk_load_mock(sarlacc_chunk* c, int64_t n, uint64_t first_index, uint64_t seed,
+        const char* adaptor1, const char* adaptor2, int insert_len, const char* const* barcodes, int nbarcodes,
+        double sub_rate, double indel_rate, int max_insert)
+{
+    if (!c) return fail("chunk handle is NULL");
+    if (n < 0 || n > c->capacity) return fail("more reads than the chunk's capacity");
+    if (!adaptor1 || !adaptor2) return fail("adaptor sequence should be a string");
+    const size_t l1 = std::strlen(adaptor1), l2 = std::strlen(adaptor2);
+    if (l1 > 127 || l2 > 127) return fail("mock adaptors are limited to 127 bases");
+    if (max_insert < 2 || max_insert > 64) return fail("max_insert out of range");
+    if (!(sub_rate >= 0 && sub_rate < 1 && indel_rate >= 0 && indel_rate < 1 && sub_rate + indel_rate > 0)) return fail("rates out of range");
+    try {
+        CUDA_CHECK(cudaSetDevice(c->device));
+        MockArgs M;
+        std::memset(&M, 0, sizeof(M));
+        M.n = n;
+        M.seed = seed;
+        M.first_index = first_index;
+        M.tol = c->tol;
+        M.stride = c->stride;
+        M.front = c->rows_f.as<uint16_t>();
+        M.back = c->rows_b.as<uint16_t>();
+        M.lens_front = c->lens_f.as<int32_t>();
+        M.lens_back = c->lens_b.as<int32_t>();
+        M.width = c->width.as<int32_t>();
+        M.flipped = c->flipped.as<uint8_t>();
+        M.len1 = (int)l1;
+        M.len2 = (int)l2;
+        for (size_t i = 0; i < l1; ++i) M.adaptor1[i] = (char)std::toupper((unsigned char)adaptor1[i]);
+        for (size_t i = 0; i < l2; ++i) M.adaptor2[i] = (char)std::toupper((unsigned char)adaptor2[i]);
+        /* the barcode slot: adaptor1's first run of N (R/mockReads.R:35-50) */
+        M.run0_start = M.run0_end = -1;
+        for (size_t i = 0; i < l1; ++i) {
+            if (M.adaptor1[i] == 'N') {
+                size_t j = i;
+                while (j < l1 && M.adaptor1[j] == 'N') ++j;
+                M.run0_start = (int)i;
+                M.run0_end = (int)j;
+                break;
+            }
+        }
+        M.nbarcodes = 0;
+        if (nbarcodes > 0 && barcodes && M.run0_start >= 0) {
+            const int bl = M.run0_end - M.run0_start;
+            std::vector<uint8_t> codes((size_t)nbarcodes * bl);
+            for (int b = 0; b < nbarcodes; ++b) {
+                if (!barcodes[b] || (int)std::strlen(barcodes[b]) != bl) return fail("barcodes must have the length of adaptor1's first N run");
+                for (int k = 0; k < bl; ++k) {
+                    const char ch = (char)std::toupper((unsigned char)barcodes[b][k]);
+                    const char* at = std::strchr("ACGT", ch);
+                    if (!at || !ch) return fail("barcodes must consist of A, C, G, T");
+                    codes[(size_t)b * bl + k] = (uint8_t)(at - "ACGT");
+                }
+            }
+            CUDA_CHECK(cudaStreamSynchronize(c->st));      /* an earlier load may still read the previous table */
+            c->barcodes.reserve(codes.size());
+            CUDA_CHECK(cudaMemcpy(c->barcodes.p, codes.data(), codes.size(), cudaMemcpyHostToDevice));
+            M.barcodes = c->barcodes.as<uint8_t>();
+            M.nbarcodes = nbarcodes;
+        }
+        M.molecule_len = (int)(l1 + l2) + insert_len;
+        M.max_insert = max_insert;
+        M.sub_thr = (uint32_t)std::floor(sub_rate * 65536.0);
+        M.indel_thr = (uint32_t)std::floor(indel_rate * 65536.0);
+        /* quality = clamp(round(-10 log10(u * max_err)), 0, 93), u = word / 2^32 (R/mockReads.R:82):
+         * quality >= k  <=>  word < 2^32 * 10^(-(k - 0.5) / 10) / max_err */
+        const double max_err = sub_rate + indel_rate;
+        M.qmin = 0;
+        for (int k = 0; k <= 94; ++k) {
+            double t = k == 0 ? 4294967296.0 : std::floor(4294967296.0 * std::pow(10.0, -((double)k - 0.5) / 10.0) / max_err);
+            if (k == 94) t = 0.0;
+            M.qthr[k] = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+            if (k <= 93 && t >= 4294967296.0) M.qmin = (uint32_t)k;
+        }
+        chunk_wait_tracebacks(c, c->st);      /* tracebacks of the previous contents still read the window lengths */
+        chunk_mark(c, 0, true);
+        launch_mock_windows(M, c->st);
+        chunk_mark(c, 0, false);
+        g_launches += 1;
+        CUDA_CHECK(cudaGetLastError());
+        c->n = n;
+        c->maxlen = c->tol;
+        c->has_width = true;
+    } catch (CudaError& e) {
+        return fail(e.msg);
+    }
+    return 0;
+}
+
+/* Host reads in: either pre-cut windows (tolerance == 0: `front` / `back` as .get_front_and_back made them, widths
+ * optional) or whole reads (tolerance > 0, back == NULL: both windows cut by the device packer).  Synchronous up to the
+ * point where the reference's per-read errors are known. */
+int sarlacc_chunk_load_reads(sarlacc_chunk* c, const sarlacc_reads* front, const sarlacc_reads* back, int tolerance, const int32_t* width)
+{
+    if (!c) return fail("chunk handle is NULL");
+    if (!front) return fail("reads must not be NULL");
+    if (tolerance < 0 || tolerance > c->tol) return fail("tolerance exceeds the chunk's");
+    if (tolerance == 0 && (!back || back->n != front->n)) return fail("front and back windows should have the same length");
+    const int64_t n = front->n;
+    if (n > c->capacity) return fail("more reads than the chunk's capacity");
+    try {
+        CUDA_CHECK(cudaSetDevice(c->device));
+        ReadView VF{front}, VB{back ? back : front};
+        if (tolerance > 0) {
+            VF.tol = tolerance;
+            VB = ReadView{front, tolerance, true};
+        }
+        PackTables PF, PB;
+        build_pack_tables(PF, front->seq_encoding, c->enc);
+        build_pack_tables(PB, VB.R->seq_encoding, c->enc);
+        const int nthreads = host_threads_for(1);
+        CUDA_CHECK(cudaStreamSynchronize(c->st));     /* the staging buffers of the previous load */
+        chunk_wait_tracebacks(c, c->st);
+        c->h_lens_f.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(n, 1));
+        c->h_lens_b.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(n, 1));
+        FirstError ef, eb;
+        int maxf = 0, maxb = 0;
+        scan_lengths(VF, 0, n, c->h_lens_f.as<int32_t>(), nthreads, ef, maxf);
+        scan_lengths(VB, 0, n, c->h_lens_b.as<int32_t>(), nthreads, eb, maxb);
+        if (std::max(maxf, maxb) > c->tol) return fail("a window is longer than the chunk's tolerance");
+        if (ef.kind != ERR_NONE || eb.kind != ERR_NONE) return fail(err_text(ef.kind != ERR_NONE ? ef.kind : eb.kind));
+        if (n > 0) {
+            chunk_mark(c, 0, true);
+            CUDA_CHECK(cudaMemcpyAsync(c->lens_f.p, c->h_lens_f.p, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->st));
+            CUDA_CHECK(cudaMemcpyAsync(c->lens_b.p, c->h_lens_b.p, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->st));
+            const bool pinned_f = !VF.R->seq && pointer_is_pinned(VF.R->seq_pool) && pointer_is_pinned(VF.R->qual_pool);
+            const bool pinned_b = !VB.R->seq && pointer_is_pinned(VB.R->seq_pool) && pointer_is_pinned(VB.R->qual_pool);
+            stage_and_pack(VF, 0, n, PF, c->h_lens_f.as<int32_t>(), c->lens_f.as<int32_t>(), c->stride, c->rows_f.as<uint16_t>(), true,
+                           pinned_f, c->raw_f, c->st, nthreads);
+            stage_and_pack(VB, 0, n, PB, c->h_lens_b.as<int32_t>(), c->lens_b.as<int32_t>(), c->stride, c->rows_b.as<uint16_t>(), true,
+                           pinned_b, c->raw_b, c->st, nthreads);
+            c->has_width = tolerance > 0 || width != nullptr;
+            if (c->has_width) {
+                c->h_width.reserve(sizeof(int32_t) * (size_t)n);
+                int32_t* hw = c->h_width.as<int32_t>();
+                for (int64_t i = 0; i < n; ++i) hw[i] = tolerance > 0 ? (int32_t)VF.full_seq_len(i) : width[i];
+                CUDA_CHECK(cudaMemcpyAsync(c->width.p, hw, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->st));
+            }
+            chunk_mark(c, 0, false);
+            CUDA_CHECK(cudaStreamSynchronize(c->st));
+            const long long fb = c->raw_f.first_bad(), fb2 = c->raw_b.first_bad();
+            if (fb >= 0 || fb2 >= 0) {
+                c->n = 0;
+                return fail(err_text(ERR_QUAL));
+            }
+        }
+        c->n = n;
+        c->maxlen = std::max(maxf, maxb);
+    } catch (CudaError& e) {
+        return fail(e.msg);
+    }
+    return 0;
+}
+
+int sarlacc_chunk_adaptor_align(sarlacc_chunk* c, double gapopen, double gapext, const char* adaptor1, const char* adaptor2,
+        int nsec1, const int32_t* sec_starts1, const int32_t* sec_ends1,
+        int nsec2, const int32_t* sec_starts2, const int32_t* sec_ends2,
+        int64_t out_pitch, int32_t* read_width, uint8_t* reversed,
+        double* score1, int32_t* start1, int32_t* end1, int32_t* sec_start1, int32_t* sec_width1,
+        double* score2, int32_t* start2, int32_t* end2, int32_t* sec_start2, int32_t* sec_width2)
+{
+    if (chunk_check_loaded(c)) return 1;
+    if (!adaptor1 || !adaptor2) return fail("adaptor sequence should be a string");
+    if (!*adaptor1 || !*adaptor2) return fail("chunk runs need two non-empty adaptors");
+    if (nsec1 < 0 || nsec2 < 0 || (nsec1 > 0 && (!sec_starts1 || !sec_ends1)) || (nsec2 > 0 && (!sec_starts2 || !sec_ends2)))
+        return fail("section starts and ends should have the same length");
+    try {
+        CUDA_CHECK(cudaSetDevice(c->device));
+        const int64_t n = c->n;
+        if (out_pitch < n) out_pitch = n;
+        sarlacc_chunk::CachedPlan* cp[2] = {chunk_plan(c, adaptor1, gapopen, gapext, true, nsec1, sec_starts1, sec_ends1),
+                                            chunk_plan(c, adaptor2, gapopen, gapext, true, nsec2, sec_starts2, sec_ends2)};
+        for (int k = 0; k < 2; ++k) {
+            const Plan& P = cp[k]->plan;
+            if (P.bad_col[0] >= 0) return fail(err_text(ERR_REF));
+            for (size_t x = 0; x < P.sec_starts.size(); ++x) {
+                if (P.sec_starts[x] < 0 || P.sec_starts[x] > P.L || P.sec_ends[x] < 0 || P.sec_ends[x] > P.L) return fail("section bounds outside the adaptor");
+            }
+        }
+        const Plan* plan[2] = {&cp[0]->plan, &cp[1]->plan};
+        const DevPlan* D[2] = {&cp[0]->d, &cp[1]->d};
+        const int nsec[2] = {nsec1, nsec2};
+        /* final columns of this call: [n] vectors and [nsec][n] matrices in one block, double-buffered across calls */
+        const int w = c->out_which;
+        c->out_which ^= 1;
+        auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        size_t o_rev = 0, o_score[2], o_start[2], o_end[2], o_ss[2], o_sw[2], at = al((size_t)n);
+        for (int k = 0; k < 2; ++k) {
+            o_score[k] = at; at += al(sizeof(double) * (size_t)n);
+            o_start[k] = at; at += al(sizeof(int32_t) * (size_t)n);
+            o_end[k] = at; at += al(sizeof(int32_t) * (size_t)n);
+            o_ss[k] = at; at += al(sizeof(int32_t) * (size_t)n * std::max(1, nsec[k]));
+            o_sw[k] = at; at += al(sizeof(int32_t) * (size_t)n * std::max(1, nsec[k]));
+        }
+        if (c->out_pending[w]) {       /* the copy-out of two calls ago still reads this block */
+            CUDA_CHECK(cudaStreamWaitEvent(c->st, c->out_copied[w], 0));
+            c->out_pending[w] = false;
+        }
+        if (at > c->out[w].cap) CUDA_CHECK(cudaStreamSynchronize(c->cp));
+        c->out[w].reserve(at);
+        uint8_t* d = c->out[w].as<uint8_t>();
+
+        /* sub-ranges: whole grid-fulls for both adaptors' kernels, four record sets within half the scratch budget each
+         * parity, so that the tracebacks of sub-range k run beside the forward passes of k+1 */
+        const long long g1 = plan_groups(*plan[0], true), g2 = plan_groups(*plan[1], true);
+        long long sub = chunk_for(1 << 17, g1, g2);
+        const long long fit = std::max<long long>(1, (long long)(scratch_budget_bytes() / pair_scratch_per_read(*plan[0], *plan[1], c->maxlen)));
+        if (sub > fit) sub = std::max<long long>(1, whole_rounds(fit, std::max(g1, g2)));
+        const char* ce = std::getenv("SARLACC_CHUNK");
+        if (ce && std::atoll(ce) > 0) sub = std::atoll(ce);
+        chunk_mark(c, 1, true);
+        const char* name = "";
+        for (long long off = 0; off < n; off += sub) {
+            const long long m = std::min<long long>(sub, n - off);
+            const int b = c->parity;
+            c->parity ^= 1;
+            if (c->tb_pending[b]) {
+                CUDA_CHECK(cudaStreamWaitEvent(c->st, c->tb_done[b], 0));
+                c->tb_pending[b] = false;
+            }
+            PairDeviceOut po;
+            po.reversed = d + o_rev + off;
+            for (int k = 0; k < 2; ++k) {
+                po.score[k] = reinterpret_cast<double*>(d + o_score[k]) + off;
+                po.start[k] = reinterpret_cast<int32_t*>(d + o_start[k]) + off;
+                po.end[k] = reinterpret_cast<int32_t*>(d + o_end[k]) + off;
+                po.sec_start[k] = reinterpret_cast<int32_t*>(d + o_ss[k]) + off;
+                po.sec_width[k] = reinterpret_cast<int32_t*>(d + o_sw[k]) + off;
+            }
+            po.pitch = n;
+            name = run_pair_device(plan, D, c->pair[b], c->st, c->tb, c->fwd_done[b], c->tb_done[b],
+                                   c->rows_f.as<uint16_t>() + (size_t)off * c->stride, c->lens_f.as<int32_t>() + off, c->stride,
+                                   c->rows_b.as<uint16_t>() + (size_t)off * c->stride, c->lens_b.as<int32_t>() + off, c->stride,
+                                   m, c->maxlen, c->has_width ? c->width.as<int32_t>() + off : nullptr,
+                                   c->tmp.as<double>() + 4 * (size_t)off, po, c->sms);
+            c->tb_pending[b] = true;
+        }
+        chunk_mark(c, 1, false);
+        for (int k = 0; k < 2; ++k) {
+            const Geometry g = geometry_for(*plan[k], c->maxlen);
+            c->last_kernel[k] = std::string(k == 0 ? name : g_last_kernel) + " G=" + std::to_string(g.G) + " C=" + std::to_string(g.C);
+        }
+        /* copy-out on the copy stream, behind the tracebacks (which are behind the forward passes and strand resolution) */
+        for (int b = 0; b < 2; ++b) {
+            if (c->tb_pending[b]) CUDA_CHECK(cudaStreamWaitEvent(c->cp, c->tb_done[b], 0));
+        }
+        chunk_copy_out(c, reversed, d + o_rev, (size_t)n);
+        double* const sc[2] = {score1, score2};
+        int32_t* const stt[2] = {start1, start2};
+        int32_t* const enn[2] = {end1, end2};
+        int32_t* const sst[2] = {sec_start1, sec_start2};
+        int32_t* const sww[2] = {sec_width1, sec_width2};
+        for (int k = 0; k < 2; ++k) {
+            chunk_copy_out(c, sc[k], d + o_score[k], sizeof(double) * (size_t)n);
+            chunk_copy_out(c, stt[k], d + o_start[k], sizeof(int32_t) * (size_t)n);
+            chunk_copy_out(c, enn[k], d + o_end[k], sizeof(int32_t) * (size_t)n);
+            for (int x = 0; x < nsec[k]; ++x) {
+                if (sst[k]) chunk_copy_out(c, sst[k] + (size_t)x * out_pitch, d + o_ss[k] + sizeof(int32_t) * (size_t)x * n, sizeof(int32_t) * (size_t)n);
+                if (sww[k]) chunk_copy_out(c, sww[k] + (size_t)x * out_pitch, d + o_sw[k] + sizeof(int32_t) * (size_t)x * n, sizeof(int32_t) * (size_t)n);
+            }
+        }
+        if (read_width && c->has_width) chunk_copy_out(c, read_width, c->width.p, sizeof(int32_t) * (size_t)n);
+        CUDA_CHECK(cudaEventRecord(c->out_copied[w], c->cp));
+        c->out_pending[w] = true;
+    } catch (CudaError& e) {
+        return fail(e.msg);
+    }
+    return 0;
+}
+
+int sarlacc_chunk_scrambled_scores(sarlacc_chunk* c, double gapopen, double gapext, const char* adaptor1, const char* adaptor2,
+        uint64_t seed, uint64_t first_index, const uint64_t* read_index, int scramble, double* score1, double* score2)
+{
+    if (chunk_check_loaded(c)) return 1;
+    if (!adaptor1 || !adaptor2) return fail("adaptor sequence should be a string");
+    if (!*adaptor1 || !*adaptor2) return fail("chunk runs need two non-empty adaptors");
+    try {
+        CUDA_CHECK(cudaSetDevice(c->device));
+        const int64_t n = c->n;
+        sarlacc_chunk::CachedPlan* cp[2] = {chunk_plan(c, adaptor1, gapopen, gapext, false, 0, nullptr, nullptr),
+                                            chunk_plan(c, adaptor2, gapopen, gapext, false, 0, nullptr, nullptr)};
+        if (cp[0]->plan.bad_col[0] >= 0 || cp[1]->plan.bad_col[0] >= 0) return fail(err_text(ERR_REF));
+        const uint16_t* rf = c->rows_f.as<uint16_t>();
+        const uint16_t* rb = c->rows_b.as<uint16_t>();
+        if (scramble) {
+            const size_t bytes = sizeof(uint16_t) * (size_t)c->capacity * c->stride;
+            c->srows_f.reserve(bytes);
+            c->srows_b.reserve(bytes);
+            DevBuf idx;
+            if (read_index) {
+                idx.reserve(sizeof(uint64_t) * (size_t)n);
+                CUDA_CHECK(cudaMemcpyAsync(idx.p, read_index, sizeof(uint64_t) * (size_t)n, cudaMemcpyDefault, c->st));
+            }
+            chunk_mark(c, 2, true);
+            launch_scramble(rf, c->srows_f.as<uint16_t>(), c->lens_f.as<int32_t>(), n, c->stride, seed, first_index,
+                            read_index ? idx.as<unsigned long long>() : nullptr, 0, c->st);
+            launch_scramble(rb, c->srows_b.as<uint16_t>(), c->lens_b.as<int32_t>(), n, c->stride, seed, first_index,
+                            read_index ? idx.as<unsigned long long>() : nullptr, 1, c->st);
+            chunk_mark(c, 2, false);
+            g_launches += 2;
+            CUDA_CHECK(cudaGetLastError());
+            if (read_index) {
+                CUDA_CHECK(cudaStreamSynchronize(c->st));
+                idx.release();
+            }
+            rf = c->srows_f.as<uint16_t>();
+            rb = c->srows_b.as<uint16_t>();
+        }
+        /* the four forward passes of .get_alignment_scores (R/tuneAlignment.R:99-112): START, END, RSTART, REND */
+        chunk_mark(c, 3, true);
+        double* tmp = c->tmp.as<double>();
+        for (int r = 0; r < 4; ++r) {
+            const int a = (r == 0 || r == 2) ? 0 : 1;
+            const bool on_front = (r == 0 || r == 3);
+            Outputs dev;
+            dev.score = tmp + (size_t)r * n;
+            forward_once(cp[a]->plan, cp[a]->d, c->score_scratch, c->st, on_front ? rf : rb,
+                         on_front ? c->lens_f.as<int32_t>() : c->lens_b.as<int32_t>(), n, c->stride, c->maxlen, false, dev, c->sms);
+        }
+        /* kept scores: straight into device destinations, through a chunk buffer + the copy stream for host ones */
+        cudaPointerAttributes at1, at2;
+        const bool dev1 = score1 && cudaPointerGetAttributes(&at1, score1) == cudaSuccess && at1.type == cudaMemoryTypeDevice;
+        const bool dev2 = score2 && cudaPointerGetAttributes(&at2, score2) == cudaSuccess && at2.type == cudaMemoryTypeDevice;
+        cudaGetLastError();
+        const int w = c->sout_which;
+        c->sout_which ^= 1;
+        if (c->sout_pending[w]) {
+            CUDA_CHECK(cudaStreamWaitEvent(c->st, c->sout_copied[w], 0));
+            c->sout_pending[w] = false;
+        }
+        c->sout[w].reserve(sizeof(double) * 2 * (size_t)c->capacity);
+        double* own = c->sout[w].as<double>();
+        StrandArgs SA;
+        SA.n = n;
+        SA.a1_front = tmp;
+        SA.a2_back = tmp + (size_t)n;
+        SA.a1_back = tmp + (size_t)2 * n;
+        SA.a2_front = tmp + (size_t)3 * n;
+        SA.reversed = nullptr;
+        SA.score1 = dev1 ? score1 : own;
+        SA.score2 = dev2 ? score2 : own + c->capacity;
+        launch_resolve_strand(SA, c->st);
+        chunk_mark(c, 3, false);
+        g_launches += 1;
+        CUDA_CHECK(cudaGetLastError());
+        if ((score1 && !dev1) || (score2 && !dev2)) {
+            CUDA_CHECK(cudaEventRecord(c->out_ready, c->st));
+            CUDA_CHECK(cudaStreamWaitEvent(c->cp, c->out_ready, 0));
+            if (score1 && !dev1) chunk_copy_out(c, score1, own, sizeof(double) * (size_t)n);
+            if (score2 && !dev2) chunk_copy_out(c, score2, own + c->capacity, sizeof(double) * (size_t)n);
+            CUDA_CHECK(cudaEventRecord(c->sout_copied[w], c->cp));
+            c->sout_pending[w] = true;
+        }
+    } catch (CudaError& e) {
+        return fail(e.msg);
+    }
+    return 0;
+}
+
+int sarlacc_chunk_sync(sarlacc_chunk* c) {
+    if (!c) return fail("chunk handle is NULL");
+    try {
+        CUDA_CHECK(cudaSetDevice(c->device));
+        CUDA_CHECK(cudaStreamSynchronize(c->st));
+        CUDA_CHECK(cudaStreamSynchronize(c->tb));
+        CUDA_CHECK(cudaStreamSynchronize(c->cp));
+        for (int b = 0; b < 2; ++b) c->tb_pending[b] = c->out_pending[b] = c->sout_pending[b] = false;
+        chunk_collect_timing(c);
+    } catch (CudaError& e) {
+        return fail(e.msg);
+    }
+    return 0;
+}
+
+/* Tests / reports: packed rows of window set `which` (0 front, 1 back, 2 scrambled front, 3 scrambled back), lengths,
+ * widths and strand flips of the loaded reads; any pointer may be NULL. */
+int sarlacc_chunk_rows(sarlacc_chunk* c, int which, uint16_t* rows, int32_t* lens, int* stride, int32_t* width, uint8_t* flipped) {
+    if (!c) return fail("chunk handle is NULL");
+    if (which < 0 || which > 3) return fail("window set must be 0..3");
+    try {
+        CUDA_CHECK(cudaSetDevice(c->device));
+        if (sarlacc_chunk_sync(c)) return 1;
+        if (stride) *stride = c->stride;
+        const DevBuf& r = which == 0 ? c->rows_f : (which == 1 ? c->rows_b : (which == 2 ? c->srows_f : c->srows_b));
+        const DevBuf& l = (which & 1) ? c->lens_b : c->lens_f;
+        if (c->n > 0 && rows) {
+            if (!r.p) return fail("that window set has not been produced");
+            CUDA_CHECK(cudaMemcpy(rows, r.p, sizeof(uint16_t) * (size_t)c->n * c->stride, cudaMemcpyDeviceToHost));
+        }
+        if (c->n > 0 && lens) CUDA_CHECK(cudaMemcpy(lens, l.p, sizeof(int32_t) * (size_t)c->n, cudaMemcpyDeviceToHost));
+        if (c->n > 0 && width && c->has_width) CUDA_CHECK(cudaMemcpy(width, c->width.p, sizeof(int32_t) * (size_t)c->n, cudaMemcpyDeviceToHost));
+        if (c->n > 0 && flipped) CUDA_CHECK(cudaMemcpy(flipped, c->flipped.p, (size_t)c->n, cudaMemcpyDeviceToHost));
+    } catch (CudaError& e) {
+        return fail(e.msg);
+    }
+    return 0;
+}
+
+void sarlacc_chunk_set_timing(sarlacc_chunk* c, int on) {
+    if (!c) return;
+    c->timing = on != 0;
+    for (double& x : c->phase_ms) x = 0;
+}
+
+int sarlacc_chunk_phase_ms(sarlacc_chunk* c, double* ms4) {
+    if (!c || !ms4) return fail("chunk handle is NULL");
+    if (sarlacc_chunk_sync(c)) return 1;
+    for (int k = 0; k < 4; ++k) ms4[k] = c->phase_ms[k];
+    return 0;
+}
+
+const char* sarlacc_chunk_last_kernel(const sarlacc_chunk* c, int adaptor) {
+    return (c && (adaptor == 0 || adaptor == 1)) ? c->last_kernel[adaptor].c_str() : "";
 }
 
 }  // extern "C"

@@ -164,14 +164,49 @@ __device__ __forceinline__ double pick_move(double h, double m, double v, bool& 
 
 constexpr int kCostEntries = 7;   /* A, C, G, T, two-fold code, three-fold code, N */
 
-/* Element x = ((q * 5 + o) * 4 + part) of the pre-tabulated cost records (see wf_forward): part 0 = entries A,C;
- * 1 = G,T; 2 = two-fold, three-fold; 3 = N, unused.  cost = AlignArgs::cost, [5][encn]. */
-__device__ __forceinline__ double2 pre_record(const double* cost, int encn, int x) {
-    const int q = x / 20, o = (x / 4) % 5, part = x & 3;
-    const double mq = cost[q], xq = cost[encn + q];
-    if (part < 2) return make_double2((o - 1 == 2 * part) ? mq : xq, (o - 1 == 2 * part + 1) ? mq : xq);
-    if (part == 2) return make_double2(cost[2 * encn + q], cost[3 * encn + q]);
-    return make_double2(cost[4 * encn + q], 0.0);
+/* Whether the solo instantiation for C columns computes the (mis)match candidate inside the chain loop (see wf_forward2).
+ * Chosen per C from the static instruction count of the row loop (tools/variant_count.sh): ptxas 12.9 runs out of
+ * predicate registers in one form or the other, differently per C, and then moves predicates through general registers
+ * (P2R / LOP3 / ISETP: +10 instructions per cell).  tests/test_abi.py watches the built library for that. */
+#ifndef SARLACC_SOLO_JIT_MASK
+#define SARLACC_SOLO_JIT_MASK 0x0   /* bit (C - 20) set: that C uses the in-loop form */
+#endif
+template <int C>
+struct SoloJit { static constexpr bool value = C >= 20 && C <= 24 && ((SARLACC_SOLO_JIT_MASK >> (C - 20)) & 1) != 0; };
+
+/* Element x = q * 4 + part of the per-quality cost records in shared memory: part 0 = {match1[q], mismatch1[q]},
+ * 1 = {mismatch2[q], match3[q]} (two-fold / three-fold codes), 2 = {match4[q], 0} (N), 3 unused -- 64 bytes per quality
+ * index, so a row's costs are one LDS.128 (+ one or two more if the reference has IUPAC codes).  Lanes whose rows have
+ * the same quality read the same address (a broadcast, no bank conflict): records indexed by (quality, observed base)
+ * cost 2-4 shared-memory wavefronts more per load, which the row loop cannot afford -- at 12 resident warps per SM it
+ * already spends 2 wavefronts per DP cell-row on the per-cell cost loads (profiles/r02_history.md).  cost = AlignArgs::cost. */
+__device__ __forceinline__ double2 q_record(const double* cost, int encn, int x) {
+    const int q = x >> 2, part = x & 3;
+    if (part == 0) return make_double2(cost[q], cost[encn + q]);
+    if (part == 1) return make_double2(cost[2 * encn + q], cost[3 * encn + q]);
+    if (part == 2) return make_double2(cost[4 * encn + q], 0.0);
+    return make_double2(0.0, 0.0);
+}
+
+/* The lane's private table of one row's possible costs (entry e at tab[e * 32]): reference A,C,G,T -> mismatch1[q],
+ * except the observed base's own entry -> match1[q] (src/reference_align.cpp:186-187); two-fold / three-fold codes and N
+ * -> mismatch2 / match3 / match4 [q] whatever was observed (:188-209).  rw = quality index | one-hot base << 8. */
+__device__ __forceinline__ void fill_cost_table(double* tab, const double2* qrec, unsigned rw, int kinds) {
+    const unsigned q = rw & 0xffu;
+    const int o = __ffs(rw >> 8);                   /* one-hot A=1,C=2,G=4,T=8 -> 1..4; 0 for anything else */
+    const double2* rec = qrec + q * 4;
+    const double2 mx = rec[0];
+    tab[0 * 32] = mx.y;
+    tab[1 * 32] = mx.y;
+    tab[2 * 32] = mx.y;
+    tab[3 * 32] = mx.y;
+    if (o) tab[(o - 1) * 32] = mx.x;
+    if (kinds & 6) {
+        const double2 iu = rec[1];
+        tab[4 * 32] = iu.x;
+        tab[5 * 32] = iu.y;
+    }
+    if (kinds & 8) tab[6 * 32] = rec[2].x;
 }
 
 template <int C, bool TRACE>
@@ -182,12 +217,8 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
     const int L = A.L, nref = A.nref, encn = A.enc_n;
     double* row0s = smem_d;                                   /* [L+1]                         */
     double* lanetab = row0s + (L + 1);                        /* [warps][kCostEntries][32] lane-private cost entries */
-    /* pre[q][o][e]: the row's possible costs given its quality index q and observed base o (0 = other, 1..4 = A,C,G,T):
-     * e = 0..3 reference A,C,G,T -> match1[q] if o-1 == e else mismatch1[q]; e = 4,5,6 two-fold / three-fold code / N ->
-     * mismatch2[q], match3[q], match4[q] whatever was observed (src/reference_align.cpp:184-212); e = 7 unused.  One
-     * 64-byte record per (q, o), read with four LDS.128 per row -- no branches on which classes the reference has. */
-    double2* pre = reinterpret_cast<double2*>(smem_d + (((size_t)(L + 1) + (kBlock / 32) * kCostEntries * 32 + 1) & ~(size_t)1));   /* 16-byte aligned */
-    uint8_t* refm = reinterpret_cast<uint8_t*>(pre + (size_t)encn * 5 * 4);   /* [nref][L] */
+    double2* qrec = reinterpret_cast<double2*>(smem_d + (((size_t)(L + 1) + (kBlock / 32) * kCostEntries * 32 + 1) & ~(size_t)1));   /* [encn][4], see q_record */
+    uint8_t* refm = reinterpret_cast<uint8_t*>(qrec + (size_t)encn * 4);   /* [nref][L] */
     uint8_t* refk = refm + (size_t)nref * L;                                                    /* [nref][L] */
 
     for (int x = threadIdx.x; x <= L; x += blockDim.x) row0s[x] = A.row0[x];
@@ -195,7 +226,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
         refm[x] = A.refmask[x];
         refk[x] = A.refkind[x];
     }
-    for (int x = threadIdx.x; x < encn * 5 * 4; x += blockDim.x) pre[x] = pre_record(A.cost, encn, x);
+    for (int x = threadIdx.x; x < encn * 4; x += blockDim.x) qrec[x] = q_record(A.cost, encn, x);
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
@@ -210,6 +241,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
     const int cfirst = wf_first_col(j, C, pad);     /* DP column of the first real slot */
     const double gop = A.gop, ge = A.ge;
     const int local = A.local;
+    const int kinds = A.kinds;
     const double NEG = neg_inf();
     const bool first_lane = (j == 0);
     /* vertical penalties of slot C-1: zero for the last reference column in local mode (:120-121) */
@@ -259,21 +291,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
 
     /* One DP row of this lane's C columns.  `live` gates the only side effect (the trace store). */
     auto row_step = [&](double Sl, double El, bool live) {
-        const unsigned rw = *rowp;
-        const unsigned q = rw & 0xffu;
-        const unsigned obs = rw >> 8;
-        {
-            const int o = __ffs(obs);                       /* one-hot A=1,C=2,G=4,T=8 -> 1..4; 0 for anything else */
-            const double2* rec = pre + (q * 5 + o) * 4;
-            const double2 ac = rec[0], gt = rec[1], iu = rec[2], nn = rec[3];
-            mytab[0 * 32] = ac.x;
-            mytab[1 * 32] = ac.y;
-            mytab[2 * 32] = gt.x;
-            mytab[3 * 32] = gt.y;
-            mytab[4 * 32] = iu.x;
-            mytab[5 * 32] = iu.y;
-            mytab[6 * 32] = nn.x;
-        }
+        fill_cost_table(mytab, qrec, *rowp, kinds);
         {   /* column 0 feeds the first lane: src/reference_align.cpp:64-78 (0 in local mode; uniform branch otherwise) */
             const double c0v = __dsub_rn(c0base, __dmul_rn(c0step, (double)(i - 1)));   /* H[i][0], i >= 1 */
             Sl = first_lane ? c0v : Sl;
@@ -440,8 +458,8 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
     const int L = A.L, nref = A.nref, encn = A.enc_n;
     double* row0s = smem_d;                                   /* [L+1]                         */
     double* lanetab = row0s + (L + 1);                        /* [warps][2 rows][kCostEntries][32] lane-private cost entries */
-    double2* pre = reinterpret_cast<double2*>(smem_d + (((size_t)(L + 1) + (kBlock / 32) * 2 * kCostEntries * 32 + 1) & ~(size_t)1));   /* see wf_forward */
-    uint8_t* refm = reinterpret_cast<uint8_t*>(pre + (size_t)encn * 5 * 4);   /* [nref][L] */
+    double2* qrec = reinterpret_cast<double2*>(smem_d + (((size_t)(L + 1) + (kBlock / 32) * 2 * kCostEntries * 32 + 1) & ~(size_t)1));   /* [encn][4], see q_record */
+    uint8_t* refm = reinterpret_cast<uint8_t*>(qrec + (size_t)encn * 4);   /* [nref][L] */
     uint8_t* refk = refm + (size_t)nref * L;                                   /* [nref][L] */
 
     for (int x = threadIdx.x; x <= L; x += blockDim.x) row0s[x] = A.row0[x];
@@ -449,7 +467,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
         refm[x] = A.refmask[x];
         refk[x] = A.refkind[x];
     }
-    for (int x = threadIdx.x; x < encn * 5 * 4; x += blockDim.x) pre[x] = pre_record(A.cost, encn, x);
+    for (int x = threadIdx.x; x < encn * 4; x += blockDim.x) qrec[x] = q_record(A.cost, encn, x);
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
@@ -464,6 +482,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
     const int cfirst = SOLO ? 1 : wf_first_col(j, C, pad);
     const double gop = A.gop, ge = A.ge;
     const int local = A.local;
+    const int kinds = A.kinds;
     const double NEG = neg_inf();
     const bool first_lane = SOLO ? true : (j == 0);
     const double vo_last = (local && j == G - 1) ? 0.0 : gop;
@@ -514,26 +533,12 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
     int bid = 0;
     int lf0 = 0, lf1 = 0;   /* last slot: landing row of the traceback's climb (land_step) */
 
-    auto fill_table = [&](double* tab, unsigned rw) {
-        const unsigned q = rw & 0xffu;
-        const int o = __ffs(rw >> 8);
-        const double2* rec = pre + (q * 5 + o) * 4;
-        const double2 ac = rec[0], gt = rec[1], iu = rec[2], nn = rec[3];
-        tab[0 * 32] = ac.x;
-        tab[1 * 32] = ac.y;
-        tab[2 * 32] = gt.x;
-        tab[3 * 32] = gt.y;
-        tab[4 * 32] = iu.x;
-        tab[5 * 32] = iu.y;
-        tab[6 * 32] = nn.x;
-    };
-
     /* Rows i+1 (A) and i+2 (B) of this lane's C columns.  MASKED: row B may not exist (hasB false) and then must leave no
      * trace in the state.  `live` gates the trace stores. */
     auto pair_step = [&](auto masked_tag, unsigned rw2, double SlA, double ElA, double SlB, double ElB, bool live, bool hasB) {
         constexpr bool MASKED = decltype(masked_tag)::value;
-        fill_table(mytab, rw2 & 0xffffu);
-        fill_table(mytab + kTab, rw2 >> 16);
+        fill_cost_table(mytab, qrec, rw2 & 0xffffu, kinds);
+        fill_cost_table(mytab + kTab, qrec, rw2 >> 16, kinds);
         {   /* column 0 feeds the first lane: src/reference_align.cpp:64-78 */
             const double c0a = __dsub_rn(c0base, __dmul_rn(c0step, (double)i));           /* H[i+1][0] */
             const double c0b = __dsub_rn(c0base, __dmul_rn(c0step, (double)(i + 1)));     /* H[i+2][0] */
@@ -552,7 +557,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
          * ptxas 12.9 makes of it: with the other form it runs out of predicate registers in the row loop of solo C = 20..22
          * (and with this form in C = 23, 24) and spills them through P2R / LOP3 / ISETP, +10 instructions per cell
          * (tests/test_abi.py::test_no_predicate_spills_in_row_loops watches the built library for that). */
-        constexpr bool JIT = (SOLO && C <= 22) || (SARLACC_WF_JIT_M != 0);
+        constexpr bool JIT = (SOLO && SoloJit<C>::value) || (SARLACC_WF_JIT_M != 0);
         double mA[JIT ? 1 : C];
         bool p2lastA = false;
         double diagA = diag0;
@@ -1388,9 +1393,9 @@ bool for_geometry(int C, bool solo, F&& f) {
 }  // namespace
 
 size_t wavefront_smem_bytes(const AlignArgs& a) {
-    /* row-0 chain + lane-private tables (two rows' worth: the row-pair kernel) + 64-byte cost records + reference columns */
+    /* row-0 chain + lane-private tables (two rows' worth: the row-pair kernel) + 64-byte per-quality cost records + reference columns */
     return sizeof(double) * ((((size_t)a.L + 1 + (size_t)(kBlock / 32) * 2 * kCostEntries * 32 + 1) & ~(size_t)1) +
-                             (size_t)a.enc_n * 5 * 8) +
+                             (size_t)a.enc_n * 8) +
            2 * (size_t)a.nref * a.L;
 }
 

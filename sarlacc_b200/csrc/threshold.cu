@@ -1,0 +1,114 @@
+/* .compute_threshold (/root/reference/R/getAdaptorThresholds.R:94-103) on the device.
+ *
+ *     real <- sort(real); scrambled <- sort(scrambled)
+ *     fdr <- (length(scrambled) - findInterval(real, scrambled)) / (length(real) - seq_along(real))
+ *     real[min(which(fdr <= error))]
+ *
+ * The one step of adaptorAlign + getAdaptorThresholds that looks at all reads at once: with 50 M reads per
+ * adaptor the two sorts are what costs, so they run on the device (CUB radix sort -- library code, like the R sort it
+ * replaces; the hot path is the alignment) and the FDR scan is one pass of binary searches with a min-index reduction.
+ * IEEE semantics as in R: integer counts divided as doubles (correctly rounded division), the last term divides by zero
+ * (Inf or NaN, never <= error unless error is Inf), an empty which() gives NA -> NaN here.
+ */
+#include "sarlacc_b200.h"
+#include "kernels.h"
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include <limits>
+#include <string>
+
+namespace sarlacc {
+int set_error(const std::string& msg);
+void count_launches(int n);
+}
+
+namespace {
+
+/* findInterval(x, v) for sorted v = number of elements <= x. */
+__device__ __forceinline__ long long count_le(const double* v, long long n, double x) {
+    long long lo = 0, hi = n;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (v[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) fdr_first_index(const double* real, long long nr, const double* scr, long long ns, double error,
+                                                      unsigned long long* first)
+{
+    long long best = nr;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nr; k += (long long)gridDim.x * blockDim.x) {
+        const double num = (double)(ns - count_le(scr, ns, real[k]));
+        const double den = (double)(nr - (k + 1));
+        const double fdr = __ddiv_rn(num, den);
+        if (fdr <= error) { best = k; break; }       /* k ascends per thread: its first hit is its smallest */
+    }
+    /* min over the block, then over the grid */
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long other = __shfl_down_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+    }
+    if ((threadIdx.x & 31) == 0 && best < nr) atomicMin(first, (unsigned long long)best);
+}
+
+struct Tmp {
+    void* p = nullptr;
+    ~Tmp() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+};
+
+}  // namespace
+
+extern "C" int sarlacc_compute_threshold(const double* real, int64_t nreal, const double* scrambled, int64_t nscr, double error,
+                                         int device, double* threshold)
+{
+    if (!threshold) return sarlacc::set_error("threshold must not be NULL");
+    if (nreal < 0 || nscr < 0 || (nreal > 0 && !real) || (nscr > 0 && !scrambled)) return sarlacc::set_error("score vectors must not be NULL");
+    *threshold = std::numeric_limits<double>::quiet_NaN();       /* real[min(integer(0))] -> NA */
+    if (nreal == 0) return 0;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        return sarlacc::set_error("sarlacc_b200 requires a CUDA device (no CPU fallback exists): no device found");
+    }
+#define TH_CHECK(expr)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t e_ = (expr);                                                                            \
+        if (e_ != cudaSuccess) return sarlacc::set_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #expr); \
+    } while (0)
+    TH_CHECK(cudaSetDevice(device));
+    Tmp r_in, r_out, s_in, s_out, work, first;
+    const size_t rb = sizeof(double) * (size_t)nreal, sb = sizeof(double) * (size_t)nscr;
+    TH_CHECK(r_in.alloc(rb));
+    TH_CHECK(r_out.alloc(rb));
+    TH_CHECK(s_in.alloc(sb));
+    TH_CHECK(s_out.alloc(sb));
+    TH_CHECK(first.alloc(sizeof(unsigned long long)));
+    /* cudaMemcpyDefault: the vectors may live on the host or on a device (e.g. gathered from all ranks) */
+    TH_CHECK(cudaMemcpy(r_in.p, real, rb, cudaMemcpyDefault));
+    if (nscr > 0) TH_CHECK(cudaMemcpy(s_in.p, scrambled, sb, cudaMemcpyDefault));
+    size_t wbytes = 0, wbytes2 = 0;
+    TH_CHECK(cub::DeviceRadixSort::SortKeys(nullptr, wbytes, (const double*)r_in.p, (double*)r_out.p, (long long)nreal));
+    TH_CHECK(cub::DeviceRadixSort::SortKeys(nullptr, wbytes2, (const double*)s_in.p, (double*)s_out.p, (long long)nscr));
+    if (wbytes2 > wbytes) wbytes = wbytes2;
+    TH_CHECK(work.alloc(wbytes));
+    TH_CHECK(cub::DeviceRadixSort::SortKeys(work.p, wbytes, (const double*)r_in.p, (double*)r_out.p, (long long)nreal));
+    if (nscr > 0) TH_CHECK(cub::DeviceRadixSort::SortKeys(work.p, wbytes, (const double*)s_in.p, (double*)s_out.p, (long long)nscr));
+    const unsigned long long none = ~0ULL;
+    TH_CHECK(cudaMemcpy(first.p, &none, sizeof(none), cudaMemcpyHostToDevice));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    long long grid = (nreal + 255) / 256;
+    if (grid > (long long)sms * 8) grid = (long long)sms * 8;
+    fdr_first_index<<<(int)grid, 256>>>((const double*)r_out.p, (long long)nreal, (const double*)s_out.p, (long long)nscr, error,
+                                        (unsigned long long*)first.p);
+    sarlacc::count_launches(1);
+    TH_CHECK(cudaGetLastError());
+    unsigned long long k = none;
+    TH_CHECK(cudaMemcpy(&k, first.p, sizeof(k), cudaMemcpyDeviceToHost));
+    if (k != none) TH_CHECK(cudaMemcpy(threshold, (const double*)r_out.p + k, sizeof(double), cudaMemcpyDeviceToHost));
+#undef TH_CHECK
+    return 0;
+}

@@ -427,3 +427,158 @@ class Resident:
 
     def last_kernel(self):
         return _lib.lib.sarlacc_resident_last_kernel(self.handle).decode()
+
+
+def _out_ptr(x):
+    """A destination the chunk calls accept: None, a numpy array (host), or an integer device address (e.g. torch's data_ptr())."""
+    if x is None:
+        return None
+    if isinstance(x, (int, np.integer)):
+        return C.c_void_p(int(x))
+    return x.ctypes.data_as(C.c_void_p)
+
+
+class Chunk:
+    """Device-resident reads re-loaded in place (sarlacc_chunk_*): what one FastqStreamer yield() is to the R drivers.
+    adaptor_align = .align_AA_internal (+ adaptor2 flip), scrambled_scores = .align_AT_internal.  Calls only enqueue work;
+    outputs (numpy arrays -- ideally page-locked -- or integer device addresses) are complete after sync()."""
+
+    def __init__(self, capacity, tolerance, encoding, device=0):
+        ea = _encoding_arg(encoding)
+        self.handle = _lib.lib.sarlacc_chunk_create(C.c_int(device), C.c_int64(int(capacity)), C.c_int(int(tolerance)), ea.ref())
+        if not self.handle:
+            raise SarlaccError(_lib.last_error())
+        self.capacity, self.tolerance, self.device = int(capacity), int(tolerance), device
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _lib.lib.sarlacc_chunk_free(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    @property
+    def n(self):
+        return int(_lib.lib.sarlacc_chunk_n(self.handle))
+
+    def load_windows(self, front, back, width=None, views=False, seq_encoding=SEQ_ASCII):
+        rf, rb = _reads_arg(front, views, seq_encoding), _reads_arg(back, views, seq_encoding)
+        w = None if width is None else np.ascontiguousarray(width, dtype=np.int32)
+        _lib.check(_lib.lib.sarlacc_chunk_load_reads(self.handle, rf.ref(), rb.ref(), C.c_int(0), _lib._ptr(w)))
+
+    def load_reads(self, reads, tolerance=None, views=False, seq_encoding=SEQ_ASCII):
+        rr = _reads_arg(reads, views, seq_encoding)
+        tol = self.tolerance if tolerance is None else int(tolerance)
+        _lib.check(_lib.lib.sarlacc_chunk_load_reads(self.handle, rr.ref(), None, C.c_int(tol), None))
+
+    def load_mock(self, n, adaptor1, adaptor2, seed=2000, first_index=0, insert_len=4908, barcodes=None,
+                  sub_rate=0.05, indel_rate=0.01, max_insert=5):
+        bs = [b.encode("latin-1") for b in (barcodes or [])]
+        arr = (C.c_char_p * max(len(bs), 1))(*bs)
+        _lib.check(_lib.lib.sarlacc_chunk_load_mock(
+            self.handle, C.c_int64(int(n)), C.c_uint64(int(first_index)), C.c_uint64(int(seed)),
+            adaptor1.encode("latin-1"), adaptor2.encode("latin-1"), C.c_int(int(insert_len)), arr if bs else None, C.c_int(len(bs)),
+            C.c_double(sub_rate), C.c_double(indel_rate), C.c_int(int(max_insert))))
+
+    def adaptor_align(self, gapopen, gapext, adaptor1, adaptor2, sec1=((), ()), sec2=((), ()), out=None, out_pitch=0):
+        """out: dict with any of reversed, width, score1, start1, end1, sec_start1, sec_width1, score2, ... (numpy arrays or
+        device addresses, already offset to this chunk's first read; section matrices have row pitch out_pitch).  Without
+        `out`, fresh arrays are allocated, the call is synchronised and (width, reversed, result1, result2) returned."""
+        secs = []
+        for st, en in (sec1, sec2):
+            ss = np.ascontiguousarray(st, dtype=np.int32).reshape(-1)
+            se = np.ascontiguousarray(en, dtype=np.int32).reshape(-1)
+            if len(ss) != len(se):
+                raise SarlaccError("section starts and ends should have the same length")
+            secs.append((ss, se))
+        own = out is None
+        n = self.n
+        if own:
+            out = {"reversed": np.empty(max(n, 1), np.uint8), "width": np.zeros(max(n, 1), np.int32)}
+            for k, (ss, _) in enumerate(secs, 1):
+                out["score%d" % k] = np.empty(n, np.float64)
+                out["start%d" % k] = np.empty(n, np.int32)
+                out["end%d" % k] = np.empty(n, np.int32)
+                out["sec_start%d" % k] = np.empty((max(len(ss), 1), max(n, 1)), np.int32)
+                out["sec_width%d" % k] = np.empty((max(len(ss), 1), max(n, 1)), np.int32)
+            out_pitch = max(n, 1)
+        self._keep = [secs, out]          # the library reads the section lists while it builds its plan only; outputs until sync
+        g = out.get
+        _lib.check(_lib.lib.sarlacc_chunk_adaptor_align(
+            self.handle, C.c_double(float(gapopen)), C.c_double(float(gapext)), adaptor1.encode("latin-1"), adaptor2.encode("latin-1"),
+            C.c_int(len(secs[0][0])), _lib._ptr(secs[0][0]), _lib._ptr(secs[0][1]),
+            C.c_int(len(secs[1][0])), _lib._ptr(secs[1][0]), _lib._ptr(secs[1][1]),
+            C.c_int64(int(out_pitch)), _out_ptr(g("width")), _out_ptr(g("reversed")),
+            _out_ptr(g("score1")), _out_ptr(g("start1")), _out_ptr(g("end1")), _out_ptr(g("sec_start1")), _out_ptr(g("sec_width1")),
+            _out_ptr(g("score2")), _out_ptr(g("start2")), _out_ptr(g("end2")), _out_ptr(g("sec_start2")), _out_ptr(g("sec_width2"))))
+        if not own:
+            return None
+        self.sync()
+        res = []
+        for k, (ss, _) in enumerate(secs, 1):
+            res.append([out["score%d" % k], out["start%d" % k], out["end%d" % k],
+                        [out["sec_start%d" % k][i, :n] for i in range(len(ss))], [out["sec_width%d" % k][i, :n] for i in range(len(ss))]])
+        return out["width"][:n], out["reversed"][:n].view(np.bool_), res[0], res[1]
+
+    def scrambled_scores(self, gapopen, gapext, adaptor1, adaptor2, seed=0, first_index=0, read_index=None, scramble=True,
+                         score1=None, score2=None):
+        """.align_AT_internal (scramble=True) or .get_alignment_scores + .resolve_strand on the windows as loaded.  Without
+        destinations, fresh arrays are allocated, the call is synchronised and (score1, score2) returned."""
+        own = score1 is None and score2 is None
+        n = self.n
+        if own:
+            score1, score2 = np.empty(n, np.float64), np.empty(n, np.float64)
+        idx = None if read_index is None else np.ascontiguousarray(read_index, dtype=np.uint64)
+        self._keep = [score1, score2, idx]
+        _lib.check(_lib.lib.sarlacc_chunk_scrambled_scores(
+            self.handle, C.c_double(float(gapopen)), C.c_double(float(gapext)), adaptor1.encode("latin-1"), adaptor2.encode("latin-1"),
+            C.c_uint64(int(seed)), C.c_uint64(int(first_index)), _lib._ptr(idx), C.c_int(1 if scramble else 0),
+            _out_ptr(score1), _out_ptr(score2)))
+        if own:
+            self.sync()
+            return score1, score2
+        return None
+
+    def sync(self):
+        _lib.check(_lib.lib.sarlacc_chunk_sync(self.handle))
+
+    def rows(self, which=0):
+        """(packed rows uint16[n][stride], window lengths, read widths, strand flips) of window set `which`
+        (0 front, 1 back, 2 scrambled front, 3 scrambled back)."""
+        stride = C.c_int(0)
+        _lib.check(_lib.lib.sarlacc_chunk_rows(self.handle, C.c_int(which), None, None, C.byref(stride), None, None))
+        n = self.n
+        rows = np.zeros((max(n, 1), stride.value), np.uint16)
+        lens = np.zeros(max(n, 1), np.int32)
+        width = np.zeros(max(n, 1), np.int32)
+        flipped = np.zeros(max(n, 1), np.uint8)
+        _lib.check(_lib.lib.sarlacc_chunk_rows(self.handle, C.c_int(which), _lib._ptr(rows), _lib._ptr(lens), C.byref(stride),
+                                              _lib._ptr(width), _lib._ptr(flipped)))
+        return rows[:n], lens[:n], width[:n], flipped[:n].view(np.bool_)
+
+    def set_timing(self, on=True):
+        _lib.lib.sarlacc_chunk_set_timing(self.handle, C.c_int(1 if on else 0))
+
+    def phase_ms(self):
+        ms = np.zeros(4, np.float64)
+        _lib.check(_lib.lib.sarlacc_chunk_phase_ms(self.handle, _lib._ptr(ms)))
+        return dict(zip(("load", "adaptor_align", "scramble", "score_only"), ms.tolist()))
+
+    def last_kernel(self, adaptor=0):
+        return _lib.lib.sarlacc_chunk_last_kernel(self.handle, C.c_int(adaptor)).decode()
+
+
+def compute_threshold(real, scrambled, error, device=0):
+    """.compute_threshold (R/getAdaptorThresholds.R:94-103) on the device.  real / scrambled: numpy float64 arrays, or
+    (device address, length) pairs for vectors already on `device`."""
+    def arg(x):
+        if isinstance(x, tuple):
+            return C.c_void_p(int(x[0])), int(x[1]), None
+        a = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        return _lib._ptr(a), len(a), a
+    rp, rn, rk = arg(real)
+    sp, sn, sk = arg(scrambled)
+    out = np.zeros(1, np.float64)
+    _lib.check(_lib.lib.sarlacc_compute_threshold(rp, C.c_int64(rn), sp, C.c_int64(sn), C.c_double(float(error)), C.c_int(device), _lib._ptr(out)))
+    return float(out[0])

@@ -96,21 +96,17 @@ def test_product_does_not_import_the_oracle():
 
 
 def test_no_predicate_spills_in_row_loops():
-    """ptxas sometimes runs out of predicate registers in the unrolled row loop of a forward kernel and spills them
-    through P2R + LOP3 + ISETP (ten extra instructions per DP cell, sarlacc_b200/csrc/kernels.cu: JIT).  A healthy
-    instantiation has a handful of P2R outside the loop; this watches the built library for the pathology."""
-    import collections
-    import subprocess
+    """ptxas sometimes runs out of predicate registers in the unrolled row loop of a forward kernel and moves them through
+    general registers (P2R + LOP3 + ISETP, or LOP3 alone: ten extra instructions per DP cell; sarlacc_b200/csrc/kernels.cu:
+    SoloJit).  This watches the row loops of the geometries the vignette adaptors and 24-bp barcodes use."""
+    import shutil
+    import sys
     from sarlacc_b200 import _lib
-    out = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True)
-    if out.returncode != 0:
+    if shutil.which("cuobjdump") is None:
         pytest.skip("cuobjdump unavailable")
-    cur, count = None, collections.Counter()
-    for line in out.stdout.splitlines():
-        if "Function :" in line:
-            cur = line.split("Function :")[1].strip()
-        elif " P2R " in line and cur and "wf_forward" in cur:
-            count[cur] += 1
-    assert count, "no forward kernels found in the library"
-    bad = {k: v for k, v in count.items() if v > 16}
-    assert not bad, bad
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_loop
+    for C, solo in ((18, 0), (20, 1), (21, 1), (22, 1), (23, 1), (24, 1), (11, 0), (12, 0)):
+        per_trace = sass_loop.analyse(_lib.LIB_PATH, "wf_forward2", C, 1, solo)[0]
+        per_score = sass_loop.analyse(_lib.LIB_PATH, "wf_forward2", C, 0, solo)[0]
+        assert per_trace < 29.0 and per_score < 23.5, (C, solo, per_trace, per_score)

@@ -105,7 +105,7 @@ def test_pair_pipeline_default_chunking(enc):
     from sarlacc_b200 import native, synth
     from oracle import r_level as R
     n = 300000
-    front, back, widths, _ = synth.mock_windows(n, VIGNETTE_A1, VIGNETTE_A2, seed=31)
+    front, back, widths, _ = synth.mock_windows_device(n, VIGNETTE_A1, VIGNETTE_A2, seed=31)
     s1, e1 = [16, 42], [28, 46]
     rev, r1, r2 = native.adaptor_align_windows(front, back, enc, 5, 1, VIGNETTE_A1, VIGNETTE_A2, (s1, e1), ((), ()), read_width=widths)
     res = {}
@@ -142,7 +142,7 @@ def test_pinned_inputs_take_the_zero_copy_path(enc):
     import torch
     from sarlacc_b200 import native, synth, ReadSet, SarlaccError
     n = 150000
-    front, back, widths, _ = synth.mock_windows(n, VIGNETTE_A1, VIGNETTE_A2, seed=55)
+    front, back, widths, _ = synth.mock_windows_device(n, VIGNETTE_A1, VIGNETTE_A2, seed=55)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()   # noqa: E731
     pf = ReadSet(pin(front.seq_pool), front.seq_off, pin(front.qual_pool), front.qual_off, front.names)
     pb = ReadSet(pin(back.seq_pool), back.seq_off, pin(back.qual_pool), back.qual_off, back.names)
@@ -342,7 +342,7 @@ def test_full_size_properties(port, enc):
     (2 x 200k windows x 4 alignments) and a strided sample against the oracle."""
     from sarlacc_b200 import native, synth
     n = 200000
-    front, back, widths, flips = synth.mock_windows(n, VIGNETTE_A1, VIGNETTE_A2, seed=2000)
+    front, back, widths, flips = synth.mock_windows_device(n, VIGNETTE_A1, VIGNETTE_A2, seed=2000)
     ss, se = [16, 42], [28, 46]
     a = native.adaptor_align(front, enc, 5, 1, VIGNETTE_A1, ss, se)
     # (1) score-only pass, resident pass and host-buffer pass agree bit for bit (batching / path invariance)

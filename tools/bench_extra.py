@@ -41,7 +41,7 @@ print("barcode_align one call per barcode (reference call pattern): %.3f s for 8
 
 # ---- configs[2]: thresholds (score-only on scrambled windows, windows resident) -----------------------------
 m = min(n, 1000000)
-front, back, widths, _ = synth.mock_windows(m, A1, A2, seed=2000)
+front, back, widths, _ = synth.mock_windows_device(m, A1, A2, seed=2000)
 rf0, rb0 = native.Resident(front, enc), native.Resident(back, enc)
 t0 = time.perf_counter()
 rf = rf0.scrambled(1, first_index=0, stream_id=0)

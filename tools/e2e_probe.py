@@ -11,7 +11,7 @@ A1 = "ACGCAGATCGATCGATNNNNNNNNNNNNCGCGCGAGCTGACTNNNNGCACGACTCTGGTTTTTTTTTTTT"
 A2 = "AAGGCCTTTTCCGACTCATGAA"
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-front, back, widths, _ = synth.mock_windows(n, A1, A2, seed=2000)
+front, back, widths, _ = synth.mock_windows_device(n, A1, A2, seed=2000)
 enc = native.phred_encoding()
 s1, e1 = [16, 42], [28, 46]
 w = widths.astype(np.int32)

@@ -16,7 +16,7 @@ which = sys.argv[2] if len(sys.argv) > 2 else "a1"
 mode = sys.argv[3] if len(sys.argv) > 3 else "trace"
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 ad = A1 if which == "a1" else A2
-front, back, _, _ = synth.mock_windows(n, A1, A2, seed=2000)
+front, back, _, _ = synth.mock_windows_device(n, A1, A2, seed=2000)
 enc = native.phred_encoding()
 r = native.Resident(front, enc)
 r.set_timing(True)

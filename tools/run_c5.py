@@ -1,12 +1,14 @@
-"""configs[4] (BASELINE.json): adaptorAlign + getAdaptorThresholds on 50 M synthetic 5 kb reads sharded over the GPUs of
-one box by read index.  Every rank (torchrun) or the single process takes `--share` reads (default 50 M / 8 = 6.25 M, the
-per-GPU share of the 8-GPU job) in batches of `--batch`, keeps the packed windows resident, runs the four alignments with
-traceback (adaptorAlign) and the four score-only alignments on device-scrambled windows (getAdaptorThresholds), and the
-thresholds are selected from all ranks' scores on rank 0.  Synthetic read generation is outside the timed phases (it
-stands in for the FASTQ file).  A strided sample of every batch is checked against the reference's own C++.
+"""configs[4] (BASELINE.json): adaptorAlign + getAdaptorThresholds on synthetic 5 kb reads sharded over the GPUs of one
+box by read index.  Every rank (torchrun) or the single process takes reads [rank * share, (rank + 1) * share) in chunks:
+the device generates the chunk's windows (sarlacc_chunk_load_mock), aligns both adaptors to both ends and walks back the
+kept strand (sarlacc_chunk_adaptor_align: result columns stream into page-locked host tables), scrambles the windows and
+scores them four more times (sarlacc_chunk_scrambled_scores: kept scores stay on the device); at the end the score vectors
+of all ranks are gathered and the two thresholds selected on rank 0's device (sarlacc_compute_threshold).  Wall time
+covers all of it, generation included.  A strided sample is checked against the reference's own C++ afterwards.
 
-usage: python tools/run_c5.py [--share N] [--batch M]      or under torchrun (one rank per GPU)"""
+usage: python tools/run_c5.py [--total N] [--chunk M] [--check-stride S]      or under torchrun (one rank per GPU)"""
 import argparse
+import json
 import os
 import sys
 import time
@@ -14,117 +16,133 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from sarlacc_b200 import api, native, synth  # noqa: E402
+from sarlacc_b200 import native, synth, _lib  # noqa: E402
 
 A1 = "ACGCAGATCGATCGATNNNNNNNNNNNNCGCGCGAGCTGACTNNNNGCACGACTCTGGTTTTTTTTTTTT"
 A2 = "AAGGCCTTTTCCGACTCATGAA"
-ap = argparse.ArgumentParser()
-ap.add_argument("--share", type=int, default=6250000)
-ap.add_argument("--batch", type=int, default=1250000)
-ap.add_argument("--check-stride", type=int, default=5003)
-args = ap.parse_args()
-rank = int(os.environ.get("RANK", "0"))
-world = int(os.environ.get("WORLD_SIZE", "1"))
-local = int(os.environ.get("LOCAL_RANK", "0"))
-import torch  # noqa: E402
-torch.cuda.set_device(local)
-if world > 1:
+S1, E1 = [16, 42], [28, 46]
+SEED, SCR_SEED, TOL = 5000, 1, 250
+
+
+def run(total, chunk, rank, world, local, check_stride=0, error=0.01, timing=True):
+    """Returns the record (dict) on every rank; thresholds / parity fields only on rank 0."""
+    import torch
     import torch.distributed as dist
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-enc = native.phred_encoding()
-s1, e1 = [16, 42], [28, 46]
-oracle = None
-try:
-    from oracle.oracle import Oracle
-    oracle = Oracle("ref" if Oracle.available("ref") else "port")
-except Exception:
-    pass
+    share = (total + world - 1) // world
+    lo, hi = rank * share, min(total, (rank + 1) * share)
+    n = max(0, hi - lo)
+    enc = native.phred_encoding()
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()   # noqa: E731
+    nn = max(n, 1)
+    out = {"reversed": pin(nn, torch.uint8), "width": pin(nn, torch.int32),
+           "start1": pin(nn, torch.int32), "end1": pin(nn, torch.int32), "sec_start1": pin((2, nn), torch.int32), "sec_width1": pin((2, nn), torch.int32),
+           "start2": pin(nn, torch.int32), "end2": pin(nn, torch.int32)}
+    dev = torch.device("cuda", local)
+    real1 = torch.empty(nn, dtype=torch.float64, device=dev)
+    real2 = torch.empty(nn, dtype=torch.float64, device=dev)
+    scr1 = torch.empty(nn, dtype=torch.float64, device=dev)
+    scr2 = torch.empty(nn, dtype=torch.float64, device=dev)
+    ch = native.Chunk(min(chunk, nn), TOL, enc, device=local)
+    # warm-up outside the timed region: module load, plan upload, scratch allocation
+    ch.load_mock(min(chunk, nn), A1, A2, seed=SEED, first_index=lo)
+    ch.adaptor_align(5, 1, A1, A2, (S1, E1), ((), ()), out={"score1": real1.data_ptr()}, out_pitch=nn)
+    ch.scrambled_scores(5, 1, A1, A2, seed=SCR_SEED, first_index=lo, score1=scr1.data_ptr(), score2=scr2.data_ptr())
+    ch.sync()
+    ch.set_timing(timing)
+    _lib.lib.sarlacc_kernel_launches(1)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for b0 in range(0, n, chunk):
+        m = min(chunk, n - b0)
+        ch.load_mock(m, A1, A2, seed=SEED, first_index=lo + b0)
+        o = {k: (v[:, b0:] if v.ndim == 2 else v[b0:]) for k, v in out.items()}
+        o["score1"] = real1.data_ptr() + 8 * b0
+        o["score2"] = real2.data_ptr() + 8 * b0
+        ch.adaptor_align(5, 1, A1, A2, (S1, E1), ((), ()), out=o, out_pitch=nn)
+        ch.scrambled_scores(5, 1, A1, A2, seed=SCR_SEED, first_index=lo + b0, score1=scr1.data_ptr() + 8 * b0, score2=scr2.data_ptr() + 8 * b0)
+    ch.sync()
+    t_align = time.perf_counter() - t0
+    # the one step that needs every read: gather the four score vectors, select the thresholds on rank 0
+    thr = None
+    if world > 1:
+        parts = [torch.empty(world * share, dtype=torch.float64, device=dev) if rank == 0 else None for _ in range(4)]
+        for src, dst in zip((real1, real2, scr1, scr2), parts):
+            pad = torch.zeros(share, dtype=torch.float64, device=dev)
+            pad[:n] = src[:n]
+            dist.gather(pad, list(dst.chunk(world)) if rank == 0 else None, dst=0)
+        if rank == 0:
+            keep = torch.cat([torch.arange(r * share, r * share + max(0, min(total, (r + 1) * share) - r * share), device=dev) for r in range(world)])
+            vecs = [p[keep] for p in parts]
+    else:
+        vecs = [real1[:n], real2[:n], scr1[:n], scr2[:n]]
+    if rank == 0:
+        thr = (native.compute_threshold((vecs[0].data_ptr(), total), (vecs[2].data_ptr(), total), error, device=local),
+               native.compute_threshold((vecs[1].data_ptr(), total), (vecs[3].data_ptr(), total), error, device=local))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_all = time.perf_counter() - t0
+    launches = int(_lib.lib.sarlacc_kernel_launches(0))
+    phases = ch.phase_ms() if timing else None
+    tt = torch.tensor([t_all, t_align], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_all, t_align = float(tt[0]), float(tt[1])
+    rec = {"reads": total, "n_gpus": world, "reads_per_gpu": share, "chunk": chunk, "seconds": t_all, "seconds_alignment_passes": t_align,
+           "reads_per_s": total / t_all, "cells_per_read": 92000, "gcups_per_gpu": total * 92000 / t_all / 1e9 / world,
+           "phases_ms_rank0": phases, "gpu_launches_rank0": launches, "kernels": [ch.last_kernel(0), ch.last_kernel(1)],
+           "d2h_bytes_per_read": 1 + 4 + 4 * 4 + 16, "thresholds": thr}
+    # parity on a strided sample: the reference's own C++ on the host mirror of the same reads
+    if check_stride and rank == 0 and n > 0:
+        from oracle.oracle import Oracle, phred_encoding
+        O = Oracle("ref" if Oracle.available("ref") else "port")
+        oenc = phred_encoding()
+        pick = np.arange(0, n, check_stride)
+        checked = 0
+        r1 = real1.cpu().numpy()
+        r2 = real2.cpu().numpy()
+        for i in pick:
+            f, b, w, _ = synth.mock_windows(1, A1, A2, seed=SEED, first_index=lo + int(i))
+            fa, ba = ((f.seq_pool, f.seq_off), (f.qual_pool, f.qual_off)), ((b.seq_pool, b.seq_off), (b.qual_pool, b.qual_off))
+            a = O.adaptor_align(*fa, oenc, 5, 1, A1, S1, E1)
+            bb = O.adaptor_align(*ba, oenc, 5, 1, A2)
+            c = O.adaptor_align(*ba, oenc, 5, 1, A1, S1, E1)
+            d = O.adaptor_align(*fa, oenc, 5, 1, A2)
+            rev = (max(a[0][0], 0) + max(bb[0][0], 0)) < (max(c[0][0], 0) + max(d[0][0], 0))
+            x, y = (c, d) if rev else (a, bb)
+            assert bool(out["reversed"][i]) == rev and out["width"][i] == w[0]
+            assert r1[i] == x[0][0] and r2[i] == y[0][0]
+            assert out["start1"][i] == x[1][0] and out["end1"][i] == x[2][0]
+            assert out["start2"][i] == w[0] - y[1][0] + 1 and out["end2"][i] == w[0] - y[2][0] + 1
+            for s in range(2):
+                assert out["sec_start1"][s, i] == x[3][s][0] and out["sec_width1"][s, i] == x[4][s][0]
+            checked += 1
+        rec["parity"] = {"checked_reads": checked, "stride": check_stride, "oracle": O.kind, "identical": True}
+    ch.close()
+    return rec
 
-t_align = t_thr = t_gen = 0.0
-real1, real2, scr1, scr2 = [], [], [], []
-checked = 0
-stream = torch.cuda.Stream(device=local)
-bufs = {}
-# one untimed warm-up batch first (module load, page-locked result buffers), then the share in batches
-for bi, b0 in enumerate([-1] + list(range(0, args.share, args.batch))):
-    warm = b0 < 0
-    b0 = max(b0, 0)
-    m = min(args.batch, args.share - b0)
-    first = rank * args.share + b0
-    t0 = time.perf_counter()
-    front, back, widths, _ = synth.mock_windows(m, A1, A2, seed=5000, first_index=first)
-    if not warm:
-        t_gen += time.perf_counter() - t0
-    rf, rb = native.Resident(front, enc, device=local), native.Resident(back, enc, device=local)
-    torch.cuda.synchronize()
-    # ---- adaptorAlign: .align_AA_internal's four alignments with traceback + strand resolution
-    t0 = time.perf_counter()
-    res = {}
-    for key, r, a, sec in (("a", rf, A1, (s1, e1)), ("b", rb, A2, ((), ())), ("c", rb, A1, (s1, e1)), ("d", rf, A2, ((), ()))):
-        r.align(r.MODE_TRACE_LOCAL, 5, 1, a, *sec, stream=stream.cuda_stream)
-        res[key] = bufs[key] = r.fetch(stream=stream.cuda_stream, pinned=True, out=bufs.get(key))
-    torch.cuda.synchronize()
-    rev = api._resolve_strand(res["a"][0], res["b"][0], res["c"][0], res["d"][0])["reversed"]
-    if not warm:
-        t_align += time.perf_counter() - t0
-        real1.append(np.where(rev, res["c"][0], res["a"][0]))
-        real2.append(np.where(rev, res["d"][0], res["b"][0]))
-    # ---- getAdaptorThresholds: scramble on the device (keyed by global read index), four score-only alignments
-    t0 = time.perf_counter()
-    idx = np.arange(first, first + m, dtype=np.uint64)
-    sf, sb = rf.scrambled(0, read_index=idx, stream_id=0), rb.scrambled(0, read_index=idx, stream_id=1)
-    sc = {}
-    for key, r, a in (("S", sf, A1), ("E", sb, A2), ("RS", sb, A1), ("RE", sf, A2)):
-        r.align(r.MODE_SCORE_LOCAL, 5, 1, a, stream=stream.cuda_stream)
-        sc[key] = bufs[key] = r.fetch(stream=stream.cuda_stream, pinned=True, out=bufs.get(key))
-    torch.cuda.synchronize()
-    srev = api._resolve_strand(sc["S"], sc["E"], sc["RS"], sc["RE"])["reversed"]
-    if not warm:
-        t_thr += time.perf_counter() - t0
-        scr1.append(np.where(srev, sc["RS"], sc["S"]))
-        scr2.append(np.where(srev, sc["RE"], sc["E"]))
-    # ---- parity on a strided sample: the reference's own C++ on the same windows
-    if oracle is not None and not warm:
-        pick = np.arange(0, m, args.check_stride)
-        sub = front[pick]
-        exp = oracle.adaptor_align((sub.seq_pool, sub.seq_off), (sub.qual_pool, sub.qual_off), enc, 5, 1, A1, s1, e1, nthreads=os.cpu_count() or 1)
-        got = res["a"]
-        assert np.array_equal(got[0][pick], exp[0]) and np.array_equal(got[1][pick], exp[1]) and np.array_equal(got[2][pick], exp[2])
-        for k in range(2):
-            assert np.array_equal(got[3][k][pick], exp[3][k]) and np.array_equal(got[4][k][pick], exp[4][k])
-        checked += len(pick)
-    for r in (rf, rb, sf, sb):
-        r.close()
 
-real1, real2, scr1, scr2 = (np.concatenate(x) for x in (real1, real2, scr1, scr2))
-t0 = time.perf_counter()
-if world > 1:
-    def gather(x):
-        t = torch.from_numpy(x).cuda()
-        out = torch.empty(world * len(x), dtype=t.dtype, device="cuda") if rank == 0 else None
-        dist.gather(t, list(out.chunk(world)) if rank == 0 else None, dst=0)
-        return out.cpu().numpy() if rank == 0 else None
-    real1, real2, scr1, scr2 = gather(real1), gather(real2), gather(scr1), gather(scr2)
-    stats = torch.tensor([t_align, t_thr, t_gen], dtype=torch.float64, device="cuda")
-    dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    t_align, t_thr, t_gen = (float(x) for x in stats.cpu())
-if rank == 0:
-    thr1 = api._compute_threshold(real1, scr1, 0.01)
-    thr2 = api._compute_threshold(real2, scr2, 0.01)
-    t_sel = time.perf_counter() - t0
-    n = world * args.share
-    cells = n * 46000
-    sms = torch.cuda.get_device_properties(local).multi_processor_count
-    peak = sms * 64 * 1.965e9 / 10 / 1e9
-    print("configs[4] share: %d reads on %d GPU(s) (%d per GPU, batches of %d)" % (n, world, args.share, args.batch))
-    print("  adaptorAlign (4 alignments + traceback, resident windows, results fetched): %.3f s = %.2f M reads/s, %.0f GCUPS per GPU (%.1f %% of %.0f)"
-          % (t_align, n / t_align / 1e6, cells / t_align / 1e9 / world, 100 * cells / t_align / 1e9 / world / peak, peak))
-    print("  getAdaptorThresholds core (device scramble + 4 score-only alignments, scores fetched): %.3f s = %.2f M reads/s, %.0f GCUPS per GPU"
-          % (t_thr, n / t_thr / 1e6, cells / t_thr / 1e9 / world))
-    both = t_align + t_thr
-    print("  both: %.3f s, %.0f GCUPS per GPU = %.1f %% of the FP64 roofline; threshold selection on the host %.2f s -> adaptor1 %.4f, adaptor2 %.4f"
-          % (both, 2 * cells / both / 1e9 / world, 100 * 2 * cells / both / 1e9 / world / peak, t_sel, thr1, thr2))
-    print("  parity: %d strided alignments per rank identical to the %s oracle; synthetic read generation (not timed above) %.1f s"
-          % (checked, oracle.kind if oracle else "no", t_gen))
-if world > 1:
-    dist.destroy_process_group()
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--total", type=int, default=6250000)
+    ap.add_argument("--chunk", type=int, default=1136640)
+    ap.add_argument("--check-stride", type=int, default=0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rec = run(args.total, args.chunk, rank, world, local, args.check_stride)
+    if rank == 0:
+        sms = torch.cuda.get_device_properties(local).multi_processor_count
+        peak = sms * 64 * 1.965e9 / 10 / 1e9
+        rec["roofline_frac"] = rec["gcups_per_gpu"] / peak
+        print(json.dumps(rec))
+    if world > 1:
+        torch.distributed.destroy_process_group()
