@@ -86,6 +86,9 @@ int64_t sarlacc_kernel_launches(int reset);
 /* Device buffers released by the library are kept for reuse (SARLACC_POOL_MB, default 24576; 0 = off); this hands them
  * back to the driver. */
 void sarlacc_trim_device_memory(void);
+/* Host-side phases of the last sarlacc_adaptor_align_windows / _reads call (first device): staging and length scans,
+ * enqueueing, waiting for results + copy-out, total -- milliseconds.  For bench.py's per-rank breakdown. */
+void sarlacc_last_pair_timing(double* ms4);
 
 /* ---- the four reference entry points (host buffers in, host buffers out) ------------------------- */
 
@@ -235,6 +238,11 @@ int sarlacc_chunk_adaptor_align(sarlacc_chunk* c, double gapopen, double gapext,
 int sarlacc_chunk_scrambled_scores(sarlacc_chunk* c, double gapopen, double gapext, const char* adaptor1, const char* adaptor2,
         uint64_t seed, uint64_t first_index, const uint64_t* read_index, int scramble, double* score1, double* score2);
 int sarlacc_chunk_sync(sarlacc_chunk* c);
+/* The chunk's compute stream (a cudaStream_t as void*), and a join that makes it wait for everything enqueued so far on
+ * the chunk's traceback and copy streams: an event recorded on the stream after sarlacc_chunk_join marks the completion of
+ * all prior calls (how bench.py brackets its timed region with CUDA events). */
+void* sarlacc_chunk_stream(sarlacc_chunk* c);
+int   sarlacc_chunk_join(sarlacc_chunk* c);
 /* Tests / reports: packed rows (uint16[n][stride]) of window set `which` (0 front, 1 back, 2 scrambled front,
  * 3 scrambled back), window lengths, read widths, strand flips of the generator; any pointer may be NULL. */
 int sarlacc_chunk_rows(sarlacc_chunk* c, int which, uint16_t* rows, int32_t* lens, int* stride, int32_t* width, uint8_t* flipped);

@@ -123,6 +123,11 @@ def _load():
     lib.sarlacc_chunk_scrambled_scores.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_char_p, C.c_char_p,
                                                    C.c_uint64, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.sarlacc_chunk_sync.argtypes = [C.c_void_p]
+    lib.sarlacc_chunk_join.argtypes = [C.c_void_p]
+    lib.sarlacc_chunk_stream.restype = C.c_void_p
+    lib.sarlacc_chunk_stream.argtypes = [C.c_void_p]
+    lib.sarlacc_last_pair_timing.restype = None
+    lib.sarlacc_last_pair_timing.argtypes = [C.c_void_p]
     lib.sarlacc_chunk_rows.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
     lib.sarlacc_chunk_set_timing.restype = None
     lib.sarlacc_chunk_set_timing.argtypes = [C.c_void_p, C.c_int]

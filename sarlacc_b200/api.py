@@ -116,7 +116,7 @@ _QUAL_ENCODINGS = {
     # Biostrings::encoding(): offset character and score range of each quality class
     "PhredQuality": (33, 0, 93, "phred"),
     "IlluminaQuality": (64, 0, 62, "phred"),
-    "SolexaQuality": (59, -5, 62, "solexa"),
+    "SolexaQuality": (64, -5, 62, "solexa"),      # ';' (59) .. '~' (126): offset 64, scores -5..62
 }
 
 
@@ -217,7 +217,8 @@ def _align_AA_internal_fused(reads, adaptor1, adaptor2, tolerance, subseq1, subs
     library call (sarlacc_adaptor_align_reads).  Same return value, except that adaptor2's start/end are already in
     read coordinates (flagged by "flipped")."""
     enc = encoding or native.phred_encoding()
-    if len(adaptor1) == 0 or len(adaptor2) == 0 or len(reads) == 0:
+    if len(adaptor1) == 0 or len(adaptor2) == 0 or len(reads) == 0 or int(tolerance) < 1:
+        # degenerate inputs the reference accepts (tolerance 0: empty windows, the score is the row-0 chain) take its own route
         return _align_AA_internal(reads, adaptor1, adaptor2, tolerance, subseq1, subseq2, gap_opening, gap_extension, encoding)
     width, rev, r1, r2 = native.adaptor_align_reads(
         reads, tolerance, enc, gap_opening, gap_extension, adaptor1, adaptor2,
@@ -294,7 +295,7 @@ def _stream(source, number, keep=None):
         for lo in range(0, n, number):
             idx = np.arange(lo, min(n, lo + number))
             yield source[idx], None
-    elif keep is not None and not str(source).endswith(".gz"):
+    elif keep is not None and int(keep) >= 1 and not str(source).endswith(".gz"):
         yield from _prefetch(read_fastq_condensed(source, keep, number))
     else:
         for reads in read_fastq(source, number):

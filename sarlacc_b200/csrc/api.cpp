@@ -1756,6 +1756,11 @@ struct FinalLayout {
     size_t o_rev, o_score[2], o_start[2], o_end[2], o_ss[2], o_sw[2], total;
 };
 
+/* Host-side phases of the last fused both-ends call on this thread's job 0 (bench.py reports them per rank):
+ * staging / length scans, enqueueing, waiting for results + copying them out, total; milliseconds. */
+std::mutex g_pair_timing_mutex;
+double g_pair_timing[4] = {0, 0, 0, 0};
+
 struct PairJob {
     int device = 0;
     int64_t lo = 0, hi = 0, n_total = 0;
@@ -1976,6 +1981,13 @@ struct PairJob {
         for (int k = 0; k < kSlots; ++k) drain(slots[(which + k) % kSlots], lay[(which + k) % kSlots]);   /* oldest first */
         t_drain += now() - t0;
         if (dbg) std::fprintf(stderr, "[sarlacc] pair job dev %d: pack %.1f ms, enqueue %.1f ms, wait+copy-out %.1f ms\n", device, t_pack * 1e3, t_enq * 1e3, t_drain * 1e3);
+        {
+            std::lock_guard<std::mutex> lock(g_pair_timing_mutex);
+            g_pair_timing[0] = t_pack * 1e3;
+            g_pair_timing[1] = t_enq * 1e3;
+            g_pair_timing[2] = t_drain * 1e3;
+            g_pair_timing[3] = (now() - t_start) * 1e3;
+        }
     }
 };
 
@@ -2018,6 +2030,12 @@ int sarlacc_set_host_threads(int nthreads) {
 }
 
 void sarlacc_trim_device_memory(void) { DevPool::instance().trim(); }
+
+void sarlacc_last_pair_timing(double* ms4) {
+    if (!ms4) return;
+    std::lock_guard<std::mutex> lock(g_pair_timing_mutex);
+    for (int k = 0; k < 4; ++k) ms4[k] = g_pair_timing[k];
+}
 
 int64_t sarlacc_kernel_launches(int reset) {
     const long long v = g_launches.load();
@@ -3493,6 +3511,25 @@ int sarlacc_chunk_scrambled_scores(sarlacc_chunk* c, double gapopen, double gape
     }
     return 0;
 }
+
+/* Makes the chunk's compute stream wait for everything enqueued so far on its traceback and copy streams, so that an
+ * event recorded on sarlacc_chunk_stream() afterwards marks the completion of all of it (bench.py times steps with CUDA
+ * events on that stream). */
+int sarlacc_chunk_join(sarlacc_chunk* c) {
+    if (!c) return fail("chunk handle is NULL");
+    try {
+        CUDA_CHECK(cudaSetDevice(c->device));
+        CUDA_CHECK(cudaEventRecord(c->out_ready, c->tb));
+        CUDA_CHECK(cudaStreamWaitEvent(c->st, c->out_ready, 0));
+        CUDA_CHECK(cudaEventRecord(c->out_ready, c->cp));
+        CUDA_CHECK(cudaStreamWaitEvent(c->st, c->out_ready, 0));
+    } catch (CudaError& e) {
+        return fail(e.msg);
+    }
+    return 0;
+}
+
+void* sarlacc_chunk_stream(sarlacc_chunk* c) { return c ? (void*)c->st : nullptr; }
 
 int sarlacc_chunk_sync(sarlacc_chunk* c) {
     if (!c) return fail("chunk handle is NULL");

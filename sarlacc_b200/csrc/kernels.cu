@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
 
     /* One DP row of this lane's C columns.  `live` gates the only side effect (the trace store). */
     auto row_step = [&](double Sl, double El, bool live) {
-        fill_cost_table(mytab, qrec, *rowp, kinds);
+        fill_cost_table(mytab, qrec, live ? *rowp : 0u, kinds);   /* idle lanes (start-up, finished) take entry 0, not whatever their row pointer last saw */
         {   /* column 0 feeds the first lane: src/reference_align.cpp:64-78 (0 in local mode; uniform branch otherwise) */
             const double c0v = __dsub_rn(c0base, __dmul_rn(c0step, (double)(i - 1)));   /* H[i][0], i >= 1 */
             Sl = first_lane ? c0v : Sl;
@@ -454,6 +454,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
     /* SOLO: one thread owns one alignment and all C = L columns (G = 1): no shuffles, no first-lane or dummy-slot
      * selects, column 0 is a constant boundary -- the geometry for 20-24 bp references (adaptor2, barcodes). */
     using WT = typename FlagWord<C>::type;
+    static_assert(kSkew == 2, "the row-pair kernel lags its left neighbour by one two-row step: record layout and traceback assume SARLACC_WF_SKEW == 2");
     extern __shared__ double smem_d[];
     const int L = A.L, nref = A.nref, encn = A.enc_n;
     double* row0s = smem_d;                                   /* [L+1]                         */

@@ -164,10 +164,12 @@ def barcode_align_multi(reads, encoding, gapopen, gapext, barcodes, all_scores=F
 
 
 def adaptor_align_windows(front, back, encoding, gapopen, gapext, adaptor1, adaptor2, sec1=((), ()), sec2=((), ()),
-                          read_width=None, views=False, seq_encoding=SEQ_ASCII):
+                          read_width=None, views=False, seq_encoding=SEQ_ASCII, reuse=None):
     """Fused .align_AA_internal (+ adaptor2 flip when read_width is given), see sarlacc_adaptor_align_windows.
     sec1/sec2 = (0-based starts, 1-based ends).  Returns reversed (bool) and two result lists shaped like
-    adaptor_align's: [score, start, end, [sec_start...], [sec_width...]]."""
+    adaptor_align's: [score, start, end, [sec_start...], [sec_width...]].  reuse: a dict the caller keeps between calls
+    of the same shape -- the output arrays live in it and are overwritten by the next call (no fresh 49 MB of
+    first-touched pages per million reads)."""
     a1 = _string(adaptor1, "adaptor sequence")
     a2 = _string(adaptor2, "adaptor sequence")
     go = _numeric_scalar(gapopen, "gap opening penalty")
@@ -186,11 +188,17 @@ def adaptor_align_windows(front, back, encoding, gapopen, gapext, adaptor1, adap
             raise SarlaccError("section starts and ends should have the same length")
         secs.append((ss, se))
     width = None if read_width is None else np.ascontiguousarray(read_width, dtype=np.int32)
-    rev = np.empty(max(n, 1), np.uint8)      # every element is written by the call (n > 0) -- no zero fill, no copies below
-    outs = []
-    for ss, se in secs:
-        outs.append([np.empty(n, np.float64), np.empty(n, np.int32), np.empty(n, np.int32),
-                     np.empty((max(len(ss), 1), max(n, 1)), np.int32), np.empty((max(len(ss), 1), max(n, 1)), np.int32)])
+    key = (n, len(secs[0][0]), len(secs[1][0]))
+    if reuse is not None and reuse.get("key") == key:
+        rev, outs = reuse["rev"], reuse["outs"]
+    else:
+        rev = np.empty(max(n, 1), np.uint8)      # every element is written by the call (n > 0) -- no zero fill, no copies below
+        outs = []
+        for ss, se in secs:
+            outs.append([np.empty(n, np.float64), np.empty(n, np.int32), np.empty(n, np.int32),
+                         np.empty((max(len(ss), 1), max(n, 1)), np.int32), np.empty((max(len(ss), 1), max(n, 1)), np.int32)])
+        if reuse is not None:
+            reuse.update(key=key, rev=rev, outs=outs)
     _lib.check(_lib.lib.sarlacc_adaptor_align_windows(
         rf.ref(), rb.ref(), ea.ref(), C.c_double(go), C.c_double(ge), a1.encode("latin-1"), a2.encode("latin-1"),
         C.c_int(len(secs[0][0])), _lib._ptr(secs[0][0]), _lib._ptr(secs[0][1]),
@@ -543,6 +551,14 @@ class Chunk:
     def sync(self):
         _lib.check(_lib.lib.sarlacc_chunk_sync(self.handle))
 
+    def join(self):
+        """Compute stream waits for the traceback and copy streams (see sarlacc_chunk_join)."""
+        _lib.check(_lib.lib.sarlacc_chunk_join(self.handle))
+
+    def stream(self):
+        """The compute stream's handle (for torch.cuda.ExternalStream)."""
+        return int(_lib.lib.sarlacc_chunk_stream(self.handle) or 0)
+
     def rows(self, which=0):
         """(packed rows uint16[n][stride], window lengths, read widths, strand flips) of window set `which`
         (0 front, 1 back, 2 scrambled front, 3 scrambled back)."""
@@ -567,6 +583,13 @@ class Chunk:
 
     def last_kernel(self, adaptor=0):
         return _lib.lib.sarlacc_chunk_last_kernel(self.handle, C.c_int(adaptor)).decode()
+
+
+def last_pair_timing():
+    """Host-side phases (ms) of the last fused both-ends host-buffer call: staging, enqueue, wait + copy-out, total."""
+    ms = np.zeros(4, np.float64)
+    _lib.lib.sarlacc_last_pair_timing(_lib._ptr(ms))
+    return dict(zip(("stage", "enqueue", "wait_copy_out", "total"), ms.tolist()))
 
 
 def compute_threshold(real, scrambled, error, device=0):

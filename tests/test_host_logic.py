@@ -173,6 +173,18 @@ def test_encoding_vector():
     assert names[0] == "!" and names[-1] == "~" and len(names) == 94
     assert err[20] == 10.0 ** -2.0 and np.all(np.diff(err) <= 0)
     assert api._qual2class("phred") == "PhredQuality" and api._qual2class("solexa") == "SolexaQuality"
+    # Biostrings::encoding(): Illumina '@' (64) .. '~' for Q 0..62; Solexa ';' (59) .. '~' for scores -5..62, error
+    # probability 1 / (1 + 10^(q / 10))
+    names, err = api._create_encoding_vector("IlluminaQuality")
+    assert names[0] == "@" and names[-1] == "~" and len(names) == 63 and err[0] == 1.0 and err[30] == 10.0 ** -3.0
+    names, err = api._create_encoding_vector("SolexaQuality")
+    assert names[0] == ";" and names[5] == "@" and names[-1] == "~" and len(names) == 68
+    assert abs(err[0] - 1.0 / (1.0 + 10.0 ** -0.5)) < 1e-15 and err[5] == 0.5 and abs(err[25] - 1.0 / 101.0) < 1e-15
+    assert np.all(np.diff(err) < 0)
+    # every table passes the reference's encoding checks (consecutive one-character names, non-increasing errors)
+    for cls in ("PhredQuality", "IlluminaQuality", "SolexaQuality"):
+        n, e = api._create_encoding_vector(cls)
+        assert [ord(b) - ord(a) for a, b in zip(n, n[1:])] == [1] * (len(n) - 1) and np.all(np.diff(e) <= 0)
 
 
 def _pack(rs_args, enc, tolerance, back, stride, force_scalar, seq_encoding=0):
