@@ -1214,23 +1214,39 @@ __global__ void __launch_bounds__(128) scramble_rows_fy_global(const uint16_t* i
  * swaps the two windows.  Every draw is stream_word(stream_key(seed, read index, field), position): the read depends on
  * (seed, index) only -- sarlacc_b200/synth.py: mock_windows is the numpy mirror, bit for bit.
  * Fields: 0/4 molecule fill (front/back molecule), 1/5 mutation, 2/6 count choice, 3/7 quality, 8 flip, 9 width. */
-__device__ __forceinline__ unsigned mock_quality(uint32_t h, const MockArgs& M) {
-    unsigned q = M.qmin;
-    while (q < 93u && h < M.qthr[q + 1]) ++q;      /* P(Q >= k) falls by 10^-0.1 per step: ~4 iterations on average */
-    return q;
+/* quality >= k  <=>  word < thr[k] with thr non-increasing in k: the quality is the number of k in 1..93 whose threshold
+ * exceeds the word, found by a fixed-depth binary search (every lane takes the same seven steps). */
+__device__ __forceinline__ unsigned mock_quality(uint32_t h, const uint32_t* thr) {
+    unsigned lo = 0, hi = 94;            /* invariant: h < thr[lo] (thr[0] = 2^32 - 1 stands for 2^32), !(h < thr[hi]) (thr[94] = 0) */
+#pragma unroll
+    for (int s = 0; s < 7; ++s) {
+        const unsigned mid = (lo + hi) >> 1;
+        const bool below = mid > lo && h < thr[mid];
+        lo = below ? mid : lo;
+        hi = below ? hi : (mid > lo ? mid : hi);
+    }
+    return lo;
 }
 
+/* Threads [0, n) build the adaptor1 molecule's window of read t, threads [n, 2n) the adaptor2 molecule's: a warp works on
+ * one molecule (uniform adaptor reads), the quality thresholds sit in shared memory (per-lane indices). */
 __global__ void __launch_bounds__(128) mock_windows_kernel(const __grid_constant__ MockArgs M)
 {
+    __shared__ uint32_t sthr[96];
+    __shared__ char sad[2][128];
+    for (int x = threadIdx.x; x < 95; x += blockDim.x) sthr[x] = M.qthr[x];
+    for (int x = threadIdx.x; x < 128; x += blockDim.x) { sad[0][x] = M.adaptor1[x]; sad[1][x] = M.adaptor2[x]; }
+    __syncthreads();
+    const long long npad = (M.n + 127) / 128 * 128;            /* molecule 1 starts at a block boundary */
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 2 * M.n) return;
-    const long long r = t >> 1;
-    const int mol = (int)(t & 1);                           /* 0: adaptor1 molecule, 1: adaptor2 molecule */
+    const int mol = t >= npad ? 1 : 0;                          /* 0: adaptor1 molecule, 1: adaptor2 molecule */
+    const long long r = mol ? t - npad : t;
+    if (r >= M.n) return;
     const unsigned long long rid = M.first_index + (unsigned long long)r;
     const bool flip = (stream_word(stream_key(M.seed, rid, 8u), 0u) >> 31) != 0u;
     const bool to_front = (mol == 0) != flip;
     uint16_t* row = (to_front ? M.front : M.back) + r * (long long)M.stride;
-    const char* ad = mol == 0 ? M.adaptor1 : M.adaptor2;
+    const char* ad = sad[mol];
     const int alen = mol == 0 ? M.len1 : M.len2;
     const int run0 = mol == 0 ? M.run0_start : -1, run1 = mol == 0 ? M.run0_end : -1;
     const uint32_t kfill = stream_key(M.seed, rid, 0u + 4u * mol), kmut = stream_key(M.seed, rid, 1u + 4u * mol);
@@ -1253,7 +1269,7 @@ __global__ void __launch_bounds__(128) mock_windows_kernel(const __grid_constant
             copies = k == 0 ? 0 : (int)k + 1;
         }
         for (int x = 0; x < copies && emitted < M.tol; ++x) {
-            const unsigned q = mock_quality(stream_word(kq, (uint32_t)emitted), M);
+            const unsigned q = mock_quality(stream_word(kq, (uint32_t)emitted), sthr);
             const uint32_t entry = ((1u << b) << 8) | q;
             acc[(emitted & 7) >> 1] |= entry << (16 * (emitted & 1));
             ++emitted;
@@ -1271,22 +1287,33 @@ __global__ void __launch_bounds__(128) mock_windows_kernel(const __grid_constant
     if (mol == 0) {
         M.lens_front[r] = M.tol;
         M.lens_back[r] = M.tol;
-        /* read width = mutated length of adaptor1 + insert + adaptor2: every base independently an indel w.p. indel_rate,
-         * changing the length by -1 or +1..max_insert-1; four bases per stream word (16-bit fields) */
-        const uint32_t kw = stream_key(M.seed, rid, 9u);
-        int width = M.molecule_len;
-        for (int p4 = 0; p4 * 4 < M.molecule_len; ++p4) {
+        if (M.flipped) M.flipped[r] = flip ? 1 : 0;
+    }
+}
+
+/* Read width = mutated length of adaptor1 + insert + adaptor2: every base independently an indel w.p. indel_rate, changing
+ * the length by -1 or +1..max_insert-1; four bases per pair of stream words (16-bit fields).  One warp per read, its
+ * lanes striding over the molecule. */
+__global__ void __launch_bounds__(256) mock_widths_kernel(const __grid_constant__ MockArgs M)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < M.n; r += warps) {
+        const uint32_t kw = stream_key(M.seed, M.first_index + (unsigned long long)r, 9u);
+        int delta = 0;
+        for (int p4 = lane; p4 * 4 < M.molecule_len; p4 += 32) {
             const uint32_t lo = stream_word(kw, 2u * p4), hi = stream_word(kw, 2u * p4 + 1u);
             const uint32_t f[4] = {lo & 0xFFFFu, lo >> 16, hi & 0xFFFFu, hi >> 16};
-            for (int x = 0; x < 4 && p4 * 4 + x < M.molecule_len; ++x) {
-                if (f[x] < M.indel_thr) {
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                if (p4 * 4 + x < M.molecule_len && f[x] < M.indel_thr) {
                     const uint32_t k = stream_word(kw, 0x80000000u + (uint32_t)(p4 * 4 + x)) % (uint32_t)M.max_insert;
-                    width += k == 0 ? -1 : (int)k;
+                    delta += k == 0 ? -1 : (int)k;
                 }
             }
         }
-        M.width[r] = width;
-        if (M.flipped) M.flipped[r] = flip ? 1 : 0;
+        delta = __reduce_add_sync(FULL, delta);
+        if (lane == 0) M.width[r] = M.molecule_len + delta;
     }
 }
 
@@ -1477,7 +1504,14 @@ void launch_resolve_strand(const StrandArgs& s, cudaStream_t st) {
 void launch_mock_windows(const MockArgs& m, cudaStream_t st) {
     if (m.n <= 0) return;
     const int block = 128;
-    mock_windows_kernel<<<(int)((2 * m.n + block - 1) / block), block, 0, st>>>(m);
+    const long long npad = (m.n + block - 1) / block * block;
+    mock_windows_kernel<<<(int)(2 * npad / block), block, 0, st>>>(m);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long grid = (m.n + 7) / 8;
+    if (grid > (long long)sms * 8) grid = (long long)sms * 8;
+    mock_widths_kernel<<<(int)grid, 256, 0, st>>>(m);
 }
 
 void launch_pack_rows(const PackArgs& a, cudaStream_t st) {

@@ -15,6 +15,9 @@
 
 #include <cub/device/device_radix_sort.cuh>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <limits>
 #include <string>
 
@@ -79,6 +82,9 @@ extern "C" int sarlacc_compute_threshold(const double* real, int64_t nreal, cons
         if (e_ != cudaSuccess) return sarlacc::set_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #expr); \
     } while (0)
     TH_CHECK(cudaSetDevice(device));
+    const bool dbg = std::getenv("SARLACC_DEBUG_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     Tmp r_in, r_out, s_in, s_out, work, first;
     const size_t rb = sizeof(double) * (size_t)nreal, sb = sizeof(double) * (size_t)nscr;
     TH_CHECK(r_in.alloc(rb));
@@ -109,6 +115,8 @@ extern "C" int sarlacc_compute_threshold(const double* real, int64_t nreal, cons
     unsigned long long k = none;
     TH_CHECK(cudaMemcpy(&k, first.p, sizeof(k), cudaMemcpyDeviceToHost));
     if (k != none) TH_CHECK(cudaMemcpy(threshold, (const double*)r_out.p + k, sizeof(double), cudaMemcpyDeviceToHost));
+    if (dbg) std::fprintf(stderr, "[sarlacc] compute_threshold: %lld real, %lld scrambled scores, %.2f ms (first index %lld)\n",
+                          (long long)nreal, (long long)nscr, (now() - t0) * 1e3, k == none ? -1LL : (long long)k);
 #undef TH_CHECK
     return 0;
 }

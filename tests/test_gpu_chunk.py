@@ -64,8 +64,8 @@ def test_generated_reads_look_like_mockreads(enc):
     f = front.seq_pool.reshape(20000, 250)
     want = np.frombuffer(("ACGT" * 30).encode(), np.uint8)
     unflipped = ~flips
-    mism = (f[unflipped, :20] != want[None, :20]).mean()          # the first 20 bases: few indels upstream
-    assert 0.02 < mism < 0.09
+    mism = (f[unflipped, :4] != want[None, :4]).mean()            # the first bases: hardly any indel upstream yet
+    assert 0.025 < mism < 0.07
     q = front.qual_pool.astype(int) - 33
     assert q.min() == 12 and q.max() <= 93
     tail = [(q >= k).mean() for k in (13, 23, 33)]
