@@ -1216,7 +1216,7 @@ __global__ void __launch_bounds__(128) scramble_rows_fy_global(const uint16_t* i
  * Fields: 0/4 molecule fill (front/back molecule), 1/5 mutation, 2/6 count choice, 3/7 quality, 8 flip, 9 width. */
 /* quality >= k  <=>  word < thr[k] with thr non-increasing in k: the quality is the number of k in 1..93 whose threshold
  * exceeds the word, found by a fixed-depth binary search (every lane takes the same seven steps). */
-__device__ __forceinline__ unsigned mock_quality(uint32_t h, const uint32_t* thr) {
+__device__ __forceinline__ unsigned mock_quality(uint32_t h, const uint32_t* thr, unsigned qmin) {
     unsigned lo = 0, hi = 94;            /* invariant: h < thr[lo] (thr[0] = 2^32 - 1 stands for 2^32), !(h < thr[hi]) (thr[94] = 0) */
 #pragma unroll
     for (int s = 0; s < 7; ++s) {
@@ -1225,7 +1225,7 @@ __device__ __forceinline__ unsigned mock_quality(uint32_t h, const uint32_t* thr
         lo = below ? mid : lo;
         hi = below ? hi : (mid > lo ? mid : hi);
     }
-    return lo;
+    return lo < qmin ? qmin : lo;        /* word 2^32 - 1 fails the saturated thresholds below qmin */
 }
 
 /* Threads [0, n) build the adaptor1 molecule's window of read t, threads [n, 2n) the adaptor2 molecule's: a warp works on
@@ -1269,7 +1269,7 @@ __global__ void __launch_bounds__(128) mock_windows_kernel(const __grid_constant
             copies = k == 0 ? 0 : (int)k + 1;
         }
         for (int x = 0; x < copies && emitted < M.tol; ++x) {
-            const unsigned q = mock_quality(stream_word(kq, (uint32_t)emitted), sthr);
+            const unsigned q = mock_quality(stream_word(kq, (uint32_t)emitted), sthr, M.qmin);
             const uint32_t entry = ((1u << b) << 8) | q;
             acc[(emitted & 7) >> 1] |= entry << (16 * (emitted & 1));
             ++emitted;

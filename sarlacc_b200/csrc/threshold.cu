@@ -93,6 +93,7 @@ extern "C" int sarlacc_compute_threshold(const double* real, int64_t nreal, cons
     TH_CHECK(s_out.alloc(sb));
     TH_CHECK(first.alloc(sizeof(unsigned long long)));
     /* cudaMemcpyDefault: the vectors may live on the host or on a device (e.g. gathered from all ranks) */
+    const double t1 = now();
     TH_CHECK(cudaMemcpy(r_in.p, real, rb, cudaMemcpyDefault));
     if (nscr > 0) TH_CHECK(cudaMemcpy(s_in.p, scrambled, sb, cudaMemcpyDefault));
     size_t wbytes = 0, wbytes2 = 0;
@@ -102,6 +103,8 @@ extern "C" int sarlacc_compute_threshold(const double* real, int64_t nreal, cons
     TH_CHECK(work.alloc(wbytes));
     TH_CHECK(cub::DeviceRadixSort::SortKeys(work.p, wbytes, (const double*)r_in.p, (double*)r_out.p, (long long)nreal));
     if (nscr > 0) TH_CHECK(cub::DeviceRadixSort::SortKeys(work.p, wbytes, (const double*)s_in.p, (double*)s_out.p, (long long)nscr));
+    if (dbg) cudaDeviceSynchronize();
+    const double t2 = now();
     const unsigned long long none = ~0ULL;
     TH_CHECK(cudaMemcpy(first.p, &none, sizeof(none), cudaMemcpyHostToDevice));
     int sms = 148;
@@ -115,8 +118,8 @@ extern "C" int sarlacc_compute_threshold(const double* real, int64_t nreal, cons
     unsigned long long k = none;
     TH_CHECK(cudaMemcpy(&k, first.p, sizeof(k), cudaMemcpyDeviceToHost));
     if (k != none) TH_CHECK(cudaMemcpy(threshold, (const double*)r_out.p + k, sizeof(double), cudaMemcpyDeviceToHost));
-    if (dbg) std::fprintf(stderr, "[sarlacc] compute_threshold: %lld real, %lld scrambled scores, %.2f ms (first index %lld)\n",
-                          (long long)nreal, (long long)nscr, (now() - t0) * 1e3, k == none ? -1LL : (long long)k);
+    if (dbg) std::fprintf(stderr, "[sarlacc] compute_threshold: %lld real, %lld scrambled scores: alloc %.2f ms, copy + sorts %.2f ms, scan %.2f ms (first index %lld)\n",
+                          (long long)nreal, (long long)nscr, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (now() - t2) * 1e3, k == none ? -1LL : (long long)k);
 #undef TH_CHECK
     return 0;
 }

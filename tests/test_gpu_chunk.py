@@ -70,7 +70,7 @@ def test_generated_reads_look_like_mockreads(enc):
     assert q.min() == 12 and q.max() <= 93
     tail = [(q >= k).mean() for k in (13, 23, 33)]
     assert abs(tail[1] / tail[0] - 0.1) < 0.02 and abs(tail[2] / tail[1] - 0.1) < 0.03
-    assert abs(widths.mean() - (120 + 1000 + 32) * (1 + 0.01 * 0.8)) < 3
+    assert abs(widths.mean() - (120 + 1000 + 32) * (1 + 0.01 * 1.8)) < 2       # an indel changes the length by (-1+1+2+3+4)/5 on average
 
 
 def compose(oracle, enc, front, back, widths, go, ge, a1, a2, sec1, sec2):

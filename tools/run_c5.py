@@ -78,9 +78,11 @@ def run(total, chunk, rank, world, local, check_stride=0, error=0.01, timing=Tru
             vecs = [p[keep] for p in parts]
     else:
         vecs = [real1[:n], real2[:n], scr1[:n], scr2[:n]]
+    t_gather = time.perf_counter() - t0 - t_align
     if rank == 0:
         thr = (native.compute_threshold((vecs[0].data_ptr(), total), (vecs[2].data_ptr(), total), error, device=local),
                native.compute_threshold((vecs[1].data_ptr(), total), (vecs[3].data_ptr(), total), error, device=local))
+    t_thr = time.perf_counter() - t0 - t_align - t_gather
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -91,7 +93,7 @@ def run(total, chunk, rank, world, local, check_stride=0, error=0.01, timing=Tru
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_all, t_align = float(tt[0]), float(tt[1])
-    rec = {"reads": total, "n_gpus": world, "reads_per_gpu": share, "chunk": chunk, "seconds": t_all, "seconds_alignment_passes": t_align,
+    rec = {"reads": total, "n_gpus": world, "reads_per_gpu": share, "chunk": chunk, "seconds": t_all, "seconds_alignment_passes": t_align, "seconds_gather_rank0": t_gather, "seconds_thresholds_rank0": t_thr,
            "reads_per_s": total / t_all, "cells_per_read": 92000, "gcups_per_gpu": total * 92000 / t_all / 1e9 / world,
            "phases_ms_rank0": phases, "gpu_launches_rank0": launches, "kernels": [ch.last_kernel(0), ch.last_kernel(1)],
            "d2h_bytes_per_read": 1 + 4 + 4 * 4 + 16, "thresholds": thr}
