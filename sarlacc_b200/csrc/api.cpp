@@ -3227,6 +3227,27 @@ int sarlacc_chunk_load_mock(sarlacc_chunk* c, int64_t n, uint64_t first_index, u
             M.qthr[k] = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
             if (k <= 93 && t >= 4294967296.0) M.qmin = (uint32_t)k;
         }
+        {   /* number of indels over the whole molecule: Binomial(molecule_len, p) with p = indel_thr / 65536, as an integer
+             * distribution function around its mean.  Only IEEE multiplications, divisions and additions in a fixed order
+             * (built with -ffp-contract=off), so that sarlacc_b200/synth.py: width_table gets the same integers. */
+            const int nmol = M.molecule_len;
+            const double pr = (double)M.indel_thr / 65536.0, qr = 1.0 - pr;
+            const int mean = (int)((double)nmol * pr);
+            M.wlo = std::max(0, mean - 128);
+            double x = 1.0;
+            for (int i = 0; i < nmol; ++i) x *= qr;              /* P(0 indels) */
+            double cdf = 0.0;
+            for (int k = 0; k < M.wlo + 256; ++k) {
+                cdf += x;
+                if (k >= M.wlo) {
+                    const double t = std::floor(cdf * 4294967296.0);
+                    M.wcdf[k - M.wlo] = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+                }
+                const double t1 = (double)(nmol - k) * pr, t2 = (double)(k + 1) * qr;
+                x = x * t1;
+                x = x / t2;
+            }
+        }
         chunk_wait_tracebacks(c, c->st);      /* tracebacks of the previous contents still read the window lengths */
         chunk_mark(c, 0, true);
         launch_mock_windows(M, c->st);

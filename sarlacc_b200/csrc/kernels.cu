@@ -174,39 +174,45 @@ constexpr int kCostEntries = 7;   /* A, C, G, T, two-fold code, three-fold code,
 template <int C>
 struct SoloJit { static constexpr bool value = C >= 20 && C <= 24 && ((SARLACC_SOLO_JIT_MASK >> (C - 20)) & 1) != 0; };
 
-/* Element x = q * 4 + part of the per-quality cost records in shared memory: part 0 = {match1[q], mismatch1[q]},
- * 1 = {mismatch2[q], match3[q]} (two-fold / three-fold codes), 2 = {match4[q], 0} (N), 3 unused -- 64 bytes per quality
- * index, so a row's costs are one LDS.128 (+ one or two more if the reference has IUPAC codes).  Lanes whose rows have
- * the same quality read the same address (a broadcast, no bank conflict): records indexed by (quality, observed base)
- * cost 2-4 shared-memory wavefronts more per load, which the row loop cannot afford -- at 12 resident warps per SM it
- * already spends 2 wavefronts per DP cell-row on the per-cell cost loads (profiles/r02_history.md).  cost = AlignArgs::cost. */
-__device__ __forceinline__ double2 q_record(const double* cost, int encn, int x) {
-    const int q = x >> 2, part = x & 3;
-    if (part == 0) return make_double2(cost[q], cost[encn + q]);
-    if (part == 1) return make_double2(cost[2 * encn + q], cost[3 * encn + q]);
-    if (part == 2) return make_double2(cost[4 * encn + q], 0.0);
-    return make_double2(0.0, 0.0);
+/* Per-quality cost tables in shared memory: mx[q] = {match1[q], mismatch1[q]} (ACGT reference columns), iu[q] =
+ * {mismatch2[q], match3[q]} (two-fold / three-fold codes), nq[q] = match4[q] (N) -- one LDS.128 per row, plus one or two
+ * more loads if the reference has IUPAC codes.  Lanes whose rows have the same quality read the same address (a
+ * broadcast); different qualities spread over 8 (16-byte entries) / 16 (8-byte entries) bank groups.  A single 64-byte
+ * record per quality put every load of a warp on two bank groups: 23 % of the kernel's shared-memory wavefronts were
+ * conflict replays (profiles/r02_ncu_summary.txt), and at 12 resident warps per SM the row loop already keeps the
+ * shared-memory pipe 55 % busy with the per-cell cost loads.  cost = AlignArgs::cost, [5][encn]. */
+struct QTables {
+    const double2* mx;
+    const double2* iu;
+    const double* nq;
+};
+
+__device__ __forceinline__ void fill_q_tables(double2* mx, double2* iu, double* nq, const double* cost, int encn) {
+    for (int q = threadIdx.x; q < encn; q += blockDim.x) {
+        mx[q] = make_double2(cost[q], cost[encn + q]);
+        iu[q] = make_double2(cost[2 * encn + q], cost[3 * encn + q]);
+        nq[q] = cost[4 * encn + q];
+    }
 }
 
 /* The lane's private table of one row's possible costs (entry e at tab[e * 32]): reference A,C,G,T -> mismatch1[q],
  * except the observed base's own entry -> match1[q] (src/reference_align.cpp:186-187); two-fold / three-fold codes and N
  * -> mismatch2 / match3 / match4 [q] whatever was observed (:188-209).  rw = quality index | one-hot base << 8. */
-__device__ __forceinline__ void fill_cost_table(double* tab, const double2* qrec, unsigned rw, int kinds) {
+__device__ __forceinline__ void fill_cost_table(double* tab, const QTables& Q, unsigned rw, int kinds) {
     const unsigned q = rw & 0xffu;
     const int o = __ffs(rw >> 8);                   /* one-hot A=1,C=2,G=4,T=8 -> 1..4; 0 for anything else */
-    const double2* rec = qrec + q * 4;
-    const double2 mx = rec[0];
+    const double2 mx = Q.mx[q];
     tab[0 * 32] = mx.y;
     tab[1 * 32] = mx.y;
     tab[2 * 32] = mx.y;
     tab[3 * 32] = mx.y;
     if (o) tab[(o - 1) * 32] = mx.x;
     if (kinds & 6) {
-        const double2 iu = rec[1];
+        const double2 iu = Q.iu[q];
         tab[4 * 32] = iu.x;
         tab[5 * 32] = iu.y;
     }
-    if (kinds & 8) tab[6 * 32] = rec[2].x;
+    if (kinds & 8) tab[6 * 32] = Q.nq[q];
 }
 
 template <int C, bool TRACE>
@@ -217,8 +223,11 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
     const int L = A.L, nref = A.nref, encn = A.enc_n;
     double* row0s = smem_d;                                   /* [L+1]                         */
     double* lanetab = row0s + (L + 1);                        /* [warps][kCostEntries][32] lane-private cost entries */
-    double2* qrec = reinterpret_cast<double2*>(smem_d + (((size_t)(L + 1) + (kBlock / 32) * kCostEntries * 32 + 1) & ~(size_t)1));   /* [encn][4], see q_record */
-    uint8_t* refm = reinterpret_cast<uint8_t*>(qrec + (size_t)encn * 4);   /* [nref][L] */
+    double2* qmx = reinterpret_cast<double2*>(smem_d + (((size_t)(L + 1) + (kBlock / 32) * kCostEntries * 32 + 1) & ~(size_t)1));   /* see QTables */
+    double2* qiu = qmx + encn;
+    double* qn = reinterpret_cast<double*>(qiu + encn);
+    const QTables Q{qmx, qiu, qn};
+    uint8_t* refm = reinterpret_cast<uint8_t*>(qn + encn);   /* [nref][L] */
     uint8_t* refk = refm + (size_t)nref * L;                                                    /* [nref][L] */
 
     for (int x = threadIdx.x; x <= L; x += blockDim.x) row0s[x] = A.row0[x];
@@ -226,7 +235,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
         refm[x] = A.refmask[x];
         refk[x] = A.refkind[x];
     }
-    for (int x = threadIdx.x; x < encn * 4; x += blockDim.x) qrec[x] = q_record(A.cost, encn, x);
+    fill_q_tables(qmx, qiu, qn, A.cost, encn);
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
@@ -291,7 +300,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
 
     /* One DP row of this lane's C columns.  `live` gates the only side effect (the trace store). */
     auto row_step = [&](double Sl, double El, bool live) {
-        fill_cost_table(mytab, qrec, live ? *rowp : 0u, kinds);   /* idle lanes (start-up, finished) take entry 0, not whatever their row pointer last saw */
+        fill_cost_table(mytab, Q, live ? *rowp : 0u, kinds);   /* idle lanes (start-up, finished) take entry 0, not whatever their row pointer last saw */
         {   /* column 0 feeds the first lane: src/reference_align.cpp:64-78 (0 in local mode; uniform branch otherwise) */
             const double c0v = __dsub_rn(c0base, __dmul_rn(c0step, (double)(i - 1)));   /* H[i][0], i >= 1 */
             Sl = first_lane ? c0v : Sl;
@@ -459,8 +468,11 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
     const int L = A.L, nref = A.nref, encn = A.enc_n;
     double* row0s = smem_d;                                   /* [L+1]                         */
     double* lanetab = row0s + (L + 1);                        /* [warps][2 rows][kCostEntries][32] lane-private cost entries */
-    double2* qrec = reinterpret_cast<double2*>(smem_d + (((size_t)(L + 1) + (kBlock / 32) * 2 * kCostEntries * 32 + 1) & ~(size_t)1));   /* [encn][4], see q_record */
-    uint8_t* refm = reinterpret_cast<uint8_t*>(qrec + (size_t)encn * 4);   /* [nref][L] */
+    double2* qmx = reinterpret_cast<double2*>(smem_d + (((size_t)(L + 1) + (kBlock / 32) * 2 * kCostEntries * 32 + 1) & ~(size_t)1));   /* see QTables */
+    double2* qiu = qmx + encn;
+    double* qn = reinterpret_cast<double*>(qiu + encn);
+    const QTables Q{qmx, qiu, qn};
+    uint8_t* refm = reinterpret_cast<uint8_t*>(qn + encn);   /* [nref][L] */
     uint8_t* refk = refm + (size_t)nref * L;                                   /* [nref][L] */
 
     for (int x = threadIdx.x; x <= L; x += blockDim.x) row0s[x] = A.row0[x];
@@ -468,7 +480,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
         refm[x] = A.refmask[x];
         refk[x] = A.refkind[x];
     }
-    for (int x = threadIdx.x; x < encn * 4; x += blockDim.x) qrec[x] = q_record(A.cost, encn, x);
+    fill_q_tables(qmx, qiu, qn, A.cost, encn);
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
@@ -538,8 +550,8 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
      * trace in the state.  `live` gates the trace stores. */
     auto pair_step = [&](auto masked_tag, unsigned rw2, double SlA, double ElA, double SlB, double ElB, bool live, bool hasB) {
         constexpr bool MASKED = decltype(masked_tag)::value;
-        fill_cost_table(mytab, qrec, rw2 & 0xffffu, kinds);
-        fill_cost_table(mytab + kTab, qrec, rw2 >> 16, kinds);
+        fill_cost_table(mytab, Q, rw2 & 0xffffu, kinds);
+        fill_cost_table(mytab + kTab, Q, rw2 >> 16, kinds);
         {   /* column 0 feeds the first lane: src/reference_align.cpp:64-78 */
             const double c0a = __dsub_rn(c0base, __dmul_rn(c0step, (double)i));           /* H[i+1][0] */
             const double c0b = __dsub_rn(c0base, __dmul_rn(c0step, (double)(i + 1)));     /* H[i+2][0] */
@@ -1214,9 +1226,9 @@ __global__ void __launch_bounds__(128) scramble_rows_fy_global(const uint16_t* i
  * swaps the two windows.  Every draw is stream_word(stream_key(seed, read index, field), position): the read depends on
  * (seed, index) only -- sarlacc_b200/synth.py: mock_windows is the numpy mirror, bit for bit.
  * Fields: 0/4 molecule fill (front/back molecule), 1/5 mutation, 2/6 count choice, 3/7 quality, 8 flip, 9 width. */
-/* quality >= k  <=>  word < thr[k] with thr non-increasing in k: the quality is the number of k in 1..93 whose threshold
+/* quality >= k  <=>  word < thr[k] with thr non-increasing in k: the quality is the largest k in 0..93 whose threshold
  * exceeds the word, found by a fixed-depth binary search (every lane takes the same seven steps). */
-__device__ __forceinline__ unsigned mock_quality(uint32_t h, const uint32_t* thr, unsigned qmin) {
+__device__ __forceinline__ unsigned mock_quality_search(uint32_t h, const uint32_t* thr, unsigned qmin) {
     unsigned lo = 0, hi = 94;            /* invariant: h < thr[lo] (thr[0] = 2^32 - 1 stands for 2^32), !(h < thr[hi]) (thr[94] = 0) */
 #pragma unroll
     for (int s = 0; s < 7; ++s) {
@@ -1228,14 +1240,32 @@ __device__ __forceinline__ unsigned mock_quality(uint32_t h, const uint32_t* thr
     return lo < qmin ? qmin : lo;        /* word 2^32 - 1 fails the saturated thresholds below qmin */
 }
 
+/* The same function through a 256-entry table on the word's top byte: lut[b] = the quality of the largest word of bucket
+ * b if the bucket spans at most two qualities (then one comparison decides), 255 otherwise (the search; only the lowest
+ * buckets, where the thresholds crowd: < 1 % of the words). */
+__device__ __forceinline__ unsigned mock_quality(uint32_t h, const uint32_t* thr, const uint8_t* lut, unsigned qmin) {
+    const unsigned base = lut[h >> 24];
+    if (base == 255u) return mock_quality_search(h, thr, qmin);
+    return base + (h < thr[base + 1] ? 1u : 0u);
+}
+
 /* Threads [0, n) build the adaptor1 molecule's window of read t, threads [n, 2n) the adaptor2 molecule's: a warp works on
- * one molecule (uniform adaptor reads), the quality thresholds sit in shared memory (per-lane indices). */
+ * one molecule (uniform adaptor reads); the quality thresholds and their lookup table sit in shared memory. */
 __global__ void __launch_bounds__(128) mock_windows_kernel(const __grid_constant__ MockArgs M)
 {
     __shared__ uint32_t sthr[96];
+    __shared__ uint32_t swcdf[256];
+    __shared__ uint8_t slut[256];
     __shared__ char sad[2][128];
     for (int x = threadIdx.x; x < 95; x += blockDim.x) sthr[x] = M.qthr[x];
+    for (int x = threadIdx.x; x < 256; x += blockDim.x) swcdf[x] = M.wcdf[x];
     for (int x = threadIdx.x; x < 128; x += blockDim.x) { sad[0][x] = M.adaptor1[x]; sad[1][x] = M.adaptor2[x]; }
+    __syncthreads();
+    for (int x = threadIdx.x; x < 256; x += blockDim.x) {
+        const unsigned qlo = mock_quality_search(((uint32_t)x << 24) | 0xFFFFFFu, sthr, M.qmin);
+        const unsigned qhi = mock_quality_search((uint32_t)x << 24, sthr, M.qmin);
+        slut[x] = (qhi - qlo <= 1u && qlo < 93u) ? (uint8_t)qlo : (uint8_t)255;
+    }
     __syncthreads();
     const long long npad = (M.n + 127) / 128 * 128;            /* molecule 1 starts at a block boundary */
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1257,7 +1287,7 @@ __global__ void __launch_bounds__(128) mock_windows_kernel(const __grid_constant
     uint32_t acc[4] = {0u, 0u, 0u, 0u};                     /* eight 16-bit entries per 128-bit store */
     for (uint32_t p = 0; emitted < M.tol; ++p) {
         unsigned b;
-        const char c = p < (uint32_t)alen ? ad[p] : 'N';
+        const char c = p < (uint32_t)alen ? ad[p] : 'N';        /* uniform over the warp: every lane is at molecule position p */
         if (c == 'A') b = 0; else if (c == 'C') b = 1; else if (c == 'G') b = 2; else if (c == 'T') b = 3;
         else if ((int)p >= run0 && (int)p < run1) b = M.nbarcodes > 0 ? (unsigned)M.barcodes[barcode_pick * (run1 - run0) + ((int)p - run0)] : barcode_base;
         else b = stream_word(kfill, p) & 3u;
@@ -1269,7 +1299,7 @@ __global__ void __launch_bounds__(128) mock_windows_kernel(const __grid_constant
             copies = k == 0 ? 0 : (int)k + 1;
         }
         for (int x = 0; x < copies && emitted < M.tol; ++x) {
-            const unsigned q = mock_quality(stream_word(kq, (uint32_t)emitted), sthr, M.qmin);
+            const unsigned q = mock_quality(stream_word(kq, (uint32_t)emitted), sthr, slut, M.qmin);
             const uint32_t entry = ((1u << b) << 8) | q;
             acc[(emitted & 7) >> 1] |= entry << (16 * (emitted & 1));
             ++emitted;
@@ -1288,32 +1318,26 @@ __global__ void __launch_bounds__(128) mock_windows_kernel(const __grid_constant
         M.lens_front[r] = M.tol;
         M.lens_back[r] = M.tol;
         if (M.flipped) M.flipped[r] = flip ? 1 : 0;
-    }
-}
-
-/* Read width = mutated length of adaptor1 + insert + adaptor2: every base independently an indel w.p. indel_rate, changing
- * the length by -1 or +1..max_insert-1; four bases per pair of stream words (16-bit fields).  One warp per read, its
- * lanes striding over the molecule. */
-__global__ void __launch_bounds__(256) mock_widths_kernel(const __grid_constant__ MockArgs M)
-{
-    const int lane = threadIdx.x & 31;
-    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
-    for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < M.n; r += warps) {
-        const uint32_t kw = stream_key(M.seed, M.first_index + (unsigned long long)r, 9u);
-        int delta = 0;
-        for (int p4 = lane; p4 * 4 < M.molecule_len; p4 += 32) {
-            const uint32_t lo = stream_word(kw, 2u * p4), hi = stream_word(kw, 2u * p4 + 1u);
-            const uint32_t f[4] = {lo & 0xFFFFu, lo >> 16, hi & 0xFFFFu, hi >> 16};
+        /* read width = mutated length of adaptor1 + insert + adaptor2 (:77-79 over the whole molecule): the number of
+         * indels is Binomial(molecule_len, indel rate), drawn by inverting its distribution function (an integer table
+         * built on the host: E = wlo + #{k : word >= wcdf[k]}); each changes the length by -1 or +1..max_insert-1 */
+        const uint32_t kw = stream_key(M.seed, rid, 9u);
+        const uint32_t u = stream_word(kw, 0u);
+        unsigned lo = 0, hi = 256;                             /* first k with u < wcdf[k] (256 if none) */
 #pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                if (p4 * 4 + x < M.molecule_len && f[x] < M.indel_thr) {
-                    const uint32_t k = stream_word(kw, 0x80000000u + (uint32_t)(p4 * 4 + x)) % (uint32_t)M.max_insert;
-                    delta += k == 0 ? -1 : (int)k;
-                }
-            }
+        for (int s = 0; s < 8; ++s) {
+            const unsigned mid = (lo + hi) >> 1;
+            const bool ge = u >= swcdf[mid];
+            lo = ge ? mid + 1 : lo;
+            hi = ge ? hi : mid;
         }
-        delta = __reduce_add_sync(FULL, delta);
-        if (lane == 0) M.width[r] = M.molecule_len + delta;
+        const int events = M.wlo + (int)lo;
+        int width = M.molecule_len;
+        for (int e = 0; e < events; ++e) {
+            const uint32_t k = stream_word(kw, 1u + (uint32_t)e) % (uint32_t)M.max_insert;
+            width += k == 0 ? -1 : (int)k;
+        }
+        M.width[r] = width;
     }
 }
 
@@ -1421,9 +1445,9 @@ bool for_geometry(int C, bool solo, F&& f) {
 }  // namespace
 
 size_t wavefront_smem_bytes(const AlignArgs& a) {
-    /* row-0 chain + lane-private tables (two rows' worth: the row-pair kernel) + 64-byte per-quality cost records + reference columns */
+    /* row-0 chain + lane-private tables (two rows' worth: the row-pair kernel) + per-quality cost tables (5 doubles) + reference columns */
     return sizeof(double) * ((((size_t)a.L + 1 + (size_t)(kBlock / 32) * 2 * kCostEntries * 32 + 1) & ~(size_t)1) +
-                             (size_t)a.enc_n * 8) +
+                             (size_t)a.enc_n * 5 + 2) +
            2 * (size_t)a.nref * a.L;
 }
 
@@ -1506,12 +1530,6 @@ void launch_mock_windows(const MockArgs& m, cudaStream_t st) {
     const int block = 128;
     const long long npad = (m.n + block - 1) / block * block;
     mock_windows_kernel<<<(int)(2 * npad / block), block, 0, st>>>(m);
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    long long grid = (m.n + 7) / 8;
-    if (grid > (long long)sms * 8) grid = (long long)sms * 8;
-    mock_widths_kernel<<<(int)grid, 256, 0, st>>>(m);
 }
 
 void launch_pack_rows(const PackArgs& a, cudaStream_t st) {

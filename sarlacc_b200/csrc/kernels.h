@@ -155,6 +155,8 @@ struct MockArgs {
     int molecule_len;                      /* adaptor1 + insert + adaptor2 before mutation */
     int max_insert;
     uint32_t sub_thr, indel_thr;           /* 16-bit thresholds: floor(rate * 65536) */
+    int wlo;                               /* read width: number of indels = wlo + #{k : word >= wcdf[k]} (Binomial(molecule_len, rate)) */
+    uint32_t wcdf[256];                    /* floor(2^32 * P(indels <= wlo + k)) */
     uint32_t qmin;                         /* smallest quality that can occur */
     uint32_t qthr[95];                     /* quality >= k  <=>  word < qthr[k]  (k = 0..93; qthr[94] = 0) */
     char adaptor1[128]; char adaptor2[128];

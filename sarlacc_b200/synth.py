@@ -111,20 +111,40 @@ def _mock_window_block(seed, rid, mol, adaptor, run0, barcodes, W, sub_thr, inde
     return seq, (q + 33).astype(np.uint8)
 
 
-def _mock_widths(seed, rid, molecule_len, indel_thr, max_insert, block=8192):
+def width_table(molecule_len, indel_thr):
+    """(wlo, wcdf[256]): the number of indels of a whole read is Binomial(molecule_len, indel_thr / 65536), drawn by
+    inverting this integer distribution function -- the table sarlacc_chunk_load_mock builds (csrc/api.cpp), same
+    operations in the same order on IEEE doubles."""
+    pr = float(indel_thr) / 65536.0
+    qr = 1.0 - pr
+    wlo = max(0, int(float(molecule_len) * pr) - 128)
+    x = 1.0
+    for _ in range(molecule_len):
+        x *= qr
+    cdf = 0.0
+    out = np.zeros(256, dtype=np.uint64)
+    for k in range(wlo + 256):
+        cdf += x
+        if k >= wlo:
+            t = float(np.floor(cdf * 4294967296.0))
+            out[k - wlo] = 0xFFFFFFFF if t >= 4294967295.0 else int(t)
+        t1 = float(molecule_len - k) * pr
+        t2 = float(k + 1) * qr
+        x = x * t1
+        x = x / t2
+    return wlo, out
+
+
+def _mock_widths(seed, rid, molecule_len, indel_thr, max_insert):
+    wlo, wcdf = width_table(molecule_len, indel_thr)
+    kw = _stream_key(seed, rid, 9)
+    u = _stream_word(kw, 0).astype(np.uint64)
+    events = wlo + np.searchsorted(wcdf, u, side="right")        # first k with u < wcdf[k]
     out = np.full(len(rid), molecule_len, dtype=np.int64)
-    nw = (molecule_len + 3) // 4
-    for b0 in range(0, len(rid), block):
-        r = rid[b0:b0 + block]
-        kw = _stream_key(seed, r, 9)[:, None]
-        p4 = np.arange(nw, dtype=np.uint32)[None, :]
-        lo, hi = _stream_word(kw, _U32(2) * p4), _stream_word(kw, _U32(2) * p4 + _U32(1))
-        f = np.stack([lo & _U32(0xFFFF), lo >> _U32(16), hi & _U32(0xFFFF), hi >> _U32(16)], axis=2).reshape(len(r), -1)[:, :molecule_len]
-        ev = f < _U32(indel_thr)
-        rows, cols = np.nonzero(ev)
-        if len(rows):
-            k = (_stream_word(kw[rows, 0], (np.uint32(0x80000000) + cols.astype(np.uint32))) % _U32(max_insert)).astype(np.int64)
-            np.add.at(out, b0 + rows, np.where(k == 0, -1, k))
+    for e in range(int(events.max()) if len(rid) else 0):
+        live = events > e
+        k = (_stream_word(kw[live], 1 + e) % _U32(max_insert)).astype(np.int64)
+        out[live] += np.where(k == 0, -1, k)
     return out
 
 

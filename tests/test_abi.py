@@ -109,4 +109,4 @@ def test_no_predicate_spills_in_row_loops():
     for C, solo in ((18, 0), (20, 1), (21, 1), (22, 1), (23, 1), (24, 1), (11, 0), (12, 0)):
         per_trace = sass_loop.analyse(_lib.LIB_PATH, "wf_forward2", C, 1, solo)[0]
         per_score = sass_loop.analyse(_lib.LIB_PATH, "wf_forward2", C, 0, solo)[0]
-        assert per_trace < 29.0 and per_score < 23.5, (C, solo, per_trace, per_score)
+        assert per_trace < 31.0 and per_score < 25.0, (C, solo, per_trace, per_score)
