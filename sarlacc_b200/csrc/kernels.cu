@@ -141,25 +141,29 @@ __device__ __forceinline__ void land_step(int& lf0, int& lf1, bool pd, bool p5, 
  * whenever pd is false -- the only case in which the traceback (and land_step) read it: if m <= v then mv = v, and if
  * m > v but the diagonal lost, h >= m > v. */
 #ifndef SARLACC_WF_SHORT_CHAIN
-#define SARLACC_WF_SHORT_CHAIN 0   /* measured: no gain without trace records (a1 1192 -> 1160, a2 1099 -> 1114 GCUPS), -12 % with (predicates spill into SELs) */
+#define SARLACC_WF_SHORT_CHAIN 0   /* 1: every row-pair kernel takes the short chain (A/B builds) */
 #endif
 #ifndef SARLACC_WF_JIT_M
 #define SARLACC_WF_JIT_M 0
 #endif
+/* SHORT is chosen per instantiation (wf_forward2): measured on B200 (profiles/r02_history.md), the short chain gains
+ * 5 % for the score-only solo kernel (1203 -> 1261 GCUPS on the 22-bp adaptor), nothing for the four-lane geometry, and
+ * costs 14-16 % wherever trace records are written (the extra live predicates are materialised through SEL). */
+template <bool SHORT>
 __device__ __forceinline__ double pick_move(double h, double m, double v, bool& pd, bool& p5) {
-#if SARLACC_WF_SHORT_CHAIN
-    const bool pmv = m > v;
-    const double mv = pmv ? m : v;
-    const bool q = h > mv;
-    pd = pmv && (m > h);
-    p5 = pmv || q;
-    return q ? h : mv;
-#else
-    p5 = h > v;
-    const double t = p5 ? h : v;
-    pd = m > t;
-    return pd ? m : t;
-#endif
+    if constexpr (SHORT) {
+        const bool pmv = m > v;
+        const double mv = pmv ? m : v;
+        const bool q = h > mv;
+        pd = pmv && (m > h);
+        p5 = pmv || q;
+        return q ? h : mv;
+    } else {
+        p5 = h > v;
+        const double t = p5 ? h : v;
+        pd = m > t;
+        return pd ? m : t;
+    }
 }
 
 constexpr int kCostEntries = 7;   /* A, C, G, T, two-fold code, three-fold code, N */
@@ -464,6 +468,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
      * selects, column 0 is a constant boundary -- the geometry for 20-24 bp references (adaptor2, barcodes). */
     using WT = typename FlagWord<C>::type;
     static_assert(kSkew == 2, "the row-pair kernel lags its left neighbour by one two-row step: record layout and traceback assume SARLACC_WF_SKEW == 2");
+    constexpr bool SHORT = (SOLO && !TRACE) || (SARLACC_WF_SHORT_CHAIN != 0);     /* see pick_move */
     extern __shared__ double smem_d[];
     const int L = A.L, nref = A.nref, encn = A.enc_n;
     double* row0s = smem_d;                                   /* [L+1]                         */
@@ -611,7 +616,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
                 const bool p1 = Ee > hO;
                 const double h = p1 ? Ee : hO;
                 bool pd, p5;
-                const double Sn = pick_move(h, mAk, F[k], pd, p5);
+                const double Sn = pick_move<SHORT>(h, mAk, F[k], pd, p5);
                 S[k] = Sn;
                 SlA = Sn;
                 ElA = h;
@@ -643,7 +648,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
                 const bool p1 = Ee > hO;
                 const double h = p1 ? Ee : hO;
                 bool pd, p5;
-                const double Sn = pick_move(h, mB, vB, pd, p5);
+                const double Sn = pick_move<SHORT>(h, mB, vB, pd, p5);
                 if (MASKED) {
                     S[kk] = hasB ? Sn : SA;
                     F[kk] = hasB ? vB : FA;
