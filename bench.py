@@ -348,6 +348,7 @@ def main():
         # raw bases + qualities of both windows, two 8-byte offsets and a 4-byte length per window, read widths
         h2d = int(2 * (sub_f.seq_off[-1] + sub_b.seq_off[-1]) + 2 * ne * (16 + 4) + ne * 4)
         d2h = ne * (1 + (8 + 4 + 4 + 8 * len(s1)) + (8 + 4 + 4 + 8 * len(s2)))
+        e2e_step_unfused()         # warm: the single-adaptor entry has its own scratch
         barrier()
         t0 = time.perf_counter()
         e2e_step_unfused()

@@ -185,7 +185,7 @@ bool choose_geometry(Plan& P) {
     }
     /* 20-24 columns: one thread per alignment, all columns in its registers -- no shuffles, no boundary selects, the
      * row overhead spread over twice the columns of the two-lane split (profiles/r02_history.md) */
-    P.solo = P.L >= kSoloMinC && P.L <= kSoloMaxC && P.nref == 1 && std::getenv("SARLACC_NO_SOLO") == nullptr;
+    P.solo = P.L >= kSoloMinC && P.L <= kSoloMaxC && std::getenv("SARLACC_NO_SOLO") == nullptr;
     double best = 1e300;
     for (int g = 1; g <= kMaxGroup; g *= 2) {
         const int c = (P.L + g - 1) / g;
@@ -783,8 +783,10 @@ int pair_rows_default(int maxlen = 1 << 30) {
 /* The geometry a run over windows of at most `maxlen` rows uses: the solo kernel is a row-pair kernel whose lanes are
  * independent alignments, so it wants windows long enough to stay in step (the same bound as pair_rows_default). */
 struct Geometry { int G, C; bool solo; int pair; };
-Geometry geometry_for(const Plan& P, int maxlen = 1 << 30) {
-    if (P.solo && pair_rows_default(maxlen)) return Geometry{1, P.L, true, 1};
+Geometry geometry_for(const Plan& P, int maxlen = 1 << 30, bool by_length = false) {
+    /* by_length: the launch walks its reads in order of length, which keeps a warp of independent alignments in step
+     * however short they are (barcode-length reads) */
+    if (P.solo && (pair_rows_default(maxlen) || by_length) && (P.nref == 1 || by_length)) return Geometry{1, P.L, true, 1};
     return Geometry{P.G, P.C, false, pair_rows_default(maxlen)};
 }
 
@@ -891,7 +893,7 @@ struct FwdRec {
 
 FwdRec forward_once(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t st,
         const uint16_t* d_rows, const int32_t* d_lens, long long m, int stride, int maxlen,
-        bool trace, const Outputs& out, int sms, FwdTimer* timer = nullptr)
+        bool trace, const Outputs& out, int sms, FwdTimer* timer = nullptr, const int32_t* d_by_length = nullptr)
 {
     FwdRec R;
     AlignArgs& A = R.A;
@@ -911,8 +913,9 @@ FwdRec forward_once(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t st
     A.cost = D.cost;
     A.enc_n = P.enc->n;
     A.kinds = P.kinds;
-    const Geometry geo = geometry_for(P, maxlen);
+    const Geometry geo = geometry_for(P, maxlen, d_by_length != nullptr);
     R.geo = geo;
+    A.index = d_by_length;
     A.G = geo.G;
     A.C = geo.C;
     A.solo = geo.solo ? 1 : 0;
@@ -991,7 +994,8 @@ TraceArgs trace_args_for(const Plan& P, const DevPlan& D, const FwdRec& R) {
 const char* run_device(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t st,
         const uint16_t* d_rows, const int32_t* d_lens, long long n, int stride, int maxlen,
         bool trace, const Outputs& out, int sms, FwdTimer* timer = nullptr,
-        cudaStream_t tb_stream = nullptr, cudaEvent_t fwd_done = nullptr, cudaEvent_t tb_done = nullptr)
+        cudaStream_t tb_stream = nullptr, cudaEvent_t fwd_done = nullptr, cudaEvent_t tb_done = nullptr,
+        const int32_t* d_by_length = nullptr)
 {
     /* With tb_stream set, the traceback of this range runs on that stream after fwd_done (recorded on `st`), and
      * tb_done is recorded behind it: the memory-bound traceback then overlaps the next range's ALU-bound forward pass
@@ -999,7 +1003,7 @@ const char* run_device(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t
      * protect the scratch buffers. */
     if (n == 0) return "";
     if (sub_chunk(P, maxlen, trace, n) < n) throw CudaError{"internal error: run_device was handed more alignments than its scratch budget covers"};
-    const FwdRec R = forward_once(P, D, S, st, d_rows, d_lens, n, stride, maxlen, trace, out, sms, timer);
+    const FwdRec R = forward_once(P, D, S, st, d_rows, d_lens, n, stride, maxlen, trace, out, sms, timer, trace ? nullptr : d_by_length);
     if (trace) {
         TraceArgs T = trace_args_for(P, D, R);
         S.map.reserve(sizeof(int32_t) * ((size_t)P.L + 1) * (size_t)n);
@@ -1287,8 +1291,8 @@ struct Slot {
      * the device -- concurrently they finish three chunks in the time of 3.4 (measured with pinned inputs, when the
      * host no longer paces the enqueues). */
     cudaEvent_t gate = nullptr;
-    PinBuf h_rows, h_lens, h_out;
-    DevBuf d_rows, d_lens, d_out;
+    PinBuf h_rows, h_lens, h_out, h_order;
+    DevBuf d_rows, d_lens, d_out, d_order;     /* *_order: the chunk's reads by length (barcode-length reads) */
     PinBuf h_rows2, h_lens2, h_width;     /* second window set + read widths of the fused both-ends entry */
     DevBuf d_rows2, d_lens2, d_width, d_tmp;
     Scratch scratch;
@@ -1313,8 +1317,8 @@ struct Slot {
         CUDA_CHECK(cudaEventCreate(&t_end));
     }
     void destroy() {
-        h_rows.release(); h_lens.release(); h_out.release();
-        d_rows.release(); d_lens.release(); d_out.release();
+        h_rows.release(); h_lens.release(); h_out.release(); h_order.release();
+        d_rows.release(); d_lens.release(); d_out.release(); d_order.release();
         h_rows2.release(); h_lens2.release(); h_width.release();
         d_rows2.release(); d_lens2.release(); d_width.release(); d_tmp.release();
         scratch.release();
@@ -1575,8 +1579,25 @@ struct DeviceJob {
                 dev.ops = d + o.o_ops;
                 dev.ops_stride = o.ops_stride;
             }
+            /* Barcode-length reads, score-only: walk the chunk in order of length (counting sort), so that the alignments a
+             * warp works on side by side end together -- 24-row alignments otherwise spend half their steps waiting for
+             * whichever lane finishes next (configs[3]: 0.11 s -> see profiles/r02_history.md). */
+            const int32_t* d_order = nullptr;
+            if (!trace && P.fast && maxlen < 48 && m > 1 && std::getenv("SARLACC_NO_LENGTH_ORDER") == nullptr) {
+                s.h_order.reserve(sizeof(int32_t) * (size_t)m);
+                s.d_order.reserve(sizeof(int32_t) * (size_t)m);
+                const int32_t* hl = s.h_lens.as<int32_t>();
+                int32_t* ho = s.h_order.as<int32_t>();
+                std::vector<long long> start((size_t)maxlen + 2, 0);
+                for (long long i = 0; i < m; ++i) ++start[(size_t)hl[i] + 1];
+                for (int l = 0; l <= maxlen; ++l) start[(size_t)l + 1] += start[(size_t)l];
+                for (long long i = 0; i < m; ++i) ho[start[(size_t)hl[i]]++] = (int32_t)i;
+                CUDA_CHECK(cudaMemcpyAsync(s.d_order.p, ho, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
+                d_order = s.d_order.as<int32_t>();
+            }
             if (prev_gate) CUDA_CHECK(cudaStreamWaitEvent(s.st, prev_gate, 0));
-            run_device(P, D, s.scratch, s.st, s.d_rows.as<uint16_t>(), s.d_lens.as<int32_t>(), m, stride, maxlen, trace, dev, sms);
+            run_device(P, D, s.scratch, s.st, s.d_rows.as<uint16_t>(), s.d_lens.as<int32_t>(), m, stride, maxlen, trace, dev, sms,
+                       nullptr, nullptr, nullptr, nullptr, d_order);
             CUDA_CHECK(cudaEventRecord(s.gate, s.st));
             prev_gate = s.gate;
             CUDA_CHECK(cudaMemcpyAsync(s.h_out.p, s.d_out.p, o.total, cudaMemcpyDeviceToHost, s.st));

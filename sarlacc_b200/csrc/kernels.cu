@@ -290,7 +290,8 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
     for (int k = 0; k < C; ++k) { S[k] = 0.0; F[k] = NEG; }
     double outS = 0.0, outE = NEG, diag0 = 0.0;
     double outS2 = 0.0, outE2 = NEG;   /* kSkew == 2: what this lane produced one row earlier */
-    long long a = gidx - NG;
+    long long a = gidx - NG;     /* position in the processing order of the launch */
+    long long r = 0;             /* the read it stands for (AlignArgs::index) */
     int b = nref - 1;
     int i = 0, len = 0, delay = kSkew * j;
     bool done = false;
@@ -387,14 +388,18 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
             if (b == nref) {
                 b = 0;
                 a += NG;
-                while (a < A.n && (len = A.lens[a]) == 0) a += NG;   /* empty reads: launch_fill_empty */
+                while (a < A.n) {                                    /* empty reads: launch_fill_empty */
+                    r = A.index ? A.index[a] : a;
+                    if ((len = A.lens[r]) != 0) break;
+                    a += NG;
+                }
             }
             if (a >= A.n) {
                 done = true;
                 act = false;
             } else {
                 i = 0;
-                rowp = A.rows + a * (long long)A.stride - 1;                                   /* advanced to row i before use */
+                rowp = A.rows + r * (long long)A.stride - 1;                                   /* advanced to row i before use */
                 if (TRACE) fidx = a * A.fstride + (long long)j * (kSkew * G + 1);   /* word (i + kSkew * j) * G + j */
 #pragma unroll
                 for (int k = 0; k < C; ++k) {
@@ -440,14 +445,14 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
 
         if (act && i == len && j == G - 1) {
             const double s = S[C - 1];
-            if (A.score) A.score[(long long)b * A.n + a] = s;
+            if (A.score) A.score[(long long)b * A.n + r] = s;
             if (TRACE) { if (A.endrow) A.endrow[a] = lf0; }
             if (A.best_id) {
                 update_best(s, b + 1, best, nextb, bid);
                 if (b == nref - 1) {
-                    A.best_id[a] = bid;
-                    A.best[a] = best;
-                    A.next_best[a] = nextb;
+                    A.best_id[r] = bid;
+                    A.best[r] = best;
+                    A.next_best[r] = nextb;
                 }
             }
         }
@@ -533,7 +538,8 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
 #pragma unroll
     for (int k = 0; k < C; ++k) { S[k] = 0.0; F[k] = NEG; }
     double outSA = 0.0, outEA = NEG, outSB = 0.0, outEB = NEG, diag0 = 0.0;
-    long long a = gidx - NG;
+    long long a = gidx - NG;     /* position in the processing order of the launch */
+    long long r = 0;             /* the read it stands for (AlignArgs::index) */
     int b = nref - 1;
     int i = 0, len = 0, delay = SOLO ? 0 : j;
     bool done = false;
@@ -704,14 +710,18 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
             if (b == nref) {
                 b = 0;
                 a += NG;
-                while (a < A.n && (len = A.lens[a]) == 0) a += NG;
+                while (a < A.n) {
+                    r = A.index ? A.index[a] : a;
+                    if ((len = A.lens[r]) != 0) break;
+                    a += NG;
+                }
             }
             if (a >= A.n) {
                 done = true;
                 act = false;
             } else {
                 i = 0;
-                rowp = A.rows + a * (long long)A.stride;
+                rowp = A.rows + r * (long long)A.stride;
                 cur = *reinterpret_cast<const unsigned*>(rowp);
                 if (TRACE) {
                     if (SOLO) fidx = ((a >> 5) * A.fstride + 1) * 32 + (a & 31);     /* [32 alignments][row][lane], row = 1 */
@@ -777,14 +787,14 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
 
         if (act && i == len && j == G - 1) {
             const double s = S[C - 1];
-            if (A.score) A.score[(long long)b * A.n + a] = s;
+            if (A.score) A.score[(long long)b * A.n + r] = s;
             if (TRACE) { if (A.endrow) A.endrow[a] = lf0; }
             if (A.best_id) {
                 update_best(s, b + 1, best, nextb, bid);
                 if (b == nref - 1) {
-                    A.best_id[a] = bid;
-                    A.best[a] = best;
-                    A.next_best[a] = nextb;
+                    A.best_id[r] = bid;
+                    A.best[r] = best;
+                    A.next_best[r] = nextb;
                 }
             }
         }

@@ -42,6 +42,10 @@ struct AlignArgs {
     const int32_t* lens;
     long long n;
     int stride;
+    /* optional processing order: the a-th alignment of the launch is read index[a] (rows, lens, scores and the running
+     * best are addressed by read; traceback records and endrow by a).  Barcode-length reads are walked in order of length,
+     * so that the lanes of a warp -- independent alignments -- reach their ends together (api.cpp: DeviceJob). */
+    const int32_t* index;
     /* reference(s): nref strings of length L (nref > 1 only for the fused multi-barcode pass) */
     int L;
     int nref;

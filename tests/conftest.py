@@ -30,6 +30,26 @@ def ref():
     return Oracle("ref")
 
 
+@pytest.fixture(scope="session", params=["port", "ref"])
+def both_oracles(request):
+    """Every GPU parity test runs against the plain-C restatement AND the reference's own reference_align.cpp compiled
+    verbatim (oracle/_ref): the GPU modules alias their `port` fixture to this one."""
+    from oracle.oracle import Oracle
+    kind = request.param
+    if not Oracle.available(kind):
+        if kind == "ref":
+            pytest.skip("oracle/_ref/libsarlacc_ref.so not built (needs /root/reference)")
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+    return Oracle(kind)
+
+
+def stable_seed(*parts):
+    """A seed that is the same in every process (str hashes are salted per process; failing cases must replay)."""
+    import zlib
+    return zlib.crc32(repr(parts).encode())
+
+
 @pytest.fixture(scope="session")
 def enc():
     from oracle.oracle import phred_encoding

@@ -8,6 +8,12 @@ from conftest import VIGNETTE_A1, VIGNETTE_A2
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(scope="module")
+def port(both_oracles):
+    """Both CPU oracles in turn: the restatement and the reference's own C++ (tests/conftest.py: both_oracles)."""
+    return both_oracles
+
+
 def compare_adaptor_align(out, exp):
     assert len(out) == len(exp)
     for side in ("adaptor1", "adaptor2"):
@@ -365,13 +371,18 @@ def test_full_size_properties(port, enc):
     assert np.median(a[0][fwd]) > 40 and np.median(a[1][fwd]) == 1
     assert np.mean(a[4][0][fwd] == 12) > 0.7 and np.mean(a[4][1][fwd] == 4) > 0.8
     assert np.median(a[0][flips]) < 10
-    # (4) strided sample against the oracle
-    idx = np.arange(0, n, 97)
-    sub = front[idx]
-    exp = port.adaptor_align(sub.seq_strings(), sub.qual_strings(), enc, 5, 1, VIGNETTE_A1, ss, se, nthreads=8)
-    assert np.array_equal(a[0][idx], exp[0]) and np.array_equal(a[1][idx], exp[1]) and np.array_equal(a[2][idx], exp[2])
-    for s in range(2):
-        assert np.array_equal(a[3][s][idx], exp[3][s]) and np.array_equal(a[4][s][idx], exp[4][s])
+    # (4) strided samples of all four alignments of .align_AA_internal against the oracle
+    got = {"a1_front": a, "a2_back": native.adaptor_align(back, enc, 5, 1, VIGNETTE_A2),
+           "a1_back": native.adaptor_align(back, enc, 5, 1, VIGNETTE_A1, ss, se), "a2_front": native.adaptor_align(front, enc, 5, 1, VIGNETTE_A2)}
+    for k, (key, rs, ad, sec) in enumerate((("a1_front", front, VIGNETTE_A1, True), ("a2_back", back, VIGNETTE_A2, False),
+                                            ("a1_back", back, VIGNETTE_A1, True), ("a2_front", front, VIGNETTE_A2, False))):
+        idx = np.arange(k * 13, n, 97)
+        sub = rs[idx]
+        exp = port.adaptor_align(sub.seq_strings(), sub.qual_strings(), enc, 5, 1, ad, ss if sec else [], se if sec else [], nthreads=8)
+        g = got[key]
+        assert np.array_equal(g[0][idx], exp[0]) and np.array_equal(g[1][idx], exp[1]) and np.array_equal(g[2][idx], exp[2]), key
+        for s in range(2 if sec else 0):
+            assert np.array_equal(g[3][s][idx], exp[3][s]) and np.array_equal(g[4][s][idx], exp[4][s]), key
 
 
 def test_multi_device_sharding_in_one_process(port, enc):

@@ -6,9 +6,15 @@ relative -- the FP64 kernels are expected to be, and are asserted to be, bit-ide
 import numpy as np
 import pytest
 
-from conftest import VIGNETTE_A1, VIGNETTE_A2, random_windows
+from conftest import VIGNETTE_A1, VIGNETTE_A2, random_windows, stable_seed
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def port(both_oracles):
+    """Both CPU oracles in turn: the restatement and the reference's own C++ (tests/conftest.py: both_oracles)."""
+    return both_oracles
 
 
 def setup_subseqs(adaptor):
@@ -55,7 +61,7 @@ def test_known_answers(port, enc):
 @pytest.mark.parametrize("go,ge", [(5, 1), (4, 1), (10, 5), (0, 1), (2.5, 0.3)])
 def test_adaptor_align_random(port, enc, adaptor, go, ge):
     from sarlacc_b200 import native
-    rng = np.random.default_rng(abs(hash((adaptor, go, ge))) % (2 ** 32))
+    rng = np.random.default_rng(stable_seed(adaptor, go, ge))
     seqs, quals = random_windows(rng, 300, adaptor, 1, 120)
     seqs += ["", "A", "ACGT" * 70]
     quals += ["", "I", "5" * 280]
@@ -302,3 +308,31 @@ def test_chunking_and_scratch_budget(port, enc, monkeypatch):
     for s in range(len(ss)):
         assert np.array_equal(got[3][s], exp[3][s]) and np.array_equal(got[4][s], exp[4][s])
     assert np.array_equal(got[1], exp[1]) and np.array_equal(got[0], exp[0])
+
+
+def test_c4_ninety_six_barcodes(port, enc):
+    """BASELINE.json configs[3] in miniature: barcodeAlign of barcode-length sequences against 96 24-bp barcodes in one
+    fused pass (sequences walked in order of length, one thread per alignment) == 96 barcode_align calls of the oracle +
+    the running best / next-best of R/barcodeAlign.R:28-34."""
+    from sarlacc_b200 import native, synth
+    barcodes = synth.random_barcodes(96, 24, 8, seed=3000)
+    seqs, pick = synth.mock_barcode_sequences(3000, barcodes, seed=3001)
+    assert len(set(seqs.width().tolist())) > 4          # indels: a spread of lengths around 24
+    bid, best, nxt, mat = native.barcode_align_multi(seqs, enc, 5, 1, barcodes, all_scores=True)
+    arg = (seqs.seq_pool, seqs.seq_off), (seqs.qual_pool, seqs.qual_off)
+    exp = np.stack([port.align_score_only(*arg, enc, 5, 1, b, local=False, nthreads=8) for b in barcodes])
+    assert np.array_equal(mat, exp)
+    e_best = np.full(len(seqs), -np.inf)
+    e_next = np.full(len(seqs), -np.inf)
+    e_id = np.zeros(len(seqs), np.int32)
+    for b in range(96):
+        keep = exp[b] > e_best
+        second = ~keep & (exp[b] > e_next)
+        e_next[keep] = e_best[keep]
+        e_best[keep] = exp[b][keep]
+        e_id[keep] = b + 1
+        e_next[second] = exp[b][second]
+    assert np.array_equal(bid, e_id) and np.array_equal(best, e_best) and np.array_equal(nxt, e_next)
+    assert np.mean(bid - 1 == pick) > 0.95
+    # one barcode at a time (barcode_align, the reference's own call) goes through the same length-ordered walk
+    assert np.array_equal(native.barcode_align(seqs, enc, 5, 1, barcodes[5]), exp[5])
