@@ -15,6 +15,8 @@
 #include "sarlacc_b200.h"
 #include "kernels.h"
 
+#include <nvtx3/nvToolsExt.h>     /* header-only; ranges cost nothing unless a profiler is attached */
+
 #include <sys/mman.h>
 #include <sys/types.h>
 #include <unistd.h>
@@ -52,6 +54,15 @@ int fail(const std::string& msg) {
 }
 
 struct CudaError { std::string msg; };
+
+/* NVTX range over a host-side phase (staging, enqueueing a pass, waiting for results): what a timeline shows next to the
+ * kernels of the same phase. */
+struct Range {
+    explicit Range(const char* name) { nvtxRangePushA(name); }
+    ~Range() { nvtxRangePop(); }
+    Range(const Range&) = delete;
+    Range& operator=(const Range&) = delete;
+};
 
 }  // namespace
 
@@ -784,9 +795,12 @@ int pair_rows_default(int maxlen = 1 << 30) {
  * independent alignments, so it wants windows long enough to stay in step (the same bound as pair_rows_default). */
 struct Geometry { int G, C; bool solo; int pair; };
 Geometry geometry_for(const Plan& P, int maxlen = 1 << 30, bool by_length = false) {
-    /* by_length: the launch walks its reads in order of length, which keeps a warp of independent alignments in step
-     * however short they are (barcode-length reads) */
-    if (P.solo && (pair_rows_default(maxlen) || by_length) && (P.nref == 1 || by_length)) return Geometry{1, P.L, true, 1};
+    /* by_length: the launch walks its reads in order of length, which keeps a warp's alignments in step however short
+     * they are.  Measured on configs[3] (1 M x 96 barcodes, profiles/r02_history.md): ordering alone 0.106 -> 0.074 s with the
+     * two-lane one-row kernel; the solo kernel on top of it 0.077 s -- so barcode-length reads keep the two-lane kernel
+     * (SARLACC_SOLO_SHORT=1 switches, for tuning). */
+    static const bool solo_short = std::getenv("SARLACC_SOLO_SHORT") != nullptr;
+    if (P.solo && (pair_rows_default(maxlen) ? P.nref == 1 : (by_length && solo_short))) return Geometry{1, P.L, true, 1};
     return Geometry{P.G, P.C, false, pair_rows_default(maxlen)};
 }
 
@@ -895,6 +909,7 @@ FwdRec forward_once(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t st
         const uint16_t* d_rows, const int32_t* d_lens, long long m, int stride, int maxlen,
         bool trace, const Outputs& out, int sms, FwdTimer* timer = nullptr, const int32_t* d_by_length = nullptr)
 {
+    Range nvtx(trace ? "sarlacc: forward pass (trace)" : "sarlacc: forward pass (score)");
     FwdRec R;
     AlignArgs& A = R.A;
     std::memset(&A, 0, sizeof(A));
@@ -1076,6 +1091,7 @@ const char* run_pair_device(const Plan* const plan[2], const DevPlan* const D[2]
         long long m, int maxlen, const int32_t* width, double* tmp_scores, const PairDeviceOut& out, int sms, FwdTimer* timer = nullptr)
 {
     if (m <= 0) return "";
+    Range nvtx("sarlacc: both adaptors x both windows");
     FwdRec rec[4];
     for (int r = 0; r < 4; ++r) {
         const int a = (r == 0 || r == 2) ? 0 : 1;          /* adaptor */
@@ -1193,6 +1209,7 @@ void stage_and_pack(const ReadView& V, int64_t c0, int64_t c1, const PackTables&
 {
     const long long m = c1 - c0;
     if (m <= 0) return;
+    Range nvtx("sarlacc: stage + H2D + device pack");
     R.h_soff.reserve(sizeof(long long) * (size_t)m);
     R.h_qoff.reserve(sizeof(long long) * (size_t)m);
     long long* soff = R.h_soff.as<long long>();
@@ -1480,6 +1497,7 @@ struct DeviceJob {
         int which = 0;
         auto drain = [&](Slot& s, const OutLayout& o) {
             if (!s.busy) return;
+            Range nvtx("sarlacc: wait for chunk + copy out");
             CUDA_CHECK(cudaEventSynchronize(s.done));
             {
                 const long long fb = s.raw.first_bad();      /* quality below the offset, found by the device packer */
@@ -1848,6 +1866,7 @@ struct PairJob {
         const double t_start = now();
         auto drain = [&](Slot& s, const FinalLayout& o) {
             if (!s.busy) return;
+            Range nvtx("sarlacc: wait for chunk + copy out");
             CUDA_CHECK(cudaEventSynchronize(s.done));
             {
                 const long long fb = s.raw.first_bad(), fb2 = s.raw2.first_bad();
@@ -3178,6 +3197,7 @@ int sarlacc_chunk_load_mock(sarlacc_chunk* c, int64_t n, uint64_t first_index, u
         const char* adaptor1, const char* adaptor2, int insert_len, const char* const* barcodes, int nbarcodes,
         double sub_rate, double indel_rate, int max_insert)
 {
+    Range nvtx("sarlacc_chunk_load_mock");
     if (!c) return fail("chunk handle is NULL");
     if (n < 0 || n > c->capacity) return fail("more reads than the chunk's capacity");
     if (!adaptor1 || !adaptor2) return fail("adaptor sequence should be a string");
@@ -3289,6 +3309,7 @@ int sarlacc_chunk_load_mock(sarlacc_chunk* c, int64_t n, uint64_t first_index, u
  * point where the reference's per-read errors are known. */
 int sarlacc_chunk_load_reads(sarlacc_chunk* c, const sarlacc_reads* front, const sarlacc_reads* back, int tolerance, const int32_t* width)
 {
+    Range nvtx("sarlacc_chunk_load_reads");
     if (!c) return fail("chunk handle is NULL");
     if (!front) return fail("reads must not be NULL");
     if (tolerance < 0 || tolerance > c->tol) return fail("tolerance exceeds the chunk's");
@@ -3356,6 +3377,7 @@ int sarlacc_chunk_adaptor_align(sarlacc_chunk* c, double gapopen, double gapext,
         double* score1, int32_t* start1, int32_t* end1, int32_t* sec_start1, int32_t* sec_width1,
         double* score2, int32_t* start2, int32_t* end2, int32_t* sec_start2, int32_t* sec_width2)
 {
+    Range nvtx("sarlacc_chunk_adaptor_align");
     if (chunk_check_loaded(c)) return 1;
     if (!adaptor1 || !adaptor2) return fail("adaptor sequence should be a string");
     if (!*adaptor1 || !*adaptor2) return fail("chunk runs need two non-empty adaptors");
@@ -3468,6 +3490,7 @@ int sarlacc_chunk_adaptor_align(sarlacc_chunk* c, double gapopen, double gapext,
 int sarlacc_chunk_scrambled_scores(sarlacc_chunk* c, double gapopen, double gapext, const char* adaptor1, const char* adaptor2,
         uint64_t seed, uint64_t first_index, const uint64_t* read_index, int scramble, double* score1, double* score2)
 {
+    Range nvtx("sarlacc_chunk_scrambled_scores");
     if (chunk_check_loaded(c)) return 1;
     if (!adaptor1 || !adaptor2) return fail("adaptor sequence should be a string");
     if (!*adaptor1 || !*adaptor2) return fail("chunk runs need two non-empty adaptors");
@@ -3574,6 +3597,7 @@ int sarlacc_chunk_join(sarlacc_chunk* c) {
 void* sarlacc_chunk_stream(sarlacc_chunk* c) { return c ? (void*)c->st : nullptr; }
 
 int sarlacc_chunk_sync(sarlacc_chunk* c) {
+    Range nvtx("sarlacc_chunk_sync");
     if (!c) return fail("chunk handle is NULL");
     try {
         CUDA_CHECK(cudaSetDevice(c->device));

@@ -1,0 +1,58 @@
+"""A small pass over every kernel of the hot path, for compute-sanitizer (memcheck / racecheck): the four-lane
+and solo row-pair kernels with and without records, the one-row kernel, the literal kernel, traceback (both layouts and the
+kept-strand form), packer, generator, scramble, strand resolution, threshold selection, UMI neighbours.  Results are
+checked against the oracle so that a sanitizer-clean run is also a correct one.
+usage: compute-sanitizer --tool memcheck python tools/sanitize_run.py"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from sarlacc_b200 import native, synth  # noqa: E402
+from oracle.oracle import Oracle, phred_encoding  # noqa: E402
+from conftest import VIGNETTE_A1, VIGNETTE_A2, random_windows  # noqa: E402
+
+O = Oracle("ref" if Oracle.available("ref") else "port")
+enc = phred_encoding()
+rng = np.random.default_rng(7)
+S1, E1 = [16, 42], [28, 46]
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+
+front, back, widths, _ = synth.mock_windows(n, VIGNETTE_A1, VIGNETTE_A2, seed=11)
+fa = (front.seq_pool, front.seq_off), (front.qual_pool, front.qual_off)
+for adaptor, sec in ((VIGNETTE_A1, (S1, E1)), (VIGNETTE_A2, ([], []))):
+    got = native.adaptor_align(front, enc, 5, 1, adaptor, *sec)
+    exp = O.adaptor_align(*fa, enc, 5, 1, adaptor, *sec)
+    assert all(np.array_equal(got[k], exp[k]) for k in range(3)), adaptor
+    assert np.array_equal(native.adaptor_align_score_only(front, enc, 5, 1, adaptor), exp[0])
+# ragged short reads: one-row kernel, masked steps, literal kernel (negative gap opening), general_align
+seqs, quals = random_windows(rng, n, "ACGTNNRYACGTVVAC", 0, 60)
+for go in (5, -1):
+    got = native.adaptor_align((seqs, quals), enc, go, 2, "ACGTNNRYACGTVVAC", [4], [8])
+    exp = O.adaptor_align(seqs, quals, enc, go, 2, "ACGTNNRYACGTVVAC", [4], [8])
+    assert all(np.array_equal(got[k], exp[k]) for k in range(3))
+g = native.general_align((seqs[:50], quals[:50]), enc, 4, 1, "AAGGAATTAAGGCCTTACGT")
+e = O.general_align(seqs[:50], quals[:50], enc, 4, 1, "AAGGAATTAAGGCCTTACGT")
+assert np.array_equal(g[0], e[0]) and list(g[2]) == list(e[2])
+# barcodes: length-ordered fused pass
+barcodes = synth.random_barcodes(8, 24, 8, seed=3)
+bs, _ = synth.mock_barcode_sequences(n, barcodes, seed=4)
+bid, best, nxt, mat = native.barcode_align_multi(bs, enc, 5, 1, barcodes, all_scores=True)
+exp = np.stack([O.align_score_only((bs.seq_pool, bs.seq_off), (bs.qual_pool, bs.qual_off), enc, 5, 1, b, local=False) for b in barcodes])
+assert np.array_equal(mat, exp)
+# chunk engine: generator, both-ends pass with kept-strand traceback, scramble + score-only, thresholds
+ch = native.Chunk(n, 250, enc)
+ch.load_mock(n, VIGNETTE_A1, VIGNETTE_A2, seed=11)
+w, rev, r1, r2 = ch.adaptor_align(5, 1, VIGNETTE_A1, VIGNETTE_A2, (S1, E1), ((), ()))
+rev2, q1, q2 = native.adaptor_align_windows(front, back, enc, 5, 1, VIGNETTE_A1, VIGNETTE_A2, (S1, E1), ((), ()), read_width=widths)
+assert np.array_equal(rev, rev2) and all(np.array_equal(r1[k], q1[k]) and np.array_equal(r2[k], q2[k]) for k in range(3))
+s1, s2 = ch.scrambled_scores(5, 1, VIGNETTE_A1, VIGNETTE_A2, seed=3)
+thr = native.compute_threshold(r1[0], s1, 0.01)
+ch.close()
+# UMI neighbours
+umis = ["".join(rng.choice(list("ACGT"), 12)) for _ in range(60)]
+native.umi_group(umis + umis, 1)
+print("sanitize_run ok: %d reads per case, threshold %.3f" % (n, thr))
