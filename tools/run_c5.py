@@ -38,10 +38,11 @@ def run(total, chunk, rank, world, local, check_stride=0, error=0.01, timing=Tru
            "start1": pin(nn, torch.int32), "end1": pin(nn, torch.int32), "sec_start1": pin((2, nn), torch.int32), "sec_width1": pin((2, nn), torch.int32),
            "start2": pin(nn, torch.int32), "end2": pin(nn, torch.int32)}
     dev = torch.device("cuda", local)
-    real1 = torch.empty(nn, dtype=torch.float64, device=dev)
-    real2 = torch.empty(nn, dtype=torch.float64, device=dev)
-    scr1 = torch.empty(nn, dtype=torch.float64, device=dev)
-    scr2 = torch.empty(nn, dtype=torch.float64, device=dev)
+    nbuf = max(nn, 8)
+    real1 = torch.zeros(nbuf, dtype=torch.float64, device=dev)
+    real2 = torch.zeros(nbuf, dtype=torch.float64, device=dev)
+    scr1 = torch.zeros(nbuf, dtype=torch.float64, device=dev)
+    scr2 = torch.zeros(nbuf, dtype=torch.float64, device=dev)
     ch = native.Chunk(min(chunk, nn), TOL, enc, device=local)
     # warm-up outside the timed region: module load, plan upload, scratch allocation
     ch.load_mock(min(chunk, nn), A1, A2, seed=SEED, first_index=lo)
@@ -49,6 +50,11 @@ def run(total, chunk, rank, world, local, check_stride=0, error=0.01, timing=Tru
     ch.scrambled_scores(5, 1, A1, A2, seed=SCR_SEED, first_index=lo, score1=scr1.data_ptr(), score2=scr2.data_ptr())
     ch.sync()
     native.compute_threshold((real1.data_ptr(), min(chunk, nn)), (scr1.data_ptr(), min(chunk, nn)), error, device=local)   # loads the sort kernels
+    gathered = [None] * 4
+    if world > 1:       # receive buffers on rank 0 and one small gather, so that the timed one finds its channels set up
+        gathered = [torch.empty(world * share, dtype=torch.float64, device=dev) if rank == 0 else None for _ in range(4)]
+        tiny = [torch.empty(world * 8, dtype=torch.float64, device=dev) if rank == 0 else None][0]
+        dist.gather(real1[:8].contiguous(), list(tiny.chunk(world)) if rank == 0 else None, dst=0)
     ch.set_timing(timing)
     _lib.lib.sarlacc_kernel_launches(1)
     if world > 1:
@@ -65,19 +71,17 @@ def run(total, chunk, rank, world, local, check_stride=0, error=0.01, timing=Tru
         ch.scrambled_scores(5, 1, A1, A2, seed=SCR_SEED, first_index=lo + b0, score1=scr1.data_ptr() + 8 * b0, score2=scr2.data_ptr() + 8 * b0)
     ch.sync()
     t_align = time.perf_counter() - t0
-    # the one step that needs every read: gather the four score vectors, select the thresholds on rank 0
+    # the one step that needs every read: gather the four score vectors, select the thresholds on rank 0.  Ranks hold
+    # consecutive index ranges of `share` reads (the last ones may be short), so the first `total` entries of the gathered
+    # buffers are exactly the reads of the job.
     thr = None
     if world > 1:
-        parts = [torch.empty(world * share, dtype=torch.float64, device=dev) if rank == 0 else None for _ in range(4)]
-        for src, dst in zip((real1, real2, scr1, scr2), parts):
-            pad = torch.zeros(share, dtype=torch.float64, device=dev)
-            pad[:n] = src[:n]
-            dist.gather(pad, list(dst.chunk(world)) if rank == 0 else None, dst=0)
-        if rank == 0:
-            keep = torch.cat([torch.arange(r * share, r * share + max(0, min(total, (r + 1) * share) - r * share), device=dev) for r in range(world)])
-            vecs = [p[keep] for p in parts]
+        for src, dst in zip((real1, real2, scr1, scr2), gathered):
+            dist.gather(src[:share] if n == share else torch.cat([src[:n], src.new_zeros(share - n)]),
+                        list(dst.chunk(world)) if rank == 0 else None, dst=0)
+        vecs = gathered
     else:
-        vecs = [real1[:n], real2[:n], scr1[:n], scr2[:n]]
+        vecs = [real1, real2, scr1, scr2]
     t_gather = time.perf_counter() - t0 - t_align
     if rank == 0:
         thr = (native.compute_threshold((vecs[0].data_ptr(), total), (vecs[2].data_ptr(), total), error, device=local),
