@@ -231,12 +231,16 @@ int sarlacc_chunk_adaptor_align(sarlacc_chunk* c, double gapopen, double gapext,
         int64_t out_pitch, int32_t* read_width, uint8_t* reversed,
         double* score1, int32_t* start1, int32_t* end1, int32_t* sec_start1, int32_t* sec_width1,
         double* score2, int32_t* start2, int32_t* end2, int32_t* sec_start2, int32_t* sec_width2);
-/* scramble != 0: both windows of every read are permuted first (.scramble_input, R/getAdaptorThresholds.R:68-92; the
+/* scramble == 1: both windows of every read are permuted first (.scramble_input, R/getAdaptorThresholds.R:68-92; the
  * permutation of read i depends on (seed, read_index[i] or first_index + i) only -- sarlacc_b200/api.py: _scramble_by_index
- * is the host mirror); scramble == 0 scores the windows as loaded (.get_alignment_scores, R/tuneAlignment.R:99-112).
- * score1 / score2 receive ifelse(is.reverse, revcomp score, forward score) per adaptor. */
+ * is the host mirror); scramble == 2 re-uses the permuted windows of the previous call (tuneAlignment scores one
+ * scramble under 35 penalty pairs, R/tuneAlignment.R:27-72); scramble == 0 scores the windows as loaded
+ * (.get_alignment_scores, R/tuneAlignment.R:99-112).  score1 / score2 receive ifelse(is.reverse, revcomp score, forward
+ * score) per adaptor (R/getAdaptorThresholds.R:123-127); strand_score receives .resolve_strand()$scores, the larger of
+ * the two strand sums (R/adaptorAlign.R:112-122), which is what tuneAlignment compares. */
 int sarlacc_chunk_scrambled_scores(sarlacc_chunk* c, double gapopen, double gapext, const char* adaptor1, const char* adaptor2,
-        uint64_t seed, uint64_t first_index, const uint64_t* read_index, int scramble, double* score1, double* score2);
+        uint64_t seed, uint64_t first_index, const uint64_t* read_index, int scramble, double* score1, double* score2,
+        double* strand_score);
 int sarlacc_chunk_sync(sarlacc_chunk* c);
 /* The chunk's compute stream (a cudaStream_t as void*), and a join that makes it wait for everything enqueued so far on
  * the chunk's traceback and copy streams: an event recorded on the stream after sarlacc_chunk_join marks the completion of
@@ -257,6 +261,9 @@ const char* sarlacc_chunk_last_kernel(const sarlacc_chunk* c, int adaptor);   /*
  * vectors may live on the host or on `device` (e.g. gathered from all ranks); they are not modified. */
 int sarlacc_compute_threshold(const double* real, int64_t nreal, const double* scrambled, int64_t nscr, double error,
                               int device, double* threshold);
+/* .tied_overlap (R/tuneAlignment.R:78-86): sum((findInterval(real, fake) + findInterval(real, fake, left.open=TRUE)) / 2)
+ * / (length(real) * length(fake)) with fake sorted on the device; vectors on the host or on `device`. */
+int sarlacc_tied_overlap(const double* real, int64_t nreal, const double* fake, int64_t nfake, int device, double* overlap);
 
 /* ---- UMI grouping ----------------------------------------------------------------
  * Replaces SEXP umi_group(umi1, thresh1, umi2, thresh2, pregroup) (src/umi_group.cpp:14-117, registered at

@@ -121,7 +121,8 @@ def _load():
                                                  C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64] +
                                                 [C.c_void_p] * 12)
     lib.sarlacc_chunk_scrambled_scores.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_char_p, C.c_char_p,
-                                                   C.c_uint64, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+                                                   C.c_uint64, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sarlacc_tied_overlap.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
     lib.sarlacc_chunk_sync.argtypes = [C.c_void_p]
     lib.sarlacc_chunk_join.argtypes = [C.c_void_p]
     lib.sarlacc_chunk_stream.restype = C.c_void_p

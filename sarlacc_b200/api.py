@@ -295,7 +295,7 @@ def _stream(source, number, keep=None):
         for lo in range(0, n, number):
             idx = np.arange(lo, min(n, lo + number))
             yield source[idx], None
-    elif keep is not None and int(keep) >= 1 and not str(source).endswith(".gz"):
+    elif keep is not None and int(keep) >= 1:
         yield from _prefetch(read_fastq_condensed(source, keep, number))
     else:
         for reads in read_fastq(source, number):
@@ -469,26 +469,6 @@ def _align_AT_internal(reads, adaptor1, adaptor2, tolerance, gap_opening, gap_ex
             "adaptor2": np.where(is_reverse, sc["REND"], sc["END"])}
 
 
-def _scrambled_scores_device(front, back, adaptor1, adaptor2, go, ge, enc, seed, read_index):
-    """.align_AT_internal's scramble + four score-only alignments with the windows resident in HBM: packed once,
-    permuted on the device (sarlacc_resident_scrambled), scored four times."""
-    rf = native.Resident(front, enc)
-    rb = native.Resident(back, enc)
-    sf = rf.scrambled(seed, read_index=read_index, stream_id=0)
-    sb = rb.scrambled(seed, read_index=read_index, stream_id=1)
-    rf.close()
-    rb.close()
-    out = {}
-    try:
-        for key, r, a in (("START", sf, adaptor1), ("END", sb, adaptor2), ("RSTART", sb, adaptor1), ("REND", sf, adaptor2)):
-            r.align(r.MODE_SCORE_LOCAL, go, ge, a)
-            out[key] = r.fetch()
-    finally:
-        sf.close()
-        sb.close()
-    return out
-
-
 def getAdaptorThresholds(aligned, error=0.01, number=1e5, seed=0, device_scramble=True):
     """R/getAdaptorThresholds.R:6-66.  device_scramble=True permutes the windows on the GPU; False builds the same
     keyed permutation with numpy and goes through the reference's four score-only .Calls.  Identical results."""
@@ -502,33 +482,46 @@ def getAdaptorThresholds(aligned, error=0.01, number=1e5, seed=0, device_scrambl
     wanted = {nm: k for k, nm in enumerate(aligned.rownames)}
     scr1, scr2, used = [], [], []
     seen = 0
-    for reads, _ in _stream(filepath, number, keep=int(tolerance)):     # thresholds only look at the windows
-        keep = np.array([nm in wanted for nm in reads.names], dtype=bool)
-        first_index = seen
-        seen += len(reads)
-        idx = np.nonzero(keep)[0]
-        sub = reads[idx]
-        used.extend(sub.names)
-        if len(sub) == 0:
-            continue
-        # the scramble is keyed by the read's position in the file, so dropping reads does not shift others
-        w = _get_front_and_back(sub, tolerance)
-        if device_scramble:
-            sc = _scrambled_scores_device(w["front"], w["back"], adaptor1, adaptor2, go, ge, enc, seed, first_index + idx)
-        else:
+    chunk = None      # device path: one chunk object re-loaded per FASTQ chunk (.align_AT_internal = sarlacc_chunk_scrambled_scores)
+    try:
+        for reads, _ in _stream(filepath, number, keep=int(tolerance)):     # thresholds only look at the windows
+            keep = np.array([nm in wanted for nm in reads.names], dtype=bool)
+            first_index = seen
+            seen += len(reads)
+            idx = np.nonzero(keep)[0]
+            sub = reads[idx]
+            used.extend(sub.names)
+            if len(sub) == 0:
+                continue
+            # the scramble is keyed by the read's position in the file, so dropping reads does not shift others
+            if device_scramble and int(tolerance) >= 1:
+                if chunk is None or chunk.capacity < len(sub):
+                    if chunk is not None:
+                        chunk.close()
+                    chunk = native.Chunk(max(len(sub), int(number)), int(tolerance), enc)
+                chunk.load_reads(sub, int(tolerance))
+                a1s, a2s = chunk.scrambled_scores(go, ge, adaptor1, adaptor2, seed=seed, read_index=first_index + idx)
+                scr1.append(a1s)
+                scr2.append(a2s)
+                continue
+            w = _get_front_and_back(sub, tolerance)
             scr_start = _scramble_by_index(w["front"], seed, first_index + idx, 0)
             scr_end = _scramble_by_index(w["back"], seed, first_index + idx, 1)
             sc = _get_alignment_scores(scr_start, scr_end, adaptor1, adaptor2, go, ge, enc)
-        is_reverse = _resolve_strand(sc["START"], sc["END"], sc["RSTART"], sc["REND"])["reversed"]
-        scr1.append(np.where(is_reverse, sc["RSTART"], sc["START"]))
-        scr2.append(np.where(is_reverse, sc["REND"], sc["END"]))
+            is_reverse = _resolve_strand(sc["START"], sc["END"], sc["RSTART"], sc["REND"])["reversed"]
+            scr1.append(np.where(is_reverse, sc["RSTART"], sc["START"]))
+            scr2.append(np.where(is_reverse, sc["REND"], sc["END"]))
+    finally:
+        if chunk is not None:
+            chunk.close()
     scram1 = np.concatenate(scr1) if scr1 else np.zeros(0)
     scram2 = np.concatenate(scr2) if scr2 else np.zeros(0)
     m = np.array([wanted[nm] for nm in used], dtype=np.int64)
     real1 = aligned["adaptor1"]["score"][m]
     real2 = aligned["adaptor2"]["score"][m]
-    return {"threshold1": _compute_threshold(real1, scram1, error),
-            "threshold2": _compute_threshold(real2, scram2, error),
+    select = native.compute_threshold if (device_scramble and len(real1)) else _compute_threshold     # same numbers (tests)
+    return {"threshold1": select(real1, scram1, error),
+            "threshold2": select(real2, scram2, error),
             "scores1": {"reads": real1, "scrambled": scram1},
             "scores2": {"reads": real2, "scrambled": scram2}}
 
@@ -569,49 +562,116 @@ def _tied_overlap(real, fake):
     return float(np.sum((upper + lower) / 2.0) / (len(real) * len(fake)))
 
 
+def _sample_reads(source, number, tolerance, seed):
+    """FastqSampler(filepath, number) + yield (R/tuneAlignment.R:21): a uniform random sample of `number` reads, in file
+    order.  R's RNG stream cannot be reproduced outside R; the sample here is reservoir sampling (algorithm R) driven by
+    numpy's Philox generator keyed by `seed` -- one pass over the stream, like FastqSampler."""
+    number = int(number)
+    rng = np.random.Generator(np.random.Philox(key=int(seed)))
+    kept = None         # ReadSet of at most `number` reads
+    order = None        # their positions in the stream
+    seen = 0
+    for chunk, _ in _stream(source, max(number, 100000), keep=int(tolerance) if int(tolerance) >= 1 else None):
+        m = len(chunk)
+        pos = seen + np.arange(m)
+        if kept is None:
+            take = min(number, m)
+            kept, order = chunk[np.arange(take)], pos[:take].copy()
+            rest = np.arange(take, m)
+        else:
+            rest = np.arange(m)
+            if len(kept) < number:
+                take = min(number - len(kept), m)
+                kept = ReadSet.concat([kept, chunk[np.arange(take)]])
+                order = np.concatenate([order, pos[:take]])
+                rest = np.arange(take, m)
+        if len(rest):
+            # element at stream position t replaces a uniformly chosen slot with probability number / (t + 1)
+            j = (rng.random(len(rest)) * (pos[rest] + 1)).astype(np.int64)
+            hit = np.nonzero(j < number)[0]
+            if len(hit):
+                last = {}
+                for h in hit:                       # later replacements of the same slot win
+                    last[int(j[h])] = int(rest[h])
+                slots = np.array(sorted(last), dtype=np.int64)
+                src = np.array([last[int(k)] for k in slots], dtype=np.int64)
+                idx = np.arange(len(kept))
+                both = ReadSet.concat([kept, chunk[src]])
+                idx[slots] = len(kept) + np.arange(len(src))
+                kept = both[idx]
+                order[slots] = pos[src]
+        seen += m
+    if kept is None:
+        return ReadSet.empty()
+    return kept[np.argsort(order, kind="stable")]
+
+
 def tuneAlignment(adaptor1, adaptor2, filepath, tolerance=200, number=10000, gapOp_range=(4, 10), gapExt_range=(1, 5),
-                  qual_type="phred", seed=0):
-    """R/tuneAlignment.R:6-76.  The reference samples `number` reads with FastqSampler (R's RNG); here the first
-    `number` reads of the stream are used.  Windows and their scrambled versions are packed once and stay
-    resident in HBM across the 35-point grid."""
+                  qual_type="phred", seed=0, sample="random"):
+    """R/tuneAlignment.R:6-76.  sample="random": a uniform sample of `number` reads like FastqSampler's (our own RNG, see
+    _sample_reads); sample="first": the first `number` reads of the stream.  The sampled windows are loaded into one
+    device-resident chunk and scrambled once; all 35 (gapOpening, gapExtension) points x {reads, scrambled} x 4
+    alignments are enqueued back to back with the scores kept on the device, .tied_overlap runs there too, and only the
+    winning pair's score vectors come back."""
     adaptor1 = str(adaptor1).upper()
     adaptor2 = str(adaptor2).upper()
     enc = _create_encoding_vector(_qual2class(qual_type))
-    reads = None
-    for chunk, _ in _stream(filepath, number, keep=int(tolerance)):
-        reads = chunk
-        break
+    if sample == "random":
+        reads = _sample_reads(filepath, number, tolerance, seed)
+    else:
+        reads = None
+        for chunk, _ in _stream(filepath, number, keep=int(tolerance) if int(tolerance) >= 1 else None):
+            reads = chunk
+            break
     if reads is None or len(reads) == 0:
         return {"parameters": {"gapOpening": None, "gapExtension": None},
                 "scores": {"reads": np.zeros(0), "scrambled": np.zeros(0)}}
+    go_r = np.maximum.accumulate(np.asarray(gapOp_range, dtype=int))
+    ge_r = np.maximum.accumulate(np.asarray(gapExt_range, dtype=int))
+    grid = [(go, ge) for go in range(int(go_r[0]), int(go_r[1]) + 1) for ge in range(int(ge_r[0]), int(ge_r[1]) + 1)]
+    if int(tolerance) < 1 or len(adaptor1) == 0 or len(adaptor2) == 0:
+        return _tune_alignment_host(reads, adaptor1, adaptor2, tolerance, grid, enc, seed)
+    import torch
+    n = len(reads)
+    ch = native.Chunk(n, int(tolerance), enc)
+    try:
+        ch.load_reads(reads, int(tolerance))
+        dev = torch.device("cuda", ch.device)
+        real = torch.empty((len(grid), n), dtype=torch.float64, device=dev)
+        fake = torch.empty((len(grid), n), dtype=torch.float64, device=dev)
+        for k, (go, ge) in enumerate(grid):
+            ch.scrambled_scores(go, ge, adaptor1, adaptor2, scramble=False, strand_score=real[k].data_ptr())
+            ch.scrambled_scores(go, ge, adaptor1, adaptor2, seed=seed, first_index=0, scramble=True if k == 0 else "reuse",
+                                strand_score=fake[k].data_ptr())
+        ch.sync()
+        max_score, final = 0.0, None
+        for k, (go, ge) in enumerate(grid):
+            cur = native.tied_overlap((real[k].data_ptr(), n), (fake[k].data_ptr(), n), device=ch.device)
+            if max_score < cur:
+                max_score, final = cur, k
+        if final is None:
+            return {"parameters": {"gapOpening": None, "gapExtension": None}, "scores": {"reads": None, "scrambled": None}}
+        return {"parameters": {"gapOpening": grid[final][0], "gapExtension": grid[final][1]},
+                "scores": {"reads": real[final].cpu().numpy(), "scrambled": fake[final].cpu().numpy()}}
+    finally:
+        ch.close()
+
+
+def _tune_alignment_host(reads, adaptor1, adaptor2, tolerance, grid, enc, seed):
+    """The reference's own loop (R/tuneAlignment.R:54-72) over the four score-only calls: degenerate inputs
+    (tolerance 0, an empty adaptor) that the chunk engine does not take."""
     w = _get_front_and_back(reads, tolerance)
     scr_start = _scramble_input(w["front"], True, seed, 0, 0)
     scr_end = _scramble_input(w["back"], True, seed, 0, 1)
-    res = {k: native.Resident(v, enc) for k, v in
-           dict(start=w["front"], end=w["back"], sstart=scr_start, send=scr_end).items()}
-    go_r = np.maximum.accumulate(np.asarray(gapOp_range, dtype=int))
-    ge_r = np.maximum.accumulate(np.asarray(gapExt_range, dtype=int))
     max_score, final = 0.0, None
-
-    def scores(rs, re_, go, ge):
-        out = {}
-        for key, r, a in (("START", rs, adaptor1), ("END", re_, adaptor2), ("RSTART", re_, adaptor1), ("REND", rs, adaptor2)):
-            r.align(r.MODE_SCORE_LOCAL, go, ge, a)
-            out[key] = r.fetch()
-        return _resolve_strand(out["START"], out["END"], out["RSTART"], out["REND"])["scores"]
-
-    try:
-        for go in range(int(go_r[0]), int(go_r[1]) + 1):
-            for ge in range(int(ge_r[0]), int(ge_r[1]) + 1):
-                read_scores = scores(res["start"], res["end"], go, ge)
-                scr_scores = scores(res["sstart"], res["send"], go, ge)
-                cur = _tied_overlap(read_scores, scr_scores)
-                if max_score < cur:
-                    max_score = cur
-                    final = (go, ge, read_scores, scr_scores)
-    finally:
-        for r in res.values():
-            r.close()
+    for go, ge in grid:
+        a = _get_alignment_scores(w["front"], w["back"], adaptor1, adaptor2, go, ge, enc)
+        b = _get_alignment_scores(scr_start, scr_end, adaptor1, adaptor2, go, ge, enc)
+        read_scores = _resolve_strand(a["START"], a["END"], a["RSTART"], a["REND"])["scores"]
+        scr_scores = _resolve_strand(b["START"], b["END"], b["RSTART"], b["REND"])["scores"]
+        cur = _tied_overlap(read_scores, scr_scores)
+        if max_score < cur:
+            max_score, final = cur, (go, ge, read_scores, scr_scores)
     if final is None:
         return {"parameters": {"gapOpening": None, "gapExtension": None}, "scores": {"reads": None, "scrambled": None}}
     return {"parameters": {"gapOpening": final[0], "gapExtension": final[1]},

@@ -18,6 +18,7 @@
 #include <nvtx3/nvToolsExt.h>     /* header-only; ranges cost nothing unless a profiler is attached */
 
 #include <sys/mman.h>
+#include <zlib.h>
 #include <sys/types.h>
 #include <unistd.h>
 
@@ -1110,6 +1111,7 @@ const char* run_pair_device(const Plan* const plan[2], const DevPlan* const D[2]
     SA.reversed = out.reversed;
     SA.score1 = out.score[0];
     SA.score2 = out.score[1];
+    SA.strand_score = nullptr;
     launch_resolve_strand(SA, st);
     g_launches += 1;
     CUDA_CHECK(cudaEventRecord(fwd_done, st));
@@ -2357,6 +2359,7 @@ int sarlacc_pack_rows(const sarlacc_reads* reads, const sarlacc_encoding* encodi
  * qualities), ready to be passed back in as a sarlacc_reads.  Plain text only; host code, excluded from timings. */
 struct sarlacc_fastq {
     FILE* fh = nullptr;
+    gzFile gz = nullptr;          /* gzip-compressed input (ShortRead reads .gz transparently, R/adaptorAlign.R:26): inflated by zlib as it is read */
     std::vector<char> buf;
     size_t pos = 0, end = 0;
     bool eof = false;
@@ -2376,7 +2379,13 @@ struct sarlacc_fastq {
             pos = 0;
         }
         if (end == buf.size()) buf.resize(buf.size() * 2);
-        const size_t got = std::fread(buf.data() + end, 1, buf.size() - end, fh);
+        size_t got = 0;
+        if (gz) {
+            const int r = gzread(gz, buf.data() + end, (unsigned)std::min<size_t>(buf.size() - end, 1u << 30));
+            got = r > 0 ? (size_t)r : 0;
+        } else {
+            got = std::fread(buf.data() + end, 1, buf.size() - end, fh);
+        }
         if (got == 0) { eof = true; return false; }
         end += got;
         return true;
@@ -2412,12 +2421,26 @@ sarlacc_fastq* sarlacc_fastq_open(const char* path) {
     sarlacc_fastq* f = new sarlacc_fastq();
     f->fh = fh;
     f->buf.resize(1 << 22);
+    unsigned char magic[2] = {0, 0};
+    const size_t got = std::fread(magic, 1, 2, fh);
+    std::rewind(fh);
+    if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+        f->gz = gzopen(path, "rb");
+        if (!f->gz) {
+            std::fclose(fh);
+            delete f;
+            fail(std::string("cannot open gzip-compressed FASTQ file: ") + path);
+            return nullptr;
+        }
+        gzbuffer(f->gz, 1u << 20);
+    }
     return f;
 }
 
 void sarlacc_fastq_close(sarlacc_fastq* f) {
     if (!f) return;
     if (f->map && f->map_size) munmap(const_cast<char*>(f->map), f->map_size);
+    if (f->gz) gzclose(f->gz);
     if (f->fh) std::fclose(f->fh);
     delete f;
 }
@@ -2555,6 +2578,53 @@ int64_t sarlacc_fastq_next_condensed(sarlacc_fastq* f, int64_t max_reads, int ke
     if (!f) { fail("FASTQ handle is NULL"); return -1; }
     if (keep < 1) { fail("the number of bases to keep per read end must be positive"); return -1; }
     if (max_reads < 1) max_reads = 1;
+    if (f->gz) {
+        /* a gzip stream cannot be cut into ranges: records are parsed one after the other as zlib inflates them, and
+         * condensed on the fly (first and last `keep` bases; the whole read when it is no longer than 2 * keep) */
+        f->seq_pool.clear(); f->qual_pool.clear(); f->name_pool.clear(); f->width.clear();
+        f->seq_off.assign(1, 0); f->qual_off.assign(1, 0); f->name_off.assign(1, 0);
+        int64_t n = 0;
+        size_t b, e;
+        auto condense = [&](std::vector<uint8_t>& pool, size_t lo, size_t hi) {
+            const size_t len = hi - lo;
+            if (len <= 2 * (size_t)keep) {
+                pool.insert(pool.end(), f->buf.begin() + lo, f->buf.begin() + hi);
+            } else {
+                pool.insert(pool.end(), f->buf.begin() + lo, f->buf.begin() + lo + keep);
+                pool.insert(pool.end(), f->buf.begin() + hi - keep, f->buf.begin() + hi);
+            }
+        };
+        while (n < max_reads) {
+            if (!f->line(b, e)) break;
+            if (e == b) continue;
+            if (f->buf[b] != '@') { fail("malformed FASTQ record: header does not start with '@'"); return -1; }
+            f->name_pool.insert(f->name_pool.end(), f->buf.begin() + b + 1, f->buf.begin() + e);
+            f->name_off.push_back((int64_t)f->name_pool.size());
+            if (!f->line(b, e)) { fail("malformed FASTQ record: missing sequence line"); return -1; }
+            const size_t slen = e - b;
+            condense(f->seq_pool, b, e);
+            f->seq_off.push_back((int64_t)f->seq_pool.size());
+            if (!f->line(b, e) || e == b || f->buf[b] != '+') { fail("malformed FASTQ record: missing '+' line"); return -1; }
+            if (!f->line(b, e)) { fail("malformed FASTQ record: missing quality line"); return -1; }
+            if (e - b != slen) { fail("malformed FASTQ record: sequence and quality lengths differ"); return -1; }
+            condense(f->qual_pool, b, e);
+            f->qual_off.push_back((int64_t)f->qual_pool.size());
+            f->width.push_back((int32_t)slen);
+            ++n;
+        }
+        if (f->seq_pool.empty()) f->seq_pool.push_back(0);
+        if (f->qual_pool.empty()) f->qual_pool.push_back(0);
+        if (f->name_pool.empty()) f->name_pool.push_back(0);
+        if (f->width.empty()) f->width.push_back(0);
+        if (seq_pool) *seq_pool = f->seq_pool.data();
+        if (seq_off) *seq_off = f->seq_off.data();
+        if (qual_pool) *qual_pool = f->qual_pool.data();
+        if (qual_off) *qual_off = f->qual_off.data();
+        if (name_pool) *name_pool = f->name_pool.data();
+        if (name_off) *name_off = f->name_off.data();
+        if (width) *width = f->width.data();
+        return n;
+    }
     if (!f->map) {
         if (fseeko(f->fh, 0, SEEK_END) != 0) { fail("cannot seek in FASTQ file"); return -1; }
         const off_t sz = ftello(f->fh);
@@ -3016,7 +3086,7 @@ double sarlacc_resident_forward_ms(sarlacc_resident* r) {
  * so the copy-out of chunk k overlaps the alignment of chunk k+1. */
 struct sarlacc_chunk {
     int device = 0, sms = 0;
-    int64_t capacity = 0, n = 0;
+    int64_t capacity = 0, n = 0, scrambled_n = -1;
     int tol = 0, stride = 0, maxlen = 0;
     bool has_width = false;
     Encoding enc;
@@ -3296,6 +3366,7 @@ int sarlacc_chunk_load_mock(sarlacc_chunk* c, int64_t n, uint64_t first_index, u
         g_launches += 1;
         CUDA_CHECK(cudaGetLastError());
         c->n = n;
+        c->scrambled_n = -1;
         c->maxlen = c->tol;
         c->has_width = true;
     } catch (CudaError& e) {
@@ -3363,6 +3434,7 @@ int sarlacc_chunk_load_reads(sarlacc_chunk* c, const sarlacc_reads* front, const
             }
         }
         c->n = n;
+        c->scrambled_n = -1;
         c->maxlen = std::max(maxf, maxb);
     } catch (CudaError& e) {
         return fail(e.msg);
@@ -3488,7 +3560,7 @@ int sarlacc_chunk_adaptor_align(sarlacc_chunk* c, double gapopen, double gapext,
 }
 
 int sarlacc_chunk_scrambled_scores(sarlacc_chunk* c, double gapopen, double gapext, const char* adaptor1, const char* adaptor2,
-        uint64_t seed, uint64_t first_index, const uint64_t* read_index, int scramble, double* score1, double* score2)
+        uint64_t seed, uint64_t first_index, const uint64_t* read_index, int scramble, double* score1, double* score2, double* strand_score)
 {
     Range nvtx("sarlacc_chunk_scrambled_scores");
     if (chunk_check_loaded(c)) return 1;
@@ -3502,7 +3574,11 @@ int sarlacc_chunk_scrambled_scores(sarlacc_chunk* c, double gapopen, double gape
         if (cp[0]->plan.bad_col[0] >= 0 || cp[1]->plan.bad_col[0] >= 0) return fail(err_text(ERR_REF));
         const uint16_t* rf = c->rows_f.as<uint16_t>();
         const uint16_t* rb = c->rows_b.as<uint16_t>();
-        if (scramble) {
+        if (scramble == 2) {          /* the permuted windows of the previous call (tuneAlignment: one scramble, 35 penalty pairs) */
+            if (!c->srows_f.p || !c->srows_b.p || c->scrambled_n != n) return fail("no scrambled windows to reuse");
+            rf = c->srows_f.as<uint16_t>();
+            rb = c->srows_b.as<uint16_t>();
+        } else if (scramble) {
             const size_t bytes = sizeof(uint16_t) * (size_t)c->capacity * c->stride;
             c->srows_f.reserve(bytes);
             c->srows_b.reserve(bytes);
@@ -3525,6 +3601,7 @@ int sarlacc_chunk_scrambled_scores(sarlacc_chunk* c, double gapopen, double gape
             }
             rf = c->srows_f.as<uint16_t>();
             rb = c->srows_b.as<uint16_t>();
+            c->scrambled_n = n;
         }
         /* the four forward passes of .get_alignment_scores (R/tuneAlignment.R:99-112): START, END, RSTART, REND */
         chunk_mark(c, 3, true);
@@ -3538,9 +3615,10 @@ int sarlacc_chunk_scrambled_scores(sarlacc_chunk* c, double gapopen, double gape
                          on_front ? c->lens_f.as<int32_t>() : c->lens_b.as<int32_t>(), n, c->stride, c->maxlen, false, dev, c->sms);
         }
         /* kept scores: straight into device destinations, through a chunk buffer + the copy stream for host ones */
-        cudaPointerAttributes at1, at2;
+        cudaPointerAttributes at1, at2, at3;
         const bool dev1 = score1 && cudaPointerGetAttributes(&at1, score1) == cudaSuccess && at1.type == cudaMemoryTypeDevice;
         const bool dev2 = score2 && cudaPointerGetAttributes(&at2, score2) == cudaSuccess && at2.type == cudaMemoryTypeDevice;
+        const bool dev3 = strand_score && cudaPointerGetAttributes(&at3, strand_score) == cudaSuccess && at3.type == cudaMemoryTypeDevice;
         cudaGetLastError();
         const int w = c->sout_which;
         c->sout_which ^= 1;
@@ -3548,7 +3626,7 @@ int sarlacc_chunk_scrambled_scores(sarlacc_chunk* c, double gapopen, double gape
             CUDA_CHECK(cudaStreamWaitEvent(c->st, c->sout_copied[w], 0));
             c->sout_pending[w] = false;
         }
-        c->sout[w].reserve(sizeof(double) * 2 * (size_t)c->capacity);
+        c->sout[w].reserve(sizeof(double) * 3 * (size_t)c->capacity);
         double* own = c->sout[w].as<double>();
         StrandArgs SA;
         SA.n = n;
@@ -3557,17 +3635,19 @@ int sarlacc_chunk_scrambled_scores(sarlacc_chunk* c, double gapopen, double gape
         SA.a1_back = tmp + (size_t)2 * n;
         SA.a2_front = tmp + (size_t)3 * n;
         SA.reversed = nullptr;
-        SA.score1 = dev1 ? score1 : own;
-        SA.score2 = dev2 ? score2 : own + c->capacity;
+        SA.score1 = dev1 ? score1 : (score1 ? own : nullptr);
+        SA.score2 = dev2 ? score2 : (score2 ? own + c->capacity : nullptr);
+        SA.strand_score = dev3 ? strand_score : (strand_score ? own + 2 * c->capacity : nullptr);
         launch_resolve_strand(SA, c->st);
         chunk_mark(c, 3, false);
         g_launches += 1;
         CUDA_CHECK(cudaGetLastError());
-        if ((score1 && !dev1) || (score2 && !dev2)) {
+        if ((score1 && !dev1) || (score2 && !dev2) || (strand_score && !dev3)) {
             CUDA_CHECK(cudaEventRecord(c->out_ready, c->st));
             CUDA_CHECK(cudaStreamWaitEvent(c->cp, c->out_ready, 0));
             if (score1 && !dev1) chunk_copy_out(c, score1, own, sizeof(double) * (size_t)n);
             if (score2 && !dev2) chunk_copy_out(c, score2, own + c->capacity, sizeof(double) * (size_t)n);
+            if (strand_score && !dev3) chunk_copy_out(c, strand_score, own + 2 * c->capacity, sizeof(double) * (size_t)n);
             CUDA_CHECK(cudaEventRecord(c->sout_copied[w], c->cp));
             c->sout_pending[w] = true;
         }

@@ -1132,8 +1132,9 @@ __global__ void resolve_strand(const StrandArgs S)
     const double r = __dadd_rn(fmax(r1, 0.0), fmax(r2, 0.0));
     const bool rev = f < r;
     if (S.reversed) S.reversed[i] = rev ? 1 : 0;
-    S.score1[i] = rev ? r1 : s1;
-    S.score2[i] = rev ? r2 : s2;
+    if (S.score1) S.score1[i] = rev ? r1 : s1;
+    if (S.score2) S.score2[i] = rev ? r2 : s2;
+    if (S.strand_score) S.strand_score[i] = rev ? r : f;
 }
 
 /* ---- counter-based randomness shared by the scramble and the synthetic-read generator ----------------------------

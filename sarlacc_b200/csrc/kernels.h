@@ -140,7 +140,8 @@ struct StrandArgs {
     long long n;
     const double* a1_front; const double* a2_back; const double* a1_back; const double* a2_front;
     uint8_t* reversed;
-    double* score1; double* score2;
+    double* score1; double* score2;       /* ifelse(is.reverse, revcomp, forward) per adaptor; may be null */
+    double* strand_score;                 /* .resolve_strand()$scores = ifelse(is.reverse, rscore, fscore); may be null */
 };
 void launch_resolve_strand(const StrandArgs& s, cudaStream_t st);
 

@@ -56,6 +56,27 @@ __global__ void __launch_bounds__(256) fdr_first_index(const double* real, long 
     if ((threadIdx.x & 31) == 0 && best < nr) atomicMin(first, (unsigned long long)best);
 }
 
+/* findInterval(x, v, left.open=TRUE) = number of elements < x. */
+__device__ __forceinline__ long long count_lt(const double* v, long long n, double x) {
+    long long lo = 0, hi = n;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (v[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) tied_overlap_sum(const double* real, long long nr, const double* fake, long long nf, unsigned long long* sum)
+{
+    unsigned long long mine = 0;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nr; k += (long long)gridDim.x * blockDim.x) {
+        const double x = real[k];
+        mine += (unsigned long long)(count_le(fake, nf, x) + count_lt(fake, nf, x));
+    }
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(sum, mine);
+}
+
 struct Tmp {
     void* p = nullptr;
     ~Tmp() { if (p) cudaFree(p); }
@@ -120,6 +141,51 @@ extern "C" int sarlacc_compute_threshold(const double* real, int64_t nreal, cons
     if (k != none) TH_CHECK(cudaMemcpy(threshold, (const double*)r_out.p + k, sizeof(double), cudaMemcpyDeviceToHost));
     if (dbg) std::fprintf(stderr, "[sarlacc] compute_threshold: %lld real, %lld scrambled scores: alloc %.2f ms, copy + sorts %.2f ms, scan %.2f ms (first index %lld)\n",
                           (long long)nreal, (long long)nscr, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (now() - t2) * 1e3, k == none ? -1LL : (long long)k);
+#undef TH_CHECK
+    return 0;
+}
+
+extern "C" int sarlacc_tied_overlap(const double* real, int64_t nreal, const double* fake, int64_t nfake, int device, double* overlap)
+{
+    if (!overlap) return sarlacc::set_error("overlap must not be NULL");
+    if (nreal < 0 || nfake < 0 || (nreal > 0 && !real) || (nfake > 0 && !fake)) return sarlacc::set_error("score vectors must not be NULL");
+    *overlap = std::numeric_limits<double>::quiet_NaN();      /* 0 / 0 in R */
+    if (nreal == 0 || nfake == 0) return 0;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        return sarlacc::set_error("sarlacc_b200 requires a CUDA device (no CPU fallback exists): no device found");
+    }
+#define TH_CHECK(expr)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t e_ = (expr);                                                                            \
+        if (e_ != cudaSuccess) return sarlacc::set_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #expr); \
+    } while (0)
+    TH_CHECK(cudaSetDevice(device));
+    Tmp r_in, f_in, f_out, work, sum;
+    const size_t rb = sizeof(double) * (size_t)nreal, fb = sizeof(double) * (size_t)nfake;
+    TH_CHECK(r_in.alloc(rb));
+    TH_CHECK(f_in.alloc(fb));
+    TH_CHECK(f_out.alloc(fb));
+    TH_CHECK(sum.alloc(sizeof(unsigned long long)));
+    TH_CHECK(cudaMemcpy(r_in.p, real, rb, cudaMemcpyDefault));
+    TH_CHECK(cudaMemcpy(f_in.p, fake, fb, cudaMemcpyDefault));
+    size_t wbytes = 0;
+    TH_CHECK(cub::DeviceRadixSort::SortKeys(nullptr, wbytes, (const double*)f_in.p, (double*)f_out.p, (long long)nfake));
+    TH_CHECK(work.alloc(wbytes));
+    TH_CHECK(cub::DeviceRadixSort::SortKeys(work.p, wbytes, (const double*)f_in.p, (double*)f_out.p, (long long)nfake));
+    TH_CHECK(cudaMemset(sum.p, 0, sizeof(unsigned long long)));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    long long grid = (nreal + 255) / 256;
+    if (grid > (long long)sms * 8) grid = (long long)sms * 8;
+    tied_overlap_sum<<<(int)grid, 256>>>((const double*)r_in.p, (long long)nreal, (const double*)f_out.p, (long long)nfake, (unsigned long long*)sum.p);
+    sarlacc::count_launches(1);
+    TH_CHECK(cudaGetLastError());
+    unsigned long long total = 0;
+    TH_CHECK(cudaMemcpy(&total, sum.p, sizeof(total), cudaMemcpyDeviceToHost));
+    /* every term (upper + lower) / 2 is a multiple of 0.5 and the sum stays far below 2^53, so R's double sum is exact */
+    *overlap = ((double)total / 2.0) / ((double)nreal * (double)nfake);
 #undef TH_CHECK
     return 0;
 }

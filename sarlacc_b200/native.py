@@ -530,19 +530,22 @@ class Chunk:
         return out["width"][:n], out["reversed"][:n].view(np.bool_), res[0], res[1]
 
     def scrambled_scores(self, gapopen, gapext, adaptor1, adaptor2, seed=0, first_index=0, read_index=None, scramble=True,
-                         score1=None, score2=None):
-        """.align_AT_internal (scramble=True) or .get_alignment_scores + .resolve_strand on the windows as loaded.  Without
-        destinations, fresh arrays are allocated, the call is synchronised and (score1, score2) returned."""
-        own = score1 is None and score2 is None
+                         score1=None, score2=None, strand_score=None):
+        """.align_AT_internal (scramble=True), the same on the windows scrambled by the previous call (scramble="reuse"), or
+        .get_alignment_scores + .resolve_strand on the windows as loaded (scramble=False).  score1 / score2: the kept score
+        per adaptor; strand_score: .resolve_strand()$scores.  Without destinations, fresh arrays are allocated, the call is
+        synchronised and (score1, score2) returned."""
+        own = score1 is None and score2 is None and strand_score is None
         n = self.n
         if own:
             score1, score2 = np.empty(n, np.float64), np.empty(n, np.float64)
         idx = None if read_index is None else np.ascontiguousarray(read_index, dtype=np.uint64)
-        self._keep = [score1, score2, idx]
+        self._keep = [score1, score2, strand_score, idx]
+        mode = 2 if scramble == "reuse" else (1 if scramble else 0)
         _lib.check(_lib.lib.sarlacc_chunk_scrambled_scores(
             self.handle, C.c_double(float(gapopen)), C.c_double(float(gapext)), adaptor1.encode("latin-1"), adaptor2.encode("latin-1"),
-            C.c_uint64(int(seed)), C.c_uint64(int(first_index)), _lib._ptr(idx), C.c_int(1 if scramble else 0),
-            _out_ptr(score1), _out_ptr(score2)))
+            C.c_uint64(int(seed)), C.c_uint64(int(first_index)), _lib._ptr(idx), C.c_int(mode),
+            _out_ptr(score1), _out_ptr(score2), _out_ptr(strand_score)))
         if own:
             self.sync()
             return score1, score2
@@ -604,4 +607,18 @@ def compute_threshold(real, scrambled, error, device=0):
     sp, sn, sk = arg(scrambled)
     out = np.zeros(1, np.float64)
     _lib.check(_lib.lib.sarlacc_compute_threshold(rp, C.c_int64(rn), sp, C.c_int64(sn), C.c_double(float(error)), C.c_int(device), _lib._ptr(out)))
+    return float(out[0])
+
+
+def tied_overlap(real, fake, device=0):
+    """.tied_overlap (R/tuneAlignment.R:78-86) on the device; numpy arrays or (device address, length) pairs."""
+    def arg(x):
+        if isinstance(x, tuple):
+            return C.c_void_p(int(x[0])), int(x[1]), None
+        a = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        return _lib._ptr(a), len(a), a
+    rp, rn, rk = arg(real)
+    fp, fn, fk = arg(fake)
+    out = np.zeros(1, np.float64)
+    _lib.check(_lib.lib.sarlacc_tied_overlap(rp, C.c_int64(rn), fp, C.c_int64(fn), C.c_int(device), _lib._ptr(out)))
     return float(out[0])

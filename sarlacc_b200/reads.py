@@ -4,7 +4,6 @@ A CSR container (byte pools + offsets) with exactly the operations the reference
 reads around the hot path: width, subseq, reverseComplement, subsetting, names
 (R/adaptorAlign.R:86-95,104-110,160-174).  Everything is vectorised numpy; nothing here aligns.
 """
-import gzip
 
 import numpy as np
 
@@ -240,28 +239,9 @@ def read_fastq_condensed(path, keep, number=None, nthreads=0):
 
 def read_fastq(path, number=None, skip=0):
     """FASTQ reader standing in for ShortRead::FastqStreamer + .FASTQ2QSDS (R/adaptorAlign.R:26,36,104-110).
-    Yields ReadSets of at most `number` reads; plain text goes through the library's reader, .gz through Python."""
-    if not str(path).endswith(".gz"):
-        yield from _read_fastq_native(path, number)
-        return
-    opener = gzip.open if str(path).endswith(".gz") else open
-    with opener(path, "rb") as fh:
-        names, seqs, quals = [], [], []
-        while True:
-            h = fh.readline()
-            if not h:
-                break
-            s = fh.readline().rstrip(b"\r\n")
-            fh.readline()
-            q = fh.readline().rstrip(b"\r\n")
-            names.append(h.rstrip(b"\r\n")[1:].decode("latin-1"))
-            seqs.append(s)
-            quals.append(q)
-            if number is not None and len(seqs) >= number:
-                yield ReadSet.from_strings(seqs, quals, names)
-                names, seqs, quals = [], [], []
-        if seqs:
-            yield ReadSet.from_strings(seqs, quals, names)
+    Yields ReadSets of at most `number` reads through the library's reader; gzip-compressed files are inflated by the
+    library as they are read (zlib), like ShortRead does."""
+    yield from _read_fastq_native(path, number)
 
 
 def write_fastq(path, reads, append=False):

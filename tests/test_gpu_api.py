@@ -434,3 +434,27 @@ def test_long_reads_and_long_references(port, enc):
     g = native.general_align((seqs[:10], quals[:10]), enc, 4, 1, ref)
     e = port.general_align(seqs[:10], quals[:10], enc, 4, 1, ref)
     assert np.array_equal(g[0], e[0]) and np.array_equal(g[1], e[1]) and g[2] == e[2] and g[3] == e[3]
+
+
+def test_tune_alignment_batched_equals_the_reference_loop(enc):
+    """The batched grid (one chunk, scores kept on the device, .tied_overlap there) picks the same point and returns the
+    same score vectors as the reference's loop over the four score-only calls + .resolve_strand + .tied_overlap on the
+    host (R/tuneAlignment.R:54-72) -- on a random sample of a larger read set."""
+    from sarlacc_b200 import api, native, synth
+    reads = synth.mock_reads(400, VIGNETTE_A1, VIGNETTE_A2, seed=5)
+    grid_args = dict(gapOp_range=(4, 6), gapExt_range=(1, 2), tolerance=150, number=150, seed=4)
+    out = api.tuneAlignment(VIGNETTE_A1, VIGNETTE_A2, reads, **grid_args)
+    sample = api._sample_reads(reads, 150, 150, 4)
+    assert len(sample) == 150 and len(set(sample.names)) == 150
+    grid = [(go, ge) for go in (4, 5, 6) for ge in (1, 2)]
+    ref = api._tune_alignment_host(sample, VIGNETTE_A1, VIGNETTE_A2, 150, grid, api._create_encoding_vector("PhredQuality"), 4)
+    assert out["parameters"] == ref["parameters"]
+    assert np.array_equal(out["scores"]["reads"], ref["scores"]["reads"]) and np.array_equal(out["scores"]["scrambled"], ref["scores"]["scrambled"])
+    assert out["scores"]["reads"].mean() > out["scores"]["scrambled"].mean() + 20
+    # .tied_overlap on the device == the R expression, ties included (tests/testthat/test-tuning.R:53-59)
+    rng = np.random.default_rng(1)
+    real, fake = np.round(rng.normal(5, 2, 5000), 1), np.round(rng.normal(4, 2, 3000), 1)
+    assert native.tied_overlap(real, fake) == api._tied_overlap(real, fake)
+    assert native.tied_overlap(np.array([1.0, 2.0]), np.array([1.0, 2.0])) == api._tied_overlap([1.0, 2.0], [1.0, 2.0]) == 0.5
+    first = api.tuneAlignment(VIGNETTE_A1, VIGNETTE_A2, reads, sample="first", **grid_args)
+    assert first["parameters"]["gapOpening"] in (4, 5, 6) and len(first["scores"]["reads"]) == 150

@@ -66,7 +66,7 @@ def test_fastq_round_trip(tmp_path):
     assert back.seq_strings() == a.seq_strings() and back.qual_strings() == a.qual_strings() and back.names == a.names
     open(str(tmp_path / "empty.fastq"), "w").close()
     assert list(read_fastq(str(tmp_path / "empty.fastq"), 10)) == []
-    # CRLF line ends, a missing final newline, an empty read, and the gzip path (Python reader)
+    # CRLF line ends, a missing final newline, an empty read, and gzip-compressed input (inflated by the library, zlib)
     with open(str(tmp_path / "crlf.fastq"), "wb") as fh:
         fh.write(b"@a\r\nACGT\r\n+\r\n!!!!\r\n@b\n\n+\n\n@c\nGG\n+c\n##")
     got = ReadSet.concat(list(read_fastq(str(tmp_path / "crlf.fastq"), 2)))
@@ -76,6 +76,14 @@ def test_fastq_round_trip(tmp_path):
         fh.write(open(p, "rb").read())
     gz = ReadSet.concat(list(read_fastq(str(tmp_path / "x.fastq.gz"), 2)))
     assert gz.seq_strings() == a.seq_strings() and gz.names == a.names
+    # the condensed (windows-only) ingest over the same gzip stream: names, widths and both windows of every read
+    from sarlacc_b200.reads import read_fastq_condensed
+    cond = list(read_fastq_condensed(str(tmp_path / "x.fastq.gz"), 3, 2))
+    crs = ReadSet.concat([c[0] for c in cond])
+    cw = np.concatenate([c[1] for c in cond])
+    assert crs.names == a.names and cw.tolist() == a.width().tolist()
+    for got, want in zip(crs.seq_strings(), a.seq_strings()):
+        assert got == (want if len(want) <= 6 else want[:3] + want[-3:])
     with open(str(tmp_path / "bad.fastq"), "wb") as fh:
         fh.write(b"@a\nACGT\nIIII\n")
     from sarlacc_b200 import SarlaccError
@@ -314,3 +322,21 @@ def test_condensed_fastq_ingest(tmp_path):
     empty = tmp_path / "empty.fastq"
     empty.write_bytes(b"")
     assert list(read_fastq_condensed(str(empty), 10)) == []
+
+
+def test_sample_reads_is_a_uniform_sample_in_stream_order():
+    """FastqSampler's job (R/tuneAlignment.R:21): `number` distinct reads, every read equally likely, stream order kept,
+    the same sample for the same seed whatever the chunking."""
+    from sarlacc_b200 import api, ReadSet
+    n = 3000
+    rs = ReadSet.from_strings(["ACGT" * 3] * n, ["5555" * 3] * n, ["r%d" % i for i in range(n)])
+    s = api._sample_reads(rs, 500, 250, seed=1)
+    pos = [int(x[1:]) for x in s.names]
+    assert len(pos) == 500 and len(set(pos)) == 500 and pos == sorted(pos)
+    assert api._sample_reads(rs, 500, 250, seed=1).names == s.names and api._sample_reads(rs, 500, 250, seed=2).names != s.names
+    hits = np.zeros(n)
+    for seed in range(40):
+        for x in api._sample_reads(rs, 300, 250, seed=seed).names:
+            hits[int(x[1:])] += 1
+    assert abs(hits[:1000].mean() - hits[2000:].mean()) < 0.6 and 3.0 < hits.mean() < 5.0     # 40 * 300 / 3000 = 4 per read
+    assert len(api._sample_reads(rs, 5000, 250, seed=0)) == n                                   # fewer reads than asked for: all of them

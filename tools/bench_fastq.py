@@ -48,5 +48,19 @@ try:
         dt = time.perf_counter() - t0
         print("api.adaptorAlign(path): %d reads in %.2f s = %.0f k reads/s; median adaptor1 score %.1f, %.1f%% reversed"
               % (len(out["reversed"]), dt, n / dt / 1e3, float(np.median(out["adaptor1"]["score"])), 100 * float(np.mean(out["reversed"]))))
+    # the same file gzip-compressed (ShortRead reads .gz transparently): a tenth of the reads, inflated by zlib in the library
+    import gzip
+    gzpath = path + ".gz"
+    m = max(1, n // 10)
+    with open(path, "rb") as src, gzip.open(gzpath, "wb", compresslevel=1) as dst:
+        for _ in range(4 * m):
+            dst.write(src.readline())
+    gsize = os.path.getsize(gzpath)
+    t0 = time.perf_counter()
+    k = sum(len(c) for c, _ in read_fastq_condensed(gzpath, 250, 100000))
+    dt = time.perf_counter() - t0
+    print("ingest, gzip (%.2f GB compressed), condensed: %d reads in %.2f s = %.0f k reads/s (%.2f GB/s inflated)"
+          % (gsize / 1e9, k, dt, k / dt / 1e3, size * (m / n) / dt / 1e9))
+    os.remove(gzpath)
 finally:
     os.remove(path)
