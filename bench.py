@@ -344,7 +344,7 @@ def main():
         torch.cuda.synchronize()
         dt = max_over_ranks((time.perf_counter() - t0) / reps)
         ph = {k: statistics.mean(p[k] for p in phases) for k in phases[0]}
-        ph_ranks = gather_ranks([ph["stage"], ph["enqueue"], ph["wait_copy_out"], ph["total"]])
+        ph_ranks = gather_ranks([ph["stage"], ph["enqueue"], ph["wait_copy_out"], ph["total"], ph["upload_sum"], ph["kernels_copyback_sum"]])
         # raw bases + qualities of both windows, two 8-byte offsets and a 4-byte length per window, read widths
         h2d = int(2 * (sub_f.seq_off[-1] + sub_b.seq_off[-1]) + 2 * ne * (16 + 4) + ne * 4)
         d2h = ne * (1 + (8 + 4 + 4 + 8 * len(s1)) + (8 + 4 + 4 + 8 * len(s2)))
@@ -367,7 +367,8 @@ def main():
                        "strand resolution + traceback of the kept strand on device -> D2H of the result columns (output arrays reused between calls)",
                "inputs_pinned": inputs_pinned, "pageable_inputs_reads_per_s": world * ne / dt_pageable,
                "host_threads_per_rank": max(1, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))),
-               "host_phases_ms_per_rank": [dict(zip(("stage", "enqueue", "wait_copy_out", "total"), r)) for r in ph_ranks],
+               "phases_ms_per_rank": [dict(zip(("host_stage", "host_enqueue", "host_wait_copy_out", "host_total", "device_upload_sum", "device_kernels_copyback_sum"), r)) for r in ph_ranks],
+               "upload_gbs_per_rank": [h2d / 1e6 / r[4] if r[4] > 0 else None for r in ph_ranks],
                "unfused_reads_per_s": world * ne / dt_unfused,
                "unfused_path": "4 x sarlacc_adaptor_align (the reference's four .Calls) + .resolve_strand on the host"}
 

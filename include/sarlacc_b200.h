@@ -86,9 +86,11 @@ int64_t sarlacc_kernel_launches(int reset);
 /* Device buffers released by the library are kept for reuse (SARLACC_POOL_MB, default 24576; 0 = off); this hands them
  * back to the driver. */
 void sarlacc_trim_device_memory(void);
-/* Host-side phases of the last sarlacc_adaptor_align_windows / _reads call (first device): staging and length scans,
- * enqueueing, waiting for results + copy-out, total -- milliseconds.  For bench.py's per-rank breakdown. */
-void sarlacc_last_pair_timing(double* ms4);
+/* Phases of the last sarlacc_adaptor_align_windows / _reads call (first device), milliseconds: host side -- staging and
+ * length scans, enqueueing, waiting for results + copy-out, total --, then two device-side sums over the call's chunks
+ * from CUDA events: upload (H2D + device packer) and kernels + copy back (chunks overlap, so these exceed the wall time).
+ * For bench.py's per-rank breakdown. */
+void sarlacc_last_pair_timing(double* ms6);
 
 /* ---- the four reference entry points (host buffers in, host buffers out) ------------------------- */
 

@@ -67,9 +67,10 @@ struct Range {
 
 }  // namespace
 
-namespace sarlacc {   /* for the other translation units of the library (umi.cu) */
+namespace sarlacc {   /* for the other translation units of the library (umi.cu, threshold.cu) */
 int set_error(const std::string& msg) { return fail(msg); }
 void count_launches(int n) { g_launches += n; }
+void threshold_trim();
 }
 
 namespace {
@@ -1800,7 +1801,7 @@ struct FinalLayout {
 /* Host-side phases of the last fused both-ends call on this thread's job 0 (bench.py reports them per rank):
  * staging / length scans, enqueueing, waiting for results + copying them out, total; milliseconds. */
 std::mutex g_pair_timing_mutex;
-double g_pair_timing[4] = {0, 0, 0, 0};
+double g_pair_timing[6] = {0, 0, 0, 0, 0, 0};
 
 struct PairJob {
     int device = 0;
@@ -1866,6 +1867,7 @@ struct PairJob {
         const bool dbg = std::getenv("SARLACC_DEBUG_TIMING") != nullptr;
         auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         const double t_start = now();
+        double t_h2d_ms = 0, t_dev_ms = 0;      /* summed over chunks: upload (incl. device packer) / kernels + copy back, from CUDA events */
         auto drain = [&](Slot& s, const FinalLayout& o) {
             if (!s.busy) return;
             Range nvtx("sarlacc: wait for chunk + copy out");
@@ -1875,12 +1877,14 @@ struct PairJob {
                 if (fb >= 0) err_front.offer(s.lo + fb, ERR_QUAL);
                 if (fb2 >= 0) err_back.offer(s.lo + fb2, ERR_QUAL);
             }
-            if (dbg) {
+            {
                 float a = 0, b = 0;
                 cudaEventElapsedTime(&a, s.t_begin, s.t_h2d);
                 cudaEventElapsedTime(&b, s.t_h2d, s.t_end);
-                std::fprintf(stderr, "[sarlacc]   chunk at %lld (%lld reads): H2D %.2f ms, kernels + D2H %.2f ms, host clock %.1f ms\n",
-                             (long long)s.lo, s.n, a, b, (now() - t_start) * 1e3);
+                t_h2d_ms += a;
+                t_dev_ms += b;
+                if (dbg) std::fprintf(stderr, "[sarlacc]   chunk at %lld (%lld reads): H2D %.2f ms, kernels + D2H %.2f ms, host clock %.1f ms\n",
+                                      (long long)s.lo, s.n, a, b, (now() - t_start) * 1e3);
             }
             const uint8_t* h = s.h_out.as<uint8_t>();
             const long long m = s.n;
@@ -1961,7 +1965,7 @@ struct PairJob {
             s.d_tmp.reserve(sizeof(double) * 4 * (size_t)m);      /* the four forward passes' scores */
             s.d_out.reserve(F.total);
             s.h_out.reserve(F.total);
-            if (dbg) CUDA_CHECK(cudaEventRecord(s.t_begin, s.st));
+            CUDA_CHECK(cudaEventRecord(s.t_begin, s.st));
             CUDA_CHECK(cudaMemcpyAsync(s.d_lens.p, s.h_lens.p, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
             CUDA_CHECK(cudaMemcpyAsync(s.d_lens2.p, s.h_lens2.p, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
             if (host_pack) {
@@ -1987,7 +1991,7 @@ struct PairJob {
                 }
                 CUDA_CHECK(cudaMemcpyAsync(s.d_width.p, s.h_width.p, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
             }
-            if (dbg) CUDA_CHECK(cudaEventRecord(s.t_h2d, s.st));
+            CUDA_CHECK(cudaEventRecord(s.t_h2d, s.st));
             if (prev_gate) CUDA_CHECK(cudaStreamWaitEvent(s.st, prev_gate, 0));
             uint8_t* d = s.d_out.as<uint8_t>();
             PairDeviceOut po;
@@ -2010,7 +2014,7 @@ struct PairJob {
             prev_gate = s.gate;
             CUDA_CHECK(cudaStreamWaitEvent(s.st, s.tb_ev[0], 0));
             CUDA_CHECK(cudaMemcpyAsync(s.h_out.p, s.d_out.p, F.total, cudaMemcpyDeviceToHost, s.st));
-            if (dbg) CUDA_CHECK(cudaEventRecord(s.t_end, s.st));
+            CUDA_CHECK(cudaEventRecord(s.t_end, s.st));
             CUDA_CHECK(cudaEventRecord(s.done, s.st));
             s.n = m;
             s.lo = c0;
@@ -2029,6 +2033,8 @@ struct PairJob {
             g_pair_timing[1] = t_enq * 1e3;
             g_pair_timing[2] = t_drain * 1e3;
             g_pair_timing[3] = (now() - t_start) * 1e3;
+            g_pair_timing[4] = t_h2d_ms;
+            g_pair_timing[5] = t_dev_ms;
         }
     }
 };
@@ -2071,12 +2077,15 @@ int sarlacc_set_host_threads(int nthreads) {
     return 0;
 }
 
-void sarlacc_trim_device_memory(void) { DevPool::instance().trim(); }
+void sarlacc_trim_device_memory(void) {
+    DevPool::instance().trim();
+    sarlacc::threshold_trim();
+}
 
-void sarlacc_last_pair_timing(double* ms4) {
-    if (!ms4) return;
+void sarlacc_last_pair_timing(double* ms6) {
+    if (!ms6) return;
     std::lock_guard<std::mutex> lock(g_pair_timing_mutex);
-    for (int k = 0; k < 4; ++k) ms4[k] = g_pair_timing[k];
+    for (int k = 0; k < 6; ++k) ms6[k] = g_pair_timing[k];
 }
 
 int64_t sarlacc_kernel_launches(int reset) {

@@ -19,11 +19,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <limits>
+#include <mutex>
 #include <string>
 
 namespace sarlacc {
 int set_error(const std::string& msg);
 void count_launches(int n);
+void threshold_trim();
 }
 
 namespace {
@@ -77,13 +79,52 @@ __global__ void __launch_bounds__(256) tied_overlap_sum(const double* real, long
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(sum, mine);
 }
 
-struct Tmp {
+/* Work buffers are kept between calls (per device, grow-only; handed back by sarlacc_trim_device_memory): cudaMalloc and
+ * cudaFree of a few hundred MB cost more than sorting them. */
+struct Cache {
+    std::mutex m;
+    struct Slot { void* p = nullptr; size_t cap = 0; int dev = -1; };
+    Slot slots[8][6];
+    void* get(int dev, int k, size_t bytes, cudaError_t* err) {
+        Slot& s = slots[dev & 7][k];
+        *err = cudaSuccess;
+        if (s.p && s.dev == dev && s.cap >= bytes) return s.p;
+        if (s.p) cudaFree(s.p);
+        s.p = nullptr;
+        s.cap = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        *err = cudaMalloc(&s.p, want);
+        if (*err != cudaSuccess) { s.p = nullptr; return nullptr; }
+        s.cap = want;
+        s.dev = dev;
+        return s.p;
+    }
+    void trim() {
+        std::lock_guard<std::mutex> lock(m);
+        for (auto& d : slots) for (auto& s : d) {
+            if (s.p) { cudaSetDevice(s.dev); cudaFree(s.p); }
+            s = Slot();
+        }
+    }
+};
+Cache& cache() {
+    static Cache* c = new Cache();      /* never destroyed: no CUDA calls during process teardown */
+    return *c;
+}
+
+struct Tmp {          /* one cached buffer, borrowed for the duration of a call (the cache mutex is held by the caller) */
     void* p = nullptr;
-    ~Tmp() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    int dev = 0, slot = 0;
+    cudaError_t alloc(size_t bytes) {
+        cudaError_t e;
+        p = cache().get(dev, slot, bytes ? bytes : 1, &e);
+        return e;
+    }
 };
 
 }  // namespace
+
+void sarlacc::threshold_trim() { cache().trim(); }
 
 extern "C" int sarlacc_compute_threshold(const double* real, int64_t nreal, const double* scrambled, int64_t nscr, double error,
                                          int device, double* threshold)
@@ -106,7 +147,8 @@ extern "C" int sarlacc_compute_threshold(const double* real, int64_t nreal, cons
     const bool dbg = std::getenv("SARLACC_DEBUG_TIMING") != nullptr;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
-    Tmp r_in, r_out, s_in, s_out, work, first;
+    std::lock_guard<std::mutex> lock(cache().m);
+    Tmp r_in{nullptr, device, 0}, r_out{nullptr, device, 1}, s_in{nullptr, device, 2}, s_out{nullptr, device, 3}, work{nullptr, device, 4}, first{nullptr, device, 5};
     const size_t rb = sizeof(double) * (size_t)nreal, sb = sizeof(double) * (size_t)nscr;
     TH_CHECK(r_in.alloc(rb));
     TH_CHECK(r_out.alloc(rb));
@@ -162,7 +204,8 @@ extern "C" int sarlacc_tied_overlap(const double* real, int64_t nreal, const dou
         if (e_ != cudaSuccess) return sarlacc::set_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #expr); \
     } while (0)
     TH_CHECK(cudaSetDevice(device));
-    Tmp r_in, f_in, f_out, work, sum;
+    std::lock_guard<std::mutex> lock(cache().m);
+    Tmp r_in{nullptr, device, 0}, f_in{nullptr, device, 2}, f_out{nullptr, device, 3}, work{nullptr, device, 4}, sum{nullptr, device, 5};
     const size_t rb = sizeof(double) * (size_t)nreal, fb = sizeof(double) * (size_t)nfake;
     TH_CHECK(r_in.alloc(rb));
     TH_CHECK(f_in.alloc(fb));

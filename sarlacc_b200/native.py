@@ -590,9 +590,9 @@ class Chunk:
 
 def last_pair_timing():
     """Host-side phases (ms) of the last fused both-ends host-buffer call: staging, enqueue, wait + copy-out, total."""
-    ms = np.zeros(4, np.float64)
+    ms = np.zeros(6, np.float64)
     _lib.lib.sarlacc_last_pair_timing(_lib._ptr(ms))
-    return dict(zip(("stage", "enqueue", "wait_copy_out", "total"), ms.tolist()))
+    return dict(zip(("stage", "enqueue", "wait_copy_out", "total", "upload_sum", "kernels_copyback_sum"), ms.tolist()))
 
 
 def compute_threshold(real, scrambled, error, device=0):

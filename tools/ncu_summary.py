@@ -9,6 +9,8 @@ rep = sys.argv[1]
 cells = float(sys.argv[2]) if len(sys.argv) > 2 else None
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
+first = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+rows = rows[first:]
 hdr, units = rows[0], rows[1]
 KEYS = [
     "gpu__time_duration.sum", "sm__cycles_elapsed.avg", "smsp__cycles_active.avg", "launch__grid_size", "launch__block_size",
@@ -22,8 +24,11 @@ KEYS = [
     "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "smsp__warps_eligible.avg.per_cycle_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
 ]
 for r in rows[2:]:
+    if len(r) != len(hdr):
+        continue
     d = dict(zip(hdr, r))
     u = dict(zip(hdr, units))
     print("kernel:", d.get("Kernel Name", "?")[:110])

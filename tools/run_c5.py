@@ -53,8 +53,9 @@ def run(total, chunk, rank, world, local, check_stride=0, error=0.01, timing=Tru
     gathered = [None] * 4
     if world > 1:       # receive buffers on rank 0 and one small gather, so that the timed one finds its channels set up
         gathered = [torch.empty(world * share, dtype=torch.float64, device=dev) if rank == 0 else None for _ in range(4)]
-        tiny = [torch.empty(world * 8, dtype=torch.float64, device=dev) if rank == 0 else None][0]
-        dist.gather(real1[:8].contiguous(), list(tiny.chunk(world)) if rank == 0 else None, dst=0)
+        dist.gather(real1[:share] if n == share else torch.cat([real1[:n], real1.new_zeros(share - n)]),
+                    list(gathered[0].chunk(world)) if rank == 0 else None, dst=0)     # same size as the timed ones: connections and buffers set up
+        torch.cuda.synchronize()
     ch.set_timing(timing)
     _lib.lib.sarlacc_kernel_launches(1)
     if world > 1:
