@@ -1207,8 +1207,31 @@ bool pointer_is_pinned(const void* p) {
 }
 
 /* Enqueues on `st`: upload of the raw bytes of windows [c0, c1) of V + the device packer writing d_rows. */
+/* The device packer of a staged window set and the read-back of its error flag, to be enqueued behind the uploads. */
+struct PendingPack {
+    PackArgs args;
+    RawStage* stage = nullptr;
+    bool check_qual = false;
+    bool valid = false;
+};
+
+void launch_pending_pack(PendingPack& P, cudaStream_t st) {
+    if (!P.valid) return;
+    launch_pack_rows(P.args, st);
+    g_launches += 1;
+    CUDA_CHECK(cudaMemcpyAsync(P.stage->h_bad.p, P.stage->d_bad.p, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    P.stage->bad_pending = P.check_qual;
+    P.valid = false;
+}
+
+/* With `defer` the packer is not launched here but handed back: a caller with two window sets enqueues BOTH uploads
+ * first and the two packers after them.  The packer has to wait for free SMs while a forward kernel of the previous
+ * chunk runs, and everything behind it on the stream waits with it -- the second window set's upload included, which
+ * left the copy engine idle for a kernel's length per chunk (N = 8: 11.6 GB/s per rank against 23 GB/s available,
+ * profiles/r02_history.md). */
 void stage_and_pack(const ReadView& V, int64_t c0, int64_t c1, const PackTables& T, const int32_t* h_lens, const int32_t* d_lens,
-        int stride, uint16_t* d_rows, bool check_qual, bool pools_pinned, RawStage& R, cudaStream_t st, int nthreads)
+        int stride, uint16_t* d_rows, bool check_qual, bool pools_pinned, RawStage& R, cudaStream_t st, int nthreads,
+        PendingPack* defer = nullptr)
 {
     const long long m = c1 - c0;
     if (m <= 0) return;
@@ -1295,10 +1318,13 @@ void stage_and_pack(const ReadView& V, int64_t c0, int64_t c1, const PackTables&
     std::memcpy(A.base, T.base, 256);
     std::memcpy(A.base_rc, T.base_rc, 256);
     std::memcpy(A.qidx, T.qidx, 512);
-    launch_pack_rows(A, st);
-    g_launches += 1;
-    CUDA_CHECK(cudaMemcpyAsync(R.h_bad.p, R.d_bad.p, sizeof(long long), cudaMemcpyDeviceToHost, st));
-    R.bad_pending = check_qual;
+    PendingPack own;
+    PendingPack& P = defer ? *defer : own;
+    P.args = A;
+    P.stage = &R;
+    P.check_qual = check_qual;
+    P.valid = true;
+    if (!defer) launch_pending_pack(P, st);
 }
 
 /* One pipeline slot: pinned staging + device buffers for a chunk of reads. */
@@ -1968,14 +1994,15 @@ struct PairJob {
             CUDA_CHECK(cudaEventRecord(s.t_begin, s.st));
             CUDA_CHECK(cudaMemcpyAsync(s.d_lens.p, s.h_lens.p, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
             CUDA_CHECK(cudaMemcpyAsync(s.d_lens2.p, s.h_lens2.p, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
+            PendingPack pf, pb;      /* both uploads first, then both packers (see stage_and_pack) */
             if (host_pack) {
                 CUDA_CHECK(cudaMemcpyAsync(s.d_rows.p, s.h_rows.p, sizeof(uint16_t) * (size_t)m * stride_f, cudaMemcpyHostToDevice, s.st));
                 CUDA_CHECK(cudaMemcpyAsync(s.d_rows2.p, s.h_rows2.p, sizeof(uint16_t) * (size_t)m * stride_b, cudaMemcpyHostToDevice, s.st));
             } else {
                 stage_and_pack(VF, c0, c1, PF, s.h_lens.as<int32_t>(), s.d_lens.as<int32_t>(), stride_f, s.d_rows.as<uint16_t>(), true,
-                               pinned_f, s.raw, s.st, nthreads);
+                               pinned_f, s.raw, s.st, nthreads, &pf);
                 stage_and_pack(VB, c0, c1, PB, s.h_lens2.as<int32_t>(), s.d_lens2.as<int32_t>(), stride_b, s.d_rows2.as<uint16_t>(), true,
-                               pinned_b, s.raw2, s.st, nthreads);
+                               pinned_b, s.raw2, s.st, nthreads, &pb);
             }
             if (width || tolerance > 0) {
                 s.h_width.reserve(sizeof(int32_t) * (size_t)m);
@@ -1991,7 +2018,9 @@ struct PairJob {
                 }
                 CUDA_CHECK(cudaMemcpyAsync(s.d_width.p, s.h_width.p, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
             }
-            CUDA_CHECK(cudaEventRecord(s.t_h2d, s.st));
+            CUDA_CHECK(cudaEventRecord(s.t_h2d, s.st));      /* uploads done; the device packers follow */
+            launch_pending_pack(pf, s.st);
+            launch_pending_pack(pb, s.st);
             if (prev_gate) CUDA_CHECK(cudaStreamWaitEvent(s.st, prev_gate, 0));
             uint8_t* d = s.d_out.as<uint8_t>();
             PairDeviceOut po;
@@ -3423,10 +3452,13 @@ int sarlacc_chunk_load_reads(sarlacc_chunk* c, const sarlacc_reads* front, const
             CUDA_CHECK(cudaMemcpyAsync(c->lens_b.p, c->h_lens_b.p, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->st));
             const bool pinned_f = !VF.R->seq && pointer_is_pinned(VF.R->seq_pool) && pointer_is_pinned(VF.R->qual_pool);
             const bool pinned_b = !VB.R->seq && pointer_is_pinned(VB.R->seq_pool) && pointer_is_pinned(VB.R->qual_pool);
+            PendingPack pf, pb;
             stage_and_pack(VF, 0, n, PF, c->h_lens_f.as<int32_t>(), c->lens_f.as<int32_t>(), c->stride, c->rows_f.as<uint16_t>(), true,
-                           pinned_f, c->raw_f, c->st, nthreads);
+                           pinned_f, c->raw_f, c->st, nthreads, &pf);
             stage_and_pack(VB, 0, n, PB, c->h_lens_b.as<int32_t>(), c->lens_b.as<int32_t>(), c->stride, c->rows_b.as<uint16_t>(), true,
-                           pinned_b, c->raw_b, c->st, nthreads);
+                           pinned_b, c->raw_b, c->st, nthreads, &pb);
+            launch_pending_pack(pf, c->st);
+            launch_pending_pack(pb, c->st);
             c->has_width = tolerance > 0 || width != nullptr;
             if (c->has_width) {
                 c->h_width.reserve(sizeof(int32_t) * (size_t)n);
