@@ -1342,7 +1342,6 @@ struct Slot {
     PinBuf h_rows2, h_lens2, h_width;     /* second window set + read widths of the fused both-ends entry */
     DevBuf d_rows2, d_lens2, d_width, d_tmp;
     Scratch scratch;
-    PairScratch pair;             /* the fused both-ends entry: four record sets, so that only the kept strand is walked */
     cudaStream_t tb = nullptr;    /* tracebacks of the fused entry */
     cudaEvent_t fwd_ev[4] = {nullptr, nullptr, nullptr, nullptr}, tb_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     RawStage raw, raw2;     /* raw bytes of the (first, second) window set on their way to the device packer */
@@ -1380,7 +1379,6 @@ struct Slot {
         }
         if (tb) cudaStreamDestroy(tb);
         tb = nullptr;
-        pair.release();
         if (t_begin) cudaEventDestroy(t_begin);
         if (t_h2d) cudaEventDestroy(t_h2d);
         if (t_end) cudaEventDestroy(t_end);
@@ -1424,7 +1422,21 @@ OutLayout make_layout(Mode mode, long long n, int nref_scores, int nsec, int max
 
 /* Per-device resources kept between host-buffer calls.  One call at a time per device (the R boundary is
  * single-threaded; concurrent callers serialise on the device's mutex). */
-constexpr int kSlots = 3;
+constexpr int kMaxSlots = 8;
+/* Pipeline depth of the host-buffer entries.  Three slots keep one GPU busy when the upload link is fast (while the device
+ * runs chunk k and chunk k+1's upload is in flight, the host stages chunk k+2).  With all eight GPUs of the box
+ * uploading at once a rank gets 23-35 GB/s instead of 55 (tools/h2d_probe.py), the upload of a chunk takes about as long
+ * as its kernels, and every pause of the copy engine -- it cannot start chunk k+3 before slot k has been drained --
+ * is lost time: five slots let the uploads run further ahead (SARLACC_SLOTS, 2..8). */
+int slot_count() {
+    static const int n = [] {
+        const char* e = std::getenv("SARLACC_SLOTS");
+        const int v = e ? std::atoi(e) : 5;
+        return v < 2 ? 2 : (v > kMaxSlots ? kMaxSlots : v);
+    }();
+    return n;
+}
+#define kSlots (slot_count())
 
 struct DeviceCache {
     std::mutex busy;
@@ -1432,8 +1444,12 @@ struct DeviceCache {
     /* three slots: while the device runs chunk k and chunk k+1's upload is in flight, the host packs chunk k+2
      * (with two, the upload of k+1 could only start after k-1 had finished and k+1 been packed: the device idled
      * ~2 ms of every 7.5 ms chunk period) */
-    Slot slots[kSlots];
+    Slot slots[kMaxSlots];
     DevPlan plan;
+    /* the fused both-ends entry: four record sets per chunk, two groups used alternately by consecutive chunks (the
+     * tracebacks of chunk k run beside the forward passes of chunk k+1) -- shared by all slots, a slot's own memory is
+     * its raw bytes, rows and result columns */
+    PairScratch pair[2];
 
     static DeviceCache& acquire(int device) {
         static std::mutex table_mutex;
@@ -1522,7 +1538,7 @@ struct DeviceJob {
         const char* ce = std::getenv("SARLACC_CHUNK");
         if (ce && std::atoll(ce) > 0) first_chunk = chunk = std::atoll(ce);
 
-        OutLayout lay[kSlots];
+        OutLayout lay[kMaxSlots];
         int which = 0;
         auto drain = [&](Slot& s, const OutLayout& o) {
             if (!s.busy) return;
@@ -1887,7 +1903,7 @@ struct PairJob {
         const char* ce = std::getenv("SARLACC_CHUNK");
         if (ce && std::atoll(ce) > 0) first_chunk = chunk = std::atoll(ce);
         auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-        FinalLayout lay[kSlots];
+        FinalLayout lay[kMaxSlots];
         int which = 0;
 
         const bool dbg = std::getenv("SARLACC_DEBUG_TIMING") != nullptr;
@@ -1930,6 +1946,8 @@ struct PairJob {
 
         double t_drain = 0, t_pack = 0, t_enq = 0;
         cudaEvent_t prev_gate = nullptr;
+        cudaEvent_t pair_free[2] = {nullptr, nullptr};     /* behind the tracebacks of the last chunk that used record group p */
+        int pair_turn = 0;
         const bool host_pack = std::getenv("SARLACC_HOST_PACK") != nullptr;     /* A/B: pack on the host as before */
         const bool pinned_f = !VF.R->seq && pointer_is_pinned(VF.R->seq_pool) && pointer_is_pinned(VF.R->qual_pool);
         const bool pinned_b = !VB.R->seq && pointer_is_pinned(VB.R->seq_pool) && pointer_is_pinned(VB.R->qual_pool);
@@ -2034,8 +2052,11 @@ struct PairJob {
             }
             po.pitch = m;
             const DevPlan* Dp[2] = {&D[0], &D[1]};
-            /* the slot's previous tracebacks finished before its results were drained, so its record sets are free */
-            run_pair_device(plan, Dp, s.pair, s.st, s.tb, s.fwd_ev[0], s.tb_ev[0],
+            const int pg = pair_turn;
+            pair_turn ^= 1;
+            if (pair_free[pg]) CUDA_CHECK(cudaStreamWaitEvent(s.st, pair_free[pg], 0));    /* chunk k-2's tracebacks read these records */
+            pair_free[pg] = s.tb_ev[0];
+            run_pair_device(plan, Dp, cache.pair[pg], s.st, s.tb, s.fwd_ev[0], s.tb_ev[0],
                             s.d_rows.as<uint16_t>(), s.d_lens.as<int32_t>(), stride_f, s.d_rows2.as<uint16_t>(), s.d_lens2.as<int32_t>(), stride_b,
                             m, std::max(maxf, maxb), (width || tolerance > 0) ? s.d_width.as<int32_t>() : nullptr,
                             s.d_tmp.as<double>(), po, sms);
