@@ -1423,15 +1423,15 @@ OutLayout make_layout(Mode mode, long long n, int nref_scores, int nsec, int max
 /* Per-device resources kept between host-buffer calls.  One call at a time per device (the R boundary is
  * single-threaded; concurrent callers serialise on the device's mutex). */
 constexpr int kMaxSlots = 8;
-/* Pipeline depth of the host-buffer entries.  Three slots keep one GPU busy when the upload link is fast (while the device
- * runs chunk k and chunk k+1's upload is in flight, the host stages chunk k+2).  With all eight GPUs of the box
- * uploading at once a rank gets 23-35 GB/s instead of 55 (tools/h2d_probe.py), the upload of a chunk takes about as long
- * as its kernels, and every pause of the copy engine -- it cannot start chunk k+3 before slot k has been drained --
- * is lost time: five slots let the uploads run further ahead (SARLACC_SLOTS, 2..8). */
+/* Pipeline depth of the host-buffer entries: three slots -- while the device runs chunk k and chunk k+1's upload is in
+ * flight, the host stages chunk k+2.  Deeper pipelines were tried for the 8-GPU case, where all ranks upload at once and
+ * a rank gets 23-35 GB/s instead of 55 (tools/h2d_probe.py): 5 and 7 slots were no faster (75 / 62 ms per 1 M reads on
+ * the slow / fast half of the GPUs with 3 slots, 78 / 67 with 5, 72 / 68 with 7; profiles/r02_history.md), so the limit
+ * there is the upload rate itself, not pauses of the copy engine.  SARLACC_SLOTS (2..8) overrides. */
 int slot_count() {
     static const int n = [] {
         const char* e = std::getenv("SARLACC_SLOTS");
-        const int v = e ? std::atoi(e) : 5;
+        const int v = e ? std::atoi(e) : 3;
         return v < 2 ? 2 : (v > kMaxSlots ? kMaxSlots : v);
     }();
     return n;
