@@ -930,6 +930,7 @@ FwdRec forward_once(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t st
     A.cost = D.cost;
     A.enc_n = P.enc->n;
     A.kinds = P.kinds;
+    A.one = 1u;
     const Geometry geo = geometry_for(P, maxlen, d_by_length != nullptr);
     R.geo = geo;
     A.index = d_by_length;

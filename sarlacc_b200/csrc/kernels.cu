@@ -149,8 +149,31 @@ __device__ __forceinline__ void land_step(int& lf0, int& lf1, bool pd, bool p5, 
 /* SHORT is chosen per instantiation (wf_forward2): measured on B200 (profiles/r02_history.md), the short chain gains
  * 5 % for the score-only solo kernel (1203 -> 1261 GCUPS on the 22-bp adaptor), nothing for the four-lane geometry, and
  * costs 14-16 % wherever trace records are written (the extra live predicates are materialised through SEL). */
+/* Records the predicate (a > b) as bit pattern BIT of the trace word f.
+ * The plain form, `if (a > b) f |= BIT`, compiles to a predicated add on the ALU pipe -- the pipe that already executes
+ * the eight FSEL of a cell and is the busiest unit of the row loop (56 %, `math_pipe_throttle` the third stall reason,
+ * profiles/r02_ncu_summary_a1_trace.txt) while the FMA pipe idles (15 %).  ON_FMA writes it as a predicated integer
+ * multiply-add f = BIT * one + f instead, `one` being a 1 the compiler cannot see through (a kernel argument), so that
+ * ptxas keeps an IMAD: the same instruction count, on the other pipe.  The comparison inside is the one the caller's
+ * select uses; ptxas merges the two DSETP. */
+#ifndef SARLACC_WF_TRACE_FMA
+#define SARLACC_WF_TRACE_FMA 0
+#endif
+__device__ __forceinline__ void trace_bit(uint32_t& f, unsigned bit, double a, double b, bool p, unsigned one) {
+#if SARLACC_WF_TRACE_FMA
+    (void)p;
+    asm("{ .reg .pred q;\n\t"
+        "setp.gt.f64 q, %1, %2;\n\t"
+        "@q mad.lo.u32 %0, %3, %4, %0; }"
+        : "+r"(f) : "d"(a), "d"(b), "r"(one), "r"(bit));      /* bit is a constant after unrolling: an immediate operand */
+#else
+    (void)a; (void)b; (void)one;
+    if (p) f |= bit;
+#endif
+}
+
 template <bool SHORT>
-__device__ __forceinline__ double pick_move(double h, double m, double v, bool& pd, bool& p5) {
+__device__ __forceinline__ double pick_move(double h, double m, double v, bool& pd, bool& p5, double* tmax = nullptr) {
     if constexpr (SHORT) {
         const bool pmv = m > v;
         const double mv = pmv ? m : v;
@@ -162,6 +185,7 @@ __device__ __forceinline__ double pick_move(double h, double m, double v, bool& 
         p5 = h > v;
         const double t = p5 ? h : v;
         pd = m > t;
+        if (tmax) *tmax = t;
         return pd ? m : t;
     }
 }
@@ -474,6 +498,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
     using WT = typename FlagWord<C>::type;
     static_assert(kSkew == 2, "the row-pair kernel lags its left neighbour by one two-row step: record layout and traceback assume SARLACC_WF_SKEW == 2");
     constexpr bool SHORT = (SOLO && !TRACE) || (SARLACC_WF_SHORT_CHAIN != 0);     /* see pick_move */
+    const unsigned one = A.one;
     extern __shared__ double smem_d[];
     const int L = A.L, nref = A.nref, encn = A.enc_n;
     double* row0s = smem_d;                                   /* [L+1]                         */
@@ -596,7 +621,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
                 mA[k] = __dadd_rn(diag, *slotp[k]);
                 diag = (k == 0 && skip0) ? diag0 : S[k];
                 if (k == C - 1) p2lastA = p2;
-                if (TRACE) { if (p2) fa[k >> 3] |= 8u << (4 * (k & 7)); }
+                if (TRACE) trace_bit(fa[k >> 3], 8u << (4 * (k & 7)), Fe, vO, p2, one);
             }
         }
         /* the two serial chains, interleaved: A(k) and B(k-1) */
@@ -613,7 +638,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
                     mAk = __dadd_rn(diagA, *slotp[k]);
                     diagA = (k == 0 && skip0) ? diag0 : S[k];
                     if (k == C - 1) p2lastA = p2A;
-                    if (TRACE) { if (p2A) fa[k >> 3] |= 8u << (4 * (k & 7)); }
+                    if (TRACE) trace_bit(fa[k >> 3], 8u << (4 * (k & 7)), Fe, vO, p2A, one);
                 } else {
                     mAk = mA[k];
                 }
@@ -622,7 +647,8 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
                 const bool p1 = Ee > hO;
                 const double h = p1 ? Ee : hO;
                 bool pd, p5;
-                const double Sn = pick_move<SHORT>(h, mAk, F[k], pd, p5);
+                double tA = 0.0;
+                const double Sn = pick_move<SHORT>(h, mAk, F[k], pd, p5, &tA);
                 S[k] = Sn;
                 SlA = Sn;
                 ElA = h;
@@ -632,9 +658,9 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
                 }
                 if (TRACE) {
                     const int sh = 4 * (k & 7);
-                    if (pd) fa[k >> 3] |= 1u << sh;
-                    if (p5) fa[k >> 3] |= 2u << sh;
-                    if (p1) fa[k >> 3] |= 4u << sh;
+                    trace_bit(fa[k >> 3], 1u << sh, mAk, tA, pd, one);
+                    trace_bit(fa[k >> 3], 2u << sh, h, F[k], p5, one);
+                    trace_bit(fa[k >> 3], 4u << sh, Ee, hO, p1, one);
                     if (k == C - 1) land_step(lf0, lf1, pd, p5, p2lastA, i + 1);
                 }
             }
@@ -654,7 +680,8 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
                 const bool p1 = Ee > hO;
                 const double h = p1 ? Ee : hO;
                 bool pd, p5;
-                const double Sn = pick_move<SHORT>(h, mB, vB, pd, p5);
+                double tB = 0.0;
+                const double Sn = pick_move<SHORT>(h, mB, vB, pd, p5, &tB);
                 if (MASKED) {
                     S[kk] = hasB ? Sn : SA;
                     F[kk] = hasB ? vB : FA;
@@ -670,10 +697,10 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
                 }
                 if (TRACE) {
                     const int sh = 4 * (kk & 7);
-                    if (p2) fb[kk >> 3] |= 8u << sh;
-                    if (pd) fb[kk >> 3] |= 1u << sh;
-                    if (p5) fb[kk >> 3] |= 2u << sh;
-                    if (p1) fb[kk >> 3] |= 4u << sh;
+                    trace_bit(fb[kk >> 3], 8u << sh, Fe, vO, p2, one);
+                    trace_bit(fb[kk >> 3], 1u << sh, mB, tB, pd, one);
+                    trace_bit(fb[kk >> 3], 2u << sh, h, vB, p5, one);
+                    trace_bit(fb[kk >> 3], 4u << sh, Ee, hO, p1, one);
                     if (kk == C - 1) {
                         if (MASKED) {
                             int t0 = lf0, t1 = lf1;

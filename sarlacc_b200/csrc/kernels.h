@@ -61,6 +61,7 @@ struct AlignArgs {
     /* wavefront geometry */
     int G, C;
     int pair_rows;            /* 1: wf_forward2 (two rows per lane step) */
+    unsigned one;             /* the value 1, opaque to the compiler (kernels.cu: trace_bit) */
     /* outputs */
     double* score;            /* [nref][n] (may be null when nref > 1 and only the reduction is wanted) */
     int32_t* best_id;         /* [n] multi-reference running best (R/barcodeAlign.R:28-34), nref > 1 only */
