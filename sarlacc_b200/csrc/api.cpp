@@ -770,8 +770,8 @@ struct Outputs {   /* device pointers; any may be null */
 
 /* Scratch for one in-flight run on one stream. */
 struct Scratch {
-    DevBuf flags, map, endrow, gS, gE, gC;
-    void release() { flags.release(); map.release(); endrow.release(); gS.release(); gE.release(); gC.release(); }
+    DevBuf flags, map, endrow, gS, gE, gC, next;
+    void release() { flags.release(); map.release(); endrow.release(); gS.release(); gE.release(); gC.release(); next.release(); }
 };
 
 size_t scratch_budget_bytes() {
@@ -898,6 +898,14 @@ struct FwdTimer {
     }
 };
 
+bool dynamic_distribution() {
+    static const bool on = [] {
+        const char* e = std::getenv("SARLACC_DYNAMIC");
+        return e ? std::atoi(e) != 0 : true;
+    }();
+    return on;
+}
+
 /* One forward launch over device-resident packed windows [0, m) (+ the scores of empty windows), with traceback records
  * into S when `trace`.  Returns what a traceback of these records needs. */
 struct FwdRec {
@@ -963,6 +971,12 @@ FwdRec forward_once(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t st
             R.wordbytes = 1;
         }
         A.flags = S.flags.p;
+    }
+    if (P.fast && geo.pair && P.nref == 1 && dynamic_distribution()) {
+        /* row-pair kernels take their alignments from a device counter: no tail round whatever the launch's length */
+        S.next.reserve(sizeof(unsigned long long));
+        CUDA_CHECK(cudaMemsetAsync(S.next.p, 0, sizeof(unsigned long long), st));
+        A.next = S.next.as<unsigned long long>();
     }
     if (timer) timer->begin(st);
     if (P.fast) {

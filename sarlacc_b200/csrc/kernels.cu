@@ -563,8 +563,14 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
 #pragma unroll
     for (int k = 0; k < C; ++k) { S[k] = 0.0; F[k] = NEG; }
     double outSA = 0.0, outEA = NEG, outSB = 0.0, outEB = NEG, diag0 = 0.0;
-    long long a = gidx - NG;     /* position in the processing order of the launch */
-    long long r = 0;             /* the read it stands for (AlignArgs::index) */
+    /* Static distribution: group g takes positions g, g + NG, ... of the processing order.  Dynamic (A.next): the group's
+     * first lane takes the next free position from a device counter when it starts an alignment, and lane j, which runs one
+     * step behind lane j-1, takes over lane j-1's position when its own alignment ends. */
+    /* (the bounds are re-read where they are needed -- bookkeeping only -- instead of being held in registers across the row loop) */
+    auto first_pos = [&]() -> long long { return (A.next && A.range) ? (long long)A.range[0] : 0; };
+    auto end_pos = [&]() -> long long { return (A.next && A.range) ? (long long)A.range[1] : A.n; };
+    long long a = A.next ? end_pos() : gidx - NG;     /* position in the processing order of the launch */
+    long long r = 0;                           /* the read it stands for (AlignArgs::index) */
     int b = nref - 1;
     int i = 0, len = 0, delay = SOLO ? 0 : j;
     bool done = false;
@@ -732,18 +738,44 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
         /* ---- bookkeeping: pipeline start-up and switches to the next chained alignment ---- */
         bool act = !done;
         if (delay > 0) { --delay; act = false; }
+        long long a_left = a;
+        const bool dyn = A.next != nullptr;
+        if (!SOLO) { if (dyn) a_left = __shfl_up_sync(FULL, a, 1, G); }      /* the left lane's position before this pass's switches */
+        const long long a_end = end_pos();
         if (act && i == len) {
             ++b;
             if (b == nref) {
                 b = 0;
-                a += NG;
-                while (a < A.n) {
-                    r = A.index ? A.index[a] : a;
-                    if ((len = A.lens[r]) != 0) break;
+                if (!dyn) {
                     a += NG;
+                    while (a < a_end) {
+                        r = A.index ? A.index[a] : a;
+                        if ((len = A.lens[r]) != 0) break;
+                        a += NG;
+                    }
+                } else if (SOLO || first_lane) {
+                    /* lanes of a warp that get here together share one atomic */
+                    const unsigned peers = __activemask();
+                    const int leader = __ffs(peers) - 1;
+                    unsigned long long base = 0;
+                    if (lane == leader) base = atomicAdd(A.next, (unsigned long long)__popc(peers));
+                    base = __shfl_sync(peers, base, leader);
+                    const long long a_begin = first_pos();
+                    a = a_begin + (long long)base + __popc(peers & ((1u << lane) - 1u));
+                    while (a < a_end) {               /* empty reads have no DP (launch_fill_empty): take another position */
+                        r = A.index ? A.index[a] : a;
+                        if ((len = A.lens[r]) != 0) break;
+                        a = a_begin + (long long)atomicAdd(A.next, 1ULL);
+                    }
+                } else {
+                    a = a_left;                       /* never an empty read: the first lane skipped those */
+                    if (a < a_end) {
+                        r = A.index ? A.index[a] : a;
+                        len = A.lens[r];
+                    }
                 }
             }
-            if (a >= A.n) {
+            if (a >= a_end) {
                 done = true;
                 act = false;
             } else {

@@ -46,6 +46,11 @@ struct AlignArgs {
      * best are addressed by read; traceback records and endrow by a).  Barcode-length reads are walked in order of length,
      * so that the lanes of a warp -- independent alignments -- reach their ends together (api.cpp: DeviceJob). */
     const int32_t* index;
+    /* optional dynamic distribution (row-pair kernels): groups take the next position of the processing order from this
+     * device counter (zeroed by the caller) instead of striding over it, so a launch has no tail round whatever its
+     * length -- which may itself live on the device: range[0], range[1] = first position and end (null: 0, n). */
+    unsigned long long* next;
+    const int32_t* range;
     /* reference(s): nref strings of length L (nref > 1 only for the fused multi-barcode pass) */
     int L;
     int nref;
