@@ -915,9 +915,20 @@ struct FwdRec {
     const char* name = "";
 };
 
+/* Which reads a forward launch covers and in what order: a list of read indices (null: all, in order), device-side
+ * bounds of the part of the list to take (null: all of it), the device counter of the dynamic distribution (null: the
+ * launch's own), a cap on the grid (0: a full grid). */
+struct FwdOrder {
+    const int32_t* index = nullptr;
+    const int32_t* range = nullptr;
+    unsigned long long* next = nullptr;
+    int grid = 0;
+};
+
 FwdRec forward_once(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t st,
         const uint16_t* d_rows, const int32_t* d_lens, long long m, int stride, int maxlen,
-        bool trace, const Outputs& out, int sms, FwdTimer* timer = nullptr, const int32_t* d_by_length = nullptr)
+        bool trace, const Outputs& out, int sms, FwdTimer* timer = nullptr, const int32_t* d_by_length = nullptr,
+        const FwdOrder* order = nullptr)
 {
     Range nvtx(trace ? "sarlacc: forward pass (trace)" : "sarlacc: forward pass (score)");
     FwdRec R;
@@ -941,7 +952,7 @@ FwdRec forward_once(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t st
     A.one = 1u;
     const Geometry geo = geometry_for(P, maxlen, d_by_length != nullptr);
     R.geo = geo;
-    A.index = d_by_length;
+    A.index = order ? order->index : d_by_length;
     A.G = geo.G;
     A.C = geo.C;
     A.solo = geo.solo ? 1 : 0;
@@ -972,7 +983,10 @@ FwdRec forward_once(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t st
         }
         A.flags = S.flags.p;
     }
-    if (P.fast && geo.pair && P.nref == 1 && dynamic_distribution()) {
+    if (order && order->next) {
+        A.next = order->next;          /* zeroed by the caller */
+        A.range = order->range;
+    } else if (P.fast && geo.pair && P.nref == 1 && dynamic_distribution()) {
         /* row-pair kernels take their alignments from a device counter: no tail round whatever the launch's length */
         S.next.reserve(sizeof(unsigned long long));
         CUDA_CHECK(cudaMemsetAsync(S.next.p, 0, sizeof(unsigned long long), st));
@@ -980,7 +994,7 @@ FwdRec forward_once(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t st
     }
     if (timer) timer->begin(st);
     if (P.fast) {
-        R.name = launch_wavefront(A, trace, P.has_alt, 0, st);
+        R.name = launch_wavefront(A, trace, P.has_alt, order ? order->grid : 0, st);
     } else {
         long long threads = std::min<long long>(m, (long long)sms * 1024);
         threads = (threads + 127) / 128 * 128;
@@ -1072,12 +1086,66 @@ const char* run_device(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t
 struct PairScratch {
     Scratch s[4];
     DevBuf map[2];
+    DevBuf spec;            /* speculative record writing: strand lists, positions, predictions, ranges, counters */
+    DevBuf seeds;           /* 8-mer seed bitmaps of the two adaptors */
+    std::string seeds_key;
+    bool seeds_usable = false;
     void release() {
         for (auto& x : s) x.release();
         map[0].release();
         map[1].release();
+        spec.release();
+        seeds.release();
+        seeds_key.clear();
     }
 };
+
+bool speculate_records() {
+    static const bool on = [] {
+        const char* e = std::getenv("SARLACC_SPECULATE");
+        return e ? std::atoi(e) != 0 : true;
+    }();
+    return on;
+}
+
+/* 8-mer seed bitmaps (2 x 2048 words) of the two adaptors' A/C/G/T stretches, for the strand predictor (kernels.h:
+ * StrandLists).  Usable only if both adaptors have enough seeds to out-vote chance hits. */
+bool prepare_seeds(PairScratch& S, const Plan& p1, const Plan& p2, cudaStream_t st) {
+    std::string key;
+    for (const Plan* P : {&p1, &p2}) {
+        key.append(reinterpret_cast<const char*>(P->refmask.data()), P->refmask.size());
+        key += '|';
+        key.append(reinterpret_cast<const char*>(P->refkind.data()), P->refkind.size());
+        key += '/';
+    }
+    if (key == S.seeds_key) return S.seeds_usable;
+    std::vector<uint32_t> bits(4096, 0);
+    int count[2] = {0, 0};
+    int which = 0;
+    for (const Plan* P : {&p1, &p2}) {
+        unsigned code = 0;
+        int valid = 0;
+        for (int c = 0; c < P->L; ++c) {
+            const unsigned m = P->refmask[(size_t)c];
+            const bool acgt = P->refkind[(size_t)c] == COL_ACGT && (m == 1 || m == 2 || m == 4 || m == 8);
+            const unsigned b = m == 1 ? 0u : (m == 2 ? 1u : (m == 4 ? 2u : 3u));
+            code = ((code << 2) | (acgt ? b : 0u)) & 0xFFFFu;
+            valid = acgt ? valid + 1 : 0;
+            if (valid >= 8) {
+                uint32_t& w = bits[(size_t)which * 2048 + (code >> 5)];
+                if (!((w >> (code & 31)) & 1u)) ++count[which];
+                w |= 1u << (code & 31);
+            }
+        }
+        ++which;
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));      /* an earlier launch may still read the previous bitmaps */
+    S.seeds.reserve(sizeof(uint32_t) * bits.size());
+    CUDA_CHECK(cudaMemcpy(S.seeds.p, bits.data(), sizeof(uint32_t) * bits.size(), cudaMemcpyHostToDevice));
+    S.seeds_key = key;
+    S.seeds_usable = count[0] >= 6 && count[1] >= 6;
+    return S.seeds_usable;
+}
 
 struct PairDeviceOut {      /* device pointers: [m] vectors, [nsec][pitch] section matrices */
     uint8_t* reversed = nullptr;
@@ -1109,16 +1177,75 @@ const char* run_pair_device(const Plan* const plan[2], const DevPlan* const D[2]
 {
     if (m <= 0) return "";
     Range nvtx("sarlacc: both adaptors x both windows");
+    /* Speculative record writing (kernels.h: StrandLists): only for the wavefront kernels' row-pair form, whose launches
+     * can take a list of reads with device-side bounds. */
+    bool spec = speculate_records() && dynamic_distribution() && m >= 1024 && m < (1LL << 31);
+    for (int a = 0; a < 2 && spec; ++a) spec = plan[a]->fast && geometry_for(*plan[a], maxlen).pair != 0;
+    if (spec) spec = prepare_seeds(S, *plan[0], *plan[1], st);
+    StrandLists L;
+    std::memset(&L, 0, sizeof(L));
+    unsigned long long* next = nullptr;
+    if (spec) {
+        const size_t mm = (size_t)m;
+        auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        const size_t o_lists = 0, o_pos = o_lists + al(sizeof(int32_t) * 4 * mm), o_pred = o_pos + al(sizeof(int32_t) * 2 * mm),
+                     o_ranges = o_pred + al(mm), o_next = o_ranges + 256, total = o_next + 256;
+        S.spec.reserve(total);
+        uint8_t* base = S.spec.as<uint8_t>();
+        L.list_fwd = reinterpret_cast<int32_t*>(base + o_lists);
+        L.list_rev = L.list_fwd + mm;
+        L.list_sfwd = L.list_rev + mm;
+        L.list_srev = L.list_sfwd + mm;
+        L.pos_fwd = reinterpret_cast<int32_t*>(base + o_pos);
+        L.pos_rev = L.pos_fwd + mm;
+        L.predicted = base + o_pred;
+        L.ranges = reinterpret_cast<int32_t*>(base + o_ranges);
+        next = reinterpret_cast<unsigned long long*>(base + o_next);
+        CUDA_CHECK(cudaMemsetAsync(base + o_ranges, 0, 512, st));      /* ranges and the twelve launch counters */
+        ClassifyArgs CA;
+        std::memset(&CA, 0, sizeof(CA));
+        CA.rows_front = rows_f;
+        CA.rows_back = rows_b;
+        CA.lens_front = lens_f;
+        CA.lens_back = lens_b;
+        CA.n = m;
+        CA.stride = stride_f;
+        CA.seeds1 = S.seeds.as<uint32_t>();
+        CA.seeds2 = S.seeds.as<uint32_t>() + 2048;
+        CA.margin = 3;
+        CA.L = L;
+        if (stride_f != stride_b) spec = false;
+        else {
+            launch_classify_strands(CA, st);
+            g_launches += 2;
+        }
+    }
     FwdRec rec[4];
     for (int r = 0; r < 4; ++r) {
         const int a = (r == 0 || r == 2) ? 0 : 1;          /* adaptor */
         const bool on_front = (r == 0 || r == 3);           /* window set */
+        const bool rev_strand = r >= 2;                     /* (adaptor1, back) and (adaptor2, front) are the reverse strand's passes */
         Outputs dev;
         dev.score = tmp_scores + (size_t)r * m;
+        if (!spec) {
+            rec[r] = forward_once(*plan[a], *D[a], S.s[r], st, on_front ? rows_f : rows_b, on_front ? lens_f : lens_b, m,
+                                  on_front ? stride_f : stride_b, maxlen, true, dev, sms, r == 0 ? timer : nullptr);
+            continue;
+        }
+        FwdOrder with_records, score_only;
+        with_records.index = rev_strand ? L.list_rev : L.list_fwd;
+        with_records.range = L.ranges + (rev_strand ? 2 : 0);
+        with_records.next = next + 2 * r;
+        score_only.index = rev_strand ? L.list_srev : L.list_sfwd;
+        score_only.range = L.ranges + (rev_strand ? 6 : 4);
+        score_only.next = next + 2 * r + 1;
         rec[r] = forward_once(*plan[a], *D[a], S.s[r], st, on_front ? rows_f : rows_b, on_front ? lens_f : lens_b, m,
-                              on_front ? stride_f : stride_b, maxlen, true, dev, sms, r == 0 ? timer : nullptr);
+                              on_front ? stride_f : stride_b, maxlen, true, dev, sms, r == 0 ? timer : nullptr, nullptr, &with_records);
+        forward_once(*plan[a], *D[a], S.s[r], st, on_front ? rows_f : rows_b, on_front ? lens_f : lens_b, m,
+                     on_front ? stride_f : stride_b, maxlen, false, dev, sms, nullptr, nullptr, &score_only);
     }
     StrandArgs SA;
+    std::memset(&SA, 0, sizeof(SA));
     SA.n = m;
     SA.a1_front = tmp_scores;
     SA.a2_back = tmp_scores + (size_t)m;
@@ -1128,8 +1255,34 @@ const char* run_pair_device(const Plan* const plan[2], const DevPlan* const D[2]
     SA.score1 = out.score[0];
     SA.score2 = out.score[1];
     SA.strand_score = nullptr;
+    if (spec) {
+        SA.predicted = L.predicted;
+        SA.list_fwd = L.list_fwd;
+        SA.list_rev = L.list_rev;
+        SA.pos_fwd = L.pos_fwd;
+        SA.pos_rev = L.pos_rev;
+        SA.ranges = L.ranges;
+    }
     launch_resolve_strand(SA, st);
     g_launches += 1;
+    if (spec) {
+        /* the reads whose kept strand was scored without records: a second pass with records, appended to the same record
+         * sets (positions behind the predicted ones); normally a handful, so a small grid */
+        for (int r = 0; r < 4; ++r) {
+            const int a = (r == 0 || r == 2) ? 0 : 1;
+            const bool on_front = (r == 0 || r == 3);
+            const bool rev_strand = r >= 2;
+            Outputs dev;
+            dev.score = tmp_scores + (size_t)r * m;
+            FwdOrder redo;
+            redo.index = rev_strand ? L.list_rev : L.list_fwd;
+            redo.range = L.ranges + (rev_strand ? 10 : 8);
+            redo.next = next + 8 + r;
+            redo.grid = sms;
+            forward_once(*plan[a], *D[a], S.s[r], st, on_front ? rows_f : rows_b, on_front ? lens_f : lens_b, m,
+                         on_front ? stride_f : stride_b, maxlen, true, dev, sms, nullptr, nullptr, &redo);
+        }
+    }
     CUDA_CHECK(cudaEventRecord(fwd_done, st));
     CUDA_CHECK(cudaStreamWaitEvent(tb, fwd_done, 0));
     for (int a = 0; a < 2; ++a) {
@@ -1141,6 +1294,10 @@ const char* run_pair_device(const Plan* const plan[2], const DevPlan* const D[2]
         T.flags2 = rev.A.flags;
         T.flags_hi2 = rev.A.flags_hi;
         T.endrow2 = rev.A.endrow;
+        if (spec) {
+            T.pos = L.pos_fwd;
+            T.pos2 = L.pos_rev;
+        }
         S.map[a].reserve(sizeof(int32_t) * ((size_t)plan[a]->L + 1) * (size_t)m);
         T.map = S.map[a].as<int32_t>();
         T.start = out.start[a];
@@ -3706,6 +3863,7 @@ int sarlacc_chunk_scrambled_scores(sarlacc_chunk* c, double gapopen, double gape
         c->sout[w].reserve(sizeof(double) * 3 * (size_t)c->capacity);
         double* own = c->sout[w].as<double>();
         StrandArgs SA;
+        std::memset(&SA, 0, sizeof(SA));
         SA.n = n;
         SA.a1_front = tmp;
         SA.a2_back = tmp + (size_t)n;

@@ -490,6 +490,26 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward(co
  * gives every warp two dependency chains in flight (the single-row kernel's top stall is `wait`, the fixed-latency
  * dependency of its one chain, profiles/).  An odd last row runs the same code with row B masked off.
  */
+/* Dynamic distribution: the next free position of the launch's processing order (skipping empty reads, which have no DP:
+ * launch_fill_empty), its read and window length.  Lanes of a warp that get here together share one atomic.  Kept out of
+ * line: inlined, its temporaries cost the row loops of some instantiations a few register moves per cell. */
+__device__ __noinline__ long long fetch_position(const AlignArgs& A, int lane, long long& r, int& len) {
+    const long long a_begin = A.range ? (long long)A.range[0] : 0;
+    const long long a_end = A.range ? (long long)A.range[1] : A.n;
+    const unsigned peers = __activemask();
+    const int leader = __ffs(peers) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(A.next, (unsigned long long)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    long long a = a_begin + (long long)base + __popc(peers & ((1u << lane) - 1u));
+    while (a < a_end) {
+        r = A.index ? A.index[a] : a;
+        if ((len = A.lens[r]) != 0) break;
+        a = a_begin + (long long)atomicAdd(A.next, 1ULL);
+    }
+    return a;
+}
+
 template <int C, bool TRACE, bool SOLO>
 __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(const __grid_constant__ AlignArgs A)
 {
@@ -754,19 +774,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
                         a += NG;
                     }
                 } else if (SOLO || first_lane) {
-                    /* lanes of a warp that get here together share one atomic */
-                    const unsigned peers = __activemask();
-                    const int leader = __ffs(peers) - 1;
-                    unsigned long long base = 0;
-                    if (lane == leader) base = atomicAdd(A.next, (unsigned long long)__popc(peers));
-                    base = __shfl_sync(peers, base, leader);
-                    const long long a_begin = first_pos();
-                    a = a_begin + (long long)base + __popc(peers & ((1u << lane) - 1u));
-                    while (a < a_end) {               /* empty reads have no DP (launch_fill_empty): take another position */
-                        r = A.index ? A.index[a] : a;
-                        if ((len = A.lens[r]) != 0) break;
-                        a = a_begin + (long long)atomicAdd(A.next, 1ULL);
-                    }
+                    a = fetch_position(A, lane, r, len);
                 } else {
                     a = a_left;                       /* never an empty read: the first lane skipped those */
                     if (a < a_end) {
@@ -1030,9 +1038,11 @@ __global__ void __launch_bounds__(128) traceback(const TraceArgs T)
     const int L = T.L;
     const int len = alt ? T.lens2[a] : T.lens[a];
     const int32_t* endrow = alt ? T.endrow2 : T.endrow;
+    const int32_t* posv = alt ? T.pos2 : T.pos;
+    const long long rec = posv ? (long long)posv[a] : a;       /* where this read's records are (speculative runs) */
     const long long n = T.n;
     const long long pitch = T.out_pitch > 0 ? T.out_pitch : n;
-    FlagReader R{T, a, len, tb_colinfo, alt ? T.flags2 : T.flags, alt ? T.flags_hi2 : T.flags_hi};
+    FlagReader R{T, rec, len, tb_colinfo, alt ? T.flags2 : T.flags, alt ? T.flags_hi2 : T.flags_hi};
     int32_t* map = T.map + a;        /* map[c*n]: (row << 1) | is_match, fill_map's mapping (:280-305) */
     uint8_t* ops = T.ops ? T.ops + a * T.ops_stride : nullptr;
     int nops = 0;
@@ -1048,7 +1058,7 @@ __global__ void __launch_bounds__(128) traceback(const TraceArgs T)
     bool pending = false;   /* p1 (in ST_E) / p2 (in ST_F) of the cell the current run came from */
     if (endrow && len > 0 && L > 0) {
         /* the forward kernel already followed the climb up the last column (land_step): skip those up-moves */
-        i = endrow[a];
+        i = endrow[rec];
         for (int x = i; x < len; ++x) {
             if (ops) ops[nops] = 'I';
             ++nops;
@@ -1194,6 +1204,76 @@ __global__ void resolve_strand(const StrandArgs S)
     if (S.score1) S.score1[i] = rev ? r1 : s1;
     if (S.score2) S.score2[i] = rev ? r2 : s2;
     if (S.strand_score) S.strand_score[i] = rev ? r : f;
+    if (S.predicted) {
+        const unsigned p = S.predicted[i];
+        if (!rev && p == 1u) {            /* predicted reverse, kept forward: its forward-strand passes wrote no records */
+            const int at = atomicAdd(S.ranges + 9, 1);
+            S.list_fwd[at] = (int32_t)i;
+            S.pos_fwd[i] = at;
+        } else if (rev && p == 0u) {
+            const int at = atomicAdd(S.ranges + 11, 1);
+            S.list_rev[at] = (int32_t)i;
+            S.pos_rev[i] = at;
+        }
+    }
+}
+
+/* See StrandLists (kernels.h).  One thread per read: exact 8-mer seeds of adaptor1 / adaptor2 counted in both windows. */
+__device__ __forceinline__ void count_seeds(const uint16_t* row, int len, const uint32_t* s1, const uint32_t* s2, int& h1, int& h2) {
+    unsigned code = 0;
+    int valid = 0;
+    for (int i = 0; i < len; ++i) {
+        const int o = __ffs((unsigned)row[i] >> 8);             /* 1..4 for A, C, G, T; 0 otherwise */
+        code = ((code << 2) | (unsigned)(o > 0 ? o - 1 : 0)) & 0xFFFFu;
+        valid = o > 0 ? valid + 1 : 0;
+        if (valid >= 8) {
+            h1 += (s1[code >> 5] >> (code & 31)) & 1u;
+            h2 += (s2[code >> 5] >> (code & 31)) & 1u;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) classify_strands(const ClassifyArgs A)
+{
+    __shared__ uint32_t s1[2048], s2[2048];
+    for (int x = threadIdx.x; x < 2048; x += blockDim.x) { s1[x] = A.seeds1[x]; s2[x] = A.seeds2[x]; }
+    __syncthreads();
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = r < A.n;
+    unsigned pred = 2;
+    if (live) {
+        int a1f = 0, a2f = 0, a1b = 0, a2b = 0;
+        count_seeds(A.rows_front + r * (long long)A.stride, A.lens_front[r], s1, s2, a1f, a2f);
+        count_seeds(A.rows_back + r * (long long)A.stride, A.lens_back[r], s1, s2, a1b, a2b);
+        const int fwd = a1f + a2b, rev = a1b + a2f;          /* adaptor1 x front + adaptor2 x back vs the swapped windows */
+        pred = fwd >= rev + A.margin ? 0u : (rev >= fwd + A.margin ? 1u : 2u);
+        A.L.predicted[r] = (uint8_t)pred;
+    }
+    /* append to the four lists, one atomic per list per warp */
+    const unsigned lane = threadIdx.x & 31;
+    auto append = [&](bool want, int32_t* list, int32_t* pos, int counter) {
+        const unsigned m = __ballot_sync(FULL, want);
+        if (m == 0) return;
+        int base = 0;
+        if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(A.L.ranges + counter, __popc(m));
+        base = __shfl_sync(FULL, base, __ffs(m) - 1);
+        if (want) {
+            const int at = base + __popc(m & ((1u << lane) - 1u));
+            list[at] = (int32_t)r;
+            if (pos) pos[r] = at;
+        }
+    };
+    append(live && pred != 1u, A.L.list_fwd, A.L.pos_fwd, 1);      /* forward-strand passes with records: predicted forward or unsure */
+    append(live && pred != 0u, A.L.list_rev, A.L.pos_rev, 3);
+    append(live && pred == 1u, A.L.list_sfwd, nullptr, 5);          /* forward-strand passes score-only */
+    append(live && pred == 0u, A.L.list_srev, nullptr, 7);
+}
+
+/* The re-run ranges start where the predicted lists end. */
+__global__ void finish_strand_lists(int32_t* ranges)
+{
+    ranges[8] = ranges[9] = ranges[1];
+    ranges[10] = ranges[11] = ranges[3];
 }
 
 /* ---- counter-based randomness shared by the scramble and the synthetic-read generator ----------------------------
@@ -1592,6 +1672,12 @@ void launch_scramble(const uint16_t* in, uint16_t* out, const int32_t* lens, lon
     else if (sizeof(uint16_t) * (size_t)stride * (64 + 2) <= budget) launch(std::integral_constant<int, 64>());
     else if (sizeof(uint16_t) * (size_t)stride * (32 + 2) <= budget) launch(std::integral_constant<int, 32>());
     else scramble_rows_fy_global<<<(int)((n + 127) / 128), 128, 0, st>>>(in, out, lens, n, stride, seed, first_index, read_index, (unsigned)stream_id);
+}
+
+void launch_classify_strands(const ClassifyArgs& c, cudaStream_t st) {
+    if (c.n <= 0) return;
+    classify_strands<<<(int)((c.n + 127) / 128), 128, 0, st>>>(c);
+    finish_strand_lists<<<1, 1, 0, st>>>(c.L.ranges);
 }
 
 void launch_resolve_strand(const StrandArgs& s, cudaStream_t st) {

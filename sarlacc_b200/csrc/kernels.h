@@ -105,6 +105,10 @@ struct TraceArgs {
     const void* flags2;
     const void* flags_hi2;
     const int32_t* endrow2;
+    /* optional: where the records of read r sit in each source (position in that forward launch's processing order);
+     * null: position == read */
+    const int32_t* pos;
+    const int32_t* pos2;
     const int32_t* width;       /* optional read widths: start/end are flipped to width - x + 1 (R/adaptorAlign.R:66-71) */
     long long out_pitch;        /* row pitch of sec_start / sec_width (0: n) */
     int nsec;
@@ -148,8 +152,41 @@ struct StrandArgs {
     uint8_t* reversed;
     double* score1; double* score2;       /* ifelse(is.reverse, revcomp, forward) per adaptor; may be null */
     double* strand_score;                 /* .resolve_strand()$scores = ifelse(is.reverse, rscore, fscore); may be null */
+    /* speculative runs (see StrandLists): reads whose kept strand was scored without records are appended to that
+     * strand's list behind the predicted ones, for a second forward pass with records */
+    const uint8_t* predicted;             /* null: no speculation */
+    int32_t* list_fwd; int32_t* list_rev; int32_t* pos_fwd; int32_t* pos_rev;
+    int32_t* ranges;
 };
 void launch_resolve_strand(const StrandArgs& s, cudaStream_t st);
+
+/* Speculative traceback records.  Only the strand .resolve_strand keeps is walked back, but which one that is is known
+ * only after all four forward passes -- so all four used to write records.  A cheap predictor (exact 8-mer seeds of the
+ * two adaptors counted in both windows) sorts the reads of a launch into "forward strand", "reverse strand" and "unsure":
+ * the passes of the predicted strand run with records, those of the other strand score-only (unsure reads: both with
+ * records), and the few reads whose prediction .resolve_strand contradicts get a second forward pass with records.  The
+ * results are those of the unspeculated run -- the predictor only decides where records are written.
+ *   lists: list_fwd / list_rev = reads whose forward- / reverse-strand passes write records (predicted ones first, the
+ *          re-runs appended by resolve_strand), list_sfwd / list_srev = reads whose forward- / reverse-strand passes are
+ *          score-only; pos_fwd / pos_rev = position of a read in list_fwd / list_rev.
+ *   ranges (int32[12], device): {0, n_fwd}, {0, n_rev}, {0, n_sfwd}, {0, n_srev}, {n_fwd, n_fwd_total}, {n_rev, n_rev_total}. */
+struct StrandLists {
+    int32_t* list_fwd; int32_t* list_rev; int32_t* list_sfwd; int32_t* list_srev;
+    int32_t* pos_fwd; int32_t* pos_rev;
+    uint8_t* predicted;       /* 0 forward, 1 reverse, 2 unsure */
+    int32_t* ranges;
+};
+struct ClassifyArgs {
+    const uint16_t* rows_front; const uint16_t* rows_back;
+    const int32_t* lens_front; const int32_t* lens_back;
+    long long n;
+    int stride;
+    const uint32_t* seeds1;   /* device, 2048 words each: bit (8-mer code) set if the 8-mer occurs in the adaptor */
+    const uint32_t* seeds2;
+    int margin;               /* hits by which one strand must lead */
+    StrandLists L;
+};
+void launch_classify_strands(const ClassifyArgs& c, cudaStream_t st);
 
 /* Synthetic mockReads-style windows generated on the device (R/mockReads.R:58-92; kernels.cu: mock_windows_kernel). */
 struct MockArgs {
