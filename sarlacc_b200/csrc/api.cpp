@@ -923,6 +923,7 @@ struct FwdOrder {
     const int32_t* range = nullptr;
     unsigned long long* next = nullptr;
     int grid = 0;
+    bool fill_empty = true;      /* false: another launch over the same reads already wrote the empty reads' scores */
 };
 
 FwdRec forward_once(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t st,
@@ -1008,8 +1009,11 @@ FwdRec forward_once(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t st
         R.name = launch_generic(A, trace, 0, st);
     }
     if (timer) timer->end(st);
-    launch_fill_empty(A, st);
-    g_launches += 2;
+    if (!order || order->fill_empty) {
+        launch_fill_empty(A, st);
+        g_launches += 1;
+    }
+    g_launches += 1;
     return R;
 }
 
@@ -1083,9 +1087,49 @@ const char* run_device(const Plan& P, const DevPlan& D, Scratch& S, cudaStream_t
  * the strand that was kept (cur.starts[rev,] <- cur.rc.starts[rev,], :195-196), writing the final columns directly
  * (adaptor2's start/end flipped into read coordinates when widths are given, :66-71).  Half the traceback work of four
  * separate adaptor_align calls, and no per-strand result sets to select from afterwards. */
+/* Independent forward launches are spread over two streams: each launch keeps the device full until its last
+ * alignments (a resident grid), so the first blocks of the launch queued on the other stream start in the tail of this one
+ * instead of behind it.  begin(): the side stream waits for what `st` holds so far; end(): `st` waits for the side stream. */
+bool overlap_launches() {
+    static const bool on = [] {
+        const char* e = std::getenv("SARLACC_OVERLAP");
+        return e ? std::atoi(e) != 0 : true;
+    }();
+    return on;
+}
+
+struct SideStream {
+    cudaStream_t aux = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    cudaStream_t begin(cudaStream_t st) {
+        if (!overlap_launches()) return st;
+        if (!aux) {
+            CUDA_CHECK(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+            CUDA_CHECK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+            CUDA_CHECK(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+        }
+        CUDA_CHECK(cudaEventRecord(fork, st));
+        CUDA_CHECK(cudaStreamWaitEvent(aux, fork, 0));
+        return aux;
+    }
+    void end(cudaStream_t st) {
+        if (!aux || !overlap_launches()) return;
+        CUDA_CHECK(cudaEventRecord(join, aux));
+        CUDA_CHECK(cudaStreamWaitEvent(st, join, 0));
+    }
+    void release() {
+        if (aux) cudaStreamDestroy(aux);
+        if (fork) cudaEventDestroy(fork);
+        if (join) cudaEventDestroy(join);
+        aux = nullptr;
+        fork = join = nullptr;
+    }
+};
+
 struct PairScratch {
     Scratch s[4];
     DevBuf map[2];
+    SideStream side;
     DevBuf spec;            /* speculative record writing: strand lists, positions, predictions, ranges, counters */
     DevBuf seeds;           /* 8-mer seed bitmaps of the two adaptors */
     std::string seeds_key;
@@ -1097,6 +1141,7 @@ struct PairScratch {
         spec.release();
         seeds.release();
         seeds_key.clear();
+        side.release();
     }
 };
 
@@ -1221,6 +1266,7 @@ const char* run_pair_device(const Plan* const plan[2], const DevPlan* const D[2]
         }
     }
     FwdRec rec[4];
+    cudaStream_t side = S.side.begin(st);
     for (int r = 0; r < 4; ++r) {
         const int a = (r == 0 || r == 2) ? 0 : 1;          /* adaptor */
         const bool on_front = (r == 0 || r == 3);           /* window set */
@@ -1228,7 +1274,7 @@ const char* run_pair_device(const Plan* const plan[2], const DevPlan* const D[2]
         Outputs dev;
         dev.score = tmp_scores + (size_t)r * m;
         if (!spec) {
-            rec[r] = forward_once(*plan[a], *D[a], S.s[r], st, on_front ? rows_f : rows_b, on_front ? lens_f : lens_b, m,
+            rec[r] = forward_once(*plan[a], *D[a], S.s[r], rev_strand ? side : st, on_front ? rows_f : rows_b, on_front ? lens_f : lens_b, m,
                                   on_front ? stride_f : stride_b, maxlen, true, dev, sms, r == 0 ? timer : nullptr);
             continue;
         }
@@ -1239,11 +1285,13 @@ const char* run_pair_device(const Plan* const plan[2], const DevPlan* const D[2]
         score_only.index = rev_strand ? L.list_srev : L.list_sfwd;
         score_only.range = L.ranges + (rev_strand ? 6 : 4);
         score_only.next = next + 2 * r + 1;
+        score_only.fill_empty = false;
         rec[r] = forward_once(*plan[a], *D[a], S.s[r], st, on_front ? rows_f : rows_b, on_front ? lens_f : lens_b, m,
                               on_front ? stride_f : stride_b, maxlen, true, dev, sms, r == 0 ? timer : nullptr, nullptr, &with_records);
-        forward_once(*plan[a], *D[a], S.s[r], st, on_front ? rows_f : rows_b, on_front ? lens_f : lens_b, m,
+        forward_once(*plan[a], *D[a], S.s[r], side, on_front ? rows_f : rows_b, on_front ? lens_f : lens_b, m,
                      on_front ? stride_f : stride_b, maxlen, false, dev, sms, nullptr, nullptr, &score_only);
     }
+    S.side.end(st);
     StrandArgs SA;
     std::memset(&SA, 0, sizeof(SA));
     SA.n = m;
@@ -1279,9 +1327,17 @@ const char* run_pair_device(const Plan* const plan[2], const DevPlan* const D[2]
             redo.range = L.ranges + (rev_strand ? 10 : 8);
             redo.next = next + 8 + r;
             redo.grid = sms;
+            redo.fill_empty = false;
             forward_once(*plan[a], *D[a], S.s[r], st, on_front ? rows_f : rows_b, on_front ? lens_f : lens_b, m,
                          on_front ? stride_f : stride_b, maxlen, true, dev, sms, nullptr, nullptr, &redo);
         }
+    }
+    if (spec && std::getenv("SARLACC_DEBUG_SPEC")) {
+        int32_t h[12];
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        CUDA_CHECK(cudaMemcpy(h, L.ranges, sizeof(h), cudaMemcpyDeviceToHost));
+        std::fprintf(stderr, "[sarlacc] speculation: %lld reads, records fwd %d rev %d, score-only fwd %d rev %d, re-run fwd %d rev %d\n",
+                     m, h[1], h[3], h[5], h[7], h[9] - h[8], h[11] - h[10]);
     }
     CUDA_CHECK(cudaEventRecord(fwd_done, st));
     CUDA_CHECK(cudaStreamWaitEvent(tb, fwd_done, 0));
@@ -3329,7 +3385,8 @@ struct sarlacc_chunk {
     struct CachedPlan { std::string key; Plan plan; DevPlan d; };
     std::vector<std::unique_ptr<CachedPlan> > plans;
     PairScratch pair[2];
-    Scratch score_scratch;
+    Scratch score_scratch, score_scratch2;   /* one per stream of the score-only passes */
+    SideStream side;
     cudaEvent_t fwd_done[2] = {nullptr, nullptr}, tb_done[2] = {nullptr, nullptr};
     bool tb_pending[2] = {false, false};
     int parity = 0;
@@ -3477,6 +3534,8 @@ void sarlacc_chunk_free(sarlacc_chunk* c) {
     c->pair[0].release();
     c->pair[1].release();
     c->score_scratch.release();
+    c->score_scratch2.release();
+    c->side.release();
     for (auto& p : c->plans) p->d.buf.release();
     for (int k = 0; k < 2; ++k) {
         if (c->fwd_done[k]) cudaEventDestroy(c->fwd_done[k]);
@@ -3840,14 +3899,16 @@ int sarlacc_chunk_scrambled_scores(sarlacc_chunk* c, double gapopen, double gape
         /* the four forward passes of .get_alignment_scores (R/tuneAlignment.R:99-112): START, END, RSTART, REND */
         chunk_mark(c, 3, true);
         double* tmp = c->tmp.as<double>();
+        cudaStream_t side = c->side.begin(c->st);
         for (int r = 0; r < 4; ++r) {
             const int a = (r == 0 || r == 2) ? 0 : 1;
             const bool on_front = (r == 0 || r == 3);
             Outputs dev;
             dev.score = tmp + (size_t)r * n;
-            forward_once(cp[a]->plan, cp[a]->d, c->score_scratch, c->st, on_front ? rf : rb,
+            forward_once(cp[a]->plan, cp[a]->d, r >= 2 ? c->score_scratch2 : c->score_scratch, r >= 2 ? side : c->st, on_front ? rf : rb,
                          on_front ? c->lens_f.as<int32_t>() : c->lens_b.as<int32_t>(), n, c->stride, c->maxlen, false, dev, c->sms);
         }
+        c->side.end(c->st);
         /* kept scores: straight into device destinations, through a chunk buffer + the copy stream for host ones */
         cudaPointerAttributes at1, at2, at3;
         const bool dev1 = score1 && cudaPointerGetAttributes(&at1, score1) == cudaSuccess && at1.type == cudaMemoryTypeDevice;

@@ -530,6 +530,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
     uint8_t* refm = reinterpret_cast<uint8_t*>(qn + encn);   /* [nref][L] */
     uint8_t* refk = refm + (size_t)nref * L;                                   /* [nref][L] */
 
+    if (A.next && A.range && A.range[0] >= A.range[1]) return;      /* an empty part of a list (the usual case for re-runs) */
     for (int x = threadIdx.x; x <= L; x += blockDim.x) row0s[x] = A.row0[x];
     for (int x = threadIdx.x; x < nref * L; x += blockDim.x) {
         refm[x] = A.refmask[x];
@@ -1218,55 +1219,104 @@ __global__ void resolve_strand(const StrandArgs S)
     }
 }
 
-/* See StrandLists (kernels.h).  One thread per read: exact 8-mer seeds of adaptor1 / adaptor2 counted in both windows. */
-__device__ __forceinline__ void count_seeds(const uint16_t* row, int len, const uint32_t* s1, const uint32_t* s2, int& h1, int& h2) {
+/* See StrandLists (kernels.h).  Exact 8-mer seeds of adaptor1 / adaptor2 counted in both windows.  Eight lanes share a
+ * read: lane k counts the 8-mers ENDING in bases [32k, 32k + 32) (+256, ...) of each window, for which it also looks at
+ * the seven bases before them; four reads per warp, warps stride over the launch. */
+__device__ __forceinline__ void count_seeds(const uint16_t* row, int len, int s, const uint32_t* s1, const uint32_t* s2, int& h1, int& h2) {
     unsigned code = 0;
     int valid = 0;
-    for (int i = 0; i < len; ++i) {
+    const int lo = s >= 7 ? s - 7 : 0, hi = min(len, s + 32);
+    for (int i = lo; i < hi; ++i) {
         const int o = __ffs((unsigned)row[i] >> 8);             /* 1..4 for A, C, G, T; 0 otherwise */
         code = ((code << 2) | (unsigned)(o > 0 ? o - 1 : 0)) & 0xFFFFu;
         valid = o > 0 ? valid + 1 : 0;
-        if (valid >= 8) {
+        if (valid >= 8 && i >= s) {
             h1 += (s1[code >> 5] >> (code & 31)) & 1u;
             h2 += (s2[code >> 5] >> (code & 31)) & 1u;
         }
     }
 }
 
-__global__ void __launch_bounds__(128) classify_strands(const ClassifyArgs A)
+/* the same from 16-byte loads (rows 16-byte aligned, pitch a multiple of 8 entries) */
+__device__ __forceinline__ void count_seeds_vec(const uint16_t* row, int len, int s, const uint32_t* s1, const uint32_t* s2, int& h1, int& h2) {
+    uint32_t w[20];                                    /* bases s-8 .. s+31, two per word */
+    const uint4* q = reinterpret_cast<const uint4*>(row + s);
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    const uint4 pre = s > 0 ? __ldg(q - 1) : zero;
+    w[0] = pre.x; w[1] = pre.y; w[2] = pre.z; w[3] = pre.w;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint4 v = (s + 8 * k < len) ? __ldg(q + k) : zero;
+        w[4 + 4 * k] = v.x; w[5 + 4 * k] = v.y; w[6 + 4 * k] = v.z; w[7 + 4 * k] = v.w;
+    }
+    unsigned code = 0;
+    int valid = 0;
+#pragma unroll
+    for (int jj = 1; jj < 40; ++jj) {
+        const int i = s - 8 + jj;
+        const unsigned e = (jj & 1) ? (w[jj >> 1] >> 16) : (w[jj >> 1] & 0xFFFFu);
+        const int o = (i >= 0 && i < len) ? __ffs(e >> 8) : 0;
+        code = ((code << 2) | (unsigned)(o > 0 ? o - 1 : 0)) & 0xFFFFu;
+        valid = o > 0 ? valid + 1 : 0;
+        if (jj >= 8 && valid >= 8) {
+            h1 += (s1[code >> 5] >> (code & 31)) & 1u;
+            h2 += (s2[code >> 5] >> (code & 31)) & 1u;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) classify_strands(const ClassifyArgs A)
 {
     __shared__ uint32_t s1[2048], s2[2048];
     for (int x = threadIdx.x; x < 2048; x += blockDim.x) { s1[x] = A.seeds1[x]; s2[x] = A.seeds2[x]; }
     __syncthreads();
-    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = r < A.n;
-    unsigned pred = 2;
-    if (live) {
-        int a1f = 0, a2f = 0, a1b = 0, a2b = 0;
-        count_seeds(A.rows_front + r * (long long)A.stride, A.lens_front[r], s1, s2, a1f, a2f);
-        count_seeds(A.rows_back + r * (long long)A.stride, A.lens_back[r], s1, s2, a1b, a2b);
-        const int fwd = a1f + a2b, rev = a1b + a2f;          /* adaptor1 x front + adaptor2 x back vs the swapped windows */
-        pred = fwd >= rev + A.margin ? 0u : (rev >= fwd + A.margin ? 1u : 2u);
-        A.L.predicted[r] = (uint8_t)pred;
-    }
-    /* append to the four lists, one atomic per list per warp */
-    const unsigned lane = threadIdx.x & 31;
-    auto append = [&](bool want, int32_t* list, int32_t* pos, int counter) {
-        const unsigned m = __ballot_sync(FULL, want);
-        if (m == 0) return;
-        int base = 0;
-        if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(A.L.ranges + counter, __popc(m));
-        base = __shfl_sync(FULL, base, __ffs(m) - 1);
-        if (want) {
-            const int at = base + __popc(m & ((1u << lane) - 1u));
-            list[at] = (int32_t)r;
-            if (pos) pos[r] = at;
+    const unsigned lane = threadIdx.x & 31, sub = lane & 7, slot = lane >> 3;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const bool vec = A.vec != 0;
+    for (long long base = warp * 4; base < A.n; base += warps * 4) {
+        const long long r = base + slot;
+        const bool live = r < A.n;
+        int fwd = 0, rev = 0;          /* adaptor1 x front + adaptor2 x back  vs  adaptor1 x back + adaptor2 x front */
+        if (live) {
+            const uint16_t* rf = A.rows_front + r * (long long)A.stride;
+            const uint16_t* rb = A.rows_back + r * (long long)A.stride;
+            const int lf = A.lens_front[r], lb = A.lens_back[r];
+            for (int s = (int)sub * 32; s < lf; s += 256) {
+                if (vec) count_seeds_vec(rf, lf, s, s1, s2, fwd, rev);
+                else count_seeds(rf, lf, s, s1, s2, fwd, rev);
+            }
+            for (int s = (int)sub * 32; s < lb; s += 256) {
+                if (vec) count_seeds_vec(rb, lb, s, s1, s2, rev, fwd);
+                else count_seeds(rb, lb, s, s1, s2, rev, fwd);
+            }
         }
-    };
-    append(live && pred != 1u, A.L.list_fwd, A.L.pos_fwd, 1);      /* forward-strand passes with records: predicted forward or unsure */
-    append(live && pred != 0u, A.L.list_rev, A.L.pos_rev, 3);
-    append(live && pred == 1u, A.L.list_sfwd, nullptr, 5);          /* forward-strand passes score-only */
-    append(live && pred == 0u, A.L.list_srev, nullptr, 7);
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+            fwd += __shfl_xor_sync(FULL, fwd, d);
+            rev += __shfl_xor_sync(FULL, rev, d);
+        }
+        const unsigned pred = fwd >= rev + A.margin ? 0u : (rev >= fwd + A.margin ? 1u : 2u);
+        const bool mine = live && sub == 0;
+        if (mine) A.L.predicted[r] = (uint8_t)pred;
+        /* append to the four lists, one atomic per list per warp */
+        auto append = [&](bool want, int32_t* list, int32_t* pos, int counter) {
+            const unsigned m = __ballot_sync(FULL, want);
+            if (m == 0) return;
+            int at0 = 0;
+            if (lane == (unsigned)(__ffs(m) - 1)) at0 = atomicAdd(A.L.ranges + counter, __popc(m));
+            at0 = __shfl_sync(FULL, at0, __ffs(m) - 1);
+            if (want) {
+                const int at = at0 + __popc(m & ((1u << lane) - 1u));
+                list[at] = (int32_t)r;
+                if (pos) pos[r] = at;
+            }
+        };
+        append(mine && pred != 1u, A.L.list_fwd, A.L.pos_fwd, 1);      /* forward-strand passes with records: predicted forward or unsure */
+        append(mine && pred != 0u, A.L.list_rev, A.L.pos_rev, 3);
+        append(mine && pred == 1u, A.L.list_sfwd, nullptr, 5);          /* forward-strand passes score-only */
+        append(mine && pred == 0u, A.L.list_srev, nullptr, 7);
+    }
 }
 
 /* The re-run ranges start where the predicted lists end. */
@@ -1676,7 +1726,10 @@ void launch_scramble(const uint16_t* in, uint16_t* out, const int32_t* lens, lon
 
 void launch_classify_strands(const ClassifyArgs& c, cudaStream_t st) {
     if (c.n <= 0) return;
-    classify_strands<<<(int)((c.n + 127) / 128), 128, 0, st>>>(c);
+    ClassifyArgs a = c;
+    a.vec = (c.stride % 8 == 0 && (reinterpret_cast<uintptr_t>(c.rows_front) & 15) == 0 && (reinterpret_cast<uintptr_t>(c.rows_back) & 15) == 0) ? 1 : 0;
+    const long long blocks = (c.n + 31) / 32;           /* 8 warps x 4 reads */
+    classify_strands<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, st>>>(a);
     finish_strand_lists<<<1, 1, 0, st>>>(c.L.ranges);
 }
 

@@ -184,6 +184,7 @@ struct ClassifyArgs {
     const uint32_t* seeds1;   /* device, 2048 words each: bit (8-mer code) set if the 8-mer occurs in the adaptor */
     const uint32_t* seeds2;
     int margin;               /* hits by which one strand must lead */
+    int vec;                  /* set by the launcher: rows allow 16-byte loads */
     StrandLists L;
 };
 void launch_classify_strands(const ClassifyArgs& c, cudaStream_t st);
