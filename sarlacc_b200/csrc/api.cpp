@@ -798,10 +798,13 @@ int pair_rows_default(int maxlen = 1 << 30) {
 struct Geometry { int G, C; bool solo; int pair; };
 Geometry geometry_for(const Plan& P, int maxlen = 1 << 30, bool by_length = false) {
     /* by_length: the launch walks its reads in order of length, which keeps a warp's alignments in step however short
-     * they are.  Measured on configs[3] (1 M x 96 barcodes, profiles/r02_history.md): ordering alone 0.106 -> 0.074 s with the
-     * two-lane one-row kernel; the solo kernel on top of it 0.077 s -- so barcode-length reads keep the two-lane kernel
-     * (SARLACC_SOLO_SHORT=1 switches, for tuning). */
-    static const bool solo_short = std::getenv("SARLACC_SOLO_SHORT") != nullptr;
+     * they are, so barcode-length reads can take the solo kernel too.  Measured on configs[3] (1 M x 96 barcodes,
+     * profiles/r02_history.md): ordering alone 0.106 -> 0.074 s with the two-lane one-row kernel, 0.066 s with the solo
+     * kernel (SARLACC_SOLO_SHORT=0 keeps the two-lane kernel, for comparison). */
+    static const bool solo_short = [] {
+        const char* e = std::getenv("SARLACC_SOLO_SHORT");
+        return e ? std::atoi(e) != 0 : true;
+    }();
     if (P.solo && (pair_rows_default(maxlen) ? P.nref == 1 : (by_length && solo_short))) return Geometry{1, P.L, true, 1};
     return Geometry{P.G, P.C, false, pair_rows_default(maxlen)};
 }
@@ -831,6 +834,22 @@ const char* g_last_kernel = "";
 long long plan_groups(const Plan& P, bool trace) {
     if (!P.fast) return 0;
     const Geometry g = geometry_for(P);
+    AlignArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.L = P.L;
+    A.nref = P.nref;
+    A.enc_n = P.enc->n;
+    A.G = g.G;
+    A.C = g.C;
+    A.solo = g.solo ? 1 : 0;
+    A.pair_rows = g.pair;
+    return wavefront_groups(A, trace);
+}
+
+/* The same for the geometry a launch over windows of at most `maxlen` rows takes. */
+long long launch_groups(const Plan& P, int maxlen, bool by_length, bool trace) {
+    if (!P.fast) return 0;
+    const Geometry g = geometry_for(P, maxlen, by_length);
     AlignArgs A;
     std::memset(&A, 0, sizeof(A));
     A.L = P.L;
@@ -1224,7 +1243,7 @@ const char* run_pair_device(const Plan* const plan[2], const DevPlan* const D[2]
     Range nvtx("sarlacc: both adaptors x both windows");
     /* Speculative record writing (kernels.h: StrandLists): only for the wavefront kernels' row-pair form, whose launches
      * can take a list of reads with device-side bounds. */
-    bool spec = speculate_records() && dynamic_distribution() && m >= 1024 && m < (1LL << 31);
+    bool spec = speculate_records() && dynamic_distribution() && m >= 512 && m < (1LL << 31);
     for (int a = 0; a < 2 && spec; ++a) spec = plan[a]->fast && geometry_for(*plan[a], maxlen).pair != 0;
     if (spec) spec = prepare_seeds(S, *plan[0], *plan[1], st);
     StrandLists L;
@@ -1258,6 +1277,10 @@ const char* run_pair_device(const Plan* const plan[2], const DevPlan* const D[2]
         CA.seeds1 = S.seeds.as<uint32_t>();
         CA.seeds2 = S.seeds.as<uint32_t>() + 2048;
         CA.margin = 3;
+        /* test switch (read per call): 1 turns every prediction round (all reads take the re-run path unless unsure),
+         * 2 makes every read unsure (both strands with records) */
+        const char* tmode = std::getenv("SARLACC_SPEC_TEST");
+        CA.test_mode = tmode ? std::atoi(tmode) : 0;
         CA.L = L;
         if (stride_f != stride_b) spec = false;
         else {
@@ -1326,7 +1349,6 @@ const char* run_pair_device(const Plan* const plan[2], const DevPlan* const D[2]
             redo.index = rev_strand ? L.list_rev : L.list_fwd;
             redo.range = L.ranges + (rev_strand ? 10 : 8);
             redo.next = next + 8 + r;
-            redo.grid = sms;
             redo.fill_empty = false;
             forward_once(*plan[a], *D[a], S.s[r], st, on_front ? rows_f : rows_b, on_front ? lens_f : lens_b, m,
                          on_front ? stride_f : stride_b, maxlen, true, dev, sms, nullptr, nullptr, &redo);
@@ -1872,7 +1894,10 @@ struct DeviceJob {
             }
             /* Barcode-length reads, score-only: walk the chunk in order of length (counting sort), so that the alignments a
              * warp works on side by side end together -- 24-row alignments otherwise spend half their steps waiting for
-             * whichever lane finishes next (configs[3]: 0.11 s -> see profiles/r02_history.md). */
+             * whichever lane finishes next (configs[3]: 0.11 s -> see profiles/r02_history.md).  Group g of the launch takes
+             * positions g, g + NG, ... of the order: every second round of NG positions is turned round, so that a group's
+             * reads add up to about the same number of rows (shortest + longest, ...) instead of the last groups getting
+             * the longest read of every round. */
             const int32_t* d_order = nullptr;
             if (!trace && P.fast && maxlen < 48 && m > 1 && std::getenv("SARLACC_NO_LENGTH_ORDER") == nullptr) {
                 s.h_order.reserve(sizeof(int32_t) * (size_t)m);
@@ -1883,10 +1908,18 @@ struct DeviceJob {
                 for (long long i = 0; i < m; ++i) ++start[(size_t)hl[i] + 1];
                 for (int l = 0; l <= maxlen; ++l) start[(size_t)l + 1] += start[(size_t)l];
                 for (long long i = 0; i < m; ++i) ho[start[(size_t)hl[i]]++] = (int32_t)i;
+                const long long NG = launch_groups(P, maxlen, true, false);
+                if (NG > 0 && std::getenv("SARLACC_NO_SERPENTINE") == nullptr) {
+                    std::reverse(ho, ho + m);          /* longest first: a last, partial round holds the shortest reads */
+                    for (long long r0 = NG; r0 < m; r0 += 2 * NG) std::reverse(ho + r0, ho + std::min(m, r0 + NG));
+                }
                 CUDA_CHECK(cudaMemcpyAsync(s.d_order.p, ho, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
                 d_order = s.d_order.as<int32_t>();
             }
-            if (prev_gate) CUDA_CHECK(cudaStreamWaitEvent(s.st, prev_gate, 0));
+            /* chunks with tracebacks run their forward passes one after the other; score-only chunks may overlap, so that
+             * the next chunk's first blocks fill the tail of this one's launch */
+            static const bool gate_all = std::getenv("SARLACC_GATE_CHUNKS") != nullptr;
+            if (prev_gate && (trace || gate_all)) CUDA_CHECK(cudaStreamWaitEvent(s.st, prev_gate, 0));
             run_device(P, D, s.scratch, s.st, s.d_rows.as<uint16_t>(), s.d_lens.as<int32_t>(), m, stride, maxlen, trace, dev, sms,
                        nullptr, nullptr, nullptr, nullptr, d_order);
             CUDA_CHECK(cudaEventRecord(s.gate, s.st));

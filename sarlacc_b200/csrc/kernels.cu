@@ -1296,7 +1296,9 @@ __global__ void __launch_bounds__(256) classify_strands(const ClassifyArgs A)
             fwd += __shfl_xor_sync(FULL, fwd, d);
             rev += __shfl_xor_sync(FULL, rev, d);
         }
-        const unsigned pred = fwd >= rev + A.margin ? 0u : (rev >= fwd + A.margin ? 1u : 2u);
+        unsigned pred = fwd >= rev + A.margin ? 0u : (rev >= fwd + A.margin ? 1u : 2u);
+        if (A.test_mode == 1 && pred != 2u) pred ^= 1u;
+        if (A.test_mode == 2) pred = 2u;
         const bool mine = live && sub == 0;
         if (mine) A.L.predicted[r] = (uint8_t)pred;
         /* append to the four lists, one atomic per list per warp */

@@ -185,6 +185,7 @@ struct ClassifyArgs {
     const uint32_t* seeds2;
     int margin;               /* hits by which one strand must lead */
     int vec;                  /* set by the launcher: rows allow 16-byte loads */
+    int test_mode;            /* 0; tests: 1 inverts the predictions, 2 calls every read unsure */
     StrandLists L;
 };
 void launch_classify_strands(const ClassifyArgs& c, cudaStream_t st);

@@ -248,3 +248,22 @@ def test_compute_threshold_edge_cases():
             want, got = api._compute_threshold(real, scr, err), native.compute_threshold(real, scr, err)
             assert (np.isnan(want) and np.isnan(got)) or want == got, (nr, ns, err, want, got)
     assert np.isnan(native.compute_threshold(np.zeros(0), np.zeros(3), 0.01))
+
+
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_speculative_records_do_not_change_results(enc, port, mode, monkeypatch):
+    """The strand predictor only decides where traceback records are written (kernels.h: StrandLists).  With every
+    prediction inverted (all reads go through the re-run) or every read called unsure (records on both strands) the
+    chunk's results are those of the default run and of the four reference calls."""
+    from sarlacc_b200 import native, synth
+    n = 3000
+    ch = native.Chunk(4096, 250, enc)
+    ch.load_mock(n, VIGNETTE_A1, VIGNETTE_A2, seed=31, first_index=10 ** 9)
+    base = ch.adaptor_align(5, 1, VIGNETTE_A1, VIGNETTE_A2, (S1, E1), ((), ()))
+    monkeypatch.setenv("SARLACC_SPEC_TEST", mode)
+    got = ch.adaptor_align(5, 1, VIGNETTE_A1, VIGNETTE_A2, (S1, E1), ((), ()))
+    monkeypatch.delenv("SARLACC_SPEC_TEST")
+    check_pair(got, (base[1], base[2], base[3]))
+    front, back, widths, _ = synth.mock_windows(n, VIGNETTE_A1, VIGNETTE_A2, seed=31, first_index=10 ** 9)
+    check_pair(got, compose(port, enc, front, back, widths, 5, 1, VIGNETTE_A1, VIGNETTE_A2, (S1, E1), ([], [])))
+    ch.close()
