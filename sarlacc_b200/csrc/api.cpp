@@ -2207,6 +2207,7 @@ struct PairJob {
 
         double t_drain = 0, t_pack = 0, t_enq = 0;
         cudaEvent_t prev_gate = nullptr;
+        cudaEvent_t prev_upload = nullptr;
         cudaEvent_t pair_free[2] = {nullptr, nullptr};     /* behind the tracebacks of the last chunk that used record group p */
         int pair_turn = 0;
         const bool host_pack = std::getenv("SARLACC_HOST_PACK") != nullptr;     /* A/B: pack on the host as before */
@@ -2270,6 +2271,10 @@ struct PairJob {
             s.d_tmp.reserve(sizeof(double) * 4 * (size_t)m);      /* the four forward passes' scores */
             s.d_out.reserve(F.total);
             s.h_out.reserve(F.total);
+            /* uploads in chunk order: copies of different streams share the link, and chunk k's forward passes should not
+             * wait for bytes of chunk k+1 (at the start of a call three chunks are enqueued at once) */
+            static const bool chain_uploads = std::getenv("SARLACC_NO_UPLOAD_CHAIN") == nullptr;
+            if (prev_upload && chain_uploads) CUDA_CHECK(cudaStreamWaitEvent(s.st, prev_upload, 0));
             CUDA_CHECK(cudaEventRecord(s.t_begin, s.st));
             CUDA_CHECK(cudaMemcpyAsync(s.d_lens.p, s.h_lens.p, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
             CUDA_CHECK(cudaMemcpyAsync(s.d_lens2.p, s.h_lens2.p, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
@@ -2298,9 +2303,14 @@ struct PairJob {
                 CUDA_CHECK(cudaMemcpyAsync(s.d_width.p, s.h_width.p, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
             }
             CUDA_CHECK(cudaEventRecord(s.t_h2d, s.st));      /* uploads done; the device packers follow */
+            prev_upload = s.t_h2d;
             launch_pending_pack(pf, s.st);
             launch_pending_pack(pb, s.st);
-            if (prev_gate) CUDA_CHECK(cudaStreamWaitEvent(s.st, prev_gate, 0));
+            /* consecutive chunks use different record sets (pair_free below), so their forward passes need not wait for
+             * each other: the next chunk's first blocks start in the tail of this chunk's last launches, as the sub-ranges
+             * of a device-resident chunk do (SARLACC_GATE_CHUNKS=1 keeps them in order, for comparison) */
+            static const bool gate_all = std::getenv("SARLACC_GATE_CHUNKS") != nullptr;
+            if (prev_gate && gate_all) CUDA_CHECK(cudaStreamWaitEvent(s.st, prev_gate, 0));
             uint8_t* d = s.d_out.as<uint8_t>();
             PairDeviceOut po;
             po.reversed = d + F.o_rev;
@@ -3412,6 +3422,8 @@ struct sarlacc_chunk {
     Encoding enc;
     int seq_encoding = SARLACC_SEQ_ASCII;
     cudaStream_t st = nullptr, tb = nullptr, cp = nullptr;
+    cudaStream_t fw[2] = {nullptr, nullptr};    /* forward passes of the sub-ranges of either scratch parity (see sarlacc_chunk_adaptor_align) */
+    cudaEvent_t rows_ready = nullptr;
     DevBuf rows_f, rows_b, lens_f, lens_b, width, flipped, srows_f, srows_b, barcodes;
     RawStage raw_f, raw_b;
     PinBuf h_lens_f, h_lens_b, h_width;
@@ -3569,6 +3581,8 @@ void sarlacc_chunk_free(sarlacc_chunk* c) {
     c->score_scratch.release();
     c->score_scratch2.release();
     c->side.release();
+    for (int k = 0; k < 2; ++k) if (c->fw[k]) cudaStreamDestroy(c->fw[k]);
+    if (c->rows_ready) cudaEventDestroy(c->rows_ready);
     for (auto& p : c->plans) p->d.buf.release();
     for (int k = 0; k < 2; ++k) {
         if (c->fwd_done[k]) cudaEventDestroy(c->fwd_done[k]);
@@ -3826,13 +3840,27 @@ int sarlacc_chunk_adaptor_align(sarlacc_chunk* c, double gapopen, double gapext,
         const char* ce = std::getenv("SARLACC_CHUNK");
         if (ce && std::atoll(ce) > 0) sub = std::atoll(ce);
         chunk_mark(c, 1, true);
+        /* Consecutive sub-ranges use different scratch, so their forward passes need not wait for each other: each parity
+         * has its own stream, and the first blocks of sub-range k+1 start in the tail of sub-range k's last launches. */
+        const bool apart = overlap_launches() && n > sub;
+        bool forked[2] = {false, false};
+        if (apart) {
+            for (int k = 0; k < 2; ++k) if (!c->fw[k]) CUDA_CHECK(cudaStreamCreateWithFlags(&c->fw[k], cudaStreamNonBlocking));
+            if (!c->rows_ready) CUDA_CHECK(cudaEventCreateWithFlags(&c->rows_ready, cudaEventDisableTiming));
+            CUDA_CHECK(cudaEventRecord(c->rows_ready, c->st));
+        }
         const char* name = "";
         for (long long off = 0; off < n; off += sub) {
             const long long m = std::min<long long>(sub, n - off);
             const int b = c->parity;
             c->parity ^= 1;
+            cudaStream_t fs = apart ? c->fw[b] : c->st;
+            if (apart && !forked[b]) {
+                CUDA_CHECK(cudaStreamWaitEvent(fs, c->rows_ready, 0));
+                forked[b] = true;
+            }
             if (c->tb_pending[b]) {
-                CUDA_CHECK(cudaStreamWaitEvent(c->st, c->tb_done[b], 0));
+                CUDA_CHECK(cudaStreamWaitEvent(fs, c->tb_done[b], 0));
                 c->tb_pending[b] = false;
             }
             PairDeviceOut po;
@@ -3845,13 +3873,14 @@ int sarlacc_chunk_adaptor_align(sarlacc_chunk* c, double gapopen, double gapext,
                 po.sec_width[k] = reinterpret_cast<int32_t*>(d + o_sw[k]) + off;
             }
             po.pitch = n;
-            name = run_pair_device(plan, D, c->pair[b], c->st, c->tb, c->fwd_done[b], c->tb_done[b],
+            name = run_pair_device(plan, D, c->pair[b], fs, c->tb, c->fwd_done[b], c->tb_done[b],
                                    c->rows_f.as<uint16_t>() + (size_t)off * c->stride, c->lens_f.as<int32_t>() + off, c->stride,
                                    c->rows_b.as<uint16_t>() + (size_t)off * c->stride, c->lens_b.as<int32_t>() + off, c->stride,
                                    m, c->maxlen, c->has_width ? c->width.as<int32_t>() + off : nullptr,
                                    c->tmp.as<double>() + 4 * (size_t)off, po, c->sms);
             c->tb_pending[b] = true;
         }
+        for (int k = 0; k < 2; ++k) if (forked[k]) CUDA_CHECK(cudaStreamWaitEvent(c->st, c->fwd_done[k], 0));
         chunk_mark(c, 1, false);
         for (int k = 0; k < 2; ++k) {
             const Geometry g = geometry_for(*plan[k], c->maxlen);
