@@ -140,6 +140,9 @@ __device__ __forceinline__ void land_step(int& lf0, int& lf1, bool pd, bool p5, 
  * maximum; pd = (m > v) && (m > h) is the same predicate; p5 is recorded as (m > v) || (h > mv), which equals (h > v)
  * whenever pd is false -- the only case in which the traceback (and land_step) read it: if m <= v then mv = v, and if
  * m > v but the diagonal lost, h >= m > v. */
+#ifndef SARLACC_WF_SHORT_SCORE
+#define SARLACC_WF_SHORT_SCORE 1   /* 1: the score-only kernels of the lane-group geometries take the short chain too (70 bp: 1215 -> 1235 GCUPS) */
+#endif
 #ifndef SARLACC_WF_SHORT_CHAIN
 #define SARLACC_WF_SHORT_CHAIN 0   /* 1: every row-pair kernel takes the short chain (A/B builds) */
 #endif
@@ -517,7 +520,7 @@ __global__ void __launch_bounds__(kBlock, WfBounds<C>::min_blocks) wf_forward2(c
      * selects, column 0 is a constant boundary -- the geometry for 20-24 bp references (adaptor2, barcodes). */
     using WT = typename FlagWord<C>::type;
     static_assert(kSkew == 2, "the row-pair kernel lags its left neighbour by one two-row step: record layout and traceback assume SARLACC_WF_SKEW == 2");
-    constexpr bool SHORT = (SOLO && !TRACE) || (SARLACC_WF_SHORT_CHAIN != 0);     /* see pick_move */
+    constexpr bool SHORT = (!TRACE && (SOLO || SARLACC_WF_SHORT_SCORE != 0)) || (SARLACC_WF_SHORT_CHAIN != 0);     /* see pick_move */
     const unsigned one = A.one;
     extern __shared__ double smem_d[];
     const int L = A.L, nref = A.nref, encn = A.enc_n;

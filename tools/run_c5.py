@@ -49,13 +49,15 @@ def run(total, chunk, rank, world, local, check_stride=0, error=0.01, timing=Tru
     ch.adaptor_align(5, 1, A1, A2, (S1, E1), ((), ()), out={"score1": real1.data_ptr()}, out_pitch=nn)
     ch.scrambled_scores(5, 1, A1, A2, seed=SCR_SEED, first_index=lo, score1=scr1.data_ptr(), score2=scr2.data_ptr())
     ch.sync()
-    native.compute_threshold((real1.data_ptr(), min(chunk, nn)), (scr1.data_ptr(), min(chunk, nn)), error, device=local)   # loads the sort kernels
     gathered = [None] * 4
     if world > 1:       # receive buffers on rank 0 and one small gather, so that the timed one finds its channels set up
-        gathered = [torch.empty(world * share, dtype=torch.float64, device=dev) if rank == 0 else None for _ in range(4)]
+        gathered = [torch.zeros(world * share, dtype=torch.float64, device=dev) if rank == 0 else None for _ in range(4)]
         dist.gather(real1[:share] if n == share else torch.cat([real1[:n], real1.new_zeros(share - n)]),
                     list(gathered[0].chunk(world)) if rank == 0 else None, dst=0)     # same size as the timed ones: connections and buffers set up
         torch.cuda.synchronize()
+    if rank == 0:       # loads the sort kernels and sizes the library's cached sort buffers for the job (a device allocation of this size can take 0.5 s)
+        w1, w2 = (gathered[0], gathered[2]) if world > 1 else (real1, scr1)
+        native.compute_threshold((w1.data_ptr(), total), (w2.data_ptr(), total), error, device=local)
     ch.set_timing(timing)
     _lib.lib.sarlacc_kernel_launches(1)
     if world > 1:
