@@ -1172,7 +1172,7 @@ bool speculate_records() {
     return on;
 }
 
-/* 8-mer seed bitmaps (2 x 2048 words) of the two adaptors' A/C/G/T stretches, for the strand predictor (kernels.h:
+/* 8-mer seed table (4096 words, two bits per 8-mer) of the two adaptors' A/C/G/T stretches, for the strand predictor (kernels.h:
  * StrandLists).  Usable only if both adaptors have enough seeds to out-vote chance hits. */
 bool prepare_seeds(PairScratch& S, const Plan& p1, const Plan& p2, cudaStream_t st) {
     std::string key;
@@ -1196,9 +1196,10 @@ bool prepare_seeds(PairScratch& S, const Plan& p1, const Plan& p2, cudaStream_t 
             code = ((code << 2) | (acgt ? b : 0u)) & 0xFFFFu;
             valid = acgt ? valid + 1 : 0;
             if (valid >= 8) {
-                uint32_t& w = bits[(size_t)which * 2048 + (code >> 5)];
-                if (!((w >> (code & 31)) & 1u)) ++count[which];
-                w |= 1u << (code & 31);
+                uint32_t& w = bits[code >> 4];
+                const unsigned at = (code & 15u) * 2u + (unsigned)which;
+                if (!((w >> at) & 1u)) ++count[which];
+                w |= 1u << at;
             }
         }
         ++which;
@@ -1274,9 +1275,17 @@ const char* run_pair_device(const Plan* const plan[2], const DevPlan* const D[2]
         CA.lens_back = lens_b;
         CA.n = m;
         CA.stride = stride_f;
-        CA.seeds1 = S.seeds.as<uint32_t>();
-        CA.seeds2 = S.seeds.as<uint32_t>() + 2048;
+        CA.seeds = S.seeds.as<uint32_t>();
         CA.margin = 3;
+        {
+            /* the predictor reads the first bases of each window only: an adaptor further in than that leaves the read
+             * "unsure" (records on both strands, as without speculation) */
+            static const int scan = [] {
+                const char* e = std::getenv("SARLACC_SPEC_SCAN");
+                return e && std::atoi(e) > 0 ? std::atoi(e) : 128;
+            }();
+            CA.scan = scan;
+        }
         /* test switch (read per call): 1 turns every prediction round (all reads take the re-run path unless unsure),
          * 2 makes every read unsure (both strands with records) */
         const char* tmode = std::getenv("SARLACC_SPEC_TEST");

@@ -1222,10 +1222,10 @@ __global__ void resolve_strand(const StrandArgs S)
     }
 }
 
-/* See StrandLists (kernels.h).  Exact 8-mer seeds of adaptor1 / adaptor2 counted in both windows.  Eight lanes share a
- * read: lane k counts the 8-mers ENDING in bases [32k, 32k + 32) (+256, ...) of each window, for which it also looks at
- * the seven bases before them; four reads per warp, warps stride over the launch. */
-__device__ __forceinline__ void count_seeds(const uint16_t* row, int len, int s, const uint32_t* s1, const uint32_t* s2, int& h1, int& h2) {
+/* See StrandLists (kernels.h).  Exact 8-mer seeds of adaptor1 / adaptor2 counted in the first `scan` bases of both
+ * windows.  Four lanes share a read: lane k counts the 8-mers ENDING in bases [32k, 32k + 32) (+128, ...) of each window,
+ * for which it also looks at the seven bases before them; eight reads per warp, warps stride over the launch. */
+__device__ __forceinline__ void count_seeds(const uint16_t* row, int len, int s, const uint32_t* tab, int& h1, int& h2) {
     unsigned code = 0;
     int valid = 0;
     const int lo = s >= 7 ? s - 7 : 0, hi = min(len, s + 32);
@@ -1234,14 +1234,15 @@ __device__ __forceinline__ void count_seeds(const uint16_t* row, int len, int s,
         code = ((code << 2) | (unsigned)(o > 0 ? o - 1 : 0)) & 0xFFFFu;
         valid = o > 0 ? valid + 1 : 0;
         if (valid >= 8 && i >= s) {
-            h1 += (s1[code >> 5] >> (code & 31)) & 1u;
-            h2 += (s2[code >> 5] >> (code & 31)) & 1u;
+            const unsigned t = tab[code >> 4] >> ((code & 15u) * 2u);
+            h1 += t & 1u;
+            h2 += (t >> 1) & 1u;
         }
     }
 }
 
 /* the same from 16-byte loads (rows 16-byte aligned, pitch a multiple of 8 entries) */
-__device__ __forceinline__ void count_seeds_vec(const uint16_t* row, int len, int s, const uint32_t* s1, const uint32_t* s2, int& h1, int& h2) {
+__device__ __forceinline__ void count_seeds_vec(const uint16_t* row, int len, int s, const uint32_t* tab, int& h1, int& h2) {
     uint32_t w[20];                                    /* bases s-8 .. s+31, two per word */
     const uint4* q = reinterpret_cast<const uint4*>(row + s);
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
@@ -1262,40 +1263,41 @@ __device__ __forceinline__ void count_seeds_vec(const uint16_t* row, int len, in
         code = ((code << 2) | (unsigned)(o > 0 ? o - 1 : 0)) & 0xFFFFu;
         valid = o > 0 ? valid + 1 : 0;
         if (jj >= 8 && valid >= 8) {
-            h1 += (s1[code >> 5] >> (code & 31)) & 1u;
-            h2 += (s2[code >> 5] >> (code & 31)) & 1u;
+            const unsigned t = tab[code >> 4] >> ((code & 15u) * 2u);
+            h1 += t & 1u;
+            h2 += (t >> 1) & 1u;
         }
     }
 }
 
 __global__ void __launch_bounds__(256) classify_strands(const ClassifyArgs A)
 {
-    __shared__ uint32_t s1[2048], s2[2048];
-    for (int x = threadIdx.x; x < 2048; x += blockDim.x) { s1[x] = A.seeds1[x]; s2[x] = A.seeds2[x]; }
+    __shared__ uint32_t tab[4096];          /* two bits per 8-mer: bit 0 = occurs in adaptor1, bit 1 = in adaptor2 */
+    for (int x = threadIdx.x; x < 4096; x += blockDim.x) tab[x] = A.seeds[x];
     __syncthreads();
-    const unsigned lane = threadIdx.x & 31, sub = lane & 7, slot = lane >> 3;
+    const unsigned lane = threadIdx.x & 31, sub = lane & 3, slot = lane >> 2;
     const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
     const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const bool vec = A.vec != 0;
-    for (long long base = warp * 4; base < A.n; base += warps * 4) {
+    for (long long base = warp * 8; base < A.n; base += warps * 8) {
         const long long r = base + slot;
         const bool live = r < A.n;
         int fwd = 0, rev = 0;          /* adaptor1 x front + adaptor2 x back  vs  adaptor1 x back + adaptor2 x front */
         if (live) {
             const uint16_t* rf = A.rows_front + r * (long long)A.stride;
             const uint16_t* rb = A.rows_back + r * (long long)A.stride;
-            const int lf = A.lens_front[r], lb = A.lens_back[r];
-            for (int s = (int)sub * 32; s < lf; s += 256) {
-                if (vec) count_seeds_vec(rf, lf, s, s1, s2, fwd, rev);
-                else count_seeds(rf, lf, s, s1, s2, fwd, rev);
+            const int lf = min(A.lens_front[r], A.scan), lb = min(A.lens_back[r], A.scan);     /* the adaptors sit at the start of their windows */
+            for (int s = (int)sub * 32; s < lf; s += 128) {
+                if (vec) count_seeds_vec(rf, lf, s, tab, fwd, rev);
+                else count_seeds(rf, lf, s, tab, fwd, rev);
             }
-            for (int s = (int)sub * 32; s < lb; s += 256) {
-                if (vec) count_seeds_vec(rb, lb, s, s1, s2, rev, fwd);
-                else count_seeds(rb, lb, s, s1, s2, rev, fwd);
+            for (int s = (int)sub * 32; s < lb; s += 128) {
+                if (vec) count_seeds_vec(rb, lb, s, tab, rev, fwd);
+                else count_seeds(rb, lb, s, tab, rev, fwd);
             }
         }
 #pragma unroll
-        for (int d = 1; d < 8; d <<= 1) {
+        for (int d = 1; d < 4; d <<= 1) {
             fwd += __shfl_xor_sync(FULL, fwd, d);
             rev += __shfl_xor_sync(FULL, rev, d);
         }
@@ -1733,7 +1735,7 @@ void launch_classify_strands(const ClassifyArgs& c, cudaStream_t st) {
     if (c.n <= 0) return;
     ClassifyArgs a = c;
     a.vec = (c.stride % 8 == 0 && (reinterpret_cast<uintptr_t>(c.rows_front) & 15) == 0 && (reinterpret_cast<uintptr_t>(c.rows_back) & 15) == 0) ? 1 : 0;
-    const long long blocks = (c.n + 31) / 32;           /* 8 warps x 4 reads */
+    const long long blocks = (c.n + 63) / 64;           /* 8 warps x 8 reads */
     classify_strands<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, st>>>(a);
     finish_strand_lists<<<1, 1, 0, st>>>(c.L.ranges);
 }

@@ -181,9 +181,9 @@ struct ClassifyArgs {
     const int32_t* lens_front; const int32_t* lens_back;
     long long n;
     int stride;
-    const uint32_t* seeds1;   /* device, 2048 words each: bit (8-mer code) set if the 8-mer occurs in the adaptor */
-    const uint32_t* seeds2;
+    const uint32_t* seeds;    /* device, 4096 words: two bits per 8-mer code c (word c >> 4, bits 2 * (c & 15)): occurs in adaptor1 / in adaptor2 */
     int margin;               /* hits by which one strand must lead */
+    int scan;                 /* bases of each window that are looked at (the adaptors sit at the windows' start) */
     int vec;                  /* set by the launcher: rows allow 16-byte loads */
     int test_mode;            /* 0; tests: 1 inverts the predictions, 2 calls every read unsure */
     StrandLists L;

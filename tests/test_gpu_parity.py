@@ -336,3 +336,21 @@ def test_c4_ninety_six_barcodes(port, enc):
     assert np.mean(bid - 1 == pick) > 0.95
     # one barcode at a time (barcode_align, the reference's own call) goes through the same length-ordered walk
     assert np.array_equal(native.barcode_align(seqs, enc, 5, 1, barcodes[5]), exp[5])
+
+
+def test_barcode_sequences_beyond_one_round_of_the_grid(port, enc):
+    """More barcode-length sequences than one launch's lanes (56 832 in the one-thread-per-alignment kernel): the chunk
+    is walked longest first with every second round of lanes turned round, and chunks overlap on the device -- neither
+    may show in the results."""
+    from sarlacc_b200 import native, synth
+    barcodes = synth.random_barcodes(3, 24, 8, seed=3100)
+    seqs, _ = synth.mock_barcode_sequences(300000, barcodes, seed=3101)
+    bid, best, nxt, mat = native.barcode_align_multi(seqs, enc, 5, 1, barcodes, all_scores=True)
+    arg = (seqs.seq_pool, seqs.seq_off), (seqs.qual_pool, seqs.qual_off)
+    exp = np.stack([port.align_score_only(*arg, enc, 5, 1, b, local=False, nthreads=8) for b in barcodes])
+    assert np.array_equal(mat, exp)
+    order = np.argsort(-exp, axis=0, kind="stable")
+    assert np.array_equal(best, np.take_along_axis(exp, order[:1], 0)[0])
+    assert np.array_equal(bid, order[0] + 1)            # ties: the first barcode wins (strict >)
+    sec = np.take_along_axis(exp, order[1:2], 0)[0]
+    assert np.array_equal(nxt, sec)
