@@ -1158,42 +1158,8 @@ __global__ void __launch_bounds__(128) traceback(const TraceArgs T)
     }
 }
 
-/* .resolve_strand (R/adaptorAlign.R:112-122): fscore = pmax(s_a1_front,0) + pmax(s_a2_back,0), rscore likewise on
- * the swapped windows, reversed = fscore < rscore (strict); then cur.starts[rev,] <- cur.rc.starts[rev,] (:195-196)
- * and adaptor2's start/end flipped into read coordinates, width - x + 1 (:66-71; unaligned 0 -> width + 1). */
-__global__ void resolve_select(const SelectArgs S)
-{
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= S.n) return;
-    const double f = __dadd_rn(fmax(S.a1_front.score[i], 0.0), fmax(S.a2_back.score[i], 0.0));
-    const double r = __dadd_rn(fmax(S.a1_back.score[i], 0.0), fmax(S.a2_front.score[i], 0.0));
-    const bool rev = f < r;
-    S.reversed[i] = rev ? 1 : 0;
-    const ResultSet& A = rev ? S.a1_back : S.a1_front;
-    const ResultSet& B = rev ? S.a2_front : S.a2_back;
-    S.score1[i] = A.score[i];
-    S.start1[i] = A.start[i];
-    S.end1[i] = A.end[i];
-    for (int s = 0; s < S.nsec1; ++s) {
-        S.sec_start1[(long long)s * S.n + i] = A.sec_start[(long long)s * S.n + i];
-        S.sec_width1[(long long)s * S.n + i] = A.sec_width[(long long)s * S.n + i];
-    }
-    S.score2[i] = B.score[i];
-    int st = B.start[i], en = B.end[i];
-    if (S.width) {
-        const int w = S.width[i];
-        st = w - st + 1;
-        en = w - en + 1;
-    }
-    S.start2[i] = st;
-    S.end2[i] = en;
-    for (int s = 0; s < S.nsec2; ++s) {
-        S.sec_start2[(long long)s * S.n + i] = B.sec_start[(long long)s * S.n + i];
-        S.sec_width2[(long long)s * S.n + i] = B.sec_width[(long long)s * S.n + i];
-    }
-}
-
-/* .resolve_strand alone (R/adaptorAlign.R:112-122), on four score vectors: reversed = fscore < rscore (strict), and
+/* .resolve_strand (R/adaptorAlign.R:112-122) on four score vectors: fscore = pmax(s_a1_front, 0) + pmax(s_a2_back, 0),
+ * rscore likewise on the swapped windows, reversed = fscore < rscore (strict), and
  * the two scores R keeps (ifelse(is.reverse, revcomp, forward), R/getAdaptorThresholds.R:123-127 / R/adaptorAlign.R:192-196).
  * Run between the forward passes and the tracebacks of a fused both-ends run, so that only the kept strand is walked. */
 __global__ void resolve_strand(const StrandArgs S)
@@ -1761,12 +1727,6 @@ void launch_pack_rows(const PackArgs& a, cudaStream_t st) {
     long long grid = (a.n + 7) / 8;
     if (grid > (long long)sms * 16) grid = (long long)sms * 16;
     pack_rows_kernel<<<(int)grid, 256, 0, st>>>(a);
-}
-
-void launch_resolve_select(const SelectArgs& s, cudaStream_t st) {
-    const int block = 256;
-    const int grid = (int)((s.n + block - 1) / block);
-    if (grid > 0) resolve_select<<<grid, block, 0, st>>>(s);
 }
 
 void launch_fill_empty(const AlignArgs& a, cudaStream_t st) {

@@ -124,27 +124,6 @@ struct TraceArgs {
     long long ops_stride;
 };
 
-/* One alignment result set on the device ([n] / [nsec][n] with row pitch n). */
-struct ResultSet {
-    const double* score;
-    const int32_t* start;
-    const int32_t* end;
-    const int32_t* sec_start;
-    const int32_t* sec_width;
-};
-
-/* Fused .resolve_strand + row selection + adaptor2 coordinate flip (R/adaptorAlign.R:112-122,192-196,66-71). */
-struct SelectArgs {
-    long long n;
-    ResultSet a1_front, a2_back, a1_back, a2_front;
-    int nsec1, nsec2;
-    const int32_t* width;      /* read widths, or null to skip the adaptor2 flip */
-    uint8_t* reversed;
-    double* score1; int32_t* start1; int32_t* end1; int32_t* sec_start1; int32_t* sec_width1;
-    double* score2; int32_t* start2; int32_t* end2; int32_t* sec_start2; int32_t* sec_width2;
-};
-void launch_resolve_select(const SelectArgs& s, cudaStream_t st);
-
 /* .resolve_strand on four device score vectors (R/adaptorAlign.R:112-122): reversed (may be null) and the two kept scores. */
 struct StrandArgs {
     long long n;
