@@ -1702,7 +1702,11 @@ void launch_classify_strands(const ClassifyArgs& c, cudaStream_t st) {
     ClassifyArgs a = c;
     a.vec = (c.stride % 8 == 0 && (reinterpret_cast<uintptr_t>(c.rows_front) & 15) == 0 && (reinterpret_cast<uintptr_t>(c.rows_back) & 15) == 0) ? 1 : 0;
     const long long blocks = (c.n + 63) / 64;           /* 8 warps x 8 reads */
-    classify_strands<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, st>>>(a);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long full = (long long)sms * 8;
+    classify_strands<<<(int)(blocks < full ? blocks : full), 256, 0, st>>>(a);
     finish_strand_lists<<<1, 1, 0, st>>>(c.L.ranges);
 }
 

@@ -52,6 +52,27 @@ assert np.array_equal(rev, rev2) and all(np.array_equal(r1[k], q1[k]) and np.arr
 s1, s2 = ch.scrambled_scores(5, 1, VIGNETTE_A1, VIGNETTE_A2, seed=3)
 thr = native.compute_threshold(r1[0], s1, 0.01)
 ch.close()
+# speculative records (sub-ranges of 512+ reads): strand predictor, list-driven launches, and -- with the predictions
+# inverted -- the re-run path; same results as the host-buffer entry on the same reads
+ns = 576
+f2, b2, w2, _ = synth.mock_windows(ns, VIGNETTE_A1, VIGNETTE_A2, seed=12)
+ch = native.Chunk(ns, 250, enc)
+ch.load_mock(ns, VIGNETTE_A1, VIGNETTE_A2, seed=12)
+base = ch.adaptor_align(5, 1, VIGNETTE_A1, VIGNETTE_A2, (S1, E1), ((), ()))
+os.environ["SARLACC_SPEC_TEST"] = "1"
+flipped = ch.adaptor_align(5, 1, VIGNETTE_A1, VIGNETTE_A2, (S1, E1), ((), ()))
+del os.environ["SARLACC_SPEC_TEST"]
+fa2, ba2 = ((f2.seq_pool, f2.seq_off), (f2.qual_pool, f2.qual_off)), ((b2.seq_pool, b2.seq_off), (b2.qual_pool, b2.qual_off))
+ea, eb = O.adaptor_align(*fa2, enc, 5, 1, VIGNETTE_A1, S1, E1), O.adaptor_align(*ba2, enc, 5, 1, VIGNETTE_A2)
+ec, ed = O.adaptor_align(*ba2, enc, 5, 1, VIGNETTE_A1, S1, E1), O.adaptor_align(*fa2, enc, 5, 1, VIGNETTE_A2)
+erev = (np.maximum(ea[0], 0) + np.maximum(eb[0], 0)) < (np.maximum(ec[0], 0) + np.maximum(ed[0], 0))
+for got in (base, flipped):
+    assert np.array_equal(got[1], erev)
+    for k in range(3):
+        assert np.array_equal(got[2][k], np.where(erev, ec[k], ea[k]))
+    assert np.array_equal(got[3][0], np.where(erev, ed[0], eb[0]))
+    assert np.array_equal(got[3][1], w2 - np.where(erev, ed[1], eb[1]) + 1)
+ch.close()
 # UMI neighbours
 umis = ["".join(rng.choice(list("ACGT"), 12)) for _ in range(60)]
 native.umi_group(umis + umis, 1)
