@@ -1840,6 +1840,7 @@ struct DeviceJob {
             s.busy = false;
         };
 
+        cudaEvent_t prev_upload = nullptr;
         cudaEvent_t prev_gate = nullptr;
         const bool host_pack = std::getenv("SARLACC_HOST_PACK") != nullptr;     /* A/B: pack on the host as before */
         const bool pools_pinned = !reads->seq && pointer_is_pinned(reads->seq_pool) && pointer_is_pinned(reads->qual_pool);
@@ -1875,13 +1876,20 @@ struct DeviceJob {
             s.d_lens.reserve(sizeof(int32_t) * (size_t)m);
             s.d_out.reserve(o.total);
             s.h_out.reserve(o.total);
+            /* uploads in chunk order (see the both-ends job below): chunk k's kernels should not wait for bytes of chunk k+1 */
+            static const bool chain_uploads = std::getenv("SARLACC_NO_UPLOAD_CHAIN") == nullptr;
+            if (prev_upload && chain_uploads) CUDA_CHECK(cudaStreamWaitEvent(s.st, prev_upload, 0));
             CUDA_CHECK(cudaMemcpyAsync(s.d_lens.p, s.h_lens.p, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
+            PendingPack pending;
             if (host_pack) {
                 CUDA_CHECK(cudaMemcpyAsync(s.d_rows.p, s.h_rows.p, sizeof(uint16_t) * (size_t)m * stride, cudaMemcpyHostToDevice, s.st));
             } else {
                 stage_and_pack(V, c0, c1, PT, s.h_lens.as<int32_t>(), s.d_lens.as<int32_t>(), stride, s.d_rows.as<uint16_t>(), P.L > 0,
-                               pools_pinned, s.raw, s.st, nthreads);
+                               pools_pinned, s.raw, s.st, nthreads, &pending);
             }
+            CUDA_CHECK(cudaEventRecord(s.t_h2d, s.st));
+            prev_upload = s.t_h2d;
+            launch_pending_pack(pending, s.st);
             uint8_t* d = s.d_out.as<uint8_t>();
             Outputs dev;
             dev.score = (mode == MODE_MULTI_GLOBAL && !want_all_scores) ? nullptr : reinterpret_cast<double*>(d + o.o_score);
