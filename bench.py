@@ -344,9 +344,13 @@ def main():
         torch.cuda.synchronize()
         dt = max_over_ranks((time.perf_counter() - t0) / reps)
         ph = {k: statistics.mean(p[k] for p in phases) for k in phases[0]}
-        ph_ranks = gather_ranks([ph["stage"], ph["enqueue"], ph["wait_copy_out"], ph["total"], ph["upload_sum"], ph["kernels_copyback_sum"]])
-        # raw bases + qualities of both windows, two 8-byte offsets and a 4-byte length per window, read widths
-        h2d = int(2 * (sub_f.seq_off[-1] + sub_b.seq_off[-1]) + 2 * ne * (16 + 4) + ne * 4)
+        ph_ranks = gather_ranks([ph["stage"], ph["enqueue"], ph["wait_copy_out"], ph["total"], ph["upload_sum"], ph["kernels_copyback_sum"], ph["upload_bytes"]])
+        # plain bytes: bases + qualities of both windows, two 8-byte offsets and a 4-byte length per window, read widths.
+        # What the library actually copied (it counts the window data; lengths and widths added here) is the same unless
+        # SARLACC_PACK_SEQ=1 makes it send the bases as 4-bit codes (include/sarlacc_b200.h; off by default).
+        h2d_plain = int(2 * (sub_f.seq_off[-1] + sub_b.seq_off[-1]) + 2 * ne * (16 + 4) + ne * 4)
+        h2d_ranks = [int(r[6]) + 2 * ne * 4 + ne * 4 for r in ph_ranks]
+        h2d = max(h2d_ranks)
         d2h = ne * (1 + (8 + 4 + 4 + 8 * len(s1)) + (8 + 4 + 4 + 8 * len(s2)))
         e2e_step_unfused()         # warm: the single-adaptor entry has its own scratch
         barrier()
@@ -362,13 +366,14 @@ def main():
         torch.cuda.synchronize()
         dt_pageable = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": world * ne / dt, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "h2d_bytes_per_step_plain": h2d_plain, "h2d_bytes_per_step_per_rank": h2d_ranks,
                "reads_per_step": ne, "ms_per_step": dt * 1000.0, "steps": reps,
                "path": "sarlacc_adaptor_align_windows: pinned host CSR buffers -> H2D of the raw bytes -> device packer -> 4 forward passes + "
                        "strand resolution + traceback of the kept strand on device -> D2H of the result columns (output arrays reused between calls)",
                "inputs_pinned": inputs_pinned, "pageable_inputs_reads_per_s": world * ne / dt_pageable,
                "host_threads_per_rank": max(1, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))),
                "phases_ms_per_rank": [dict(zip(("host_stage", "host_enqueue", "host_wait_copy_out", "host_total", "device_upload_sum", "device_kernels_copyback_sum"), r)) for r in ph_ranks],
-               "upload_gbs_per_rank": [h2d / 1e6 / r[4] if r[4] > 0 else None for r in ph_ranks],
+               "upload_gbs_per_rank": [hb / 1e6 / r[4] if r[4] > 0 else None for hb, r in zip(h2d_ranks, ph_ranks)],
                "unfused_reads_per_s": world * ne / dt_unfused,
                "unfused_path": "4 x sarlacc_adaptor_align (the reference's four .Calls) + .resolve_strand on the host"}
 

@@ -91,6 +91,10 @@ void sarlacc_trim_device_memory(void);
  * from CUDA events: upload (H2D + device packer) and kernels + copy back (chunks overlap, so these exceed the wall time).
  * For bench.py's per-rank breakdown. */
 void sarlacc_last_pair_timing(double* ms6);
+/* Bytes of window data the same call copied to the (first) device: bases + qualities + offsets of both window sets.  With
+ * SARLACC_PACK_SEQ=1 in the environment the bases go up as 4-bit codes -- one pass of the host over the sequence bytes for
+ * 25 % fewer bytes on the link; worth it only where host cores are plentiful and the link is not (off by default). */
+int64_t sarlacc_last_pair_upload_bytes(void);
 
 /* ---- the four reference entry points (host buffers in, host buffers out) ------------------------- */
 

@@ -129,6 +129,8 @@ def _load():
     lib.sarlacc_chunk_stream.argtypes = [C.c_void_p]
     lib.sarlacc_last_pair_timing.restype = None
     lib.sarlacc_last_pair_timing.argtypes = [C.c_void_p]
+    lib.sarlacc_last_pair_upload_bytes.restype = C.c_int64
+    lib.sarlacc_last_pair_upload_bytes.argtypes = []
     lib.sarlacc_chunk_rows.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
     lib.sarlacc_chunk_set_timing.restype = None
     lib.sarlacc_chunk_set_timing.argtypes = [C.c_void_p, C.c_int]

@@ -1455,6 +1455,49 @@ struct RawStage {
     }
 };
 
+/* Sequence bytes as 4-bit one-hot base codes, two per byte (base k of the range in nibble k & 1 of byte k >> 1): what a
+ * job that waits for its uploads sends instead of the bytes themselves (see stage_and_pack).  The codes are the
+ * forward packer table's (PackTables::base): four byte values map to 1, 2, 4, 8, everything else to 0, so the
+ * device packer gets exactly what it would have looked up itself. */
+#ifdef SARLACC_HAVE_AVX2_PACK
+struct NibbleConsts { __m256i c0, c1, c2, c3, b1, b2, b4, b8; };
+__attribute__((target("avx2"))) static inline __m256i nibble_codes_avx2(__m256i x, const NibbleConsts& K) {
+    __m256i k = _mm256_and_si256(_mm256_cmpeq_epi8(x, K.c0), K.b1);
+    k = _mm256_or_si256(k, _mm256_and_si256(_mm256_cmpeq_epi8(x, K.c1), K.b2));
+    k = _mm256_or_si256(k, _mm256_and_si256(_mm256_cmpeq_epi8(x, K.c2), K.b4));
+    return _mm256_or_si256(k, _mm256_and_si256(_mm256_cmpeq_epi8(x, K.c3), K.b8));
+}
+__attribute__((target("avx2"))) static size_t nibble_pack_avx2(const uint8_t* src, size_t n, uint8_t* dst, const uint8_t code[4]) {
+    NibbleConsts K;
+    K.c0 = _mm256_set1_epi8((char)code[0]); K.c1 = _mm256_set1_epi8((char)code[1]);
+    K.c2 = _mm256_set1_epi8((char)code[2]); K.c3 = _mm256_set1_epi8((char)code[3]);
+    K.b1 = _mm256_set1_epi8(1); K.b2 = _mm256_set1_epi8(2); K.b4 = _mm256_set1_epi8(4); K.b8 = _mm256_set1_epi8(8);
+    const __m256i mul = _mm256_set1_epi16(0x1001);      /* even byte x 1 + odd byte x 16 */
+    size_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+        const __m256i w0 = _mm256_maddubs_epi16(nibble_codes_avx2(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i)), K), mul);
+        const __m256i w1 = _mm256_maddubs_epi16(nibble_codes_avx2(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 32)), K), mul);
+        const __m256i p = _mm256_permute4x64_epi64(_mm256_packus_epi16(w0, w1), 0xD8);
+        _mm256_storeu_si256(reinterpret_cast<__m256i*>(dst + i / 2), p);
+    }
+    return i;
+}
+#endif
+
+/* dst[(n + 1) / 2] <- nibbles of src[0, n); threads split the range at multiples of 64 bases */
+void nibble_pack(const uint8_t* src, size_t n, uint8_t* dst, const PackTables& T, int nthreads) {
+    const int64_t blocks = (int64_t)((n + 63) / 64);
+    parallel_for(0, blocks, nthreads, [&](int64_t a, int64_t b, int) {
+        size_t lo = (size_t)a * 64, hi = std::min(n, (size_t)b * 64);
+        size_t i = lo;
+#ifdef SARLACC_HAVE_AVX2_PACK
+        if (have_avx2()) i += nibble_pack_avx2(src + lo, hi - lo, dst + lo / 2, T.code);
+#endif
+        for (; i + 1 < hi; i += 2) dst[i / 2] = (uint8_t)(T.base[src[i]] | (T.base[src[i + 1]] << 4));
+        if (i < hi) dst[i / 2] = T.base[src[i]];
+    });
+}
+
 bool pointer_is_pinned(const void* p) {
     if (!p) return false;
     cudaPointerAttributes at;
@@ -1466,6 +1509,8 @@ bool pointer_is_pinned(const void* p) {
 }
 
 /* Enqueues on `st`: upload of the raw bytes of windows [c0, c1) of V + the device packer writing d_rows. */
+struct UploadBytes { size_t sent = 0, raw = 0; };      /* bytes a chunk's window sets put on the link / would have put as plain bytes */
+
 /* The device packer of a staged window set and the read-back of its error flag, to be enqueued behind the uploads. */
 struct PendingPack {
     PackArgs args;
@@ -1488,13 +1533,23 @@ void launch_pending_pack(PendingPack& P, cudaStream_t st) {
  * chunk runs, and everything behind it on the stream waits with it -- the second window set's upload included, which
  * left the copy engine idle for a kernel's length per chunk (N = 8: 11.6 GB/s per rank against 23 GB/s available,
  * profiles/r02_history.md). */
-void stage_and_pack(const ReadView& V, int64_t c0, int64_t c1, const PackTables& T, const int32_t* h_lens, const int32_t* d_lens,
-        int stride, uint16_t* d_rows, bool check_qual, bool pools_pinned, RawStage& R, cudaStream_t st, int nthreads,
-        PendingPack* defer = nullptr)
+/* The host half of stage_and_pack: offsets and, where needed, the staged (or 4-bit coded) bytes of windows [c0, c1). */
+struct Staged {
+    const uint8_t* src_seq = nullptr;
+    const uint8_t* src_qual = nullptr;
+    size_t nseq = 0, nqual = 0;
+    bool seq4 = false;
+    long long m = 0;
+};
+
+Staged stage_host(const ReadView& V, int64_t c0, int64_t c1, const PackTables& T, const int32_t* h_lens, bool pools_pinned,
+        RawStage& R, int nthreads, bool nibbles)
 {
+    Staged G;
     const long long m = c1 - c0;
-    if (m <= 0) return;
-    Range nvtx("sarlacc: stage + H2D + device pack");
+    G.m = m;
+    if (m <= 0) return G;
+    Range nvtx("sarlacc: stage windows");
     R.h_soff.reserve(sizeof(long long) * (size_t)m);
     R.h_qoff.reserve(sizeof(long long) * (size_t)m);
     long long* soff = R.h_soff.as<long long>();
@@ -1504,6 +1559,7 @@ void stage_and_pack(const ReadView& V, int64_t c0, int64_t c1, const PackTables&
     const uint8_t* src_seq = nullptr;
     const uint8_t* src_qual = nullptr;
     size_t nseq = 0, nqual = 0;
+    bool seq4 = false;
     if (csr_whole) {
         /* the chunk is one contiguous byte range of each pool; a window's offsets are its entry's */
         const int64_t s0 = S->seq_off[c0], q0 = S->qual_off[c0];
@@ -1513,7 +1569,24 @@ void stage_and_pack(const ReadView& V, int64_t c0, int64_t c1, const PackTables&
         }
         nseq = (size_t)(S->seq_off[c1] - s0);
         nqual = (size_t)(S->qual_off[c1] - q0);
-        if (pools_pinned) {
+        if (nibbles) {
+            /* SARLACC_PACK_SEQ=1 (see PairJob): the bases go up as 4-bit codes -- half their bytes for one pass of the
+             * host over them; qualities as they are */
+            seq4 = true;
+            R.h_seq.reserve((nseq + 1) / 2 + 64);
+            nibble_pack(S->seq_pool + s0, nseq, R.h_seq.as<uint8_t>(), T, nthreads);
+            src_seq = R.h_seq.as<uint8_t>();
+            if (pools_pinned) {
+                src_qual = S->qual_pool + q0;
+            } else {
+                R.h_qual.reserve(nqual);
+                uint8_t* hq = R.h_qual.as<uint8_t>();
+                parallel_for(0, m, nthreads, [&](int64_t a, int64_t b, int) {
+                    std::memcpy(hq + qoff[a], S->qual_pool + q0 + qoff[a], (size_t)(S->qual_off[c0 + b] - S->qual_off[c0 + a]));
+                });
+                src_qual = hq;
+            }
+        } else if (pools_pinned) {
             src_seq = S->seq_pool + s0;
             src_qual = S->qual_pool + q0;
         } else {
@@ -1551,13 +1624,39 @@ void stage_and_pack(const ReadView& V, int64_t c0, int64_t c1, const PackTables&
         src_seq = hs;
         src_qual = hq;
     }
+    G.src_seq = src_seq;
+    G.src_qual = src_qual;
+    G.nseq = nseq;
+    G.nqual = nqual;
+    G.seq4 = seq4;
+    return G;
+}
+
+/* The device half: uploads of what stage_host prepared + the device packer (handed back with `defer`). */
+void stage_enqueue(const Staged& G, const ReadView& V, const PackTables& T, const int32_t* d_lens, int stride, uint16_t* d_rows,
+        bool check_qual, RawStage& R, cudaStream_t st, PendingPack* defer = nullptr, UploadBytes* bytes = nullptr)
+{
+    const long long m = G.m;
+    if (m <= 0) return;
+    Range nvtx("sarlacc: H2D + device pack");
+    const uint8_t* src_seq = G.src_seq;
+    const uint8_t* src_qual = G.src_qual;
+    const size_t nseq = G.nseq, nqual = G.nqual;
+    const bool seq4 = G.seq4;
+    const long long* soff = R.h_soff.as<long long>();
+    const long long* qoff = R.h_qoff.as<long long>();
     R.d_seq.reserve(nseq);
     R.d_qual.reserve(nqual);
     R.d_soff.reserve(sizeof(long long) * (size_t)m);
     R.d_qoff.reserve(sizeof(long long) * (size_t)m);
     R.d_bad.reserve(sizeof(long long));
     R.h_bad.reserve(sizeof(long long));
-    if (nseq) CUDA_CHECK(cudaMemcpyAsync(R.d_seq.p, src_seq, nseq, cudaMemcpyHostToDevice, st));
+    const size_t seq_bytes = seq4 ? (nseq + 1) / 2 : nseq;
+    if (bytes) {
+        bytes->sent += seq_bytes + nqual + 2 * sizeof(long long) * (size_t)m;
+        bytes->raw += nseq + nqual + 2 * sizeof(long long) * (size_t)m;
+    }
+    if (nseq) CUDA_CHECK(cudaMemcpyAsync(R.d_seq.p, src_seq, seq_bytes, cudaMemcpyHostToDevice, st));
     if (nqual) CUDA_CHECK(cudaMemcpyAsync(R.d_qual.p, src_qual, nqual, cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaMemcpyAsync(R.d_soff.p, soff, sizeof(long long) * (size_t)m, cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaMemcpyAsync(R.d_qoff.p, qoff, sizeof(long long) * (size_t)m, cudaMemcpyHostToDevice, st));
@@ -1572,6 +1671,7 @@ void stage_and_pack(const ReadView& V, int64_t c0, int64_t c1, const PackTables&
     A.n = m;
     A.stride = stride;
     A.back = V.back ? 1 : 0;
+    A.seq4 = seq4 ? 1 : 0;
     A.rows = d_rows;
     A.first_bad = check_qual ? R.d_bad.as<long long>() : nullptr;
     std::memcpy(A.base, T.base, 256);
@@ -1584,6 +1684,14 @@ void stage_and_pack(const ReadView& V, int64_t c0, int64_t c1, const PackTables&
     P.check_qual = check_qual;
     P.valid = true;
     if (!defer) launch_pending_pack(P, st);
+}
+
+void stage_and_pack(const ReadView& V, int64_t c0, int64_t c1, const PackTables& T, const int32_t* h_lens, const int32_t* d_lens,
+        int stride, uint16_t* d_rows, bool check_qual, bool pools_pinned, RawStage& R, cudaStream_t st, int nthreads,
+        PendingPack* defer = nullptr, bool nibbles = false, UploadBytes* bytes = nullptr)
+{
+    const Staged G = stage_host(V, c0, c1, T, h_lens, pools_pinned, R, nthreads, nibbles);
+    stage_enqueue(G, V, T, d_lens, stride, d_rows, check_qual, R, st, defer, bytes);
 }
 
 /* One pipeline slot: pinned staging + device buffers for a chunk of reads. */
@@ -1607,6 +1715,7 @@ struct Slot {
     long long n = 0;        /* reads in flight */
     int64_t lo = 0;
     bool busy = false;
+    UploadBytes up;         /* of the chunk in flight (both-ends job) */
     void init() {
         CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         CUDA_CHECK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
@@ -1709,7 +1818,6 @@ struct DeviceCache {
      * tracebacks of chunk k run beside the forward passes of chunk k+1) -- shared by all slots, a slot's own memory is
      * its raw bytes, rows and result columns */
     PairScratch pair[2];
-
     static DeviceCache& acquire(int device) {
         static std::mutex table_mutex;
         static std::vector<std::unique_ptr<DeviceCache> > table;
@@ -2122,6 +2230,7 @@ struct FinalLayout {
  * staging / length scans, enqueueing, waiting for results + copying them out, total; milliseconds. */
 std::mutex g_pair_timing_mutex;
 double g_pair_timing[6] = {0, 0, 0, 0, 0, 0};
+long long g_pair_upload_bytes = 0;
 
 struct PairJob {
     int device = 0;
@@ -2188,6 +2297,7 @@ struct PairJob {
         auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         const double t_start = now();
         double t_h2d_ms = 0, t_dev_ms = 0;      /* summed over chunks: upload (incl. device packer) / kernels + copy back, from CUDA events */
+        size_t bytes_sent = 0;
         auto drain = [&](Slot& s, const FinalLayout& o) {
             if (!s.busy) return;
             Range nvtx("sarlacc: wait for chunk + copy out");
@@ -2203,8 +2313,10 @@ struct PairJob {
                 cudaEventElapsedTime(&b, s.t_h2d, s.t_end);
                 t_h2d_ms += a;
                 t_dev_ms += b;
-                if (dbg) std::fprintf(stderr, "[sarlacc]   chunk at %lld (%lld reads): H2D %.2f ms, kernels + D2H %.2f ms, host clock %.1f ms\n",
-                                      (long long)s.lo, s.n, a, b, (now() - t_start) * 1e3);
+                bytes_sent += s.up.sent;
+                const double t_now = now();
+                if (dbg) std::fprintf(stderr, "[sarlacc]   chunk at %lld (%lld reads): H2D %.2f ms (%.1f MB%s), kernels + D2H %.2f ms, host clock %.1f ms\n",
+                                      (long long)s.lo, s.n, a, s.up.sent / 1e6, s.up.sent < s.up.raw ? ", bases as 4-bit codes" : "", b, (t_now - t_start) * 1e3);
             }
             const uint8_t* h = s.h_out.as<uint8_t>();
             const long long m = s.n;
@@ -2228,6 +2340,11 @@ struct PairJob {
         cudaEvent_t pair_free[2] = {nullptr, nullptr};     /* behind the tracebacks of the last chunk that used record group p */
         int pair_turn = 0;
         const bool host_pack = std::getenv("SARLACC_HOST_PACK") != nullptr;     /* A/B: pack on the host as before */
+        /* SARLACC_PACK_SEQ=1: send the bases as 4-bit codes (see stage_host).  Off by default: on the 8-GPU box, where the
+         * ranks do wait for the link, the 4 host cores per rank need longer for the pass over the sequence bytes than the
+         * link saves (61 -> 91 ms per step, profiles/r02_history.md); a host with cores to spare is the use case. */
+        const char* nib_env = std::getenv("SARLACC_PACK_SEQ");
+        const bool nib = nib_env && std::atoi(nib_env) != 0;
         const bool pinned_f = !VF.R->seq && pointer_is_pinned(VF.R->seq_pool) && pointer_is_pinned(VF.R->qual_pool);
         const bool pinned_b = !VB.R->seq && pointer_is_pinned(VB.R->seq_pool) && pointer_is_pinned(VB.R->qual_pool);
         for (int64_t c0 = lo; c0 < hi;) {
@@ -2288,6 +2405,13 @@ struct PairJob {
             s.d_tmp.reserve(sizeof(double) * 4 * (size_t)m);      /* the four forward passes' scores */
             s.d_out.reserve(F.total);
             s.h_out.reserve(F.total);
+            /* host work first (offsets, staging or 4-bit coding of the bases), so that the stream holds nothing but copies
+             * between t_begin and t_h2d */
+            Staged gf, gb;
+            if (!host_pack) {
+                gf = stage_host(VF, c0, c1, PF, s.h_lens.as<int32_t>(), pinned_f, s.raw, nthreads, nib);
+                gb = stage_host(VB, c0, c1, PB, s.h_lens2.as<int32_t>(), pinned_b, s.raw2, nthreads, nib);
+            }
             /* uploads in chunk order: copies of different streams share the link, and chunk k's forward passes should not
              * wait for bytes of chunk k+1 (at the start of a call three chunks are enqueued at once) */
             static const bool chain_uploads = std::getenv("SARLACC_NO_UPLOAD_CHAIN") == nullptr;
@@ -2296,14 +2420,13 @@ struct PairJob {
             CUDA_CHECK(cudaMemcpyAsync(s.d_lens.p, s.h_lens.p, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
             CUDA_CHECK(cudaMemcpyAsync(s.d_lens2.p, s.h_lens2.p, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, s.st));
             PendingPack pf, pb;      /* both uploads first, then both packers (see stage_and_pack) */
+            s.up = UploadBytes();
             if (host_pack) {
                 CUDA_CHECK(cudaMemcpyAsync(s.d_rows.p, s.h_rows.p, sizeof(uint16_t) * (size_t)m * stride_f, cudaMemcpyHostToDevice, s.st));
                 CUDA_CHECK(cudaMemcpyAsync(s.d_rows2.p, s.h_rows2.p, sizeof(uint16_t) * (size_t)m * stride_b, cudaMemcpyHostToDevice, s.st));
             } else {
-                stage_and_pack(VF, c0, c1, PF, s.h_lens.as<int32_t>(), s.d_lens.as<int32_t>(), stride_f, s.d_rows.as<uint16_t>(), true,
-                               pinned_f, s.raw, s.st, nthreads, &pf);
-                stage_and_pack(VB, c0, c1, PB, s.h_lens2.as<int32_t>(), s.d_lens2.as<int32_t>(), stride_b, s.d_rows2.as<uint16_t>(), true,
-                               pinned_b, s.raw2, s.st, nthreads, &pb);
+                stage_enqueue(gf, VF, PF, s.d_lens.as<int32_t>(), stride_f, s.d_rows.as<uint16_t>(), true, s.raw, s.st, &pf, &s.up);
+                stage_enqueue(gb, VB, PB, s.d_lens2.as<int32_t>(), stride_b, s.d_rows2.as<uint16_t>(), true, s.raw2, s.st, &pb, &s.up);
             }
             if (width || tolerance > 0) {
                 s.h_width.reserve(sizeof(int32_t) * (size_t)m);
@@ -2373,6 +2496,7 @@ struct PairJob {
             g_pair_timing[3] = (now() - t_start) * 1e3;
             g_pair_timing[4] = t_h2d_ms;
             g_pair_timing[5] = t_dev_ms;
+            g_pair_upload_bytes = (long long)bytes_sent;
         }
     }
 };
@@ -2424,6 +2548,11 @@ void sarlacc_last_pair_timing(double* ms6) {
     if (!ms6) return;
     std::lock_guard<std::mutex> lock(g_pair_timing_mutex);
     for (int k = 0; k < 6; ++k) ms6[k] = g_pair_timing[k];
+}
+
+int64_t sarlacc_last_pair_upload_bytes(void) {
+    std::lock_guard<std::mutex> lock(g_pair_timing_mutex);
+    return g_pair_upload_bytes;
 }
 
 int64_t sarlacc_kernel_launches(int reset) {

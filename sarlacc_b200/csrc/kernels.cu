@@ -1534,7 +1534,8 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const __grid_constant__ 
     const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
     for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < A.n; i += warps) {
         const int len = A.lens[i];
-        const uint8_t* s = A.seq + A.soff[i];
+        const long long so = A.soff[i];
+        const uint8_t* s = A.seq + so;
         const uint8_t* q = A.qual + A.qoff[i];
         uint16_t* out = A.rows + i * (long long)A.stride;
         bool bad = false;
@@ -1542,7 +1543,15 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const __grid_constant__ 
             const int src = A.back ? len - 1 - r : r;
             unsigned qi = sq[q[src]];
             if (qi & 0xFF00u) { bad = true; qi = 0; }
-            out[r] = (uint16_t)(qi | ((unsigned)sbase[s[src]] << 8));
+            unsigned code;
+            if (A.seq4) {       /* the host sent the forward table's codes; the complement of a one-hot code is its bit reversal */
+                const long long at = so + src;
+                code = ((unsigned)A.seq[at >> 1] >> (((unsigned)at & 1u) * 4u)) & 15u;
+                if (A.back) code = __brev(code) >> 28;
+            } else {
+                code = sbase[s[src]];
+            }
+            out[r] = (uint16_t)(qi | (code << 8));
         }
         if (A.first_bad && __any_sync(FULL, bad) && lane == 0) atomicMin(A.first_bad, i);
     }

@@ -213,6 +213,7 @@ struct PackArgs {
     long long n;
     int stride;
     int back;
+    int seq4;                  /* seq holds 4-bit one-hot base codes, two per byte (base k: nibble k & 1 of byte k >> 1), soff counts bases */
     uint16_t* rows;
     long long* first_bad;      /* initialised to LLONG_MAX by the caller; may be null */
     uint8_t base[256];

@@ -592,7 +592,9 @@ def last_pair_timing():
     """Host-side phases (ms) of the last fused both-ends host-buffer call: staging, enqueue, wait + copy-out, total."""
     ms = np.zeros(6, np.float64)
     _lib.lib.sarlacc_last_pair_timing(_lib._ptr(ms))
-    return dict(zip(("stage", "enqueue", "wait_copy_out", "total", "upload_sum", "kernels_copyback_sum"), ms.tolist()))
+    out = dict(zip(("stage", "enqueue", "wait_copy_out", "total", "upload_sum", "kernels_copyback_sum"), ms.tolist()))
+    out["upload_bytes"] = float(_lib.lib.sarlacc_last_pair_upload_bytes())      # window bytes actually put on the link
+    return out
 
 
 def compute_threshold(real, scrambled, error, device=0):

@@ -458,3 +458,40 @@ def test_tune_alignment_batched_equals_the_reference_loop(enc):
     assert native.tied_overlap(np.array([1.0, 2.0]), np.array([1.0, 2.0])) == api._tied_overlap([1.0, 2.0], [1.0, 2.0]) == 0.5
     first = api.tuneAlignment(VIGNETTE_A1, VIGNETTE_A2, reads, sample="first", **grid_args)
     assert first["parameters"]["gapOpening"] in (4, 5, 6) and len(first["scores"]["reads"]) == 150
+
+
+def test_bases_sent_as_four_bit_codes(enc, monkeypatch):
+    """With SARLACC_PACK_SEQ=1 a both-ends job sends the bases as 4-bit codes: same results as the plain bytes, for ragged windows of odd lengths with N, IUPAC and lower-case bases (all "not ACGT" to the packer),
+    pageable and pinned pools, and fewer bytes on the link."""
+    import torch
+    from conftest import random_windows, stable_seed
+    from sarlacc_b200 import native, ReadSet
+    rng = np.random.default_rng(stable_seed("nibbles"))
+    n = 4000
+    fs, fq = random_windows(rng, n, VIGNETTE_A1, 1, 251, alphabet="ACGTACGTACGTNRacgt")
+    bs, bq = random_windows(rng, n, VIGNETTE_A2, 0, 130, alphabet="ACGTACGTACGTNYt")
+    bs = [b if len(b) else "A" for b in bs]
+    bq = [q if len(q) else "I" for q in bq]
+    front, back = ReadSet.from_strings(fs, fq), ReadSet.from_strings(bs, bq)
+    widths = (front.width() + back.width() + 100).astype(np.int32)
+    s1, e1 = [16, 42], [28, 46]
+    monkeypatch.setenv("SARLACC_CHUNK", "1100")
+    results = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("SARLACC_PACK_SEQ", mode)
+        results[mode] = native.adaptor_align_windows(front, back, enc, 5, 1, VIGNETTE_A1, VIGNETTE_A2, (s1, e1), ((), ()), read_width=widths)
+        results[mode + "bytes"] = native.last_pair_timing()["upload_bytes"]
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()   # noqa: E731
+    pf = ReadSet(pin(front.seq_pool), front.seq_off, pin(front.qual_pool), front.qual_off, front.names)
+    pb = ReadSet(pin(back.seq_pool), back.seq_off, pin(back.qual_pool), back.qual_off, back.names)
+    results["pinned"] = native.adaptor_align_windows(pf, pb, enc, 5, 1, VIGNETTE_A1, VIGNETTE_A2, (s1, e1), ((), ()), read_width=widths)
+    a = results["0"]
+    for other in (results["1"], results["pinned"]):
+        assert np.array_equal(a[0], other[0])
+        for x, y in ((a[1], other[1]), (a[2], other[2])):
+            for k in range(3):
+                assert np.array_equal(x[k], y[k])
+            for k in range(len(x[3])):
+                assert np.array_equal(x[3][k], y[3][k]) and np.array_equal(x[4][k], y[4][k])
+    nbases = int(front.seq_off[-1] + back.seq_off[-1])
+    assert results["0bytes"] - results["1bytes"] >= nbases // 2 - 8       # half the sequence bytes stayed at home
