@@ -29,7 +29,10 @@ namespace sarlacc {
 
 namespace {
 
-constexpr int kBlock = 128;
+#ifndef SARLACC_WF_BLOCK
+#define SARLACC_WF_BLOCK 128
+#endif
+constexpr int kBlock = SARLACC_WF_BLOCK;
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xfff0000000000000LL); }
