@@ -17,7 +17,7 @@ for spec in "a1 trace" "a1 score" "a2 trace" "a2 score"; do
   python tools/ncu_summary.py /tmp/prof/${1}_$2.ncu-rep $(( 100000 * 250 * $( [ $1 = a1 ] && echo 70 || echo 22 ) )) > gpurun_out/ncu_summary_${tag}_$1_$2.txt 2>&1
 done
 cp /tmp/prof/a1_trace.ncu-rep gpurun_out/prof_${tag}_a1_trace.ncu-rep
-timeout 600 ncu --set full --clock-control none -k regex:"traceback|mock_windows|scramble_rows|resolve_strand|pack_rows" -c 10 -f -o /tmp/prof/aux \
+timeout 600 ncu --set full --clock-control none -k regex:"traceback|mock_windows|scramble_rows|resolve_strand|pack_rows|classify_strands" -c 12 -f -o /tmp/prof/aux \
     python tools/run_c5.py --total 200000 --chunk 200000 > gpurun_out/ncu_${tag}_aux.log 2>&1
 python tools/ncu_summary.py /tmp/prof/aux.ncu-rep > gpurun_out/ncu_summary_${tag}_aux.txt 2>&1
 for a in a1 a2; do for m in trace score; do python tools/profile_forward.py 200000 $a $m 3 | tail -1; done; done
