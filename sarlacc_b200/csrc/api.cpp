@@ -2354,7 +2354,12 @@ struct PairJob {
             t_drain += now() - t0;
             if ((err_front.kind != ERR_NONE && err_front.at < c0) || (err_back.kind != ERR_NONE && err_back.at < c0)) break;
             t0 = now();
-            int64_t c1 = std::min<int64_t>(hi, c0 + (c0 == lo ? first_chunk : chunk));
+            /* chunk sizes: a quarter, a half, then whole chunks -- each upload is hidden behind the chunk before it (a whole
+             * chunk right after the quarter left the device idle for half an upload) -- and the tail of the range split so
+             * that the last chunk, whose copy back nothing hides, is a small one */
+            int64_t step = c0 == lo ? first_chunk : (c0 == lo + first_chunk && first_chunk < chunk ? std::max<int64_t>(first_chunk, chunk / 2) : chunk);
+            if (first_chunk < chunk && hi - c0 > step / 4 && hi - c0 <= step + step / 4) step = hi - c0 - step / 4;
+            int64_t c1 = std::min<int64_t>(hi, c0 + step);
             s.h_lens.reserve(sizeof(int32_t) * (size_t)(c1 - c0));
             s.h_lens2.reserve(sizeof(int32_t) * (size_t)(c1 - c0));
             int maxf = 0, maxb = 0;
