@@ -1244,7 +1244,11 @@ const char* run_pair_device(const Plan* const plan[2], const DevPlan* const D[2]
     Range nvtx("sarlacc: both adaptors x both windows");
     /* Speculative record writing (kernels.h: StrandLists): only for the wavefront kernels' row-pair form, whose launches
      * can take a list of reads with device-side bounds. */
-    bool spec = speculate_records() && dynamic_distribution() && m >= 512 && m < (1LL << 31);
+    /* below ~40 000 reads the extra launches cost more than the records save (28 416 reads: 4.88 vs 4.63 ms per call,
+     * 56 832: 7.87 vs 8.01); SARLACC_SPEC_MIN moves the bound (tests: 512) */
+    const char* spec_min_env = std::getenv("SARLACC_SPEC_MIN");
+    const long long spec_min = spec_min_env && std::atoll(spec_min_env) > 0 ? std::atoll(spec_min_env) : 40000;
+    bool spec = speculate_records() && dynamic_distribution() && m >= spec_min && m < (1LL << 31);
     for (int a = 0; a < 2 && spec; ++a) spec = plan[a]->fast && geometry_for(*plan[a], maxlen).pair != 0;
     if (spec) spec = prepare_seeds(S, *plan[0], *plan[1], st);
     StrandLists L;

@@ -80,6 +80,7 @@ def test_fused_windows_entry(port, enc, monkeypatch):
     front, back, widths, _ = synth.mock_windows(n, VIGNETTE_A1, VIGNETTE_A2, seed=77)
     s1, e1 = [16, 42], [28, 46]
     monkeypatch.setenv("SARLACC_CHUNK", "700")
+    monkeypatch.setenv("SARLACC_SPEC_MIN", "512")       # speculative records on these small chunks too
     rev, r1, r2 = native.adaptor_align_windows(front, back, enc, 5, 1, VIGNETTE_A1, VIGNETTE_A2, (s1, e1), ((), ()), read_width=widths)
     a = native.adaptor_align(front, enc, 5, 1, VIGNETTE_A1, s1, e1)
     b = native.adaptor_align(back, enc, 5, 1, VIGNETTE_A2)

@@ -107,6 +107,7 @@ def test_chunk_adaptor_align_matches_the_four_calls(oracle, enc, go, ge, monkeyp
     n = 2500
     ch = native.Chunk(4096, 250, enc)
     monkeypatch.setenv("SARLACC_CHUNK", "601")
+    monkeypatch.setenv("SARLACC_SPEC_MIN", "512")       # speculative records on these small sub-ranges too
     for first in (0, 77777):
         ch.load_mock(n, VIGNETTE_A1, VIGNETTE_A2, seed=5000, first_index=first)
         front, back, widths, _ = synth.mock_windows(n, VIGNETTE_A1, VIGNETTE_A2, seed=5000, first_index=first)
@@ -259,6 +260,7 @@ def test_speculative_records_do_not_change_results(enc, port, mode, monkeypatch)
     n = 3000
     ch = native.Chunk(4096, 250, enc)
     ch.load_mock(n, VIGNETTE_A1, VIGNETTE_A2, seed=31, first_index=10 ** 9)
+    monkeypatch.setenv("SARLACC_SPEC_MIN", "512")
     base = ch.adaptor_align(5, 1, VIGNETTE_A1, VIGNETTE_A2, (S1, E1), ((), ()))
     monkeypatch.setenv("SARLACC_SPEC_TEST", mode)
     got = ch.adaptor_align(5, 1, VIGNETTE_A1, VIGNETTE_A2, (S1, E1), ((), ()))

@@ -55,6 +55,7 @@ ch.close()
 # speculative records (sub-ranges of 512+ reads): strand predictor, list-driven launches, and -- with the predictions
 # inverted -- the re-run path; same results as the host-buffer entry on the same reads
 ns = 576
+os.environ["SARLACC_SPEC_MIN"] = "512"
 f2, b2, w2, _ = synth.mock_windows(ns, VIGNETTE_A1, VIGNETTE_A2, seed=12)
 ch = native.Chunk(ns, 250, enc)
 ch.load_mock(ns, VIGNETTE_A1, VIGNETTE_A2, seed=12)
