@@ -1459,6 +1459,41 @@ struct RawStage {
     }
 };
 
+/* Copy into pinned staging with non-temporal stores: the destination is read next by the DMA engine, not by a core, so
+ * there is no point in pulling its lines into the cache first (a thread's piece, ~2 MB, is below the size at which
+ * memcpy switches to such stores by itself). */
+#ifdef SARLACC_HAVE_AVX2_PACK
+__attribute__((target("avx2"))) static void copy_nt_avx2(uint8_t* dst, const uint8_t* src, size_t n) {
+    size_t head = (32 - (reinterpret_cast<uintptr_t>(dst) & 31)) & 31;
+    if (head > n) head = n;
+    std::memcpy(dst, src, head);
+    size_t i = head;
+    for (; i + 128 <= n; i += 128) {
+        const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i));
+        const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 32));
+        const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 64));
+        const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 96));
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), a);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 32), b);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 64), c);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 96), d);
+    }
+    _mm_sfence();
+    std::memcpy(dst + i, src + i, n - i);
+}
+#endif
+
+void copy_to_staging(uint8_t* dst, const uint8_t* src, size_t n) {
+#ifdef SARLACC_HAVE_AVX2_PACK
+    static const bool nt = have_avx2() && std::getenv("SARLACC_NO_NT_COPY") == nullptr;
+    if (nt && n >= 4096) {
+        copy_nt_avx2(dst, src, n);
+        return;
+    }
+#endif
+    std::memcpy(dst, src, n);
+}
+
 /* Sequence bytes as 4-bit one-hot base codes, two per byte (base k of the range in nibble k & 1 of byte k >> 1): what a
  * job that waits for its uploads sends instead of the bytes themselves (see stage_and_pack).  The codes are the
  * forward packer table's (PackTables::base): four byte values map to 1, 2, 4, 8, everything else to 0, so the
@@ -1586,7 +1621,7 @@ Staged stage_host(const ReadView& V, int64_t c0, int64_t c1, const PackTables& T
                 R.h_qual.reserve(nqual);
                 uint8_t* hq = R.h_qual.as<uint8_t>();
                 parallel_for(0, m, nthreads, [&](int64_t a, int64_t b, int) {
-                    std::memcpy(hq + qoff[a], S->qual_pool + q0 + qoff[a], (size_t)(S->qual_off[c0 + b] - S->qual_off[c0 + a]));
+                    copy_to_staging(hq + qoff[a], S->qual_pool + q0 + qoff[a], (size_t)(S->qual_off[c0 + b] - S->qual_off[c0 + a]));
                 });
                 src_qual = hq;
             }
@@ -1599,8 +1634,8 @@ Staged stage_host(const ReadView& V, int64_t c0, int64_t c1, const PackTables& T
             uint8_t* hs = R.h_seq.as<uint8_t>();
             uint8_t* hq = R.h_qual.as<uint8_t>();
             parallel_for(0, m, nthreads, [&](int64_t a, int64_t b, int) {
-                std::memcpy(hs + soff[a], S->seq_pool + s0 + soff[a], (size_t)(S->seq_off[c0 + b] - S->seq_off[c0 + a]));
-                std::memcpy(hq + qoff[a], S->qual_pool + q0 + qoff[a], (size_t)(S->qual_off[c0 + b] - S->qual_off[c0 + a]));
+                copy_to_staging(hs + soff[a], S->seq_pool + s0 + soff[a], (size_t)(S->seq_off[c0 + b] - S->seq_off[c0 + a]));
+                copy_to_staging(hq + qoff[a], S->qual_pool + q0 + qoff[a], (size_t)(S->qual_off[c0 + b] - S->qual_off[c0 + a]));
             });
             src_seq = hs;
             src_qual = hq;
