@@ -309,6 +309,12 @@ void    sarlacc_lists_free(sarlacc_lists* r);
 int sarlacc_pack_rows(const sarlacc_reads* reads, const sarlacc_encoding* encoding, int tolerance, int back,
                       int stride, uint16_t* rows, int32_t* lens, int force_scalar);
 
+/* The host half of the optional 4-bit upload (SARLACC_PACK_SEQ=1): out[(n + 1) / 2] <- one-hot base codes of seq[0, n), two
+ * per byte (base k in nibble k & 1 of byte k >> 1; A = 1, C = 2, G = 4, T = 8, anything else 0 -- the table the device
+ * packer applies to plain bytes, src/DNA_input.cpp:64-75 for Biostrings codes).  force_scalar: the table loop instead of
+ * the AVX2 one.  Exposed for tests. */
+int sarlacc_pack_bases(const uint8_t* seq, int64_t n, int seq_encoding, uint8_t* out, int force_scalar);
+
 /* ---- FASTQ ingest (host side; stands in for ShortRead::FastqStreamer + .FASTQ2QSDS, R/adaptorAlign.R:26,36,104-110) --
  * Buffered reader of plain-text 4-line FASTQ records yielding chunks as CSR pools that can be handed straight back as a
  * sarlacc_reads (CSR layout).  Names exclude the leading '@'.  Pointers stay valid until the next call on the handle. */

@@ -108,6 +108,8 @@ def _load():
     lib.sarlacc_lists_free.restype = None
     lib.sarlacc_lists_free.argtypes = [C.c_void_p]
     lib.sarlacc_pack_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    lib.sarlacc_pack_bases.restype = C.c_int
+    lib.sarlacc_pack_bases.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int]
     lib.sarlacc_chunk_create.restype = C.c_void_p
     lib.sarlacc_chunk_create.argtypes = [C.c_int, C.c_int64, C.c_int, C.POINTER(_Encoding)]
     lib.sarlacc_chunk_free.restype = None

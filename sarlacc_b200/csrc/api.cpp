@@ -2873,6 +2873,22 @@ int sarlacc_pack_rows(const sarlacc_reads* reads, const sarlacc_encoding* encodi
     return 0;
 }
 
+int sarlacc_pack_bases(const uint8_t* seq, int64_t n, int seq_encoding, uint8_t* out, int force_scalar) {
+    if (n < 0 || (n > 0 && (!seq || !out))) return fail("sequence bytes must not be NULL");
+    Encoding enc;
+    enc.offset = 33;
+    enc.n = 1;
+    PackTables T;
+    build_pack_tables(T, seq_encoding, enc);
+    if (force_scalar) {
+        for (int64_t i = 0; i + 1 < n; i += 2) out[i / 2] = (uint8_t)(T.base[seq[i]] | (T.base[seq[i + 1]] << 4));
+        if (n & 1) out[n / 2] = T.base[seq[n - 1]];
+    } else {
+        nibble_pack(seq, (size_t)n, out, T, host_threads_for(1));
+    }
+    return 0;
+}
+
 /* ---- FASTQ ingest ----------------------------------------------------------------
  * Stands in for ShortRead::FastqStreamer + .FASTQ2QSDS (R/adaptorAlign.R:26,36,104-110) on the host side of the
  * ABI: a buffered reader of 4-line FASTQ records that yields chunks of reads as CSR pools (names, sequences,

@@ -340,3 +340,31 @@ def test_sample_reads_is_a_uniform_sample_in_stream_order():
             hits[int(x[1:])] += 1
     assert abs(hits[:1000].mean() - hits[2000:].mean()) < 0.6 and 3.0 < hits.mean() < 5.0     # 40 * 300 / 3000 = 4 per read
     assert len(api._sample_reads(rs, 5000, 250, seed=0)) == n                                   # fewer reads than asked for: all of them
+
+
+def test_bases_as_four_bit_codes():
+    """sarlacc_pack_bases (the host half of SARLACC_PACK_SEQ=1): every byte value, odd lengths, the vector and the table
+    loop, ASCII and Biostrings codes == the packer table (A, C, G, T -> 1, 2, 4, 8; anything else, lower case included,
+    -> 0)."""
+    import ctypes as C
+    from sarlacc_b200 import _lib
+    rng = np.random.default_rng(5)
+    tables = {0: {65: 1, 67: 2, 71: 4, 84: 8}, 1: {1: 1, 2: 2, 4: 4, 8: 8}}
+    for enc_id, tab in tables.items():
+        lut = np.zeros(256, np.uint8)
+        for k, v in tab.items():
+            lut[k] = v
+        for n in (0, 1, 2, 63, 64, 65, 127, 4097, 300001):
+            seq = rng.integers(0, 256, n).astype(np.uint8)
+            if n >= 256:
+                seq[:256] = np.arange(256)
+                seq[256:] = np.frombuffer(b"ACGTNacgt\x01\x02\x04\x08", np.uint8)[rng.integers(0, 13, n - 256)]
+            codes = lut[seq]
+            if n & 1:
+                codes = np.append(codes, np.uint8(0))
+            exp = (codes[0::2] | (codes[1::2] << 4)).astype(np.uint8)
+            for scalar in (0, 1):
+                out = np.full((n + 1) // 2 + 8, 0xEE, np.uint8)
+                _lib.check(_lib.lib.sarlacc_pack_bases(_lib._ptr(seq), C.c_int64(n), C.c_int(enc_id), _lib._ptr(out), C.c_int(scalar)))
+                assert np.array_equal(out[:(n + 1) // 2], exp), (enc_id, n, scalar)
+                assert np.all(out[(n + 1) // 2:] == 0xEE)
