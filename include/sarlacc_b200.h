@@ -17,8 +17,12 @@
  * plus fused entries that fold R-level loops into one device pass -- sarlacc_barcode_align_multi (the per-barcode
  * loop of R/barcodeAlign.R:20-35), sarlacc_adaptor_align_windows / sarlacc_adaptor_align_reads (.align_AA_internal,
  * R/adaptorAlign.R:178-199) --, a "resident" variant of the same calls that keeps packed read windows in HBM between
- * calls (what adaptorAlign -> getAdaptorThresholds -> tuneAlignment re-use), and host-side helpers: FASTQ ingest
- * (sarlacc_fastq_*, standing in for ShortRead::FastqStreamer, R/adaptorAlign.R:26,36) and the packer test hook.
+ * calls (what adaptorAlign -> getAdaptorThresholds -> tuneAlignment re-use), device-resident chunks re-loaded in place
+ * (sarlacc_chunk_*: .align_AA_internal / .align_AT_internal on one FastqStreamer yield, R/adaptorAlign.R:26-48,
+ * R/getAdaptorThresholds.R:35-48), threshold selection on the device (sarlacc_compute_threshold, sarlacc_tied_overlap),
+ * and host-side helpers: FASTQ ingest (sarlacc_fastq_*, standing in for ShortRead::FastqStreamer, R/adaptorAlign.R:26,36),
+ * the packer test hooks (sarlacc_pack_rows, sarlacc_pack_bases) and counters for bench.py (sarlacc_kernel_launches,
+ * sarlacc_last_pair_timing, sarlacc_last_pair_upload_bytes).
  *
  * Plain pointers and sizes only: no R, Rcpp, torch or CUDA types appear in any signature.  The R-side
  * glue a maintainer would add (SEXP unpacking -> these calls) is shown in INTEGRATION.md and kept as
