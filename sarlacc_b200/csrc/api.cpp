@@ -1738,10 +1738,11 @@ struct Slot {
     cudaStream_t st = nullptr;
     cudaEvent_t done = nullptr;
     cudaEvent_t t_begin = nullptr, t_h2d = nullptr, t_end = nullptr;   /* SARLACC_DEBUG_TIMING: per-chunk device phases */
-    /* recorded behind the chunk's alignment kernels: the next chunk's kernels (on another slot's stream) wait for it.
-     * Uploads and result copies of neighbouring chunks still overlap, but two grid-filling forward kernels never share
-     * the device -- concurrently they finish three chunks in the time of 3.4 (measured with pinned inputs, when the
-     * host no longer paces the enqueues). */
+    /* recorded behind the chunk's alignment kernels.  Chunks whose kernels must not start before the previous chunk's
+     * have finished wait for it: those with tracebacks in the single-adaptor jobs (round 1 measured two static-grid
+     * forward kernels sharing the device at three chunks in the time of 3.4).  Score-only chunks and the both-ends job
+     * do not wait (SARLACC_GATE_CHUNKS=1 makes them): their launches are resident grids fed from a device counter, and
+     * the next chunk's blocks simply start as this chunk's blocks retire. */
     cudaEvent_t gate = nullptr;
     PinBuf h_rows, h_lens, h_out, h_order;
     DevBuf d_rows, d_lens, d_out, d_order;     /* *_order: the chunk's reads by length (barcode-length reads) */
