@@ -1,5 +1,5 @@
-/* R-side glue: the four hot-path `.Call` entry points of sarlacc (and, at the end of the file, umi_group and
- * cluster_umis_test), re-implemented as thin SEXP unpackers over the C ABI in include/sarlacc_b200.h.  Drop this file into
+/* R-side glue: the four hot-path `.Call` entry points of sarlacc (then two optional fused routines and, at the end of the
+ * file, umi_group and cluster_umis_test), re-implemented as thin SEXP unpackers over the C ABI in include/sarlacc_b200.h.  Drop this file into
  * the package's src/ in place of adaptor_align.cpp, barcode_align.cpp, general_align.cpp and reference_align.{h,cpp};
  * src/init.cpp keeps its registration table (src/init.cpp:9-35) unchanged, because the symbols, arities and return shapes
  * are the same.  It depends only on Rinternals.h, Biostrings_interface.h and sarlacc_b200.h.  There is no R in this image:
@@ -225,6 +225,91 @@ SEXP general_align(SEXP inputseq, SEXP inputqual, SEXP encoding, SEXP gapopen, S
             for (int i = 0; i < n; ++i) {
                 SET_STRING_ELT(rs, i, Rf_mkChar(ra.data() + (size_t)i * stride));
                 SET_STRING_ELT(qs, i, Rf_mkChar(qa.data() + (size_t)i * stride));
+            }
+        }
+        UNPROTECT(1);
+        return out;
+    });
+}
+
+}
+
+/* ---- optional extra routines: R-level loops folded into one call each ------------------------------
+ * barcode_align_multi(seq, qual, encoding, gapopen, gapext, barcodes): the per-barcode loop of R/barcodeAlign.R:20-35.
+ * Returns list(id, best, next): id = 1-based index of the best barcode (strict >, in barcode order, :28-34), its score,
+ * the runner-up's score -- what the R loop leaves in `current.id`, `current.score` and `next.best`.
+ * adaptor_align_reads(readseq, readqual, tolerance, encoding, gapopen, gapext, adaptor1, adaptor2, starts1, ends1, starts2,
+ * ends2): .align_AA_internal (R/adaptorAlign.R:178-199) on whole reads + adaptorAlign's adaptor2 flip (:66-71).  Returns
+ * list(reversed, width, adaptor1, adaptor2), the last two shaped like adaptor_align()'s return value. */
+extern "C" {
+
+SEXP barcode_align_multi(SEXP barcodeseq, SEXP barcodequal, SEXP encoding, SEXP gapopen, SEXP gapext, SEXP barcodes) {
+    return guarded([&]() -> SEXP {
+        const double go = numeric_scalar(gapopen, "gap opening penalty"), ge = numeric_scalar(gapext, "gap extension penalty");
+        if (!Rf_isString(barcodes) || LENGTH(barcodes) < 1) stop("barcodes should be a non-empty character vector");
+        const int n = read_count(barcodeseq), nb = LENGTH(barcodes);
+        SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+        SEXP id = Rf_allocVector(INTSXP, n);    SET_VECTOR_ELT(out, 0, id);
+        SEXP best = Rf_allocVector(REALSXP, n); SET_VECTOR_ELT(out, 1, best);
+        SEXP next = Rf_allocVector(REALSXP, n); SET_VECTOR_ELT(out, 2, next);
+        {
+            Reads R(barcodeseq, barcodequal);
+            Enc E(encoding);
+            std::vector<const char*> bc((size_t)nb);
+            for (int b = 0; b < nb; ++b) bc[(size_t)b] = CHAR(STRING_ELT(barcodes, b));
+            check(sarlacc_barcode_align_multi(&R.r, &E.e, go, ge, bc.data(), nb, INTEGER(id), REAL(best), REAL(next), NULL));
+        }
+        UNPROTECT(1);
+        return out;
+    });
+}
+
+SEXP adaptor_align_reads(SEXP readseq, SEXP readqual, SEXP tolerance, SEXP encoding, SEXP gapopen, SEXP gapext,
+                         SEXP adaptor1, SEXP adaptor2, SEXP starts1, SEXP ends1, SEXP starts2, SEXP ends2) {
+    return guarded([&]() -> SEXP {
+        const char* a1 = string_scalar(adaptor1, "adaptor sequence");
+        const char* a2 = string_scalar(adaptor2, "adaptor sequence");
+        const double go = numeric_scalar(gapopen, "gap opening penalty"), ge = numeric_scalar(gapext, "gap extension penalty");
+        const int tol = (int)numeric_scalar(tolerance, "tolerance");
+        const int ns[2] = {LENGTH(starts1), LENGTH(starts2)};
+        if (ns[0] != LENGTH(ends1) || ns[1] != LENGTH(ends2)) stop("section starts and ends should have the same length");
+        const int n = read_count(readseq);
+        SEXP out = PROTECT(Rf_allocVector(VECSXP, 4));
+        SEXP rev = Rf_allocVector(LGLSXP, n);   SET_VECTOR_ELT(out, 0, rev);
+        SEXP width = Rf_allocVector(INTSXP, n); SET_VECTOR_ELT(out, 1, width);
+        SEXP per[2], score[2], start[2], end[2], ss[2], sw[2];
+        for (int k = 0; k < 2; ++k) {
+            per[k] = Rf_allocVector(VECSXP, 5);        SET_VECTOR_ELT(out, 2 + k, per[k]);
+            score[k] = Rf_allocVector(REALSXP, n);     SET_VECTOR_ELT(per[k], 0, score[k]);
+            start[k] = Rf_allocVector(INTSXP, n);      SET_VECTOR_ELT(per[k], 1, start[k]);
+            end[k] = Rf_allocVector(INTSXP, n);        SET_VECTOR_ELT(per[k], 2, end[k]);
+            ss[k] = Rf_allocVector(VECSXP, ns[k]);     SET_VECTOR_ELT(per[k], 3, ss[k]);
+            sw[k] = Rf_allocVector(VECSXP, ns[k]);     SET_VECTOR_ELT(per[k], 4, sw[k]);
+            for (int s = 0; s < ns[k]; ++s) {
+                SET_VECTOR_ELT(ss[k], s, Rf_allocVector(INTSXP, n));
+                SET_VECTOR_ELT(sw[k], s, Rf_allocVector(INTSXP, n));
+            }
+        }
+        {
+            Reads R(readseq, readqual);
+            Enc E(encoding);
+            std::vector<uint8_t> flag((size_t)n + 1);
+            std::vector<int32_t> sst[2], swd[2];
+            for (int k = 0; k < 2; ++k) {
+                sst[k].assign((size_t)ns[k] * n + 1, 0);
+                swd[k].assign((size_t)ns[k] * n + 1, 0);
+            }
+            check(sarlacc_adaptor_align_reads(&R.r, tol, &E.e, go, ge, a1, a2,
+                                              ns[0], INTEGER(starts1), INTEGER(ends1), ns[1], INTEGER(starts2), INTEGER(ends2),
+                                              INTEGER(width), flag.data(),
+                                              REAL(score[0]), INTEGER(start[0]), INTEGER(end[0]), sst[0].data(), swd[0].data(),
+                                              REAL(score[1]), INTEGER(start[1]), INTEGER(end[1]), sst[1].data(), swd[1].data()));
+            for (int i = 0; i < n; ++i) LOGICAL(rev)[i] = flag[(size_t)i] ? 1 : 0;
+            for (int k = 0; k < 2; ++k) {
+                for (int s = 0; s < ns[k] && n > 0; ++s) {
+                    std::memcpy(INTEGER(VECTOR_ELT(ss[k], s)), sst[k].data() + (size_t)s * n, sizeof(int32_t) * (size_t)n);
+                    std::memcpy(INTEGER(VECTOR_ELT(sw[k], s)), swd[k].data() + (size_t)s * n, sizeof(int32_t) * (size_t)n);
+                }
             }
         }
         UNPROTECT(1);

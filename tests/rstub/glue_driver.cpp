@@ -23,6 +23,8 @@ SEXP barcode_align(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 SEXP general_align(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 SEXP umi_group(SEXP, SEXP, SEXP, SEXP, SEXP);
 SEXP cluster_umis_test(SEXP);
+SEXP barcode_align_multi(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
+SEXP adaptor_align_reads(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 }
 
 namespace {
@@ -152,6 +154,17 @@ int errors_mode(bool have_gpu) {
             expect_error("umi vectors differ", run([&] { SEXP pg = rstub_list(1); SET_VECTOR_ELT(pg, 0, rstub_integers(g0, 2)); return umi_group(reads(), rstub_integers(&t, 1), rstub_string_vector(sp.data(), 1), rstub_integers(&t, 1), pg); }),
                          "'umi1' and 'umi2' should have the same length");
         }
+        /* the optional fused routines */
+        expect_error("barcodes not character", run([&] { return barcode_align_multi(reads(), rqual(), phred_encoding(), rstub_real(5), rstub_real(1), rstub_real(2)); }),
+                     "barcodes should be a non-empty character vector");
+        expect_error("vector lengths differ (multi)", run([&] { return barcode_align_multi(reads(), rstub_xstringset(qp.data(), 1, 0), phred_encoding(), rstub_real(5), rstub_real(1), rstub_string_vector(sp.data(), 2)); }),
+                     "sequence and quality vectors should have the same length");
+        expect_error("tolerance not numeric", run([&] { return adaptor_align_reads(reads(), rqual(), rstub_string("x"), phred_encoding(), rstub_real(5), rstub_real(1), rstub_string("ACGT"), rstub_string("TTGA"), rstub_integers(&one, 0), rstub_integers(&one, 0), rstub_integers(&one, 0), rstub_integers(&one, 0)); }),
+                     "tolerance should be a numeric scalar");
+        expect_error("section lengths differ (reads)", run([&] { return adaptor_align_reads(reads(), rqual(), rstub_real(250), phred_encoding(), rstub_real(5), rstub_real(1), rstub_string("ACGT"), rstub_string("TTGA"), rstub_integers(&one, 0), rstub_integers(&one, 0), rstub_integers(two, 2), rstub_integers(&one, 1)); }),
+                     "section starts and ends should have the same length");
+        expect_error("second adaptor not a string", run([&] { return adaptor_align_reads(reads(), rqual(), rstub_real(250), phred_encoding(), rstub_real(5), rstub_real(1), rstub_string("ACGT"), rstub_real(1), rstub_integers(&one, 0), rstub_integers(&one, 0), rstub_integers(&one, 0), rstub_integers(&one, 0)); }),
+                     "adaptor sequence should be a string");
         /* a valid call without a device: the library's own refusal travels the same way, with every container alive */
         const std::string nodev = run([&] { return adaptor_align(reads(), rqual(), phred_encoding(), rstub_real(5), rstub_real(1), rstub_string("ACGT"), rstub_integers(&one, 0), rstub_integers(&one, 0)); });
         const bool refused = nodev.find("requires a CUDA device") != std::string::npos;
@@ -233,6 +246,22 @@ int parity_mode(const char* path) {
         std::printf("{\"call\": \"umi_group\", \"groups\": [");
         for (int g = 0; g < LENGTH(res); ++g) { std::printf("%s{", g ? ", " : ""); print_int_lists("clusters", VECTOR_ELT(res, g)); std::printf("}"); }
         std::printf("]}\n");
+        /* the optional fused routines: three barcodes in one call; both adaptors on both ends of the whole reads */
+        const char* bcs[3] = {"AAGGCCTTTTCCGACTCATGAACC", "ACGTACGTACGTACGTACGTACGT", "TTGACCAGTTGACCAGTTGACCAG"};
+        run([&] { return barcode_align_multi(rstub_string_vector(sp.data(), n), rstub_xstringset(qp.data(), n, 0), phred_encoding(), rstub_real(5), rstub_real(1), rstub_string_vector(bcs, 3)); }, &res);
+        std::printf("{\"call\": \"barcode_align_multi\", "); print_ints("id", VECTOR_ELT(res, 0)); std::printf(", ");
+        print_doubles("best", VECTOR_ELT(res, 1)); std::printf(", "); print_doubles("next", VECTOR_ELT(res, 2)); std::printf("}\n");
+        const std::string m2 = run([&] { return adaptor_align_reads(rstub_xstringset(sp.data(), n, 1), rstub_xstringset(qp.data(), n, 0), rstub_real(100), phred_encoding(), rstub_real(5), rstub_real(1),
+                                              rstub_string(A1), rstub_string("AAGGCCTTTTCCGACTCATGAA"), rstub_integers(st, 2), rstub_integers(en, 2), rstub_integers(st, 0), rstub_integers(en, 0)); }, &res);
+        if (!m2.empty()) { std::printf("{\"call\": \"adaptor_align_reads\", \"error\": \"%s\"}\n", m2.c_str()); return 1; }
+        std::printf("{\"call\": \"adaptor_align_reads\", "); print_ints("reversed", VECTOR_ELT(res, 0)); std::printf(", "); print_ints("width", VECTOR_ELT(res, 1));
+        for (int k = 0; k < 2; ++k) {
+            SEXP a = VECTOR_ELT(res, 2 + k);
+            std::printf(", \"adaptor%d\": {", k + 1);
+            print_doubles("score", VECTOR_ELT(a, 0)); std::printf(", "); print_ints("start", VECTOR_ELT(a, 1)); std::printf(", "); print_ints("end", VECTOR_ELT(a, 2)); std::printf(", ");
+            print_int_lists("sec_start", VECTOR_ELT(a, 3)); std::printf(", "); print_int_lists("sec_width", VECTOR_ELT(a, 4)); std::printf("}");
+        }
+        std::printf("}\n");
     }
     rstub_free_all();
     return 0;

@@ -92,3 +92,14 @@ def test_glue_results_match_the_library(drivers, enc, tmp_path):
     for got, grp in zip(by["umi_group"]["groups"], groups):
         want = native.umi_group(umis, 1, groups=[grp])
         assert got["clusters"] == [c.tolist() for c in want]
+    # the optional fused routines
+    bid, best, nxt = native.barcode_align_multi((seqs, quals), enc, 5, 1, ["AAGGCCTTTTCCGACTCATGAACC", "ACGTACGTACGTACGTACGTACGT", "TTGACCAGTTGACCAGTTGACCAG"])
+    m = by["barcode_align_multi"]
+    assert m["id"] == bid.tolist() and np.array_equal(hexf(m["best"]), best) and np.array_equal(hexf(m["next"]), nxt)
+    from sarlacc_b200 import ReadSet
+    width, rev, r1, r2 = native.adaptor_align_reads(ReadSet.from_strings(seqs, quals), 100, enc, 5, 1, VIGNETTE_A1, "AAGGCCTTTTCCGACTCATGAA", ([16, 42], [28, 46]), ((), ()))
+    g = by["adaptor_align_reads"]
+    assert g["reversed"] == rev.astype(int).tolist() and g["width"] == width.tolist()
+    for got, want in ((g["adaptor1"], r1), (g["adaptor2"], r2)):
+        assert np.array_equal(hexf(got["score"]), want[0]) and got["start"] == want[1].tolist() and got["end"] == want[2].tolist()
+        assert got["sec_start"] == [x.tolist() for x in want[3]] and got["sec_width"] == [x.tolist() for x in want[4]]
